@@ -1,0 +1,441 @@
+"""Host-side mirror of the reference interface for the two hot paths.
+
+Names, argument meaning and error behaviour follow halo2_proofs:
+
+* ``best_multiexp``, ``best_fft``            -- src/arithmetic.rs:132, :171
+* ``EvaluationDomain``                       -- src/poly/domain.rs:19-361
+* ``ParamsKZG.commit / commit_lagrange``     -- src/poly/kzg/commitment.rs:281-292, 327-334
+
+Field elements cross the boundary exactly as the reference stores them:
+``numpy.uint64`` arrays of shape (n, 4) holding little-endian Montgomery limbs
+(halo2curves ``Fr([u64; 4])``); affine points are (n, 8) (x limbs, y limbs),
+the identity is all zeros.  Where the reference panics, these raise
+``H2BError``.  Everything runs in libhalo2b200 on the GPU; nothing here
+computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import H2B_DEVICE, H2B_HOST, H2BError
+
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+Q_MOD = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+_MASK64 = (1 << 64) - 1
+
+
+# --------------------------------------------------------------------------
+# encodings (pure data conversion, no arithmetic on the hot path)
+# --------------------------------------------------------------------------
+def _to_limbs(vals: Sequence[int], mod: int) -> np.ndarray:
+    out = np.empty((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        m = (v % mod) * (1 << 256) % mod
+        out[i, 0] = m & _MASK64
+        out[i, 1] = (m >> 64) & _MASK64
+        out[i, 2] = (m >> 128) & _MASK64
+        out[i, 3] = m >> 192
+    return out
+
+
+def _from_limbs(arr: np.ndarray, mod: int) -> list:
+    rinv = pow(1 << 256, -1, mod)
+    a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+    out = []
+    for row in a.tolist():
+        m = row[0] | (row[1] << 64) | (row[2] << 128) | (row[3] << 192)
+        out.append(m * rinv % mod)
+    return out
+
+
+def fr_encode(vals: Sequence[int]) -> np.ndarray:
+    """Canonical integers -> (n, 4) Montgomery limbs of Fr."""
+    return _to_limbs(vals, R_MOD)
+
+
+def fr_decode(arr: np.ndarray) -> list:
+    return _from_limbs(arr, R_MOD)
+
+
+def fq_encode(vals: Sequence[int]) -> np.ndarray:
+    return _to_limbs(vals, Q_MOD)
+
+
+def fq_decode(arr: np.ndarray) -> list:
+    return _from_limbs(arr, Q_MOD)
+
+
+def g1_encode(points) -> np.ndarray:
+    """[(x, y) | None] -> (n, 8) limbs; None (identity) -> zeros."""
+    out = np.zeros((len(points), 8), dtype=np.uint64)
+    idx = [i for i, p in enumerate(points) if p is not None]
+    if idx:
+        out[idx, :4] = fq_encode([points[i][0] for i in idx])
+        out[idx, 4:] = fq_encode([points[i][1] for i in idx])
+    return out
+
+
+def g1_decode(arr: np.ndarray) -> list:
+    a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 8)
+    xs = fq_decode(a[:, :4])
+    ys = fq_decode(a[:, 4:])
+    out = []
+    for i in range(a.shape[0]):
+        out.append(None if not a[i].any() else (xs[i], ys[i]))
+    return out
+
+
+def g1_jacobian_to_affine(arr: np.ndarray):
+    """(12,) Jacobian limbs -> affine (x, y) or None.  Normalisation of a single
+    returned point, as the reference does with `.to_affine()` before hashing."""
+    a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(3, 4)
+    x, y, z = fq_decode(a)
+    if z == 0:
+        return None
+    zi = pow(z, -1, Q_MOD)
+    return (x * zi * zi % Q_MOD, y * zi * zi * zi % Q_MOD)
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def _fr_array(a, n: Optional[int] = None) -> np.ndarray:
+    arr = np.ascontiguousarray(a, dtype=np.uint64)
+    if arr.ndim == 1:
+        arr = arr.reshape(-1, 4)
+    if arr.ndim != 2 or arr.shape[1] != 4:
+        raise H2BError(_ffi.H2B_ERR_ARG, "expected (n, 4) uint64 limbs")
+    return arr
+
+
+# --------------------------------------------------------------------------
+# context and device buffers
+# --------------------------------------------------------------------------
+class DeviceBuffer:
+    """A device-resident array of Fr (or raw bytes) owned by a Context."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx = ctx
+        self.nbytes = nbytes
+        p = C.c_void_p()
+        ctx._check(ctx.lib.h2b_device_alloc(ctx.h, nbytes, C.byref(p)))
+        self.ptr = p
+
+    def upload(self, arr: np.ndarray, offset_bytes: int = 0) -> "DeviceBuffer":
+        a = np.ascontiguousarray(arr)
+        if offset_bytes + a.nbytes > self.nbytes:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "upload larger than the buffer")
+        self.ctx._check(self.ctx.lib.h2b_copy_h2d(self.ctx.h, C.c_void_p(self.ptr.value + offset_bytes),
+                                                  _ptr(a), a.nbytes))
+        return self
+
+    def download(self, count: int, offset_bytes: int = 0, width: int = 4) -> np.ndarray:
+        out = np.empty((count, width), dtype=np.uint64)
+        if offset_bytes + out.nbytes > self.nbytes:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "download larger than the buffer")
+        self.ctx._check(self.ctx.lib.h2b_copy_d2h(self.ctx.h, _ptr(out),
+                                                  C.c_void_p(self.ptr.value + offset_bytes), out.nbytes))
+        return out
+
+    def at(self, offset_bytes: int) -> C.c_void_p:
+        return C.c_void_p(self.ptr.value + offset_bytes)
+
+    def free(self) -> None:
+        if self.ptr is not None and self.ctx.h is not None:
+            self.ctx.lib.h2b_device_free(self.ctx.h, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedArray:
+    """Page-locked host memory viewed as a numpy uint64 array (pinned staging)."""
+
+    def __init__(self, lib, shape: Tuple[int, ...]):
+        self.lib = lib
+        n = int(np.prod(shape)) * 8
+        p = C.c_void_p()
+        rc = lib.h2b_host_alloc(n, C.byref(p))
+        if rc != 0:
+            raise H2BError(rc, "pinned allocation failed")
+        self.ptr = p
+        buf = (C.c_uint64 * (n // 8)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=np.uint64).reshape(shape)
+
+    def free(self):
+        if self.ptr is not None:
+            self.array = None
+            self.lib.h2b_host_free(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """One GPU + stream + scratch.  `lib_path` is for the test-suite's emulator
+    build only; the product always loads halo2-pse_b200/lib/libhalo2b200.so."""
+
+    def __init__(self, device: int = 0, lib_path: Optional[str] = None):
+        self.lib = _ffi.load(lib_path)
+        h = C.c_void_p()
+        rc = self.lib.h2b_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise H2BError(rc, "h2b_ctx_create failed: no usable CUDA device (there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self) -> None:
+        if self.h is not None:
+            self.lib.h2b_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        pass  # explicit close(); buffers may outlive GC ordering otherwise
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            msg = self.lib.h2b_last_error(self.h)
+            raise H2BError(rc, msg.decode() if msg else "")
+
+    def sync(self) -> None:
+        self._check(self.lib.h2b_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.h2b_ctx_launches(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.h2b_ctx_stream(self.h) or 0)
+
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def pinned(self, shape) -> PinnedArray:
+        return PinnedArray(self.lib, tuple(shape))
+
+    def upload_fr(self, arr) -> DeviceBuffer:
+        a = _fr_array(arr)
+        return self.alloc(max(a.nbytes, 32)).upload(a)
+
+    # ---- synthetic inputs ----
+    def synth_scalars(self, n: int, seed: int = 0x68616C6F32, kind: int = 0) -> DeviceBuffer:
+        buf = self.alloc(max(n, 1) * 32)
+        self._check(self.lib.h2b_synth_scalars(self.h, buf.ptr, n, seed, kind))
+        return buf
+
+    def synth_bases(self, n: int, seed: int = 0x6B7A67) -> "Bases":
+        buf = self.alloc(max(n, 1) * 64)
+        self._check(self.lib.h2b_synth_bases(self.h, buf.ptr, n, seed))
+        b = Bases(self, buf.ptr, n, H2B_DEVICE)
+        buf.free()
+        return b
+
+    def synth_base_scalar(self, seed: int, i: int) -> int:
+        return int(self.lib.h2b_synth_base_scalar(seed, i))
+
+    def imad_peak(self) -> float:
+        v = C.c_double()
+        m = C.c_double()
+        self._check(self.lib.h2b_imad_peak(self.h, C.byref(v), C.byref(m)))
+        return v.value
+
+    # ---- the two reference entry points ----
+    def best_multiexp(self, coeffs, bases):
+        """arithmetic.rs:132 -- host slices in, affine point (x, y) | None out."""
+        c = _fr_array(coeffs)
+        b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        if c.shape[0] != b.shape[0]:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert_eq!(coeffs.len(), bases.len())")  # :133
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(self.lib.h2b_best_multiexp(self.h, _ptr(c), _ptr(b), c.shape[0], _ptr(out)))
+        return g1_jacobian_to_affine(out)
+
+    def best_fft(self, a: np.ndarray, omega, log_n: int) -> np.ndarray:
+        """arithmetic.rs:171 -- in place on the (n, 4) limb array `a`."""
+        arr = _fr_array(a)
+        if arr.shape[0] != 1 << log_n:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert_eq!(a.len(), 1 << log_n)")  # :184
+        w = fr_encode([omega]) if isinstance(omega, int) else _fr_array(omega)
+        self._check(self.lib.h2b_best_fft(self.h, _ptr(arr), H2B_HOST, _ptr(w), log_n))
+        if arr is not a:
+            np.copyto(np.asarray(a).reshape(-1, 4), arr)
+        return a
+
+    def best_fft_device(self, buf: DeviceBuffer, omega, log_n: int, ncols: int = 1,
+                        stride: Optional[int] = None) -> None:
+        w = fr_encode([omega]) if isinstance(omega, int) else _fr_array(omega)
+        stride = stride if stride is not None else 1 << log_n
+        self._check(self.lib.h2b_best_fft_batch(self.h, buf.ptr, H2B_DEVICE, _ptr(w), log_n, ncols, stride))
+
+
+class Bases:
+    """Device-resident, immutable affine bases: ParamsKZG.g or .g_lagrange
+    (poly/kzg/commitment.rs:23-31)."""
+
+    def __init__(self, ctx: Context, src, n: int, loc: int = H2B_HOST):
+        self.ctx = ctx
+        h = C.c_void_p()
+        if loc == H2B_HOST:
+            arr = np.ascontiguousarray(src, dtype=np.uint64).reshape(-1, 8)
+            n = arr.shape[0]
+            ctx._check(ctx.lib.h2b_bases_upload(ctx.h, _ptr(arr), n, H2B_HOST, C.byref(h)))
+        else:
+            ctx._check(ctx.lib.h2b_bases_upload(ctx.h, src, n, H2B_DEVICE, C.byref(h)))
+        self.h = h
+        self.n = n
+
+    def __len__(self) -> int:
+        return self.n
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.n, 8), dtype=np.uint64)
+        p = self.ctx.lib.h2b_bases_device_ptr(self.h)
+        self.ctx._check(self.ctx.lib.h2b_copy_d2h(self.ctx.h, _ptr(out), p, out.nbytes))
+        return out
+
+    def msm(self, scalars, n: Optional[int] = None, offset: int = 0, affine: bool = True):
+        """best_multiexp(scalars, &bases[offset..offset+n]); scalars are host limbs
+        or a DeviceBuffer.  Returns the affine point (x, y) | None."""
+        if isinstance(scalars, DeviceBuffer):
+            if n is None:
+                raise H2BError(_ffi.H2B_ERR_ARG, "n required for device scalars")
+            sp, loc = scalars.ptr, H2B_DEVICE
+        else:
+            arr = _fr_array(scalars)
+            n = arr.shape[0] if n is None else n
+            sp, loc = _ptr(arr), H2B_HOST
+        if affine:
+            out = np.zeros(8, dtype=np.uint64)
+            self.ctx._check(self.ctx.lib.h2b_msm_affine(self.ctx.h, self.h, offset, sp, loc, n, _ptr(out)))
+            return g1_decode(out)[0]
+        out = np.zeros(12, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.h2b_msm(self.ctx.h, self.h, offset, sp, loc, n, _ptr(out)))
+        return g1_jacobian_to_affine(out)
+
+    def free(self) -> None:
+        if self.h is not None and self.ctx.h is not None:
+            self.ctx.lib.h2b_bases_free(self.h)
+        self.h = None
+
+
+class ParamsKZG:
+    """The commit half of poly/kzg/commitment.rs: k, n, g, g_lagrange."""
+
+    def __init__(self, ctx: Context, k: int, g, g_lagrange):
+        self.ctx = ctx
+        self.k = k
+        self.n = 1 << k
+        self.g = g if isinstance(g, Bases) else Bases(ctx, g, self.n)
+        self.g_lagrange = g_lagrange if isinstance(g_lagrange, Bases) else Bases(ctx, g_lagrange, self.n)
+
+    def commit(self, poly, blind=None):
+        """:327-334 -- blind is accepted and ignored, as in the reference."""
+        a = _fr_array(poly)
+        if a.shape[0] > len(self.g):
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert!(bases.len() >= size)")  # :332
+        return self.g.msm(a)
+
+    def commit_lagrange(self, poly, blind=None):
+        """:281-292"""
+        a = _fr_array(poly)
+        if a.shape[0] > len(self.g_lagrange):
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert!(bases.len() >= size)")  # :290
+        return self.g_lagrange.msm(a)
+
+
+class EvaluationDomain:
+    """poly/domain.rs:19-361 for G = Fr."""
+
+    _CONST = {"omega": 0, "omega_inv": 1, "extended_omega": 2, "extended_omega_inv": 3, "g_coset": 4,
+              "g_coset_inv": 5, "ifft_divisor": 6, "extended_ifft_divisor": 7}
+
+    def __init__(self, ctx: Context, j: int, k: int):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._check(ctx.lib.h2b_domain_new(ctx.h, j, k, C.byref(h)))
+        self.h = h
+        self.k = int(ctx.lib.h2b_domain_k(h))
+        self.extended_k = int(ctx.lib.h2b_domain_extended_k(h))
+        self.n = 1 << self.k
+        self.quotient_len = int(ctx.lib.h2b_domain_quotient_len(h))
+
+    def constant(self, name: str) -> int:
+        out = np.zeros(4, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.h2b_domain_constant(self.h, self._CONST[name], _ptr(out)))
+        return fr_decode(out)[0]
+
+    def t_evaluations(self) -> list:
+        out = []
+        for i in range(1 << (self.extended_k - self.k)):
+            v = np.zeros(4, dtype=np.uint64)
+            self.ctx._check(self.ctx.lib.h2b_domain_constant(self.h, 8 + i, _ptr(v)))
+            out.append(fr_decode(v)[0])
+        return out
+
+    def extended_len(self) -> int:
+        return 1 << self.extended_k
+
+    def lagrange_to_coeff(self, a) -> np.ndarray:
+        arr = _fr_array(a).copy()
+        if arr.shape[0] != self.n:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert_eq!(a.values.len(), 1 << self.k)")  # :227
+        self.ctx._check(self.ctx.lib.h2b_lagrange_to_coeff(self.h, _ptr(arr), H2B_HOST))
+        return arr
+
+    def coeff_to_extended(self, a) -> np.ndarray:
+        arr = _fr_array(a)
+        if arr.shape[0] != self.n:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert_eq!(a.values.len(), 1 << self.k)")  # :244
+        out = np.empty((self.extended_len(), 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.h2b_coeff_to_extended(self.h, _ptr(arr), _ptr(out), H2B_HOST))
+        return out
+
+    def extended_to_coeff(self, a, divide_by_vanishing: bool = False) -> np.ndarray:
+        arr = _fr_array(a)
+        if arr.shape[0] != self.extended_len():
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert_eq!(a.values.len(), extended_len())")  # :282
+        out = np.empty((self.quotient_len, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.h2b_extended_to_coeff(self.h, _ptr(arr), _ptr(out), H2B_HOST,
+                                                           1 if divide_by_vanishing else 0))
+        return out
+
+    def divide_by_vanishing_poly(self, a) -> np.ndarray:
+        arr = _fr_array(a).copy()
+        if arr.shape[0] != self.extended_len():
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert_eq!(a.values.len(), extended_len())")  # :311
+        self.ctx._check(self.ctx.lib.h2b_divide_by_vanishing_poly(self.h, _ptr(arr), H2B_HOST))
+        return arr
+
+    # device-resident, batched (column-parallel) forms
+    def lagrange_to_coeff_device(self, buf: DeviceBuffer, ncols: int = 1, stride: Optional[int] = None):
+        stride = self.n if stride is None else stride
+        self.ctx._check(self.ctx.lib.h2b_lagrange_to_coeff_batch(self.h, buf.ptr, H2B_DEVICE, ncols, stride))
+
+    def coeff_to_extended_device(self, src: DeviceBuffer, dst: DeviceBuffer, ncols: int = 1,
+                                 in_stride: Optional[int] = None, out_stride: Optional[int] = None):
+        in_stride = self.n if in_stride is None else in_stride
+        out_stride = self.extended_len() if out_stride is None else out_stride
+        self.ctx._check(self.ctx.lib.h2b_coeff_to_extended_batch(self.h, src.ptr, in_stride, dst.ptr,
+                                                                 out_stride, H2B_DEVICE, ncols))
+
+    def extended_to_coeff_device(self, src: DeviceBuffer, dst: DeviceBuffer, ncols: int = 1,
+                                 in_stride: Optional[int] = None, out_stride: Optional[int] = None,
+                                 divide_by_vanishing: bool = False):
+        in_stride = self.extended_len() if in_stride is None else in_stride
+        out_stride = self.quotient_len if out_stride is None else out_stride
+        self.ctx._check(self.ctx.lib.h2b_extended_to_coeff_batch(
+            self.h, src.ptr, in_stride, dst.ptr, out_stride, H2B_DEVICE, ncols,
+            1 if divide_by_vanishing else 0))
+
+    def free(self) -> None:
+        if self.h is not None and self.ctx.h is not None:
+            self.ctx.lib.h2b_domain_free(self.h)
+        self.h = None

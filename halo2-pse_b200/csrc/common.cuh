@@ -1,0 +1,177 @@
+// Shared host-side plumbing of libhalo2b200: context, scratch, error handling,
+// the kernel-launch helper and the vectorised global-memory accessors.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/halo2_b200.h"
+#include "ec.cuh"
+#include "field.cuh"
+
+namespace h2b {
+
+// Twiddle tables of one (omega, log_n) pair, all on device (ntt.cu).
+struct TwTable {
+  Fr omega;
+  uint32_t k;      // omega has exact order 2^k
+  uint32_t h;      // split of the two-level table: e = (e_hi << h) | e_lo
+  Fr* d_lo;        // omega^i,           i < 2^h
+  Fr* d_hi;        // omega^(i << h),    i < 2^(k-h)
+  Fr* d_rt;        // omega_R^i, R = 2^min(k,8), i < R   (intra-pass roots)
+};
+
+struct MsmWorkspace;
+
+}  // namespace h2b
+
+struct h2b_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::recursive_mutex mu;
+  std::string last_error;
+  // grow-only device scratch (NTT ping buffer)
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // grow-only device staging for host-pointer calls
+  void* stage[2] = {nullptr, nullptr};
+  size_t stage_bytes[2] = {0, 0};
+  std::vector<h2b::TwTable> tw;
+  h2b::MsmWorkspace* msm_ws = nullptr;
+  uint64_t launches = 0;  // kernels launched by this library (bench.py reports it)
+  // timing of the last MSM / NTT call's dominant kernel (CUDA events on `stream`)
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float last_kernel_ms = 0.f;
+  int profile = 0;
+  bool ntt_attr_done = false;
+};
+
+struct h2b_bases {
+  h2b_ctx* ctx;
+  h2b::G1Affine* d_pts;
+  size_t n;
+};
+
+struct h2b_domain {
+  h2b_ctx* ctx;
+  uint32_t j, k, extended_k, quotient_poly_degree;
+  h2b::Fr omega, omega_inv, extended_omega, extended_omega_inv;
+  h2b::Fr g_coset, g_coset_inv, ifft_divisor, extended_ifft_divisor;
+  std::vector<h2b::Fr> t_evaluations;  // already inverted (domain.rs:84-124)
+  // device-side small tables
+  h2b::Fr* d_zeta_in;    // [1, zeta, zeta^2]                 (coeff_to_extended pre-scale)
+  h2b::Fr* d_ext_post;   // 1/2^ek * [1, zeta^2, zeta]        (extended_to_coeff post-scale)
+  h2b::Fr* d_ifft_post;  // [1/n]
+  h2b::Fr* d_t_inv;      // t_evaluations
+};
+
+namespace h2b {
+
+inline int fail(h2b_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+#define H2B_CUDA(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      char _b[512];                                                                      \
+      snprintf(_b, sizeof _b, "%s:%d %s: %s", __FILE__, __LINE__, #expr,                 \
+               cudaGetErrorString(_e));                                                  \
+      return h2b::fail((ctx), _e == cudaErrorMemoryAllocation ? H2B_ERR_OOM : H2B_ERR_CUDA, _b); \
+    }                                                                                    \
+  } while (0)
+
+#define H2B_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != H2B_OK) return _r; \
+  } while (0)
+
+// Launch `kern` on the context's stream and count it.  Under H2B_EMU (the CPU
+// test build, tests/emu/cuda_runtime.h) the same call runs the kernel on the
+// fiber emulator; the product build never defines H2B_EMU.
+template <class... KArgs, class... Args>
+inline int launch(h2b_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                  Args&&... args) {
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return H2B_OK;
+#ifdef H2B_EMU
+  emu::launch(grid, block, smem, [&]() { kern(args...); });
+#else
+  kern<<<grid, block, smem, ctx->stream>>>(std::forward<Args>(args)...);
+  H2B_CUDA(ctx, cudaGetLastError());
+#endif
+  ctx->launches++;
+  return H2B_OK;
+}
+
+#ifdef H2B_EMU
+#define H2B_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+#else
+#define H2B_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+// 256-bit global accessors (LDG.E.256 / STG.E.256 on sm_100a).  Pointers must
+// be 32-byte aligned: every device buffer of this library is.
+template <class P>
+H2B_D Fp<P> ld_fp(const Fp<P>* p) {
+  Fp<P> r;
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]),
+                 "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+#else
+  r = *p;
+#endif
+  return r;
+}
+// read-only path (tables)
+template <class P>
+H2B_D Fp<P> ld_fp_nc(const Fp<P>* p) {
+  Fp<P> r;
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]),
+                 "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+#else
+  r = *p;
+#endif
+  return r;
+}
+template <class P>
+H2B_D void st_fp(Fp<P>* p, const Fp<P>& r) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.global.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(r.v[0]), "r"(r.v[1]),
+               "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]),
+               "l"(p)
+               : "memory");
+#else
+  *p = r;
+#endif
+}
+
+int ensure_scratch(h2b_ctx* ctx, size_t bytes);
+int ensure_stage(h2b_ctx* ctx, int which, size_t bytes);
+
+// ntt.cu
+int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t log_n, const TwTable** out);
+int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t log_n, const TwTable* tw,
+            uint64_t n_in, const Fr* d_pre, uint32_t pre_mod, const Fr* d_post,
+            uint32_t post_mod, uint64_t n_out, uint32_t batch, uint64_t in_stride,
+            uint64_t out_stride);
+void ntt_free_tables(h2b_ctx* ctx);
+
+// msm.cu
+int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, G1Xyzz* out_host);
+void msm_ws_free(h2b_ctx* ctx);
+
+}  // namespace h2b

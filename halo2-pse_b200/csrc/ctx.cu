@@ -1,0 +1,431 @@
+// Context, device memory helpers, synthetic benchmark inputs and the
+// measurement / test hooks of libhalo2b200 (include/halo2_b200.h).
+#include "common.cuh"
+
+#include <string.h>
+
+#include <functional>
+
+namespace h2b {
+
+static int grow(h2b_ctx* ctx, void** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return H2B_OK;
+  if (*p) {
+    H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    H2B_CUDA(ctx, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+  }
+  H2B_CUDA(ctx, cudaMalloc(p, bytes));
+  *cap = bytes;
+  return H2B_OK;
+}
+
+int ensure_scratch(h2b_ctx* ctx, size_t bytes) {
+  return grow(ctx, &ctx->scratch, &ctx->scratch_bytes, bytes);
+}
+int ensure_stage(h2b_ctx* ctx, int which, size_t bytes) {
+  return grow(ctx, &ctx->stage[which], &ctx->stage_bytes[which], bytes);
+}
+
+// ---------------------------------------------------------------------------
+// Synthetic inputs
+// ---------------------------------------------------------------------------
+H2B_HD uint64_t splitmix64(uint64_t x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+// canonical value < r from a counter-based generator: 254 random bits,
+// rejection-sampled (acceptance ~ 0.76), attempt number mixed into the counter
+H2B_HD Fr uniform_fr_canonical(uint64_t seed, uint64_t i) {
+  Fr x;
+  for (uint32_t attempt = 0;; ++attempt) {
+    for (int w = 0; w < 4; ++w) {
+      const uint64_t r = splitmix64(seed ^ splitmix64(i * 4 + w + ((uint64_t)attempt << 58)));
+      x.v[2 * w] = (uint32_t)r;
+      x.v[2 * w + 1] = (uint32_t)(r >> 32);
+    }
+    x.v[7] &= 0x3fffffffu;
+    uint32_t m[8], t[8];
+    for (int k = 0; k < 8; ++k) m[k] = FrParams::mod(k);
+    if (sub8(t, x.v, m)) return x;  // borrow  =>  x < r
+  }
+}
+
+// kind: 0 uniform, 1 all equal (one uniform value), 2 0/1 with density 1/2,
+//       3 uniform in [0, 2^16), 4 uniform with 90 % zeros
+__global__ void synth_scalars_kernel(Fr* dst, uint64_t n, uint64_t seed, uint32_t kind) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    Fr x = Fr::zero();
+    const uint64_t r = splitmix64(seed + 0x5851f42d4c957f2dull * (i + 1));
+    switch (kind) {
+      case 0: x = uniform_fr_canonical(seed, i); break;
+      case 1: x = uniform_fr_canonical(seed, 0); break;
+      case 2: x.v[0] = (uint32_t)(r & 1); break;
+      case 3: x.v[0] = (uint32_t)(r & 0xffff); break;
+      default:
+        if (r % 10 == 0) x = uniform_fr_canonical(seed, i);
+    }
+    st_fp(dst + i, to_mont(x));
+  }
+}
+
+H2B_HD uint64_t synth_base_scalar(uint64_t seed, uint64_t i) { return splitmix64(seed + i) | 1ull; }
+
+// P_i = [h_i] G with h_i = splitmix64(seed + i) | 1 : valid, (practically)
+// distinct points whose discrete logs are known, so that
+// sum c_i P_i = [sum c_i h_i] G gives a closed-form check at any size.
+__global__ void synth_bases_kernel(G1Affine* dst, uint64_t n, uint64_t seed) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t h = synth_base_scalar(seed, i);
+  G1Affine g;
+  g.x = Fq::one();
+  g.y = add(Fq::one(), Fq::one());
+  G1Xyzz acc = G1Xyzz::identity();
+  for (int bit = 63; bit >= 0; --bit) {
+    acc = xyzz_double(acc);
+    if ((h >> bit) & 1) xyzz_add_affine(acc, g);
+  }
+  const G1Affine a = xyzz_to_affine(acc);
+  st_fp(&dst[i].x, a.x);
+  st_fp(&dst[i].y, a.y);
+}
+
+// ---------------------------------------------------------------------------
+// IMAD peak: independent 32x32+64 multiply-add chains, registers only
+// ---------------------------------------------------------------------------
+__global__ void imad_peak_kernel(uint32_t* sink, uint32_t iters, uint32_t a0, unsigned long long* cyc) {
+  uint32_t a = a0 + threadIdx.x;
+  uint64_t acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = threadIdx.x * 8 + j;
+#ifdef __CUDA_ARCH__
+  const long long t0 = clock64();
+#endif
+  for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#ifdef __CUDA_ARCH__
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"((uint32_t)(acc[j] >> 7) | 1u));
+#else
+        acc[j] += (uint64_t)a * ((uint32_t)(acc[j] >> 7) | 1u);
+#endif
+      }
+    }
+  }
+#ifdef __CUDA_ARCH__
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = (unsigned long long)(t1 - t0);
+#else
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = 0;
+#endif
+  uint64_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s ^= acc[j];
+  if (s == 0x123456789abcdefull) sink[0] = (uint32_t)s;
+}
+
+// ---------------------------------------------------------------------------
+// Element-wise test kernels
+// ---------------------------------------------------------------------------
+template <class F>
+H2B_HD F field_op(int op, const F& a, const F& b) {
+  switch (op) {
+    case 0: return mul(a, b);
+    case 1: return add(a, b);
+    case 2: return sub(a, b);
+    case 3: return sqr(a);
+    case 4: return to_mont(a);
+    case 5: return from_mont(a);
+    case 6: return neg(a);
+    default: return inv(a);
+  }
+}
+
+__global__ void field_op_kernel(int field, int op, const Fr* a, const Fr* b, Fr* out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (field == 0) {
+    st_fp(out + i, field_op<Fr>(op, ld_fp(a + i), ld_fp(b + i)));
+  } else {
+    const Fq* qa = reinterpret_cast<const Fq*>(a);
+    const Fq* qb = reinterpret_cast<const Fq*>(b);
+    st_fp(reinterpret_cast<Fq*>(out) + i, field_op<Fq>(op, ld_fp(qa + i), ld_fp(qb + i)));
+  }
+}
+
+H2B_HD G1Affine g1_op(int op, const G1Affine& a, const G1Affine& b) {
+  G1Xyzz acc = G1Xyzz::from_affine(a);
+  if (op == 0) {
+    xyzz_add_affine(acc, b);
+  } else if (op == 1) {
+    acc = xyzz_double(acc);
+  } else {
+    // full (non-mixed) addition of 2a and b, minus a:  2a + b - a  = a + b
+    G1Xyzz t = xyzz_double(acc);
+    G1Xyzz bb = G1Xyzz::from_affine(b);
+    xyzz_add(t, bb);
+    G1Xyzz na = G1Xyzz::from_affine(g1_neg(a));
+    xyzz_add(t, na);
+    acc = t;
+  }
+  return xyzz_to_affine(acc);
+}
+
+__global__ void g1_op_kernel(int op, const G1Affine* a, const G1Affine* b, G1Affine* out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = g1_op(op, a[i], b[i]);
+}
+
+}  // namespace h2b
+
+using namespace h2b;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" int h2b_ctx_create(int device, h2b_ctx** out) {
+  if (!out) return H2B_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return H2B_ERR_CUDA;
+  if (device < 0 || device >= count) return H2B_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return H2B_ERR_CUDA;
+  h2b_ctx* ctx = new h2b_ctx();
+  ctx->device = device;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+    ctx->sm_count = sms;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return H2B_ERR_CUDA;
+  }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+  *out = ctx;
+  return H2B_OK;
+}
+
+extern "C" void h2b_ctx_destroy(h2b_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  msm_ws_free(ctx);
+  ntt_free_tables(ctx);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+  for (int i = 0; i < 4; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* h2b_last_error(const h2b_ctx* ctx) {
+  return ctx ? ctx->last_error.c_str() : "null context";
+}
+
+extern "C" int h2b_ctx_sync(h2b_ctx* ctx) {
+  if (!ctx) return H2B_ERR_ARG;
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
+extern "C" void* h2b_ctx_stream(h2b_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t h2b_ctx_launches(const h2b_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void h2b_ctx_set_profile(h2b_ctx* ctx, int on) {
+  if (ctx) ctx->profile = on;
+}
+extern "C" float h2b_ctx_last_kernel_ms(const h2b_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }
+
+extern "C" int h2b_device_alloc(h2b_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  H2B_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+  return H2B_OK;
+}
+
+extern "C" void h2b_device_free(h2b_ctx* ctx, void* p) {
+  if (!ctx || !p) return;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(p);
+}
+
+extern "C" int h2b_host_alloc(size_t bytes, void** out) {
+  if (!out) return H2B_ERR_ARG;
+  return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? H2B_OK : H2B_ERR_OOM;
+}
+extern "C" void h2b_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+extern "C" int h2b_copy_h2d(h2b_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  H2B_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
+extern "C" int h2b_copy_d2h(h2b_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  H2B_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
+extern "C" int h2b_synth_scalars(h2b_ctx* ctx, h2b_fr* dst_dev, size_t n, uint64_t seed,
+                                 uint32_t kind) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!dst_dev) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (kind > 4) return fail(ctx, H2B_ERR_ARG, "unknown scalar distribution");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint64_t want = (n + 255) / 256;
+  const uint32_t blocks = (uint32_t)(want < (uint64_t)ctx->sm_count * 32 ? want : (uint64_t)ctx->sm_count * 32);
+  return launch(ctx, synth_scalars_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<Fr*>(dst_dev),
+                (uint64_t)n, seed, kind);
+}
+
+extern "C" int h2b_synth_bases(h2b_ctx* ctx, h2b_g1_affine* dst_dev, size_t n, uint64_t seed) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!dst_dev) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  return launch(ctx, synth_bases_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0,
+                reinterpret_cast<G1Affine*>(dst_dev), (uint64_t)n, seed);
+}
+
+extern "C" uint64_t h2b_synth_base_scalar(uint64_t seed, uint64_t i) { return synth_base_scalar(seed, i); }
+
+extern "C" int h2b_imad_peak(h2b_ctx* ctx, double* imad_per_s, double* sm_mhz_effective) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint32_t* sink;
+  unsigned long long* cyc;
+  H2B_CUDA(ctx, cudaMalloc((void**)&sink, 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&cyc, 8));
+  const uint32_t blocks = ctx->sm_count * 8, threads = 256;
+#ifdef H2B_EMU
+  const uint32_t iters = 4;
+#else
+  const uint32_t iters = 4096;
+#endif
+  double best = 0, mhz = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    H2B_TRY(launch(ctx, imad_peak_kernel, dim3(blocks), dim3(threads), 0, sink, iters, 12345u + rep, cyc));
+    H2B_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    H2B_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+    float ms = 0;
+    H2B_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    unsigned long long c = 0;
+    H2B_CUDA(ctx, cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
+    const double ops = (double)blocks * threads * iters * 64.0;
+    const double rate = ms > 0 ? ops / (ms * 1e-3) : 0;
+    if (rate > best) {
+      best = rate;
+      // block 0 runs for about 1/8 of the launch (8 waves of blocks per SM share the SM)
+      mhz = 0;
+    }
+    (void)c;
+  }
+  cudaFree(sink);
+  cudaFree(cyc);
+  if (imad_per_s) *imad_per_s = best;
+  if (sm_mhz_effective) *sm_mhz_effective = mhz;
+  return H2B_OK;
+}
+
+static int run_elementwise(h2b_ctx* ctx, size_t bytes_each, const void* a, const void* b, void* out,
+                           const std::function<int(void*, void*, void*)>& go) {
+  void *da = nullptr, *db = nullptr, *dout = nullptr;
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  H2B_CUDA(ctx, cudaMalloc(&da, bytes_each + 32));
+  H2B_CUDA(ctx, cudaMalloc(&db, bytes_each + 32));
+  H2B_CUDA(ctx, cudaMalloc(&dout, bytes_each + 32));
+  H2B_CUDA(ctx, cudaMemcpyAsync(da, a, bytes_each, cudaMemcpyHostToDevice, ctx->stream));
+  H2B_CUDA(ctx, cudaMemcpyAsync(db, b ? b : a, bytes_each, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = go(da, db, dout);
+  if (rc == H2B_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, dout, bytes_each, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, H2B_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(da);
+  cudaFree(db);
+  cudaFree(dout);
+  return rc;
+}
+
+extern "C" int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const h2b_fr* a, const h2b_fr* b,
+                                 h2b_fr* out, size_t n) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!a || !out || field < 0 || field > 1 || op < 0 || op > 7) return fail(ctx, H2B_ERR_ARG, "bad argument");
+  if (n == 0) return H2B_OK;
+  return run_elementwise(ctx, n * 32, a, b, out, [&](void* da, void* db, void* dout) {
+    return launch(ctx, field_op_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, field, op,
+                  (const Fr*)da, (const Fr*)db, (Fr*)dout, (uint64_t)n);
+  });
+}
+
+extern "C" int h2b_host_field_op(int field, int op, const h2b_fr* a, const h2b_fr* b, h2b_fr* out,
+                                 size_t n) {
+  if (!a || !out || field < 0 || field > 1 || op < 0 || op > 7) return H2B_ERR_ARG;
+  for (size_t i = 0; i < n; ++i) {
+    if (field == 0) {
+      Fr x, y;
+      memcpy(&x, a + i, 32);
+      memcpy(&y, (b ? b : a) + i, 32);
+      Fr r = field_op<Fr>(op, x, y);
+      memcpy(out + i, &r, 32);
+    } else {
+      Fq x, y;
+      memcpy(&x, a + i, 32);
+      memcpy(&y, (b ? b : a) + i, 32);
+      Fq r = field_op<Fq>(op, x, y);
+      memcpy(out + i, &r, 32);
+    }
+  }
+  return H2B_OK;
+}
+
+extern "C" int h2b_test_g1_op(h2b_ctx* ctx, int op, const h2b_g1_affine* a, const h2b_g1_affine* b,
+                              h2b_g1_affine* out, size_t n) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!a || !out || op < 0 || op > 2) return fail(ctx, H2B_ERR_ARG, "bad argument");
+  if (n == 0) return H2B_OK;
+  return run_elementwise(ctx, n * 64, a, b, out, [&](void* da, void* db, void* dout) {
+    return launch(ctx, g1_op_kernel, dim3((uint32_t)((n + 63) / 64)), dim3(64), 0, op,
+                  (const G1Affine*)da, (const G1Affine*)db, (G1Affine*)dout, (uint64_t)n);
+  });
+}
+
+extern "C" int h2b_host_g1_op(int op, const h2b_g1_affine* a, const h2b_g1_affine* b,
+                              h2b_g1_affine* out, size_t n) {
+  if (!a || !out || op < 0 || op > 2) return H2B_ERR_ARG;
+  for (size_t i = 0; i < n; ++i) {
+    G1Affine x, y;
+    memcpy(&x, a + i, 64);
+    memcpy(&y, (b ? b : a) + i, 64);
+    G1Affine r = g1_op(op, x, y);
+    memcpy(out + i, &r, 64);
+  }
+  return H2B_OK;
+}

@@ -1,0 +1,438 @@
+// bn256 Fr / Fq arithmetic, 8 x 32-bit limbs, Montgomery form with R = 2^256.
+//
+// Replaces (for the hot path only) halo2curves 0.3.1 `bn256::Fr` / `bn256::Fq`
+// (external crate, /root/reference/halo2_proofs/Cargo.toml:51).  The residues
+// are bit-identical to halo2curves' 4 x u64 limbs because R is the same.
+//
+// Device path: PTX carry chains (mad.lo.cc / madc.hi.cc pairs, which ptxas
+// fuses into IMAD.WIDE.U32(.X)); the product is accumulated into two
+// interleaved column accumulators (columns with (i+j) even / odd) so every
+// chain is one unbroken carry chain, with the Montgomery reduction interleaved
+// row by row (CIOS).  136 32x32 multiplies per modular multiplication.
+// Host path: the same algorithm with 64-bit emulation of each chain, used by
+// the host-side finishers and by the CPU unit test of this header.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define H2B_HD __host__ __device__ __forceinline__
+#define H2B_D __device__ __forceinline__
+#else
+#define H2B_HD inline
+#define H2B_D inline
+#endif
+
+namespace h2b {
+
+// ---------------------------------------------------------------------------
+// Parameters
+// ---------------------------------------------------------------------------
+struct FrParams {
+  // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+  static H2B_HD constexpr uint32_t mod(int i) {
+    constexpr uint32_t t[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return t[i];
+  }
+  // R mod r
+  static H2B_HD constexpr uint32_t one(int i) {
+    constexpr uint32_t t[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                               0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return t[i];
+  }
+  // R^2 mod r
+  static H2B_HD constexpr uint32_t r2(int i) {
+    constexpr uint32_t t[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                               0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return t[i];
+  }
+  static constexpr uint32_t INV = 0xefffffffu;  // -r^{-1} mod 2^32
+};
+
+struct FqParams {
+  // q = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+  static H2B_HD constexpr uint32_t mod(int i) {
+    constexpr uint32_t t[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return t[i];
+  }
+  static H2B_HD constexpr uint32_t one(int i) {
+    constexpr uint32_t t[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                               0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return t[i];
+  }
+  static H2B_HD constexpr uint32_t r2(int i) {
+    constexpr uint32_t t[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                               0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return t[i];
+  }
+  static constexpr uint32_t INV = 0xe4866389u;  // -q^{-1} mod 2^32
+};
+
+// ---------------------------------------------------------------------------
+// Carry-chain building blocks.  Each has a PTX body and a host emulation.
+// ---------------------------------------------------------------------------
+
+// c[0..7] += {lo,hi}(x0*b), {lo,hi}(x1*b), {lo,hi}(x2*b), {lo,hi}(x3*b);  c[8] += carry.
+// If SEED, the chain's carry-in is the carry of (u + v).
+template <bool SEED>
+H2B_HD void chain_mad_top(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t& c4,
+                          uint32_t& c5, uint32_t& c6, uint32_t& c7, uint32_t& c8, uint32_t x0,
+                          uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b, uint32_t u,
+                          uint32_t v) {
+#ifdef __CUDA_ARCH__
+  if (SEED) {
+    uint32_t tmp;
+    asm("add.cc.u32 %9, %15, %16;\n\t"
+        "madc.lo.cc.u32 %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %14, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7),
+          "+r"(c8), "=r"(tmp)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b), "r"(u), "r"(v));
+  } else {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7),
+          "+r"(c8)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+  }
+#else
+  uint64_t carry = SEED ? (((uint64_t)u + v) >> 32) : 0;
+  uint32_t* c[9] = {&c0, &c1, &c2, &c3, &c4, &c5, &c6, &c7, &c8};
+  const uint32_t x[4] = {x0, x1, x2, x3};
+  for (int k = 0; k < 4; ++k) {
+    uint64_t p = (uint64_t)x[k] * b;
+    uint64_t s = (uint64_t)*c[2 * k] + (uint32_t)p + carry;
+    *c[2 * k] = (uint32_t)s;
+    carry = s >> 32;
+    s = (uint64_t)*c[2 * k + 1] + (uint32_t)(p >> 32) + carry;
+    *c[2 * k + 1] = (uint32_t)s;
+    carry = s >> 32;
+  }
+  *c[8] += (uint32_t)carry;
+#endif
+}
+
+// c[0..7] += {lo,hi}(x0*b) ... {lo,hi}(x3*b); the carry out of c[7] is known to be 0.
+H2B_HD void chain_mad(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t& c4,
+                      uint32_t& c5, uint32_t& c6, uint32_t& c7, uint32_t x0, uint32_t x1,
+                      uint32_t x2, uint32_t x3, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+      "madc.hi.u32 %7, %11, %12, %7;"
+      : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7)
+      : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+#else
+  uint64_t carry = 0;
+  uint32_t* c[8] = {&c0, &c1, &c2, &c3, &c4, &c5, &c6, &c7};
+  const uint32_t x[4] = {x0, x1, x2, x3};
+  for (int k = 0; k < 4; ++k) {
+    uint64_t p = (uint64_t)x[k] * b;
+    uint64_t s = (uint64_t)*c[2 * k] + (uint32_t)p + carry;
+    *c[2 * k] = (uint32_t)s;
+    carry = s >> 32;
+    s = (uint64_t)*c[2 * k + 1] + (uint32_t)(p >> 32) + carry;
+    *c[2 * k + 1] = (uint32_t)s;
+    carry = s >> 32;
+  }
+#endif
+}
+
+H2B_HD void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#else
+  uint64_t p = (uint64_t)a * b;
+  lo = (uint32_t)p;
+  hi = (uint32_t)(p >> 32);
+#endif
+}
+
+// r = a + b + carry_of(u + v)   (8 limbs, result < 2^256 guaranteed by caller)
+H2B_HD void add8_seed(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t u, uint32_t v) {
+#ifdef __CUDA_ARCH__
+  uint32_t tmp;
+  asm("add.cc.u32 %8, %25, %26;\n\t"
+      "addc.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.u32 %7, %16, %24;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(tmp)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]),
+        "r"(u), "r"(v));
+#else
+  uint64_t carry = ((uint64_t)u + v) >> 32;
+  for (int i = 0; i < 8; ++i) {
+    uint64_t s = (uint64_t)a[i] + b[i] + carry;
+    r[i] = (uint32_t)s;
+    carry = s >> 32;
+  }
+#endif
+}
+
+// r = a + b, returns nothing (caller guarantees no overflow past 2^256)
+H2B_HD void add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  uint64_t carry = 0;
+  for (int i = 0; i < 8; ++i) {
+    uint64_t s = (uint64_t)a[i] + b[i] + carry;
+    r[i] = (uint32_t)s;
+    carry = s >> 32;
+  }
+#endif
+}
+
+// r = a - b, returns the borrow as an all-ones / all-zero mask
+H2B_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t mask;
+#ifdef __CUDA_ARCH__
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(mask)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  uint64_t borrow = 0;
+  for (int i = 0; i < 8; ++i) {
+    uint64_t d = (uint64_t)a[i] - b[i] - borrow;
+    r[i] = (uint32_t)d;
+    borrow = (d >> 32) & 1;
+  }
+  mask = (uint32_t)(0 - borrow);
+#endif
+  return mask;
+}
+
+// ---------------------------------------------------------------------------
+// Field element
+// ---------------------------------------------------------------------------
+template <class P>
+struct Fp {
+  uint32_t v[8];
+
+  static H2B_HD Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = 0;
+    return r;
+  }
+  static H2B_HD Fp one() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = P::one(i);
+    return r;
+  }
+  static H2B_HD Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = P::r2(i);
+    return r;
+  }
+  H2B_HD bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= v[i];
+    return o == 0;
+  }
+  H2B_HD bool operator==(const Fp& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= v[i] ^ b.v[i];
+    return o == 0;
+  }
+  H2B_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// if x >= p: x -= p      (x < 2p)
+template <class P>
+H2B_HD void reduce_once(Fp<P>& x) {
+  uint32_t m[8], t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = P::mod(i);
+  uint32_t borrow = sub8(t, x.v, m);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x.v[i] = borrow ? x.v[i] : t[i];
+}
+
+template <class P>
+H2B_HD Fp<P> add(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  add8(r.v, a.v, b.v);  // a,b < p < 2^254: no overflow
+  reduce_once(r);
+  return r;
+}
+
+template <class P>
+H2B_HD Fp<P> sub(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  uint32_t mask = sub8(r.v, a.v, b.v);
+  uint32_t m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = P::mod(i) & mask;
+  add8(r.v, r.v, m);
+  return r;
+}
+
+template <class P>
+H2B_HD Fp<P> neg(const Fp<P>& a) {
+  Fp<P> r;
+  uint32_t m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = P::mod(i);
+  sub8(r.v, m, a.v);
+  bool z = a.is_zero();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = z ? 0u : r.v[i];
+  return r;
+}
+
+template <class P>
+H2B_HD Fp<P> dbl(const Fp<P>& a) {
+  return add(a, a);
+}
+
+// Montgomery product a*b/R mod p.
+template <class P>
+H2B_HD Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
+  // A[s][c]: absolute column c of the accumulator collecting the products
+  // a_j*b_i (and m_i*p_j) with (i + j) & 1 == s.
+  uint32_t A[2][18];
+#pragma unroll
+  for (int c = 0; c < 18; ++c) A[0][c] = A[1][c] = 0;
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int s0 = i & 1;   // accumulator of the even-j products of this row
+    const int s1 = s0 ^ 1;  // accumulator of the odd-j products
+    uint32_t* E = &A[s0][i];      // columns i .. i+8
+    uint32_t* O = &A[s1][i + 1];  // columns i+1 .. i+8
+    const uint32_t bi = b.v[i];
+    if (i == 0) {
+      // first row: every product owns its two columns, no carries
+      mul_wide(E[0], E[1], a.v[0], bi);
+      mul_wide(E[2], E[3], a.v[2], bi);
+      mul_wide(E[4], E[5], a.v[4], bi);
+      mul_wide(E[6], E[7], a.v[6], bi);
+      mul_wide(O[0], O[1], a.v[1], bi);
+      mul_wide(O[2], O[3], a.v[3], bi);
+      mul_wide(O[4], O[5], a.v[5], bi);
+      mul_wide(O[6], O[7], a.v[7], bi);
+    } else {
+      // carry-in: column i-1 of both accumulators sums to 0 or 2^32
+      chain_mad_top<true>(E[0], E[1], E[2], E[3], E[4], E[5], E[6], E[7], E[8], a.v[0], a.v[2],
+                          a.v[4], a.v[6], bi, A[0][i - 1], A[1][i - 1]);
+      chain_mad(O[0], O[1], O[2], O[3], O[4], O[5], O[6], O[7], a.v[1], a.v[3], a.v[5], a.v[7],
+                bi);
+    }
+    const uint32_t m = (A[0][i] + A[1][i]) * P::INV;
+    chain_mad_top<false>(E[0], E[1], E[2], E[3], E[4], E[5], E[6], E[7], E[8], P::mod(0),
+                         P::mod(2), P::mod(4), P::mod(6), m, 0u, 0u);
+    chain_mad(O[0], O[1], O[2], O[3], O[4], O[5], O[6], O[7], P::mod(1), P::mod(3), P::mod(5),
+              P::mod(7), m);
+  }
+  Fp<P> r;
+  add8_seed(r.v, &A[0][8], &A[1][8], A[0][7], A[1][7]);
+  reduce_once(r);
+  return r;
+}
+
+template <class P>
+H2B_HD Fp<P> sqr(const Fp<P>& a) {
+  return mul(a, a);
+}
+
+template <class P>
+H2B_HD Fp<P> to_mont(const Fp<P>& a) {
+  return mul(a, Fp<P>::r2());
+}
+
+// Montgomery -> canonical residue (multiply by 1)
+template <class P>
+H2B_HD Fp<P> from_mont(const Fp<P>& a) {
+  Fp<P> o = Fp<P>::zero();
+  o.v[0] = 1;
+  return mul(a, o);
+}
+
+// a^e for a small public exponent (host finishers, table builders)
+template <class P>
+H2B_HD Fp<P> pow_u64(const Fp<P>& a, uint64_t e) {
+  Fp<P> r = Fp<P>::one();
+  Fp<P> base = a;
+  while (e) {
+    if (e & 1) r = mul(r, base);
+    base = sqr(base);
+    e >>= 1;
+  }
+  return r;
+}
+
+// a^(p-2): inversion by Fermat (host finishers, table builders; not a hot op)
+template <class P>
+H2B_HD Fp<P> inv(const Fp<P>& a) {
+  // exponent p-2, processed MSB first
+  uint32_t e[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) e[i] = P::mod(i);
+  e[0] -= 2;  // low limb of both moduli is >= 2, no borrow
+  Fp<P> r = Fp<P>::one();
+  for (int i = 7; i >= 0; --i) {
+    for (int bit = 31; bit >= 0; --bit) {
+      r = sqr(r);
+      if ((e[i] >> bit) & 1) r = mul(r, a);
+    }
+  }
+  return r;
+}
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+}  // namespace h2b

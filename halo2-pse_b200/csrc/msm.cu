@@ -1,0 +1,620 @@
+// Pippenger multi-scalar multiplication over bn256 G1 for sm_100a: replaces
+// `best_multiexp` / `multiexp_serial`
+// (/root/reference/halo2_proofs/src/arithmetic.rs:13-159) behind
+// ParamsKZG::commit / commit_lagrange (poly/kzg/commitment.rs:281-292,327-334).
+//
+// Same result (sum_i coeffs[i] * bases[i]), different algorithm.  The reference
+// walks 256/c+1 unsigned windows serially per rayon chunk with 2^c-1 buckets;
+// here all windows are processed at once:
+//
+//  1. msm_digits_kernel: Montgomery -> canonical, signed c-bit digits
+//     (|d| <= 2^(c-1)), one (key, value) pair per (scalar, window):
+//     key = window * 2^(c-1) + |d| - 1, value = point index | sign << 31;
+//     zero digits get an all-ones key (the reference skips them too, :86).
+//  2. one radix sort of all pairs by key (cub::DeviceRadixSort) -- every bucket
+//     of every window becomes one contiguous run, zero digits sort to the end.
+//  3. bucket accumulation, load-balanced independent of the scalar
+//     distribution: the sorted array is cut into fixed chunks of L entries, one
+//     thread per chunk, mixed XYZZ additions.  A run (= bucket) that lies
+//     wholly inside a chunk is written straight to the dense bucket array; a
+//     run cut by a chunk boundary is emitted as a partial sum into a (still
+//     sorted) next-level list, which is reduced the same way until no run is
+//     cut.  All level sizes stay on the device: no host round trip.
+//  4. bucket reduction: segmented running sums (sum_b b * B_b per window) ->
+//     per-segment weights by double-and-add -> shared-memory tree sums.
+//  5. the W window sums are combined on the host (c doublings per window).
+#include "common.cuh"
+
+#ifndef H2B_EMU
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#endif
+#include <algorithm>
+
+namespace h2b {
+
+static const int kMaxLevels = 16;
+
+struct MsmWorkspace {
+  // capacities
+  size_t cap_pairs = 0, cap_chunks = 0, cap_list = 0, cap_buckets = 0, cap_seg = 0;
+  uint32_t *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
+  void* cub_temp = nullptr;
+  size_t cub_temp_bytes = 0;
+  uint32_t *cnt = nullptr, *incl = nullptr;
+  uint32_t* n_level = nullptr;  // [kMaxLevels + 2]
+  uint32_t* lkeys[2] = {nullptr, nullptr};
+  G1Xyzz* lpts[2] = {nullptr, nullptr};
+  G1Xyzz* buckets = nullptr;
+  G1Xyzz* seg[2] = {nullptr, nullptr};  // tree-sum ping-pong
+  G1Xyzz* h_out = nullptr;              // pinned, W window sums
+};
+
+static void ws_release(MsmWorkspace* ws) {
+  cudaFree(ws->keys_in);
+  cudaFree(ws->keys_out);
+  cudaFree(ws->vals_in);
+  cudaFree(ws->vals_out);
+  cudaFree(ws->cub_temp);
+  cudaFree(ws->cnt);
+  cudaFree(ws->incl);
+  cudaFree(ws->n_level);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(ws->lkeys[i]);
+    cudaFree(ws->lpts[i]);
+    cudaFree(ws->seg[i]);
+  }
+  cudaFree(ws->buckets);
+  if (ws->h_out) cudaFreeHost(ws->h_out);
+  *ws = MsmWorkspace();
+}
+
+void msm_ws_free(h2b_ctx* ctx) {
+  if (!ctx->msm_ws) return;
+  ws_release(ctx->msm_ws);
+  delete ctx->msm_ws;
+  ctx->msm_ws = nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// 1. digits
+// ---------------------------------------------------------------------------
+__global__ void msm_digits_kernel(const Fr* scalars, uint64_t n, uint32_t c, uint32_t W,
+                                  uint32_t* keys, uint32_t* vals) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const Fr s = from_mont(ld_fp(scalars + i));  // to_repr(), arithmetic.rs:14
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1);
+    for (uint32_t w = 0; w < W; ++w) {
+      const uint32_t bit = w * c;
+      uint32_t d = 0;
+      if (bit < 256) {
+        const uint32_t limb = bit >> 5, sh = bit & 31;
+        uint64_t two = s.v[limb];
+        if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
+        d = (uint32_t)(two >> sh) & ((1u << c) - 1u);
+      }
+      d += carry;
+      uint32_t negf = 0;
+      if (d > half) {
+        d = (1u << c) - d;
+        negf = 1;
+        carry = 1;
+      } else {
+        carry = 0;
+      }
+      keys[(uint64_t)w * n + i] = d ? w * half + d - 1 : 0xffffffffu;
+      vals[(uint64_t)w * n + i] = (uint32_t)i | (negf << 31);
+    }
+  }
+}
+
+// first index whose key has a bit at or above `kb` set (= number of non-zero digits)
+__global__ void msm_find_valid_kernel(const uint32_t* keys, uint64_t total, uint32_t kb,
+                                      uint32_t* n_level) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint64_t lo = 0, hi = total;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if ((keys[mid] >> kb) != 0)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  n_level[0] = (uint32_t)lo;
+}
+
+// ---------------------------------------------------------------------------
+// 3. chunked, level-wise bucket accumulation
+// ---------------------------------------------------------------------------
+// emissions of chunk t into the next level: its head run if the previous chunk
+// ends with the same key, its tail run if the next chunk starts with it
+__global__ void msm_count_kernel(const uint32_t* keys, const uint32_t* n_cur, uint32_t L,
+                                 uint32_t nchunks, uint32_t* cnt) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  const uint32_t N = *n_cur;
+  const uint64_t start = (uint64_t)t * L;
+  if (start >= N) {
+    cnt[t] = 0;
+    return;
+  }
+  const uint64_t end = start + L < N ? start + L : N;
+  const uint32_t kf = keys[start], kl = keys[end - 1];
+  const uint32_t head = start > 0 && keys[start - 1] == kf;
+  const uint32_t tail = end < N && keys[end] == kl;
+  cnt[t] = (kf == kl) ? (head | tail) : head + tail;
+}
+
+#ifdef H2B_EMU
+static void emu_inclusive_scan(const uint32_t* in, uint32_t* out, size_t n) {
+  uint32_t s = 0;
+  for (size_t i = 0; i < n; ++i) {
+    s += in[i];
+    out[i] = s;
+  }
+}
+#endif
+
+struct Level0Src {
+  const uint32_t* vals;
+  const G1Affine* bases;
+  H2B_D void add_to(G1Xyzz& acc, uint64_t i) const {
+    const uint32_t v = vals[i];
+    const G1Affine* src = bases + (v & 0x7fffffffu);
+    G1Affine p;
+    p.x = ld_fp_nc(&src->x);
+    p.y = ld_fp_nc(&src->y);
+    if (v >> 31) p.y = neg(p.y);
+    xyzz_add_affine(acc, p);
+  }
+};
+
+struct LevelNSrc {
+  const G1Xyzz* pts;
+  H2B_D void add_to(G1Xyzz& acc, uint64_t i) const {
+    G1Xyzz b;
+    b.x = ld_fp(&pts[i].x);
+    b.y = ld_fp(&pts[i].y);
+    b.zz = ld_fp(&pts[i].zz);
+    b.zzz = ld_fp(&pts[i].zzz);
+    xyzz_add(acc, b);
+  }
+};
+
+H2B_D void st_xyzz(G1Xyzz* dst, const G1Xyzz& p) {
+  st_fp(&dst->x, p.x);
+  st_fp(&dst->y, p.y);
+  st_fp(&dst->zz, p.zz);
+  st_fp(&dst->zzz, p.zzz);
+}
+
+template <class Src>
+H2B_D void msm_accum_body(const Src& src, const uint32_t* keys, const uint32_t* n_cur, uint32_t L,
+                          const uint32_t* cnt, const uint32_t* incl, uint32_t nchunks,
+                          uint32_t* n_next, uint32_t* okeys, G1Xyzz* opts, G1Xyzz* buckets) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  if (t == nchunks - 1) *n_next = incl[t];
+  const uint32_t N = *n_cur;
+  const uint64_t start = (uint64_t)t * L;
+  if (start >= N) return;
+  const uint64_t end = start + L < N ? start + L : N;
+  uint32_t o = incl[t] - cnt[t];
+  uint32_t cur = keys[start];
+  const bool head = start > 0 && keys[start - 1] == cur;
+  const bool tail = end < N && keys[end] == keys[end - 1];
+  bool first_run = true;
+  G1Xyzz acc = G1Xyzz::identity();
+  for (uint64_t i = start; i < end; ++i) {
+    const uint32_t k = keys[i];
+    if (k != cur) {
+      if (first_run && head) {
+        okeys[o] = cur;
+        st_xyzz(opts + o, acc);
+        ++o;
+      } else {
+        st_xyzz(buckets + cur, acc);
+      }
+      first_run = false;
+      acc = G1Xyzz::identity();
+      cur = k;
+    }
+    src.add_to(acc, i);
+  }
+  if ((first_run && head) || tail) {
+    okeys[o] = cur;
+    st_xyzz(opts + o, acc);
+  } else {
+    st_xyzz(buckets + cur, acc);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    msm_accum0_kernel(Level0Src src, const uint32_t* keys, const uint32_t* n_cur, uint32_t L,
+                      const uint32_t* cnt, const uint32_t* incl, uint32_t nchunks, uint32_t* n_next,
+                      uint32_t* okeys, G1Xyzz* opts, G1Xyzz* buckets) {
+  msm_accum_body(src, keys, n_cur, L, cnt, incl, nchunks, n_next, okeys, opts, buckets);
+}
+
+__global__ void __launch_bounds__(128)
+    msm_accumN_kernel(LevelNSrc src, const uint32_t* keys, const uint32_t* n_cur, uint32_t L,
+                      const uint32_t* cnt, const uint32_t* incl, uint32_t nchunks, uint32_t* n_next,
+                      uint32_t* okeys, G1Xyzz* opts, G1Xyzz* buckets) {
+  msm_accum_body(src, keys, n_cur, L, cnt, incl, nchunks, n_next, okeys, opts, buckets);
+}
+
+// ---------------------------------------------------------------------------
+// 4. bucket reduction
+// ---------------------------------------------------------------------------
+H2B_D G1Xyzz ld_xyzz(const G1Xyzz* p) {
+  G1Xyzz b;
+  b.x = ld_fp(&p->x);
+  b.y = ld_fp(&p->y);
+  b.zz = ld_fp(&p->zz);
+  b.zzz = ld_fp(&p->zzz);
+  return b;
+}
+
+// Segment s of window w covers buckets [s*M, (s+1)*M) (bucket index b holds
+// digit value b+1).  out[w*nseg + s] = sum_r (r + 1 + s*M) * B[s*M + r]:
+// running sums give A = sum (r+1) B and S = sum B; then A + [s*M] S by
+// double-and-add.
+__global__ void __launch_bounds__(128)
+    msm_bucket_seg_kernel(const G1Xyzz* buckets, uint32_t nb_per_window, uint32_t lM, uint32_t nseg,
+                          uint32_t total, G1Xyzz* out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const uint32_t w = t / nseg, s = t % nseg;
+  const uint32_t M = 1u << lM;
+  const G1Xyzz* seg = buckets + (uint64_t)w * nb_per_window + ((uint64_t)s << lM);
+  G1Xyzz running = G1Xyzz::identity(), acc = G1Xyzz::identity();
+  for (int r = (int)M - 1; r >= 0; --r) {  // arithmetic.rs:95-99
+    const G1Xyzz b = ld_xyzz(seg + r);
+    xyzz_add(running, b);
+    xyzz_add(acc, running);
+  }
+  // acc += [s * M] running
+  if (s != 0 && !running.is_identity()) {
+    G1Xyzz m = G1Xyzz::identity();
+    for (int bit = 31 - __clz((int)s); bit >= 0; --bit) {
+      m = xyzz_double(m);
+      if ((s >> bit) & 1) xyzz_add(m, running);
+    }
+    for (uint32_t i = 0; i < lM; ++i) m = xyzz_double(m);
+    xyzz_add(acc, m);
+  }
+  st_xyzz(out + t, acc);
+}
+
+// out[w * nout + b] = sum of in[w * nin + b*256 .. +256)
+__global__ void __launch_bounds__(256)
+    msm_tree_sum_kernel(const G1Xyzz* in, uint32_t nin, uint32_t nout, G1Xyzz* out) {
+  H2B_DYN_SMEM(smem_raw);
+  G1Xyzz* sm = reinterpret_cast<G1Xyzz*>(smem_raw);
+  const uint32_t w = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
+  const uint32_t idx = b * 256 + tid;
+  G1Xyzz v = G1Xyzz::identity();
+  if (idx < nin) v = ld_xyzz(in + (uint64_t)w * nin + idx);
+  sm[tid] = v;
+  __syncthreads();
+  for (uint32_t stride = 128; stride > 0; stride >>= 1) {
+    if (tid < stride) {
+      G1Xyzz a = sm[tid];
+      xyzz_add(a, sm[tid + stride]);
+      sm[tid] = a;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) st_xyzz(out + (uint64_t)w * nout + b, sm[0]);
+}
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+static uint32_t ceil_log2(uint64_t x) {
+  uint32_t l = 0;
+  while ((1ull << l) < x) ++l;
+  return l;
+}
+
+struct MsmPlan {
+  uint32_t c, W, kb, L0, LN, lM;
+  uint64_t pairs;
+  uint32_t nb_per_window, nseg;
+};
+
+static MsmPlan msm_plan(size_t n) {
+  MsmPlan p;
+  const uint32_t k = ceil_log2(n < 2 ? 2 : n);
+  int c = (int)k - 4;
+  if (c < 4) c = 4;
+  if (c > 20) c = 20;
+  if (const char* e = getenv("H2B_MSM_C")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= 24) c = v;
+  }
+  p.c = (uint32_t)c;
+  p.W = (255 + p.c - 1) / p.c;
+  p.nb_per_window = 1u << (p.c - 1);
+  p.kb = ceil_log2((uint64_t)p.W * p.nb_per_window);
+  p.pairs = (uint64_t)n * p.W;
+  p.L0 = p.pairs >= (1ull << 24) ? 64 : 32;
+  if (const char* e = getenv("H2B_MSM_L0")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= 4096) p.L0 = (uint32_t)v;
+  }
+  p.LN = 16;
+  p.lM = p.c - 1 < 5 ? p.c - 1 : 5;
+  p.nseg = p.nb_per_window >> p.lM;
+  return p;
+}
+
+static int ws_ensure(h2b_ctx* ctx, const MsmPlan& p) {
+  if (!ctx->msm_ws) ctx->msm_ws = new MsmWorkspace();
+  MsmWorkspace* ws = ctx->msm_ws;
+  const size_t chunks0 = (size_t)((p.pairs + p.L0 - 1) / p.L0);
+  const size_t list = 2 * chunks0 + 16;
+  const size_t nbuckets = (size_t)p.W * p.nb_per_window;
+  const size_t nsegs = (size_t)p.W * p.nseg;
+  if (p.pairs <= ws->cap_pairs && chunks0 <= ws->cap_chunks && list <= ws->cap_list &&
+      nbuckets <= ws->cap_buckets && nsegs <= ws->cap_seg)
+    return H2B_OK;
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ws_release(ws);
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->keys_in, p.pairs * 4 + 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->keys_out, p.pairs * 4 + 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->vals_in, p.pairs * 4 + 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->vals_out, p.pairs * 4 + 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->cnt, chunks0 * 4 + 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->incl, chunks0 * 4 + 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->n_level, (kMaxLevels + 2) * 4));
+  for (int i = 0; i < 2; ++i) {
+    H2B_CUDA(ctx, cudaMalloc((void**)&ws->lkeys[i], list * 4));
+    H2B_CUDA(ctx, cudaMalloc((void**)&ws->lpts[i], list * sizeof(G1Xyzz)));
+    H2B_CUDA(ctx, cudaMalloc((void**)&ws->seg[i], (nsegs + 256) * sizeof(G1Xyzz)));
+  }
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->buckets, nbuckets * sizeof(G1Xyzz)));
+  H2B_CUDA(ctx, cudaMallocHost((void**)&ws->h_out, 64 * sizeof(G1Xyzz)));
+#ifndef H2B_EMU
+  size_t t1 = 0, t2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, ws->keys_in, ws->keys_out, ws->vals_in,
+                                  ws->vals_out, p.pairs, 0, (int)p.kb + 1, ctx->stream);
+  cub::DeviceScan::InclusiveSum(nullptr, t2, ws->cnt, ws->incl, (int)chunks0, ctx->stream);
+  ws->cub_temp_bytes = std::max(t1, t2) + 256;
+  H2B_CUDA(ctx, cudaMalloc(&ws->cub_temp, ws->cub_temp_bytes));
+#endif
+  ws->cap_pairs = p.pairs;
+  ws->cap_chunks = chunks0;
+  ws->cap_list = list;
+  ws->cap_buckets = nbuckets;
+  ws->cap_seg = nsegs;
+  return H2B_OK;
+}
+
+int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n,
+            G1Xyzz* out_host) {
+  *out_host = G1Xyzz::identity();
+  if (n == 0) return H2B_OK;
+  if (n >= (1ull << 31)) return fail(ctx, H2B_ERR_ARG, "MSM larger than 2^31 points");
+  const MsmPlan p = msm_plan(n);
+  H2B_TRY(ws_ensure(ctx, p));
+  MsmWorkspace* ws = ctx->msm_ws;
+  cudaStream_t st = ctx->stream;
+  (void)st;
+
+  // 1. digits
+  {
+    const uint64_t want = (n + 255) / 256;
+    const uint64_t cap = (uint64_t)ctx->sm_count * 16;
+    H2B_TRY(launch(ctx, msm_digits_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0,
+                   d_scalars, (uint64_t)n, p.c, p.W, ws->keys_in, ws->vals_in));
+  }
+  // 2. sort
+#ifdef H2B_EMU
+  {
+    std::vector<std::pair<uint32_t, uint32_t>> v(p.pairs);
+    for (uint64_t i = 0; i < p.pairs; ++i) v[i] = {ws->keys_in[i], ws->vals_in[i]};
+    std::stable_sort(v.begin(), v.end(),
+                     [](const std::pair<uint32_t, uint32_t>& a,
+                        const std::pair<uint32_t, uint32_t>& b) { return a.first < b.first; });
+    for (uint64_t i = 0; i < p.pairs; ++i) {
+      ws->keys_out[i] = v[i].first;
+      ws->vals_out[i] = v[i].second;
+    }
+  }
+#else
+  H2B_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ws->cub_temp, ws->cub_temp_bytes, ws->keys_in,
+                                                ws->keys_out, ws->vals_in, ws->vals_out, p.pairs,
+                                                0, (int)p.kb + 1, st));
+  ctx->launches += 1 + (p.kb + 1 + 7) / 8;  // onesweep: histogram + one pass per 8 key bits
+#endif
+  H2B_TRY(launch(ctx, msm_find_valid_kernel, dim3(1), dim3(32), 0, (const uint32_t*)ws->keys_out,
+                 (uint64_t)p.pairs, p.kb, ws->n_level));
+  H2B_CUDA(ctx, cudaMemsetAsync(ws->buckets, 0,
+                                (size_t)p.W * p.nb_per_window * sizeof(G1Xyzz), st));
+
+  // 3. level-wise accumulation; Nmax bounds the list size of each level
+  if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+  {
+    uint64_t nmax = p.pairs;
+    const uint32_t* keys = ws->keys_out;
+    for (int level = 0; level < kMaxLevels; ++level) {
+      const uint32_t L = level == 0 ? p.L0 : p.LN;
+      const uint32_t nchunks = (uint32_t)((nmax + L - 1) / L);
+      const int o = level & 1;
+      H2B_TRY(launch(ctx, msm_count_kernel, dim3((nchunks + 255) / 256), dim3(256), 0, keys,
+                     (const uint32_t*)(ws->n_level + level), L, nchunks, ws->cnt));
+#ifdef H2B_EMU
+      emu_inclusive_scan(ws->cnt, ws->incl, nchunks);
+#else
+      H2B_CUDA(ctx, cub::DeviceScan::InclusiveSum(ws->cub_temp, ws->cub_temp_bytes, ws->cnt,
+                                                  ws->incl, (int)nchunks, st));
+      ctx->launches += 1;
+#endif
+      if (level == 0) {
+        Level0Src src{ws->vals_out, d_bases};
+        H2B_TRY(launch(ctx, msm_accum0_kernel, dim3((nchunks + 127) / 128), dim3(128), 0, src, keys,
+                       (const uint32_t*)(ws->n_level + level), L, (const uint32_t*)ws->cnt,
+                       (const uint32_t*)ws->incl, nchunks, ws->n_level + level + 1, ws->lkeys[o],
+                       ws->lpts[o], ws->buckets));
+        if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+      } else {
+        LevelNSrc src{ws->lpts[o ^ 1]};
+        H2B_TRY(launch(ctx, msm_accumN_kernel, dim3((nchunks + 127) / 128), dim3(128), 0, src, keys,
+                       (const uint32_t*)(ws->n_level + level), L, (const uint32_t*)ws->cnt,
+                       (const uint32_t*)ws->incl, nchunks, ws->n_level + level + 1, ws->lkeys[o],
+                       ws->lpts[o], ws->buckets));
+      }
+      if (nmax <= L) break;  // a single chunk cuts no run
+      nmax = 2ull * nchunks;
+      keys = ws->lkeys[o];
+      if (level + 1 == kMaxLevels) return fail(ctx, H2B_ERR_ARG, "MSM level overflow");
+    }
+  }
+
+  // 4. bucket reduction
+  {
+    const uint32_t total = p.W * p.nseg;
+    H2B_TRY(launch(ctx, msm_bucket_seg_kernel, dim3((total + 127) / 128), dim3(128), 0,
+                   (const G1Xyzz*)ws->buckets, p.nb_per_window, p.lM, p.nseg, total, ws->seg[0]));
+    uint32_t nin = p.nseg;
+    int cur = 0;
+    while (nin > 1) {
+      const uint32_t nout = (nin + 255) / 256;
+      H2B_TRY(launch(ctx, msm_tree_sum_kernel, dim3(nout, p.W), dim3(256), 256 * sizeof(G1Xyzz),
+                     (const G1Xyzz*)ws->seg[cur], nin, nout, ws->seg[cur ^ 1]));
+      cur ^= 1;
+      nin = nout;
+    }
+    H2B_CUDA(ctx, cudaMemcpyAsync(ws->h_out, ws->seg[cur], p.W * sizeof(G1Xyzz),
+                                  cudaMemcpyDeviceToHost, st));
+  }
+  H2B_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ctx->profile) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_kernel_ms = ms;
+  }
+
+  // 5. combine windows, top first: acc = 2^c * acc + R_w   (arithmetic.rs:46-49)
+  G1Xyzz acc = G1Xyzz::identity();
+  for (int w = (int)p.W - 1; w >= 0; --w) {
+    for (uint32_t i = 0; i < p.c; ++i) acc = xyzz_double(acc);
+    xyzz_add(acc, ws->h_out[w]);
+  }
+  *out_host = acc;
+  return H2B_OK;
+}
+
+}  // namespace h2b
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace h2b;
+
+extern "C" int h2b_bases_upload(h2b_ctx* ctx, const h2b_g1_affine* bases, size_t n, int loc,
+                                h2b_bases** out) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!out || (!bases && n)) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  h2b_bases* b = new h2b_bases();
+  b->ctx = ctx;
+  b->n = n;
+  b->d_pts = nullptr;
+  cudaError_t e = cudaMalloc((void**)&b->d_pts, (n ? n : 1) * sizeof(G1Affine));
+  if (e == cudaSuccess && n)
+    e = cudaMemcpyAsync(b->d_pts, bases, n * sizeof(G1Affine),
+                        loc == H2B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                        ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    if (b->d_pts) cudaFree(b->d_pts);
+    delete b;
+    return fail(ctx, e == cudaErrorMemoryAllocation ? H2B_ERR_OOM : H2B_ERR_CUDA,
+                cudaGetErrorString(e));
+  }
+  *out = b;
+  return H2B_OK;
+}
+
+extern "C" void h2b_bases_free(h2b_bases* b) {
+  if (!b) return;
+  std::lock_guard<std::recursive_mutex> lk(b->ctx->mu);
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  cudaFree(b->d_pts);
+  delete b;
+}
+
+extern "C" size_t h2b_bases_len(const h2b_bases* b) { return b ? b->n : 0; }
+extern "C" void* h2b_bases_device_ptr(const h2b_bases* b) { return b ? (void*)b->d_pts : nullptr; }
+
+static int msm_common(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
+                      const h2b_fr* scalars, int loc, size_t n, G1Xyzz* acc) {
+  if (!bases || bases->ctx != ctx) return fail(ctx, H2B_ERR_ARG, "bases belong to another context");
+  if (!scalars && n) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  // assert_eq!(coeffs.len(), bases.len()) / assert!(bases.len() >= size):
+  // arithmetic.rs:133, kzg/commitment.rs:290,332
+  if (base_offset > bases->n || n > bases->n - base_offset)
+    return fail(ctx, H2B_ERR_LENGTH, "more scalars than bases");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const Fr* d_scalars = reinterpret_cast<const Fr*>(scalars);
+  if (loc != H2B_DEVICE && n) {
+    H2B_TRY(ensure_stage(ctx, 0, n * sizeof(Fr)));
+    H2B_CUDA(ctx, cudaMemcpyAsync(ctx->stage[0], scalars, n * sizeof(Fr), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    d_scalars = reinterpret_cast<const Fr*>(ctx->stage[0]);
+  }
+  return msm_run(ctx, bases->d_pts + base_offset, d_scalars, n, acc);
+}
+
+static void xyzz_to_jacobian(const G1Xyzz& p, h2b_g1* out) {
+  // (X/ZZ, Y/ZZZ) with Z := ZZ: X_j = X*ZZ, Y_j = Y*ZZZ (ZZ^3 = ZZZ^2)
+  Fq xj = Fq::zero(), yj = Fq::one(), zj = Fq::zero();
+  if (!p.is_identity()) {
+    xj = mul(p.x, p.zz);
+    yj = mul(p.y, p.zzz);
+    zj = p.zz;
+  }
+  memcpy(&out->x, &xj, 32);
+  memcpy(&out->y, &yj, 32);
+  memcpy(&out->z, &zj, 32);
+}
+
+extern "C" int h2b_msm(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
+                       const h2b_fr* scalars, int loc, size_t n, h2b_g1* out) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!out) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  G1Xyzz acc;
+  H2B_TRY(msm_common(ctx, bases, base_offset, scalars, loc, n, &acc));
+  xyzz_to_jacobian(acc, out);
+  return H2B_OK;
+}
+
+extern "C" int h2b_msm_affine(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
+                              const h2b_fr* scalars, int loc, size_t n,
+                              h2b_g1_affine* out_affine) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!out_affine) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  G1Xyzz acc;
+  H2B_TRY(msm_common(ctx, bases, base_offset, scalars, loc, n, &acc));
+  const G1Affine a = xyzz_to_affine(acc);
+  memcpy(out_affine, &a, 64);
+  return H2B_OK;
+}
+
+extern "C" int h2b_best_multiexp(h2b_ctx* ctx, const h2b_fr* coeffs, const h2b_g1_affine* bases,
+                                 size_t n, h2b_g1* out) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  h2b_bases* b = nullptr;
+  H2B_TRY(h2b_bases_upload(ctx, bases, n, H2B_HOST, &b));
+  const int rc = h2b_msm(ctx, b, 0, coeffs, H2B_HOST, n, out);
+  h2b_bases_free(b);
+  return rc;
+}

@@ -1,0 +1,752 @@
+// Radix-2 NTT over bn256 Fr for sm_100a: replaces `best_fft`
+// (/root/reference/halo2_proofs/src/arithmetic.rs:171-274) and the
+// EvaluationDomain transforms built on it (poly/domain.rs:226-361).
+//
+// Same function (natural order in, natural order out, X[K] = sum_j a[j] w^(jK)),
+// different algorithm: instead of bit-reversal + log n radix-2 sweeps, the
+// transform is split into P = ceil(k/8) passes over HBM.  With digits
+// s_1..s_P (R_p = 2^s_p, m_1 = n, m_(p+1) = m_p / R_p) pass p computes, for
+// every sub-problem q of m_p contiguous elements and every jr < m_(p+1),
+//
+//   Y[q*m_p + K*m_(p+1) + jr] = w_(m_p)^(jr*K) * sum_(j1<R_p) X[q*m_p + j1*m_(p+1) + jr] * w_(R_p)^(j1*K)
+//
+// i.e. an R_p-point DFT down a strided column followed by the inter-pass
+// twiddle.  After the last pass the element at position K_1*m_2 + K_2*m_3 + ...
+// is output K_1 + R_1*K_2 + R_1*R_2*K_3 + ..., so the last pass scatters its
+// results to natural order (the "bit reversal" of the reference folded into
+// one pass).  A tile is R_p rows x C columns (C*32 B contiguous in HBM).
+//
+// The R_p-point column DFT itself is done by R_p/8 threads holding 8 elements
+// each: register radix-8 -> shared memory -> register radix-8 -> shared memory
+// -> radix-4/2, with a conflict-free XOR-swizzled limb-plane layout.  Scaling
+// steps of the domain transforms (zeta coset, zero padding, 1/n, division by
+// the vanishing polynomial, truncation) are fused into the first pass's load
+// and the last pass's store.
+#include "common.cuh"
+
+namespace h2b {
+
+struct PassParams {
+  const Fr* in;
+  Fr* out;
+  uint64_t in_bstride, out_bstride;  // elements between batch members
+  uint32_t k;                        // log2 n
+  uint32_t lm;                       // log2 m_p
+  uint32_t s;                        // log2 R_p
+  uint32_t lc;                       // log2 C
+  uint32_t first, last, single;
+  uint32_t s1;                       // log2 R_1
+  uint32_t nmid;                     // number of middle digits (s_2 .. s_(P-1))
+  uint32_t mid_s[4];                 // their widths, s_2 first
+  uint64_t n_in, n_out;
+  const Fr* pre;
+  uint32_t pre_mod;
+  const Fr* post;
+  uint32_t post_mod;
+  const Fr* tw_lo;
+  const Fr* tw_hi;
+  uint32_t h;
+  const Fr* rt;
+  uint32_t rt_log;
+};
+
+struct Tile {
+  uint64_t in_base, in_rs, in_cs;
+  uint64_t out_base, out_rs;
+  uint64_t jr0;
+};
+
+H2B_HD Tile tile_geom(const PassParams& p, uint64_t t) {
+  Tile g;
+  if (p.single) {
+    g.in_base = 0;
+    g.in_rs = 1;
+    g.in_cs = 0;
+    g.out_base = 0;
+    g.out_rs = 1;
+    g.jr0 = 0;
+  } else if (!p.last) {
+    const uint32_t lmn = p.lm - p.s;  // log2 m_(p+1)
+    const uint64_t jb = t & ((1ull << (lmn - p.lc)) - 1);
+    const uint64_t q = t >> (lmn - p.lc);
+    g.in_base = (q << p.lm) + (jb << p.lc);
+    g.in_rs = 1ull << lmn;
+    g.in_cs = 1;
+    g.out_base = g.in_base;
+    g.out_rs = g.in_rs;
+    g.jr0 = jb << p.lc;
+  } else {
+    // columns = consecutive values of the lowest output digit K_1
+    const uint64_t b1 = t & ((1ull << (p.s1 - p.lc)) - 1);
+    uint64_t rest = t >> (p.s1 - p.lc);
+    g.in_base = ((b1 << p.lc) << (p.k - p.s1)) + (rest << p.s);
+    g.in_cs = 1ull << (p.k - p.s1);
+    g.in_rs = 1;
+    uint32_t shift = 0;
+    for (uint32_t i = 0; i < p.nmid; ++i) shift += p.mid_s[i];
+    uint64_t acc = 0;
+    for (int i = (int)p.nmid - 1; i >= 0; --i) {
+      const uint64_t d = rest & ((1ull << p.mid_s[i]) - 1);
+      rest >>= p.mid_s[i];
+      shift -= p.mid_s[i];
+      acc |= d << shift;
+    }
+    g.out_base = (b1 << p.lc) + (acc << p.s1);
+    g.out_rs = 1ull << (p.k - p.s);
+    g.jr0 = 0;
+  }
+  return g;
+}
+
+H2B_D Fr load_in(const PassParams& p, const Fr* in, uint64_t gi) {
+  Fr x = (gi < p.n_in) ? ld_fp(in + gi) : Fr::zero();
+  if (p.first && p.pre) x = mul(x, ld_fp_nc(p.pre + (uint32_t)gi % p.pre_mod));
+  return x;
+}
+
+H2B_D void store_out(const PassParams& p, Fr* out, const Tile& g, uint32_t K, uint32_t c, Fr x) {
+  if (!p.last) {
+    const uint64_t e = ((g.jr0 + c) * (uint64_t)K) << (p.k - p.lm);
+    const uint32_t elo = (uint32_t)e & ((1u << p.h) - 1u);
+    const uint32_t ehi = (uint32_t)(e >> p.h);
+    x = mul(x, ld_fp_nc(p.tw_lo + elo));
+    x = mul(x, ld_fp_nc(p.tw_hi + ehi));
+    st_fp(out + g.out_base + (uint64_t)K * g.out_rs + c, x);
+  } else {
+    const uint64_t Ko = g.out_base + (uint64_t)K * g.out_rs + c;
+    if (p.post) x = mul(x, ld_fp_nc(p.post + (uint32_t)Ko % p.post_mod));
+    if (Ko < p.n_out) st_fp(out + Ko, x);
+  }
+}
+
+H2B_HD uint32_t bitrev32(uint32_t x, uint32_t bits) {
+  uint32_t r = 0;
+  for (uint32_t i = 0; i < bits; ++i) {
+    r = (r << 1) | (x & 1u);
+    x >>= 1;
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// Generic pass: any s <= 8, any C; radix-2 sweeps in shared memory.  Used for
+// the digit widths the register kernel does not cover (tiny transforms and the
+// odd leftover digit) -- never for the k = 16..28 benchmark shapes.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ntt_pass_generic(PassParams p) {
+  H2B_DYN_SMEM(smem_raw);
+  Fr* tile = reinterpret_cast<Fr*>(smem_raw);
+  const uint32_t R = 1u << p.s, C = 1u << p.lc;
+  const Tile g = tile_geom(p, blockIdx.x);
+  const Fr* in = p.in + (uint64_t)blockIdx.y * p.in_bstride;
+  Fr* out = p.out + (uint64_t)blockIdx.y * p.out_bstride;
+  for (uint32_t idx = threadIdx.x; idx < R * C; idx += blockDim.x) {
+    const uint32_t row = idx >> p.lc, col = idx & (C - 1);
+    const uint64_t gi = g.in_base + row * g.in_rs + col * g.in_cs;
+    tile[(bitrev32(row, p.s) << p.lc) + col] = load_in(p, in, gi);
+  }
+  __syncthreads();
+  for (uint32_t u = 1; u <= p.s; ++u) {
+    const uint32_t half = 1u << (u - 1);
+    for (uint32_t idx = threadIdx.x; idx < (R / 2) * C; idx += blockDim.x) {
+      const uint32_t col = idx & (C - 1), bi = idx >> p.lc;
+      const uint32_t i = bi & (half - 1), blk = bi >> (u - 1);
+      const uint32_t r0 = (blk << u) + i, r1 = r0 + half;
+      Fr a = tile[(r0 << p.lc) + col], b = tile[(r1 << p.lc) + col];
+      if (i) b = mul(b, ld_fp_nc(p.rt + (i << (p.rt_log - u))));
+      tile[(r0 << p.lc) + col] = add(a, b);
+      tile[(r1 << p.lc) + col] = sub(a, b);
+    }
+    __syncthreads();
+  }
+  for (uint32_t idx = threadIdx.x; idx < R * C; idx += blockDim.x) {
+    const uint32_t K = idx >> p.lc, col = idx & (C - 1);
+    store_out(p, out, g, K, col, tile[idx]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Register/shared-memory pass for s in {6,7,8}
+// ---------------------------------------------------------------------------
+// 8-point DFT, natural order in and out: x[K] <- sum_a x[a] * w8^(a*K).
+// w8 = rt[N/8], w4 = rt[N/4], w8^3 = rt[3N/8] with N = 2^rt_log.
+H2B_D void dft8(Fr* x, const Fr* rt, uint32_t rt_log) {
+  Fr s0 = add(x[0], x[4]), d0 = sub(x[0], x[4]);
+  Fr s1 = add(x[1], x[5]), d1 = sub(x[1], x[5]);
+  Fr s2 = add(x[2], x[6]), d2 = sub(x[2], x[6]);
+  Fr s3 = add(x[3], x[7]), d3 = sub(x[3], x[7]);
+  const Fr w4 = ld_fp_nc(rt + (1u << (rt_log - 2)));
+  d1 = mul(d1, ld_fp_nc(rt + (1u << (rt_log - 3))));
+  d2 = mul(d2, w4);
+  d3 = mul(d3, ld_fp_nc(rt + (3u << (rt_log - 3))));
+  // even outputs from s, odd outputs from d
+  Fr e0 = add(s0, s2), f0 = sub(s0, s2);
+  Fr e1 = add(s1, s3), f1 = mul(sub(s1, s3), w4);
+  x[0] = add(e0, e1);
+  x[4] = sub(e0, e1);
+  x[2] = add(f0, f1);
+  x[6] = sub(f0, f1);
+  e0 = add(d0, d2);
+  f0 = sub(d0, d2);
+  e1 = add(d1, d3);
+  f1 = mul(sub(d1, d3), w4);
+  x[1] = add(e0, e1);
+  x[5] = sub(e0, e1);
+  x[3] = add(f0, f1);
+  x[7] = sub(f0, f1);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
+  constexpr int R = 1 << S, T = R / 8, LC = 11 - S, C = 1 << LC;
+  constexpr int LM2 = S - 6, M2 = 1 << LM2;  // 4, 2, 1
+  constexpr int PLANE = 2048;
+  H2B_DYN_SMEM(smem_raw);
+  uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t c = tid & (C - 1), u = tid >> LC;
+  const Tile g = tile_geom(p, blockIdx.x);
+  const Fr* in = p.in + (uint64_t)blockIdx.y * p.in_bstride;
+  Fr* out = p.out + (uint64_t)blockIdx.y * p.out_bstride;
+  const uint32_t rsh = p.rt_log - S;  // w_R^e = rt[e << rsh]
+
+  auto slot = [&](uint32_t pos) -> uint32_t {
+    return ((pos ^ ((pos >> LM2) & (M2 - 1))) << LC) + c;
+  };
+  auto put = [&](uint32_t pos, const Fr& v) {
+    const uint32_t w = slot(pos);
+#pragma unroll
+    for (int l = 0; l < 8; ++l) sm[l * PLANE + w] = v.v[l];
+  };
+  auto get = [&](uint32_t pos) -> Fr {
+    const uint32_t w = slot(pos);
+    Fr v;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) v.v[l] = sm[l * PLANE + w];
+    return v;
+  };
+
+  Fr x[8];
+  // round 1: b = u, elements a*T + u
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const uint32_t row = a * T + u;
+    x[a] = load_in(p, in, g.in_base + row * g.in_rs + c * g.in_cs);
+  }
+  dft8(x, p.rt, p.rt_log);
+#pragma unroll
+  for (int Ka = 1; Ka < 8; ++Ka) x[Ka] = mul(x[Ka], ld_fp_nc(p.rt + ((u * Ka) << rsh)));
+#pragma unroll
+  for (int Ka = 0; Ka < 8; ++Ka) put(Ka * T + u, x[Ka]);
+  __syncthreads();
+  // round 2: (Ka, b2) = (u / M2, u % M2), elements Ka*T + a2*M2 + b2
+  const uint32_t Ka = u >> LM2, b2 = u & (M2 - 1);
+#pragma unroll
+  for (int a2 = 0; a2 < 8; ++a2) x[a2] = get(Ka * T + a2 * M2 + b2);
+  dft8(x, p.rt, p.rt_log);
+  if (M2 == 1) {
+#pragma unroll
+    for (int Ka2 = 0; Ka2 < 8; ++Ka2) store_out(p, out, g, Ka + 8 * Ka2, c, x[Ka2]);
+    return;
+  }
+#pragma unroll
+  for (int Ka2 = 1; Ka2 < 8; ++Ka2)
+    x[Ka2] = mul(x[Ka2], ld_fp_nc(p.rt + ((8 * b2 * Ka2) << rsh)));
+#pragma unroll
+  for (int Ka2 = 0; Ka2 < 8; ++Ka2) put(Ka * T + Ka2 * M2 + b2, x[Ka2]);
+  __syncthreads();
+  // round 3: groups gq = Ka*8 + Ka2 (64 per column), M2-point DFT over b2
+  if (M2 == 4) {
+    const Fr w4 = ld_fp_nc(p.rt + (1u << (p.rt_log - 2)));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t gq = u + 32 * i;
+      Fr v0 = get(gq * 4 + 0), v1 = get(gq * 4 + 1), v2 = get(gq * 4 + 2), v3 = get(gq * 4 + 3);
+      Fr t0 = add(v0, v2), t1 = sub(v0, v2), t2 = add(v1, v3), t3 = mul(sub(v1, v3), w4);
+      const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
+      store_out(p, out, g, K0, c, add(t0, t2));
+      store_out(p, out, g, K0 + 64, c, add(t1, t3));
+      store_out(p, out, g, K0 + 128, c, sub(t0, t2));
+      store_out(p, out, g, K0 + 192, c, sub(t1, t3));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t gq = u + 16 * i;
+      Fr v0 = get(gq * 2 + 0), v1 = get(gq * 2 + 1);
+      const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
+      store_out(p, out, g, K0, c, add(v0, v1));
+      store_out(p, out, g, K0 + 64, c, sub(v0, v1));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Element-wise kernels
+// ---------------------------------------------------------------------------
+// a[i] *= tab[i % mod]          (divide_by_vanishing_poly, domain.rs:307-326)
+__global__ void scale_mod_kernel(Fr* a, uint64_t n, const Fr* tab, uint32_t mod) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    st_fp(a + i, mul(ld_fp(a + i), ld_fp_nc(tab + (uint32_t)i % mod)));
+}
+
+// tab[i] = base^(i << shift), i < count
+__global__ void pow_table_kernel(Fr* tab, Fr base, uint32_t shift, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  uint64_t e = (uint64_t)i << shift;
+  Fr r = Fr::one(), b = base;
+  while (e) {
+    if (e & 1) r = mul(r, b);
+    b = sqr(b);
+    e >>= 1;
+  }
+  tab[i] = r;
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+static bool omega_has_order(const Fr& omega, uint32_t k) {
+  if (k == 0) return omega == Fr::one();
+  Fr t = omega;
+  for (uint32_t i = 0; i + 1 < k; ++i) t = sqr(t);
+  return t == neg(Fr::one());  // omega^(2^(k-1)) = -1  <=>  exact order 2^k
+}
+
+int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t k, const TwTable** out) {
+  for (auto& t : ctx->tw)
+    if (t.k == k && t.omega == omega) {
+      *out = &t;
+      return H2B_OK;
+    }
+  if (!omega_has_order(omega, k))
+    return fail(ctx, H2B_ERR_BAD_OMEGA, "omega is not a primitive 2^log_n-th root of unity");
+  TwTable t;
+  t.omega = omega;
+  t.k = k;
+  t.h = (k + 1) / 2;
+  const uint32_t nlo = 1u << t.h, nhi = 1u << (k - t.h);
+  const uint32_t rt_log = k < 8 ? k : 8;
+  H2B_CUDA(ctx, cudaMalloc((void**)&t.d_lo, (size_t)nlo * sizeof(Fr)));
+  H2B_CUDA(ctx, cudaMalloc((void**)&t.d_hi, (size_t)nhi * sizeof(Fr)));
+  H2B_CUDA(ctx, cudaMalloc((void**)&t.d_rt, ((size_t)1 << rt_log) * sizeof(Fr)));
+  H2B_TRY(launch(ctx, pow_table_kernel, dim3((nlo + 127) / 128), dim3(128), 0, t.d_lo, omega, 0u,
+                 nlo));
+  H2B_TRY(launch(ctx, pow_table_kernel, dim3((nhi + 127) / 128), dim3(128), 0, t.d_hi, omega, t.h,
+                 nhi));
+  H2B_TRY(launch(ctx, pow_table_kernel, dim3(((1u << rt_log) + 127) / 128), dim3(128), 0, t.d_rt,
+                 omega, k - rt_log, 1u << rt_log));
+  ctx->tw.push_back(t);
+  *out = &ctx->tw.back();
+  return H2B_OK;
+}
+
+void ntt_free_tables(h2b_ctx* ctx) {
+  for (auto& t : ctx->tw) {
+    cudaFree(t.d_lo);
+    cudaFree(t.d_hi);
+    cudaFree(t.d_rt);
+  }
+  ctx->tw.clear();
+}
+
+// Digit widths of the passes, ascending so the widest (fewest columns, best
+// coalescing on its strided load) comes last.
+static int ntt_plan(uint32_t k, uint32_t* s) {
+  if (k <= 8) {
+    s[0] = k;
+    return 1;
+  }
+  const int P = (int)((k + 7) / 8);
+  const uint32_t base = k / P, rem = k % P;
+  for (int i = 0; i < P; ++i) s[i] = base + ((uint32_t)i >= (uint32_t)P - rem ? 1u : 0u);
+  return P;
+}
+
+int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* tw, uint64_t n_in,
+            const Fr* d_pre, uint32_t pre_mod, const Fr* d_post, uint32_t post_mod,
+            uint64_t n_out, uint32_t batch, uint64_t in_stride, uint64_t out_stride) {
+  if (batch == 0) return H2B_OK;
+  if (k > 28) return fail(ctx, H2B_ERR_ARG, "log_n > 28 (Fr two-adicity)");
+  const uint64_t n = 1ull << k;
+  uint32_t s[4];
+  const int P = ntt_plan(k, s);
+
+  if (!ctx->ntt_attr_done) {
+    H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_generic,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_fast<6>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_fast<7>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_fast<8>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    ctx->ntt_attr_done = true;
+  }
+
+  // Scratch holds the intermediate passes of a group of batch members.
+  const uint64_t kScratchCap = 8ull << 30;
+  uint32_t group = batch;
+  if (P > 1) {
+    const uint64_t per = n * sizeof(Fr);
+    uint64_t g = kScratchCap / per;
+    if (g < 1) g = 1;
+    if (g < group) group = (uint32_t)g;
+    H2B_TRY(ensure_scratch(ctx, (size_t)(per * group)));
+  }
+  Fr* scratch = reinterpret_cast<Fr*>(ctx->scratch);
+
+  for (uint32_t b0 = 0; b0 < batch; b0 += group) {
+    const uint32_t nb = (batch - b0 < group) ? batch - b0 : group;
+    uint32_t lm = k;
+    for (int pi = 0; pi < P; ++pi) {
+      PassParams p;
+      p.k = k;
+      p.lm = lm;
+      p.s = s[pi];
+      p.first = pi == 0;
+      p.last = pi == P - 1;
+      p.single = P == 1;
+      p.s1 = s[0];
+      p.nmid = 0;
+      for (int i = 1; i + 1 < P; ++i) p.mid_s[p.nmid++] = s[i];
+      p.n_in = p.first ? n_in : n;
+      p.n_out = p.last ? n_out : n;
+      p.pre = p.first ? d_pre : nullptr;
+      p.pre_mod = pre_mod ? pre_mod : 1;
+      p.post = p.last ? d_post : nullptr;
+      p.post_mod = post_mod ? post_mod : 1;
+      p.tw_lo = tw->d_lo;
+      p.tw_hi = tw->d_hi;
+      p.h = tw->h;
+      p.rt = tw->d_rt;
+      p.rt_log = k < 8 ? k : 8;
+      if (p.first) {
+        p.in = d_in + (uint64_t)b0 * in_stride;
+        p.in_bstride = in_stride;
+      } else {
+        p.in = scratch;
+        p.in_bstride = n;
+      }
+      if (p.last) {
+        p.out = d_out + (uint64_t)b0 * out_stride;
+        p.out_bstride = out_stride;
+      } else {
+        p.out = scratch;
+        p.out_bstride = n;
+      }
+      // columns per tile
+      uint32_t lc = 11 - p.s;
+      const uint32_t avail = p.single ? 0 : (p.last ? p.s1 : lm - p.s);
+      const bool fast = !p.single && p.s >= 6 && p.s <= 8 && lc <= avail;
+      if (lc > avail) lc = avail;
+      p.lc = lc;
+      const uint32_t tiles = (uint32_t)(n >> (p.s + lc));
+      const dim3 grid(tiles, nb);
+      if (fast) {
+        if (p.s == 6) H2B_TRY(launch(ctx, ntt_pass_fast<6>, grid, dim3(256), 65536, p));
+        if (p.s == 7) H2B_TRY(launch(ctx, ntt_pass_fast<7>, grid, dim3(256), 65536, p));
+        if (p.s == 8) H2B_TRY(launch(ctx, ntt_pass_fast<8>, grid, dim3(256), 65536, p));
+      } else {
+        H2B_TRY(launch(ctx, ntt_pass_generic, grid, dim3(256), 65536, p));
+      }
+      lm -= p.s;
+    }
+  }
+  return H2B_OK;
+}
+
+}  // namespace h2b
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace h2b;
+
+static const Fr* as_fr(const h2b_fr* p) { return reinterpret_cast<const Fr*>(p); }
+static Fr* as_fr(h2b_fr* p) { return reinterpret_cast<Fr*>(p); }
+
+namespace {
+// Device view of a caller buffer: the pointer itself for H2B_DEVICE, a staged
+// copy for H2B_HOST.
+struct Staged {
+  h2b_ctx* ctx;
+  int which;
+  Fr* dev = nullptr;
+  int in(const h2b_fr* p, int loc, size_t count, bool copy) {
+    if (loc == H2B_DEVICE) {
+      dev = const_cast<Fr*>(as_fr(p));
+      return H2B_OK;
+    }
+    H2B_TRY(ensure_stage(ctx, which, count * sizeof(Fr)));
+    dev = reinterpret_cast<Fr*>(ctx->stage[which]);
+    if (copy)
+      H2B_CUDA(ctx, cudaMemcpyAsync(dev, p, count * sizeof(Fr), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+    return H2B_OK;
+  }
+  int out(h2b_fr* p, int loc, size_t count) {
+    if (loc == H2B_DEVICE) return H2B_OK;
+    H2B_CUDA(ctx,
+             cudaMemcpyAsync(p, dev, count * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2B_OK;
+  }
+};
+}  // namespace
+
+extern "C" int h2b_best_fft_batch(h2b_ctx* ctx, h2b_fr* a, int loc, const h2b_fr* omega,
+                                  uint32_t log_n, uint32_t ncols, size_t stride) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!a || !omega) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (log_n > 28) return fail(ctx, H2B_ERR_ARG, "log_n > 28");
+  const size_t n = (size_t)1 << log_n;
+  if (ncols == 0) return H2B_OK;
+  if (stride < n) return fail(ctx, H2B_ERR_LENGTH, "stride < 2^log_n");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const TwTable* tw;
+  H2B_TRY(ntt_get_table(ctx, *as_fr(omega), log_n, &tw));
+  Staged st{ctx, 0};
+  const size_t count = (size_t)(ncols - 1) * stride + n;
+  H2B_TRY(st.in(a, loc, count, true));
+  H2B_TRY(ntt_run(ctx, st.dev, st.dev, log_n, tw, n, nullptr, 1, nullptr, 1, n, ncols, stride,
+                  stride));
+  return st.out(a, loc, count);
+}
+
+extern "C" int h2b_best_fft(h2b_ctx* ctx, h2b_fr* a, int loc, const h2b_fr* omega,
+                            uint32_t log_n) {
+  return h2b_best_fft_batch(ctx, a, loc, omega, log_n, 1, (size_t)1 << (log_n > 28 ? 0 : log_n));
+}
+
+// ---- EvaluationDomain ------------------------------------------------------
+static Fr fr_from_u64_canonical(const uint64_t l[4]) {
+  Fr r;
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = (uint32_t)l[i];
+    r.v[2 * i + 1] = (uint32_t)(l[i] >> 32);
+  }
+  return to_mont(r);
+}
+
+static Fr fr_pow2k(Fr a, uint32_t times) {
+  for (uint32_t i = 0; i < times; ++i) a = sqr(a);
+  return a;
+}
+
+extern "C" int h2b_domain_new(h2b_ctx* ctx, uint32_t j, uint32_t k, h2b_domain** out) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!out) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (j < 2) return fail(ctx, H2B_ERR_ARG, "j < 2");
+  // Fr::ROOT_OF_UNITY (order 2^28) and Fr::ZETA, canonical values
+  static const uint64_t kRoot[4] = {0xd34f1ed960c37c9cull, 0x3215cf6dd39329c8ull,
+                                    0x98865ea93dd31f74ull, 0x03ddb9f5166d18b7ull};
+  static const uint64_t kZeta[4] = {0x8b17ea66b99c90ddull, 0x5bfc41088d8daaa7ull,
+                                    0xb3c4d79d41a91758ull, 0x0ull};
+  const uint32_t S = 28;
+  const uint32_t qd = j - 1;  // quotient_poly_degree, domain.rs:41
+  uint32_t ek = k;
+  while (ek <= S && (1ull << ek) < (1ull << k) * qd) ++ek;  // domain.rs:49-52
+  if (k > S || ek > S) return fail(ctx, H2B_ERR_ARG, "extended_k exceeds Fr two-adicity 28");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  h2b_domain* d = new h2b_domain();
+  d->ctx = ctx;
+  d->j = j;
+  d->k = k;
+  d->extended_k = ek;
+  d->quotient_poly_degree = qd;
+  d->extended_omega = fr_pow2k(fr_from_u64_canonical(kRoot), S - ek);  // domain.rs:54-61
+  d->omega = fr_pow2k(d->extended_omega, ek - k);                        // domain.rs:70-73
+  d->extended_omega_inv = inv(d->extended_omega);
+  d->omega_inv = inv(d->omega);
+  d->g_coset = fr_from_u64_canonical(kZeta);  // domain.rs:81
+  d->g_coset_inv = sqr(d->g_coset);            // domain.rs:82
+  Fr two = add(Fr::one(), Fr::one());
+  Fr nk = Fr::one(), nek = Fr::one();
+  for (uint32_t i = 0; i < k; ++i) nk = mul(nk, two);
+  for (uint32_t i = 0; i < ek; ++i) nek = mul(nek, two);
+  d->ifft_divisor = inv(nk);
+  d->extended_ifft_divisor = inv(nek);
+  // t_evaluations, domain.rs:84-124
+  {
+    Fr orig = fr_pow2k(d->g_coset, 0);
+    // zeta^n with n = 2^k
+    orig = fr_pow2k(d->g_coset, k);
+    const Fr step = fr_pow2k(d->extended_omega, k);
+    Fr cur = orig;
+    const Fr one = Fr::one();
+    do {
+      d->t_evaluations.push_back(inv(sub(cur, one)));
+      cur = mul(cur, step);
+    } while (cur != orig && d->t_evaluations.size() < ((size_t)1 << (ek - k)) + 1);
+    if (d->t_evaluations.size() != (size_t)1 << (ek - k)) {
+      delete d;
+      return fail(ctx, H2B_ERR_ARG, "t_evaluations cycle length mismatch");
+    }
+  }
+  // device tables
+  std::vector<Fr> zin = {Fr::one(), d->g_coset, d->g_coset_inv};
+  std::vector<Fr> zout = {d->extended_ifft_divisor, mul(d->extended_ifft_divisor, d->g_coset_inv),
+                          mul(d->extended_ifft_divisor, d->g_coset)};
+  auto up = [&](Fr** dst, const std::vector<Fr>& v) -> int {
+    H2B_CUDA(ctx, cudaMalloc((void**)dst, v.size() * sizeof(Fr)));
+    H2B_CUDA(ctx, cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(Fr), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2B_OK;
+  };
+  int rc = up(&d->d_zeta_in, zin);
+  if (rc == H2B_OK) rc = up(&d->d_ext_post, zout);
+  if (rc == H2B_OK) rc = up(&d->d_ifft_post, std::vector<Fr>{d->ifft_divisor});
+  if (rc == H2B_OK) rc = up(&d->d_t_inv, d->t_evaluations);
+  if (rc != H2B_OK) {
+    delete d;
+    return rc;
+  }
+  *out = d;
+  return H2B_OK;
+}
+
+extern "C" void h2b_domain_free(h2b_domain* d) {
+  if (!d) return;
+  std::lock_guard<std::recursive_mutex> lk(d->ctx->mu);
+  cudaFree(d->d_zeta_in);
+  cudaFree(d->d_ext_post);
+  cudaFree(d->d_ifft_post);
+  cudaFree(d->d_t_inv);
+  delete d;
+}
+
+extern "C" uint32_t h2b_domain_k(const h2b_domain* d) { return d ? d->k : 0; }
+extern "C" uint32_t h2b_domain_extended_k(const h2b_domain* d) { return d ? d->extended_k : 0; }
+extern "C" size_t h2b_domain_quotient_len(const h2b_domain* d) {
+  return d ? ((size_t)1 << d->k) * d->quotient_poly_degree : 0;
+}
+
+extern "C" int h2b_domain_constant(const h2b_domain* d, uint32_t which, h2b_fr* out) {
+  if (!d || !out) return H2B_ERR_ARG;
+  const Fr* src = nullptr;
+  switch (which) {
+    case 0: src = &d->omega; break;
+    case 1: src = &d->omega_inv; break;
+    case 2: src = &d->extended_omega; break;
+    case 3: src = &d->extended_omega_inv; break;
+    case 4: src = &d->g_coset; break;
+    case 5: src = &d->g_coset_inv; break;
+    case 6: src = &d->ifft_divisor; break;
+    case 7: src = &d->extended_ifft_divisor; break;
+    default:
+      if (which - 8 < d->t_evaluations.size()) src = &d->t_evaluations[which - 8];
+  }
+  if (!src) return H2B_ERR_ARG;
+  memcpy(out, src, sizeof(Fr));
+  return H2B_OK;
+}
+
+extern "C" int h2b_lagrange_to_coeff_batch(h2b_domain* d, h2b_fr* a, int loc, uint32_t ncols,
+                                           size_t stride) {
+  if (!d) return H2B_ERR_ARG;
+  h2b_ctx* ctx = d->ctx;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!a) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (ncols == 0) return H2B_OK;
+  const size_t n = (size_t)1 << d->k;
+  if (stride < n) return fail(ctx, H2B_ERR_LENGTH, "stride < n");  // domain.rs:227
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const TwTable* tw;
+  H2B_TRY(ntt_get_table(ctx, d->omega_inv, d->k, &tw));
+  Staged st{ctx, 0};
+  const size_t count = (size_t)(ncols - 1) * stride + n;
+  H2B_TRY(st.in(a, loc, count, true));
+  H2B_TRY(ntt_run(ctx, st.dev, st.dev, d->k, tw, n, nullptr, 1, d->d_ifft_post, 1, n, ncols,
+                  stride, stride));
+  return st.out(a, loc, count);
+}
+
+extern "C" int h2b_lagrange_to_coeff(h2b_domain* d, h2b_fr* a, int loc) {
+  return h2b_lagrange_to_coeff_batch(d, a, loc, 1, d ? (size_t)1 << d->k : 0);
+}
+
+extern "C" int h2b_coeff_to_extended_batch(h2b_domain* d, const h2b_fr* in, size_t in_stride,
+                                           h2b_fr* out, size_t out_stride, int loc,
+                                           uint32_t ncols) {
+  if (!d) return H2B_ERR_ARG;
+  h2b_ctx* ctx = d->ctx;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!in || !out) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (ncols == 0) return H2B_OK;
+  const size_t n = (size_t)1 << d->k, ne = (size_t)1 << d->extended_k;
+  if (in_stride < n || out_stride < ne)
+    return fail(ctx, H2B_ERR_LENGTH, "stride shorter than the polynomial");  // domain.rs:244
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const TwTable* tw;
+  H2B_TRY(ntt_get_table(ctx, d->extended_omega, d->extended_k, &tw));
+  Staged sin{ctx, 0}, sout{ctx, 1};
+  const size_t cin = (size_t)(ncols - 1) * in_stride + n;
+  const size_t cout = (size_t)(ncols - 1) * out_stride + ne;
+  H2B_TRY(sin.in(in, loc, cin, true));
+  H2B_TRY(sout.in(out, loc, cout, false));
+  H2B_TRY(ntt_run(ctx, sin.dev, sout.dev, d->extended_k, tw, n, d->d_zeta_in, 3, nullptr, 1, ne,
+                  ncols, in_stride, out_stride));
+  return sout.out(out, loc, cout);
+}
+
+extern "C" int h2b_coeff_to_extended(h2b_domain* d, const h2b_fr* in, h2b_fr* out, int loc) {
+  if (!d) return H2B_ERR_ARG;
+  return h2b_coeff_to_extended_batch(d, in, (size_t)1 << d->k, out, (size_t)1 << d->extended_k,
+                                     loc, 1);
+}
+
+extern "C" int h2b_extended_to_coeff_batch(h2b_domain* d, const h2b_fr* in, size_t in_stride,
+                                           h2b_fr* out, size_t out_stride, int loc,
+                                           uint32_t ncols, int divide_by_vanishing) {
+  if (!d) return H2B_ERR_ARG;
+  h2b_ctx* ctx = d->ctx;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!in || !out) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (ncols == 0) return H2B_OK;
+  const size_t ne = (size_t)1 << d->extended_k;
+  const size_t nq = ((size_t)1 << d->k) * d->quotient_poly_degree;
+  if (in_stride < ne || out_stride < nq)
+    return fail(ctx, H2B_ERR_LENGTH, "stride shorter than the polynomial");  // domain.rs:282
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const TwTable* tw;
+  H2B_TRY(ntt_get_table(ctx, d->extended_omega_inv, d->extended_k, &tw));
+  Staged sin{ctx, 0}, sout{ctx, 1};
+  const size_t cin = (size_t)(ncols - 1) * in_stride + ne;
+  const size_t cout = (size_t)(ncols - 1) * out_stride + nq;
+  H2B_TRY(sin.in(in, loc, cin, true));
+  H2B_TRY(sout.in(out, loc, cout, false));
+  H2B_TRY(ntt_run(ctx, sin.dev, sout.dev, d->extended_k, tw, ne,
+                  divide_by_vanishing ? d->d_t_inv : nullptr,
+                  (uint32_t)d->t_evaluations.size(), d->d_ext_post, 3, nq, ncols, in_stride,
+                  out_stride));
+  return sout.out(out, loc, cout);
+}
+
+extern "C" int h2b_extended_to_coeff(h2b_domain* d, const h2b_fr* in, h2b_fr* out, int loc,
+                                     int divide_by_vanishing) {
+  if (!d) return H2B_ERR_ARG;
+  return h2b_extended_to_coeff_batch(d, in, (size_t)1 << d->extended_k, out,
+                                     h2b_domain_quotient_len(d), loc, 1, divide_by_vanishing);
+}
+
+extern "C" int h2b_divide_by_vanishing_poly(h2b_domain* d, h2b_fr* a, int loc) {
+  if (!d) return H2B_ERR_ARG;
+  h2b_ctx* ctx = d->ctx;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!a) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  const size_t ne = (size_t)1 << d->extended_k;
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  Staged st{ctx, 0};
+  H2B_TRY(st.in(a, loc, ne, true));
+  const uint32_t blocks = (uint32_t)((ne + 255) / 256 < 148 * 16 ? (ne + 255) / 256 : 148 * 16);
+  H2B_TRY(launch(ctx, scale_mod_kernel, dim3(blocks), dim3(256), 0, st.dev, (uint64_t)ne,
+                 (const Fr*)d->d_t_inv, (uint32_t)d->t_evaluations.size()));
+  return st.out(a, loc, ne);
+}

@@ -1,0 +1,159 @@
+/* libhalo2b200 -- C ABI of the B200-native backend for halo2_proofs' two
+ * data-parallel hot paths over bn256 (MSM and NTT).
+ *
+ * The reference (eldenpark/halo2-pse, 100 % Rust) has no FFI: its boundary is
+ * the Rust function signatures below.  Each export names the signature it
+ * replaces (paths relative to /root/reference/halo2_proofs/src).  The Rust
+ * shim a maintainer would add on the reference side is in INTEGRATION.md.
+ *
+ * Data layout (identical bytes to halo2curves 0.3.1):
+ *   h2b_fr / h2b_fq : four little-endian u64 limbs holding the Montgomery
+ *                     residue a * 2^256 mod p, fully reduced.
+ *   h2b_g1_affine   : {x, y}; the identity is (0, 0).
+ *   h2b_g1          : Jacobian {x, y, z} (x/z^2, y/z^3); identity has z = 0.
+ *
+ * Conventions: every function returns H2B_OK (0) or a negative error code and
+ * never throws; the reference panics where this ABI returns H2B_ERR_LENGTH /
+ * H2B_ERR_ARG (arithmetic.rs:133,184; domain.rs:227,244,282,311;
+ * kzg/commitment.rs:290,332).  `loc` says where a data pointer lives:
+ * H2B_HOST (the drop-in case: the library stages through pinned memory) or
+ * H2B_DEVICE (device-resident polynomials/scalars on the context's device).
+ * All calls on one context are serialised internally (thread-safe); use one
+ * context per caller thread for concurrency.  There is no CPU fallback: every
+ * compute entry point fails with H2B_ERR_CUDA when no device is usable.
+ */
+#ifndef HALO2_B200_H
+#define HALO2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } h2b_fr;
+typedef struct { uint64_t l[4]; } h2b_fq;
+typedef struct { h2b_fq x, y; } h2b_g1_affine;
+typedef struct { h2b_fq x, y, z; } h2b_g1;
+
+typedef struct h2b_ctx h2b_ctx;       /* one device + stream + scratch            */
+typedef struct h2b_bases h2b_bases;   /* device-resident, immutable affine bases  */
+typedef struct h2b_domain h2b_domain; /* EvaluationDomain: constants + tables     */
+
+enum {
+  H2B_OK = 0,
+  H2B_ERR_ARG = -1,       /* null pointer, bad enum, k out of range              */
+  H2B_ERR_LENGTH = -2,    /* the reference's assert_eq!(len) panics              */
+  H2B_ERR_CUDA = -3,      /* CUDA runtime / launch failure, or no device         */
+  H2B_ERR_OOM = -4,       /* device or pinned allocation failed                  */
+  H2B_ERR_BAD_OMEGA = -5  /* omega is not a primitive 2^log_n-th root of unity   */
+};
+enum { H2B_HOST = 0, H2B_DEVICE = 1 };
+
+/* ---- context ----------------------------------------------------------- */
+int h2b_ctx_create(int device, h2b_ctx** out);
+void h2b_ctx_destroy(h2b_ctx* ctx);
+const char* h2b_last_error(const h2b_ctx* ctx);
+int h2b_ctx_sync(h2b_ctx* ctx);
+/* the cudaStream_t every kernel of this context is launched on */
+void* h2b_ctx_stream(h2b_ctx* ctx);
+/* number of kernels this context has launched so far */
+uint64_t h2b_ctx_launches(const h2b_ctx* ctx);
+
+/* ---- MSM --------------------------------------------------------------- */
+/* Upload `g` / `g_lagrange` once (ParamsKZG fields, poly/kzg/commitment.rs:23-31). */
+int h2b_bases_upload(h2b_ctx* ctx, const h2b_g1_affine* bases, size_t n, int loc,
+                     h2b_bases** out);
+void h2b_bases_free(h2b_bases* bases);
+size_t h2b_bases_len(const h2b_bases* bases);
+
+/* best_multiexp(coeffs, &bases[offset..offset+n])          arithmetic.rs:132
+ * = ParamsKZG::commit_lagrange / commit with the matching base set
+ *                                  poly/kzg/commitment.rs:281-292, 327-334
+ * `out` is written on the host. */
+int h2b_msm(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset, const h2b_fr* scalars,
+            int loc, size_t n, h2b_g1* out);
+/* Same result, normalised: out_affine = to_affine(sum) ((0,0) for identity). */
+int h2b_msm_affine(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
+                   const h2b_fr* scalars, int loc, size_t n, h2b_g1_affine* out_affine);
+/* One-shot drop-in with the exact shape of best_multiexp (host slices).  arithmetic.rs:132 */
+int h2b_best_multiexp(h2b_ctx* ctx, const h2b_fr* coeffs, const h2b_g1_affine* bases, size_t n,
+                      h2b_g1* out);
+
+/* ---- NTT --------------------------------------------------------------- */
+/* best_fft(a, omega, log_n): in place, natural order in and out.  arithmetic.rs:171
+ * omega must be a primitive 2^log_n-th root of unity (every non-bench caller
+ * passes one: domain.rs:230,248,285-290; arithmetic.rs:285). */
+int h2b_best_fft(h2b_ctx* ctx, h2b_fr* a, int loc, const h2b_fr* omega, uint32_t log_n);
+
+/* EvaluationDomain::new(j, k)                                     poly/domain.rs:39 */
+int h2b_domain_new(h2b_ctx* ctx, uint32_t j, uint32_t k, h2b_domain** out);
+void h2b_domain_free(h2b_domain* dom);
+uint32_t h2b_domain_k(const h2b_domain* dom);
+uint32_t h2b_domain_extended_k(const h2b_domain* dom);
+/* n * quotient_poly_degree: the length extended_to_coeff returns (domain.rs:299-300) */
+size_t h2b_domain_quotient_len(const h2b_domain* dom);
+/* which = 0 omega, 1 omega_inv, 2 extended_omega, 3 extended_omega_inv,
+ *         4 g_coset, 5 g_coset_inv, 6 ifft_divisor, 7 extended_ifft_divisor,
+ *         8 + i  t_evaluations[i]                           (domain.rs:19-34) */
+int h2b_domain_constant(const h2b_domain* dom, uint32_t which, h2b_fr* out);
+
+/* lagrange_to_coeff: a (2^k) in place                       poly/domain.rs:226 */
+int h2b_lagrange_to_coeff(h2b_domain* dom, h2b_fr* a, int loc);
+/* coeff_to_extended: in (2^k) -> out (2^extended_k)         poly/domain.rs:240 */
+int h2b_coeff_to_extended(h2b_domain* dom, const h2b_fr* in, h2b_fr* out, int loc);
+/* extended_to_coeff: in (2^extended_k) -> out (quotient_len); when
+ * divide_by_vanishing != 0 the preceding divide_by_vanishing_poly is fused in
+ * (the only call order in the reference, plonk/vanishing/prover.rs:84-87).
+ * `in` is not modified.                                     poly/domain.rs:281 */
+int h2b_extended_to_coeff(h2b_domain* dom, const h2b_fr* in, h2b_fr* out, int loc,
+                          int divide_by_vanishing);
+/* divide_by_vanishing_poly: a (2^extended_k) in place       poly/domain.rs:307 */
+int h2b_divide_by_vanishing_poly(h2b_domain* dom, h2b_fr* a, int loc);
+
+/* Batched (column-parallel) forms: `ncols` polynomials, column c at
+ * base + c * stride elements (stride >= the column's length).  One launch per
+ * pass covers all columns. */
+int h2b_best_fft_batch(h2b_ctx* ctx, h2b_fr* a, int loc, const h2b_fr* omega, uint32_t log_n,
+                       uint32_t ncols, size_t stride);
+int h2b_lagrange_to_coeff_batch(h2b_domain* dom, h2b_fr* a, int loc, uint32_t ncols,
+                                size_t stride);
+int h2b_coeff_to_extended_batch(h2b_domain* dom, const h2b_fr* in, size_t in_stride, h2b_fr* out,
+                                size_t out_stride, int loc, uint32_t ncols);
+int h2b_extended_to_coeff_batch(h2b_domain* dom, const h2b_fr* in, size_t in_stride, h2b_fr* out,
+                                size_t out_stride, int loc, uint32_t ncols,
+                                int divide_by_vanishing);
+
+/* ---- device helpers for callers that keep data resident ------------------ */
+int h2b_device_alloc(h2b_ctx* ctx, size_t bytes, void** out);
+void h2b_device_free(h2b_ctx* ctx, void* p);
+int h2b_copy_h2d(h2b_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int h2b_copy_d2h(h2b_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* Synthetic benchmark inputs, generated on device:
+ * uniform Fr in Montgomery form from a counter-based generator; and n valid
+ * distinct G1 points P_i = P_0 + i*D. */
+int h2b_synth_scalars(h2b_ctx* ctx, h2b_fr* dst_dev, size_t n, uint64_t seed, uint32_t kind);
+int h2b_synth_bases(h2b_ctx* ctx, h2b_g1_affine* dst_dev, size_t n, uint64_t seed);
+
+/* ---- measurement / test hooks ------------------------------------------- */
+/* Register-only IMAD microbenchmark: returns achieved 32x32 multiply-adds/s. */
+int h2b_imad_peak(h2b_ctx* ctx, double* imad_per_s, double* sm_mhz_effective);
+/* Element-wise device ops (op: 0 mul, 1 add, 2 sub, 3 sqr, 4 to_mont, 5 from_mont,
+ * 6 neg, 7 inv); field: 0 Fr, 1 Fq.  Host pointers. */
+int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const h2b_fr* a, const h2b_fr* b,
+                      h2b_fr* out, size_t n);
+/* Same ops on the host code path of the same header (no device needed). */
+int h2b_host_field_op(int field, int op, const h2b_fr* a, const h2b_fr* b, h2b_fr* out, size_t n);
+/* Device group law: op 0: out[i] = a[i] + b[i] (affine + affine via XYZZ),
+ * 1: out[i] = 2*a[i].  Host pointers; results normalised to affine. */
+int h2b_test_g1_op(h2b_ctx* ctx, int op, const h2b_g1_affine* a, const h2b_g1_affine* b,
+                   h2b_g1_affine* out, size_t n);
+int h2b_host_g1_op(int op, const h2b_g1_affine* a, const h2b_g1_affine* b, h2b_g1_affine* out,
+                   size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HALO2_B200_H */
