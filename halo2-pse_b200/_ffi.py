@@ -83,7 +83,7 @@ SYMBOLS = {
     "h2b_synth_scalars": (_I, [_P, _P, _SZ, _U64, _U32]),
     "h2b_synth_bases": (_I, [_P, _P, _SZ, _U64]),
     "h2b_synth_base_scalar": (_U64, [_U64, _U64]),
-    "h2b_imad_peak": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "h2b_pipe_peak": (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "h2b_test_field_op": (_I, [_P, _I, _I, _P, _P, _P, _SZ]),
     "h2b_host_field_op": (_I, [_I, _I, _P, _P, _P, _SZ]),
     "h2b_test_g1_op": (_I, [_P, _I, _P, _P, _P, _SZ]),

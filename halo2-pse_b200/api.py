@@ -241,11 +241,14 @@ class Context:
     def synth_base_scalar(self, seed: int, i: int) -> int:
         return int(self.lib.h2b_synth_base_scalar(seed, i))
 
-    def imad_peak(self) -> float:
+    PIPE_BENCH = {"imad": 0, "imad_hi": 1, "imad_wide": 2, "carry_chain": 3, "fr_mul": 4}
+
+    def pipe_peak(self, which: str = "imad_wide"):
+        """(32x32 multiplies/s, instructions-or-mulmods/s) of a register-only microbenchmark."""
         v = C.c_double()
         m = C.c_double()
-        self._check(self.lib.h2b_imad_peak(self.h, C.byref(v), C.byref(m)))
-        return v.value
+        self._check(self.lib.h2b_pipe_peak(self.h, self.PIPE_BENCH[which], C.byref(v), C.byref(m)))
+        return v.value, m.value
 
     # ---- the two reference entry points ----
     def best_multiexp(self, coeffs, bases):

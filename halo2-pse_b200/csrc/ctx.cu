@@ -97,39 +97,85 @@ __global__ void synth_bases_kernel(G1Affine* dst, uint64_t n, uint64_t seed) {
 }
 
 // ---------------------------------------------------------------------------
-// IMAD peak: independent 32x32+64 multiply-add chains, registers only
+// Integer-pipe peaks: register-only microbenchmarks (the roofline denominators
+// of the MSM / NTT kernels).  16 independent chains per thread, loop-invariant
+// multiplicands, nothing but the measured instruction in the loop body.
+//   which = 0  IMAD      (mad.lo.u32,   32x32 -> low 32  + 32)
+//           1  IMAD.HI   (mad.hi.u32,   32x32 -> high 32 + 32)
+//           2  IMAD.WIDE (mad.wide.u32, 32x32 -> 64      + 64)
+//           3  the carry-chain pattern of field.cuh (mad.lo.cc / madc.hi.cc, 8 per chain)
+//           4  Fr Montgomery multiplications (field.cuh mul), counted as 136 multiplies each
 // ---------------------------------------------------------------------------
-__global__ void imad_peak_kernel(uint32_t* sink, uint32_t iters, uint32_t a0, unsigned long long* cyc) {
-  uint32_t a = a0 + threadIdx.x;
-  uint64_t acc[8];
+template <int WHICH>
+__global__ void __launch_bounds__(256) pipe_peak_kernel(uint32_t* sink, uint32_t iters, uint32_t a0) {
+  uint32_t x = a0 | 1u, y = (a0 * 2654435761u) | 1u;
+  if (WHICH <= 2) {
+    uint64_t acc[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = threadIdx.x * 8 + j;
+    for (int j = 0; j < 16; ++j) acc[j] = ((uint64_t)threadIdx.x << 20) + j * 977u + a0;
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
 #ifdef __CUDA_ARCH__
-  const long long t0 = clock64();
-#endif
-  for (uint32_t it = 0; it < iters; ++it) {
-#pragma unroll
-    for (int rep = 0; rep < 8; ++rep) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-#ifdef __CUDA_ARCH__
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"((uint32_t)(acc[j] >> 7) | 1u));
+          uint32_t lo = (uint32_t)acc[j];
+          if (WHICH == 0) {
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(lo) : "r"(x), "r"(y));
+            acc[j] = lo;
+          } else if (WHICH == 1) {
+            asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(lo) : "r"(x), "r"(y));
+            acc[j] = lo;
+          } else {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(x), "r"(y));
+          }
 #else
-        acc[j] += (uint64_t)a * ((uint32_t)(acc[j] >> 7) | 1u);
+          acc[j] += (uint64_t)x * y;
 #endif
+        }
       }
     }
-  }
-#ifdef __CUDA_ARCH__
-  const long long t1 = clock64();
-  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = (unsigned long long)(t1 - t0);
-#else
-  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = 0;
-#endif
-  uint64_t s = 0;
+    uint64_t s = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s ^= acc[j];
-  if (s == 0x123456789abcdefull) sink[0] = (uint32_t)s;
+    for (int j = 0; j < 16; ++j) s ^= acc[j];
+    if (s == 0x123456789abcdefull) sink[0] = (uint32_t)s;
+  } else if (WHICH == 3) {
+    uint32_t c[2][9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) c[0][j] = c[1][j] = threadIdx.x + j + a0;
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int rep = 0; rep < 4; ++rep) {
+        chain_mad_top<false>(c[0][0], c[0][1], c[0][2], c[0][3], c[0][4], c[0][5], c[0][6], c[0][7],
+                             c[0][8], x, y, x + 2, y + 2, x + 4, 0u, 0u);
+        chain_mad_top<false>(c[1][0], c[1][1], c[1][2], c[1][3], c[1][4], c[1][5], c[1][6], c[1][7],
+                             c[1][8], y, x, y + 2, x + 2, y + 4, 0u, 0u);
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) s ^= c[0][j] ^ c[1][j];
+    if (s == 0x12345678u) sink[0] = s;
+  } else {
+    Fr a[2], b;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[0].v[j] = threadIdx.x + j + a0;
+      a[1].v[j] = threadIdx.x * 3 + j + a0;
+      b.v[j] = FrParams::one(j) ^ (a0 & 0xff);
+    }
+    a[0].v[7] &= 0x0fffffffu;
+    a[1].v[7] &= 0x0fffffffu;
+    b.v[7] &= 0x0fffffffu;
+    for (uint32_t it = 0; it < iters; ++it) {
+      a[0] = mul(a[0], b);
+      a[1] = mul(a[1], b);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s ^= a[0].v[j] ^ a[1].v[j];
+    if (s == 0x12345678u) sink[0] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -311,43 +357,49 @@ extern "C" int h2b_synth_bases(h2b_ctx* ctx, h2b_g1_affine* dst_dev, size_t n, u
 
 extern "C" uint64_t h2b_synth_base_scalar(uint64_t seed, uint64_t i) { return synth_base_scalar(seed, i); }
 
-extern "C" int h2b_imad_peak(h2b_ctx* ctx, double* imad_per_s, double* sm_mhz_effective) {
+extern "C" int h2b_pipe_peak(h2b_ctx* ctx, int which, double* mults_per_s, double* instr_per_s) {
   if (!ctx) return H2B_ERR_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (which < 0 || which > 4) return fail(ctx, H2B_ERR_ARG, "unknown pipe benchmark");
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
   uint32_t* sink;
-  unsigned long long* cyc;
   H2B_CUDA(ctx, cudaMalloc((void**)&sink, 64));
-  H2B_CUDA(ctx, cudaMalloc((void**)&cyc, 8));
   const uint32_t blocks = ctx->sm_count * 8, threads = 256;
 #ifdef H2B_EMU
-  const uint32_t iters = 4;
+  const uint32_t iters = 2;
 #else
-  const uint32_t iters = 4096;
+  const uint32_t iters = which == 4 ? 2048 : 8192;
 #endif
-  double best = 0, mhz = 0;
-  for (int rep = 0; rep < 5; ++rep) {
+  // instructions per thread per iteration, and 32x32 multiplies per instruction
+  const double per_iter = which <= 2 ? 64.0 : which == 3 ? 64.0 : 2.0;
+  const double mults_per = which == 4 ? 136.0 : 1.0;
+  double best = 0;
+  for (int rep = 0; rep < 6; ++rep) {
     H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    H2B_TRY(launch(ctx, imad_peak_kernel, dim3(blocks), dim3(threads), 0, sink, iters, 12345u + rep, cyc));
+    int rc = H2B_OK;
+    const uint32_t a0 = 12345u + rep;
+    switch (which) {
+      case 0: rc = launch(ctx, pipe_peak_kernel<0>, dim3(blocks), dim3(threads), 0, sink, iters, a0); break;
+      case 1: rc = launch(ctx, pipe_peak_kernel<1>, dim3(blocks), dim3(threads), 0, sink, iters, a0); break;
+      case 2: rc = launch(ctx, pipe_peak_kernel<2>, dim3(blocks), dim3(threads), 0, sink, iters, a0); break;
+      case 3: rc = launch(ctx, pipe_peak_kernel<3>, dim3(blocks), dim3(threads), 0, sink, iters, a0); break;
+      default: rc = launch(ctx, pipe_peak_kernel<4>, dim3(blocks), dim3(threads), 0, sink, iters, a0);
+    }
+    if (rc != H2B_OK) {
+      cudaFree(sink);
+      return rc;
+    }
     H2B_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     H2B_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
     float ms = 0;
     H2B_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-    unsigned long long c = 0;
-    H2B_CUDA(ctx, cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
-    const double ops = (double)blocks * threads * iters * 64.0;
-    const double rate = ms > 0 ? ops / (ms * 1e-3) : 0;
-    if (rate > best) {
-      best = rate;
-      // block 0 runs for about 1/8 of the launch (8 waves of blocks per SM share the SM)
-      mhz = 0;
-    }
-    (void)c;
+    const double instr = (double)blocks * threads * iters * per_iter;
+    const double rate = ms > 0 ? instr / (ms * 1e-3) : 0;
+    if (rate > best) best = rate;
   }
   cudaFree(sink);
-  cudaFree(cyc);
-  if (imad_per_s) *imad_per_s = best;
-  if (sm_mhz_effective) *sm_mhz_effective = mhz;
+  if (instr_per_s) *instr_per_s = best;
+  if (mults_per_s) *mults_per_s = best * mults_per;
   return H2B_OK;
 }
 

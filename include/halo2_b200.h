@@ -67,6 +67,7 @@ int h2b_bases_upload(h2b_ctx* ctx, const h2b_g1_affine* bases, size_t n, int loc
                      h2b_bases** out);
 void h2b_bases_free(h2b_bases* bases);
 size_t h2b_bases_len(const h2b_bases* bases);
+void* h2b_bases_device_ptr(const h2b_bases* bases);
 
 /* best_multiexp(coeffs, &bases[offset..offset+n])          arithmetic.rs:132
  * = ParamsKZG::commit_lagrange / commit with the matching base set
@@ -128,6 +129,9 @@ int h2b_extended_to_coeff_batch(h2b_domain* dom, const h2b_fr* in, size_t in_str
 /* ---- device helpers for callers that keep data resident ------------------ */
 int h2b_device_alloc(h2b_ctx* ctx, size_t bytes, void** out);
 void h2b_device_free(h2b_ctx* ctx, void* p);
+/* pinned (page-locked) host staging memory */
+int h2b_host_alloc(size_t bytes, void** out);
+void h2b_host_free(void* p);
 int h2b_copy_h2d(h2b_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int h2b_copy_d2h(h2b_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 
@@ -136,10 +140,20 @@ int h2b_copy_d2h(h2b_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes
  * distinct G1 points P_i = P_0 + i*D. */
 int h2b_synth_scalars(h2b_ctx* ctx, h2b_fr* dst_dev, size_t n, uint64_t seed, uint32_t kind);
 int h2b_synth_bases(h2b_ctx* ctx, h2b_g1_affine* dst_dev, size_t n, uint64_t seed);
+/* discrete log h_i of synthetic base i (P_i = [h_i] G): closed-form MSM checks */
+uint64_t h2b_synth_base_scalar(uint64_t seed, uint64_t i);
 
 /* ---- measurement / test hooks ------------------------------------------- */
-/* Register-only IMAD microbenchmark: returns achieved 32x32 multiply-adds/s. */
-int h2b_imad_peak(h2b_ctx* ctx, double* imad_per_s, double* sm_mhz_effective);
+/* Register-only integer-pipe microbenchmarks (the roofline denominators):
+ * which = 0 IMAD (mad.lo.u32), 1 IMAD.HI, 2 IMAD.WIDE (mad.wide.u32),
+ * 3 the mad.lo.cc/madc.hi.cc carry-chain pattern, 4 Fr Montgomery multiplications
+ * (counted as 136 32x32 multiplies each).  Returns 32x32 multiplies/s and
+ * instructions (or mulmods, for 4) per second, best of 6 launches. */
+int h2b_pipe_peak(h2b_ctx* ctx, int which, double* mults_per_s, double* instr_per_s);
+/* When on, MSM / NTT calls record CUDA events on the context's stream around
+ * their dominant kernel; h2b_ctx_last_kernel_ms returns that duration. */
+void h2b_ctx_set_profile(h2b_ctx* ctx, int on);
+float h2b_ctx_last_kernel_ms(const h2b_ctx* ctx);
 /* Element-wise device ops (op: 0 mul, 1 add, 2 sub, 3 sqr, 4 to_mont, 5 from_mont,
  * 6 neg, 7 inv); field: 0 Fr, 1 Fq.  Host pointers. */
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const h2b_fr* a, const h2b_fr* b,

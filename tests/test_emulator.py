@@ -1,0 +1,174 @@
+"""The product's .cu sources, compiled as C++ on the CPU fiber emulator
+(tests/emu/cuda_runtime.h, TEST INFRASTRUCTURE), checked against the oracle
+through the same C ABI and Python mirror the GPU tests use.  This validates the
+kernels' index arithmetic, tiling, carry-chain host twins and the host
+orchestration without a GPU; it is not a product code path.
+"""
+import random
+
+import numpy as np
+import pytest
+
+import halo2_pse_b200 as h
+from oracle import bn256 as O
+from tests import helpers as H
+
+KAT = H.load_golden("kat_bn256.json")["vectors"]
+
+
+def _np(hexs, width):
+    return np.frombuffer(bytes.fromhex(hexs), dtype=np.uint64).reshape(-1, width).copy()
+
+
+def test_host_field_ops_match_big_integers(emu_ctx):
+    rng = random.Random(1)
+    for field, mod in ((0, O.R_MOD), (1, O.Q_MOD)):
+        a = [rng.randrange(mod) for _ in range(200)] + [0, 1, mod - 1, mod - 1]
+        b = [rng.randrange(mod) for _ in range(200)] + [mod - 1, 0, mod - 1, 1]
+        A, B = H.to_limbs(a, mod), H.to_limbs(b, mod)
+        for op, f in ((0, lambda x, y: x * y % mod), (1, lambda x, y: (x + y) % mod),
+                      (2, lambda x, y: (x - y) % mod), (3, lambda x, y: x * x % mod),
+                      (6, lambda x, y: -x % mod)):
+            out = np.zeros_like(A)
+            assert emu_ctx.lib.h2b_host_field_op(field, op, A.ctypes.data, B.ctypes.data, out.ctypes.data, len(a)) == 0
+            assert H.from_limbs(out, mod) == [f(x, y) for x, y in zip(a, b)], (field, op)
+            out2 = np.zeros_like(A)
+            emu_ctx._check(emu_ctx.lib.h2b_test_field_op(emu_ctx.h, field, op, A.ctypes.data, B.ctypes.data,
+                                                         out2.ctypes.data, len(a)))
+            assert (out2 == out).all()
+
+
+def test_golden_best_fft(emu_ctx):
+    for v in KAT["best_fft"]:
+        a = _np(v["in"], 4)
+        emu_ctx.best_fft(a, _np(v["omega"], 4), v["log_n"])
+        assert a.tobytes().hex() == v["out"], v["log_n"]
+
+
+@pytest.mark.parametrize("k", [2, 5, 8, 9, 10, 12, 13, 14])
+def test_best_fft_vs_oracle(emu_ctx, oracle_c, k):
+    a = H.rand_fr_limbs(k, 1 << k)
+    w = H.fr_enc([O.omega_for(k)])[0]
+    want = oracle_c.best_fft(a, w, k)
+    got = a.copy()
+    emu_ctx.best_fft(got, w.reshape(1, 4), k)
+    assert (got == want).all()
+
+
+def test_best_fft_rejects_bad_input(emu_ctx):
+    a = H.rand_fr_limbs(0, 8)
+    with pytest.raises(h.H2BError) as e:  # assert_eq!(n, 1 << log_n)   arithmetic.rs:184
+        emu_ctx.best_fft(a, O.omega_for(4), 4)
+    assert e.value.code == h.H2B_ERR_LENGTH
+    with pytest.raises(h.H2BError) as e:  # omega of the wrong order
+        emu_ctx.best_fft(a, O.omega_for(4), 3)
+    assert e.value.code == h.H2B_ERR_BAD_OMEGA
+
+
+def test_golden_domain(emu_ctx):
+    for v in KAT["domain"]:
+        d = h.EvaluationDomain(emu_ctx, v["j"], v["k"])
+        assert d.extended_k == v["extended_k"]
+        assert H.fr_enc([d.constant("omega")]).tobytes().hex() == v["omega"]
+        assert H.fr_enc(d.t_evaluations()).tobytes().hex() == v["t_evaluations"]
+        assert d.lagrange_to_coeff(_np(v["a"], 4)).tobytes().hex() == v["lagrange_to_coeff"]
+        assert d.coeff_to_extended(_np(v["a"], 4)).tobytes().hex() == v["coeff_to_extended"]
+        assert d.divide_by_vanishing_poly(_np(v["ext"], 4)).tobytes().hex() == v["divide_by_vanishing_poly"]
+        assert d.extended_to_coeff(_np(v["ext"], 4)).tobytes().hex() == v["extended_to_coeff"]
+        fused = d.extended_to_coeff(_np(v["ext"], 4), divide_by_vanishing=True)
+        want = d.extended_to_coeff(_np(v["divide_by_vanishing_poly"], 4))
+        assert (fused == want).all()
+        d.free()
+
+
+def test_domain_length_checks(emu_ctx):
+    d = h.EvaluationDomain(emu_ctx, 5, 4)
+    for fn, n in ((d.lagrange_to_coeff, 8), (d.coeff_to_extended, 32), (d.extended_to_coeff, 16),
+                  (d.divide_by_vanishing_poly, 16)):
+        with pytest.raises(h.H2BError) as e:  # domain.rs:227,244,282,311
+            fn(H.rand_fr_limbs(0, n))
+        assert e.value.code == h.H2B_ERR_LENGTH
+    d.free()
+
+
+def test_batched_domain_transforms(emu_ctx, oracle_c):
+    j, k, ncols = 5, 7, 3
+    d = h.EvaluationDomain(emu_ctx, j, k)
+    od = oracle_c.domain(j, k, 2)
+    n, ne, nq = 1 << k, 1 << d.extended_k, d.quotient_len
+    cols = [H.rand_fr_limbs(100 + c, n) for c in range(ncols)]
+    stride = n + 5
+    buf = emu_ctx.alloc(ncols * stride * 32)
+    for c in range(ncols):
+        buf.upload(cols[c], c * stride * 32)
+    d.lagrange_to_coeff_device(buf, ncols, stride)
+    coeffs = [buf.download(n, c * stride * 32) for c in range(ncols)]
+    for c in range(ncols):
+        assert (coeffs[c] == od.lagrange_to_coeff(cols[c])).all()
+    ext = emu_ctx.alloc(ncols * ne * 32)
+    d.coeff_to_extended_device(buf, ext, ncols, stride, ne)
+    exts = [ext.download(ne, c * ne * 32) for c in range(ncols)]
+    for c in range(ncols):
+        assert (exts[c] == od.coeff_to_extended(coeffs[c])).all()
+    back = emu_ctx.alloc(ncols * nq * 32)
+    d.extended_to_coeff_device(ext, back, ncols, ne, nq, divide_by_vanishing=True)
+    for c in range(ncols):
+        want = od.extended_to_coeff(od.divide_by_vanishing_poly(exts[c]))
+        assert (back.download(nq, c * nq * 32) == want).all()
+    for b in (buf, ext, back):
+        b.free()
+    d.free()
+    od.free()
+
+
+def test_golden_best_multiexp(emu_ctx):
+    for v in KAT["best_multiexp"]:
+        got = emu_ctx.best_multiexp(_np(v["scalars"], 4), _np(v["bases"], 8))
+        assert O.g1_to_bytes(got).hex() == v["result"], v["name"]
+
+
+@pytest.mark.parametrize("n,kind", [(1, "uni"), (2, "uni"), (257, "uni"), (1500, "uni"), (1500, "eq"),
+                                    (1500, "01"), (1500, "small"), (700, "sparse")])
+def test_msm_vs_oracle(emu_ctx, oracle_c, n, kind):
+    rng = random.Random(n)
+    hs = [rng.randrange(1, 1 << 64) for _ in range(n)]
+    bases = oracle_c.g1_mul_gen(hs)
+    sc = {"uni": lambda: H.rand_fr(rng, n), "eq": lambda: [rng.randrange(O.R_MOD)] * n,
+          "01": lambda: [rng.randrange(2) for _ in range(n)],
+          "small": lambda: [rng.randrange(1 << 16) for _ in range(n)],
+          "sparse": lambda: [rng.randrange(O.R_MOD) if rng.random() < 0.1 else 0 for _ in range(n)]}[kind]()
+    S = H.fr_enc(sc)
+    B = h.Bases(emu_ctx, bases, n)
+    got = B.msm(S)
+    assert got == H.g1_dec(oracle_c.best_multiexp(S, bases, 4))[0]
+    assert got == O.g1_mul(O.G1_GEN, sum(c * x for c, x in zip(sc, hs)) % O.R_MOD)
+    assert B.msm(S, affine=False) == got  # Jacobian output of h2b_msm
+    if n > 10:  # prefix / offset forms used by commit on shorter polynomials
+        assert B.msm(S[:10], offset=3) == H.g1_dec(oracle_c.best_multiexp(S[:10], bases[3:13], 1))[0]
+    B.free()
+
+
+def test_msm_length_checks(emu_ctx, oracle_c):
+    bases = oracle_c.g1_mul_gen([1, 2, 3, 4])
+    B = h.Bases(emu_ctx, bases, 4)
+    with pytest.raises(h.H2BError) as e:  # assert!(bases.len() >= size)  kzg/commitment.rs:290
+        B.msm(H.rand_fr_limbs(0, 5))
+    assert e.value.code == h.H2B_ERR_LENGTH
+    with pytest.raises(h.H2BError) as e:  # assert_eq!(coeffs.len(), bases.len())  arithmetic.rs:133
+        emu_ctx.best_multiexp(H.rand_fr_limbs(0, 3), bases)
+    assert e.value.code == h.H2B_ERR_LENGTH
+    assert B.msm(np.zeros((0, 4), dtype=np.uint64)) is None  # empty input -> identity
+    B.free()
+
+
+def test_kzg_commit_identity(emu_ctx):
+    """kzg/commitment.rs:361-384 through the mirror: commit(lagrange_to_coeff(a)) == commit_lagrange(a)."""
+    v = KAT["kzg"]
+    P = h.ParamsKZG(emu_ctx, v["k"], _np(v["g"], 8), _np(v["g_lagrange"], 8))
+    d = h.EvaluationDomain(emu_ctx, 2, v["k"])
+    a = _np(v["lagrange"], 4)
+    coeff = d.lagrange_to_coeff(a)
+    assert coeff.tobytes().hex() == v["coeff"]
+    c1, c2 = P.commit(coeff), P.commit_lagrange(a)
+    assert c1 == c2 and O.g1_to_bytes(c1).hex() == v["commitment"]
+    d.free()
