@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the two hot paths at BASELINE.json's headline configuration:
+bn256 MSM (Mpts/s) and NTT (Melem/s) at k = 24, on 1/2/4/8 B200s of one node.
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+one best_multiexp over 2^24 uniformly random scalars (bases device-resident, as
+ParamsKZG keeps them) followed by one best_fft of 2^24 elements.  With N > 1 the
+MSM is the N*2^24-point MSM sharded by point range (per-rank partial points
+all-gathered and folded, arithmetic.rs:139-153) and the NTTs are independent
+columns, one per rank (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU
+algorithm (the C++ restatement under oracle/: the reference is Rust and cannot
+be compiled in this image) on the host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_LOG = 24
+METRIC = "bn256 MSM Mpts/s (and NTT Melem/s, key `ntt`) at k=24"
+SEED = 0x68616C6F32
+# algorithmic work of one bucket addition = 11 modular multiplications
+# (mixed Jacobian add, 7M+4S) of 136 32x32-bit multiplies each.
+MULMODS_PER_ADD = 11
+MULTS_PER_MULMOD = 136
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle/ref_cpu.cpp)
+# ---------------------------------------------------------------------------
+CPU_MSM_LOG, CPU_NTT_LOG = 20, 22
+
+
+def cpu_pass(oc, H, O, scalars, bases, ntt_in, omega, threads):
+    t0 = time.perf_counter()
+    oc.lib.oracle_best_multiexp(scalars.ctypes.data, bases.ctypes.data, scalars.shape[0], threads,
+                                _OUT.ctypes.data)
+    t1 = time.perf_counter()
+    oc.lib.oracle_best_fft(ntt_in.ctypes.data, omega.ctypes.data, CPU_NTT_LOG, threads)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+_OUT = None
+
+
+def cpu_setup():
+    global _OUT
+    import numpy as np
+    from oracle import bn256 as O
+    from tests import helpers as H
+    oc = H.load_oracle_c()
+    threads = host_threads()
+    _OUT = np.zeros(8, dtype=np.uint64)
+    bases = oc.synth_bases(1 << CPU_MSM_LOG, threads=threads)
+    scalars = H.rand_fr_limbs(SEED & 0xFFFF, 1 << CPU_MSM_LOG)
+    ntt_in = H.rand_fr_limbs(7, 1 << CPU_NTT_LOG)
+    omega = H.fr_enc([O.omega_for(CPU_NTT_LOG)])[0]
+    return oc, H, O, scalars, bases, ntt_in, omega, threads
+
+
+def cpu_baseline(steps: int = 1, warmup: int = 0):
+    oc, H, O, scalars, bases, ntt_in, omega, threads = cpu_setup()
+    for _ in range(warmup):
+        cpu_pass(oc, H, O, scalars, bases, ntt_in, omega, threads)
+    tm = tn = 0.0
+    for _ in range(steps):
+        a, b = cpu_pass(oc, H, O, scalars, bases, ntt_in, omega, threads)
+        tm += a
+        tn += b
+    sample = (f"oracle/ref_cpu.cpp (C++ restatement of arithmetic.rs, std::thread for rayon): best_multiexp on "
+              f"2^{CPU_MSM_LOG} points + best_fft at k={CPU_NTT_LOG}, {steps} pass(es), {threads} threads")
+    return {"value": (1 << CPU_MSM_LOG) * steps / tm / 1e6, "unit": "Mpts/s", "cores": threads, "kind": "port",
+            "sample": sample, "ntt": {"value": (1 << CPU_NTT_LOG) * steps / tn / 1e6, "unit": "Melem/s"},
+            "ms_per_pass": (tm + tn) / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_baseline(steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "Mpts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_pass"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic",
+        "config": {"workload": f"msm_k{K_LOG}+ntt_k{K_LOG}",
+                   "note": f"CPU arm times a bounded sample (MSM 2^{CPU_MSM_LOG}, NTT 2^{CPU_NTT_LOG}) of that workload"},
+        "ntt": base["ntt"],
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    import halo2_pse_b200 as h
+    from halo2_pse_b200 import dist as D
+
+    rank, world, local = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    ctx = h.Context(local)
+    k, n = K_LOG, 1 << K_LOG
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+
+    # ---- synthetic inputs, generated on the device ------------------------------
+    bases = ctx.synth_bases(n, 0x6B7A67 + rank)   # this rank's point range
+    scalars = ctx.synth_scalars(n, SEED + rank, 0)
+    poly = ctx.synth_scalars(n, SEED + 1000 + rank, 0)
+    dom = h.EvaluationDomain(ctx, 2, k)
+    omega = h.fr_encode([dom.constant("omega")])  # the primitive 2^k-th root every caller passes
+    msm = D.ShardedMSM(ctx, bases)
+    ctx.sync()
+
+    def step_device():
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e2 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        msm.msm(scalars, n)
+        e1.record(stream)
+        ctx.best_fft_device(poly, omega, k)
+        e2.record(stream)
+        return e0, e1, e2
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launches
+    evs = []
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        evs.append(step_device())
+    ctx.sync()
+    torch.cuda.synchronize()
+    t_msm = sum(a.elapsed_time(b) for a, b, _ in evs)
+    t_ntt = sum(b.elapsed_time(c) for _, b, c in evs)
+    t_all = evs[0][0].elapsed_time(evs[-1][2])
+    barrier()
+    t_wall = (time.perf_counter() - t_wall) * 1e3
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if sampler else None
+
+    def max_over_ranks(*vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=torch.device("cuda", local))
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return t.tolist()
+
+    t_msm, t_ntt, t_all = max_over_ranks(t_msm, t_ntt, t_all)
+
+    # ---- roofline of the dominant kernels (live, CUDA events on the library stream) ----
+    ctx.set_profile(True)
+    acc_ms, pass_ms = [], []
+    for _ in range(3):
+        msm.msm(scalars, n)
+        acc_ms.append(ctx.last_kernel_ms())
+        ctx.best_fft_device(poly, omega, k)
+        pass_ms.append(ctx.last_ntt_pass_ms())
+    ctx.set_profile(False)
+    acc_ms = sorted(acc_ms)[1]
+    pass_ms = [sorted(p[i] for p in pass_ms)[1] for i in range(len(pass_ms[0]))]
+    peaks, peak_src = measured_peaks()
+    c_win = int(ctx.lib.h2b_msm_window_bits(n))
+    windows = (255 + c_win - 1) // c_win
+    adds = n * windows
+    mults = adds * MULMODS_PER_ADD * MULTS_PER_MULMOD
+    pipe = {name: ctx.pipe_peak(name) for name in ("imad", "imad_wide", "fr_mul")}
+    mult_peak = max(pipe["imad"][0], pipe["imad_wide"][0])
+    roofline = {
+        "kernel": "msm_accum0_kernel (bucket accumulation, level 0)", "bound": "int32-multiply (IMAD pipe)",
+        "achieved": mults / (acc_ms * 1e-3) / 1e12, "peak": mult_peak / 1e12, "unit": "Tmul/s",
+        "frac": mults / (acc_ms * 1e-3) / mult_peak, "traffic": None,
+        "peak_source": "live register-only microbenchmark h2b_pipe_peak (max of IMAD and IMAD.WIDE rates)",
+        "algorithmic": f"n*W*{MULMODS_PER_ADD}*{MULTS_PER_MULMOD} 32x32 multiplies, n=2^{k}, c={c_win}, W={windows}",
+        "kernel_ms": acc_ms, "ec_adds_per_s": adds / (acc_ms * 1e-3),
+        "fr_mul_microbench_Tmul_s": pipe["fr_mul"][0] / 1e12,
+        "imad_Tmul_s": pipe["imad"][0] / 1e12, "imad_wide_Tmul_s": pipe["imad_wide"][0] / 1e12,
+    }
+    slow = max(pass_ms)
+    roofline_ntt = {
+        "kernel": "ntt_pass_fast<8> (one radix-256 pass over HBM)", "bound": "hbm",
+        "achieved": 64.0 * n / (slow * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": 64.0 * n / (slow * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+        "algorithmic": f"64 B per element per pass (one read + one write), n=2^{k}", "pass_ms": pass_ms,
+        "int_Tmul_s": (n / 2) * k * MULTS_PER_MULMOD / (sum(pass_ms) * 1e-3) / 1e12,
+    }
+
+    # ---- end to end through the C ABI with HOST buffers ---------------------------
+    h_sc = ctx.pinned((n, 4))
+    h_poly = ctx.pinned((n, 4))
+    ctx._check(ctx.lib.h2b_copy_d2h(ctx.h, C.c_void_p(h_sc.ptr.value), scalars.ptr, n * 32))
+    ctx._check(ctx.lib.h2b_copy_d2h(ctx.h, C.c_void_p(h_poly.ptr.value), poly.ptr, n * 32))
+    out = np.zeros(8, dtype=np.uint64)
+
+    def step_host():
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e2 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        msm.msm(h_sc.array)                    # H2D of the scalars inside, 64 B result back
+        e1.record(stream)
+        ctx.best_fft(h_poly.array, omega, k)   # H2D + in-place transform + D2H inside
+        e2.record(stream)
+        return e0, e1, e2
+
+    for _ in range(min(args.warmup, 2)):
+        step_host()
+    barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    evs = [step_host() for _ in range(e2e_steps)]
+    ctx.sync()
+    torch.cuda.synchronize()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    e_msm = sum(a.elapsed_time(b) for a, b, _ in evs)
+    e_ntt = sum(b.elapsed_time(c) for _, b, c in evs)
+    e_msm, e_ntt, e2e_wall = max_over_ranks(e_msm, e_ntt, e2e_wall)
+
+    # ---- four-step NTT with all-to-all (configs[4]) when sharded -------------------
+    four = None
+    if world > 1:
+        k4 = 26
+        loc = (1 << k4) // world
+        buf = torch.empty(loc * 4, dtype=torch.int64, device=torch.device("cuda", local))
+        ctx._check(ctx.lib.h2b_synth_scalars(ctx.h, C.c_void_p(buf.data_ptr()), loc, SEED + 77 + rank, 0))
+        fs = D.FourStepNTT(ctx, k4, h.EvaluationDomain(ctx, 2, k4).constant("omega"))
+        fs.run(buf)
+        barrier()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            fs.run(buf)
+            barrier()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        (best,) = max_over_ranks(min(ts))
+        four = {"k": k4, "ms": best, "melem_s": (1 << k4) / (best * 1e-3) / 1e6,
+                "method": "four-step, NCCL all-to-all transposes, wall clock max over ranks"}
+
+    if rank == 0:
+        total_pts = world * n * args.steps
+        line = {
+            "metric": METRIC, "value": total_pts / (t_msm * 1e-3) / 1e6, "unit": "Mpts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic",
+            "config": {"workload": f"msm_k{K_LOG}+ntt_k{K_LOG}", "points_per_gpu": n, "scalars": "uniform in [0, r)",
+                       "msm_window_bits": c_win, "sharding": "MSM by point range, NTT by column" if world > 1 else "none",
+                       "l2": "inputs (1.5 GiB MSM, 0.5 GiB NTT per step) exceed the 126 MB L2; no flush needed"},
+            "ntt": {"value": world * n * args.steps / (t_ntt * 1e-3) / 1e6, "unit": "Melem/s",
+                    "ms": t_ntt / args.steps},
+            "msm_ms": t_msm / args.steps, "wall_ms_per_step": t_wall / args.steps,
+            "roofline": roofline, "roofline_ntt": roofline_ntt,
+            "e2e": {"value": world * n * e2e_steps / (e_msm * 1e-3) / 1e6, "unit": "Mpts/s",
+                    "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 32 + 64,
+                    "ntt": {"value": world * n * e2e_steps / (e_ntt * 1e-3) / 1e6, "unit": "Melem/s"},
+                    "ms_per_step": e2e_wall / e2e_steps,
+                    "path": "h2b_msm_affine + h2b_best_fft with H2B_HOST pointers (pinned), copies inside the timed region"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if four:
+            line["four_step_ntt"] = four
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(steps=1)
+        print(json.dumps(line), flush=True)
+    barrier()
+    ctx.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,7 @@ SYMBOLS = {
     "h2b_ctx_launches": (_U64, [_P]),
     "h2b_ctx_set_profile": (None, [_P, _I]),
     "h2b_ctx_last_kernel_ms": (C.c_float, [_P]),
+    "h2b_ctx_last_ntt_passes": (_I, [_P, C.POINTER(C.c_float), _I]),
     "h2b_bases_upload": (_I, [_P, _P, _SZ, _I, C.POINTER(_P)]),
     "h2b_bases_free": (None, [_P]),
     "h2b_bases_len": (_SZ, [_P]),
@@ -59,6 +60,8 @@ SYMBOLS = {
     "h2b_msm": (_I, [_P, _P, _SZ, _P, _I, _SZ, _P]),
     "h2b_msm_affine": (_I, [_P, _P, _SZ, _P, _I, _SZ, _P]),
     "h2b_best_multiexp": (_I, [_P, _P, _P, _SZ, _P]),
+    "h2b_msm_window_bits": (_U32, [_SZ]),
+    "h2b_g1_sum": (_I, [_P, _SZ, _P]),
     "h2b_best_fft": (_I, [_P, _P, _I, _P, _U32]),
     "h2b_best_fft_batch": (_I, [_P, _P, _I, _P, _U32, _U32, _SZ]),
     "h2b_domain_new": (_I, [_P, _U32, _U32, C.POINTER(_P)]),
@@ -74,6 +77,9 @@ SYMBOLS = {
     "h2b_lagrange_to_coeff_batch": (_I, [_P, _P, _I, _U32, _SZ]),
     "h2b_coeff_to_extended_batch": (_I, [_P, _P, _SZ, _P, _SZ, _I, _U32]),
     "h2b_extended_to_coeff_batch": (_I, [_P, _P, _SZ, _P, _SZ, _I, _U32, _I]),
+    "h2b_fr_transpose_batch": (_I, [_P, _P, _P, _U32, _U32, _SZ, _U32, _SZ, _SZ]),
+    "h2b_fr_permute3": (_I, [_P, _P, _P, _U32, _U32, _U32]),
+    "h2b_fr_twiddle_rows": (_I, [_P, _P, _P, _U32, _U64, _U32, _U32]),
     "h2b_device_alloc": (_I, [_P, _SZ, C.POINTER(_P)]),
     "h2b_device_free": (None, [_P, _P]),
     "h2b_host_alloc": (_I, [_SZ, C.POINTER(_P)]),

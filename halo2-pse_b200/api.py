@@ -215,6 +215,18 @@ class Context:
     def stream(self) -> int:
         return int(self.lib.h2b_ctx_stream(self.h) or 0)
 
+    def set_profile(self, on: bool) -> None:
+        self.lib.h2b_ctx_set_profile(self.h, 1 if on else 0)
+
+    def last_kernel_ms(self) -> float:
+        """Duration of the dominant kernel of the last MSM call made in profile mode."""
+        return float(self.lib.h2b_ctx_last_kernel_ms(self.h))
+
+    def last_ntt_pass_ms(self) -> list:
+        buf = (C.c_float * 5)()
+        n = self.lib.h2b_ctx_last_ntt_passes(self.h, buf, 5)
+        return [float(buf[i]) for i in range(n)]
+
     def alloc(self, nbytes: int) -> DeviceBuffer:
         return DeviceBuffer(self, nbytes)
 

@@ -49,6 +49,10 @@ struct h2b_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_kernel_ms = 0.f;
   int profile = 0;
+  // per-pass timing of the last NTT call (profile mode): events around every pass launch
+  cudaEvent_t pass_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float last_pass_ms[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  int last_npass = 0;
   bool ntt_attr_done = false;
 };
 

@@ -255,6 +255,7 @@ extern "C" int h2b_ctx_create(int device, h2b_ctx** out) {
     return H2B_ERR_CUDA;
   }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->pass_ev[i]);
   *out = ctx;
   return H2B_OK;
 }
@@ -270,6 +271,8 @@ extern "C" void h2b_ctx_destroy(h2b_ctx* ctx) {
     if (ctx->stage[i]) cudaFree(ctx->stage[i]);
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 6; ++i)
+    if (ctx->pass_ev[i]) cudaEventDestroy(ctx->pass_ev[i]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -290,6 +293,18 @@ extern "C" void h2b_ctx_set_profile(h2b_ctx* ctx, int on) {
   if (ctx) ctx->profile = on;
 }
 extern "C" float h2b_ctx_last_kernel_ms(const h2b_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }
+extern "C" int h2b_ctx_last_ntt_passes(h2b_ctx* ctx, float* ms, int cap) {
+  if (!ctx || !ms) return 0;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
+  int n = 0;
+  for (; n < ctx->last_npass && n < cap; ++n) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ctx->pass_ev[n], ctx->pass_ev[n + 1]) != cudaSuccess) break;
+    ms[n] = t;
+  }
+  return n;
+}
 
 extern "C" int h2b_device_alloc(h2b_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return H2B_ERR_ARG;

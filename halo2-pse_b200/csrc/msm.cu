@@ -436,7 +436,6 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
                                 (size_t)p.W * p.nb_per_window * sizeof(G1Xyzz), st));
 
   // 3. level-wise accumulation; Nmax bounds the list size of each level
-  if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
   {
     uint64_t nmax = p.pairs;
     const uint32_t* keys = ws->keys_out;
@@ -455,6 +454,7 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
 #endif
       if (level == 0) {
         Level0Src src{ws->vals_out, d_bases};
+        if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
         H2B_TRY(launch(ctx, msm_accum0_kernel, dim3((nchunks + 127) / 128), dim3(128), 0, src, keys,
                        (const uint32_t*)(ws->n_level + level), L, (const uint32_t*)ws->cnt,
                        (const uint32_t*)ws->incl, nchunks, ws->n_level + level + 1, ws->lkeys[o],
@@ -549,6 +549,7 @@ extern "C" void h2b_bases_free(h2b_bases* b) {
   delete b;
 }
 
+extern "C" uint32_t h2b_msm_window_bits(size_t n) { return msm_plan(n).c; }
 extern "C" size_t h2b_bases_len(const h2b_bases* b) { return b ? b->n : 0; }
 extern "C" void* h2b_bases_device_ptr(const h2b_bases* b) { return b ? (void*)b->d_pts : nullptr; }
 
@@ -605,6 +606,22 @@ extern "C" int h2b_msm_affine(h2b_ctx* ctx, const h2b_bases* bases, size_t base_
   H2B_TRY(msm_common(ctx, bases, base_offset, scalars, loc, n, &acc));
   const G1Affine a = xyzz_to_affine(acc);
   memcpy(out_affine, &a, 64);
+  return H2B_OK;
+}
+
+// Sum of n affine points on the host: the fold of per-shard partial results
+// (arithmetic.rs:153 `results.iter().fold(identity, |a, b| a + b)`), used when
+// an MSM is sharded by point range across GPUs.
+extern "C" int h2b_g1_sum(const h2b_g1_affine* pts, size_t n, h2b_g1_affine* out) {
+  if ((!pts && n) || !out) return H2B_ERR_ARG;
+  G1Xyzz acc = G1Xyzz::identity();
+  for (size_t i = 0; i < n; ++i) {
+    G1Affine p;
+    memcpy(&p, pts + i, 64);
+    xyzz_add_affine(acc, p);
+  }
+  const G1Affine a = xyzz_to_affine(acc);
+  memcpy(out, &a, 64);
   return H2B_OK;
 }
 

@@ -306,6 +306,69 @@ __global__ void pow_table_kernel(Fr* tab, Fr base, uint32_t shift, uint32_t coun
 }
 
 // ---------------------------------------------------------------------------
+// Four-step helpers (single giant NTT sharded across GPUs; no counterpart in
+// the reference, SURVEY.md 2.2 "four-step transpose / twiddle")
+// ---------------------------------------------------------------------------
+// out[b][c][r] = in[b * in_bstride + r * in_rstride + c],  r < rows, c < cols
+__global__ void __launch_bounds__(256)
+    transpose_kernel(const Fr* in, Fr* out, uint32_t rows, uint32_t cols, uint64_t in_rstride,
+                     uint64_t in_bstride, uint64_t out_bstride) {
+  __shared__ uint32_t tile[8][32][33];  // limb planes, padded: conflict-free both ways
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const Fr* src = in + (uint64_t)blockIdx.z * in_bstride;
+  Fr* dst = out + (uint64_t)blockIdx.z * out_bstride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t r = r0 + ty + 8 * i, c = c0 + tx;
+    if (r < rows && c < cols) {
+      const Fr v = ld_fp(src + (uint64_t)r * in_rstride + c);
+#pragma unroll
+      for (int l = 0; l < 8; ++l) tile[l][ty + 8 * i][tx] = v.v[l];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t c = c0 + ty + 8 * i, r = r0 + tx;
+    if (r < rows && c < cols) {
+      Fr v;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) v.v[l] = tile[l][tx][ty + 8 * i];
+      st_fp(dst + (uint64_t)c * rows + r, v);
+    }
+  }
+}
+
+// out[b][a][c] = in[a][b][c]   (a < A, b < B, c < C; C-element runs stay contiguous)
+__global__ void permute3_kernel(const Fr* in, Fr* out, uint32_t A, uint32_t B, uint32_t C) {
+  const uint64_t total = (uint64_t)A * B * C;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = (uint32_t)(i % C);
+    const uint64_t ab = i / C;
+    const uint32_t a = (uint32_t)(ab % A), b = (uint32_t)(ab / A);  // i indexes out[b][a][c]
+    st_fp(out + i, ld_fp(in + ((uint64_t)a * B + b) * C + c));
+  }
+}
+
+// a[r][c] *= omega^((row0 + r) * c),  r < nrows, c < ncols; exponent < 2^tw.k
+__global__ void twiddle_rows_kernel(Fr* a, uint64_t row0, uint32_t nrows, uint32_t ncols,
+                                    const Fr* tw_lo, const Fr* tw_hi, uint32_t h) {
+  const uint64_t total = (uint64_t)nrows * ncols;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = row0 + i / ncols, c = i % ncols;
+    const uint64_t e = r * c;
+    if (e == 0) continue;
+    Fr x = ld_fp(a + i);
+    x = mul(x, ld_fp_nc(tw_lo + (uint32_t)(e & ((1ull << h) - 1))));
+    x = mul(x, ld_fp_nc(tw_hi + (uint32_t)(e >> h)));
+    st_fp(a + i, x);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
 static bool omega_has_order(const Fr& omega, uint32_t k) {
@@ -445,12 +508,18 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       p.lc = lc;
       const uint32_t tiles = (uint32_t)(n >> (p.s + lc));
       const dim3 grid(tiles, nb);
+      const bool prof = ctx->profile && b0 == 0 && pi < 5;
+      if (prof) H2B_CUDA(ctx, cudaEventRecord(ctx->pass_ev[pi], ctx->stream));
       if (fast) {
         if (p.s == 6) H2B_TRY(launch(ctx, ntt_pass_fast<6>, grid, dim3(256), 65536, p));
         if (p.s == 7) H2B_TRY(launch(ctx, ntt_pass_fast<7>, grid, dim3(256), 65536, p));
         if (p.s == 8) H2B_TRY(launch(ctx, ntt_pass_fast<8>, grid, dim3(256), 65536, p));
       } else {
         H2B_TRY(launch(ctx, ntt_pass_generic, grid, dim3(256), 65536, p));
+      }
+      if (prof) {
+        H2B_CUDA(ctx, cudaEventRecord(ctx->pass_ev[pi + 1], ctx->stream));
+        ctx->last_npass = pi + 1;
       }
       lm -= p.s;
     }
@@ -749,4 +818,50 @@ extern "C" int h2b_divide_by_vanishing_poly(h2b_domain* d, h2b_fr* a, int loc) {
   H2B_TRY(launch(ctx, scale_mod_kernel, dim3(blocks), dim3(256), 0, st.dev, (uint64_t)ne,
                  (const Fr*)d->d_t_inv, (uint32_t)d->t_evaluations.size()));
   return st.out(a, loc, ne);
+}
+
+// ---- four-step helpers (device pointers only) --------------------------------
+extern "C" int h2b_fr_transpose_batch(h2b_ctx* ctx, const h2b_fr* in, h2b_fr* out, uint32_t rows,
+                                      uint32_t cols, size_t in_row_stride, uint32_t nbatch,
+                                      size_t in_batch_stride, size_t out_batch_stride) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!in || !out || in == out) return fail(ctx, H2B_ERR_ARG, "null or aliased pointer");
+  if (in_row_stride < cols) return fail(ctx, H2B_ERR_LENGTH, "row stride < cols");
+  if (rows == 0 || cols == 0 || nbatch == 0) return H2B_OK;
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  return launch(ctx, transpose_kernel, dim3((cols + 31) / 32, (rows + 31) / 32, nbatch), dim3(256), 0,
+                as_fr(in), as_fr(out), rows, cols, (uint64_t)in_row_stride, (uint64_t)in_batch_stride,
+                (uint64_t)out_batch_stride);
+}
+
+extern "C" int h2b_fr_permute3(h2b_ctx* ctx, const h2b_fr* in, h2b_fr* out, uint32_t A, uint32_t B,
+                               uint32_t C) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!in || !out || in == out) return fail(ctx, H2B_ERR_ARG, "null or aliased pointer");
+  const uint64_t total = (uint64_t)A * B * C;
+  if (total == 0) return H2B_OK;
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint64_t want = (total + 255) / 256, cap = (uint64_t)ctx->sm_count * 16;
+  return launch(ctx, permute3_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0, as_fr(in),
+                as_fr(out), A, B, C);
+}
+
+extern "C" int h2b_fr_twiddle_rows(h2b_ctx* ctx, h2b_fr* a, const h2b_fr* omega, uint32_t log_n,
+                                   uint64_t row0, uint32_t nrows, uint32_t ncols) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!a || !omega) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (log_n > 28) return fail(ctx, H2B_ERR_ARG, "log_n > 28");
+  const uint64_t total = (uint64_t)nrows * ncols;
+  if (total == 0) return H2B_OK;
+  if ((row0 + nrows - 1) * (uint64_t)(ncols - 1) >= (1ull << log_n))
+    return fail(ctx, H2B_ERR_LENGTH, "twiddle exponent exceeds 2^log_n");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const TwTable* tw;
+  H2B_TRY(ntt_get_table(ctx, *as_fr(omega), log_n, &tw));
+  const uint64_t want = (total + 255) / 256, cap = (uint64_t)ctx->sm_count * 16;
+  return launch(ctx, twiddle_rows_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0, as_fr(a),
+                row0, nrows, ncols, (const Fr*)tw->d_lo, (const Fr*)tw->d_hi, tw->h);
 }

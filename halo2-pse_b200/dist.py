@@ -1,0 +1,207 @@
+"""Multi-GPU sharding of the two hot paths (one process per GPU, torch.distributed).
+
+The reference is single-process (rayon threads only); the
+analogue of its per-thread partitioning is kept where the path shards naturally:
+
+* MSM            -- contiguous point ranges per rank, exactly the chunking of
+                    `best_multiexp` (arithmetic.rs:135-153): each rank runs a full
+                    local Pippenger on its range, the per-rank partial points
+                    (64 B each) are all-gathered and folded.  No data-path collective.
+* column batches -- column c of a batch of independent transforms/commitments
+                    belongs to rank c % world.  No communication at all.
+* one giant NTT  -- four-step decomposition n = n1 * n2 over row-sharded
+                    matrices; the only real exchange step of the path is the
+                    transpose, an all-to-all (NCCL over NVLink on GPUs).
+
+Buffers that take part in a collective are torch tensors (int64 views of the Fr
+limbs) on the process group's device; the kernels run on them through the C ABI
+with H2B_DEVICE pointers.  With the test-suite's CPU emulator build and the
+gloo backend the same code runs on CPU tensors (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import H2B_DEVICE, H2BError
+from .api import Bases, Context, DeviceBuffer, fr_encode, g1_decode
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from torchrun's environment; initialises the
+    default process group when world_size > 1."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            if backend is None:
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+            if backend == "nccl":
+                torch.cuda.set_device(local)
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29511")
+            kw = {}
+            if backend == "nccl":
+                kw["device_id"] = torch.device("cuda", local)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous point range [start, end) of `rank`: ceil(n / world) points per rank,
+    the last ranks may be short or empty (the reference chunks the same way,
+    arithmetic.rs:135-145, with the remainder in a trailing chunk)."""
+    per = -(-n // world) if n else 0
+    start = min(n, rank * per)
+    return start, min(n, start + per)
+
+
+def column_owner(col: int, world: int) -> int:
+    return col % world
+
+
+def _group_device(group=None):
+    import torch
+    import torch.distributed as dist
+    be = dist.get_backend(group)
+    return torch.device("cuda", torch.cuda.current_device()) if be == "nccl" else torch.device("cpu")
+
+
+class ShardedMSM:
+    """best_multiexp over a point range sharded across ranks.
+
+    Each rank holds `bases` = its contiguous slice of the global base vector
+    (device-resident) and passes the matching slice of the scalars."""
+
+    def __init__(self, ctx: Context, bases: Bases, group=None):
+        self.ctx = ctx
+        self.bases = bases
+        self.group = group
+
+    def msm(self, scalars, n_local: Optional[int] = None):
+        """Returns the affine point sum over ALL ranks' ranges (same value on every rank)."""
+        import torch
+        import torch.distributed as dist
+        out = np.zeros(8, dtype=np.uint64)
+        if isinstance(scalars, DeviceBuffer):
+            sp, loc, n = scalars.ptr, H2B_DEVICE, n_local
+        else:
+            arr = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+            sp, loc, n = C.c_void_p(arr.ctypes.data), _ffi.H2B_HOST, arr.shape[0]
+        self.ctx._check(self.ctx.lib.h2b_msm_affine(self.ctx.h, self.bases.h, 0, sp, loc, n,
+                                                    C.c_void_p(out.ctypes.data)))
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return g1_decode(out)[0]
+        world = dist.get_world_size(self.group)
+        dev = _group_device(self.group)
+        mine = torch.from_numpy(out.view(np.int64)).to(dev)
+        parts = torch.empty(world * 8, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(parts, mine, group=self.group)
+        allp = np.ascontiguousarray(parts.cpu().numpy().view(np.uint64)).reshape(world, 8)
+        total = np.zeros(8, dtype=np.uint64)
+        rc = self.ctx.lib.h2b_g1_sum(C.c_void_p(allp.ctypes.data), world, C.c_void_p(total.ctypes.data))
+        if rc != 0:
+            raise H2BError(rc, "h2b_g1_sum")
+        return g1_decode(total)[0]
+
+
+class FourStepNTT:
+    """One 2^k-point best_fft whose vector is sharded in natural order across the
+    ranks of `group` (rank g holds elements [g*n/G, (g+1)*n/G)), natural order out.
+
+    n = n1 * n2 viewed as an n1 x n2 row-major matrix A[j1][j2]; with
+    K = K1 + n1*K2:
+        X[K] = sum_j2 w^(j2*K1) * ( sum_j1 A[j1][j2] * (w^n2)^(j1*K1) ) * (w^n1)^(j2*K2)
+    Steps (T = distributed transpose = local tile transposes + all-to-all + local permute):
+        T ; n1-point row NTTs ; twiddle w^(j2*K1) ; T ; n2-point row NTTs ; T
+    """
+
+    def __init__(self, ctx: Context, log_n: int, omega: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.ctx, self.k, self.group = ctx, log_n, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        G = self.world
+        if G & (G - 1):
+            raise H2BError(_ffi.H2B_ERR_ARG, "world size must be a power of two")
+        lg = G.bit_length() - 1
+        self.k1 = log_n // 2
+        self.k2 = log_n - self.k1
+        if self.k1 < lg or self.k2 < lg:
+            raise H2BError(_ffi.H2B_ERR_ARG, "transform too small to shard over this many ranks")
+        self.n1, self.n2 = 1 << self.k1, 1 << self.k2
+        self.omega = omega
+        from .api import R_MOD
+        self.w = fr_encode([omega])
+        self.w1 = fr_encode([pow(omega, self.n2, R_MOD)])  # order n1
+        self.w2 = fr_encode([pow(omega, self.n1, R_MOD)])  # order n2
+        self.dev = _group_device(group) if self.world > 1 else None
+        self.local = (1 << log_n) // G
+        self._bufs = None
+
+    # -- helpers ---------------------------------------------------------
+    def _p(self, t) -> C.c_void_p:
+        return C.c_void_p(t.data_ptr())
+
+    def _alloc(self, like):
+        return self.torch.empty_like(like)
+
+    def _sync_torch(self) -> None:
+        if self.dev is not None and self.dev.type == "cuda":
+            self.torch.cuda.current_stream().synchronize()
+
+    def _transpose(self, src, dst, tmp, R: int, Cn: int) -> None:
+        """Global R x Cn matrix sharded by rows (src: [R/G][Cn]) -> its transpose
+        sharded by rows (dst: [Cn/G][R]).  src is clobbered (it is the receive
+        buffer of the all-to-all); tmp is scratch of the same size."""
+        G, ctx = self.world, self.ctx
+        Rl, Cl = R // G, Cn // G
+        if G == 1:
+            ctx._check(ctx.lib.h2b_fr_transpose_batch(ctx.h, self._p(src), self._p(dst), Rl, Cl, Cn, 1, Cl,
+                                                      Cl * Rl))
+            return
+        # send[h][c][r] = src[r][h*Cl + c]: G tile transposes, one launch
+        ctx._check(ctx.lib.h2b_fr_transpose_batch(ctx.h, self._p(src), self._p(tmp), Rl, Cl, Cn, G, Cl,
+                                                  Cl * Rl))
+        ctx.sync()  # the library's stream is not the collective's stream
+        self.dist.all_to_all_single(src, tmp, group=self.group)
+        self._sync_torch()
+        # src now holds [g][c][r_g]; wanted [c][g][r_g]
+        ctx._check(ctx.lib.h2b_fr_permute3(ctx.h, self._p(src), self._p(dst), G, Cl, Rl))
+
+    def run(self, a):
+        """a: int64 tensor of 4 * n/G limbs words (this rank's natural-order slice), transformed
+        in place; returns `a`."""
+        ctx, G = self.ctx, self.world
+        n1, n2 = self.n1, self.n2
+        self.dev = a.device
+        t1, t2 = self._alloc(a), self._alloc(a)
+        self._sync_torch()
+        # A[j1][j2] rows sharded  ->  A^T[j2][j1]
+        self._transpose(a, t1, t2, n1, n2)
+        rows = n2 // G
+        ctx._check(ctx.lib.h2b_best_fft_batch(ctx.h, self._p(t1), H2B_DEVICE, C.c_void_p(self.w1.ctypes.data),
+                                              self.k1, rows, n1))
+        # B^T[j2][K1] *= w^(j2*K1)
+        ctx._check(ctx.lib.h2b_fr_twiddle_rows(ctx.h, self._p(t1), C.c_void_p(self.w.ctypes.data), self.k,
+                                               self.rank * rows, rows, n1))
+        # -> B[K1][j2]
+        self._transpose(t1, a, t2, n2, n1)
+        rows = n1 // G
+        ctx._check(ctx.lib.h2b_best_fft_batch(ctx.h, self._p(a), H2B_DEVICE, C.c_void_p(self.w2.ctypes.data),
+                                              self.k2, rows, n2))
+        # C[K1][K2] = X[K1 + n1*K2]  ->  natural order is the transpose [K2][K1]
+        self._transpose(a, t1, t2, n1, n2)
+        ctx.sync()
+        a.copy_(t1)
+        self._sync_torch()
+        return a

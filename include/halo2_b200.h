@@ -82,6 +82,13 @@ int h2b_msm_affine(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
 int h2b_best_multiexp(h2b_ctx* ctx, const h2b_fr* coeffs, const h2b_g1_affine* bases, size_t n,
                       h2b_g1* out);
 
+/* signed-digit window width c the Pippenger kernels use for an n-point MSM
+ * (ceil(255 / c) windows of 2^(c-1) buckets) */
+uint32_t h2b_msm_window_bits(size_t n);
+/* out = sum of n affine points, on the host: the fold of per-chunk partial sums
+ * (arithmetic.rs:153) when an MSM is sharded by point range across GPUs. */
+int h2b_g1_sum(const h2b_g1_affine* pts, size_t n, h2b_g1_affine* out);
+
 /* ---- NTT --------------------------------------------------------------- */
 /* best_fft(a, omega, log_n): in place, natural order in and out.  arithmetic.rs:171
  * omega must be a primitive 2^log_n-th root of unity (every non-bench caller
@@ -126,6 +133,19 @@ int h2b_extended_to_coeff_batch(h2b_domain* dom, const h2b_fr* in, size_t in_str
                                 size_t out_stride, int loc, uint32_t ncols,
                                 int divide_by_vanishing);
 
+/* Four-step pieces for ONE transform sharded over several GPUs (device pointers
+ * only; no counterpart in the reference, which is single-process).  The host
+ * side (halo2-pse_b200/dist.py) composes them with an all-to-all over NCCL:
+ *   transpose:  out[b][c][r] = in[b*in_batch_stride + r*in_row_stride + c]
+ *   permute3:   out[b][a][c] = in[a][b][c]
+ *   twiddle:    a[r][c] *= omega^((row0 + r) * c), omega of order 2^log_n */
+int h2b_fr_transpose_batch(h2b_ctx* ctx, const h2b_fr* in, h2b_fr* out, uint32_t rows, uint32_t cols,
+                           size_t in_row_stride, uint32_t nbatch, size_t in_batch_stride,
+                           size_t out_batch_stride);
+int h2b_fr_permute3(h2b_ctx* ctx, const h2b_fr* in, h2b_fr* out, uint32_t A, uint32_t B, uint32_t C);
+int h2b_fr_twiddle_rows(h2b_ctx* ctx, h2b_fr* a, const h2b_fr* omega, uint32_t log_n, uint64_t row0,
+                        uint32_t nrows, uint32_t ncols);
+
 /* ---- device helpers for callers that keep data resident ------------------ */
 int h2b_device_alloc(h2b_ctx* ctx, size_t bytes, void** out);
 void h2b_device_free(h2b_ctx* ctx, void* p);
@@ -137,7 +157,7 @@ int h2b_copy_d2h(h2b_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes
 
 /* Synthetic benchmark inputs, generated on device:
  * uniform Fr in Montgomery form from a counter-based generator; and n valid
- * distinct G1 points P_i = P_0 + i*D. */
+ * distinct G1 points P_i = [h_i] G with h_i = h2b_synth_base_scalar(seed, i). */
 int h2b_synth_scalars(h2b_ctx* ctx, h2b_fr* dst_dev, size_t n, uint64_t seed, uint32_t kind);
 int h2b_synth_bases(h2b_ctx* ctx, h2b_g1_affine* dst_dev, size_t n, uint64_t seed);
 /* discrete log h_i of synthetic base i (P_i = [h_i] G): closed-form MSM checks */
@@ -154,6 +174,8 @@ int h2b_pipe_peak(h2b_ctx* ctx, int which, double* mults_per_s, double* instr_pe
  * their dominant kernel; h2b_ctx_last_kernel_ms returns that duration. */
 void h2b_ctx_set_profile(h2b_ctx* ctx, int on);
 float h2b_ctx_last_kernel_ms(const h2b_ctx* ctx);
+/* durations (ms) of the passes of the last NTT call made in profile mode; returns their number */
+int h2b_ctx_last_ntt_passes(h2b_ctx* ctx, float* ms, int cap);
 /* Element-wise device ops (op: 0 mul, 1 add, 2 sub, 3 sqr, 4 to_mont, 5 from_mont,
  * 6 neg, 7 inv); field: 0 Fr, 1 Fq.  Host pointers. */
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const h2b_fr* a, const h2b_fr* b,

@@ -694,4 +694,45 @@ int oracle_g1_mul_gen_u64(const uint64_t* ks, size_t n, int threads, uint64_t* o
   return 0;
 }
 
+// Synthetic MSM bases for the CPU baseline: out[i] = [a + i*d] G (valid, distinct
+// points; an MSM's cost does not depend on the base values).  Each thread walks
+// its range with mixed additions and normalises with one batch inversion.
+int oracle_synth_bases(uint64_t a, uint64_t d, size_t n, int threads, uint64_t* out_affine) {
+  threads = clamp_threads(threads);
+  const Aff g{Fq::one(), fadd(Fq::one(), Fq::one())};
+  auto mul_u64 = [&](uint64_t k) {
+    Jac acc = Jac::identity();
+    for (int b = 63; b >= 0; --b) {
+      acc = jdouble(acc);
+      if ((k >> b) & 1) acc = jadd_mixed(acc, g);
+    }
+    return acc;
+  };
+  const Aff D = to_affine(mul_u64(d));
+  Aff* out = reinterpret_cast<Aff*>(out_affine);
+  parallelize(out, n, threads, [=](Aff* v, size_t len, size_t index) {
+    std::vector<Jac> pts(len);
+    Jac cur = mul_u64(a + d * index);
+    for (size_t i = 0; i < len; ++i) {
+      pts[i] = cur;
+      cur = jadd_mixed(cur, D);
+    }
+    // batch inversion of the z coordinates (none is zero: a + i*d < r for the sizes used)
+    std::vector<Fq> pre(len);
+    Fq run = Fq::one();
+    for (size_t i = 0; i < len; ++i) {
+      pre[i] = run;
+      run = fmul(run, pts[i].z);
+    }
+    Fq inv = finv(run);
+    for (size_t i = len; i-- > 0;) {
+      const Fq zi = fmul(inv, pre[i]);
+      inv = fmul(inv, pts[i].z);
+      const Fq zi2 = fsqr(zi);
+      v[i] = Aff{fmul(pts[i].x, zi2), fmul(pts[i].y, fmul(zi2, zi))};
+    }
+  });
+  return 0;
+}
+
 }  // extern "C"

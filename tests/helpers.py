@@ -46,6 +46,7 @@ class OracleC:
         lib.oracle_extended_to_coeff.argtypes = [P, P]
         lib.oracle_field_op.argtypes = [I, I, P, P, P, SZ]
         lib.oracle_g1_mul_gen_u64.argtypes = [P, SZ, I, P]
+        lib.oracle_synth_bases.argtypes = [C.c_uint64, C.c_uint64, SZ, I, P]
         self.lib = lib
 
     @staticmethod
@@ -78,6 +79,12 @@ class OracleC:
         k = np.ascontiguousarray(ks, dtype=np.uint64)
         out = np.zeros((k.shape[0], 8), dtype=np.uint64)
         self.lib.oracle_g1_mul_gen_u64(self._p(k), k.shape[0], threads, self._p(out))
+        return out
+
+    def synth_bases(self, n: int, a: int = 0x1234567, d: int = 0x9E3779B9, threads: int = 0) -> np.ndarray:
+        """out[i] = [a + i*d] G"""
+        out = np.zeros((n, 8), dtype=np.uint64)
+        self.lib.oracle_synth_bases(a, d, n, threads, self._p(out))
         return out
 
     def domain(self, j: int, k: int, threads: int = 0) -> "OracleCDomain":
