@@ -55,6 +55,8 @@ SYMBOLS = {
     "h2b_ctx_last_ntt_passes": (_I, [_P, C.POINTER(C.c_float), _I]),
     "h2b_bases_upload": (_I, [_P, _P, _SZ, _I, C.POINTER(_P)]),
     "h2b_bases_free": (None, [_P]),
+    "h2b_bases_precompute": (_I, [_P, _P, _U32]),
+    "h2b_bases_table_window_bits": (_U32, [_P]),
     "h2b_bases_len": (_SZ, [_P]),
     "h2b_bases_device_ptr": (_P, [_P]),
     "h2b_msm": (_I, [_P, _P, _SZ, _P, _I, _SZ, _P]),

@@ -310,6 +310,15 @@ class Bases:
     def __len__(self) -> int:
         return self.n
 
+    def precompute(self, window_bits: int = 0) -> "Bases":
+        """Build the window table (one-time; the bases of a ParamsKZG never change)."""
+        self.ctx._check(self.ctx.lib.h2b_bases_precompute(self.ctx.h, self.h, window_bits))
+        return self
+
+    @property
+    def table_window_bits(self) -> int:
+        return int(self.ctx.lib.h2b_bases_table_window_bits(self.h))
+
     def download(self) -> np.ndarray:
         out = np.empty((self.n, 8), dtype=np.uint64)
         p = self.ctx.lib.h2b_bases_device_ptr(self.h)

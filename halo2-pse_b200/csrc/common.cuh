@@ -60,6 +60,9 @@ struct h2b_bases {
   h2b_ctx* ctx;
   h2b::G1Affine* d_pts;
   size_t n;
+  // optional window table (h2b_bases_precompute): d_table[w * n + i] = 2^(pre_c * w) * d_pts[i]
+  h2b::G1Affine* d_table = nullptr;
+  uint32_t pre_c = 0, pre_W = 0;
 };
 
 struct h2b_domain {
@@ -175,7 +178,10 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t log_n, const TwTab
 void ntt_free_tables(h2b_ctx* ctx);
 
 // msm.cu
-int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, G1Xyzz* out_host);
+// table_stride == 0: classic per-window buckets over `d_points` (n points).
+// table_stride  > 0: `d_points` is a window table (w * table_stride + i), all windows share one bucket set.
+int msm_run(h2b_ctx* ctx, const G1Affine* d_points, const Fr* d_scalars, size_t n, G1Xyzz* out_host,
+            size_t table_stride = 0, uint32_t table_c = 0);
 void msm_ws_free(h2b_ctx* ctx);
 
 }  // namespace h2b

@@ -28,7 +28,10 @@
 #ifndef H2B_EMU
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 #endif
+#include <string.h>
 #include <algorithm>
 
 namespace h2b {
@@ -48,6 +51,14 @@ struct MsmWorkspace {
   G1Xyzz* buckets = nullptr;
   G1Xyzz* seg[2] = {nullptr, nullptr};  // tree-sum ping-pong
   G1Xyzz* h_out = nullptr;              // pinned, W window sums
+  // batched-affine accumulation (window-table MSMs)
+  size_t cap_aff = 0, cap_slots = 0;
+  uint32_t* akeys[2] = {nullptr, nullptr};
+  G1Affine* apts[2] = {nullptr, nullptr};
+  uint32_t* acnt = nullptr;   // inclusive count of merged pair slots
+  Fq* apre = nullptr;         // prefix products of the batched inversion
+  G1Affine* astage = nullptr;  // round-0 staging of one tile of gathered points
+  uint32_t* h_scalar = nullptr;  // pinned, device->host readbacks of list sizes
 };
 
 static void ws_release(MsmWorkspace* ws) {
@@ -65,6 +76,14 @@ static void ws_release(MsmWorkspace* ws) {
     cudaFree(ws->seg[i]);
   }
   cudaFree(ws->buckets);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(ws->akeys[i]);
+    cudaFree(ws->apts[i]);
+  }
+  cudaFree(ws->acnt);
+  cudaFree(ws->apre);
+  cudaFree(ws->astage);
+  if (ws->h_scalar) cudaFreeHost(ws->h_scalar);
   if (ws->h_out) cudaFreeHost(ws->h_out);
   *ws = MsmWorkspace();
 }
@@ -79,8 +98,9 @@ void msm_ws_free(h2b_ctx* ctx) {
 // ---------------------------------------------------------------------------
 // 1. digits
 // ---------------------------------------------------------------------------
+// table_stride > 0 (window table): key = |d| - 1 for every window, val = w * table_stride + i
 __global__ void msm_digits_kernel(const Fr* scalars, uint64_t n, uint32_t c, uint32_t W,
-                                  uint32_t* keys, uint32_t* vals) {
+                                  uint32_t* keys, uint32_t* vals, uint64_t table_stride) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
     const Fr s = from_mont(ld_fp(scalars + i));  // to_repr(), arithmetic.rs:14
@@ -104,8 +124,13 @@ __global__ void msm_digits_kernel(const Fr* scalars, uint64_t n, uint32_t c, uin
       } else {
         carry = 0;
       }
-      keys[(uint64_t)w * n + i] = d ? w * half + d - 1 : 0xffffffffu;
-      vals[(uint64_t)w * n + i] = (uint32_t)i | (negf << 31);
+      if (table_stride) {
+        keys[(uint64_t)w * n + i] = d ? d - 1 : 0xffffffffu;
+        vals[(uint64_t)w * n + i] = (uint32_t)(w * table_stride + i) | (negf << 31);
+      } else {
+        keys[(uint64_t)w * n + i] = d ? w * half + d - 1 : 0xffffffffu;
+        vals[(uint64_t)w * n + i] = (uint32_t)i | (negf << 31);
+      }
     }
   }
 }
@@ -246,6 +271,205 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---------------------------------------------------------------------------
+// 3'. batched-affine bucket accumulation (window-table MSMs)
+//
+// The sorted list is reduced by rounds of pairwise additions: in a round of
+// parity q the elements (2s+q, 2s+q+1) of pair slot s are added when they carry
+// the same key (= lie in the same bucket), everything else is copied through,
+// and the list is compacted (positions from a prefix count of the merged
+// slots).  Parities alternate so that every run of equal keys keeps halving
+// wherever it starts; the loop ends when neither parity merges anything, i.e.
+// every bucket is down to one point.  All additions of a round are independent
+// affine additions x3 = l^2 - x1 - x2, y3 = l (x1 - x3) - y1 with
+// l = (y2 - y1) / (x2 - x1): 2M + 1S plus 3M for the thread's batched inversion
+// (Montgomery's trick over the ~10^3 slots a thread owns, prefix products in
+// HBM) instead of the 8M + 2S of a mixed XYZZ addition.  P + P, P + (-P) and
+// identity operands are handled in-band (denominator 2y, or 1).
+// ---------------------------------------------------------------------------
+struct PairFlag {
+  const uint32_t* keys;
+  uint32_t n, parity;
+  H2B_HD uint32_t operator()(uint32_t s) const {
+    const uint64_t i = 2ull * s + parity;
+    return (i + 1 < n && keys[i] == keys[i + 1]) ? 1u : 0u;
+  }
+};
+
+struct PairSrc0 {  // round 0: points come from the window table through the sorted indices
+  const uint32_t* vals;
+  const G1Affine* table;
+  H2B_D Fq load_x(uint64_t i) const { return ld_fp_nc(&table[vals[i] & 0x7fffffffu].x); }
+  H2B_D G1Affine load(uint64_t i) const {
+    const uint32_t v = vals[i];
+    const G1Affine* src = table + (v & 0x7fffffffu);
+    G1Affine p;
+    p.x = ld_fp_nc(&src->x);
+    p.y = ld_fp_nc(&src->y);
+    if (v >> 31) p.y = neg(p.y);
+    return p;
+  }
+};
+
+struct PairSrcN {
+  const G1Affine* pts;
+  H2B_D Fq load_x(uint64_t i) const { return ld_fp(&pts[i].x); }
+  H2B_D G1Affine load(uint64_t i) const {
+    G1Affine p;
+    p.x = ld_fp(&pts[i].x);
+    p.y = ld_fp(&pts[i].y);
+    return p;
+  }
+};
+
+// kind: 0 chord (den = x2 - x1), 1 tangent (den = 2 y1), 2 result = p2, 3 result = p1, 4 result = identity
+H2B_D int pair_classify(const G1Affine& p1, const G1Affine& p2, Fq& den) {
+  den = Fq::one();
+  if (p1.is_identity()) return 2;
+  if (p2.is_identity()) return 3;
+  const Fq d = sub(p2.x, p1.x);
+  if (!d.is_zero()) {
+    den = d;
+    return 0;
+  }
+  if (p1.y == p2.y) {  // y != 0: the group has odd order
+    den = dbl(p1.y);
+    return 1;
+  }
+  return 4;
+}
+
+template <class Src>
+H2B_D Fq pair_den(const Src& src, uint64_t i) {
+  const Fq x1 = src.load_x(i), x2 = src.load_x(i + 1);
+  const Fq d = sub(x2, x1);
+  if (!d.is_zero() && !x1.is_zero() && !x2.is_zero()) return d;  // the common case needs no y
+  Fq den;
+  pair_classify(src.load(i), src.load(i + 1), den);
+  return den;
+}
+
+H2B_D void st_affine(G1Affine* dst, const G1Affine& p) {
+  st_fp(&dst->x, p.x);
+  st_fp(&dst->y, p.y);
+}
+
+// Slots [s0, s1) of one round.  With `stage` (round 0) pass 1 gathers every point
+// of the tile once from the window table and parks it in a sequential staging
+// buffer, so that the random HBM accesses are not repeated by pass 2.
+template <class Src>
+H2B_D void msm_pair_round_body(const Src& src, const uint32_t* keys, uint32_t n, uint32_t parity,
+                               uint32_t s0, uint32_t s1, const uint32_t* cnt_incl, Fq* pre,
+                               G1Affine* stage, uint32_t* okeys, G1Affine* opts) {
+  const uint32_t T = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+  const PairFlag flag{keys, n, parity};
+  if (t == 0 && s0 == 0 && parity == 1 && n > 0) {  // element 0 has no slot in an odd round
+    st_affine(opts, src.load(0));
+    okeys[0] = keys[0];
+  }
+  const uint32_t nloc = s1 - s0;
+  if (t >= nloc) return;
+  // pass 1: running product of the denominators of this thread's merged slots
+  Fq run = Fq::one();
+  bool any = false;
+  for (uint32_t j = t; j < nloc; j += T) {
+    const uint32_t s = s0 + j;
+    const uint64_t i = 2ull * s + parity;
+    const uint32_t f = flag(s);
+    Fq den;
+    if (stage) {
+      const G1Affine p1 = src.load(i);
+      st_affine(stage + 2ull * j, p1);
+      if (i + 1 < n) {
+        const G1Affine p2 = src.load(i + 1);
+        st_affine(stage + 2ull * j + 1, p2);
+        if (f) pair_classify(p1, p2, den);
+      }
+    } else if (f) {
+      den = pair_den(src, i);
+    }
+    if (!f) continue;
+    st_fp(pre + j, run);
+    run = mul(run, den);
+    any = true;
+  }
+  Fq inv_run = any ? inv(run) : run;
+  // pass 2, backwards: peel one inverse per slot, add, write to the compacted position
+  const PairSrcN staged{stage};
+  const uint32_t last = t + ((nloc - 1 - t) / T) * T;
+  for (int64_t j = last; j >= (int64_t)t; j -= T) {
+    const uint32_t s = s0 + (uint32_t)j;
+    const uint64_t i = 2ull * s + parity;
+    const uint32_t f = flag(s);
+    const uint64_t o = i - (cnt_incl[s] - f);
+    const G1Affine p1 = stage ? staged.load(2ull * j) : src.load(i);
+    if (!f) {
+      st_affine(opts + o, p1);
+      okeys[o] = keys[i];
+      if (i + 1 < n) {
+        st_affine(opts + o + 1, stage ? staged.load(2ull * j + 1) : src.load(i + 1));
+        okeys[o + 1] = keys[i + 1];
+      }
+      continue;
+    }
+    const G1Affine p2 = stage ? staged.load(2ull * j + 1) : src.load(i + 1);
+    Fq den;
+    const int kind = pair_classify(p1, p2, den);
+    const Fq inv_s = mul(inv_run, ld_fp(pre + j));
+    inv_run = mul(inv_run, den);
+    G1Affine r;
+    if (kind <= 1) {
+      Fq num;
+      if (kind == 0) {
+        num = sub(p2.y, p1.y);
+      } else {
+        const Fq xx = sqr(p1.x);
+        num = add(dbl(xx), xx);
+      }
+      const Fq lam = mul(num, inv_s);
+      r.x = sub(sub(sqr(lam), p1.x), p2.x);
+      r.y = sub(mul(lam, sub(p1.x, r.x)), p1.y);
+    } else if (kind == 2) {
+      r = p2;
+    } else if (kind == 3) {
+      r = p1;
+    } else {
+      r.x = Fq::zero();
+      r.y = Fq::zero();
+    }
+    st_affine(opts + o, r);
+    okeys[o] = keys[i];
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    msm_pair_round0_kernel(PairSrc0 src, const uint32_t* keys, uint32_t n, uint32_t parity, uint32_t s0,
+                           uint32_t s1, const uint32_t* cnt_incl, Fq* pre, G1Affine* stage,
+                           uint32_t* okeys, G1Affine* opts) {
+  msm_pair_round_body(src, keys, n, parity, s0, s1, cnt_incl, pre, stage, okeys, opts);
+}
+
+__global__ void __launch_bounds__(128)
+    msm_pair_roundN_kernel(PairSrcN src, const uint32_t* keys, uint32_t n, uint32_t parity, uint32_t s0,
+                           uint32_t s1, const uint32_t* cnt_incl, Fq* pre, G1Affine* stage,
+                           uint32_t* okeys, G1Affine* opts) {
+  msm_pair_round_body(src, keys, n, parity, s0, s1, cnt_incl, pre, stage, okeys, opts);
+}
+
+// one point per bucket left: write the dense bucket array
+template <class Src>
+H2B_D void msm_scatter_body(const Src& src, const uint32_t* keys, uint32_t n, G1Xyzz* buckets) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    st_xyzz(buckets + keys[i], G1Xyzz::from_affine(src.load(i)));
+}
+__global__ void msm_scatter0_kernel(PairSrc0 src, const uint32_t* keys, uint32_t n, G1Xyzz* buckets) {
+  msm_scatter_body(src, keys, n, buckets);
+}
+__global__ void msm_scatterN_kernel(PairSrcN src, const uint32_t* keys, uint32_t n, G1Xyzz* buckets) {
+  msm_scatter_body(src, keys, n, buckets);
+}
+
+// ---------------------------------------------------------------------------
 // 4. bucket reduction
 // ---------------------------------------------------------------------------
 H2B_D G1Xyzz ld_xyzz(const G1Xyzz* p) {
@@ -320,12 +544,12 @@ static uint32_t ceil_log2(uint64_t x) {
 }
 
 struct MsmPlan {
-  uint32_t c, W, kb, L0, LN, lM;
+  uint32_t c, W, Wb, kb, L0, LN, lM;  // Wb: number of bucket sets (W, or 1 with a window table)
   uint64_t pairs;
   uint32_t nb_per_window, nseg;
 };
 
-static MsmPlan msm_plan(size_t n) {
+static MsmPlan msm_plan(size_t n, uint32_t table_c = 0) {
   MsmPlan p;
   const uint32_t k = ceil_log2(n < 2 ? 2 : n);
   int c = (int)k - 4;
@@ -335,10 +559,12 @@ static MsmPlan msm_plan(size_t n) {
     const int v = atoi(e);
     if (v >= 2 && v <= 24) c = v;
   }
+  if (table_c) c = (int)table_c;
   p.c = (uint32_t)c;
   p.W = (255 + p.c - 1) / p.c;
+  p.Wb = table_c ? 1 : p.W;
   p.nb_per_window = 1u << (p.c - 1);
-  p.kb = ceil_log2((uint64_t)p.W * p.nb_per_window);
+  p.kb = ceil_log2((uint64_t)p.Wb * p.nb_per_window);
   p.pairs = (uint64_t)n * p.W;
   p.L0 = p.pairs >= (1ull << 24) ? 64 : 32;
   if (const char* e = getenv("H2B_MSM_L0")) {
@@ -356,8 +582,8 @@ static int ws_ensure(h2b_ctx* ctx, const MsmPlan& p) {
   MsmWorkspace* ws = ctx->msm_ws;
   const size_t chunks0 = (size_t)((p.pairs + p.L0 - 1) / p.L0);
   const size_t list = 2 * chunks0 + 16;
-  const size_t nbuckets = (size_t)p.W * p.nb_per_window;
-  const size_t nsegs = (size_t)p.W * p.nseg;
+  const size_t nbuckets = (size_t)p.Wb * p.nb_per_window;
+  const size_t nsegs = (size_t)p.Wb * p.nseg;
   if (p.pairs <= ws->cap_pairs && chunks0 <= ws->cap_chunks && list <= ws->cap_list &&
       nbuckets <= ws->cap_buckets && nsegs <= ws->cap_seg)
     return H2B_OK;
@@ -380,8 +606,9 @@ static int ws_ensure(h2b_ctx* ctx, const MsmPlan& p) {
 #ifndef H2B_EMU
   size_t t1 = 0, t2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, t1, ws->keys_in, ws->keys_out, ws->vals_in,
-                                  ws->vals_out, p.pairs, 0, (int)p.kb + 1, ctx->stream);
-  cub::DeviceScan::InclusiveSum(nullptr, t2, ws->cnt, ws->incl, (int)chunks0, ctx->stream);
+                                  ws->vals_out, p.pairs, 0, 32, ctx->stream);  // worst case: any key width
+  cub::DeviceScan::InclusiveSum(nullptr, t2, ws->cnt, ws->incl,
+                                (int)std::max<size_t>(chunks0, (size_t)(p.pairs / 2) + 2), ctx->stream);
   ws->cub_temp_bytes = std::max(t1, t2) + 256;
   H2B_CUDA(ctx, cudaMalloc(&ws->cub_temp, ws->cub_temp_bytes));
 #endif
@@ -393,12 +620,139 @@ static int ws_ensure(h2b_ctx* ctx, const MsmPlan& p) {
   return H2B_OK;
 }
 
+// pair slots per round-0 launch (2^25 slots = 4 GiB of staging); H2B_MSM_TILE overrides (tests)
+static size_t stage_tile() {
+  if (const char* e = getenv("H2B_MSM_TILE")) {
+    const long v = atol(e);
+    if (v >= 1) return (size_t)v;
+  }
+  return (size_t)1 << 25;
+}
+
+// Batched-affine accumulation of the sorted (key, index) list into ws->buckets.
+static int accumulate_affine(h2b_ctx* ctx, MsmWorkspace* ws, const MsmPlan& p, const G1Affine* d_table) {
+  cudaStream_t st = ctx->stream;
+  (void)st;
+  // capacities: after the first round a list holds at most N0/2 + #buckets elements
+  const size_t nbuckets = (size_t)p.Wb * p.nb_per_window;
+  const size_t cap = (size_t)(p.pairs / 2) + nbuckets + 16;
+  const size_t slots = (size_t)(p.pairs / 2) + 2;
+  const size_t kStageTile = stage_tile();
+  if (cap > ws->cap_aff || slots > ws->cap_slots) {
+    H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(ws->akeys[i]);
+      cudaFree(ws->apts[i]);
+      ws->akeys[i] = nullptr;
+      ws->apts[i] = nullptr;
+    }
+    cudaFree(ws->acnt);
+    cudaFree(ws->apre);
+    cudaFree(ws->astage);
+    ws->acnt = nullptr;
+    ws->apre = nullptr;
+    ws->astage = nullptr;
+    ws->cap_aff = ws->cap_slots = 0;
+    for (int i = 0; i < 2; ++i) {
+      H2B_CUDA(ctx, cudaMalloc((void**)&ws->akeys[i], cap * 4));
+      H2B_CUDA(ctx, cudaMalloc((void**)&ws->apts[i], cap * sizeof(G1Affine)));
+    }
+    H2B_CUDA(ctx, cudaMalloc((void**)&ws->acnt, slots * 4));
+    H2B_CUDA(ctx, cudaMalloc((void**)&ws->apre, slots * sizeof(Fq)));
+    H2B_CUDA(ctx, cudaMalloc((void**)&ws->astage,
+                             2 * std::min<size_t>(slots, kStageTile) * sizeof(G1Affine)));
+    if (!ws->h_scalar) H2B_CUDA(ctx, cudaMallocHost((void**)&ws->h_scalar, 64));
+    ws->cap_aff = cap;
+    ws->cap_slots = slots;
+  }
+  auto read_u32 = [&](const uint32_t* d, uint32_t* out) -> int {
+    H2B_CUDA(ctx, cudaMemcpyAsync(ws->h_scalar, d, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = ws->h_scalar[0];
+    return H2B_OK;
+  };
+  uint32_t N = 0;
+  H2B_TRY(read_u32(ws->n_level, &N));  // number of non-zero digits
+  const uint32_t* keys = ws->keys_out;
+  int cur = -1;  // -1: the list still lives in (keys_out, vals_out); else index into akeys / apts
+  uint32_t parity = 0;
+  int idle = 0, round = 0;
+  const uint32_t max_blocks = (uint32_t)ctx->sm_count * 4;
+  while (N > 1) {
+    const uint32_t nslots = N > parity ? (N - parity + 1) / 2 : 0;
+    uint32_t merged = 0;
+    if (nslots) {
+      const PairFlag flag{keys, N, parity};
+#ifdef H2B_EMU
+      uint32_t acc = 0;
+      for (uint32_t s = 0; s < nslots; ++s) {
+        acc += flag(s);
+        ws->acnt[s] = acc;
+      }
+#else
+      cub::TransformInputIterator<uint32_t, PairFlag, cub::CountingInputIterator<uint32_t>> it(
+          cub::CountingInputIterator<uint32_t>(0), flag);
+      H2B_CUDA(ctx, cub::DeviceScan::InclusiveSum(ws->cub_temp, ws->cub_temp_bytes, it, ws->acnt,
+                                                  (int)nslots, st));
+      ctx->launches += 2;
+#endif
+      H2B_TRY(read_u32(ws->acnt + (nslots - 1), &merged));
+    }
+    if (merged == 0) {
+      if (++idle == 2) break;
+      parity ^= 1;
+      continue;
+    }
+    idle = 0;
+    const int o = cur < 0 ? 0 : cur ^ 1;
+    auto nblocks = [&](uint32_t cnt) {
+      uint32_t b = (cnt + 256 * 128 - 1) / (256 * 128);
+      return b > max_blocks ? max_blocks : (b < 1 ? 1u : b);
+    };
+    if (cur < 0) {
+      const PairSrc0 src{ws->vals_out, d_table};
+      if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+      for (uint64_t s0 = 0; s0 < nslots; s0 += kStageTile) {
+        const uint32_t s1 = (uint32_t)std::min<uint64_t>(nslots, s0 + kStageTile);
+        H2B_TRY(launch(ctx, msm_pair_round0_kernel, dim3(nblocks(s1 - (uint32_t)s0)), dim3(128), 0, src, keys,
+                       N, parity, (uint32_t)s0, s1, (const uint32_t*)ws->acnt, ws->apre, ws->astage,
+                       ws->akeys[o], ws->apts[o]));
+      }
+      if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    } else {
+      const PairSrcN src{ws->apts[cur]};
+      H2B_TRY(launch(ctx, msm_pair_roundN_kernel, dim3(nblocks(nslots)), dim3(128), 0, src, keys, N, parity,
+                     0u, nslots, (const uint32_t*)ws->acnt, ws->apre, (G1Affine*)nullptr, ws->akeys[o],
+                     ws->apts[o]));
+    }
+    N -= merged;
+    cur = o;
+    keys = ws->akeys[o];
+    parity ^= 1;
+    if (++round > 200) return fail(ctx, H2B_ERR_ARG, "batched-affine accumulation did not converge");
+  }
+  if (N) {
+    uint32_t blocks = (N + 255) / 256;
+    if (blocks > max_blocks * 4) blocks = max_blocks * 4;
+    if (cur < 0) {
+      const PairSrc0 src{ws->vals_out, d_table};
+      H2B_TRY(launch(ctx, msm_scatter0_kernel, dim3(blocks), dim3(256), 0, src, keys, N, ws->buckets));
+    } else {
+      const PairSrcN src{ws->apts[cur]};
+      H2B_TRY(launch(ctx, msm_scatterN_kernel, dim3(blocks), dim3(256), 0, src, keys, N, ws->buckets));
+    }
+  }
+  return H2B_OK;
+}
+
 int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n,
-            G1Xyzz* out_host) {
+            G1Xyzz* out_host, size_t table_stride, uint32_t table_c) {
   *out_host = G1Xyzz::identity();
   if (n == 0) return H2B_OK;
   if (n >= (1ull << 31)) return fail(ctx, H2B_ERR_ARG, "MSM larger than 2^31 points");
-  const MsmPlan p = msm_plan(n);
+  const MsmPlan p = msm_plan(n, table_stride ? table_c : 0);
+  if (table_stride && (uint64_t)p.W * table_stride >= (1ull << 31))
+    return fail(ctx, H2B_ERR_ARG, "window table larger than 2^31 points");
   H2B_TRY(ws_ensure(ctx, p));
   MsmWorkspace* ws = ctx->msm_ws;
   cudaStream_t st = ctx->stream;
@@ -409,7 +763,7 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
     const uint64_t want = (n + 255) / 256;
     const uint64_t cap = (uint64_t)ctx->sm_count * 16;
     H2B_TRY(launch(ctx, msm_digits_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0,
-                   d_scalars, (uint64_t)n, p.c, p.W, ws->keys_in, ws->vals_in));
+                   d_scalars, (uint64_t)n, p.c, p.W, ws->keys_in, ws->vals_in, (uint64_t)table_stride));
   }
   // 2. sort
 #ifdef H2B_EMU
@@ -433,10 +787,14 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   H2B_TRY(launch(ctx, msm_find_valid_kernel, dim3(1), dim3(32), 0, (const uint32_t*)ws->keys_out,
                  (uint64_t)p.pairs, p.kb, ws->n_level));
   H2B_CUDA(ctx, cudaMemsetAsync(ws->buckets, 0,
-                                (size_t)p.W * p.nb_per_window * sizeof(G1Xyzz), st));
+                                (size_t)p.Wb * p.nb_per_window * sizeof(G1Xyzz), st));
 
-  // 3. level-wise accumulation; Nmax bounds the list size of each level
-  {
+  // 3. bucket accumulation: batched affine on a window table, else level-wise XYZZ chunks
+  bool affine = table_stride != 0;
+  if (const char* e = getenv("H2B_MSM_ACC")) affine = affine && strcmp(e, "xyzz") != 0;
+  if (affine) {
+    H2B_TRY(accumulate_affine(ctx, ws, p, d_bases));
+  } else {
     uint64_t nmax = p.pairs;
     const uint32_t* keys = ws->keys_out;
     for (int level = 0; level < kMaxLevels; ++level) {
@@ -476,19 +834,19 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
 
   // 4. bucket reduction
   {
-    const uint32_t total = p.W * p.nseg;
+    const uint32_t total = p.Wb * p.nseg;
     H2B_TRY(launch(ctx, msm_bucket_seg_kernel, dim3((total + 127) / 128), dim3(128), 0,
                    (const G1Xyzz*)ws->buckets, p.nb_per_window, p.lM, p.nseg, total, ws->seg[0]));
     uint32_t nin = p.nseg;
     int cur = 0;
     while (nin > 1) {
       const uint32_t nout = (nin + 255) / 256;
-      H2B_TRY(launch(ctx, msm_tree_sum_kernel, dim3(nout, p.W), dim3(256), 256 * sizeof(G1Xyzz),
+      H2B_TRY(launch(ctx, msm_tree_sum_kernel, dim3(nout, p.Wb), dim3(256), 256 * sizeof(G1Xyzz),
                      (const G1Xyzz*)ws->seg[cur], nin, nout, ws->seg[cur ^ 1]));
       cur ^= 1;
       nin = nout;
     }
-    H2B_CUDA(ctx, cudaMemcpyAsync(ws->h_out, ws->seg[cur], p.W * sizeof(G1Xyzz),
+    H2B_CUDA(ctx, cudaMemcpyAsync(ws->h_out, ws->seg[cur], p.Wb * sizeof(G1Xyzz),
                                   cudaMemcpyDeviceToHost, st));
   }
   H2B_CUDA(ctx, cudaStreamSynchronize(st));
@@ -499,12 +857,67 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
 
   // 5. combine windows, top first: acc = 2^c * acc + R_w   (arithmetic.rs:46-49)
   G1Xyzz acc = G1Xyzz::identity();
-  for (int w = (int)p.W - 1; w >= 0; --w) {
-    for (uint32_t i = 0; i < p.c; ++i) acc = xyzz_double(acc);
-    xyzz_add(acc, ws->h_out[w]);
+  if (table_stride) {
+    acc = ws->h_out[0];  // the table already carries the 2^(c*w) factors
+  } else {
+    for (int w = (int)p.W - 1; w >= 0; --w) {
+      for (uint32_t i = 0; i < p.c; ++i) acc = xyzz_double(acc);
+      xyzz_add(acc, ws->h_out[w]);
+    }
   }
   *out_host = acc;
   return H2B_OK;
+}
+
+// ---------------------------------------------------------------------------
+// window table: T_w[i] = 2^(c*w) * P_i, affine            (h2b_bases_precompute)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    msm_table_double_kernel(const G1Affine* src, G1Xyzz* dst, uint64_t n, uint32_t c) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p;
+  p.x = ld_fp(&src[i].x);
+  p.y = ld_fp(&src[i].y);
+  G1Xyzz acc = G1Xyzz::identity();
+  if (!p.is_identity()) {
+    acc = xyzz_double_affine(p);
+    for (uint32_t j = 1; j < c; ++j) acc = xyzz_double(acc);
+  }
+  st_xyzz(dst + i, acc);
+}
+
+// XYZZ -> affine with one inversion per thread (Montgomery's trick over kBatch points)
+static const int kNormBatch = 16;
+__global__ void __launch_bounds__(128)
+    msm_table_normalize_kernel(const G1Xyzz* src, G1Affine* dst, uint64_t n) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t i0 = t * kNormBatch;
+  if (i0 >= n) return;
+  const int cnt = (int)(n - i0 < (uint64_t)kNormBatch ? n - i0 : (uint64_t)kNormBatch);
+  Fq pre[kNormBatch];
+  Fq run = Fq::one();
+  for (int j = 0; j < cnt; ++j) {
+    pre[j] = run;
+    const Fq z = ld_fp(&src[i0 + j].zzz);
+    if (!z.is_zero()) run = mul(run, z);
+  }
+  Fq invr = inv(run);
+  for (int j = cnt - 1; j >= 0; --j) {
+    const G1Xyzz p = ld_xyzz(src + i0 + j);
+    G1Affine a;
+    a.x = Fq::zero();
+    a.y = Fq::zero();
+    if (!p.zzz.is_zero()) {
+      const Fq izzz = mul(invr, pre[j]);
+      invr = mul(invr, p.zzz);
+      const Fq izz = sqr(mul(p.zz, izzz));  // zz^2 / zzz^2 = 1 / zz
+      a.x = mul(p.x, izz);
+      a.y = mul(p.y, izzz);
+    }
+    st_fp(&dst[i0 + j].x, a.x);
+    st_fp(&dst[i0 + j].y, a.y);
+  }
 }
 
 }  // namespace h2b
@@ -546,10 +959,68 @@ extern "C" void h2b_bases_free(h2b_bases* b) {
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
   cudaFree(b->d_pts);
+  if (b->d_table) cudaFree(b->d_table);
   delete b;
 }
 
+// Builds the window table of a base set (one-time, at upload: the bases of a
+// ParamsKZG are immutable).  window_bits = 0 picks the width from n.
+extern "C" int h2b_bases_precompute(h2b_ctx* ctx, h2b_bases* b, uint32_t window_bits) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!b || b->ctx != ctx) return fail(ctx, H2B_ERR_ARG, "bases belong to another context");
+  if (b->n == 0) return H2B_OK;
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint32_t c = window_bits;
+  if (c == 0) {
+    const uint32_t k = ceil_log2(b->n < 2 ? 2 : b->n);
+    c = k < 10 ? 8 : (k - 2 > 24 ? 24 : k - 2);
+    if (k >= 22 && k <= 25) c = 22;
+  }
+  if (c < 2 || c > 24) return fail(ctx, H2B_ERR_ARG, "window_bits out of range");
+  const uint32_t W = (255 + c - 1) / c;
+  if ((uint64_t)W * b->n >= (1ull << 31)) return fail(ctx, H2B_ERR_ARG, "window table larger than 2^31 points");
+  if (b->d_table) {
+    H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(b->d_table);
+    b->d_table = nullptr;
+    b->pre_c = b->pre_W = 0;
+  }
+  G1Affine* table = nullptr;
+  G1Xyzz* tmp = nullptr;
+  H2B_CUDA(ctx, cudaMalloc((void**)&table, (size_t)W * b->n * sizeof(G1Affine)));
+  cudaError_t e = cudaMalloc((void**)&tmp, b->n * sizeof(G1Xyzz));
+  if (e != cudaSuccess) {
+    cudaFree(table);
+    return fail(ctx, H2B_ERR_OOM, cudaGetErrorString(e));
+  }
+  int rc = H2B_OK;
+  e = cudaMemcpyAsync(table, b->d_pts, b->n * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e != cudaSuccess) rc = fail(ctx, H2B_ERR_CUDA, cudaGetErrorString(e));
+  const uint32_t nblk = (uint32_t)((b->n + 127) / 128);
+  const uint32_t nblk_norm = (uint32_t)(((b->n + kNormBatch - 1) / kNormBatch + 127) / 128);
+  for (uint32_t w = 1; w < W && rc == H2B_OK; ++w) {
+    rc = launch(ctx, msm_table_double_kernel, dim3(nblk), dim3(128), 0,
+                (const G1Affine*)(table + (size_t)(w - 1) * b->n), tmp, (uint64_t)b->n, c);
+    if (rc == H2B_OK)
+      rc = launch(ctx, msm_table_normalize_kernel, dim3(nblk_norm), dim3(128), 0, (const G1Xyzz*)tmp,
+                  table + (size_t)w * b->n, (uint64_t)b->n);
+  }
+  if (rc == H2B_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    rc = fail(ctx, H2B_ERR_CUDA, "window table build failed");
+  cudaFree(tmp);
+  if (rc != H2B_OK) {
+    cudaFree(table);
+    return rc;
+  }
+  b->d_table = table;
+  b->pre_c = c;
+  b->pre_W = W;
+  return H2B_OK;
+}
+
 extern "C" uint32_t h2b_msm_window_bits(size_t n) { return msm_plan(n).c; }
+extern "C" uint32_t h2b_bases_table_window_bits(const h2b_bases* b) { return b ? b->pre_c : 0; }
 extern "C" size_t h2b_bases_len(const h2b_bases* b) { return b ? b->n : 0; }
 extern "C" void* h2b_bases_device_ptr(const h2b_bases* b) { return b ? (void*)b->d_pts : nullptr; }
 
@@ -569,6 +1040,8 @@ static int msm_common(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
                                   ctx->stream));
     d_scalars = reinterpret_cast<const Fr*>(ctx->stage[0]);
   }
+  if (bases->d_table && n >= 1024)  // commit on resident bases: all windows share one bucket set
+    return msm_run(ctx, bases->d_table + base_offset, d_scalars, n, acc, bases->n, bases->pre_c);
   return msm_run(ctx, bases->d_pts + base_offset, d_scalars, n, acc);
 }
 

@@ -66,6 +66,13 @@ uint64_t h2b_ctx_launches(const h2b_ctx* ctx);
 int h2b_bases_upload(h2b_ctx* ctx, const h2b_g1_affine* bases, size_t n, int loc,
                      h2b_bases** out);
 void h2b_bases_free(h2b_bases* bases);
+/* One-time window table of an immutable base set: T_w[i] = 2^(c*w) * bases[i] for every
+ * signed-digit window w, so that all windows of later h2b_msm calls share ONE set of
+ * 2^(c-1) buckets (fewer windows, a W-times smaller bucket reduction).  Costs
+ * ceil(255/c) * n * 64 B of device memory.  window_bits = 0 picks c from n.  Results
+ * are unchanged; h2b_msm uses the table when present. */
+int h2b_bases_precompute(h2b_ctx* ctx, h2b_bases* bases, uint32_t window_bits);
+uint32_t h2b_bases_table_window_bits(const h2b_bases* bases);
 size_t h2b_bases_len(const h2b_bases* bases);
 void* h2b_bases_device_ptr(const h2b_bases* bases);
 

@@ -9,6 +9,8 @@ k = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 n = 1 << k
 ctx = h.Context(0)
 bases = ctx.synth_bases(n, 0x6B7A67)
+if os.environ.get("H2B_NO_TABLE") != "1":
+    bases.precompute()
 sc = ctx.synth_scalars(n, 0x68616C6F32, 0)
 poly = ctx.synth_scalars(n, 7, 0)
 omega = h.fr_encode([h.EvaluationDomain(ctx, 2, k).constant("omega")])

@@ -145,6 +145,33 @@ def test_msm_vs_oracle(emu_ctx, oracle_c, n, kind):
     assert B.msm(S, affine=False) == got  # Jacobian output of h2b_msm
     if n > 10:  # prefix / offset forms used by commit on shorter polynomials
         assert B.msm(S[:10], offset=3) == H.g1_dec(oracle_c.best_multiexp(S[:10], bases[3:13], 1))[0]
+    if n >= 1024:  # window table: all windows share one bucket set
+        for c in (0, 5, 11):
+            B.precompute(c)
+            assert B.table_window_bits == (c or 9)
+            assert B.msm(S) == got
+            assert B.msm(S[:1100], offset=200) == H.g1_dec(oracle_c.best_multiexp(S[:1100], bases[200:1300], 2))[0]
+    B.free()
+
+
+def test_msm_exceptional_cases_batched_affine(emu_ctx, oracle_c, monkeypatch):
+    """Window-table / batched-affine path with P + P, P + (-P) and identity operands everywhere."""
+    rng = random.Random(77)
+    n = 1300
+    base = H.g1_dec(oracle_c.g1_mul_gen([rng.randrange(1, 1 << 64) for _ in range(3)]))
+    pts = []
+    for i in range(n):
+        q = base[i % 3]
+        pts.append(O.g1_neg(q) if (i // 3) % 2 else q)
+    for i in (0, 17, 18, 500, n - 1):
+        pts[i] = None
+    bases = H.g1_enc(pts)
+    B = h.Bases(emu_ctx, bases, n).precompute(6)
+    monkeypatch.setenv("H2B_MSM_TILE", "1000")  # several round-0 tiles
+    for sc in ([5] * n, [rng.randrange(2) for _ in range(n)], [rng.randrange(1 << 12) for _ in range(n)],
+               H.rand_fr(rng, n), [O.R_MOD - 1] * n):
+        S = H.fr_enc(sc)
+        assert B.msm(S) == H.g1_dec(oracle_c.best_multiexp(S, bases, 3))[0]
     B.free()
 
 

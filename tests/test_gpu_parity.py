@@ -295,6 +295,12 @@ def test_msm_vs_oracle(gpu_ctx, oracle_c, n, kind):
     got = B.msm(S)
     assert got == H.g1_dec(oracle_c.best_multiexp(S, bases, 0))[0]
     assert B.msm(S, affine=False) == got
+    if n >= 1024:  # window table path (h2b_bases_precompute): same result
+        for c in (0, 7, 13):
+            B.precompute(c)
+            assert B.msm(S) == got, c
+        m = n // 2 + 5
+        assert B.msm(S[:m], offset=3) == H.g1_dec(oracle_c.best_multiexp(S[:m], bases[3:3 + m], 0))[0]
     B.free()
 
 
@@ -308,10 +314,14 @@ def test_msm_repeated_and_opposite_bases(gpu_ctx, oracle_c):
         pts.append(O.g1_neg(p) if (i // 4) % 2 else p)
     pts[17] = None
     bases = H.g1_enc(pts)
-    for kind in ("uni", "eq", "01"):
+    for kind in ("uni", "eq", "01", "small", "top"):
         S = H.fr_enc(SCALAR_KINDS[kind](rng, n))
         B = h.Bases(gpu_ctx, bases, n)
-        assert B.msm(S) == H.g1_dec(oracle_c.best_multiexp(S, bases, 0))[0], kind
+        want = H.g1_dec(oracle_c.best_multiexp(S, bases, 0))[0]
+        assert B.msm(S) == want, kind
+        for c in (4, 9, 0):  # window table + batched-affine accumulation: P + P, P - P, identities in-band
+            B.precompute(c)
+            assert B.msm(S) == want, (kind, c)
         B.free()
 
 
@@ -354,6 +364,8 @@ def test_msm_closed_form_synthetic(gpu_ctx, k, kind):
     s = H.fr_dec(sc.download(n))
     hs = [gpu_ctx.synth_base_scalar(99, i) for i in range(n)]
     assert got == O.g1_mul(O.G1_GEN, sum(c * x for c, x in zip(s, hs)) % O.R_MOD)
+    B.precompute()
+    assert B.msm(sc, n=n) == got
     sc.free()
     B.free()
 
@@ -382,6 +394,10 @@ def test_msm_k24_linearity(gpu_ctx):
     hs = [gpu_ctx.synth_base_scalar(99, i) for i in range(m)]
     assert B.msm(a, n=m) == O.g1_mul(O.G1_GEN, sum(c * x for c, x in zip(s, hs)) % O.R_MOD)
     assert pa != pb
+    # window table at the benchmark size: identical commitments
+    B.precompute()
+    assert B.table_window_bits == 22
+    assert B.msm(a, n=n) == pa and B.msm(b, n=n) == pb
     for x in (a, b):
         x.free()
     B.free()
