@@ -144,6 +144,101 @@ def cpu_baseline(steps: int = 1, warmup: int = 0):
             "ms_per_pass": (tm + tn) / steps * 1e3}
 
 
+OPMIX_K = 20
+OPMIX = ("create_proof op-mix replay of benches/plonk.rs at k=20 (SURVEY.md 3.1): 11 commits (3 constant advice "
+         "columns + 8 uniform), 4 lagrange_to_coeff (2^20), 4 coeff_to_extended (2^22), 1 divide_by_vanishing + "
+         "extended_to_coeff (2^22); witness synthesis, evaluate_h, eval_polynomial and multiopen algebra NOT included")
+
+
+def cpu_opmix():
+    """The same op mix on the host cores with the C++ restatement of the reference algorithms."""
+    import numpy as np
+    from tests import helpers as H
+    oc = H.load_oracle_c()
+    threads = host_threads()
+    n = 1 << OPMIX_K
+    bases = oc.synth_bases(n, threads=threads)
+    uni = H.rand_fr_limbs(3, n)
+    const = np.tile(H.rand_fr_limbs(4, 1), (n, 1))
+    d = oc.domain(5, OPMIX_K, threads)
+    out = np.zeros(8, dtype=np.uint64)
+    ext = np.zeros((1 << d.extended_k, 4), dtype=np.uint64)
+    t0 = time.perf_counter()
+    for i in range(11):
+        sc = const if i < 3 else uni
+        oc.lib.oracle_best_multiexp(sc.ctypes.data, bases.ctypes.data, n, threads, out.ctypes.data)
+    t1 = time.perf_counter()
+    a = uni.copy()
+    for _ in range(4):
+        oc.lib.oracle_lagrange_to_coeff(d.h, a.ctypes.data)
+    for _ in range(4):
+        oc.lib.oracle_coeff_to_extended(d.h, a.ctypes.data, ext.ctypes.data)
+    oc.lib.oracle_divide_by_vanishing_poly(d.h, ext.ctypes.data)
+    oc.lib.oracle_extended_to_coeff(d.h, ext.ctypes.data)
+    t2 = time.perf_counter()
+    d.free()
+    return {"seconds": t2 - t0, "msm_seconds": t1 - t0, "ntt_seconds": t2 - t1, "cores": threads, "kind": "port"}
+
+
+def gpu_opmix(ctx, h):
+    """The op mix through the drop-in entry points with HOST (pinned) polynomials, as create_proof holds them."""
+    import ctypes as C
+    k, n = OPMIX_K, 1 << OPMIX_K
+    bases = ctx.synth_bases(n, 0xABCD)
+    bases.precompute()
+    dom = h.EvaluationDomain(ctx, 5, k)
+    ne, nq = dom.extended_len(), dom.quotient_len
+    uni_d = ctx.synth_scalars(n, 31, 0)
+    const_d = ctx.synth_scalars(n, 32, 1)
+    ext_d = ctx.synth_scalars(ne, 33, 0)
+    uni, const, ext, extout = ctx.pinned((n, 4)), ctx.pinned((n, 4)), ctx.pinned((ne, 4)), ctx.pinned((ne, 4))
+    for src, dst, cnt in ((uni_d, uni, n), (const_d, const, n), (ext_d, ext, ne)):
+        ctx._check(ctx.lib.h2b_copy_d2h(ctx.h, C.c_void_p(dst.ptr.value), src.ptr, cnt * 32))
+
+    def one(host):
+        t0 = time.perf_counter()
+        for i in range(11):
+            if host:
+                bases.msm(const.array if i < 3 else uni.array)
+            else:
+                bases.msm(const_d if i < 3 else uni_d, n=n)
+        ctx.sync()
+        t1 = time.perf_counter()
+        for _ in range(4):
+            if host:
+                ctx._check(ctx.lib.h2b_lagrange_to_coeff(dom.h, C.c_void_p(uni.ptr.value), h.H2B_HOST))
+            else:
+                dom.lagrange_to_coeff_device(uni_d)
+        for _ in range(4):
+            if host:
+                ctx._check(ctx.lib.h2b_coeff_to_extended(dom.h, C.c_void_p(uni.ptr.value), C.c_void_p(extout.ptr.value),
+                                                         h.H2B_HOST))
+            else:
+                dom.coeff_to_extended_device(uni_d, ext_d)
+        if host:
+            ctx._check(ctx.lib.h2b_extended_to_coeff(dom.h, C.c_void_p(ext.ptr.value), C.c_void_p(extout.ptr.value),
+                                                     h.H2B_HOST, 1))
+        else:
+            dom.extended_to_coeff_device(ext_d, ext_d, divide_by_vanishing=True)
+        ctx.sync()
+        t2 = time.perf_counter()
+        return t2 - t0, t1 - t0, t2 - t1
+
+    one(True)
+    res = {}
+    for host in (True, False):
+        best = min(one(host) for _ in range(2))
+        res["host_buffers" if host else "device_resident"] = {"seconds": best[0], "msm_seconds": best[1],
+                                                              "ntt_seconds": best[2]}
+    for x in (uni, const, ext, extout):
+        x.free()
+    for x in (uni_d, const_d, ext_d):
+        x.free()
+    dom.free()
+    bases.free()
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -327,6 +422,7 @@ def run_ours(args):
         four = {"k": k4, "ms": best, "melem_s": (1 << k4) / (best * 1e-3) / 1e6,
                 "method": "four-step, NCCL all-to-all transposes, wall clock max over ranks"}
 
+    opmix = gpu_opmix(ctx, h) if (rank == 0 and world == 1) else None
     if rank == 0:
         total_pts = world * n * args.steps
         line = {
@@ -352,6 +448,7 @@ def run_ours(args):
             line["four_step_ntt"] = four
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(steps=1)
+            line["create_proof_opmix"] = {"what": OPMIX, "gpu": opmix, "cpu": cpu_opmix()}
         print(json.dumps(line), flush=True)
     barrier()
     ctx.close()

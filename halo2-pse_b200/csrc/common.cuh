@@ -34,6 +34,9 @@ struct h2b_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  // second stream + events for host->device copies overlapped with compute (drop-in calls on host slices)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::recursive_mutex mu;
   std::string last_error;
   // grow-only device scratch (NTT ping buffer)
@@ -180,8 +183,10 @@ void ntt_free_tables(h2b_ctx* ctx);
 // msm.cu
 // table_stride == 0: classic per-window buckets over `d_points` (n points).
 // table_stride  > 0: `d_points` is a window table (w * table_stride + i), all windows share one bucket set.
+// h_scalars != nullptr: the scalars still live on the host; they are copied into d_scalars in chunks
+// on the copy stream while the digit kernel consumes the chunks already there.
 int msm_run(h2b_ctx* ctx, const G1Affine* d_points, const Fr* d_scalars, size_t n, G1Xyzz* out_host,
-            size_t table_stride = 0, uint32_t table_c = 0);
+            size_t table_stride = 0, uint32_t table_c = 0, const Fr* h_scalars = nullptr);
 void msm_ws_free(h2b_ctx* ctx);
 
 }  // namespace h2b

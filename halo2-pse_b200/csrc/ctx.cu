@@ -274,6 +274,12 @@ extern "C" int h2b_ctx_create(int device, h2b_ctx** out) {
     delete ctx;
     return H2B_ERR_CUDA;
   }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return H2B_ERR_CUDA;
+  }
+  for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
   for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->pass_ev[i]);
   *out = ctx;
@@ -293,6 +299,9 @@ extern "C" void h2b_ctx_destroy(h2b_ctx* ctx) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 6; ++i)
     if (ctx->pass_ev[i]) cudaEventDestroy(ctx->pass_ev[i]);
+  for (int i = 0; i < 8; ++i)
+    if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -99,9 +99,11 @@ void msm_ws_free(h2b_ctx* ctx) {
 // 1. digits
 // ---------------------------------------------------------------------------
 // table_stride > 0 (window table): key = |d| - 1 for every window, val = w * table_stride + i
+// Processes scalars [i0, i1) of n.
 __global__ void msm_digits_kernel(const Fr* scalars, uint64_t n, uint32_t c, uint32_t W,
-                                  uint32_t* keys, uint32_t* vals, uint64_t table_stride) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+                                  uint32_t* keys, uint32_t* vals, uint64_t table_stride, uint64_t i0,
+                                  uint64_t i1) {
+  for (uint64_t i = i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1;
        i += (uint64_t)gridDim.x * blockDim.x) {
     const Fr s = from_mont(ld_fp(scalars + i));  // to_repr(), arithmetic.rs:14
     uint32_t carry = 0;
@@ -746,7 +748,7 @@ static int accumulate_affine(h2b_ctx* ctx, MsmWorkspace* ws, const MsmPlan& p, c
 }
 
 int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n,
-            G1Xyzz* out_host, size_t table_stride, uint32_t table_c) {
+            G1Xyzz* out_host, size_t table_stride, uint32_t table_c, const Fr* h_scalars) {
   *out_host = G1Xyzz::identity();
   if (n == 0) return H2B_OK;
   if (n >= (1ull << 31)) return fail(ctx, H2B_ERR_ARG, "MSM larger than 2^31 points");
@@ -758,12 +760,34 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   cudaStream_t st = ctx->stream;
   (void)st;
 
-  // 1. digits
+  // 1. digits (host scalars: chunked H2D on the copy stream, overlapped with the digit kernel)
   {
-    const uint64_t want = (n + 255) / 256;
     const uint64_t cap = (uint64_t)ctx->sm_count * 16;
-    H2B_TRY(launch(ctx, msm_digits_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0,
-                   d_scalars, (uint64_t)n, p.c, p.W, ws->keys_in, ws->vals_in, (uint64_t)table_stride));
+    const int nchunk = (h_scalars && n >= (1u << 16)) ? 8 : 1;
+    const uint64_t per = (n + nchunk - 1) / nchunk;
+    if (h_scalars && nchunk > 1) {
+      // the copy stream must not overwrite the staging buffer while an earlier call still reads it
+      H2B_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], st));
+      H2B_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+    }
+    for (int ci = 0; ci < nchunk; ++ci) {
+      const uint64_t i0 = (uint64_t)ci * per, i1 = std::min<uint64_t>(n, i0 + per);
+      if (i0 >= i1) break;
+      if (h_scalars) {
+        Fr* dst = const_cast<Fr*>(d_scalars) + i0;
+        if (nchunk == 1) {
+          H2B_CUDA(ctx, cudaMemcpyAsync(dst, h_scalars + i0, (i1 - i0) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        } else {
+          H2B_CUDA(ctx, cudaMemcpyAsync(dst, h_scalars + i0, (i1 - i0) * sizeof(Fr), cudaMemcpyHostToDevice,
+                                        ctx->copy_stream));
+          H2B_CUDA(ctx, cudaEventRecord(ctx->copy_ev[ci], ctx->copy_stream));
+          H2B_CUDA(ctx, cudaStreamWaitEvent(st, ctx->copy_ev[ci], 0));
+        }
+      }
+      const uint64_t want = (i1 - i0 + 255) / 256;
+      H2B_TRY(launch(ctx, msm_digits_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0,
+                     d_scalars, (uint64_t)n, p.c, p.W, ws->keys_in, ws->vals_in, (uint64_t)table_stride, i0, i1));
+    }
   }
   // 2. sort
 #ifdef H2B_EMU
@@ -790,8 +814,9 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
                                 (size_t)p.Wb * p.nb_per_window * sizeof(G1Xyzz), st));
 
   // 3. bucket accumulation: batched affine on a window table, else level-wise XYZZ chunks
-  bool affine = table_stride != 0;
-  if (const char* e = getenv("H2B_MSM_ACC")) affine = affine && strcmp(e, "xyzz") != 0;
+  // (the batched-affine path is correct but not yet faster than the XYZZ chunks: opt-in)
+  bool affine = false;
+  if (const char* e = getenv("H2B_MSM_ACC")) affine = table_stride != 0 && strcmp(e, "affine") == 0;
   if (affine) {
     H2B_TRY(accumulate_affine(ctx, ws, p, d_bases));
   } else {
@@ -1034,15 +1059,15 @@ static int msm_common(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
     return fail(ctx, H2B_ERR_LENGTH, "more scalars than bases");
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
   const Fr* d_scalars = reinterpret_cast<const Fr*>(scalars);
+  const Fr* h_scalars = nullptr;
   if (loc != H2B_DEVICE && n) {
     H2B_TRY(ensure_stage(ctx, 0, n * sizeof(Fr)));
-    H2B_CUDA(ctx, cudaMemcpyAsync(ctx->stage[0], scalars, n * sizeof(Fr), cudaMemcpyHostToDevice,
-                                  ctx->stream));
+    h_scalars = d_scalars;  // copied inside msm_run, chunk by chunk, under the digit kernel
     d_scalars = reinterpret_cast<const Fr*>(ctx->stage[0]);
   }
   if (bases->d_table && n >= 1024)  // commit on resident bases: all windows share one bucket set
-    return msm_run(ctx, bases->d_table + base_offset, d_scalars, n, acc, bases->n, bases->pre_c);
-  return msm_run(ctx, bases->d_pts + base_offset, d_scalars, n, acc);
+    return msm_run(ctx, bases->d_table + base_offset, d_scalars, n, acc, bases->n, bases->pre_c, h_scalars);
+  return msm_run(ctx, bases->d_pts + base_offset, d_scalars, n, acc, 0, 0, h_scalars);
 }
 
 static void xyzz_to_jacobian(const G1Xyzz& p, h2b_g1* out) {

@@ -472,6 +472,12 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t* e) {
   *e = new emu_event();
   return cudaSuccess;
 }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
+  *e = new emu_event();
+  return cudaSuccess;
+}
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
   delete e;
   return cudaSuccess;

@@ -129,7 +129,7 @@ def test_golden_best_multiexp(emu_ctx):
 
 @pytest.mark.parametrize("n,kind", [(1, "uni"), (2, "uni"), (257, "uni"), (1500, "uni"), (1500, "eq"),
                                     (1500, "01"), (1500, "small"), (700, "sparse")])
-def test_msm_vs_oracle(emu_ctx, oracle_c, n, kind):
+def test_msm_vs_oracle(emu_ctx, oracle_c, n, kind, monkeypatch):
     rng = random.Random(n)
     hs = [rng.randrange(1, 1 << 64) for _ in range(n)]
     bases = oracle_c.g1_mul_gen(hs)
@@ -149,6 +149,7 @@ def test_msm_vs_oracle(emu_ctx, oracle_c, n, kind):
         for c in (0, 5, 11):
             B.precompute(c)
             assert B.table_window_bits == (c or 9)
+            monkeypatch.setenv("H2B_MSM_ACC", "affine" if c else "xyzz")
             assert B.msm(S) == got
             assert B.msm(S[:1100], offset=200) == H.g1_dec(oracle_c.best_multiexp(S[:1100], bases[200:1300], 2))[0]
     B.free()
@@ -168,10 +169,11 @@ def test_msm_exceptional_cases_batched_affine(emu_ctx, oracle_c, monkeypatch):
     bases = H.g1_enc(pts)
     B = h.Bases(emu_ctx, bases, n).precompute(6)
     monkeypatch.setenv("H2B_MSM_TILE", "1000")  # several round-0 tiles
-    for sc in ([5] * n, [rng.randrange(2) for _ in range(n)], [rng.randrange(1 << 12) for _ in range(n)],
-               H.rand_fr(rng, n), [O.R_MOD - 1] * n):
+    for acc, sc in [(a, x) for a in ("affine", "xyzz") for x in ([5] * n, [rng.randrange(2) for _ in range(n)], [rng.randrange(1 << 12) for _ in range(n)],
+               H.rand_fr(rng, n), [O.R_MOD - 1] * n)]:
+        monkeypatch.setenv("H2B_MSM_ACC", acc)
         S = H.fr_enc(sc)
-        assert B.msm(S) == H.g1_dec(oracle_c.best_multiexp(S, bases, 3))[0]
+        assert B.msm(S) == H.g1_dec(oracle_c.best_multiexp(S, bases, 3))[0], acc
     B.free()
 
 

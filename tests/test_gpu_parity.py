@@ -285,7 +285,7 @@ SCALAR_KINDS = {
 
 @pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 1000, 4097, 70000])
 @pytest.mark.parametrize("kind", sorted(SCALAR_KINDS))
-def test_msm_vs_oracle(gpu_ctx, oracle_c, n, kind):
+def test_msm_vs_oracle(gpu_ctx, oracle_c, n, kind, monkeypatch):
     rng = random.Random(n * 7 + len(kind))
     hs = np.array([rng.randrange(1, 1 << 64) for _ in range(n)], dtype=np.uint64)
     bases = oracle_c.g1_mul_gen(hs)
@@ -298,13 +298,15 @@ def test_msm_vs_oracle(gpu_ctx, oracle_c, n, kind):
     if n >= 1024:  # window table path (h2b_bases_precompute): same result
         for c in (0, 7, 13):
             B.precompute(c)
-            assert B.msm(S) == got, c
+            for acc in ("xyzz", "affine"):  # both bucket-accumulation paths
+                monkeypatch.setenv("H2B_MSM_ACC", acc)
+                assert B.msm(S) == got, (c, acc)
         m = n // 2 + 5
         assert B.msm(S[:m], offset=3) == H.g1_dec(oracle_c.best_multiexp(S[:m], bases[3:3 + m], 0))[0]
     B.free()
 
 
-def test_msm_repeated_and_opposite_bases(gpu_ctx, oracle_c):
+def test_msm_repeated_and_opposite_bases(gpu_ctx, oracle_c, monkeypatch):
     rng = random.Random(9)
     n = 5000
     base = H.g1_dec(oracle_c.g1_mul_gen([rng.randrange(1, 1 << 64) for _ in range(4)]))
@@ -321,7 +323,9 @@ def test_msm_repeated_and_opposite_bases(gpu_ctx, oracle_c):
         assert B.msm(S) == want, kind
         for c in (4, 9, 0):  # window table + batched-affine accumulation: P + P, P - P, identities in-band
             B.precompute(c)
-            assert B.msm(S) == want, (kind, c)
+            for acc in ("xyzz", "affine"):
+                monkeypatch.setenv("H2B_MSM_ACC", acc)
+                assert B.msm(S) == want, (kind, c, acc)
         B.free()
 
 
