@@ -48,6 +48,10 @@ struct PassParams {
   uint32_t h;
   const Fr* rt;
   uint32_t rt_log;
+  // single-level inter-pass twiddle table: w = tw1[(jr*K) << tw1_shift], negated when
+  // tw1_half != 0 and the index has bit tw1_half set (table folded by omega^(n/2) = -1)
+  const Fr* tw1;
+  uint32_t tw1_shift, tw1_half;
 };
 
 struct Tile {
@@ -106,11 +110,22 @@ H2B_D Fr load_in(const PassParams& p, const Fr* in, uint64_t gi) {
 
 H2B_D void store_out(const PassParams& p, Fr* out, const Tile& g, uint32_t K, uint32_t c, Fr x) {
   if (!p.last) {
-    const uint64_t e = ((g.jr0 + c) * (uint64_t)K) << (p.k - p.lm);
-    const uint32_t elo = (uint32_t)e & ((1u << p.h) - 1u);
-    const uint32_t ehi = (uint32_t)(e >> p.h);
-    x = mul(x, ld_fp_nc(p.tw_lo + elo));
-    x = mul(x, ld_fp_nc(p.tw_hi + ehi));
+    if (p.tw1) {
+      uint64_t idx = ((g.jr0 + c) * (uint64_t)K) << p.tw1_shift;
+      bool negate = false;
+      if (p.tw1_half) {
+        negate = (idx >> p.tw1_half) & 1;
+        idx &= (1ull << p.tw1_half) - 1;
+      }
+      x = mul(x, ld_fp_nc(p.tw1 + idx));
+      if (negate) x = neg(x);
+    } else {
+      const uint64_t e = ((g.jr0 + c) * (uint64_t)K) << (p.k - p.lm);
+      const uint32_t elo = (uint32_t)e & ((1u << p.h) - 1u);
+      const uint32_t ehi = (uint32_t)(e >> p.h);
+      x = mul(x, ld_fp_nc(p.tw_lo + elo));
+      x = mul(x, ld_fp_nc(p.tw_hi + ehi));
+    }
     st_fp(out + g.out_base + (uint64_t)K * g.out_rs + c, x);
   } else {
     const uint64_t Ko = g.out_base + (uint64_t)K * g.out_rs + c;
@@ -378,6 +393,8 @@ static bool omega_has_order(const Fr& omega, uint32_t k) {
   return t == neg(Fr::one());  // omega^(2^(k-1)) = -1  <=>  exact order 2^k
 }
 
+static int ntt_plan(uint32_t k, uint32_t* s);
+
 int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t k, const TwTable** out) {
   for (auto& t : ctx->tw)
     if (t.k == k && t.omega == omega) {
@@ -401,6 +418,31 @@ int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t k, const TwTable** out
                  nhi));
   H2B_TRY(launch(ctx, pow_table_kernel, dim3(((1u << rt_log) + 127) / 128), dim3(128), 0, t.d_rt,
                  omega, k - rt_log, 1u << rt_log));
+  // single-level tables (later passes: 2^(k-6) entries at most; first pass: folded full table, opt-in)
+  if (k > 8) {
+    uint32_t s[4];
+    ntt_plan(k, s);
+    t.mid_log = k - s[0];
+    const uint32_t nmid = 1u << t.mid_log;
+    if (cudaMalloc((void**)&t.d_mid, (size_t)nmid * sizeof(Fr)) == cudaSuccess) {
+      H2B_TRY(launch(ctx, pow_table_kernel, dim3((nmid + 127) / 128), dim3(128), 0, t.d_mid, omega, k - t.mid_log,
+                     nmid));
+    } else {
+      t.d_mid = nullptr;
+      cudaGetLastError();
+    }
+    // Measured on B200 at k = 24: the random 32-byte reads of a 256 MiB table cost more (2.18 ms)
+    // than the second multiplication they save (1.62 ms): opt-in only.
+    if (k <= 26 && getenv("H2B_NTT_FULL_TABLE") != nullptr) {
+      const uint32_t nfull = 1u << (k - 1);
+      if (cudaMalloc((void**)&t.d_full, (size_t)nfull * sizeof(Fr)) == cudaSuccess) {
+        H2B_TRY(launch(ctx, pow_table_kernel, dim3((nfull + 127) / 128), dim3(128), 0, t.d_full, omega, 0u, nfull));
+      } else {
+        t.d_full = nullptr;
+        cudaGetLastError();
+      }
+    }
+  }
   ctx->tw.push_back(t);
   *out = &ctx->tw.back();
   return H2B_OK;
@@ -411,6 +453,8 @@ void ntt_free_tables(h2b_ctx* ctx) {
     cudaFree(t.d_lo);
     cudaFree(t.d_hi);
     cudaFree(t.d_rt);
+    if (t.d_full) cudaFree(t.d_full);
+    if (t.d_mid) cudaFree(t.d_mid);
   }
   ctx->tw.clear();
 }
@@ -486,6 +530,15 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       p.h = tw->h;
       p.rt = tw->d_rt;
       p.rt_log = k < 8 ? k : 8;
+      p.tw1 = nullptr;
+      p.tw1_shift = p.tw1_half = 0;
+      if (!p.last && pi == 0 && tw->d_full) {
+        p.tw1 = tw->d_full;
+        p.tw1_half = k - 1;
+      } else if (!p.last && pi > 0 && tw->d_mid && lm <= tw->mid_log) {
+        p.tw1 = tw->d_mid;
+        p.tw1_shift = tw->mid_log - lm;
+      }
       if (p.first) {
         p.in = d_in + (uint64_t)b0 * in_stride;
         p.in_bstride = in_stride;
