@@ -23,7 +23,7 @@ struct TwTable {
   uint32_t h;      // split of the two-level table: e = (e_hi << h) | e_lo
   Fr* d_lo;        // omega^i,           i < 2^h
   Fr* d_hi;        // omega^(i << h),    i < 2^(k-h)
-  Fr* d_rt;        // omega_R^i, R = 2^min(k,8), i < R   (intra-pass roots)
+  Fr* d_rt;        // omega_R^i, R = 2^min(k,9), i < R   (intra-pass roots)
   // single-multiplication inter-pass twiddles (optional; nullptr -> two-level lo/hi product)
   Fr* d_full = nullptr;  // omega^i, i < 2^(k-1); omega^(i + 2^(k-1)) = -omega^i   (first pass)
   Fr* d_mid = nullptr;   // (omega^(2^(k-mid_log)))^i, i < 2^mid_log               (later passes)

@@ -214,7 +214,7 @@ H2B_D void dft8(Fr* x, const Fr* rt, uint32_t rt_log) {
 template <int S>
 __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   constexpr int R = 1 << S, T = R / 8, LC = 11 - S, C = 1 << LC;
-  constexpr int LM2 = S - 6, M2 = 1 << LM2;  // 4, 2, 1
+  constexpr int LM2 = S - 6, M2 = 1 << LM2;  // 8, 4, 2, 1
   constexpr int PLANE = 2048;
   H2B_DYN_SMEM(smem_raw);
   uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw);
@@ -271,7 +271,15 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   for (int Ka2 = 0; Ka2 < 8; ++Ka2) put(Ka * T + Ka2 * M2 + b2, x[Ka2]);
   __syncthreads();
   // round 3: groups gq = Ka*8 + Ka2 (64 per column), M2-point DFT over b2
-  if (M2 == 4) {
+  if (M2 == 8) {
+    const uint32_t gq = u;  // 64 threads per column, one group each
+#pragma unroll
+    for (int b = 0; b < 8; ++b) x[b] = get(gq * 8 + b);
+    dft8(x, p.rt, p.rt_log);
+    const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) store_out(p, out, g, K0 + 64 * i, c, x[i]);
+  } else if (M2 == 4) {
     const Fr w4 = ld_fp_nc(p.rt + (1u << (p.rt_log - 2)));
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -408,7 +416,7 @@ int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t k, const TwTable** out
   t.k = k;
   t.h = (k + 1) / 2;
   const uint32_t nlo = 1u << t.h, nhi = 1u << (k - t.h);
-  const uint32_t rt_log = k < 8 ? k : 8;
+  const uint32_t rt_log = k < 9 ? k : 9;
   H2B_CUDA(ctx, cudaMalloc((void**)&t.d_lo, (size_t)nlo * sizeof(Fr)));
   H2B_CUDA(ctx, cudaMalloc((void**)&t.d_hi, (size_t)nhi * sizeof(Fr)));
   H2B_CUDA(ctx, cudaMalloc((void**)&t.d_rt, ((size_t)1 << rt_log) * sizeof(Fr)));
@@ -466,7 +474,10 @@ static int ntt_plan(uint32_t k, uint32_t* s) {
     s[0] = k;
     return 1;
   }
-  const int P = (int)((k + 7) / 8);
+  // fewest passes with digits <= 9; below 12 bits two digits of >= 6 are not possible anyway
+  int P = (int)((k + 8) / 9);
+  if (const char* e = getenv("H2B_NTT_MAX_DIGIT"))
+    if (atoi(e) == 8) P = (int)((k + 7) / 8);
   const uint32_t base = k / P, rem = k % P;
   for (int i = 0; i < P; ++i) s[i] = base + ((uint32_t)i >= (uint32_t)P - rem ? 1u : 0u);
   return P;
@@ -489,6 +500,8 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
     H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_fast<7>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_fast<8>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_fast<9>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     ctx->ntt_attr_done = true;
   }
@@ -529,7 +542,7 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       p.tw_hi = tw->d_hi;
       p.h = tw->h;
       p.rt = tw->d_rt;
-      p.rt_log = k < 8 ? k : 8;
+      p.rt_log = k < 9 ? k : 9;
       p.tw1 = nullptr;
       p.tw1_shift = p.tw1_half = 0;
       if (!p.last && pi == 0 && tw->d_full) {
@@ -556,7 +569,7 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       // columns per tile
       uint32_t lc = 11 - p.s;
       const uint32_t avail = p.single ? 0 : (p.last ? p.s1 : lm - p.s);
-      const bool fast = !p.single && p.s >= 6 && p.s <= 8 && lc <= avail;
+      const bool fast = !p.single && p.s >= 6 && p.s <= 9 && lc <= avail;
       if (lc > avail) lc = avail;
       p.lc = lc;
       const uint32_t tiles = (uint32_t)(n >> (p.s + lc));
@@ -567,6 +580,7 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
         if (p.s == 6) H2B_TRY(launch(ctx, ntt_pass_fast<6>, grid, dim3(256), 65536, p));
         if (p.s == 7) H2B_TRY(launch(ctx, ntt_pass_fast<7>, grid, dim3(256), 65536, p));
         if (p.s == 8) H2B_TRY(launch(ctx, ntt_pass_fast<8>, grid, dim3(256), 65536, p));
+        if (p.s == 9) H2B_TRY(launch(ctx, ntt_pass_fast<9>, grid, dim3(256), 65536, p));
       } else {
         H2B_TRY(launch(ctx, ntt_pass_generic, grid, dim3(256), 65536, p));
       }

@@ -45,7 +45,7 @@ def test_golden_best_fft(emu_ctx):
         assert a.tobytes().hex() == v["out"], v["log_n"]
 
 
-@pytest.mark.parametrize("k", [2, 5, 8, 9, 10, 12, 13, 14])
+@pytest.mark.parametrize("k", [2, 5, 8, 9, 10, 12, 13, 14, 17, 18])
 def test_best_fft_vs_oracle(emu_ctx, oracle_c, k):
     a = H.rand_fr_limbs(k, 1 << k)
     w = H.fr_enc([O.omega_for(k)])[0]
