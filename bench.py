@@ -423,26 +423,39 @@ def run_ours(args):
         part = torch.empty(lv * 4, dtype=torch.int64, device=torch.device("cuda", local))
         mine = np.ascontiguousarray(full.download(1 << kv)[rank * lv:(rank + 1) * lv])
         ctx._check(ctx.lib.h2b_copy_h2d(ctx.h, C.c_void_p(part.data_ptr()), C.c_void_p(mine.ctypes.data), lv * 32))
-        D.FourStepNTT(ctx, kv, wv).run(part)
+        fsv = D.FourStepNTT(ctx, kv, wv)
+        vmethod = fsv.p2p
+        fsv.run(part)
         ctx.best_fft_device(full, h.fr_encode([wv]), kv)
         want = full.download(1 << kv)[rank * lv:(rank + 1) * lv]
         got = part.cpu().numpy().view(np.uint64).reshape(-1, 4)
         four_ok = bool((got == want).all())
         full.free()
-        fs = D.FourStepNTT(ctx, k4, h.EvaluationDomain(ctx, 2, k4).constant("omega"))
-        fs.run(buf)
-        barrier()
-        ts = []
-        for _ in range(3):
-            t0 = time.perf_counter()
+        w4 = h.EvaluationDomain(ctx, 2, k4).constant("omega")
+        four = {"k": k4}
+        for label, p2p in (("p2p", None), ("nccl_all_to_all", False)):
+            fs = D.FourStepNTT(ctx, k4, w4, p2p=p2p)
+            if label == "p2p" and not fs.p2p:
+                four["p2p_unavailable"] = fs.p2p_error
+                continue
             fs.run(buf)
             barrier()
-            ts.append((time.perf_counter() - t0) * 1e3)
-        (best,) = max_over_ranks(min(ts))
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                fs.run(buf)
+                barrier()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            (best,) = max_over_ranks(min(ts))
+            four[label] = {"ms": best, "melem_s": (1 << k4) / (best * 1e-3) / 1e6}
         (ok_all,) = max_over_ranks(0.0 if four_ok else 1.0)
-        four = {"k": k4, "ms": best, "melem_s": (1 << k4) / (best * 1e-3) / 1e6,
-                "verified_vs_single_gpu_k20": ok_all == 0.0,
-                "method": "four-step, NCCL all-to-all transposes, wall clock max over ranks"}
+        four["verified_vs_single_gpu_k20"] = ok_all == 0.0
+        four["verified_method"] = "p2p" if vmethod else "nccl_all_to_all"
+        four["method"] = ("four-step; p2p = transposes fused with the exchange as direct stores into NVLink-mapped peer "
+                          "buffers (symmetric memory), device-side barriers; nccl_all_to_all = tile transposes + "
+                          "all_to_all_single + permute; wall clock, max over ranks")
+        best = four.get("p2p", four.get("nccl_all_to_all"))
+        four["ms"], four["melem_s"] = best["ms"], best["melem_s"]
 
     opmix = gpu_opmix(ctx, h) if (rank == 0 and world == 1) else None
     if rank == 0:

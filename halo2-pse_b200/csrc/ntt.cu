@@ -363,6 +363,43 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Transpose fused with the exchange: rank `rank` holds rows [rank*rows, (rank+1)*rows) of a
+// global R x cols matrix (R = G*rows); element (r, c) is stored straight into the buffer of
+// the peer h = c / cl that owns column c of the transposed matrix, at its final place
+// dst_h[(c % cl) * R + rank*rows + r].  Peer buffers are NVLink-mapped device pointers
+// (symmetric memory), so the all-to-all IS these stores: no pack, no collective, no unpack.
+struct PeerPtrs {
+  Fr* p[16];
+};
+__global__ void __launch_bounds__(256)
+    transpose_scatter_kernel(const Fr* in, PeerPtrs peers, uint32_t rank, uint32_t rows, uint32_t cols,
+                             uint32_t cl, uint64_t R) {
+  __shared__ uint32_t tile[8][32][33];
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t r = r0 + ty + 8 * i, c = c0 + tx;
+    if (r < rows && c < cols) {
+      const Fr v = ld_fp(in + (uint64_t)r * cols + c);
+#pragma unroll
+      for (int l = 0; l < 8; ++l) tile[l][ty + 8 * i][tx] = v.v[l];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t c = c0 + ty + 8 * i, r = r0 + tx;
+    if (r < rows && c < cols) {
+      Fr v;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) v.v[l] = tile[l][tx][ty + 8 * i];
+      Fr* dst = peers.p[c / cl];
+      st_fp(dst + (uint64_t)(c % cl) * R + (uint64_t)rank * rows + r, v);
+    }
+  }
+}
+
 // out[b][a][c] = in[a][b][c]   (a < A, b < B, c < C; C-element runs stay contiguous)
 __global__ void permute3_kernel(const Fr* in, Fr* out, uint32_t A, uint32_t B, uint32_t C) {
   const uint64_t total = (uint64_t)A * B * C;
@@ -931,4 +968,22 @@ extern "C" int h2b_fr_twiddle_rows(h2b_ctx* ctx, h2b_fr* a, const h2b_fr* omega,
   const uint64_t want = (total + 255) / 256, cap = (uint64_t)ctx->sm_count * 16;
   return launch(ctx, twiddle_rows_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0, as_fr(a),
                 row0, nrows, ncols, (const Fr*)tw->d_lo, (const Fr*)tw->d_hi, tw->h);
+}
+
+extern "C" int h2b_fr_transpose_scatter(h2b_ctx* ctx, const h2b_fr* in, void* const* peer_out,
+                                        uint32_t world, uint32_t rank, uint32_t rows_local,
+                                        uint32_t cols) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!in || !peer_out) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (world == 0 || world > 16 || rank >= world || cols % world)
+    return fail(ctx, H2B_ERR_ARG, "bad world / rank / column count");
+  if (rows_local == 0 || cols == 0) return H2B_OK;
+  PeerPtrs peers;
+  for (uint32_t i = 0; i < 16; ++i) peers.p[i] = i < world ? reinterpret_cast<Fr*>(peer_out[i]) : nullptr;
+  for (uint32_t i = 0; i < world; ++i)
+    if (!peers.p[i] || peers.p[i] == as_fr(in)) return fail(ctx, H2B_ERR_ARG, "null or aliased peer buffer");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  return launch(ctx, transpose_scatter_kernel, dim3((cols + 31) / 32, (rows_local + 31) / 32), dim3(256), 0,
+                as_fr(in), peers, rank, rows_local, cols, cols / world, (uint64_t)rows_local * world);
 }

@@ -123,7 +123,9 @@ class FourStepNTT:
         T ; n1-point row NTTs ; twiddle w^(j2*K1) ; T ; n2-point row NTTs ; T
     """
 
-    def __init__(self, ctx: Context, log_n: int, omega: int, group=None):
+    def __init__(self, ctx: Context, log_n: int, omega: int, group=None, p2p: Optional[bool] = None):
+        """p2p: None = use NVLink peer stores (symmetric memory) when the group is NCCL and it can be
+        set up, else the all-to-all collective; True = require it; False = collective only."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -146,7 +148,59 @@ class FourStepNTT:
         self.w2 = fr_encode([pow(omega, self.n1, R_MOD)])  # order n2
         self.dev = _group_device(group) if self.world > 1 else None
         self.local = (1 << log_n) // G
-        self._bufs = None
+        self.p2p = False
+        self.p2p_error = None
+        if self.world > 1 and self.dev is not None and self.dev.type == "cuda" and p2p is not False:
+            try:
+                self._init_p2p()
+            except Exception as e:  # symmetric memory unavailable: keep the collective path
+                if p2p:
+                    raise
+                self.p2p_error = f"{type(e).__name__}: {e}"
+
+    def _init_p2p(self) -> None:
+        import torch.distributed._symmetric_memory as sm
+        torch, dist = self.torch, self.dist
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self.S = [sm.empty(self.local * 4, dtype=torch.int64, device=self.dev) for _ in range(2)]
+        self.H = [sm.rendezvous(t, grp) for t in self.S]
+        G = self.world
+        self.peer = [(C.c_void_p * G)(*[int(p) for p in hd.buffer_ptrs]) for hd in self.H]
+        self.xstream = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
+        self.p2p = True
+
+    def _scatter(self, src_ptr, dst: int, rows_local: int, cols: int) -> None:
+        ctx = self.ctx
+        ctx._check(ctx.lib.h2b_fr_transpose_scatter(ctx.h, src_ptr, self.peer[dst], self.world, self.rank,
+                                                    rows_local, cols))
+
+    def _run_p2p(self, a):
+        """Three fused transpose+exchange kernels over NVLink peer memory, device-side barriers only;
+        everything is enqueued on the library's stream."""
+        ctx, G, torch = self.ctx, self.world, self.torch
+        n1, n2 = self.n1, self.n2
+        S1, S2 = self.S
+        H1, H2 = self.H
+        torch.cuda.current_stream().synchronize()  # `a` may have been produced on torch's stream
+        with torch.cuda.stream(self.xstream):
+            H1.barrier(0)  # every peer is done with S1 of the previous transform
+            self._scatter(self._p(a), 0, n1 // G, n2)           # A[j1][j2] -> A^T[j2][j1] in S1
+            H1.barrier(0)
+            rows = n2 // G
+            ctx._check(ctx.lib.h2b_best_fft_batch(ctx.h, self._p(S1), H2B_DEVICE,
+                                                  C.c_void_p(self.w1.ctypes.data), self.k1, rows, n1))
+            ctx._check(ctx.lib.h2b_fr_twiddle_rows(ctx.h, self._p(S1), C.c_void_p(self.w.ctypes.data), self.k,
+                                                   self.rank * rows, rows, n1))
+            self._scatter(self._p(S1), 1, rows, n1)               # -> B[K1][j2] in S2
+            H2.barrier(0)
+            rows = n1 // G
+            ctx._check(ctx.lib.h2b_best_fft_batch(ctx.h, self._p(S2), H2B_DEVICE,
+                                                  C.c_void_p(self.w2.ctypes.data), self.k2, rows, n2))
+            self._scatter(self._p(S2), 0, rows, n2)               # C[K1][K2] -> natural order in S1
+            H1.barrier(0)
+            a.copy_(S1)
+        ctx.sync()
+        return a
 
     # -- helpers ---------------------------------------------------------
     def _p(self, t) -> C.c_void_p:
@@ -181,6 +235,8 @@ class FourStepNTT:
     def run(self, a):
         """a: int64 tensor of 4 * n/G limbs words (this rank's natural-order slice), transformed
         in place; returns `a`."""
+        if self.p2p:
+            return self._run_p2p(a)
         ctx, G = self.ctx, self.world
         n1, n2 = self.n1, self.n2
         self.dev = a.device

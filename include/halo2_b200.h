@@ -149,6 +149,12 @@ int h2b_extended_to_coeff_batch(h2b_domain* dom, const h2b_fr* in, size_t in_str
 int h2b_fr_transpose_batch(h2b_ctx* ctx, const h2b_fr* in, h2b_fr* out, uint32_t rows, uint32_t cols,
                            size_t in_row_stride, uint32_t nbatch, size_t in_batch_stride,
                            size_t out_batch_stride);
+/* Transpose fused with the exchange step: `in` = this rank's rows of a global
+ * (world*rows_local) x cols matrix; element (r, c) is stored directly into
+ * peer_out[c / (cols/world)] (NVLink-mapped device pointers of every rank's destination
+ * buffer, own rank included) at its place in the row-sharded transposed matrix. */
+int h2b_fr_transpose_scatter(h2b_ctx* ctx, const h2b_fr* in, void* const* peer_out, uint32_t world,
+                             uint32_t rank, uint32_t rows_local, uint32_t cols);
 int h2b_fr_permute3(h2b_ctx* ctx, const h2b_fr* in, h2b_fr* out, uint32_t A, uint32_t B, uint32_t C);
 int h2b_fr_twiddle_rows(h2b_ctx* ctx, h2b_fr* a, const h2b_fr* omega, uint32_t log_n, uint64_t row0,
                         uint32_t nrows, uint32_t ncols);

@@ -102,3 +102,22 @@ def test_four_step_single_rank(emu_ctx, oracle_c):
         t = torch.from_numpy(a.copy().view(np.int64).reshape(-1))
         D.FourStepNTT(emu_ctx, k, omega).run(t)
         assert (t.numpy().view(np.uint64).reshape(-1, 4) == want).all()
+
+
+def test_transpose_scatter_kernel(emu_ctx):
+    """The fused transpose+exchange kernel, all ranks emulated in one process: rank g stores its
+    rows straight into every rank's destination buffer; together they form the row-sharded transpose."""
+    import ctypes as C
+    from tests import helpers as H
+    for G, R, Cn in ((1, 40, 24), (2, 64, 96), (4, 32, 64), (8, 64, 40)):
+        M = H.rand_fr_limbs(G * 1000 + R, R * Cn).reshape(R, Cn, 4)
+        Rl, Cl = R // G, Cn // G
+        dst = [np.zeros((Cl * R, 4), dtype=np.uint64) for _ in range(G)]
+        ptrs = (C.c_void_p * G)(*[d.ctypes.data for d in dst])
+        for g in range(G):
+            src = np.ascontiguousarray(M[g * Rl:(g + 1) * Rl]).reshape(-1, 4)
+            emu_ctx._check(emu_ctx.lib.h2b_fr_transpose_scatter(emu_ctx.h, C.c_void_p(src.ctypes.data), ptrs, G, g,
+                                                                Rl, Cn))
+        MT = np.ascontiguousarray(M.transpose(1, 0, 2))  # [Cn][R]
+        for hh in range(G):
+            assert (dst[hh].reshape(Cl, R, 4) == MT[hh * Cl:(hh + 1) * Cl]).all(), (G, hh)
