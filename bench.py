@@ -359,7 +359,11 @@ def run_ours(args):
     roofline = {
         "kernel": "msm_accum0_kernel (bucket accumulation, level 0)", "bound": "int32-multiply (IMAD pipe)",
         "achieved": mults / (acc_ms * 1e-3) / 1e12, "peak": mult_peak / 1e12, "unit": "Tmul/s",
-        "frac": mults / (acc_ms * 1e-3) / mult_peak, "traffic": None,
+        "frac": mults / (acc_ms * 1e-3) / mult_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at k=24, c=22 from the committed
+        # ncu --set full capture profiles/r1_final_msm_accum0_ntt_pass_k24_ncu_full.txt (28.79 GB + 0.72 GB)
+        "traffic": 29.52e9 if (k == 24 and c_win == 22) else None,
+        "mulmod_ceiling_frac": (adds * 10 / (acc_ms * 1e-3)) / (pipe["fr_mul"][1] or 1.0),
         "peak_source": "live register-only microbenchmark h2b_pipe_peak: plain IMAD.WIDE.U32 (32x32+64) rate",
         "algorithmic": f"n*W*{MULMODS_PER_ADD}*{MULTS_PER_MULMOD} 32x32 multiplies, n=2^{k}, c={c_win}, W={windows}",
         "kernel_ms": acc_ms, "ec_adds_per_s": adds / (acc_ms * 1e-3),
@@ -371,7 +375,9 @@ def run_ours(args):
     roofline_ntt = {
         "kernel": "ntt_pass_fast<8> (one radix-256 pass over HBM)", "bound": "hbm",
         "achieved": 64.0 * n / (slow * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": 64.0 * n / (slow * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+        "frac": 64.0 * n / (slow * 1e-3) / 1e9 / peaks["hbm_gbs"],
+        # same capture: 537.5 MB read + 491.5 MB written per pass at k=24 (= the algorithmic 2 x 512 MiB)
+        "traffic": 1.029e9 if k == 24 else None, "peak_source": peak_src,
         "algorithmic": f"64 B per element per pass (one read + one write), n=2^{k}", "pass_ms": pass_ms,
         "int_Tmul_s": (n / 2) * k * MULTS_PER_MULMOD / (sum(pass_ms) * 1e-3) / 1e12,
     }

@@ -405,3 +405,67 @@ def test_msm_k24_linearity(gpu_ctx):
     for x in (a, b):
         x.free()
     B.free()
+
+
+def test_concurrent_callers(oracle_c):
+    """The reference calls the transforms from rayon workers concurrently
+    (plonk/permutation/keygen.rs:214-234): one context per caller thread, results unchanged."""
+    import threading
+    k, n = 14, 3000
+    hs = np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    bases = oracle_c.g1_mul_gen(hs)
+    w = H.fr_enc([O.omega_for(k)])[0]
+    errors = []
+
+    def worker(seed):
+        try:
+            ctx = h.Context(0)
+            B = h.Bases(ctx, bases, n)
+            dom = h.EvaluationDomain(ctx, 5, k)
+            od = oracle_c.domain(5, k, 1)
+            for it in range(4):
+                a = H.rand_fr_limbs(seed * 10 + it, 1 << k)
+                got = a.copy()
+                ctx.best_fft(got, w.reshape(1, 4), k)
+                assert (got == oracle_c.best_fft(a, w, k, 1)).all()
+                assert (dom.coeff_to_extended(a) == od.coeff_to_extended(a)).all()
+                S = H.rand_fr_limbs(seed * 100 + it, n)
+                assert B.msm(S) == H.g1_dec(oracle_c.best_multiexp(S, bases, 1))[0]
+            od.free()
+            dom.free()
+            B.free()
+            ctx.close()
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
+def test_shared_context_is_serialised(gpu_ctx, oracle_c):
+    """Several threads on ONE context: calls are serialised by the library's lock."""
+    import threading
+    k = 12
+    w = H.fr_enc([O.omega_for(k)])[0]
+    errors = []
+
+    def worker(seed):
+        try:
+            for it in range(6):
+                a = H.rand_fr_limbs(seed * 10 + it, 1 << k)
+                got = a.copy()
+                gpu_ctx.best_fft(got, w.reshape(1, 4), k)
+                assert (got == oracle_c.best_fft(a, w, k, 1)).all()
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
