@@ -284,6 +284,79 @@ class Context:
             np.copyto(np.asarray(a).reshape(-1, 4), arr)
         return a
 
+    # ---- polynomial helpers: host arrays or DeviceBuffers ----
+    @staticmethod
+    def _fr_arg(x, n=None):
+        """(pointer, loc, count, keepalive) of a host limb array or a DeviceBuffer."""
+        if isinstance(x, DeviceBuffer):
+            if n is None:
+                raise H2BError(_ffi.H2B_ERR_ARG, "n required for device polynomials")
+            return x.ptr, H2B_DEVICE, n, x
+        arr = _fr_array(x)
+        return _ptr(arr), H2B_HOST, arr.shape[0] if n is None else n, arr
+
+    def eval_polynomial(self, poly, point: int, n: Optional[int] = None) -> int:
+        """arithmetic.rs:304 -- sum poly[i] * point^i."""
+        p, loc, n, _keep = self._fr_arg(poly, n)
+        x = fr_encode([point])
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(self.lib.h2b_eval_polynomial(self.h, p, loc, n, _ptr(x), _ptr(out)))
+        return fr_decode(out)[0]
+
+    def kate_division(self, a, b: int, n: Optional[int] = None, out: Optional[DeviceBuffer] = None):
+        """arithmetic.rs:348 -- a(X) / (X - b); host arrays in -> (n-1, 4) array out, DeviceBuffer in -> `out`."""
+        p, loc, n, _keep = self._fr_arg(a, n)
+        if n == 0:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "kate_division of an empty polynomial")
+        x = fr_encode([b])
+        if loc == H2B_DEVICE:
+            if out is None:
+                out = self.alloc(max(n - 1, 1) * 32)
+            self._check(self.lib.h2b_kate_division(self.h, p, loc, n, _ptr(x), out.ptr))
+            return out
+        q = np.zeros((n - 1, 4), dtype=np.uint64)
+        self._check(self.lib.h2b_kate_division(self.h, p, loc, n, _ptr(x), _ptr(q) if n > 1 else None))
+        return q
+
+    def inner_product(self, a, b, n: Optional[int] = None) -> int:
+        """arithmetic.rs:331 -- panics (H2B_ERR_LENGTH) if the lengths differ."""
+        pa, la, na, _ka = self._fr_arg(a, n)
+        pb, lb, nb, _kb = self._fr_arg(b, n)
+        if na != nb or la != lb:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert_eq!(a.len(), b.len())")  # :334
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(self.lib.h2b_inner_product(self.h, pa, pb, la, na, _ptr(out)))
+        return fr_decode(out)[0]
+
+    def _poly_binop(self, fn, lhs, rhs, n):
+        pl, ll, nl, keep = self._fr_arg(lhs, n)
+        pr, lr, nr, _k = self._fr_arg(rhs, n)
+        if nl != nr or ll != lr:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "polynomials of different length")
+        if ll == H2B_HOST:
+            keep = keep.copy()
+            pl = _ptr(keep)
+        self._check(fn(self.h, pl, pr, ll, nl))
+        return keep
+
+    def poly_add(self, lhs, rhs, n: Optional[int] = None):
+        """poly.rs:229 -- lhs + rhs (host: new array; DeviceBuffer: in place)."""
+        return self._poly_binop(self.lib.h2b_poly_add, lhs, rhs, n)
+
+    def poly_sub(self, lhs, rhs, n: Optional[int] = None):
+        """poly.rs:243"""
+        return self._poly_binop(self.lib.h2b_poly_sub, lhs, rhs, n)
+
+    def poly_scale(self, a, scalar: int, n: Optional[int] = None):
+        """poly.rs:278 -- a * scalar."""
+        p, loc, n, keep = self._fr_arg(a, n)
+        if loc == H2B_HOST:
+            keep = keep.copy()
+            p = _ptr(keep)
+        s = fr_encode([scalar])
+        self._check(self.lib.h2b_poly_scale(self.h, p, loc, n, _ptr(s)))
+        return keep
+
     def best_fft_device(self, buf: DeviceBuffer, omega, log_n: int, ncols: int = 1,
                         stride: Optional[int] = None) -> None:
         w = fr_encode([omega]) if isinstance(omega, int) else _fr_array(omega)

@@ -1,0 +1,267 @@
+// Device-resident polynomial helpers around the two hot paths (SURVEY.md 8f,
+// rank 2): the O(n) passes halo2_proofs runs on the host between the NTTs and
+// the commitments, so that a prover can keep its polynomials on the GPU.
+//
+//   eval_polynomial(poly, point)          halo2_proofs/src/arithmetic.rs:304-329
+//   compute_inner_product(a, b)           halo2_proofs/src/arithmetic.rs:331-345
+//   kate_division(a, b)                   halo2_proofs/src/arithmetic.rs:348-367
+//   Polynomial + / - / * scalar           halo2_proofs/src/poly.rs:229-305
+//
+// The reference evaluates with per-thread Horner chunks and divides with a
+// serial recurrence q_i = a_(i+1) + b q_(i+1).  Both are the suffix Horner scan
+//   S_i = a_i + x S_(i+1),  S_n = 0:   eval = S_0,  q_i = S_(i+1),
+// computed here as: per-thread Horner over 8 coefficients, a Hillis-Steele
+// suffix scan of the 256 thread totals in shared memory (step d multiplies by
+// x^(8*2^d)), block totals scanned recursively with x^2048, and a second
+// Horner sweep seeded with each thread's carry.  Exact field arithmetic: the
+// result is identical to the reference's whatever the association order.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace h2b {
+
+static const uint32_t kPolyE = 8;                // coefficients per thread
+static const uint32_t kPolyChunk = 256 * kPolyE;  // coefficients per block
+
+// Block b handles in[b*2048 .. +2048).  carry[b] (optional) is S at the end of the block.
+//   totals != null : totals[b] = S at the start of the block
+//   out    != null : out[i + out_shift] = S_i for every i of the block with 0 <= i + out_shift
+__global__ void __launch_bounds__(256)
+    poly_suffix_horner_kernel(const Fr* in, Fr* out, int64_t out_shift, uint64_t n, Fr x, Fr x8,
+                              const Fr* carry, Fr* totals) {
+  __shared__ Fr sc[256];
+  const uint32_t t = threadIdx.x;
+  const uint64_t base = (uint64_t)blockIdx.x * kPolyChunk + (uint64_t)t * kPolyE;
+  Fr a[kPolyE];
+#pragma unroll
+  for (uint32_t e = 0; e < kPolyE; ++e) a[e] = base + e < n ? ld_fp(in + base + e) : Fr::zero();
+  Fr v = a[kPolyE - 1];
+#pragma unroll
+  for (int e = (int)kPolyE - 2; e >= 0; --e) v = add(a[e], mul(x, v));
+  const Fr cb = carry ? ld_fp(carry + blockIdx.x) : Fr::zero();
+  if (t == 255 && carry) v = add(v, mul(x8, cb));  // the carry enters as the element after the block
+  sc[t] = v;
+  __syncthreads();
+  Fr pw = x8;
+  for (uint32_t off = 1; off < 256; off <<= 1) {
+    Fr other = Fr::zero();
+    const bool has = t + off < 256;
+    if (has) other = sc[t + off];
+    __syncthreads();
+    if (has) sc[t] = add(sc[t], mul(pw, other));
+    __syncthreads();
+    pw = sqr(pw);
+  }
+  if (totals && t == 0) st_fp(totals + blockIdx.x, sc[0]);
+  if (!out) return;
+  v = t < 255 ? sc[t + 1] : cb;
+#pragma unroll
+  for (int e = (int)kPolyE - 1; e >= 0; --e) {
+    v = add(a[e], mul(x, v));
+    const int64_t o = (int64_t)(base + e) + out_shift;
+    if (base + e < n && o >= 0) st_fp(out + o, v);
+  }
+}
+
+// op 0: a += b, 1: a -= b, 2: a *= s, 3: a = a * b (element-wise product, for inner products)
+__global__ void poly_elementwise_kernel(Fr* a, const Fr* b, uint64_t n, int op, Fr s) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const Fr x = ld_fp(a + i);
+    Fr r;
+    if (op == 0)
+      r = add(x, ld_fp(b + i));
+    else if (op == 1)
+      r = sub(x, ld_fp(b + i));
+    else if (op == 2)
+      r = mul(x, s);
+    else
+      r = mul(x, ld_fp(b + i));
+    st_fp(a + i, r);
+  }
+}
+
+// out[i] = a[i] * b[i] into a fresh buffer (inner product, first stage)
+__global__ void poly_product_kernel(const Fr* a, const Fr* b, Fr* out, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    st_fp(out + i, mul(ld_fp(a + i), ld_fp(b + i)));
+}
+
+static Fr fr_pow(Fr a, uint64_t e) { return pow_u64(a, e); }
+
+// S_0 of `in` (n coefficients) at x, left in d_tmp[0]; d_tmp holds ceil(n / 2048) + 2048 elements
+static int eval_device(h2b_ctx* ctx, const Fr* in, uint64_t n, Fr x, Fr* d_tmp, Fr** result) {
+  Fr* bufs[2] = {d_tmp, d_tmp + ((n + kPolyChunk - 1) / kPolyChunk + 1)};
+  int cur = 0;
+  const Fr* src = in;
+  uint64_t len = n;
+  while (true) {
+    const uint64_t nb = (len + kPolyChunk - 1) / kPolyChunk;
+    H2B_TRY(launch(ctx, poly_suffix_horner_kernel, dim3((uint32_t)nb), dim3(256), 0, src, (Fr*)nullptr,
+                   (int64_t)0, len, x, fr_pow(x, kPolyE), (const Fr*)nullptr, bufs[cur]));
+    if (nb == 1) break;
+    src = bufs[cur];
+    len = nb;
+    x = fr_pow(x, kPolyChunk);
+    cur ^= 1;
+  }
+  *result = bufs[cur];
+  return H2B_OK;
+}
+
+// Inclusive suffix scan written with out_shift; scratch d_tmp as above (sized for n).
+static int scan_device(h2b_ctx* ctx, const Fr* in, Fr* out, int64_t out_shift, uint64_t n, Fr x,
+                       Fr* d_tmp) {
+  const uint64_t nb = (n + kPolyChunk - 1) / kPolyChunk;
+  const Fr x8 = fr_pow(x, kPolyE);
+  if (nb == 1)
+    return launch(ctx, poly_suffix_horner_kernel, dim3(1), dim3(256), 0, in, out, out_shift, n, x, x8,
+                  (const Fr*)nullptr, (Fr*)nullptr);
+  // totals T_b, their inclusive scan C_b with x^2048, carry of block b = C_(b+1)
+  Fr* T = d_tmp;              // nb + 1 elements (the extra one is the zero carry of the last block)
+  Fr* Cs = d_tmp + (nb + 1);  // nb + 1
+  Fr* rest = Cs + (nb + 1);
+  H2B_TRY(launch(ctx, poly_suffix_horner_kernel, dim3((uint32_t)nb), dim3(256), 0, in, (Fr*)nullptr, (int64_t)0,
+                 n, x, x8, (const Fr*)nullptr, T));
+  H2B_CUDA(ctx, cudaMemsetAsync(Cs + nb, 0, sizeof(Fr), ctx->stream));
+  H2B_TRY(scan_device(ctx, T, Cs, 0, nb, fr_pow(x, kPolyChunk), rest));
+  return launch(ctx, poly_suffix_horner_kernel, dim3((uint32_t)nb), dim3(256), 0, in, out, out_shift, n, x, x8,
+                (const Fr*)(Cs + 1), (Fr*)nullptr);
+}
+
+static size_t poly_tmp_elems(uint64_t n) {
+  // T and Cs of every recursion level (geometric) + slack
+  size_t total = 0;
+  uint64_t len = n;
+  while (len > 1) {
+    const uint64_t nb = (len + kPolyChunk - 1) / kPolyChunk;
+    total += 2 * (nb + 1);
+    len = nb;
+  }
+  return total + 2 * kPolyChunk + 16;
+}
+
+}  // namespace h2b
+
+using namespace h2b;
+
+namespace {
+const Fr* as_fr(const h2b_fr* p) { return reinterpret_cast<const Fr*>(p); }
+Fr* as_fr(h2b_fr* p) { return reinterpret_cast<Fr*>(p); }
+
+// device view of a caller buffer (the pointer itself, or a staged copy of a host slice)
+int stage_in(h2b_ctx* ctx, int which, const h2b_fr* p, int loc, size_t count, const Fr** dev) {
+  if (loc == H2B_DEVICE) {
+    *dev = as_fr(p);
+    return H2B_OK;
+  }
+  H2B_TRY(ensure_stage(ctx, which, (count ? count : 1) * sizeof(Fr)));
+  H2B_CUDA(ctx, cudaMemcpyAsync(ctx->stage[which], p, count * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  *dev = reinterpret_cast<const Fr*>(ctx->stage[which]);
+  return H2B_OK;
+}
+}  // namespace
+
+extern "C" int h2b_eval_polynomial(h2b_ctx* ctx, const h2b_fr* poly, int loc, size_t n, const h2b_fr* point,
+                                   h2b_fr* out) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if ((!poly && n) || !point || !out) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (n == 0) {  // the fold over an empty slice is zero
+    memset(out, 0, sizeof(h2b_fr));
+    return H2B_OK;
+  }
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const Fr* d_in;
+  H2B_TRY(stage_in(ctx, 0, poly, loc, n, &d_in));
+  H2B_TRY(ensure_scratch(ctx, poly_tmp_elems(n) * sizeof(Fr)));
+  Fr* res;
+  H2B_TRY(eval_device(ctx, d_in, n, *as_fr(point), reinterpret_cast<Fr*>(ctx->scratch), &res));
+  H2B_CUDA(ctx, cudaMemcpyAsync(out, res, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
+extern "C" int h2b_kate_division(h2b_ctx* ctx, const h2b_fr* a, int loc, size_t n, const h2b_fr* b,
+                                 h2b_fr* q_out) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!a || !b || (!q_out && n > 1)) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (n == 0) return fail(ctx, H2B_ERR_LENGTH, "kate_division of an empty polynomial");  // a.len() - 1 underflows
+  if (n == 1) return H2B_OK;
+  if (loc == H2B_DEVICE && as_fr(q_out) == as_fr(a)) return fail(ctx, H2B_ERR_ARG, "aliased output");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const Fr* d_in;
+  H2B_TRY(stage_in(ctx, 0, a, loc, n, &d_in));
+  Fr* d_out = as_fr(q_out);
+  if (loc != H2B_DEVICE) {
+    H2B_TRY(ensure_stage(ctx, 1, (n - 1) * sizeof(Fr)));
+    d_out = reinterpret_cast<Fr*>(ctx->stage[1]);
+  }
+  H2B_TRY(ensure_scratch(ctx, poly_tmp_elems(n) * sizeof(Fr)));
+  // q_i = S_(i+1): the scan of a at b, shifted down by one
+  H2B_TRY(scan_device(ctx, d_in, d_out, -1, n, *as_fr(b), reinterpret_cast<Fr*>(ctx->scratch)));
+  if (loc != H2B_DEVICE)
+    H2B_CUDA(ctx, cudaMemcpyAsync(q_out, d_out, (n - 1) * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
+extern "C" int h2b_inner_product(h2b_ctx* ctx, const h2b_fr* a, const h2b_fr* b, int loc, size_t n,
+                                 h2b_fr* out) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if ((n && (!a || !b)) || !out) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (n == 0) {
+    memset(out, 0, sizeof(h2b_fr));
+    return H2B_OK;
+  }
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const Fr *da, *db;
+  H2B_TRY(stage_in(ctx, 0, a, loc, n, &da));
+  H2B_TRY(stage_in(ctx, 1, b, loc, n, &db));
+  H2B_TRY(ensure_scratch(ctx, (n + poly_tmp_elems(n)) * sizeof(Fr)));
+  Fr* prod = reinterpret_cast<Fr*>(ctx->scratch);
+  const uint64_t want = (n + 255) / 256, cap = (uint64_t)ctx->sm_count * 16;
+  H2B_TRY(launch(ctx, poly_product_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0, da, db, prod,
+                 (uint64_t)n));
+  Fr* res;
+  H2B_TRY(eval_device(ctx, prod, n, Fr::one(), prod + n, &res));  // Horner at 1 = the plain sum
+  H2B_CUDA(ctx, cudaMemcpyAsync(out, res, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
+static int poly_elementwise(h2b_ctx* ctx, h2b_fr* a, const h2b_fr* b, int loc, size_t n, int op, const h2b_fr* s) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (n && (!a || (op != 2 && !b) || (op == 2 && !s))) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (n == 0) return H2B_OK;
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const Fr* da_c;
+  H2B_TRY(stage_in(ctx, 0, a, loc, n, &da_c));
+  Fr* da = const_cast<Fr*>(da_c);
+  const Fr* db = nullptr;
+  if (op != 2) H2B_TRY(stage_in(ctx, 1, b, loc, n, &db));
+  Fr sc = Fr::zero();
+  if (s) memcpy(&sc, s, sizeof(Fr));
+  const uint64_t want = (n + 255) / 256, cap = (uint64_t)ctx->sm_count * 16;
+  H2B_TRY(launch(ctx, poly_elementwise_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0, da, db,
+                 (uint64_t)n, op, sc));
+  if (loc != H2B_DEVICE)
+    H2B_CUDA(ctx, cudaMemcpyAsync(a, da, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
+extern "C" int h2b_poly_add(h2b_ctx* ctx, h2b_fr* lhs, const h2b_fr* rhs, int loc, size_t n) {
+  return poly_elementwise(ctx, lhs, rhs, loc, n, 0, nullptr);
+}
+extern "C" int h2b_poly_sub(h2b_ctx* ctx, h2b_fr* lhs, const h2b_fr* rhs, int loc, size_t n) {
+  return poly_elementwise(ctx, lhs, rhs, loc, n, 1, nullptr);
+}
+extern "C" int h2b_poly_scale(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n, const h2b_fr* scalar) {
+  return poly_elementwise(ctx, a, nullptr, loc, n, 2, scalar);
+}

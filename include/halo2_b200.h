@@ -140,6 +140,21 @@ int h2b_extended_to_coeff_batch(h2b_domain* dom, const h2b_fr* in, size_t in_str
                                 size_t out_stride, int loc, uint32_t ncols,
                                 int divide_by_vanishing);
 
+/* ---- polynomial helpers around the hot paths (the O(n) host passes
+ * between the transforms and the commitments, so polynomials can stay on the device) ---- */
+/* eval_polynomial(poly, point): sum poly[i] * point^i                 arithmetic.rs:304 */
+int h2b_eval_polynomial(h2b_ctx* ctx, const h2b_fr* poly, int loc, size_t n, const h2b_fr* point,
+                        h2b_fr* out);
+/* kate_division(a, b): quotient of a(X) by (X - b), n - 1 coefficients, the remainder a(b) is
+ * dropped as in the reference; q_out has the same loc as a and must not alias it.  arithmetic.rs:348 */
+int h2b_kate_division(h2b_ctx* ctx, const h2b_fr* a, int loc, size_t n, const h2b_fr* b, h2b_fr* q_out);
+/* compute_inner_product(a, b)                                          arithmetic.rs:331 */
+int h2b_inner_product(h2b_ctx* ctx, const h2b_fr* a, const h2b_fr* b, int loc, size_t n, h2b_fr* out);
+/* Polynomial += / -= / *= scalar, in place on lhs                      poly.rs:229, 243, 278 */
+int h2b_poly_add(h2b_ctx* ctx, h2b_fr* lhs, const h2b_fr* rhs, int loc, size_t n);
+int h2b_poly_sub(h2b_ctx* ctx, h2b_fr* lhs, const h2b_fr* rhs, int loc, size_t n);
+int h2b_poly_scale(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n, const h2b_fr* scalar);
+
 /* Four-step pieces for ONE transform sharded over several GPUs (device pointers
  * only; no counterpart in the reference, which is single-process).  The host
  * side (halo2-pse_b200/dist.py) composes them with an all-to-all over NCCL:

@@ -388,6 +388,27 @@ def eval_polynomial(poly: Sequence[int], x: int) -> int:
     return acc
 
 
+def compute_inner_product(a: Sequence[int], b: Sequence[int]) -> int:
+    """arithmetic.rs:331-345."""
+    assert len(a) == len(b)  # :334
+    acc = 0
+    for x, y in zip(a, b):
+        acc = (acc + x * y) % R_MOD
+    return acc
+
+
+def kate_division(a: Sequence[int], b: int) -> List[int]:
+    """arithmetic.rs:348-367: divides a(X) by X - b, no remainder kept."""
+    b = (-b) % R_MOD  # :352
+    q = [0] * (len(a) - 1)
+    tmp = 0
+    for i in range(len(q) - 1, -1, -1):  # q.iter_mut().rev().zip(a.rev())
+        lead = (a[i + 1] - tmp) % R_MOD
+        q[i] = lead
+        tmp = lead * b % R_MOD
+    return q
+
+
 # --------------------------------------------------------------------------
 # KZG params (kzg/commitment.rs:61-129) -- only what commit/commit_lagrange need
 # --------------------------------------------------------------------------

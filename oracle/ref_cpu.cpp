@@ -694,6 +694,67 @@ int oracle_g1_mul_gen_u64(const uint64_t* ks, size_t n, int threads, uint64_t* o
   return 0;
 }
 
+// eval_polynomial                                                   arithmetic.rs:304-329
+int oracle_eval_polynomial(const uint64_t* poly, size_t n, const uint64_t* point, int threads, uint64_t* out) {
+  threads = clamp_threads(threads);
+  const Fr* p = reinterpret_cast<const Fr*>(poly);
+  Fr x;
+  memcpy(&x, point, 32);
+  auto evaluate = [&](const Fr* c, size_t len) {
+    Fr acc = Fr::zero();
+    for (size_t i = len; i-- > 0;) acc = fadd(fmul(acc, x), c[i]);
+    return acc;
+  };
+  Fr res = Fr::zero();
+  if (n * 2 < (size_t)threads) {
+    res = evaluate(p, n);
+  } else {
+    const size_t chunk = (n + threads - 1) / threads;
+    std::vector<Fr> parts(threads, Fr::zero());
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+      const size_t start = (size_t)t * chunk;
+      if (start >= n) break;
+      const size_t len = std::min(chunk, n - start);
+      pool.emplace_back([&, t, start, len]() {
+        const uint64_t e[4] = {start, 0, 0, 0};
+        parts[t] = fmul(evaluate(p + start, len), fpow(x, e));
+      });
+    }
+    for (auto& th : pool) th.join();
+    for (auto& v : parts) res = fadd(res, v);
+  }
+  memcpy(out, &res, 32);
+  return 0;
+}
+
+// kate_division (serial, as in the reference)                        arithmetic.rs:348-367
+int oracle_kate_division(const uint64_t* a, size_t n, const uint64_t* b, uint64_t* q) {
+  if (n == 0) return -1;
+  const Fr* A = reinterpret_cast<const Fr*>(a);
+  Fr* Q = reinterpret_cast<Fr*>(q);
+  Fr nb;
+  memcpy(&nb, b, 32);
+  nb = fneg(nb);
+  Fr tmp = Fr::zero();
+  for (size_t i = n - 1; i-- > 0;) {
+    const Fr lead = fsub(A[i + 1], tmp);
+    Q[i] = lead;
+    tmp = fmul(lead, nb);
+  }
+  return 0;
+}
+
+// compute_inner_product (serial, as in the reference)                arithmetic.rs:331-345
+int oracle_inner_product(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+  const Fr* A = reinterpret_cast<const Fr*>(a);
+  const Fr* B = reinterpret_cast<const Fr*>(b);
+  Fr acc = Fr::zero();
+  for (size_t i = 0; i < n; ++i) acc = fadd(acc, fmul(A[i], B[i]));
+  memcpy(out, &acc, 32);
+  return 0;
+}
+
 // Synthetic MSM bases for the CPU baseline: out[i] = [a + i*d] G (valid, distinct
 // points; an MSM's cost does not depend on the base values).  Each thread walks
 // its range with mixed additions and normalises with one batch inversion.

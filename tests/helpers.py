@@ -47,6 +47,9 @@ class OracleC:
         lib.oracle_field_op.argtypes = [I, I, P, P, P, SZ]
         lib.oracle_g1_mul_gen_u64.argtypes = [P, SZ, I, P]
         lib.oracle_synth_bases.argtypes = [C.c_uint64, C.c_uint64, SZ, I, P]
+        lib.oracle_eval_polynomial.argtypes = [P, SZ, P, I, P]
+        lib.oracle_kate_division.argtypes = [P, SZ, P, P]
+        lib.oracle_inner_product.argtypes = [P, P, SZ, P]
         self.lib = lib
 
     @staticmethod
@@ -79,6 +82,27 @@ class OracleC:
         k = np.ascontiguousarray(ks, dtype=np.uint64)
         out = np.zeros((k.shape[0], 8), dtype=np.uint64)
         self.lib.oracle_g1_mul_gen_u64(self._p(k), k.shape[0], threads, self._p(out))
+        return out
+
+    def eval_polynomial(self, poly: np.ndarray, point: np.ndarray, threads: int = 0) -> np.ndarray:
+        p = np.ascontiguousarray(poly, dtype=np.uint64).reshape(-1, 4)
+        x = np.ascontiguousarray(point, dtype=np.uint64).reshape(4)
+        out = np.zeros(4, dtype=np.uint64)
+        self.lib.oracle_eval_polynomial(self._p(p), p.shape[0], self._p(x), threads, self._p(out))
+        return out
+
+    def kate_division(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        x = np.ascontiguousarray(b, dtype=np.uint64).reshape(4)
+        q = np.zeros((a.shape[0] - 1, 4), dtype=np.uint64)
+        assert self.lib.oracle_kate_division(self._p(a), a.shape[0], self._p(x), self._p(q)) == 0
+        return q
+
+    def inner_product(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+        out = np.zeros(4, dtype=np.uint64)
+        self.lib.oracle_inner_product(self._p(a), self._p(b), a.shape[0], self._p(out))
         return out
 
     def synth_bases(self, n: int, a: int = 0x1234567, d: int = 0x9E3779B9, threads: int = 0) -> np.ndarray:

@@ -201,3 +201,40 @@ def test_kzg_commit_identity(emu_ctx):
     c1, c2 = P.commit(coeff), P.commit_lagrange(a)
     assert c1 == c2 and O.g1_to_bytes(c1).hex() == v["commitment"]
     d.free()
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 9, 2047, 2048, 2049, 5000, 70000])
+def test_poly_helpers(emu_ctx, oracle_c, n):
+    """eval_polynomial, kate_division, inner product, + / - / * scalar."""
+    a, b = H.rand_fr_limbs(n, n), H.rand_fr_limbs(n + 1, n)
+    x = random.Random(n).randrange(O.R_MOD)
+    X = H.fr_enc([x])[0]
+    assert emu_ctx.eval_polynomial(a, x) == H.fr_dec(oracle_c.eval_polynomial(a, X, 2))[0]
+    assert (emu_ctx.kate_division(a, x) == oracle_c.kate_division(a, X)).all()
+    assert emu_ctx.inner_product(a, b) == H.fr_dec(oracle_c.inner_product(a, b))[0]
+    assert (emu_ctx.poly_add(a, b) == oracle_c.field_op(0, 1, a, b)).all()
+    assert (emu_ctx.poly_sub(a, b) == oracle_c.field_op(0, 2, a, b)).all()
+    assert (emu_ctx.poly_scale(a, x) == oracle_c.field_op(0, 0, a, np.tile(X, (n, 1)))).all()
+    # device-resident forms
+    da, db = emu_ctx.upload_fr(a), emu_ctx.upload_fr(b)
+    assert emu_ctx.eval_polynomial(da, x, n=n) == emu_ctx.eval_polynomial(a, x)
+    if n > 1:
+        q = emu_ctx.kate_division(da, x, n=n)
+        assert (q.download(n - 1) == oracle_c.kate_division(a, X)).all()
+        q.free()
+    emu_ctx.poly_add(da, db, n=n)
+    assert (da.download(n) == oracle_c.field_op(0, 1, a, b)).all()
+    da.free()
+    db.free()
+
+
+def test_poly_helpers_edge_cases(emu_ctx):
+    assert emu_ctx.eval_polynomial(np.zeros((0, 4), dtype=np.uint64), 5) == 0
+    with pytest.raises(h.H2BError):
+        emu_ctx.kate_division(np.zeros((0, 4), dtype=np.uint64), 5)
+    with pytest.raises(h.H2BError) as e:  # assert_eq!(a.len(), b.len())  arithmetic.rs:334
+        emu_ctx.inner_product(H.rand_fr_limbs(0, 3), H.rand_fr_limbs(0, 4))
+    assert e.value.code == h.H2B_ERR_LENGTH
+    one = H.fr_enc([7])
+    assert emu_ctx.eval_polynomial(one, 12345) == 7
+    assert emu_ctx.kate_division(one, 3).shape == (0, 4)

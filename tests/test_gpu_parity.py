@@ -469,3 +469,56 @@ def test_shared_context_is_serialised(gpu_ctx, oracle_c):
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+# ---------------------------------------------------------------------------
+# polynomial helpers around the hot paths   arithmetic.rs:304-367, poly.rs:229-305
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 8, 9, 2047, 2048, 2049, 100000, 1 << 20])
+def test_poly_helpers_vs_oracle(gpu_ctx, oracle_c, n):
+    a, b = H.rand_fr_limbs(n, n), H.rand_fr_limbs(n + 1, n)
+    x = random.Random(n).randrange(O.R_MOD)
+    X = H.fr_enc([x])[0]
+    assert gpu_ctx.eval_polynomial(a, x) == H.fr_dec(oracle_c.eval_polynomial(a, X, 0))[0]
+    assert (gpu_ctx.kate_division(a, x) == oracle_c.kate_division(a, X)).all()
+    assert gpu_ctx.inner_product(a, b) == H.fr_dec(oracle_c.inner_product(a, b))[0]
+    assert (gpu_ctx.poly_add(a, b) == oracle_c.field_op(0, 1, a, b)).all()
+    assert (gpu_ctx.poly_sub(a, b) == oracle_c.field_op(0, 2, a, b)).all()
+    assert (gpu_ctx.poly_scale(a, x) == oracle_c.field_op(0, 0, a, np.tile(X, (n, 1)))).all()
+    da = gpu_ctx.upload_fr(a)
+    assert gpu_ctx.eval_polynomial(da, x, n=n) == gpu_ctx.eval_polynomial(a, x)
+    if n > 1:
+        q = gpu_ctx.kate_division(da, x, n=n)
+        assert (q.download(n - 1) == oracle_c.kate_division(a, X)).all()
+        q.free()
+    da.free()
+
+
+def test_poly_helpers_k24_properties(gpu_ctx):
+    """Full size: a(X) = q(X) (X - b) + a(b), checked at a random point with the device evaluator itself,
+    and eval at omega^j against the NTT output (two independent kernels must agree)."""
+    k = 24
+    n = 1 << k
+    rng = random.Random(5)
+    a = gpu_ctx.synth_scalars(n, 77, 0)
+    b, z = rng.randrange(O.R_MOD), rng.randrange(O.R_MOD)
+    q = gpu_ctx.kate_division(a, b, n=n)
+    ab, az, qz = gpu_ctx.eval_polynomial(a, b, n=n), gpu_ctx.eval_polynomial(a, z, n=n), \
+        gpu_ctx.eval_polynomial(q, z, n=n - 1)
+    assert (qz * (z - b) + ab) % O.R_MOD == az
+    w = O.omega_for(k)
+    j = 123457
+    ej = gpu_ctx.eval_polynomial(a, pow(w, j, O.R_MOD), n=n)
+    gpu_ctx.best_fft_device(a, w, k)
+    assert H.fr_dec(a.download(1, offset_bytes=j * 32))[0] == ej
+    for x in (a, q):
+        x.free()
+
+
+def test_poly_helpers_edge_cases(gpu_ctx):
+    assert gpu_ctx.eval_polynomial(np.zeros((0, 4), dtype=np.uint64), 5) == 0
+    with pytest.raises(h.H2BError):
+        gpu_ctx.kate_division(np.zeros((0, 4), dtype=np.uint64), 5)
+    with pytest.raises(h.H2BError) as e:  # arithmetic.rs:334
+        gpu_ctx.inner_product(H.rand_fr_limbs(0, 3), H.rand_fr_limbs(0, 4))
+    assert e.value.code == h.H2B_ERR_LENGTH

@@ -216,3 +216,22 @@ def test_c_oracle_vs_python_medium(oracle_c):
     want = O.g1_mul(O.G1_GEN, sum(c * h for c, h in zip(sc, hs)) % O.R_MOD)
     for threads in (1, 7):
         assert H.g1_dec(oracle_c.best_multiexp(H.fr_enc(sc), bases, threads))[0] == want
+
+
+def test_poly_helpers_oracles(oracle_c):
+    """eval_polynomial / kate_division / compute_inner_product (arithmetic.rs:304-367): Python vs C++ vs identities."""
+    rng = random.Random(21)
+    for n in (1, 2, 7, 33, 500):
+        a = H.rand_fr(rng, n)
+        b = H.rand_fr(rng, n)
+        x = rng.randrange(O.R_MOD)
+        ev = O.eval_polynomial(a, x)
+        assert ev == sum(c * pow(x, i, O.R_MOD) for i, c in enumerate(a)) % O.R_MOD
+        for threads in (1, 3, 64):
+            assert H.fr_dec(oracle_c.eval_polynomial(H.fr_enc(a), H.fr_enc([x])[0], threads))[0] == ev
+        assert H.fr_dec(oracle_c.inner_product(H.fr_enc(a), H.fr_enc(b)))[0] == O.compute_inner_product(a, b)
+        q = O.kate_division(a, x)
+        assert H.fr_dec(oracle_c.kate_division(H.fr_enc(a), H.fr_enc([x])[0])) == q
+        # a(X) = q(X) (X - x) + a(x): check at a random point
+        z = rng.randrange(O.R_MOD)
+        assert (O.eval_polynomial(q, z) * (z - x) + ev) % O.R_MOD == O.eval_polynomial(a, z)
