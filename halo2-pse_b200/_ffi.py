@@ -85,6 +85,8 @@ SYMBOLS = {
     "h2b_poly_add": (_I, [_P, _P, _P, _I, _SZ]),
     "h2b_poly_sub": (_I, [_P, _P, _P, _I, _SZ]),
     "h2b_poly_scale": (_I, [_P, _P, _I, _SZ, _P]),
+    "h2b_batch_invert": (_I, [_P, _P, _I, _SZ]),
+    "h2b_running_product": (_I, [_P, _P, _I, _SZ, _P, _P]),
     "h2b_fr_transpose_batch": (_I, [_P, _P, _P, _U32, _U32, _SZ, _U32, _SZ, _SZ]),
     "h2b_fr_transpose_scatter": (_I, [_P, _P, C.POINTER(_P), _U32, _U32, _U32, _U32]),
     "h2b_fr_permute3": (_I, [_P, _P, _P, _U32, _U32, _U32]),

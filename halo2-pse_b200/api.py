@@ -357,6 +357,28 @@ class Context:
         self._check(self.lib.h2b_poly_scale(self.h, p, loc, n, _ptr(s)))
         return keep
 
+    def batch_invert(self, a, n: Optional[int] = None):
+        """ff::BatchInvert (plonk/permutation/prover.rs:119): element-wise inverses, zeros stay zero."""
+        p, loc, n, keep = self._fr_arg(a, n)
+        if loc == H2B_HOST:
+            keep = keep.copy()
+            p = _ptr(keep)
+        self._check(self.lib.h2b_batch_invert(self.h, p, loc, n))
+        return keep
+
+    def running_product(self, f, init: int = 1, n: Optional[int] = None, out: Optional[DeviceBuffer] = None):
+        """z[0] = init, z[i] = z[i-1] * f[i-1] (plonk/permutation/prover.rs:152-158), n values."""
+        p, loc, n, _keep = self._fr_arg(f, n)
+        i0 = fr_encode([init])
+        if loc == H2B_DEVICE:
+            if out is None:
+                out = self.alloc(max(n, 1) * 32)
+            self._check(self.lib.h2b_running_product(self.h, p, loc, n, _ptr(i0), out.ptr))
+            return out
+        z = np.zeros((n, 4), dtype=np.uint64)
+        self._check(self.lib.h2b_running_product(self.h, p, loc, n, _ptr(i0), _ptr(z)))
+        return z
+
     def best_fft_device(self, buf: DeviceBuffer, omega, log_n: int, ncols: int = 1,
                         stride: Optional[int] = None) -> None:
         w = fr_encode([omega]) if isinstance(omega, int) else _fr_array(omega)

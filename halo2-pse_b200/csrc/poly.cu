@@ -6,6 +6,8 @@
 //   compute_inner_product(a, b)           halo2_proofs/src/arithmetic.rs:331-345
 //   kate_division(a, b)                   halo2_proofs/src/arithmetic.rs:348-367
 //   Polynomial + / - / * scalar           halo2_proofs/src/poly.rs:229-305
+//   batch_invert + the running product z[i] = z[i-1] * f[i-1] of the permutation / lookup grand
+//   products        halo2_proofs/src/plonk/permutation/prover.rs:119, 152-158
 //
 // The reference evaluates with per-thread Horner chunks and divides with a
 // serial recurrence q_i = a_(i+1) + b q_(i+1).  Both are the suffix Horner scan
@@ -89,7 +91,81 @@ __global__ void poly_product_kernel(const Fr* a, const Fr* b, Fr* out, uint64_t 
     st_fp(out + i, mul(ld_fp(a + i), ld_fp(b + i)));
 }
 
+// Exclusive running product: out[i] = carry[b] * prod_{j < i, j in block} in[j] (elements past n count as 1).
+//   totals != null : totals[b] = product of the block's elements
+//   out    != null : the running products of the block
+__global__ void __launch_bounds__(256)
+    poly_prefix_product_kernel(const Fr* in, Fr* out, uint64_t n, const Fr* carry, Fr* totals) {
+  __shared__ Fr sc[256];
+  const uint32_t t = threadIdx.x;
+  const uint64_t base = (uint64_t)blockIdx.x * kPolyChunk + (uint64_t)t * kPolyE;
+  Fr a[kPolyE];
+#pragma unroll
+  for (uint32_t e = 0; e < kPolyE; ++e) a[e] = base + e < n ? ld_fp(in + base + e) : Fr::one();
+  Fr v = a[0];
+#pragma unroll
+  for (uint32_t e = 1; e < kPolyE; ++e) v = mul(v, a[e]);
+  sc[t] = v;
+  __syncthreads();
+  for (uint32_t off = 1; off < 256; off <<= 1) {  // inclusive prefix products of the thread totals
+    Fr other = Fr::one();
+    const bool has = t >= off;
+    if (has) other = sc[t - off];
+    __syncthreads();
+    if (has) sc[t] = mul(other, sc[t]);
+    __syncthreads();
+  }
+  if (totals && t == 255) st_fp(totals + blockIdx.x, sc[255]);
+  if (!out) return;
+  v = ld_fp(carry + blockIdx.x);
+  if (t > 0) v = mul(v, sc[t - 1]);
+#pragma unroll
+  for (uint32_t e = 0; e < kPolyE; ++e) {
+    if (base + e < n) st_fp(out + base + e, v);
+    v = mul(v, a[e]);
+  }
+}
+
+// a[i] <- 1 / a[i] (zeros stay zero, as ff::BatchInvert): Montgomery's trick, one inversion per thread
+// over the strided elements it owns, prefix products parked in `pre`.
+__global__ void __launch_bounds__(128) poly_batch_invert_kernel(Fr* a, Fr* pre, uint64_t n) {
+  const uint64_t T = (uint64_t)gridDim.x * blockDim.x, t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  Fr run = Fr::one();
+  for (uint64_t i = t; i < n; i += T) {
+    const Fr x = ld_fp(a + i);
+    st_fp(pre + i, run);
+    if (!x.is_zero()) run = mul(run, x);
+  }
+  Fr inv_run = inv(run);
+  const uint64_t last = t + ((n - 1 - t) / T) * T;
+  for (int64_t i = (int64_t)last; i >= (int64_t)t; i -= (int64_t)T) {
+    const Fr x = ld_fp(a + i);
+    if (x.is_zero()) continue;
+    st_fp(a + i, mul(inv_run, ld_fp(pre + i)));
+    inv_run = mul(inv_run, x);
+  }
+}
+
 static Fr fr_pow(Fr a, uint64_t e) { return pow_u64(a, e); }
+
+// out[i] = init * prod_{j<i} in[j], i < n; d_tmp sized by poly_tmp_elems(n)
+static int prefix_product_device(h2b_ctx* ctx, const Fr* in, Fr* out, uint64_t n, const Fr& init, Fr* d_tmp) {
+  const uint64_t nb = (n + kPolyChunk - 1) / kPolyChunk;
+  Fr* T = d_tmp;              // nb + 1
+  Fr* Cx = d_tmp + (nb + 1);  // nb + 1
+  Fr* rest = Cx + (nb + 1);
+  if (nb == 1) {
+    H2B_CUDA(ctx, cudaMemcpyAsync(Cx, &init, sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `init` may live on the caller's stack
+    return launch(ctx, poly_prefix_product_kernel, dim3(1), dim3(256), 0, in, out, n, (const Fr*)Cx, (Fr*)nullptr);
+  }
+  H2B_TRY(launch(ctx, poly_prefix_product_kernel, dim3((uint32_t)nb), dim3(256), 0, in, (Fr*)nullptr, n,
+                 (const Fr*)nullptr, T));
+  H2B_TRY(prefix_product_device(ctx, T, Cx, nb, init, rest));
+  return launch(ctx, poly_prefix_product_kernel, dim3((uint32_t)nb), dim3(256), 0, in, out, n, (const Fr*)Cx,
+                (Fr*)nullptr);
+}
 
 // S_0 of `in` (n coefficients) at x, left in d_tmp[0]; d_tmp holds ceil(n / 2048) + 2048 elements
 static int eval_device(h2b_ctx* ctx, const Fr* in, uint64_t n, Fr x, Fr* d_tmp, Fr** result) {
@@ -264,4 +340,52 @@ extern "C" int h2b_poly_sub(h2b_ctx* ctx, h2b_fr* lhs, const h2b_fr* rhs, int lo
 }
 extern "C" int h2b_poly_scale(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n, const h2b_fr* scalar) {
   return poly_elementwise(ctx, a, nullptr, loc, n, 2, scalar);
+}
+
+extern "C" int h2b_batch_invert(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (n && !a) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (n == 0) return H2B_OK;
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const Fr* d_c;
+  H2B_TRY(stage_in(ctx, 0, a, loc, n, &d_c));
+  Fr* d = const_cast<Fr*>(d_c);
+  H2B_TRY(ensure_scratch(ctx, n * sizeof(Fr)));
+  // >= 256 elements per thread keep the Fermat inversion (381 multiplications) at ~1.5 per element
+  uint64_t threads = (n + 255) / 256;
+  const uint64_t cap = (uint64_t)ctx->sm_count * 4 * 128;
+  if (threads > cap) threads = cap;
+  const uint32_t blocks = (uint32_t)((threads + 127) / 128);
+  H2B_TRY(launch(ctx, poly_batch_invert_kernel, dim3(blocks), dim3(128), 0, d, reinterpret_cast<Fr*>(ctx->scratch),
+                 (uint64_t)n));
+  if (loc != H2B_DEVICE)
+    H2B_CUDA(ctx, cudaMemcpyAsync(a, d, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
+extern "C" int h2b_running_product(h2b_ctx* ctx, const h2b_fr* in, int loc, size_t n, const h2b_fr* init,
+                                   h2b_fr* out) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (n && (!in || !out || !init)) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (n == 0) return H2B_OK;
+  if (loc == H2B_DEVICE && as_fr(out) == as_fr(in)) return fail(ctx, H2B_ERR_ARG, "aliased output");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const Fr* d_in;
+  H2B_TRY(stage_in(ctx, 0, in, loc, n, &d_in));
+  Fr* d_out = as_fr(out);
+  if (loc != H2B_DEVICE) {
+    H2B_TRY(ensure_stage(ctx, 1, n * sizeof(Fr)));
+    d_out = reinterpret_cast<Fr*>(ctx->stage[1]);
+  }
+  H2B_TRY(ensure_scratch(ctx, poly_tmp_elems(n) * sizeof(Fr)));
+  Fr i0;
+  memcpy(&i0, init, sizeof(Fr));
+  H2B_TRY(prefix_product_device(ctx, d_in, d_out, n, i0, reinterpret_cast<Fr*>(ctx->scratch)));
+  if (loc != H2B_DEVICE)
+    H2B_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
 }

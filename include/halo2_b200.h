@@ -155,6 +155,12 @@ int h2b_poly_add(h2b_ctx* ctx, h2b_fr* lhs, const h2b_fr* rhs, int loc, size_t n
 int h2b_poly_sub(h2b_ctx* ctx, h2b_fr* lhs, const h2b_fr* rhs, int loc, size_t n);
 int h2b_poly_scale(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n, const h2b_fr* scalar);
 
+/* The two data-parallel pieces of the grand-product constructions:
+ * a[i] <- 1/a[i] in place, zeros stay zero (ff::BatchInvert, plonk/permutation/prover.rs:119), and
+ * out[0] = init, out[i] = out[i-1] * in[i-1] for i < n (plonk/permutation/prover.rs:152-158). */
+int h2b_batch_invert(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n);
+int h2b_running_product(h2b_ctx* ctx, const h2b_fr* in, int loc, size_t n, const h2b_fr* init, h2b_fr* out);
+
 /* Four-step pieces for ONE transform sharded over several GPUs (device pointers
  * only; no counterpart in the reference, which is single-process).  The host
  * side (halo2-pse_b200/dist.py) composes them with an all-to-all over NCCL:

@@ -238,3 +238,28 @@ def test_poly_helpers_edge_cases(emu_ctx):
     one = H.fr_enc([7])
     assert emu_ctx.eval_polynomial(one, 12345) == 7
     assert emu_ctx.kate_division(one, 3).shape == (0, 4)
+
+
+@pytest.mark.parametrize("n", [1, 2, 9, 2048, 2049, 5000, 40000])
+def test_grand_product_pieces(emu_ctx, oracle_c, n):
+    """batch_invert and the running product of the permutation argument."""
+    rng = random.Random(n)
+    vals = H.rand_fr(rng, n)
+    for i in range(0, n, 7):
+        vals[i] = 0  # zeros stay zero (ff::BatchInvert skips them)
+    a = H.fr_enc(vals)
+    inv = emu_ctx.batch_invert(a)
+    assert H.fr_dec(inv) == [pow(v, -1, O.R_MOD) if v else 0 for v in vals]
+    f = H.rand_fr(rng, n)
+    init = rng.randrange(O.R_MOD)
+    z = emu_ctx.running_product(H.fr_enc(f), init)
+    want, cur = [], init
+    for i in range(n):
+        want.append(cur)
+        cur = cur * f[i] % O.R_MOD
+    assert H.fr_dec(z) == want
+    d = emu_ctx.upload_fr(H.fr_enc(f))
+    zd = emu_ctx.running_product(d, init, n=n)
+    assert (zd.download(n) == z).all()
+    d.free()
+    zd.free()

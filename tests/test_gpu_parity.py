@@ -522,3 +522,26 @@ def test_poly_helpers_edge_cases(gpu_ctx):
     with pytest.raises(h.H2BError) as e:  # arithmetic.rs:334
         gpu_ctx.inner_product(H.rand_fr_limbs(0, 3), H.rand_fr_limbs(0, 4))
     assert e.value.code == h.H2B_ERR_LENGTH
+
+
+@pytest.mark.parametrize("n", [1, 2, 9, 2048, 2049, 100000, 1 << 20])
+def test_grand_product_pieces(gpu_ctx, oracle_c, n):
+    """batch_invert (zeros stay zero) and z[i] = z[i-1] * f[i-1]
+    (plonk/permutation/prover.rs:119, 152-158)."""
+    a = H.rand_fr_limbs(n, n)
+    a[::7] = 0
+    inv = gpu_ctx.batch_invert(a)
+    want = oracle_c.field_op(0, 7, a, a)  # Fermat inverse, 0 -> 0
+    assert (inv == want).all()
+    assert (oracle_c.field_op(0, 0, inv[1:2], a[1:2]) == H.fr_enc([1])).all() if n > 1 else True
+    f = H.rand_fr_limbs(n + 5, n)
+    z = gpu_ctx.running_product(f, 1)
+    # z[i+1] = z[i] * f[i] everywhere (one vectorised oracle multiplication), z[0] = 1
+    assert (z[0] == H.fr_enc([1])[0]).all()
+    if n > 1:
+        assert (z[1:] == oracle_c.field_op(0, 0, z[:-1], f[:-1])).all()
+    d = gpu_ctx.upload_fr(f)
+    zd = gpu_ctx.running_product(d, 1, n=n)
+    assert (zd.download(n) == z).all()
+    d.free()
+    zd.free()
