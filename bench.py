@@ -300,6 +300,21 @@ def run_ours(args):
     msm = D.ShardedMSM(ctx, bases)
     ctx.sync()
 
+    # sanity of the sharded path on this very process group (cheap, untimed): the first 2^12 points of
+    # every rank against the closed form  sum_i c_i [h_i] G = [sum_i c_i h_i] G  over ALL ranks' ranges
+    m = 1 << 12
+    got = msm.msm(scalars, m)
+    cs = h.fr_decode(scalars.download(m))
+    part = sum(c * ctx.synth_base_scalar(0x6B7A67 + rank, i) for i, c in enumerate(cs)) % h.R_MOD
+    if world > 1:
+        parts = [None] * world
+        torch.distributed.all_gather_object(parts, part)
+        part = sum(parts) % h.R_MOD
+    gen = h.Bases(ctx, h.g1_encode([(1, 2)]), 1)
+    want = gen.msm(h.fr_encode([part]))  # [t] G through the library's own scalar multiplication
+    gen.free()
+    sharded_ok = got == want
+
     def step_device():
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -483,7 +498,7 @@ def run_ours(args):
                     "ntt": {"value": world * n * e2e_steps / (e_ntt * 1e-3) / 1e6, "unit": "Melem/s"},
                     "ms_per_step": e2e_wall / e2e_steps,
                     "path": "h2b_msm_affine + h2b_best_fft with H2B_HOST pointers (pinned), copies inside the timed region"},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks, "sharded_msm_closed_form_check": bool(sharded_ok),
         }
         if four:
             line["four_step_ntt"] = four

@@ -99,6 +99,7 @@ inline int fail(h2b_ctx* ctx, int code, const std::string& msg) {
       char _b[512];                                                                      \
       snprintf(_b, sizeof _b, "%s:%d %s: %s", __FILE__, __LINE__, #expr,                 \
                cudaGetErrorString(_e));                                                  \
+      cudaGetLastError(); /* clear the non-sticky error so that later launches are not blamed */ \
       return h2b::fail((ctx), _e == cudaErrorMemoryAllocation ? H2B_ERR_OOM : H2B_ERR_CUDA, _b); \
     }                                                                                    \
   } while (0)

@@ -545,3 +545,16 @@ def test_grand_product_pieces(gpu_ctx, oracle_c, n):
     assert (zd.download(n) == z).all()
     d.free()
     zd.free()
+
+
+def test_allocation_failure_is_an_error_code(gpu_ctx):
+    """A failed device allocation comes back as H2B_ERR_OOM, never as a crash or a CPU fallback."""
+    with pytest.raises(h.H2BError) as e:
+        gpu_ctx.alloc(1 << 46)
+    assert e.value.code in (h.H2B_ERR_OOM, h.H2B_ERR_CUDA)
+    # the context stays usable afterwards
+    a = H.rand_fr_limbs(1, 256)
+    w = H.fr_enc([O.omega_for(8)])
+    b = a.copy()
+    gpu_ctx.best_fft(b, w, 8)
+    assert not (a == b).all()
