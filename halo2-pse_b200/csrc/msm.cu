@@ -998,9 +998,15 @@ extern "C" int h2b_bases_precompute(h2b_ctx* ctx, h2b_bases* b, uint32_t window_
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
   uint32_t c = window_bits;
   if (c == 0) {
-    const uint32_t k = ceil_log2(b->n < 2 ? 2 : b->n);
-    c = k < 10 ? 8 : (k - 2 > 24 ? 24 : k - 2);
-    if (k >= 22 && k <= 25) c = 22;
+    // minimise  n * ceil(255 / c)  bucket additions  +  ~2.8 * 2^(c-1)  addition-equivalents of bucket reduction
+    double best = 0;
+    for (uint32_t cc = 8; cc <= 24; ++cc) {
+      const double cost = (double)b->n * ((255 + cc - 1) / cc) + 2.8 * (double)(1u << (cc - 1));
+      if (c == 0 || cost < best) {
+        best = cost;
+        c = cc;
+      }
+    }
   }
   if (c < 2 || c > 24) return fail(ctx, H2B_ERR_ARG, "window_bits out of range");
   const uint32_t W = (255 + c - 1) / c;

@@ -148,7 +148,8 @@ def test_msm_vs_oracle(emu_ctx, oracle_c, n, kind, monkeypatch):
     if n >= 1024:  # window table: all windows share one bucket set
         for c in (0, 5, 11):
             B.precompute(c)
-            assert B.table_window_bits == (c or 9)
+            auto = min(range(8, 25), key=lambda cc: (n * ((255 + cc - 1) // cc) + 2.8 * (1 << (cc - 1)), cc))
+            assert B.table_window_bits == (c or auto)
             monkeypatch.setenv("H2B_MSM_ACC", "affine" if c else "xyzz")
             assert B.msm(S) == got
             assert B.msm(S[:1100], offset=200) == H.g1_dec(oracle_c.best_multiexp(S[:1100], bases[200:1300], 2))[0]
