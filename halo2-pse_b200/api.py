@@ -455,6 +455,45 @@ class ParamsKZG:
         self.g = g if isinstance(g, Bases) else Bases(ctx, g, self.n)
         self.g_lagrange = g_lagrange if isinstance(g_lagrange, Bases) else Bases(ctx, g_lagrange, self.n)
 
+    @classmethod
+    def setup(cls, ctx: Context, k: int, s: int, precompute: bool = False) -> "ParamsKZG":
+        """ParamsKZG::setup (poly/kzg/commitment.rs:61-129) with the toxic secret `s` given instead of
+        drawn from an rng (MUST NOT be used in production, as the reference says): g[i] = [s^i] G and
+        g_lagrange[i] = [(s^n - 1)/n * w^i / (s - w^i)] G.  The O(n) scalar bookkeeping is host integers;
+        the 2n scalar multiplications run on the GPU."""
+        if k > 28:
+            raise H2BError(_ffi.H2B_ERR_ARG, "assert!(k <= E::Scalar::S)")  # :64
+        r = R_MOD
+        n = 1 << k
+        root = pow(pow(7, (r - 1) >> 28, r), 1 << (28 - k), r)  # :90-93
+        powers, roots = [1] * n, [1] * n
+        for i in range(1, n):
+            powers[i] = powers[i - 1] * s % r
+            roots[i] = roots[i - 1] * root % r
+        multiplier = (pow(s, n, r) - 1) * pow(n, -1, r) % r  # :96
+        dens = [(s - w) % r for w in roots]
+        # one inversion for all denominators (Montgomery's trick)
+        pre, run = [1] * n, 1
+        for i in range(n):
+            pre[i] = run
+            run = run * dens[i] % r
+        inv = pow(run, -1, r)
+        lag = [0] * n
+        for i in range(n - 1, -1, -1):
+            lag[i] = multiplier * roots[i] % r * (inv * pre[i] % r) % r  # :101-102
+            inv = inv * dens[i] % r
+        out = []
+        for scalars in (powers, lag):
+            sc = fr_encode(scalars)
+            buf = ctx.alloc(n * 64)
+            ctx._check(ctx.lib.h2b_g1_mul_generator(ctx.h, _ptr(sc), H2B_HOST, n, buf.ptr, H2B_DEVICE))
+            b = Bases(ctx, buf.ptr, n, H2B_DEVICE)
+            buf.free()
+            if precompute:
+                b.precompute()
+            out.append(b)
+        return cls(ctx, k, out[0], out[1])
+
     def commit(self, poly, blind=None):
         """:327-334 -- blind is accepted and ignored, as in the reference."""
         a = _fr_array(poly)

@@ -952,6 +952,66 @@ __global__ void __launch_bounds__(128)
 // ===========================================================================
 using namespace h2b;
 
+// ---------------------------------------------------------------------------
+// [k_i] G for many scalars: the 2 * 2^k scalar multiplications of ParamsKZG::setup
+// (poly/kzg/commitment.rs:67-116), double-and-add per thread, one batched
+// normalisation.  Not a hot path of the prover; it makes test / benchmark SRS
+// generation a GPU job instead of minutes of CPU time.
+// ---------------------------------------------------------------------------
+namespace h2b {
+__global__ void __launch_bounds__(128)
+    g1_mul_generator_kernel(const Fr* scalars, G1Xyzz* out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr k = from_mont(ld_fp(scalars + i));
+  G1Affine g;
+  g.x = Fq::one();
+  g.y = add(Fq::one(), Fq::one());
+  G1Xyzz acc = G1Xyzz::identity();
+  bool started = false;
+  for (int limb = 7; limb >= 0; --limb) {
+    for (int bit = 31; bit >= 0; --bit) {
+      if (started) acc = xyzz_double(acc);
+      if ((k.v[limb] >> bit) & 1) {
+        xyzz_add_affine(acc, g);
+        started = true;
+      }
+    }
+  }
+  st_xyzz(out + i, acc);
+}
+}  // namespace h2b
+
+extern "C" int h2b_g1_mul_generator(h2b_ctx* ctx, const h2b_fr* scalars, int loc, size_t n,
+                                    h2b_g1_affine* out, int out_loc) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (n && (!scalars || !out)) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (n == 0) return H2B_OK;
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const Fr* d_sc = reinterpret_cast<const Fr*>(scalars);
+  if (loc != H2B_DEVICE) {
+    H2B_TRY(ensure_stage(ctx, 0, n * sizeof(Fr)));
+    H2B_CUDA(ctx, cudaMemcpyAsync(ctx->stage[0], scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    d_sc = reinterpret_cast<const Fr*>(ctx->stage[0]);
+  }
+  G1Affine* d_out = reinterpret_cast<G1Affine*>(out);
+  if (out_loc != H2B_DEVICE) {
+    H2B_TRY(ensure_stage(ctx, 1, n * sizeof(G1Affine)));
+    d_out = reinterpret_cast<G1Affine*>(ctx->stage[1]);
+  }
+  H2B_TRY(ensure_scratch(ctx, n * sizeof(G1Xyzz)));
+  G1Xyzz* tmp = reinterpret_cast<G1Xyzz*>(ctx->scratch);
+  H2B_TRY(launch(ctx, g1_mul_generator_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, d_sc, tmp,
+                 (uint64_t)n));
+  const uint32_t nblk = (uint32_t)(((n + kNormBatch - 1) / kNormBatch + 127) / 128);
+  H2B_TRY(launch(ctx, msm_table_normalize_kernel, dim3(nblk), dim3(128), 0, (const G1Xyzz*)tmp, d_out, (uint64_t)n));
+  if (out_loc != H2B_DEVICE)
+    H2B_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
 extern "C" int h2b_bases_upload(h2b_ctx* ctx, const h2b_g1_affine* bases, size_t n, int loc,
                                 h2b_bases** out) {
   if (!ctx) return H2B_ERR_ARG;

@@ -92,6 +92,10 @@ int h2b_best_multiexp(h2b_ctx* ctx, const h2b_fr* coeffs, const h2b_g1_affine* b
 /* signed-digit window width c the Pippenger kernels use for an n-point MSM
  * (ceil(255 / c) windows of 2^(c-1) buckets) */
 uint32_t h2b_msm_window_bits(size_t n);
+/* out[i] = [scalars[i]] G for the generator G = (1, 2): the scalar multiplications of
+ * ParamsKZG::setup (poly/kzg/commitment.rs:67-116), affine outputs (identity = (0, 0)). */
+int h2b_g1_mul_generator(h2b_ctx* ctx, const h2b_fr* scalars, int loc, size_t n, h2b_g1_affine* out,
+                         int out_loc);
 /* out = sum of n affine points, on the host: the fold of per-chunk partial sums
  * (arithmetic.rs:153) when an MSM is sharded by point range across GPUs. */
 int h2b_g1_sum(const h2b_g1_affine* pts, size_t n, h2b_g1_affine* out);

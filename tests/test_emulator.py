@@ -264,3 +264,22 @@ def test_grand_product_pieces(emu_ctx, oracle_c, n):
     assert (zd.download(n) == z).all()
     d.free()
     zd.free()
+
+
+def test_kzg_setup_on_device(emu_ctx):
+    """ParamsKZG::setup (kzg/commitment.rs:61-129): the golden k=4 SRS, and the reference's own test
+    identity commit(lagrange_to_coeff(a)) == commit_lagrange(a) (:361-384) on it."""
+    v = KAT["kzg"]
+    P = h.ParamsKZG.setup(emu_ctx, v["k"], int(v["s"], 16))
+    assert P.g.download().tobytes().hex() == v["g"]
+    assert P.g_lagrange.download().tobytes().hex() == v["g_lagrange"]
+    d = h.EvaluationDomain(emu_ctx, 2, v["k"])
+    a = _np(v["lagrange"], 4)
+    assert P.commit(d.lagrange_to_coeff(a)) == P.commit_lagrange(a)
+    assert O.g1_to_bytes(P.commit_lagrange(a)).hex() == v["commitment"]
+    d.free()
+    # scalar edge cases of the fixed-base multiplication: 0, 1, r - 1
+    sc = H.fr_enc([0, 1, 2, O.R_MOD - 1])
+    out = np.zeros((4, 8), dtype=np.uint64)
+    emu_ctx._check(emu_ctx.lib.h2b_g1_mul_generator(emu_ctx.h, sc.ctypes.data, h.H2B_HOST, 4, out.ctypes.data, h.H2B_HOST))
+    assert H.g1_dec(out) == [None, O.G1_GEN, O.g1_mul(O.G1_GEN, 2), O.g1_neg(O.G1_GEN)]

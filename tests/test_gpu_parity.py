@@ -558,3 +558,21 @@ def test_allocation_failure_is_an_error_code(gpu_ctx):
     b = a.copy()
     gpu_ctx.best_fft(b, w, 8)
     assert not (a == b).all()
+
+
+def test_kzg_setup_and_commit_identity(gpu_ctx, oracle_c):
+    """ParamsKZG::setup on the device (kzg/commitment.rs:61-129) against the golden k=4 SRS, then the
+    reference's own test (:361-384) at k = 6 (its size) and k = 14 with the window table."""
+    v = KAT["kzg"]
+    P = h.ParamsKZG.setup(gpu_ctx, v["k"], int(v["s"], 16))
+    assert P.g.download().tobytes().hex() == v["g"]
+    assert P.g_lagrange.download().tobytes().hex() == v["g_lagrange"]
+    for k, pre in ((6, False), (14, True)):
+        P = h.ParamsKZG.setup(gpu_ctx, k, 0x1234567 + k, precompute=pre)
+        d = h.EvaluationDomain(gpu_ctx, 2, k)
+        a = H.rand_fr_limbs(k, 1 << k)
+        c1, c2 = P.commit(d.lagrange_to_coeff(a)), P.commit_lagrange(a)
+        assert c1 == c2 and c1 is not None
+        # and against the CPU oracle on the same (downloaded) bases
+        assert c2 == H.g1_dec(oracle_c.best_multiexp(a, P.g_lagrange.download(), 0))[0]
+        d.free()
