@@ -568,13 +568,27 @@ static MsmPlan msm_plan(size_t n, uint32_t table_c = 0) {
   p.nb_per_window = 1u << (p.c - 1);
   p.kb = ceil_log2((uint64_t)p.Wb * p.nb_per_window);
   p.pairs = (uint64_t)n * p.W;
-  p.L0 = p.pairs >= (1ull << 24) ? 64 : 32;
+  // chunk length of level 0: long enough to amortise the two boundary partials, short enough to
+  // keep >= ~64k threads in flight (tuned on B200: k = 16 / 18 / 20 / 24)
+  p.L0 = p.pairs >= (1ull << 25) ? 128 : p.pairs >= (1ull << 23) ? 64 : p.pairs >= (1ull << 21) ? 32 : 16;
   if (const char* e = getenv("H2B_MSM_L0")) {
     const int v = atoi(e);
     if (v >= 2 && v <= 4096) p.L0 = (uint32_t)v;
   }
   p.LN = 16;
-  p.lM = p.c - 1 < 5 ? p.c - 1 : 5;
+  if (const char* e = getenv("H2B_MSM_LN")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= 4096) p.LN = (uint32_t)v;
+  }
+  {  // buckets per reduction segment: ~2^15 segments or more, 8..64 buckets each (tuned likewise)
+    const int lb = (int)ceil_log2((uint64_t)p.Wb * p.nb_per_window) - 15;
+    p.lM = (uint32_t)(lb < 3 ? 3 : (lb > 6 ? 6 : lb));
+    if (p.lM > p.c - 1) p.lM = p.c - 1;
+  }
+  if (const char* e = getenv("H2B_MSM_LM")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 10 && (uint32_t)v <= p.c - 1) p.lM = (uint32_t)v;
+  }
   p.nseg = p.nb_per_window >> p.lM;
   return p;
 }
