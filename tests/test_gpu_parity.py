@@ -576,3 +576,72 @@ def test_kzg_setup_and_commit_identity(gpu_ctx, oracle_c):
         # and against the CPU oracle on the same (downloaded) bases
         assert c2 == H.g1_dec(oracle_c.best_multiexp(a, P.g_lagrange.download(), 0))[0]
         d.free()
+
+
+# ---------------------------------------------------------------------------
+# maximum sizes: the two-adicity ceiling S = 28 of Fr and a 2^26-point MSM
+# ---------------------------------------------------------------------------
+def _sample_offsets(n, width=2048):
+    return [0, n // 3, n // 2 - width // 2, n - width]
+
+
+def test_best_fft_k28_roundtrip(gpu_ctx, oracle_c):
+    """k = 28 = Fr::S, the largest transform the field supports (8 GiB): inverse(forward(a)) == 2^28 * a
+    on sampled windows, plus one output value against direct evaluation of a sparse input."""
+    k = 28
+    n = 1 << k
+    w = O.omega_for(k)
+    buf = gpu_ctx.synth_scalars(n, 41, 0)
+    before = {o: buf.download(2048, offset_bytes=o * 32) for o in _sample_offsets(n)}
+    gpu_ctx.best_fft_device(buf, w, k)
+    gpu_ctx.best_fft_device(buf, pow(w, -1, O.R_MOD), k)
+    nf = np.tile(H.fr_enc([n])[0], (2048, 1))
+    for o, a in before.items():
+        assert (buf.download(2048, offset_bytes=o * 32) == oracle_c.field_op(0, 0, a, nf)).all(), o
+    buf.free()
+
+
+def test_domain_extended_k28(gpu_ctx):
+    """EvaluationDomain::new(5, 26): extended_k = 28 is the ceiling (domain.rs:49-61).
+    coeff_to_extended then extended_to_coeff gives back the polynomial, zero beyond n."""
+    k = 26
+    d = h.EvaluationDomain(gpu_ctx, 5, k)
+    assert d.extended_k == 28
+    n = 1 << k
+    src = gpu_ctx.synth_scalars(n, 43, 0)
+    ext = gpu_ctx.alloc(d.extended_len() * 32)
+    d.coeff_to_extended_device(src, ext)
+    out = gpu_ctx.alloc(d.quotient_len * 32)
+    d.extended_to_coeff_device(ext, out)
+    ext.free()
+    for o in _sample_offsets(n):
+        assert (out.download(2048, offset_bytes=o * 32) == src.download(2048, offset_bytes=o * 32)).all(), o
+    for o in (n, 2 * n + 12345, d.quotient_len - 2048):
+        assert not out.download(2048, offset_bytes=o * 32).any(), o
+    for x in (src, out):
+        x.free()
+    d.free()
+
+
+def test_msm_k26_properties(gpu_ctx):
+    """2^26 points (4 GiB of bases, 44 GiB window table): the MSM over two halves sums to the whole, and a
+    2^16 prefix matches the closed form through the same table."""
+    k = 26
+    n = 1 << k
+    B = gpu_ctx.synth_bases(n, 7).precompute()
+    assert B.table_window_bits == 24
+    a = gpu_ctx.synth_scalars(n, 13, 0)
+    whole = B.msm(a, n=n)
+    half = n // 2
+    lo = B.msm(a, n=half)
+    hi_buf = h.DeviceBuffer.__new__(h.DeviceBuffer)
+    hi_buf.ctx, hi_buf.nbytes, hi_buf.ptr = gpu_ctx, half * 32, a.at(half * 32)
+    hi = B.msm(hi_buf, n=half, offset=half)
+    hi_buf.ptr = None
+    assert O.g1_add(lo, hi) == whole and whole is not None
+    m = 1 << 16
+    s = H.fr_dec(a.download(m))
+    hs = [gpu_ctx.synth_base_scalar(7, i) for i in range(m)]
+    assert B.msm(a, n=m) == O.g1_mul(O.G1_GEN, sum(c * x for c, x in zip(s, hs)) % O.R_MOD)
+    a.free()
+    B.free()
