@@ -544,7 +544,11 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
   }
 
   // Scratch holds the intermediate passes of a group of batch members.
-  const uint64_t kScratchCap = 8ull << 30;
+  uint64_t kScratchCap = 8ull << 30;
+  if (const char* e = getenv("H2B_NTT_SCRATCH_CAP")) {  // tests: force several column groups
+    const long long v = atoll(e);
+    if (v > 0) kScratchCap = (uint64_t)v;
+  }
   uint32_t group = batch;
   if (P > 1) {
     const uint64_t per = n * sizeof(Fr);

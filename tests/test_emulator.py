@@ -91,7 +91,8 @@ def test_domain_length_checks(emu_ctx):
     d.free()
 
 
-def test_batched_domain_transforms(emu_ctx, oracle_c):
+def test_batched_domain_transforms(emu_ctx, oracle_c, monkeypatch):
+    monkeypatch.setenv("H2B_NTT_SCRATCH_CAP", str(2 * (1 << 9) * 32))  # two columns per group: 3 columns -> 2 groups
     j, k, ncols = 5, 7, 3
     d = h.EvaluationDomain(emu_ctx, j, k)
     od = oracle_c.domain(j, k, 2)

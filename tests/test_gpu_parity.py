@@ -221,9 +221,13 @@ def test_domain_length_checks(gpu_ctx):
         h.EvaluationDomain(gpu_ctx, 9, 27)
 
 
-def test_domain_batched_64_columns(gpu_ctx, oracle_c):
-    """configs[2]: coset NTT batched over 64 columns (here k=12 so the oracle finishes in seconds)."""
+@pytest.mark.parametrize("cap_cols", [0, 5])
+def test_domain_batched_64_columns(gpu_ctx, oracle_c, monkeypatch, cap_cols):
+    """configs[2]: coset NTT batched over 64 columns (here k=12 so the oracle finishes in seconds);
+    cap_cols = 5 shrinks the scratch so that the 64 columns are processed in 13 groups."""
     j, k, ncols = 5, 12, 64
+    if cap_cols:
+        monkeypatch.setenv("H2B_NTT_SCRATCH_CAP", str(cap_cols * (1 << 14) * 32))
     d = h.EvaluationDomain(gpu_ctx, j, k)
     od = oracle_c.domain(j, k, 0)
     n, ne, nq = 1 << k, 1 << d.extended_k, d.quotient_len
