@@ -8,3 +8,5 @@ from ._ffi import (H2B_DEVICE, H2B_ERR_ARG, H2B_ERR_BAD_OMEGA, H2B_ERR_CUDA, H2B
 from .api import (Bases, Context, DeviceBuffer, EvaluationDomain, ParamsKZG, PinnedArray, Q_MOD, R_MOD,
                   fq_decode, fq_encode, fr_decode, fr_encode, g1_decode, g1_encode,
                   g1_jacobian_to_affine)
+from .plonk import (ADVICE, FIXED, INSTANCE, Column, ConstraintSystem, Evaluator, Expression, GraphEvaluator,
+                    LookupArgument, PermutationArgument, make_eval_columns)

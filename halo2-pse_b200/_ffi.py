@@ -98,6 +98,15 @@ SYMBOLS = {
     "h2b_host_free": (None, [_P]),
     "h2b_copy_h2d": (_I, [_P, _P, _P, _SZ]),
     "h2b_copy_d2h": (_I, [_P, _P, _P, _SZ]),
+    "h2b_copy_d2d": (_I, [_P, _P, _P, _SZ]),
+    "h2b_device_memset": (_I, [_P, _P, _I, _SZ]),
+    "h2b_graph_new": (_I, [_P, _P, _SZ, _P, _U32, _P, _U32, _U32, C.POINTER(_P)]),
+    "h2b_graph_free": (None, [_P]),
+    "h2b_graph_num_slots": (_U32, [_P]),
+    "h2b_graph_num_instructions": (_U32, [_P]),
+    "h2b_evaluate_h_gates": (_I, [_P, _P, _P, _P]),
+    "h2b_evaluate_h_permutation": (_I, [_P, _P, _P, _P, _U32, _P, _P, _U32, _U32, _U32, _P, _P, _P, _P]),
+    "h2b_evaluate_h_lookup": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "h2b_synth_scalars": (_I, [_P, _P, _SZ, _U64, _U32]),
     "h2b_synth_bases": (_I, [_P, _P, _SZ, _U64]),
     "h2b_synth_base_scalar": (_U64, [_U64, _U64]),

@@ -233,6 +233,16 @@ class Context:
     def pinned(self, shape) -> PinnedArray:
         return PinnedArray(self.lib, tuple(shape))
 
+    def memset(self, buf: DeviceBuffer, value: int = 0, nbytes: Optional[int] = None, offset_bytes: int = 0) -> None:
+        nbytes = buf.nbytes - offset_bytes if nbytes is None else nbytes
+        self._check(self.lib.h2b_device_memset(self.h, buf.at(offset_bytes), value, nbytes))
+
+    def clone(self, buf: DeviceBuffer, nbytes: Optional[int] = None) -> DeviceBuffer:
+        nbytes = buf.nbytes if nbytes is None else nbytes
+        out = self.alloc(nbytes)
+        self._check(self.lib.h2b_copy_d2d(self.h, out.ptr, buf.ptr, nbytes))
+        return out
+
     def upload_fr(self, arr) -> DeviceBuffer:
         a = _fr_array(arr)
         return self.alloc(max(a.nbytes, 32)).upload(a)

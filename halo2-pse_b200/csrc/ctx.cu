@@ -377,6 +377,24 @@ extern "C" int h2b_copy_d2h(h2b_ctx* ctx, void* dst_host, const void* src_dev, s
   return H2B_OK;
 }
 
+extern "C" int h2b_copy_d2d(h2b_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  H2B_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
+extern "C" int h2b_device_memset(h2b_ctx* ctx, void* dst_dev, int value, size_t bytes) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  H2B_CUDA(ctx, cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return H2B_OK;
+}
+
 extern "C" int h2b_synth_scalars(h2b_ctx* ctx, h2b_fr* dst_dev, size_t n, uint64_t seed,
                                  uint32_t kind) {
   if (!ctx) return H2B_ERR_ARG;

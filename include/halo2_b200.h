@@ -165,6 +165,53 @@ int h2b_poly_scale(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n, const h2b_fr* sca
 int h2b_batch_invert(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n);
 int h2b_running_product(h2b_ctx* ctx, const h2b_fr* in, int loc, size_t n, const h2b_fr* init, h2b_fr* out);
 
+/* ---- quotient evaluation: Evaluator::evaluate_h, plonk/evaluation.rs:280-522 ----
+ * A GraphEvaluator (evaluation.rs:193-202) is handed over as a flat word stream, one record per
+ * CalculationInfo in order:  op, target, operands...  with
+ *   op      0 Add(a,b) 1 Sub(a,b) 2 Mul(a,b) 3 Square(a) 4 Double(a) 5 Negate(a)
+ *           6 Horner(start, factor, nparts, part_0 .. part_{nparts-1})   7 Store(a)      (evaluation.rs:110-127)
+ *   operand three words (kind, i, j):  0 Constant(i) 1 Intermediate(i) 2 Fixed(column i, rotation index j)
+ *           3 Advice(i, j) 4 Instance(i, j) 5 Challenge(i) 6 Beta 7 Gamma 8 Theta 9 Y 10 PreviousValue
+ *                                                                                         (evaluation.rs:38-61)
+ * `rotations` are GraphEvaluator::rotations (Rotation.0 values); h2b_graph_new compiles the stream once, as
+ * Evaluator::new does at keygen (evaluation.rs:224-277). */
+typedef struct h2b_graph h2b_graph;
+int h2b_graph_new(h2b_ctx* ctx, const uint32_t* calculations, size_t n_words, const h2b_fr* constants,
+                  uint32_t n_constants, const int32_t* rotations, uint32_t n_rotations,
+                  uint32_t num_intermediates, h2b_graph** out);
+void h2b_graph_free(h2b_graph* graph);
+uint32_t h2b_graph_num_slots(const h2b_graph* graph);        /* live intermediates after renaming */
+uint32_t h2b_graph_num_instructions(const h2b_graph* graph); /* three-address instructions */
+
+/* The polynomials evaluate_h reads, as DEVICE pointers to cosets of 2^extended_k elements each (the outputs
+ * of h2b_coeff_to_extended), plus the challenges (host values). */
+typedef struct {
+  const h2b_fr* const* fixed;    uint32_t n_fixed;     /* pk.fixed_cosets              */
+  const h2b_fr* const* advice;   uint32_t n_advice;    /* coeff_to_extended(advice)    */
+  const h2b_fr* const* instance; uint32_t n_instance;  /* coeff_to_extended(instance)  */
+  const h2b_fr* challenges;      uint32_t n_challenges;
+  h2b_fr beta, gamma, theta, y;
+} h2b_eval_columns;
+
+/* custom gates: values[i] = custom_gates.evaluate(previous_value = values[i]) for every row of the extended
+ * domain; `values` is a device array of 2^extended_k elements, in place.        evaluation.rs:336-362 */
+int h2b_evaluate_h_gates(h2b_domain* dom, h2b_graph* graph, const h2b_eval_columns* cols, h2b_fr* values);
+/* permutation constraints folded into `values` with y.  column_type: 0 Advice, 1 Fixed, 2 Instance (plonk
+ * circuit.rs `Any`); set s covers columns [s*chunk_len, (s+1)*chunk_len); n_sets = 0 is a no-op.
+ *                                                                               evaluation.rs:364-444 */
+int h2b_evaluate_h_permutation(h2b_domain* dom, const h2b_eval_columns* cols, const uint32_t* column_type,
+                               const uint32_t* column_index, uint32_t n_columns,
+                               const h2b_fr* const* sigma_cosets, const h2b_fr* const* product_cosets,
+                               uint32_t n_sets, uint32_t chunk_len, uint32_t blinding_factors,
+                               const h2b_fr* l0, const h2b_fr* l_last, const h2b_fr* l_active_row,
+                               h2b_fr* values);
+/* one lookup argument: table_value = lookup_graph.evaluate(previous_value = 0), then the five lookup
+ * constraints folded into `values` with y.                                      evaluation.rs:446-519 */
+int h2b_evaluate_h_lookup(h2b_domain* dom, h2b_graph* graph, const h2b_eval_columns* cols,
+                          const h2b_fr* product_coset, const h2b_fr* permuted_input_coset,
+                          const h2b_fr* permuted_table_coset, const h2b_fr* l0, const h2b_fr* l_last,
+                          const h2b_fr* l_active_row, h2b_fr* values);
+
 /* Four-step pieces for ONE transform sharded over several GPUs (device pointers
  * only; no counterpart in the reference, which is single-process).  The host
  * side (halo2-pse_b200/dist.py) composes them with an all-to-all over NCCL:
@@ -192,6 +239,8 @@ int h2b_host_alloc(size_t bytes, void** out);
 void h2b_host_free(void* p);
 int h2b_copy_h2d(h2b_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int h2b_copy_d2h(h2b_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int h2b_copy_d2d(h2b_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
+int h2b_device_memset(h2b_ctx* ctx, void* dst_dev, int value, size_t bytes);
 
 /* Synthetic benchmark inputs, generated on device:
  * uniform Fr in Montgomery form from a counter-based generator; and n valid

@@ -1,0 +1,133 @@
+"""Shared bodies of the quotient-evaluation parity tests: the same function runs against the CPU kernel
+emulator (tests/test_emulator_plonk.py) and on the GPU (tests/test_gpu_plonk.py)."""
+from __future__ import annotations
+
+import random
+from types import SimpleNamespace
+
+import halo2_pse_b200 as h
+from oracle import bn256 as O
+from oracle import plonk as OP
+from tests import helpers as H
+
+
+def build_cs(variant: str) -> h.ConstraintSystem:
+    cs = h.ConstraintSystem()
+    if variant == "bench":  # benches/plonk.rs:203-241
+        cs.set_minimum_degree(5)
+        a, b, c = cs.advice_column(), cs.advice_column(), cs.advice_column()
+        for col in (a, b, c):
+            cs.enable_equality(col)
+        sm, sa, sb, sc = (cs.fixed_column() for _ in range(4))
+        qa, qb, qc = cs.query_advice(a), cs.query_advice(b), cs.query_advice(c)
+        qsa, qsb, qsc, qsm = cs.query_fixed(sa), cs.query_fixed(sb), cs.query_fixed(sc), cs.query_fixed(sm)
+        cs.create_gate("Combined add-mult", [qa * qsa + qb * qsb + qa * qb * qsm - (qc * qsc)])
+        return cs
+    # "rich": rotations, constants, scaling, negation, challenges, instance, repeated sub-expressions,
+    # several gates, two lookups, a permutation over advice + fixed + instance columns in several sets
+    a, b, c, d = (cs.advice_column() for _ in range(4))
+    f0, f1, f2 = (cs.fixed_column() for _ in range(3))
+    inst = cs.instance_column()
+    ch = cs.challenge_usable_after(0)
+    for col in (a, b, f1, inst, d):
+        cs.enable_equality(col)
+    qa, qb, qc, qd = cs.query_advice(a), cs.query_advice(b), cs.query_advice(c), cs.query_advice(d)
+    qa_next, qb_prev, qc_far = cs.query_advice(a, 1), cs.query_advice(b, -1), cs.query_advice(c, 3)
+    q0, q1, q2 = cs.query_fixed(f0), cs.query_fixed(f1), cs.query_fixed(f2, -2)
+    qi = cs.query_instance(inst)
+    one, two = h.Expression.constant(1), h.Expression.constant(2)
+    cs.create_gate("mul", [q0 * (qa * qb - qc), q0 * (qa_next - qa - one)])
+    cs.create_gate("misc", [
+        q1 * (qa * qa * two - qd * 7 + (-qb_prev)) + h.Expression.constant(0) * qa,
+        (qa + qb) * (qa + qb) * q2 - qc_far * ch + qi * (O.R_MOD - 5),
+        -(h.Expression.constant(3)) + two * qd - (qa * qb - qc) * one,
+        (qa - h.Expression.constant(0)) * (qb * 1) * (qc * 0 + q1),
+    ])
+    if variant == "rich":
+        cs.lookup("l0", [(qa * q0, q1), (qb + qd, q2 * two)])
+        cs.lookup("l1", [(qc_far * ch, q0 + one)])
+    return cs
+
+
+def random_case(cs: h.ConstraintSystem, k: int, seed: int, n_circuits: int = 1):
+    """Random coefficient-form polynomials for everything evaluate_h reads (it is a function of arbitrary
+    inputs: no satisfying witness is needed to compare values)."""
+    rng = random.Random(seed)
+    n = 1 << k
+    rp = lambda: H.rand_fr(rng, n)  # noqa: E731
+    case = SimpleNamespace(k=k, n=n)
+    case.fixed_polys = [rp() for _ in range(cs.num_fixed_columns)]
+    case.l0, case.l_last, case.l_active = rp(), rp(), rp()
+    case.sigma_polys = [rp() for _ in cs.permutation.columns]
+    chunk = cs.degree() - 2
+    n_sets = (len(cs.permutation.columns) + chunk - 1) // chunk
+    case.circuits = []
+    for _ in range(n_circuits):
+        case.circuits.append(SimpleNamespace(
+            advice=[rp() for _ in range(cs.num_advice_columns)],
+            instance=[rp() for _ in range(cs.num_instance_columns)],
+            z=[rp() for _ in range(n_sets)],
+            lookups=[SimpleNamespace(product=rp(), permuted_input=rp(), permuted_table=rp()) for _ in cs.lookups]))
+    case.challenges = H.rand_fr(rng, cs.num_challenges)
+    case.y, case.beta, case.gamma, case.theta = H.rand_fr(rng, 4)
+    return case
+
+
+def oracle_h(cs: h.ConstraintSystem, case) -> list:
+    dom = O.EvaluationDomain(cs.degree(), case.k)
+    ext = dom.coeff_to_extended
+    circuits = []
+    for c in case.circuits:
+        circuits.append(dict(advice=[ext(p) for p in c.advice], instance=[ext(p) for p in c.instance],
+                             perm_sets=[ext(p) for p in c.z],
+                             lookups=[dict(product=ext(l.product), permuted_input=ext(l.permuted_input),
+                                           permuted_table=ext(l.permuted_table)) for l in c.lookups]))
+    return OP.evaluate_h(
+        k=case.k, extended_k=dom.extended_k, extended_omega=dom.extended_omega,
+        gates=[[p.to_tuple() for p in polys] for _, polys in cs.gates],
+        lookups=[([e.to_tuple() for e in l.input_expressions], [e.to_tuple() for e in l.table_expressions])
+                 for l in cs.lookups],
+        perm_columns=[tuple(c) for c in cs.permutation.columns], chunk_len=cs.degree() - 2,
+        blinding_factors=cs.blinding_factors(), fixed=[ext(p) for p in case.fixed_polys], l0=ext(case.l0),
+        l_last=ext(case.l_last), l_active_row=ext(case.l_active), sigma_cosets=[ext(p) for p in case.sigma_polys],
+        circuits=circuits, challenges=case.challenges, y=case.y, beta=case.beta, gamma=case.gamma, theta=case.theta)
+
+
+def device_h(ctx: h.Context, cs: h.ConstraintSystem, case) -> list:
+    """Evaluator.evaluate_h through the C ABI, everything device-resident."""
+    dom = h.EvaluationDomain(ctx, cs.degree(), case.k)
+    up = lambda vals: ctx.upload_fr(h.fr_encode(vals))  # noqa: E731
+
+    def coset(vals):
+        src = up(vals)
+        out = ctx.alloc(dom.extended_len() * 32)
+        dom.coeff_to_extended_device(src, out)
+        src.free()
+        return out
+
+    pk = SimpleNamespace(domain=dom, cs=cs, fixed_cosets=[coset(p) for p in case.fixed_polys], l0=coset(case.l0),
+                         l_last=coset(case.l_last), l_active_row=coset(case.l_active),
+                         permutation_cosets=[coset(p) for p in case.sigma_polys])
+    ev = h.Evaluator(cs)
+    perms = [SimpleNamespace(sets=[SimpleNamespace(permutation_product_coset=coset(z)) for z in c.z])
+             for c in case.circuits]
+    lookups = [[SimpleNamespace(product_poly=up(l.product), permuted_input_poly=up(l.permuted_input),
+                                permuted_table_poly=up(l.permuted_table)) for l in c.lookups]
+               for c in case.circuits]
+    values = ev.evaluate_h(pk, [[up(p) for p in c.advice] for c in case.circuits],
+                           [[up(p) for p in c.instance] for c in case.circuits], case.challenges, case.y, case.beta,
+                           case.gamma, case.theta, lookups, perms)
+    out = h.fr_decode(values.download(dom.extended_len()))
+    ev.free()
+    dom.free()
+    return out
+
+
+def check_evaluate_h(ctx: h.Context, variant: str, k: int, seed: int, n_circuits: int = 1):
+    cs = build_cs(variant)
+    case = random_case(cs, k, seed, n_circuits)
+    want = oracle_h(cs, case)
+    got = device_h(ctx, cs, case)
+    assert len(got) == len(want)
+    bad = [i for i in range(len(want)) if got[i] != want[i]]
+    assert not bad, (variant, k, len(bad), bad[:4])

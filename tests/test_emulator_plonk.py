@@ -1,0 +1,52 @@
+"""Quotient evaluation on the CPU kernel emulator (TEST INFRASTRUCTURE) against the
+direct big-integer oracle: graph compiler, slot renaming, interpreter, permutation and lookup kernels."""
+import numpy as np
+import pytest
+
+import halo2_pse_b200 as h
+from tests import plonk_cases as PC
+
+
+@pytest.mark.parametrize("variant,k,ncirc", [("bench", 4, 1), ("rich", 4, 1), ("rich", 5, 2), ("gates_only", 3, 1)])
+def test_evaluate_h_vs_oracle(emu_ctx, variant, k, ncirc):
+    PC.check_evaluate_h(emu_ctx, variant, k, seed=100 + k, n_circuits=ncirc)
+
+
+def test_graph_compiler_renames_slots(emu_ctx):
+    cs = PC.build_cs("rich")
+    ev = h.Evaluator(cs)
+    g = ev.custom_gates
+    hnd = g.compile(emu_ctx)
+    slots = emu_ctx.lib.h2b_graph_num_slots(hnd)
+    instrs = emu_ctx.lib.h2b_graph_num_instructions(hnd)
+    # Horner over the six gate polynomials is unrolled; live slots are far fewer than intermediates
+    assert instrs == len(g.calculations) - 1 + 6
+    assert 0 < slots < g.num_intermediates
+    ev.free()
+
+
+def test_graph_rejects_malformed_streams(emu_ctx):
+    import ctypes as C
+    consts = h.fr_encode([0, 1, 2])
+    rots = np.asarray([0], dtype=np.int32)
+
+    def new(words, n_inter=4):
+        code = np.asarray(words, dtype=np.uint32)
+        out = C.c_void_p()
+        return emu_ctx.lib.h2b_graph_new(emu_ctx.h, C.c_void_p(code.ctypes.data), code.size,
+                                         C.c_void_p(consts.ctypes.data), 3, C.c_void_p(rots.ctypes.data), 1, n_inter,
+                                         C.byref(out))
+
+    assert new([7, 0, 0, 1, 0]) == 0                    # Store(Constant(1))
+    assert new([7, 0, 0, 9, 0]) == h.H2B_ERR_ARG        # constant index out of range
+    assert new([0, 0, 1, 1, 0, 0, 1, 0]) == h.H2B_ERR_ARG  # reads intermediate 1 before it exists
+    assert new([7, 9, 0, 1, 0]) == h.H2B_ERR_ARG        # target out of range
+    assert new([7, 0, 2, 0, 5]) == h.H2B_ERR_ARG        # rotation index out of range
+    assert new([6, 0, 0, 1, 0, 9, 0, 0, 3, 0, 0, 0]) == h.H2B_ERR_ARG  # Horner with a truncated part list
+    assert new([42, 0, 0, 1, 0]) == h.H2B_ERR_ARG       # unknown opcode
+
+
+def test_evaluate_h_slot_overflow_path(emu_ctx, monkeypatch):
+    """More live slots than shared memory holds: the slot file moves to a global overflow area."""
+    monkeypatch.setenv("H2B_EVALH_SMEM_CAP", "4096")
+    PC.check_evaluate_h(emu_ctx, "rich", 4, seed=7)
