@@ -45,7 +45,8 @@ class Column(tuple):
 class Expression:
     """plonk/circuit.rs:780-1100 without `Selector` (the prover works from the constraint system of
     the verifying key, where selectors are already fixed columns: plonk/prover.rs:69-71).
-    node: ("constant", v) | ("fixed"|"advice"|"instance", column_index, rotation) | ("challenge", index)
+    node: ("constant", v) | ("fixed"|"advice"|"instance", column_index, rotation, query_index)
+          | ("challenge", index, phase)
           | ("negated", e) | ("sum", a, b) | ("product", a, b) | ("scaled", e, f)"""
 
     __slots__ = ("node",)
@@ -169,7 +170,7 @@ class ConstraintSystem:
         idx = self.num_challenges
         self.num_challenges += 1
         self.challenge_phase.append(phase)
-        return Expression("challenge", idx)
+        return Expression("challenge", idx, phase)
 
     def phases(self) -> List[int]:
         return list(range(max([0] + self.advice_column_phase) + 1))
@@ -186,16 +187,13 @@ class ConstraintSystem:
         return len(qs) - 1
 
     def query_advice(self, column: Column, at: int = 0) -> Expression:
-        self._query_index(column, at)
-        return Expression("advice", column.index, at)
+        return Expression("advice", column.index, at, self._query_index(column, at))
 
     def query_fixed(self, column: Column, at: int = 0) -> Expression:
-        self._query_index(column, at)
-        return Expression("fixed", column.index, at)
+        return Expression("fixed", column.index, at, self._query_index(column, at))
 
     def query_instance(self, column: Column, at: int = 0) -> Expression:
-        self._query_index(column, at)
-        return Expression("instance", column.index, at)
+        return Expression("instance", column.index, at, self._query_index(column, at))
 
     def enable_equality(self, column: Column) -> None:  # :1516-1520
         self._query_index(column, 0)

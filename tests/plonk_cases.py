@@ -131,3 +131,45 @@ def check_evaluate_h(ctx: h.Context, variant: str, k: int, seed: int, n_circuits
     assert len(got) == len(want)
     bad = [i for i in range(len(want)) if got[i] != want[i]]
     assert not bad, (variant, k, len(bad), bad[:4])
+
+
+# ---------------------------------------------------------------------------
+# prover cases
+# ---------------------------------------------------------------------------
+def oracle_cs(cs: h.ConstraintSystem):
+    """The product's ConstraintSystem as the oracle's plain-data CS (data copying only)."""
+    from oracle import prover as OV
+    return OV.CS(num_fixed_columns=cs.num_fixed_columns, num_advice_columns=cs.num_advice_columns,
+                 num_instance_columns=cs.num_instance_columns,
+                 gates=[[p.to_tuple() for p in polys] for _, polys in cs.gates],
+                 advice_queries=[(c.index, r) for c, r in cs.advice_queries],
+                 instance_queries=[(c.index, r) for c, r in cs.instance_queries],
+                 fixed_queries=[(c.index, r) for c, r in cs.fixed_queries],
+                 perm_columns=[tuple(c) for c in cs.permutation.columns],
+                 num_advice_queries=cs.num_advice_queries, minimum_degree=cs.minimum_degree,
+                 num_challenges=cs.num_challenges, advice_column_phase=cs.advice_column_phase,
+                 challenge_phase=cs.challenge_phase,
+                 lookups=[([e.to_tuple() for e in l.input_expressions], [e.to_tuple() for e in l.table_expressions])
+                          for l in cs.lookups])
+
+
+def bench_circuit(k: int, a: int):
+    """MyCircuit of benches/plonk.rs:246-270 laid out by SimpleFloorPlanner: iteration i puts raw_multiply on
+    row 2i and raw_add on row 2i+1, then copies a0 = a1 and b1 = c0.
+    -> (fixed columns [sm, sa, sb, sc], advice columns [a, b, c], copy constraints)"""
+    iters = (1 << (k - 1)) - 3
+    r = O.R_MOD
+    a2 = a * a % r
+    fin = (a2 + a) % r
+    sm, sa, sb, sc, ca, cb, cc, copies = [], [], [], [], [], [], [], []
+    A, B, C_ = (h.ADVICE, 0), (h.ADVICE, 1), (h.ADVICE, 2)
+    for i in range(iters):
+        # raw_multiply: (a, a, a^2), sa = sb = 0, sc = sm = 1
+        ca.append(a), cb.append(a), cc.append(a2)
+        sa.append(0), sb.append(0), sc.append(1), sm.append(1)
+        # raw_add: (a, a^2, a^2 + a), sa = sb = sc = 1, sm = 0
+        ca.append(a), cb.append(a2), cc.append(fin)
+        sa.append(1), sb.append(1), sc.append(1), sm.append(0)
+        copies.append((A, 2 * i, A, 2 * i + 1))
+        copies.append((B, 2 * i + 1, C_, 2 * i))
+    return [sm, sa, sb, sc], [ca, cb, cc], copies
