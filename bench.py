@@ -239,6 +239,47 @@ def gpu_opmix(ctx, h):
     return res
 
 
+PROOF_K = 20
+
+
+def gpu_create_proof(ctx, h):
+    """keygen + create_proof (KZG/bn256, GWC, Blake2b) of the reference's bench circuit at k = 20 with every
+    commitment, transform, quotient evaluation and opening on the GPU; the witness starts in host memory."""
+    from halo2_pse_b200 import circuits
+    k = PROOF_K
+    t0 = time.perf_counter()
+    params = h.ParamsKZG.setup(ctx, k, 0x1234567890ABCDEF1234567890ABCDEF, precompute=True)
+    t_setup = time.perf_counter() - t0
+    cs = circuits.standard_plonk_cs()
+    fixed, advice, copies = circuits.my_circuit(k, 0xDEADBEEF)
+    t0 = time.perf_counter()
+    pk = h.keygen(params, cs, fixed, copies)
+    ctx.sync()
+    t_keygen = time.perf_counter() - t0
+    witness = lambda phase, ch: dict(enumerate(advice))  # noqa: E731
+    best = None
+    for rep in range(4):
+        timings = {}
+        tr = h.Blake2bWrite()
+        l0 = ctx.launches
+        t0 = time.perf_counter()
+        h.create_proof(params, pk, [witness], [[]], h.CounterRng(1234 + rep), tr, timings=timings)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        if rep and (best is None or dt < best[0]):
+            best = (dt, timings, ctx.launches - l0, len(tr.finalize()))
+    pk.free()
+    params.g.free()
+    params.g_lagrange.free()
+    return {"what": f"create_proof of benches/plonk.rs MyCircuit at k={k} over KZG/bn256 (ProverGWC, Blake2bWrite, "
+                    "Challenge255): 11 MSMs, 7 iNTT 2^20, 4 coset NTT 2^22, evaluate_h on 2^22 rows, 1 inverse coset "
+                    "NTT, 17 Horner evaluations, 2 Kate divisions; witness columns start in host memory; proof bytes "
+                    "are checked against the big-integer oracle and the restated verifier in tests/ (k = 5, 6, 14)",
+            "seconds": best[0], "stages_seconds": {kk: round(v, 5) for kk, v in best[1].items()},
+            "gpu_launches": best[2], "proof_bytes": best[3], "keygen_seconds": t_keygen,
+            "setup_seconds_untimed_host_bookkeeping": t_setup, "wall_clock": "host perf_counter, best of 3 after 1 warm-up"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -506,6 +547,7 @@ def run_ours(args):
         sb.free()
 
     opmix = gpu_opmix(ctx, h) if (rank == 0 and world == 1) else None
+    proof = gpu_create_proof(ctx, h) if (rank == 0 and world == 1) else None
     if rank == 0:
         total_pts = world * n * args.steps
         line = {
@@ -534,6 +576,7 @@ def run_ours(args):
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(steps=1)
             line["create_proof_opmix"] = {"what": OPMIX, "gpu": opmix, "cpu": cpu_opmix()}
+            line["create_proof"] = proof
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     barrier()

@@ -107,6 +107,10 @@ SYMBOLS = {
     "h2b_evaluate_h_gates": (_I, [_P, _P, _P, _P]),
     "h2b_evaluate_h_permutation": (_I, [_P, _P, _P, _P, _U32, _P, _P, _U32, _U32, _U32, _P, _P, _P, _P]),
     "h2b_evaluate_h_lookup": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "h2b_fr_from_u512": (_I, [_P, _P, _I, _SZ, _P]),
+    "h2b_fr_random_counter": (_I, [_P, _U64, _U64, _SZ, _P]),
+    "h2b_permutation_fractions": (_I, [_P, _P, _P, _U32, _U32, _P, _P, _P]),
+    "h2b_poly_fma": (_I, [_P, _P, _P, _P, _P, _SZ]),
     "h2b_synth_scalars": (_I, [_P, _P, _SZ, _U64, _U32]),
     "h2b_synth_bases": (_I, [_P, _P, _SZ, _U64]),
     "h2b_synth_base_scalar": (_U64, [_U64, _U64]),

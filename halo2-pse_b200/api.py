@@ -430,15 +430,17 @@ class Bases:
         self.ctx._check(self.ctx.lib.h2b_copy_d2h(self.ctx.h, _ptr(out), p, out.nbytes))
         return out
 
-    def msm(self, scalars, n: Optional[int] = None, offset: int = 0, affine: bool = True):
-        """best_multiexp(scalars, &bases[offset..offset+n]); scalars are host limbs
+    def msm(self, scalars, n: Optional[int] = None, offset: int = 0, affine: bool = True, scalar_offset: int = 0):
+        """best_multiexp(scalars[scalar_offset..][..n], &bases[offset..offset+n]); scalars are host limbs
         or a DeviceBuffer.  Returns the affine point (x, y) | None."""
         if isinstance(scalars, DeviceBuffer):
             if n is None:
                 raise H2BError(_ffi.H2B_ERR_ARG, "n required for device scalars")
-            sp, loc = scalars.ptr, H2B_DEVICE
+            if (scalar_offset + n) * 32 > scalars.nbytes:
+                raise H2BError(_ffi.H2B_ERR_LENGTH, "scalar slice outside the buffer")
+            sp, loc = scalars.at(scalar_offset * 32), H2B_DEVICE
         else:
-            arr = _fr_array(scalars)
+            arr = _fr_array(scalars)[scalar_offset:]
             n = arr.shape[0] if n is None else n
             sp, loc = _ptr(arr), H2B_HOST
         if affine:

@@ -88,7 +88,7 @@ class Expression:
         return self.node[1].degree() + self.node[2].degree()
 
     def to_tuple(self):
-        """Nested tuples (the tests hand these to the oracle)."""
+        """Nested tuples (plain data, for tests and serialisation)."""
         k = self.node[0]
         if k in ("negated",):
             return (k, self.node[1].to_tuple())

@@ -212,6 +212,26 @@ int h2b_evaluate_h_lookup(h2b_domain* dom, h2b_graph* graph, const h2b_eval_colu
                           const h2b_fr* permuted_table_coset, const h2b_fr* l0, const h2b_fr* l_last,
                           const h2b_fr* l_active_row, h2b_fr* values);
 
+/* ---- device pieces of create_proof between the transforms and the commitments -------------------- */
+/* out[i] = (wide[i] as a 512-bit little-endian integer) mod r, Montgomery form: Fr::from_u512, the body of
+ * Fr::random (eight rng.next_u64() draws, low limb first) and Fr::from_bytes_wide (halo2curves 0.3.1).
+ * `wide` holds 8 u64 per element (host or device per `loc`); `out_dev` is a device array. */
+int h2b_fr_from_u512(h2b_ctx* ctx, const uint64_t* wide, int loc, size_t n, h2b_fr* out_dev);
+/* n draws of Fr::random from the counter-mode RngCore of the host mirror (CounterRng: word w >= 1 of the stream
+ * is the splitmix64 finaliser of seed + w * 0x9E3779B97F4A7C15), starting after `ctr` words already drawn:
+ * the 2^k draws of the vanishing argument's random polynomial without a host round trip
+ * (plonk/vanishing/prover.rs:49-53).  Same values as h2b_fr_from_u512 over the host-generated words. */
+int h2b_fr_random_counter(h2b_ctx* ctx, uint64_t seed, uint64_t ctr, size_t n, h2b_fr* out_dev);
+/* The permutation argument's per-row fractions for one chunk of columns
+ *   out[i] = prod_j (v_j[i] + delta^(first_column+j) omega^i beta + gamma) / (v_j[i] + beta sigma_j[i] + gamma)
+ * values / sigma: n_cols device arrays of 2^k Lagrange values; out_dev: 2^k elements.
+ *                                                                  plonk/permutation/prover.rs:96-144 */
+int h2b_permutation_fractions(h2b_domain* dom, const h2b_fr* const* values, const h2b_fr* const* sigma,
+                              uint32_t n_cols, uint32_t first_column, const h2b_fr* beta, const h2b_fr* gamma,
+                              h2b_fr* out_dev);
+/* acc = acc * a + p * b on device arrays (poly * F + &poly: vanishing/prover.rs:131-135, gwc/prover.rs:62-76) */
+int h2b_poly_fma(h2b_ctx* ctx, h2b_fr* acc_dev, const h2b_fr* a, const h2b_fr* p_dev, const h2b_fr* b, size_t n);
+
 /* Four-step pieces for ONE transform sharded over several GPUs (device pointers
  * only; no counterpart in the reference, which is single-process).  The host
  * side (halo2-pse_b200/dist.py) composes them with an all-to-all over NCCL:

@@ -173,3 +173,69 @@ def bench_circuit(k: int, a: int):
         copies.append((A, 2 * i, A, 2 * i + 1))
         copies.append((B, 2 * i + 1, C_, 2 * i))
     return [sm, sa, sb, sc], [ca, cb, cc], copies
+
+
+S_TOXIC = 0x1234567890ABCDEF1234567890ABCDEF
+
+
+def oracle_bench_proof(k: int, a: int, seed: bytes):
+    """Proof bytes of the bench circuit from the big-integer oracle (+ what is needed to verify them)."""
+    from oracle import prover as OV
+    params = O.ParamsKZG.setup(k, S_TOXIC)
+    cs = oracle_cs(build_cs("bench"))
+    fixed, advice, copies = bench_circuit(k, a)
+    pk = OV.keygen(params, cs, fixed, copies)
+    t = OV.Blake2bWrite()
+    OV.create_proof(params, pk, [lambda phase, ch: dict(enumerate(advice))], [[]], OV.XorShiftRng(seed), t)
+    return params, pk, t.finalize()
+
+
+def device_bench_proof(ctx: h.Context, k: int, a: int, seed: bytes, precompute: bool = False, timings=None):
+    """The same proof through keygen / create_proof of the product on `ctx`."""
+    params = h.ParamsKZG.setup(ctx, k, S_TOXIC, precompute=precompute)
+    cs = build_cs("bench")
+    fixed, advice, copies = bench_circuit(k, a)
+    pk = h.keygen(params, cs, fixed, copies)
+    t = h.Blake2bWrite()
+    h.create_proof(params, pk, [lambda phase, ch: dict(enumerate(advice))], [[]], h.XorShiftRng(seed), t,
+                   timings=timings)
+    return params, pk, t.finalize()
+
+
+def check_bench_proof_bytes(ctx: h.Context, k: int, seed: bytes = b"\x07" * 16):
+    from oracle import prover as OV
+    a = 0xDEADBEEF
+    oparams, opk, want = oracle_bench_proof(k, a, seed)
+    _, pk, got = device_bench_proof(ctx, k, a, seed)
+    assert pk.pinned == opk.debug            # identical verifying key (commitments included)
+    assert pk.transcript_repr == opk.transcript_repr
+    assert got == want, [i for i in range(0, len(want), 32) if got[i:i + 32] != want[i:i + 32]][:4]
+    assert OV.verify_proof(oparams, S_TOXIC, opk, [[]], got)
+    pk.free()
+
+
+def bench_circuit_limbs(k: int, a: int):
+    """bench_circuit() as numpy limb arrays (the columns have period 2: tiled, no per-row Python)."""
+    import numpy as np
+    iters = (1 << (k - 1)) - 3
+    r = O.R_MOD
+    a2, fin = a * a % r, (a * a + a) % r
+    tile = lambda even, odd: np.tile(h.fr_encode([even, odd]), (iters, 1))  # noqa: E731
+    fixed = [tile(1, 0), tile(0, 1), tile(0, 1), tile(1, 1)]  # sm, sa, sb, sc
+    advice = [tile(a, a), tile(a, a2), tile(a2, fin)]
+    A, B, C_ = (h.ADVICE, 0), (h.ADVICE, 1), (h.ADVICE, 2)
+    copies = []
+    for i in range(iters):
+        copies.append((A, 2 * i, A, 2 * i + 1))
+        copies.append((B, 2 * i + 1, C_, 2 * i))
+    return fixed, advice, copies
+
+
+def oracle_vk_of(pk):
+    """The verifying-key half of a device ProvingKey as the object oracle.prover.verify_proof reads
+    (constants and commitments only: cheap at any k)."""
+    from types import SimpleNamespace
+    cs = oracle_cs(pk.cs)
+    return SimpleNamespace(cs=cs, domain=O.EvaluationDomain(cs.degree(), pk.k), n=pk.n, k=pk.k,
+                           fixed_commitments=pk.fixed_commitments, perm_commitments=pk.perm_commitments,
+                           transcript_repr=pk.transcript_repr)

@@ -50,3 +50,39 @@ def test_evaluate_h_slot_overflow_path(emu_ctx, monkeypatch):
     """More live slots than shared memory holds: the slot file moves to a global overflow area."""
     monkeypatch.setenv("H2B_EVALH_SMEM_CAP", "4096")
     PC.check_evaluate_h(emu_ctx, "rich", 4, seed=7)
+
+
+def test_create_proof_bytes_equal_the_oracle(emu_ctx):
+    """keygen + create_proof of the bench circuit (benches/plonk.rs) at k = 5: identical verifying key,
+    identical proof bytes for the same rng seed, accepted by the restated verifier."""
+    PC.check_bench_proof_bytes(emu_ctx, 5)
+
+
+def test_counter_rng_host_and_device_streams_agree(emu_ctx):
+    """CounterRng draws the same Fr::random values one u64 at a time, in bulk on the host
+    (h2b_fr_from_u512) and generated on the device (h2b_fr_random_counter)."""
+    n = 37
+    a, b, c = h.CounterRng(99), h.CounterRng(99), h.CounterRng(99)
+    a.next_u64(), b.next_u64(), c.next_u64()  # a non-zero starting counter
+    want = [h.fr_random(a) for _ in range(n)]
+    dev = h.fr_random_device(emu_ctx, b, n)                      # device generator
+    assert h.fr_decode(dev.download(n)) == want
+
+    class HostOnly:  # no fill_fr_device: words from the host, reduction on the device
+        def __init__(self, r):
+            self.r = r
+
+        def fill_u64(self, m):
+            return self.r.fill_u64(m)
+
+    dev2 = h.fr_random_device(emu_ctx, HostOnly(c), n)
+    assert h.fr_decode(dev2.download(n)) == want
+    assert a.next_u64() == b.next_u64() == c.next_u64()          # the counters moved identically
+    # from_u512 edge cases: all-ones words, values just above r
+    import numpy as np
+    wide = np.array([[2**64 - 1] * 8, [0] * 8, [h.R_MOD & (2**64 - 1), (h.R_MOD >> 64) & (2**64 - 1),
+                     (h.R_MOD >> 128) & (2**64 - 1), h.R_MOD >> 192, 1, 0, 0, 0]], dtype=np.uint64)
+    out = emu_ctx.alloc(3 * 32)
+    import ctypes as C
+    emu_ctx._check(emu_ctx.lib.h2b_fr_from_u512(emu_ctx.h, C.c_void_p(wide.ctypes.data), 0, 3, out.ptr))
+    assert h.fr_decode(out.download(3)) == [(2**512 - 1) % h.R_MOD, 0, (h.R_MOD + 2**256) % h.R_MOD]

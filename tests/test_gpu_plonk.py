@@ -18,3 +18,39 @@ def test_evaluate_h_vs_oracle(gpu_ctx, variant, k, ncirc):
 def test_evaluate_h_slot_overflow_path(gpu_ctx, monkeypatch):
     monkeypatch.setenv("H2B_EVALH_SMEM_CAP", "4096")
     PC.check_evaluate_h(gpu_ctx, "rich", 5, seed=9)
+
+
+@pytest.mark.parametrize("k", [5, 6])
+def test_create_proof_bytes_equal_the_oracle(gpu_ctx, k):
+    """Identical verifying key and identical proof bytes for the same circuit and rng seed."""
+    PC.check_bench_proof_bytes(gpu_ctx, k, seed=bytes(range(16)))
+
+
+def test_create_proof_k14_is_accepted_by_the_reference_verifier(gpu_ctx):
+    """Size-independent property at a size the big-integer prover cannot reach: the proof of a 2^14-row
+    circuit verifies under the restated reference verifier; a flipped bit or another witness does not."""
+    from types import SimpleNamespace
+    from oracle import prover as OV
+    k = 14
+    params = h.ParamsKZG.setup(gpu_ctx, k, PC.S_TOXIC, precompute=True)
+    cs = PC.build_cs("bench")
+    fixed, advice, copies = PC.bench_circuit_limbs(k, 0xC0FFEE)
+    pk = h.keygen(params, cs, fixed, copies)
+    vk = PC.oracle_vk_of(pk)
+    vparams = SimpleNamespace(g=[h.g1_decode(params.g.download()[:1])[0]])
+
+    def prove(adv, seed):
+        t = h.Blake2bWrite()
+        h.create_proof(params, pk, [lambda phase, ch: dict(enumerate(adv))], [[]], h.CounterRng(seed), t)
+        return t.finalize()
+
+    proof = prove(advice, 1)
+    assert OV.verify_proof(vparams, PC.S_TOXIC, vk, [[]], proof)
+    assert proof == prove(advice, 1) and proof != prove(advice, 2)
+    bad = bytearray(proof)
+    bad[100] ^= 4
+    assert not OV.verify_proof(vparams, PC.S_TOXIC, vk, [[]], bytes(bad))
+    wrong = [a.copy() for a in advice]
+    wrong[2][10] = wrong[2][11]
+    assert not OV.verify_proof(vparams, PC.S_TOXIC, vk, [[]], prove(wrong, 1))
+    pk.free()
