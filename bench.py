@@ -547,7 +547,11 @@ def run_ours(args):
         sb.free()
 
     opmix = gpu_opmix(ctx, h) if (rank == 0 and world == 1) else None
-    proof = gpu_create_proof(ctx, h) if (rank == 0 and world == 1) else None
+    proof = None
+    if rank == 0 and world == 1:
+        pctx = h.Context(local)  # its own context: scratch and MSM workspace sized for k = 20, not for the k = 24 runs
+        proof = gpu_create_proof(pctx, h)
+        pctx.close()
     if rank == 0:
         total_pts = world * n * args.steps
         line = {

@@ -32,9 +32,12 @@ namespace h2b {
 // ---- compiled instruction format ---------------------------------------------------------
 // word x: op | dst_slot << 8;  words y, z, w: sources.
 // source: kind << 30 | payload;  kind 0 uniform(idx)  1 slot(idx)  2 column(rot << 22 | col)  3 previous value
-enum : uint32_t { EV_ADD = 0, EV_SUB = 1, EV_MUL = 2, EV_DBL = 3, EV_NEG = 4, EV_MOV = 5, EV_MULADD = 6 };
+enum : uint32_t { EV_ADD = 0, EV_SUB = 1, EV_MUL = 2, EV_DBL = 3, EV_NEG = 4, EV_MOV = 5, EV_MULADD = 6,
+                  EV_PREFETCH = 7,  // slot <- column value, asynchronously (cp.async straight into the slot file)
+                  EV_WAIT = 8 };    // all prefetches of this thread have landed
 enum : uint32_t { SRC_UNIFORM = 0, SRC_SLOT = 1, SRC_COLUMN = 2, SRC_PREV = 3 };
 static const uint32_t kMaxRot = 255, kMaxCol = (1u << 22) - 1;
+static const size_t kEvalSmemCap = 200 * 1024;  // slot file per block (128 threads x 32 B per slot)
 
 struct EvalProgram {
   const uint4* code;     // n_instr instructions
@@ -43,6 +46,7 @@ struct EvalProgram {
   const Fr* uniforms;
   const Fr* const* cols;  // fixed ++ advice ++ instance device pointers
   const int32_t* rot;     // rotation * rot_scale, per rotation index
+  int async_ok;           // the slot file is in shared memory: EV_PREFETCH may use cp.async
 };
 
 struct SlotFile {
@@ -54,6 +58,23 @@ struct SlotFile {
     r.v[0] = lo.x, r.v[1] = lo.y, r.v[2] = lo.z, r.v[3] = lo.w;
     r.v[4] = hi.x, r.v[5] = hi.y, r.v[6] = hi.z, r.v[7] = hi.w;
     return r;
+  }
+  // slot s <- the 32 bytes at g, without passing through registers (shared slot files only)
+  H2B_D void put_async(uint32_t s, const Fr* g) const {
+#if defined(__CUDA_ARCH__)
+    const uint32_t lo = (uint32_t)__cvta_generic_to_shared(base + (2 * s) * stride + threadIdx.x);
+    const uint32_t hi = (uint32_t)__cvta_generic_to_shared(base + (2 * s + 1) * stride + threadIdx.x);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lo), "l"(g) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hi), "l"(reinterpret_cast<const uint4*>(g) + 1)
+                 : "memory");
+#else
+    put(s, *g);
+#endif
+  }
+  static H2B_D void wait_async() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
   }
   H2B_D void put(uint32_t s, const Fr& r) const {
     base[(2 * s) * stride + threadIdx.x] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
@@ -79,6 +100,16 @@ H2B_D Fr ev_run(const EvalProgram& p, const SlotFile& sf, uint64_t row, uint64_t
   for (uint32_t pc = 0; pc < p.n_instr; ++pc) {
     const uint4 ins = __ldg(p.code + pc);
     const uint32_t op = ins.x & 0xffu, dst = ins.x >> 8;
+    if (op == EV_WAIT) {
+      SlotFile::wait_async();
+      continue;
+    }
+    if (op == EV_PREFETCH && p.async_ok) {
+      const uint32_t payload = ins.y & 0x3fffffffu;
+      const uint64_t r = (uint64_t)((int64_t)row + (int64_t)p.rot[payload >> 22]) & mask;
+      sf.put_async(dst, p.cols[payload & kMaxCol] + r);
+      continue;
+    }
     const Fr a = ev_fetch(ins.y, p, sf, row, mask, prev);
     Fr r;
     if (op == EV_MUL || op == EV_MULADD) {
@@ -318,6 +349,7 @@ extern "C" int h2b_graph_new(h2b_ctx* ctx, const uint32_t* calc, size_t n_words,
     }
   };
   int64_t last_target = -1;
+  bool single_assignment = true;  // every intermediate is the target of exactly one calculation
   while (pos < n_words && ok) {
     const uint32_t op = rd(), target = rd();
     if (!ok || target >= num_intermediates) return bad("calculation target out of range");
@@ -351,6 +383,7 @@ extern "C" int h2b_graph_new(h2b_ctx* ctx, const uint32_t* calc, size_t n_words,
       default: return bad("unknown calculation opcode");
     }
     if (!ok) break;
+    if (defined[target]) single_assignment = false;
     for (PreInstr& pi : emit) {
       for (int i = 0; i < pi.ns; ++i)
         if (!check_src(pi.s[i], pre.size())) return bad("value source out of range or read before it is computed");
@@ -362,44 +395,85 @@ extern "C" int h2b_graph_new(h2b_ctx* ctx, const uint32_t* calc, size_t n_words,
   if (!ok) return bad("truncated calculation stream");
 
   // ---- slot renaming: linear scan over the live ranges of the intermediates ----
-  if (last_target >= 0) last_use[last_target] = (int64_t)pre.size();  // the result is read after the program
-  std::vector<int64_t> slot_of(num_intermediates, -1);
-  std::vector<uint32_t> free_slots;
-  std::multimap<int64_t, uint32_t> expiring;  // last use -> intermediate
-  uint32_t n_slots = 0;
-  for (size_t at = 0; at < pre.size(); ++at) {
-    const PreInstr& pi = pre[at];
-    h2b_graph::Instr in;
-    in.op = pi.op;
-    for (int i = 0; i < 3; ++i) {
-      in.kind[i] = VS_NONE, in.a[i] = in.b[i] = 0;
-      if (i >= pi.ns) continue;
-      in.kind[i] = pi.s[i].kind, in.a[i] = pi.s[i].a, in.b[i] = pi.s[i].b;
-      if (pi.s[i].kind == VS_INTERMEDIATE) in.a[i] = (uint32_t)slot_of[pi.s[i].a];
-    }
-    // Slots whose last reader is this instruction are free for its destination: every source is read
-    // before the destination is written.
-    while (!expiring.empty() && expiring.begin()->first <= (int64_t)at) {
-      free_slots.push_back((uint32_t)slot_of[expiring.begin()->second]);
-      expiring.erase(expiring.begin());
-    }
-    if (slot_of[pi.target] < 0) {
-      uint32_t s;
-      if (!free_slots.empty()) {
-        s = free_slots.back();
-        free_slots.pop_back();
-      } else {
-        s = n_slots++;
+  auto allocate = [&](const std::vector<PreInstr>& order, std::vector<h2b_graph::Instr>& code, uint32_t& n_slots,
+                      int64_t& result_slot) {
+    std::vector<int64_t> last(num_intermediates, -1);
+    for (size_t at = 0; at < order.size(); ++at)
+      for (int i = 0; i < order[at].ns; ++i)
+        if (order[at].s[i].kind == VS_INTERMEDIATE) last[order[at].s[i].a] = (int64_t)at;
+    if (last_target >= 0) last[last_target] = (int64_t)order.size();  // the result is read after the program
+    std::vector<int64_t> slot_of(num_intermediates, -1);
+    std::vector<uint32_t> free_slots;
+    std::multimap<int64_t, uint32_t> expiring;  // last use -> intermediate
+    n_slots = 0;
+    code.clear();
+    for (size_t at = 0; at < order.size(); ++at) {
+      const PreInstr& pi = order[at];
+      h2b_graph::Instr in;
+      in.op = pi.op;
+      in.dst_slot = 0;
+      for (int i = 0; i < 3; ++i) {
+        in.kind[i] = VS_NONE, in.a[i] = in.b[i] = 0;
+        if (i >= pi.ns) continue;
+        in.kind[i] = pi.s[i].kind, in.a[i] = pi.s[i].a, in.b[i] = pi.s[i].b;
+        if (pi.s[i].kind == VS_INTERMEDIATE) in.a[i] = (uint32_t)slot_of[pi.s[i].a];
       }
-      slot_of[pi.target] = s;
-      expiring.emplace(last_use[pi.target] >= 0 ? last_use[pi.target] : (int64_t)at + 1, pi.target);
+      if (pi.op == EV_WAIT) {
+        code.push_back(in);
+        continue;
+      }
+      // Slots whose last reader is this instruction are free for its destination: every source is read
+      // before the destination is written.
+      while (!expiring.empty() && expiring.begin()->first <= (int64_t)at) {
+        free_slots.push_back((uint32_t)slot_of[expiring.begin()->second]);
+        expiring.erase(expiring.begin());
+      }
+      if (slot_of[pi.target] < 0) {
+        uint32_t sl;
+        if (!free_slots.empty()) {
+          sl = free_slots.back();
+          free_slots.pop_back();
+        } else {
+          sl = n_slots++;
+        }
+        slot_of[pi.target] = sl;
+        expiring.emplace(last[pi.target] >= 0 ? last[pi.target] : (int64_t)at + 1, pi.target);
+      }
+      in.dst_slot = (uint32_t)slot_of[pi.target];
+      code.push_back(in);
     }
-    in.dst_slot = (uint32_t)slot_of[pi.target];
-    g->code.push_back(in);
+    result_slot = last_target >= 0 ? slot_of[last_target] : -1;
+  };
+  // Preferred order: every column read hoisted to the top as an asynchronous copy straight into its slot
+  // (all of a row's loads in flight at once instead of one round trip to HBM per Store), one wait, then the
+  // arithmetic.  Kept only while the longer live ranges still fit a shared-memory slot file.
+  uint32_t n_slots = 0;
+  bool hoisted = false;
+  if (single_assignment && getenv("H2B_EVALH_NO_PREFETCH") == nullptr) {
+    std::vector<PreInstr> order, rest;
+    for (const PreInstr& pi : pre) {
+      const bool col = pi.op == EV_MOV && (pi.s[0].kind == VS_FIXED || pi.s[0].kind == VS_ADVICE ||
+                                           pi.s[0].kind == VS_INSTANCE);
+      if (col) {
+        PreInstr q = pi;
+        q.op = EV_PREFETCH;
+        order.push_back(q);
+      } else {
+        rest.push_back(pi);
+      }
+    }
+    if (!order.empty()) {
+      PreInstr w;
+      w.op = EV_WAIT, w.target = 0, w.ns = 0;
+      order.push_back(w);
+      order.insert(order.end(), rest.begin(), rest.end());
+      allocate(order, g->code, n_slots, g->result_slot);
+      hoisted = (size_t)n_slots * 32 * 128 <= kEvalSmemCap;
+    }
   }
+  if (!hoisted) allocate(pre, g->code, n_slots, g->result_slot);
   if (n_slots >= (1u << 22)) return bad("too many live intermediates");
   g->n_slots = std::max(n_slots, 1u);
-  g->result_slot = last_target >= 0 ? slot_of[last_target] : -1;
   g->constants.resize(n_constants);
   for (uint32_t i = 0; i < n_constants; ++i) g->constants[i] = load_fr(constants[i]);
   g->rotations.assign(rotations, rotations + n_rotations);
@@ -504,12 +578,12 @@ int run_graph(h2b_domain* dom, h2b_graph* g, const h2b_eval_columns* c, Fr* valu
   // launch geometry: slots in shared memory when they fit, else in a global overflow area
   const uint32_t threads = 128;
   const size_t slot_bytes = (size_t)g->n_slots * 32 * threads;
-  size_t smem_cap = 200 * 1024;
+  size_t smem_cap = kEvalSmemCap;
   if (const char* e = getenv("H2B_EVALH_SMEM_CAP")) smem_cap = (size_t)atoll(e);  // tests: force the overflow path
   const bool overflow = slot_bytes > smem_cap;
   uint64_t want = (size + threads - 1) / threads;
   const uint32_t per_sm =
-      overflow ? 4 : (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(slot_bytes, 1)));
+      overflow ? 4 : (uint32_t)std::max<size_t>(1, std::min<size_t>(8, kEvalSmemCap / std::max<size_t>(slot_bytes, 1)));
   const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
   const uint32_t grid = (uint32_t)std::min<uint64_t>(want, cap);
   const size_t ovf_bytes = overflow ? (size_t)grid * slot_bytes : 0;
@@ -527,10 +601,11 @@ int run_graph(h2b_domain* dom, h2b_graph* g, const h2b_eval_columns* c, Fr* valu
   p.cols = reinterpret_cast<const Fr* const*>(d_tab + off_cols);
   p.rot = reinterpret_cast<const int32_t*>(d_tab + off_rot);
   uint4* d_ovf = overflow ? reinterpret_cast<uint4*>(d_tab + tab_bytes) : nullptr;
+  p.async_ok = overflow ? 0 : 1;
   const size_t smem = overflow ? 0 : slot_bytes;
 #ifndef H2B_EMU
   if (smem > 48 * 1024)
-    H2B_CUDA(ctx, cudaFuncSetAttribute(evalh_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    H2B_CUDA(ctx, cudaFuncSetAttribute(evalh_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEvalSmemCap));
 #endif
   if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   H2B_TRY(launch(ctx, evalh_graph_kernel, dim3(grid), dim3(threads), smem, p, values, size, d_ovf, g->n_slots, mode,

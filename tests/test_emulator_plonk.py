@@ -19,8 +19,9 @@ def test_graph_compiler_renames_slots(emu_ctx):
     hnd = g.compile(emu_ctx)
     slots = emu_ctx.lib.h2b_graph_num_slots(hnd)
     instrs = emu_ctx.lib.h2b_graph_num_instructions(hnd)
-    # Horner over the six gate polynomials is unrolled; live slots are far fewer than intermediates
-    assert instrs == len(g.calculations) - 1 + 6
+    # Horner over the six gate polynomials is unrolled, one wait follows the hoisted column prefetches;
+    # live slots are far fewer than intermediates
+    assert instrs == len(g.calculations) - 1 + 6 + 1
     assert 0 < slots < g.num_intermediates
     ev.free()
 
@@ -44,6 +45,12 @@ def test_graph_rejects_malformed_streams(emu_ctx):
     assert new([7, 0, 2, 0, 5]) == h.H2B_ERR_ARG        # rotation index out of range
     assert new([6, 0, 0, 1, 0, 9, 0, 0, 3, 0, 0, 0]) == h.H2B_ERR_ARG  # Horner with a truncated part list
     assert new([42, 0, 0, 1, 0]) == h.H2B_ERR_ARG       # unknown opcode
+
+
+def test_evaluate_h_without_prefetch_hoisting(emu_ctx, monkeypatch):
+    """The original instruction order (kept when hoisted live ranges would not fit shared memory)."""
+    monkeypatch.setenv("H2B_EVALH_NO_PREFETCH", "1")
+    PC.check_evaluate_h(emu_ctx, "rich", 4, seed=8)
 
 
 def test_evaluate_h_slot_overflow_path(emu_ctx, monkeypatch):

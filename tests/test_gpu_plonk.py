@@ -15,6 +15,11 @@ def test_evaluate_h_vs_oracle(gpu_ctx, variant, k, ncirc):
     PC.check_evaluate_h(gpu_ctx, variant, k, seed=200 + k, n_circuits=ncirc)
 
 
+def test_evaluate_h_without_prefetch_hoisting(gpu_ctx, monkeypatch):
+    monkeypatch.setenv("H2B_EVALH_NO_PREFETCH", "1")
+    PC.check_evaluate_h(gpu_ctx, "rich", 5, seed=8)
+
+
 def test_evaluate_h_slot_overflow_path(gpu_ctx, monkeypatch):
     monkeypatch.setenv("H2B_EVALH_SMEM_CAP", "4096")
     PC.check_evaluate_h(gpu_ctx, "rich", 5, seed=9)
