@@ -17,6 +17,7 @@ H2B_ERR_LENGTH = -2
 H2B_ERR_CUDA = -3
 H2B_ERR_OOM = -4
 H2B_ERR_BAD_OMEGA = -5
+H2B_ERR_CONSTRAINT = -6
 H2B_HOST = 0
 H2B_DEVICE = 1
 
@@ -26,6 +27,7 @@ _ERR_NAMES = {
     H2B_ERR_CUDA: "H2B_ERR_CUDA",
     H2B_ERR_OOM: "H2B_ERR_OOM",
     H2B_ERR_BAD_OMEGA: "H2B_ERR_BAD_OMEGA",
+    H2B_ERR_CONSTRAINT: "H2B_ERR_CONSTRAINT",
 }
 
 
@@ -110,6 +112,9 @@ SYMBOLS = {
     "h2b_fr_from_u512": (_I, [_P, _P, _I, _SZ, _P]),
     "h2b_fr_random_counter": (_I, [_P, _U64, _U64, _SZ, _P]),
     "h2b_permutation_fractions": (_I, [_P, _P, _P, _U32, _U32, _P, _P, _P]),
+    "h2b_lookup_permute": (_I, [_P, _P, _P, _SZ, _P, _P]),
+    "h2b_lookup_product_fractions": (_I, [_P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "h2b_graph_evaluate_lagrange": (_I, [_P, _P, _P, _P]),
     "h2b_poly_fma": (_I, [_P, _P, _P, _P, _P, _SZ]),
     "h2b_synth_scalars": (_I, [_P, _P, _SZ, _U64, _U32]),
     "h2b_synth_bases": (_I, [_P, _P, _SZ, _U64]),

@@ -503,7 +503,8 @@ int check_columns(h2b_ctx* ctx, const h2b_eval_columns* c) {
 }
 
 // uniforms = [constants][challenges][beta, gamma, theta, y][0]
-int run_graph(h2b_domain* dom, h2b_graph* g, const h2b_eval_columns* c, Fr* values, int mode, LookupTail lt) {
+int run_graph(h2b_domain* dom, h2b_graph* g, const h2b_eval_columns* c, Fr* values, int mode, LookupTail lt,
+              bool lagrange_basis = false) {
   h2b_ctx* ctx = dom->ctx;
   if (g->need_fixed > c->n_fixed || g->need_advice > c->n_advice || g->need_instance > c->n_instance ||
       g->need_challenges > c->n_challenges)
@@ -511,8 +512,8 @@ int run_graph(h2b_domain* dom, h2b_graph* g, const h2b_eval_columns* c, Fr* valu
   const uint32_t n_const = (uint32_t)g->constants.size();
   const uint32_t n_cols = c->n_fixed + c->n_advice + c->n_instance;
   const uint32_t n_uni = n_const + c->n_challenges + 5;
-  const uint64_t size = 1ull << dom->extended_k;
-  const int32_t rot_scale = 1 << (dom->extended_k - dom->k);
+  const uint64_t size = 1ull << (lagrange_basis ? dom->k : dom->extended_k);
+  const int32_t rot_scale = lagrange_basis ? 1 : 1 << (dom->extended_k - dom->k);
 
   // code for this table layout
   if (!g->d_code || g->lay_fixed != c->n_fixed || g->lay_advice != c->n_advice || g->lay_instance != c->n_instance ||
@@ -632,6 +633,19 @@ extern "C" int h2b_evaluate_h_gates(h2b_domain* dom, h2b_graph* graph, const h2b
   LookupTail lt;
   memset(&lt, 0, sizeof lt);
   return run_graph(dom, graph, cols, as_fr(values), 0, lt);
+}
+
+extern "C" int h2b_graph_evaluate_lagrange(h2b_domain* dom, h2b_graph* graph, const h2b_eval_columns* cols,
+                                           h2b_fr* values) {
+  if (!dom) return H2B_ERR_ARG;
+  h2b_ctx* ctx = dom->ctx;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!graph || !values) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  H2B_TRY(check_columns(ctx, cols));
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  LookupTail lt;
+  memset(&lt, 0, sizeof lt);
+  return run_graph(dom, graph, cols, as_fr(values), 0, lt, true);
 }
 
 extern "C" int h2b_evaluate_h_lookup(h2b_domain* dom, h2b_graph* graph, const h2b_eval_columns* cols,

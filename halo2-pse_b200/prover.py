@@ -15,8 +15,8 @@ The host does what the reference's host code does besides arithmetic over rows: 
 Fiat-Shamir schedule, O(#columns) scalar bookkeeping and the copy-constraint union-find of keygen.  All
 row-wise work (MSMs, NTTs, quotient evaluation, grand products, batched inversion, Horner evaluations,
 Kate division, linear combinations, the 512-bit reduction of random scalars) runs in libhalo2b200 on the
-GPU; there is no CPU fallback.  Circuits with lookup arguments are rejected here (their permuted-column
-construction sorts field elements, which this build does not have on the device yet).
+GPU; there is no CPU fallback.  The lookup argument's permuted columns (plonk/lookup/prover.rs:55-475) are a
+device radix sort + scans (h2b_lookup_permute).
 
 Encodings that live in halo2curves 0.3.1 (absent from the reference tree) are assumptions A2-A4 of DESIGN.md.
 """
@@ -31,7 +31,8 @@ import numpy as np
 from . import _ffi
 from ._ffi import H2B_DEVICE, H2B_HOST, H2BError
 from .api import (Q_MOD, R_MOD, Context, DeviceBuffer, EvaluationDomain, ParamsKZG, fr_decode, fr_encode)
-from .plonk import ADVICE, FIXED, INSTANCE, ConstraintSystem, Evaluator, Expression, _ptr_array
+from .plonk import (ADVICE, C_HORNER, FIXED, INSTANCE, VS_CONSTANT, VS_THETA, ConstraintSystem, Evaluator, Expression,
+                    GraphEvaluator, _ptr_array, _vs, make_eval_columns)
 
 DELTA = pow(7, 1 << 28, R_MOD)  # Fr::DELTA
 SIGN_BIT = 7                    # A2: G1Affine::to_bytes keeps the parity of y in bit 7 of byte 31
@@ -266,6 +267,9 @@ class ProvingKey:
             if getattr(self, name, None) is not None:
                 getattr(self, name).free()
         self.ev.free()
+        for pair in getattr(self, "lookup_compress", []):
+            for g in pair:
+                g.free()
         self.domain.free()
 
 
@@ -357,6 +361,17 @@ def keygen(params: ParamsKZG, cs: ConstraintSystem, fixed_values: Sequence, copi
     l_blind.free()
 
     pk.ev = Evaluator(cs)  # keygen.rs:353
+    # theta-compression of every lookup's input and table expressions over the Lagrange rows
+    # (lookup/prover.rs:82-104), as interpreter graphs
+    pk.lookup_compress = []
+    for lookup in cs.lookups:
+        pair = []
+        for exprs in (lookup.input_expressions, lookup.table_expressions):
+            g = GraphEvaluator()
+            parts = tuple(g.add_expression(e) for e in exprs)
+            g.add_calculation((C_HORNER, _vs(VS_CONSTANT, 0), parts, _vs(VS_THETA)))
+            pair.append(g)
+        pk.lookup_compress.append(tuple(pair))
     pk.pinned = pinned_debug(cs, k, dom.extended_k, omega, pk.fixed_commitments, pk.perm_commitments)
     hsh = hashlib.blake2b(digest_size=64, person=b"Halo2-Verify-Key")
     hsh.update(len(pk.pinned).to_bytes(8, "little") + pk.pinned.encode())
@@ -367,6 +382,15 @@ def keygen(params: ParamsKZG, cs: ConstraintSystem, fixed_values: Sequence, copi
 # --------------------------------------------------------------------------
 # create_proof
 # --------------------------------------------------------------------------
+class _LookupPolys:
+    """The three coefficient-form polynomials Evaluator.evaluate_h reads of a committed lookup."""
+
+    def __init__(self, lk):
+        self.product_poly = lk.product_poly.buf
+        self.permuted_input_poly = lk.permuted_input_poly.buf
+        self.permuted_table_poly = lk.permuted_table_poly.buf
+
+
 class _Poly:
     """A coefficient-form polynomial on the device with the evaluations already computed for it
     (ProverQuery::get_eval recomputes eval_polynomial; the value is the same)."""
@@ -404,8 +428,6 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
             t_last[0] = now
 
     cs, dom, ctx, n = pk.cs, pk.domain, params.ctx, pk.n
-    if cs.lookups:
-        raise H2BError(_ffi.H2B_ERR_ARG, "lookup arguments are not supported by this prover yet")
     if len(witnesses) != len(instances):
         raise H2BError(_ffi.H2B_ERR_LENGTH, "one instance list per circuit")
     for inst in instances:
@@ -480,6 +502,43 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
     challenge_list = [challenges[i] for i in range(cs.num_challenges)]
 
     theta = transcript.squeeze_challenge_scalar()  # :410
+
+    # ---- lookups: permuted columns (:412-437, lookup/prover.rs:55-140) ----
+    class _Lookup:
+        pass
+
+    lookups: List[List[_Lookup]] = []
+    for ci in range(len(instances)):
+        cols, keep = make_eval_columns(pk.fixed_values, advice_values[ci], instance_values[ci], challenge_list, 0, 0,
+                                       theta, 0)
+        lks = []
+        for g_in, g_tab in pk.lookup_compress:
+            lk = _Lookup()
+            compressed = []
+            for g in (g_in, g_tab):
+                buf = ctx.alloc(n * 32)
+                ctx.memset(buf, 0)
+                ctx._check(ctx.lib.h2b_graph_evaluate_lagrange(dom.h, g.compile(ctx), C.byref(cols), buf.ptr))
+                compressed.append(buf)
+            lk.compressed_input, lk.compressed_table = compressed
+            lk.permuted_input, lk.permuted_table = ctx.alloc(n * 32), ctx.alloc(n * 32)
+            ctx._check(ctx.lib.h2b_lookup_permute(ctx.h, lk.compressed_input.ptr, lk.compressed_table.ptr,
+                                                  unusable_rows_start, lk.permuted_input.ptr, lk.permuted_table.ptr))
+            for b in (lk.permuted_input, lk.permuted_table):  # blinding rows (:447-449)
+                b.upload(fr_encode([fr_random(rng) for _ in range(bf + 1)]), unusable_rows_start * 32)
+            commitments = []
+            for name in ("permuted_input", "permuted_table"):  # commit_values (:114-125)
+                values = getattr(lk, name)
+                setattr(lk, name + "_poly", _Poly(ctx, to_coeff(values), n))
+                fr_random(rng)  # Blind
+                commitments.append(params.g_lagrange.msm(values, n))
+            transcript.write_point(commitments[0])
+            transcript.write_point(commitments[1])
+            lks.append(lk)
+        del keep
+        lookups.append(lks)
+    lap("lookup_permuted")
+
     beta = transcript.squeeze_challenge_scalar()   # :440
     gamma = transcript.squeeze_challenge_scalar()  # :443
     beta_l, gamma_l = fr_encode([beta]), fr_encode([gamma])
@@ -526,6 +585,25 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
         permutations.append(committed)
     lap("permutation_commit")
 
+    # ---- lookups: grand products (:466-475, lookup/prover.rs:146-250) ----
+    for lks in lookups:
+        for lk in lks:
+            frac = ctx.alloc(n * 32)
+            ctx._check(ctx.lib.h2b_lookup_product_fractions(
+                ctx.h, lk.permuted_input.ptr, lk.permuted_table.ptr, lk.compressed_input.ptr, lk.compressed_table.ptr,
+                C.c_void_p(beta_l.ctypes.data), C.c_void_p(gamma_l.ctypes.data), n, frac.ptr))
+            z = ctx.running_product(frac, 1, n)  # [1, f0, f0 f1, ...], the first n - bf of them kept (:201-209)
+            frac.free()
+            z.upload(fr_encode([fr_random(rng) for _ in range(bf)]), (n - bf) * 32)
+            fr_random(rng)  # product_blind
+            commitment = params.g_lagrange.msm(z, n)
+            dom.lagrange_to_coeff_device(z)
+            lk.product_poly = _Poly(ctx, z, n)
+            transcript.write_point(commitment)
+            for b in (lk.permuted_input, lk.permuted_table, lk.compressed_input, lk.compressed_table):
+                b.free()
+    lap("lookup_product")
+
     # ---- vanishing argument: random polynomial (vanishing/prover.rs:36-66) ----
     random_poly = _Poly(ctx, fr_random_device(ctx, rng, n), n)
     fr_random(rng)  # random_blind
@@ -545,7 +623,7 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
 
     # ---- h(X) (:502-520) ----
     h_ext = pk.ev.evaluate_h(pk, [[p.buf for p in adv] for adv in advice_polys], instance_polys, challenge_list, y,
-                             beta, gamma, theta, [[] for _ in instances], permutations)
+                             beta, gamma, theta, [[_LookupPolys(lk) for lk in lks] for lks in lookups], permutations)
     for committed in permutations:
         for st in committed.sets:
             st.permutation_product_coset.free()
@@ -594,6 +672,13 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
             transcript.write_scalar(st.poly.eval(x_next))
             if si + 1 < len(committed.sets):
                 transcript.write_scalar(st.poly.eval(x_last))
+    # lookup evaluations (:588-595, lookup/prover.rs:253-283)
+    x_inv = rot(x, -1)
+    for lks in lookups:
+        for lk in lks:
+            for poly, pt in ((lk.product_poly, x), (lk.product_poly, x_next), (lk.permuted_input_poly, x),
+                             (lk.permuted_input_poly, x_inv), (lk.permuted_table_poly, x)):
+                transcript.write_scalar(poly.eval(pt))
     lap("evals")
 
     # ---- the opening queries in the reference's order (:596-645) ----
@@ -607,6 +692,12 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
             queries.append((x_next, st.poly))
         for st in list(reversed(sets))[1:]:
             queries.append((x_last, st.poly))
+        for lk in lookups[ci]:  # lookup/prover.rs:286-323
+            queries.append((x, lk.product_poly))
+            queries.append((x, lk.permuted_input_poly))
+            queries.append((x, lk.permuted_table_poly))
+            queries.append((x_inv, lk.permuted_input_poly))
+            queries.append((x_next, lk.product_poly))
     for c, at in cs.fixed_queries:
         queries.append((rot(x, at), fixed_polys[c.index]))
     for p in sigma_polys:
@@ -626,6 +717,10 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
     for committed in permutations:
         for st in committed.sets:
             st.poly.buf.free()
+    for lks in lookups:
+        for lk in lks:
+            for p in (lk.product_poly, lk.permuted_input_poly, lk.permuted_table_poly):
+                p.buf.free()
     random_poly.buf.free()
     h_buf.free()
 

@@ -47,7 +47,8 @@ enum {
   H2B_ERR_LENGTH = -2,    /* the reference's assert_eq!(len) panics              */
   H2B_ERR_CUDA = -3,      /* CUDA runtime / launch failure, or no device         */
   H2B_ERR_OOM = -4,       /* device or pinned allocation failed                  */
-  H2B_ERR_BAD_OMEGA = -5  /* omega is not a primitive 2^log_n-th root of unity   */
+  H2B_ERR_BAD_OMEGA = -5, /* omega is not a primitive 2^log_n-th root of unity   */
+  H2B_ERR_CONSTRAINT = -6 /* Error::ConstraintSystemFailure (lookup input not in the table) */
 };
 enum { H2B_HOST = 0, H2B_DEVICE = 1 };
 
@@ -196,6 +197,10 @@ typedef struct {
 /* custom gates: values[i] = custom_gates.evaluate(previous_value = values[i]) for every row of the extended
  * domain; `values` is a device array of 2^extended_k elements, in place.        evaluation.rs:336-362 */
 int h2b_evaluate_h_gates(h2b_domain* dom, h2b_graph* graph, const h2b_eval_columns* cols, h2b_fr* values);
+/* The same interpreter over the 2^k rows of the Lagrange basis with rot_scale = 1 (columns are 2^k-element
+ * Lagrange vectors): `evaluate(expression, n, 1, ...)` folded with theta by a Horner graph, as the lookup
+ * argument compresses its expressions.   plonk/evaluation.rs:749-787, plonk/lookup/prover.rs:82-104 */
+int h2b_graph_evaluate_lagrange(h2b_domain* dom, h2b_graph* graph, const h2b_eval_columns* cols, h2b_fr* values);
 /* permutation constraints folded into `values` with y.  column_type: 0 Advice, 1 Fixed, 2 Instance (plonk
  * circuit.rs `Any`); set s covers columns [s*chunk_len, (s+1)*chunk_len); n_sets = 0 is a no-op.
  *                                                                               evaluation.rs:364-444 */
@@ -229,6 +234,18 @@ int h2b_fr_random_counter(h2b_ctx* ctx, uint64_t seed, uint64_t ctr, size_t n, h
 int h2b_permutation_fractions(h2b_domain* dom, const h2b_fr* const* values, const h2b_fr* const* sigma,
                               uint32_t n_cols, uint32_t first_column, const h2b_fr* beta, const h2b_fr* gamma,
                               h2b_fr* out_dev);
+/* permute_expression_pair on the first `usable_rows` elements of two device columns: the input sorted
+ * ascending (Ord for Fr = canonical integer order), each first occurrence's value beside it in the table
+ * column, the unused table values spread over the repeated rows (largest row first, values ascending).
+ * H2B_ERR_CONSTRAINT if an input value is missing from the table.  The caller appends the blinding rows.
+ *                                                                          plonk/lookup/prover.rs:390-475 */
+int h2b_lookup_permute(h2b_ctx* ctx, const h2b_fr* input_dev, const h2b_fr* table_dev, size_t usable_rows,
+                       h2b_fr* permuted_input_dev, h2b_fr* permuted_table_dev);
+/* out[i] = (compressed_input[i] + beta)(compressed_table[i] + gamma) / ((permuted_input[i] + beta)
+ * (permuted_table[i] + gamma)), device arrays of n elements.                plonk/lookup/prover.rs:160-191 */
+int h2b_lookup_product_fractions(h2b_ctx* ctx, const h2b_fr* permuted_input, const h2b_fr* permuted_table,
+                                 const h2b_fr* compressed_input, const h2b_fr* compressed_table,
+                                 const h2b_fr* beta, const h2b_fr* gamma, size_t n, h2b_fr* out_dev);
 /* acc = acc * a + p * b on device arrays (poly * F + &poly: vanishing/prover.rs:131-135, gwc/prover.rs:62-76) */
 int h2b_poly_fma(h2b_ctx* ctx, h2b_fr* acc_dev, const h2b_fr* a, const h2b_fr* p_dev, const h2b_fr* b, size_t n);
 

@@ -15,8 +15,7 @@ GWC multi-opening, Blake2b transcript and `Challenge255`:
                                       (the final pairing check e(L,[s]H) e(R,-H) = 1 of kzg/msm.rs:151-169 is
                                       replaced by the equivalent G1 equation [s]L = R, since tests know s)
 
-Scope: circuits without lookup arguments (the prover panics on them here); lookups are covered for the
-quotient evaluation only (oracle/plonk.py).
+* lookup argument (prover/verifier) -- src/plonk/lookup/prover.rs:55-475, src/plonk/lookup/verifier.rs:35-210
 
 PARITY UNPINNED by reference bytes: the reference cannot be built here (no Rust toolchain) and holds no bn256
 proof fixtures.  Encodings that live in the absent crate halo2curves 0.3.1 are restated from its published
@@ -393,15 +392,19 @@ def _poly_add(a, b):
     return [(x + y) % R_MOD for x, y in zip(a, b)]
 
 
-def _evaluate_h(pk, advice_polys_all, instance_polys_all, challenges, y, beta, gamma, theta, perm_sets_all):
+def _evaluate_h(pk, advice_polys_all, instance_polys_all, challenges, y, beta, gamma, theta, perm_sets_all,
+                lookups_all):
     from .plonk import evaluate_h
     cs, dom = pk.cs, pk.domain
     strip = lambda e: e  # noqa: E731  (evaluate_expression ignores the query index)
     circuits = [dict(advice=[dom.coeff_to_extended(p) for p in adv], instance=[dom.coeff_to_extended(p) for p in ins],
-                     perm_sets=[s["coset"] for s in sets], lookups=[])
-                for adv, ins, sets in zip(advice_polys_all, instance_polys_all, perm_sets_all)]
+                     perm_sets=[s["coset"] for s in sets],
+                     lookups=[dict(product=dom.coeff_to_extended(lk["product_poly"]),
+                                   permuted_input=dom.coeff_to_extended(lk["permuted_input_poly"]),
+                                   permuted_table=dom.coeff_to_extended(lk["permuted_table_poly"])) for lk in lks])
+                for adv, ins, sets, lks in zip(advice_polys_all, instance_polys_all, perm_sets_all, lookups_all)]
     return evaluate_h(k=pk.k, extended_k=dom.extended_k, extended_omega=dom.extended_omega,
-                      gates=[[strip(p) for p in polys] for polys in cs.gates], lookups=[],
+                      gates=[[strip(p) for p in polys] for polys in cs.gates], lookups=cs.lookups,
                       perm_columns=cs.perm_columns, chunk_len=cs.degree() - 2, blinding_factors=cs.blinding_factors(),
                       fixed=pk.fixed_cosets, l0=pk.l0, l_last=pk.l_last, l_active_row=pk.l_active_row,
                       sigma_cosets=pk.perm_cosets, circuits=circuits, challenges=challenges, y=y, beta=beta,
@@ -414,7 +417,6 @@ def create_proof(params: O.ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callab
     witnesses[i](phase, challenges: dict) -> {advice column index: [values]} for the columns of that phase
     (the role of Circuit::synthesize); instances[i] = list of instance columns (lists of ints)."""
     cs, dom, n = pk.cs, pk.domain, pk.n
-    assert not cs.lookups, "lookup arguments are outside the prover oracle's scope"
     for inst in instances:
         assert len(inst) == cs.num_instance_columns  # Error::InvalidInstances
     transcript.common_scalar(pk.transcript_repr)  # :64
@@ -459,6 +461,29 @@ def create_proof(params: O.ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callab
                 challenges[index] = transcript.squeeze_challenge_scalar()
     challenges = [challenges[i] for i in range(cs.num_challenges)]
     theta = transcript.squeeze_challenge_scalar()  # :410
+    # lookups: permuted columns (:412-437, lookup/prover.rs:55-140)
+    lookups_all = []
+    for ci in range(len(instances)):
+        lks = []
+        for inp, tab in cs.lookups:
+            def compress(exprs):
+                acc = [0] * n
+                for e in exprs:
+                    vals = [evaluate_expression(e, i, 1, n, pk.fixed_values, advice_values[ci], instance_values[ci],
+                                                challenges) for i in range(n)]
+                    acc = [(a * theta + v) % R_MOD for a, v in zip(acc, vals)]
+                return acc
+            lk = dict(compressed_input=compress(inp), compressed_table=compress(tab))
+            lk["permuted_input"], lk["permuted_table"] = permute_expression_pair(
+                lk["compressed_input"], lk["compressed_table"], n - (bf + 1), bf, rng)
+            for name in ("permuted_input", "permuted_table"):  # commit_values (:114-125)
+                lk[name + "_poly"] = dom.lagrange_to_coeff(lk[name])
+                fr_random(rng)  # blind
+                lk[name + "_commitment"] = params.commit_lagrange(lk[name])
+            transcript.write_point(lk["permuted_input_commitment"])
+            transcript.write_point(lk["permuted_table_commitment"])
+            lks.append(lk)
+        lookups_all.append(lks)
     beta = transcript.squeeze_challenge_scalar()   # :440
     gamma = transcript.squeeze_challenge_scalar()  # :443
     # permutation argument commit (permutation/prover.rs:44-190)
@@ -499,13 +524,31 @@ def create_proof(params: O.ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callab
             transcript.write_point(commitment)
             sets.append(dict(poly=poly, coset=coset))
         perm_sets_all.append(sets)
+    # lookups: grand products (:466-475, lookup/prover.rs:146-250)
+    for lks in lookups_all:
+        for lk in lks:
+            prod = [(beta + a) * (gamma + t) % R_MOD for a, t in zip(lk["permuted_input"], lk["permuted_table"])]
+            prod = [pow(v, -1, R_MOD) if v else 0 for v in prod]
+            prod = [p * ((a + beta) % R_MOD) % R_MOD * ((t + gamma) % R_MOD) % R_MOD
+                    for p, a, t in zip(prod, lk["compressed_input"], lk["compressed_table"])]
+            z, state = [], 1
+            for cur in [1] + prod:
+                state = state * cur % R_MOD
+                z.append(state)
+            z = z[:n - bf] + [fr_random(rng) for _ in range(bf)]
+            assert len(z) == n
+            fr_random(rng)  # product_blind
+            commitment = params.commit_lagrange(z)
+            lk["product_poly"] = dom.lagrange_to_coeff(z)
+            transcript.write_point(commitment)
     # vanishing argument: random polynomial (vanishing/prover.rs:36-66)
     random_poly = [fr_random(rng) for _ in range(n)]
     fr_random(rng)  # random_blind
     transcript.write_point(params.commit(random_poly))
     y = transcript.squeeze_challenge_scalar()  # :478
     advice_polys = [[dom.lagrange_to_coeff(v) for v in adv] for adv in advice_values]
-    h_ext = _evaluate_h(pk, advice_polys, instance_polys, challenges, y, beta, gamma, theta, perm_sets_all)
+    h_ext = _evaluate_h(pk, advice_polys, instance_polys, challenges, y, beta, gamma, theta, perm_sets_all,
+                        lookups_all)
     # vanishing.construct (vanishing/prover.rs:69-121)
     h_coeff = dom.extended_to_coeff(dom.divide_by_vanishing_poly(h_ext))
     h_pieces = [h_coeff[i:i + n] for i in range(0, len(h_coeff) - n + 1, n)]  # chunks_exact(n)
@@ -538,6 +581,13 @@ def create_proof(params: O.ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callab
             transcript.write_scalar(O.eval_polynomial(s["poly"], x_next))
             if si + 1 < len(sets):
                 transcript.write_scalar(O.eval_polynomial(s["poly"], x_last))
+    # lookup evals (:588-595, lookup/prover.rs:253-283)
+    x_inv = rotate_omega(dom, x, -1)
+    for lks in lookups_all:
+        for lk in lks:
+            for poly, pt in ((lk["product_poly"], x), (lk["product_poly"], x_next), (lk["permuted_input_poly"], x),
+                             (lk["permuted_input_poly"], x_inv), (lk["permuted_table_poly"], x)):
+                transcript.write_scalar(O.eval_polynomial(poly, pt))
     # the opening queries, in the reference's order (:596-645)
     queries: List[Tuple[int, List[int]]] = []
     for ci in range(len(instances)):
@@ -549,6 +599,12 @@ def create_proof(params: O.ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callab
             queries.append((x_next, s["poly"]))
         for s in list(reversed(sets))[1:]:
             queries.append((x_last, s["poly"]))
+        for lk in lookups_all[ci]:  # lookup/prover.rs:286-323
+            queries.append((x, lk["product_poly"]))
+            queries.append((x, lk["permuted_input_poly"]))
+            queries.append((x, lk["permuted_table_poly"]))
+            queries.append((x_inv, lk["permuted_input_poly"]))
+            queries.append((x_next, lk["product_poly"]))
     for col, rot in cs.fixed_queries:
         queries.append((rotate_omega(dom, x, rot), pk.fixed_polys[col]))
     for poly in pk.perm_polys:
@@ -556,6 +612,31 @@ def create_proof(params: O.ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callab
     queries.append((x, h_poly))
     queries.append((x, random_poly))
     gwc_create_proof(params, transcript, queries)
+
+
+def permute_expression_pair(input_expression, table_expression, usable_rows: int, blinding_factors: int, rng):
+    """lookup/prover.rs:390-475: sort the input, put each first occurrence's table value beside it, spread the
+    unused table values over the repeated rows (largest row first, values ascending), then blinding rows."""
+    permuted_input = sorted(input_expression[:usable_rows])
+    leftover = {}
+    for c in table_expression[:usable_rows]:
+        leftover[c] = leftover.get(c, 0) + 1
+    permuted_table = [0] * usable_rows
+    repeated = []
+    for row, v in enumerate(permuted_input):
+        if row == 0 or v != permuted_input[row - 1]:
+            permuted_table[row] = v
+            assert leftover.get(v, 0) > 0, "Error::ConstraintSystemFailure"
+            leftover[v] -= 1
+        else:
+            repeated.append(row)
+    for coeff in sorted(leftover):
+        for _ in range(leftover[coeff]):
+            permuted_table[repeated.pop()] = coeff
+    assert not repeated
+    permuted_input += [fr_random(rng) for _ in range(blinding_factors + 1)]
+    permuted_table += [fr_random(rng) for _ in range(blinding_factors + 1)]
+    return permuted_input, permuted_table
 
 
 def construct_intermediate_sets(queries):
@@ -644,12 +725,13 @@ def verify_proof(params: O.ParamsKZG, s: int, vk: ProvingKey, instances, proof: 
                 if p == phase:
                     challenges[i] = t.squeeze_challenge_scalar()
         theta = t.squeeze_challenge_scalar()
-        assert not cs.lookups
+        lookups_permuted = [[(t.read_point(), t.read_point()) for _ in cs.lookups] for _ in range(num_proofs)]
         beta = t.squeeze_challenge_scalar()
         gamma = t.squeeze_challenge_scalar()
         chunk_len = cs.degree() - 2
         n_sets = (len(cs.perm_columns) + chunk_len - 1) // chunk_len
         perm_commitments = [[t.read_point() for _ in range(n_sets)] for _ in range(num_proofs)]
+        lookups_product = [[t.read_point() for _ in cs.lookups] for _ in range(num_proofs)]
         random_poly_commitment = t.read_point()
         y = t.squeeze_challenge_scalar()
         h_commitments = [t.read_point() for _ in range(dom.quotient_poly_degree)]
@@ -680,6 +762,9 @@ def verify_proof(params: O.ParamsKZG, s: int, vk: ProvingKey, instances, proof: 
                 e["last"] = t.read_scalar() if si + 1 < n_sets else None
                 sets.append(e)
             perm_evals.append(sets)
+        lookup_evals = [[dict(product=t.read_scalar(), product_next=t.read_scalar(), permuted_input=t.read_scalar(),
+                              permuted_input_inv=t.read_scalar(), permuted_table=t.read_scalar())
+                         for _ in cs.lookups] for _ in range(num_proofs)]
         # expected h(x) (verifier.rs:240-327, permutation/verifier.rs:101-196)
         bf = cs.blinding_factors()
         l_evals = l_i_range(dom, x, xn, list(range(-(bf + 1), 1)))
@@ -712,6 +797,22 @@ def verify_proof(params: O.ParamsKZG, s: int, vk: ProvingKey, instances, proof: 
                         right = right * ((col_eval(c) + current_delta + gamma) % R_MOD) % R_MOD
                         current_delta = current_delta * DELTA % R_MOD
                     exprs.append((left - right) * (1 - (l_last + l_blind)) % R_MOD)
+            for (inp, tab), le in zip(cs.lookups, lookup_evals[pi]):  # lookup/verifier.rs:92-163
+                active_rows = (1 - (l_last + l_blind)) % R_MOD
+
+                def compress(es):
+                    acc = 0
+                    for e in es:
+                        acc = (acc * theta + _eval_expr_at(e, fixed_evals, ae, ie, challenges)) % R_MOD
+                    return acc
+                left = le["product_next"] * (le["permuted_input"] + beta) % R_MOD * (le["permuted_table"] + gamma) % R_MOD
+                right = le["product"] * (compress(inp) + beta) % R_MOD * (compress(tab) + gamma) % R_MOD
+                a_minus_s = (le["permuted_input"] - le["permuted_table"]) % R_MOD
+                exprs.append(l_0 * (1 - le["product"]) % R_MOD)
+                exprs.append(l_last * (le["product"] ** 2 - le["product"]) % R_MOD)
+                exprs.append((left - right) * active_rows % R_MOD)
+                exprs.append(l_0 * a_minus_s % R_MOD)
+                exprs.append(a_minus_s * (le["permuted_input"] - le["permuted_input_inv"]) % R_MOD * active_rows % R_MOD)
         expected_h_eval = 0
         for v in exprs:
             expected_h_eval = (expected_h_eval * y + v) % R_MOD
@@ -731,6 +832,13 @@ def verify_proof(params: O.ParamsKZG, s: int, vk: ProvingKey, instances, proof: 
                 queries.append((x_next, c, e["next"]))
             for c, e in list(zip(perm_commitments[pi], perm_evals[pi]))[::-1][1:]:
                 queries.append((x_last, c, e["last"]))
+            x_inv = rotate_omega(dom, x, -1)
+            for (ci_, ct_), cp_, le in zip(lookups_permuted[pi], lookups_product[pi], lookup_evals[pi]):
+                queries.append((x, cp_, le["product"]))          # lookup/verifier.rs:166-208
+                queries.append((x, ci_, le["permuted_input"]))
+                queries.append((x, ct_, le["permuted_table"]))
+                queries.append((x_inv, ci_, le["permuted_input_inv"]))
+                queries.append((x_next, cp_, le["product_next"]))
         for qi, (col, rot) in enumerate(cs.fixed_queries):
             queries.append((rotate_omega(dom, x, rot), vk.fixed_commitments[col], fixed_evals[qi]))
         for c, e in zip(vk.perm_commitments, perm_common):

@@ -239,3 +239,86 @@ def oracle_vk_of(pk):
     return SimpleNamespace(cs=cs, domain=O.EvaluationDomain(cs.degree(), pk.k), n=pk.n, k=pk.k,
                            fixed_commitments=pk.fixed_commitments, perm_commitments=pk.perm_commitments,
                            transcript_repr=pk.transcript_repr)
+
+
+def build_lookup_cs() -> h.ConstraintSystem:
+    """A small circuit with a gate, copy constraints and one lookup argument (degree 5):
+    q_mul * (a * a - b) = 0,  (q_lk * a) in t."""
+    cs = h.ConstraintSystem()
+    a, b = cs.advice_column(), cs.advice_column()
+    q_mul, q_lk, t = cs.fixed_column(), cs.fixed_column(), cs.fixed_column()
+    cs.enable_equality(a)
+    cs.enable_equality(b)
+    qa, qb = cs.query_advice(a), cs.query_advice(b)
+    qm, ql, qt = cs.query_fixed(q_mul), cs.query_fixed(q_lk), cs.query_fixed(t)
+    cs.create_gate("square", [qm * (qa * qa - qb)])
+    cs.lookup("range", [(ql * qa, qt)])
+    return cs
+
+
+def lookup_circuit(k: int, seed: int = 5):
+    """-> (fixed [q_mul, q_lk, t], advice [a, b], copies) satisfying build_lookup_cs() on 2^k rows."""
+    cs = build_lookup_cs()
+    n = 1 << k
+    usable = n - (cs.blinding_factors() + 1)
+    rng = random.Random(seed)
+    table = list(range(usable))
+    a = [rng.randrange(min(usable, 11)) for _ in range(usable)]  # many repeats, all inside the table
+    a[3] = a[2]
+    q_lk = [1 if i < usable - 4 else 0 for i in range(usable)]
+    q_mul = [1 if i % 3 else 0 for i in range(usable)]
+    b = [x * x % O.R_MOD if q else rng.randrange(O.R_MOD) for x, q in zip(a, q_mul)]
+    copies = [((h.ADVICE, 0), 3, (h.ADVICE, 0), 2)]
+    if q_mul[4] and q_mul[7]:
+        a[7] = a[4]
+        b[7] = b[4]
+        copies.append(((h.ADVICE, 1), 7, (h.ADVICE, 1), 4))
+    return [q_mul, q_lk, table], [a, b], copies
+
+
+def check_lookup_proof_bytes(ctx: h.Context, k: int = 5, seed: bytes = b"\x21" * 16):
+    """keygen + create_proof of the lookup circuit: same vk, same proof bytes as the big-integer oracle."""
+    from oracle import prover as OV
+    fixed, advice, copies = lookup_circuit(k)
+    oparams = O.ParamsKZG.setup(k, S_TOXIC)
+    opk = OV.keygen(oparams, oracle_cs(build_lookup_cs()), fixed, copies)
+    t = OV.Blake2bWrite()
+    OV.create_proof(oparams, opk, [lambda phase, ch: dict(enumerate(advice))], [[]], OV.XorShiftRng(seed), t)
+    want = t.finalize()
+    params = h.ParamsKZG.setup(ctx, k, S_TOXIC)
+    pk = h.keygen(params, build_lookup_cs(), fixed, copies)
+    t = h.Blake2bWrite()
+    h.create_proof(params, pk, [lambda phase, ch: dict(enumerate(advice))], [[]], h.XorShiftRng(seed), t)
+    got = t.finalize()
+    assert pk.pinned == opk.debug
+    assert got == want, [i // 32 for i in range(0, len(want), 32) if got[i:i + 32] != want[i:i + 32]][:6]
+    assert OV.verify_proof(oparams, S_TOXIC, opk, [[]], got)
+    # an input value outside the table: Error::ConstraintSystemFailure
+    bad = [list(c) for c in advice]
+    bad[0][0] = 1 << 40
+    try:
+        h.create_proof(params, pk, [lambda phase, ch: dict(enumerate(bad))], [[]], h.XorShiftRng(seed), h.Blake2bWrite())
+        raise AssertionError("expected H2B_ERR_CONSTRAINT")
+    except h.H2BError as e:
+        assert e.code == h.H2B_ERR_CONSTRAINT
+    pk.free()
+
+
+def check_lookup_permute(ctx: h.Context, n: int, seed: int, distinct: int):
+    """h2b_lookup_permute against the oracle's permute_expression_pair on random columns with many repeats."""
+    from oracle import prover as OV
+    rng = random.Random(seed)
+    table = [rng.randrange(O.R_MOD) for _ in range(distinct)]
+    table = (table + [rng.choice(table) for _ in range(n - distinct)])[:n]
+    rng.shuffle(table)
+    inp = [rng.choice(table) for _ in range(n)]
+
+    class Zero:
+        def next_u64(self):
+            return 0
+    want_i, want_t = OV.permute_expression_pair(inp, table, n, -1, Zero())
+    di, dt = ctx.upload_fr(h.fr_encode(inp)), ctx.upload_fr(h.fr_encode(table))
+    oi, ot = ctx.alloc(n * 32), ctx.alloc(n * 32)
+    ctx._check(ctx.lib.h2b_lookup_permute(ctx.h, di.ptr, dt.ptr, n, oi.ptr, ot.ptr))
+    assert h.fr_decode(oi.download(n)) == want_i
+    assert h.fr_decode(ot.download(n)) == want_t

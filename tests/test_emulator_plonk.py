@@ -93,3 +93,12 @@ def test_counter_rng_host_and_device_streams_agree(emu_ctx):
     import ctypes as C
     emu_ctx._check(emu_ctx.lib.h2b_fr_from_u512(emu_ctx.h, C.c_void_p(wide.ctypes.data), 0, 3, out.ptr))
     assert h.fr_decode(out.download(3)) == [(2**512 - 1) % h.R_MOD, 0, (h.R_MOD + 2**256) % h.R_MOD]
+
+
+@pytest.mark.parametrize("n,distinct", [(1, 1), (7, 3), (64, 5), (300, 300), (1000, 37)])
+def test_lookup_permute_vs_oracle(emu_ctx, n, distinct):
+    PC.check_lookup_permute(emu_ctx, n, seed=n, distinct=distinct)
+
+
+def test_create_proof_with_a_lookup_equals_the_oracle(emu_ctx):
+    PC.check_lookup_proof_bytes(emu_ctx, 5)

@@ -59,3 +59,13 @@ def test_create_proof_k14_is_accepted_by_the_reference_verifier(gpu_ctx):
     wrong[2][10] = wrong[2][11]
     assert not OV.verify_proof(vparams, PC.S_TOXIC, vk, [[]], prove(wrong, 1))
     pk.free()
+
+
+@pytest.mark.parametrize("n,distinct", [(1, 1), (7, 3), (1000, 37), (5000, 5000), (1 << 15, 1000)])
+def test_lookup_permute_vs_oracle(gpu_ctx, n, distinct):
+    PC.check_lookup_permute(gpu_ctx, n, seed=n, distinct=distinct)
+
+
+@pytest.mark.parametrize("k", [5, 6])
+def test_create_proof_with_a_lookup_equals_the_oracle(gpu_ctx, k):
+    PC.check_lookup_proof_bytes(gpu_ctx, k)

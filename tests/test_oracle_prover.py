@@ -113,3 +113,45 @@ def test_unsatisfied_witness_does_not_verify(bench_k5):
     bad = [list(c) for c in advice]
     bad[2][4] = (bad[2][4] + 1) % O.R_MOD  # break one gate and one copy constraint
     assert not OV.verify_proof(params, S_TOXIC, pk, [[]], _prove(params, pk, bad))
+
+
+@pytest.fixture(scope="module")
+def lookup_k5():
+    k = 5
+    params = O.ParamsKZG.setup(k, S_TOXIC)
+    cs = PC.oracle_cs(PC.build_lookup_cs())
+    fixed, advice, copies = PC.lookup_circuit(k)
+    return params, cs, OV.keygen(params, cs, fixed, copies), advice
+
+
+def test_permute_expression_pair_known_case():
+    class NoRng:
+        def next_u64(self):
+            return 1
+    inp = [3, 1, 3, 3, 2, 1]
+    tab = [1, 2, 3, 4, 5, 6]
+    pi, pt = OV.permute_expression_pair(inp, tab, 6, 0, NoRng())
+    assert pi[:6] == [1, 1, 2, 3, 3, 3]
+    # first occurrences carry their own value; leftovers {4, 5, 6} ascending go to the repeated rows 5, 4, 1
+    assert pt[:6] == [1, 6, 2, 3, 5, 4]
+    assert len(pi) == len(pt) == 7
+    with pytest.raises(AssertionError):
+        OV.permute_expression_pair([9], [1], 1, 0, NoRng())
+
+
+def test_lookup_circuit_proof_verifies(lookup_k5):
+    params, cs, pk, advice = lookup_k5
+    assert cs.degree() == 5 and len(cs.lookups) == 1
+    proof = _prove(params, pk, advice)
+    assert OV.verify_proof(params, S_TOXIC, pk, [[]], proof)
+    bad = bytearray(proof)
+    bad[32 * 3 + 1] ^= 2  # inside the permuted-table commitment
+    assert not OV.verify_proof(params, S_TOXIC, pk, [[]], bytes(bad))
+
+
+def test_lookup_outside_the_table_fails(lookup_k5):
+    params, cs, pk, advice = lookup_k5
+    bad = [list(c) for c in advice]
+    bad[0][0] = 1 << 40  # q_lk = 1 on row 0 and 2^40 is not in the table
+    with pytest.raises(AssertionError):
+        _prove(params, pk, bad)
