@@ -13,3 +13,4 @@ from .plonk import (ADVICE, FIXED, INSTANCE, Column, ConstraintSystem, Evaluator
 from .prover import (Blake2bWrite, CounterRng, PermutationAssembly, ProverGWC, ProvingKey, XorShiftRng, create_proof,
                      fr_random, fr_random_device, keygen, pinned_debug)
 from . import circuits
+from . import serde

@@ -115,6 +115,9 @@ SYMBOLS = {
     "h2b_lookup_permute": (_I, [_P, _P, _P, _SZ, _P, _P]),
     "h2b_lookup_product_fractions": (_I, [_P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "h2b_graph_evaluate_lagrange": (_I, [_P, _P, _P, _P]),
+    "h2b_g1_check_on_curve": (_I, [_P, _P, _SZ, C.POINTER(_I)]),
+    "h2b_g1_compress": (_I, [_P, _P, _SZ, _U32, _P]),
+    "h2b_g1_decompress": (_I, [_P, _P, _SZ, _U32, _P, C.POINTER(_I)]),
     "h2b_poly_fma": (_I, [_P, _P, _P, _P, _P, _SZ]),
     "h2b_synth_scalars": (_I, [_P, _P, _SZ, _U64, _U32]),
     "h2b_synth_bases": (_I, [_P, _P, _SZ, _U64]),

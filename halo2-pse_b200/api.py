@@ -466,6 +466,7 @@ class ParamsKZG:
         self.n = 1 << k
         self.g = g if isinstance(g, Bases) else Bases(ctx, g, self.n)
         self.g_lagrange = g_lagrange if isinstance(g_lagrange, Bases) else Bases(ctx, g_lagrange, self.n)
+        self.g2 = self.s_g2 = None  # the two G2 points of the verifier half (host integers; see serde.py)
 
     @classmethod
     def setup(cls, ctx: Context, k: int, s: int, precompute: bool = False) -> "ParamsKZG":
@@ -504,7 +505,10 @@ class ParamsKZG:
             if precompute:
                 b.precompute()
             out.append(b)
-        return cls(ctx, k, out[0], out[1])
+        params = cls(ctx, k, out[0], out[1])
+        from . import serde  # :118-119  g2 = generator of G2, s_g2 = [s] g2
+        params.g2, params.s_g2 = serde.G2_GENERATOR, serde.g2_mul(serde.G2_GENERATOR, s % R_MOD)
+        return params
 
     def commit(self, poly, blind=None):
         """:327-334 -- blind is accepted and ignored, as in the reference."""

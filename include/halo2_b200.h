@@ -268,6 +268,16 @@ int h2b_fr_permute3(h2b_ctx* ctx, const h2b_fr* in, h2b_fr* out, uint32_t A, uin
 int h2b_fr_twiddle_rows(h2b_ctx* ctx, h2b_fr* a, const h2b_fr* omega, uint32_t log_n, uint64_t row0,
                         uint32_t nrows, uint32_t ncols);
 
+/* ---- wire formats of G1 points: SerdeFormat of helpers.rs:8-52, for ParamsKZG::read_custom / write_custom
+ * (poly/kzg/commitment.rs:142-244).  RawBytes[Unchecked] = the Montgomery limbs as they are (h2b_bases_upload
+ * takes them unchanged; RawBytes also checks the curve equation); Processed = G1Affine::to_bytes / from_bytes:
+ * 32-byte little-endian canonical x, parity of y in bit `sign_bit` of byte 31 (halo2curves 0.3.1: 7),
+ * identity = zeros.  *all_valid = 0 if some point is off the curve / not canonical. ---- */
+int h2b_g1_check_on_curve(h2b_ctx* ctx, const h2b_g1_affine* pts_dev, size_t n, int* all_valid);
+int h2b_g1_compress(h2b_ctx* ctx, const h2b_g1_affine* pts_dev, size_t n, uint32_t sign_bit, uint8_t* out_host);
+int h2b_g1_decompress(h2b_ctx* ctx, const uint8_t* in_host, size_t n, uint32_t sign_bit, h2b_g1_affine* out_dev,
+                      int* all_valid);
+
 /* ---- device helpers for callers that keep data resident ------------------ */
 int h2b_device_alloc(h2b_ctx* ctx, size_t bytes, void** out);
 void h2b_device_free(h2b_ctx* ctx, void* p);

@@ -69,3 +69,29 @@ def test_lookup_permute_vs_oracle(gpu_ctx, n, distinct):
 @pytest.mark.parametrize("k", [5, 6])
 def test_create_proof_with_a_lookup_equals_the_oracle(gpu_ctx, k):
     PC.check_lookup_proof_bytes(gpu_ctx, k)
+
+
+@pytest.mark.parametrize("fmt", ["Processed", "RawBytes", "RawBytesUnchecked"])
+def test_params_serde_round_trip(gpu_ctx, fmt):
+    """ParamsKZG::write_custom / read_custom in the three SerdeFormats (k = 10); compressed points equal the
+    oracle's to_bytes; an off-curve point is rejected by the checked formats."""
+    import io
+    from halo2_pse_b200 import serde
+    from oracle import bn256 as O
+    from oracle import prover as OV
+    params = h.ParamsKZG.setup(gpu_ctx, 10, PC.S_TOXIC)
+    blob = serde.params_to_bytes(params, fmt)
+    back = serde.read_params(gpu_ctx, io.BytesIO(blob), fmt)
+    assert (back.g.download() == params.g.download()).all()
+    assert (back.g_lagrange.download() == params.g_lagrange.download()).all()
+    assert serde.params_to_bytes(back, fmt) == blob and back.s_g2 == params.s_g2
+    if fmt == "Processed":
+        pts = h.g1_decode(params.g_lagrange.download()[:64])
+        off = 4 + 32 * params.n
+        assert all(blob[off + 32 * i:off + 32 * i + 32] == OV.g1_to_bytes(p) for i, p in enumerate(pts))
+    else:
+        bad = bytearray(blob)
+        bad[4 + 64 * 100 + 40] ^= 8
+        if fmt == "RawBytes":
+            with pytest.raises(h.H2BError):
+                serde.read_params(gpu_ctx, io.BytesIO(bytes(bad)), fmt)
