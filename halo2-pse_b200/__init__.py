@@ -10,7 +10,7 @@ from .api import (Bases, Context, DeviceBuffer, EvaluationDomain, ParamsKZG, Pin
                   g1_jacobian_to_affine)
 from .plonk import (ADVICE, FIXED, INSTANCE, Column, ConstraintSystem, Evaluator, Expression, GraphEvaluator,
                     LookupArgument, PermutationArgument, make_eval_columns)
-from .prover import (Blake2bWrite, CounterRng, PermutationAssembly, ProverGWC, ProvingKey, XorShiftRng, create_proof,
+from .prover import (Blake2bWrite, CounterRng, PermutationAssembly, ProverGWC, ProverSHPLONK, ProvingKey, XorShiftRng, create_proof,
                      fr_random, fr_random_device, keygen, pinned_debug)
 from . import circuits
 from . import serde

@@ -413,8 +413,9 @@ def rotate_omega(dom: EvaluationDomain, omega: int, omega_inv: int, value: int, 
 
 
 def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable], instances: Sequence[Sequence],
-                 rng, transcript: Blake2bWrite, timings: Optional[dict] = None) -> None:
-    """plonk/prover.rs:37-651 with Scheme = KZGCommitmentScheme<Bn256>, P = ProverGWC, E = Challenge255.
+                 rng, transcript: Blake2bWrite, timings: Optional[dict] = None, prover=None) -> None:
+    """plonk/prover.rs:37-651 with Scheme = KZGCommitmentScheme<Bn256>, E = Challenge255 and P = `prover`
+    (ProverGWC by default, or ProverSHPLONK).
     witnesses[i](phase, challenges) -> {advice column index: assigned values (ints or (m, 4) limbs)}: the
     role of Circuit::synthesize through WitnessCollection (:143-285); instances[i] = the instance columns."""
     import time
@@ -704,7 +705,7 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
         queries.append((x, p))
     queries.append((x, h_poly))
     queries.append((x, random_poly))
-    ProverGWC(params).create_proof(rng, transcript, queries)
+    (prover or ProverGWC)(params).create_proof(rng, transcript, queries)
     lap("multiopen")
 
     # per-proof device buffers
@@ -764,3 +765,139 @@ class ProverGWC:
             poly_batch.free()
             transcript.write_point(self.params.g.msm(witness, n - 1))
             witness.free()
+
+
+def lagrange_interpolate(points: Sequence[int], evals: Sequence[int]) -> List[int]:
+    """arithmetic.rs:405-458 on a handful of points (host integers)."""
+    if len(points) != len(evals):
+        raise H2BError(_ffi.H2B_ERR_LENGTH, "assert_eq!(points.len(), evals.len())")
+    if len(points) == 1:
+        return [evals[0] % R_MOD]
+    final = [0] * len(points)
+    for j, xj in enumerate(points):
+        tmp = [1]
+        for k, xk in enumerate(points):
+            if k != j:
+                denom = pow((xj - xk) % R_MOD, -1, R_MOD)
+                tmp = [(a * (-denom * xk) + b * denom) % R_MOD for a, b in zip(tmp + [0], [0] + tmp)]
+        final = [(f + c * evals[j]) % R_MOD for f, c in zip(final, tmp)]
+    return final
+
+
+def evaluate_vanishing_polynomial(roots: Sequence[int], z: int) -> int:
+    """arithmetic.rs:460-478"""
+    acc = 1
+    for r in roots:
+        acc = acc * (z - r) % R_MOD
+    return acc
+
+
+class ProverSHPLONK:
+    """poly/kzg/multiopen/shplonk/prover.rs:94-285 with the rotation sets of shplonk.rs:55-134."""
+
+    QUERY_INSTANCE = False
+
+    def __init__(self, params: ParamsKZG):
+        self.params = params
+
+    @staticmethod
+    def construct_intermediate_sets(queries):
+        """-> ([(points ascending, [(poly, evals at those points)])], super_point_set ascending).
+        Polynomials are told apart by identity, as the reference's PolynomialPointer equality does."""
+        super_points = sorted({pt for pt, _ in queries})
+        by_commitment: List[Tuple["_Poly", set]] = []
+        for pt, p in queries:
+            for poly, rots in by_commitment:
+                if poly is p:
+                    rots.add(pt)
+                    break
+            else:
+                by_commitment.append((p, {pt}))
+        by_set: List[Tuple[set, list]] = []
+        for poly, rots in by_commitment:
+            for rs, polys in by_set:
+                if rs == rots:
+                    polys.append(poly)
+                    break
+            else:
+                by_set.append((rots, [poly]))
+        out = []
+        for rots, polys in by_set:
+            pts = sorted(rots)
+            out.append((pts, [(p, [p.eval(pt) for pt in pts]) for p in polys]))
+        return out, super_points
+
+    def create_proof(self, rng, transcript: Blake2bWrite, queries: Sequence[Tuple[int, "_Poly"]]) -> None:
+        ctx, n = self.params.ctx, self.params.n
+        lib = ctx.lib
+        one_l = fr_encode([1])
+
+        def fma(acc: DeviceBuffer, a: int, p: DeviceBuffer, b: int, count: int) -> None:
+            al, bl = fr_encode([a]), fr_encode([b])
+            ctx._check(lib.h2b_poly_fma(ctx.h, acc.ptr, C.c_void_p(al.ctypes.data), p.ptr, C.c_void_p(bl.ctypes.data),
+                                        count))
+
+        def sub_low(buf: DeviceBuffer, low: Sequence[int]) -> None:
+            """buf[0..len(low)) -= low (the first coefficients only)."""
+            head = fr_decode(buf.download(len(low)))
+            buf.upload(fr_encode([(a - b) % R_MOD for a, b in zip(head, low)]))
+
+        y = transcript.squeeze_challenge_scalar()
+        rotation_sets, super_points = self.construct_intermediate_sets(queries)
+        extended = [(pts, [(p, lagrange_interpolate(pts, evals)) for p, evals in coms]) for pts, coms in rotation_sets]
+        v = transcript.squeeze_challenge_scalar()
+
+        # h(X) = sum_i v^i * (sum_j y^j (p_j - r_j)) / Z_i   (:120-177)
+        h_x = ctx.alloc(n * 32)
+        ctx.memset(h_x, 0)
+        pv = 1
+        for pts, coms in extended:
+            n_x = ctx.alloc(n * 32)
+            ctx.memset(n_x, 0)
+            py = 1
+            for p, low in coms:
+                num = ctx.clone(p.buf, n * 32)
+                sub_low(num, low)
+                fma(n_x, 1, num, py, n)
+                num.free()
+                py = py * y % R_MOD
+            length = n
+            for pt in pts:  # div_by_vanishing: one Kate division per point
+                q_ = ctx.kate_division(n_x, pt, length)
+                n_x.free()
+                n_x = q_
+                length -= 1
+            fma(h_x, 1, n_x, pv, length)  # poly.resize(n, zero) * v^i, accumulated
+            n_x.free()
+            pv = pv * v % R_MOD
+        transcript.write_point(self.params.g.msm(h_x, n))
+        u = transcript.squeeze_challenge_scalar()
+
+        # l(X) = sum_i v^i z_i(u) sum_j y^j (p_j - r_j(u)) - Z_T(u) h(X)   (:183-232)
+        l_x = ctx.alloc(n * 32)
+        ctx.memset(l_x, 0)
+        z_diffs, pv = [], 1
+        for pts, coms in extended:
+            z_i = evaluate_vanishing_polynomial([p for p in super_points if p not in pts], u)
+            py = 1
+            const = 0
+            for p, low in coms:
+                r_eval = 0
+                for c in reversed(low):  # eval_polynomial of the low-degree equivalent at u
+                    r_eval = (r_eval * u + c) % R_MOD
+                w = py * z_i % R_MOD * pv % R_MOD
+                fma(l_x, 1, p.buf, w, n)
+                const = (const + r_eval * w) % R_MOD
+                py = py * y % R_MOD
+            c0 = fr_decode(l_x.download(1))[0]
+            l_x.upload(fr_encode([(c0 - const) % R_MOD]))
+            z_diffs.append(z_i)
+            pv = pv * v % R_MOD
+        zt_eval = evaluate_vanishing_polynomial(super_points, u)
+        fma(l_x, 1, h_x, -zt_eval % R_MOD, n)
+        h_x.free()
+        h2 = ctx.kate_division(l_x, u, n)  # div_by_vanishing(l_x, [u])   (:240)
+        l_x.free()
+        ctx.poly_scale(h2, pow(z_diffs[0], -1, R_MOD), n - 1)
+        transcript.write_point(self.params.g.msm(h2, n - 1))
+        h2.free()

@@ -15,6 +15,8 @@ GWC multi-opening, Blake2b transcript and `Challenge255`:
                                       (the final pairing check e(L,[s]H) e(R,-H) = 1 of kzg/msm.rs:151-169 is
                                       replaced by the equivalent G1 equation [s]L = R, since tests know s)
 
+* SHPLONK multiopen (prover/verifier) -- src/poly/kzg/multiopen/shplonk.rs:55-134, shplonk/prover.rs:26-285,
+                                      shplonk/verifier.rs:52-148; arithmetic.rs:405-478
 * lookup argument (prover/verifier) -- src/plonk/lookup/prover.rs:55-475, src/plonk/lookup/verifier.rs:35-210
 
 PARITY UNPINNED by reference bytes: the reference cannot be built here (no Rust toolchain) and holds no bn256
@@ -412,7 +414,7 @@ def _evaluate_h(pk, advice_polys_all, instance_polys_all, challenges, y, beta, g
 
 
 def create_proof(params: O.ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable], instances, rng,
-                 transcript: Blake2bWrite) -> None:
+                 transcript: Blake2bWrite, multiopen: str = "gwc") -> None:
     """plonk/prover.rs:37-651 with P = ProverGWC (QUERY_INSTANCE = false).
     witnesses[i](phase, challenges: dict) -> {advice column index: [values]} for the columns of that phase
     (the role of Circuit::synthesize); instances[i] = list of instance columns (lists of ints)."""
@@ -611,7 +613,10 @@ def create_proof(params: O.ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callab
         queries.append((x, poly))
     queries.append((x, h_poly))
     queries.append((x, random_poly))
-    gwc_create_proof(params, transcript, queries)
+    if multiopen == "gwc":
+        gwc_create_proof(params, transcript, queries)
+    else:
+        shplonk_create_proof(params, transcript, queries)
 
 
 def permute_expression_pair(input_expression, table_expression, usable_rows: int, blinding_factors: int, rng):
@@ -668,6 +673,117 @@ def gwc_create_proof(params, transcript, queries) -> None:
         transcript.write_point(params.commit(witness))
 
 
+def lagrange_interpolate(points: Sequence[int], evals: Sequence[int]) -> List[int]:
+    """arithmetic.rs:405-458 (coefficients of the interpolant, lowest degree first)."""
+    assert len(points) == len(evals)
+    if len(points) == 1:
+        return [evals[0] % R_MOD]
+    final = [0] * len(points)
+    for j, (xj, ev) in enumerate(zip(points, evals)):
+        tmp = [1]
+        for k, xk in enumerate(points):
+            if k == j:
+                continue
+            denom = pow((xj - xk) % R_MOD, -1, R_MOD)
+            tmp = [(a * (-denom * xk) + b * denom) % R_MOD for a, b in zip(tmp + [0], [0] + tmp)]
+        final = [(f + c * ev) % R_MOD for f, c in zip(final, tmp)]
+    return final
+
+
+def evaluate_vanishing_polynomial(roots: Sequence[int], z: int) -> int:
+    acc = 1
+    for r in roots:
+        acc = acc * (z - r) % R_MOD
+    return acc
+
+
+def shplonk_intermediate_sets(queries, key=lambda q: id(q[1]), get_eval=None):
+    """shplonk.rs:55-134.  queries: (point, commitment, ...); `key` identifies a commitment the way the
+    reference's pointer equality does.  -> (rotation_sets [(points sorted, [(commitment query, evals)])],
+    super_point_set sorted)."""
+    super_points = sorted({q[0] for q in queries})
+    commitment_rotations = []  # [(key, representative query, set of points)]
+    for q in queries:
+        for entry in commitment_rotations:
+            if entry[0] == key(q):
+                entry[2].add(q[0])
+                break
+        else:
+            commitment_rotations.append((key(q), q, {q[0]}))
+    rotation_sets = []  # [(frozenset, [representative queries])]
+    for kk, q, rots in commitment_rotations:
+        for entry in rotation_sets:
+            if entry[0] == rots:
+                entry[1].append(q)
+                break
+        else:
+            rotation_sets.append((rots, [q]))
+    out = []
+    for rots, qs in rotation_sets:
+        pts = sorted(rots)
+        coms = []
+        for q in qs:
+            evals = []
+            for pt in pts:
+                match = next(qq for qq in queries if key(qq) == key(q) and qq[0] == pt)
+                evals.append(get_eval(match))
+            coms.append((q, evals))
+        out.append((pts, coms))
+    return out, super_points
+
+
+def shplonk_create_proof(params, transcript, queries) -> None:
+    """shplonk/prover.rs:108-285; queries: (point, coefficient list)."""
+    n = params.n
+    y = transcript.squeeze_challenge_scalar()
+    rotation_sets, super_points = shplonk_intermediate_sets(
+        queries, key=lambda q: id(q[1]), get_eval=lambda q: O.eval_polynomial(q[1], q[0]))
+    ext = []  # per rotation set: (points, [(poly, low_degree_equivalent)])
+    for pts, coms in rotation_sets:
+        ext.append((pts, [(q[1], lagrange_interpolate(pts, evals)) for q, evals in coms]))
+    v = transcript.squeeze_challenge_scalar()
+    h_x = None
+    pv = 1
+    for pts, coms in ext:
+        n_x, py = None, 1
+        for poly, low in coms:
+            num = list(poly)
+            for i, c in enumerate(low):
+                num[i] = (num[i] - c) % R_MOD
+            num = _poly_scale(num, py)
+            n_x = num if n_x is None else _poly_add(n_x, num)
+            py = py * y % R_MOD
+        for pt in pts:  # div_by_vanishing
+            n_x = O.kate_division(n_x, pt)
+        n_x = n_x + [0] * (n - len(n_x))
+        n_x = _poly_scale(n_x, pv)
+        h_x = n_x if h_x is None else _poly_add(h_x, n_x)
+        pv = pv * v % R_MOD
+    transcript.write_point(params.commit(h_x))
+    u = transcript.squeeze_challenge_scalar()
+    l_x, z_diffs, pv = None, [], 1
+    for pts, coms in ext:
+        diffs = [p for p in super_points if p not in pts]
+        z_i = evaluate_vanishing_polynomial(diffs, u)
+        inner, py = None, 1
+        for poly, low in coms:
+            c = list(poly)
+            c[0] = (c[0] - O.eval_polynomial(low, u)) % R_MOD
+            c = _poly_scale(c, py)
+            inner = c if inner is None else _poly_add(inner, c)
+            py = py * y % R_MOD
+        inner = _poly_scale(_poly_scale(inner, z_i), pv)
+        l_x = inner if l_x is None else _poly_add(l_x, inner)
+        z_diffs.append(z_i)
+        pv = pv * v % R_MOD
+    zt_eval = evaluate_vanishing_polynomial(super_points, u)
+    l_x = [(a - b * zt_eval) % R_MOD for a, b in zip(l_x, h_x)]
+    assert O.eval_polynomial(l_x, u) == 0
+    h2 = O.kate_division(l_x, u)
+    h2 = _poly_scale(h2, pow(z_diffs[0], -1, R_MOD))
+    transcript.write_point(params.commit(h2))
+
+
 # --------------------------------------------------------------------------
 # verifier
 # --------------------------------------------------------------------------
@@ -701,7 +817,7 @@ def _eval_expr_at(e, fixed_evals, advice_evals, instance_evals, challenges) -> i
     return f(e[1]) * e[2] % R_MOD
 
 
-def verify_proof(params: O.ParamsKZG, s: int, vk: ProvingKey, instances, proof: bytes) -> bool:
+def verify_proof(params: O.ParamsKZG, s: int, vk: ProvingKey, instances, proof: bytes, multiopen: str = "gwc") -> bool:
     """plonk/verifier.rs:27-399 + GWC verifier; `vk` is the verifying-key half of the ProvingKey object
     (cs, domain, commitments, transcript_repr); `s` replaces the pairing (see the module docstring)."""
     cs, dom, n = vk.cs, vk.domain, vk.n
@@ -845,6 +961,8 @@ def verify_proof(params: O.ParamsKZG, s: int, vk: ProvingKey, instances, proof: 
             queries.append((x, c, e))
         queries.append((x, h_commitment, expected_h_eval))
         queries.append((x, random_poly_commitment, random_eval))
+        if multiopen != "gwc":
+            return _shplonk_verify(params, s, t, queries)
         # GWC verifier (gwc/verifier.rs:60-129)
         v = t.squeeze_challenge_scalar()
         sets = construct_intermediate_sets(queries)
@@ -871,3 +989,44 @@ def verify_proof(params: O.ParamsKZG, s: int, vk: ProvingKey, instances, proof: 
         return O.g1_mul(left, s) == right  # e(left, [s]H) = e(right, H)
     except AssertionError:
         return False
+
+
+def _shplonk_verify(params, s: int, t: Blake2bRead, queries) -> bool:
+    """shplonk/verifier.rs:52-148; queries: (point, commitment, eval).  Commitments are identified by the
+    position of their first query with the same point object identity rules as the reference's pointer
+    equality: here by the identity of the commitment value held in the verifier's tables."""
+    # the reference compares commitment *references*; equal values from different columns stay distinct, so
+    # key on (id of the tuple object) -- every column's commitment is a distinct object read from the proof
+    # or the vk, and repeated queries of one column reuse that object
+    rotation_sets, super_points = shplonk_intermediate_sets(queries, key=lambda q: id(q[1]), get_eval=lambda q: q[2])
+    y = t.squeeze_challenge_scalar()
+    v = t.squeeze_challenge_scalar()
+    h1 = t.read_point()
+    u = t.squeeze_challenge_scalar()
+    h2 = t.read_point()
+    z_0_diff_inverse = z_0 = 0
+    outer, r_outer_acc, pv = None, 0, 1
+    for i, (pts, coms) in enumerate(rotation_sets):
+        diffs = [p for p in super_points if p not in pts]
+        z_diff_i = evaluate_vanishing_polynomial(diffs, u)
+        if i == 0:
+            z_0 = evaluate_vanishing_polynomial(pts, u)
+            z_0_diff_inverse = pow(z_diff_i, -1, R_MOD)
+            z_diff_i = 1
+        else:
+            z_diff_i = z_diff_i * z_0_diff_inverse % R_MOD
+        inner, r_inner_acc, py = None, 0, 1
+        for q, evals in coms:
+            r_x = lagrange_interpolate(pts, evals)
+            r_inner_acc = (r_inner_acc + py * O.eval_polynomial(r_x, u)) % R_MOD
+            inner = O.g1_add(inner, O.g1_mul(q[1], py))
+            py = py * y % R_MOD
+        outer = O.g1_add(outer, O.g1_mul(inner, pv * z_diff_i % R_MOD))
+        r_outer_acc = (r_outer_acc + pv * r_inner_acc % R_MOD * z_diff_i) % R_MOD
+        pv = pv * v % R_MOD
+    outer = O.g1_add(outer, O.g1_mul(params.g[0], -r_outer_acc % R_MOD))
+    outer = O.g1_add(outer, O.g1_mul(h1, -z_0 % R_MOD))
+    outer = O.g1_add(outer, O.g1_mul(h2, u))
+    if t.pos != len(t.buf):
+        return False
+    return O.g1_mul(h2, s) == outer  # e(h2, [s]H) = e(right, H)

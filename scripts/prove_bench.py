@@ -13,9 +13,10 @@ from tests import plonk_cases as PC
 
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+scheme = sys.argv[3] if len(sys.argv) > 3 else "gwc"
 lib = os.environ.get("H2B_LIB")
 ctx = h.Context(0, lib_path=lib)
-res = {"k": k}
+res = {"k": k, "multiopen": scheme}
 t0 = time.perf_counter()
 params = h.ParamsKZG.setup(ctx, k, PC.S_TOXIC, precompute=True)
 res["setup_s"] = time.perf_counter() - t0
@@ -32,7 +33,8 @@ for rep in range(reps):
     tr = h.Blake2bWrite()
     l0 = ctx.launches
     t0 = time.perf_counter()
-    h.create_proof(params, pk, [witness], [[]], h.CounterRng(1234 + rep), tr, timings=timings)
+    h.create_proof(params, pk, [witness], [[]], h.CounterRng(1234 + rep), tr, timings=timings,
+                   prover=h.ProverSHPLONK if scheme == "shplonk" else h.ProverGWC)
     ctx.sync()
     dt = time.perf_counter() - t0
     if best is None or dt < best[0]:
@@ -46,6 +48,6 @@ from oracle import prover as OV
 from oracle import bn256 as O
 g0 = h.g1_decode(params.g.download()[:1])[0]
 t0 = time.perf_counter()
-res["verified"] = bool(OV.verify_proof(SimpleNamespace(g=[g0]), PC.S_TOXIC, PC.oracle_vk_of(pk), [[]], proof))
+res["verified"] = bool(OV.verify_proof(SimpleNamespace(g=[g0]), PC.S_TOXIC, PC.oracle_vk_of(pk), [[]], proof, multiopen=scheme))
 res["verify_s"] = time.perf_counter() - t0
 print(json.dumps(res))

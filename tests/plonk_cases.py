@@ -322,3 +322,26 @@ def check_lookup_permute(ctx: h.Context, n: int, seed: int, distinct: int):
     ctx._check(ctx.lib.h2b_lookup_permute(ctx.h, di.ptr, dt.ptr, n, oi.ptr, ot.ptr))
     assert h.fr_decode(oi.download(n)) == want_i
     assert h.fr_decode(ot.download(n)) == want_t
+
+
+def check_shplonk_proof_bytes(ctx: h.Context, which: str, k: int = 5, seed: bytes = b"\x33" * 16):
+    """create_proof with ProverSHPLONK: same proof bytes as the big-integer oracle, accepted by its verifier."""
+    from oracle import prover as OV
+    if which == "bench":
+        cs_fn, (fixed, advice, copies) = (lambda: build_cs("bench")), bench_circuit(k, 0xFACE)
+    else:
+        cs_fn, (fixed, advice, copies) = build_lookup_cs, lookup_circuit(k)
+    witness = lambda phase, ch: dict(enumerate(advice))  # noqa: E731
+    oparams = O.ParamsKZG.setup(k, S_TOXIC)
+    opk = OV.keygen(oparams, oracle_cs(cs_fn()), fixed, copies)
+    t = OV.Blake2bWrite()
+    OV.create_proof(oparams, opk, [witness], [[]], OV.XorShiftRng(seed), t, multiopen="shplonk")
+    want = t.finalize()
+    params = h.ParamsKZG.setup(ctx, k, S_TOXIC)
+    pk = h.keygen(params, cs_fn(), fixed, copies)
+    t = h.Blake2bWrite()
+    h.create_proof(params, pk, [witness], [[]], h.XorShiftRng(seed), t, prover=h.ProverSHPLONK)
+    got = t.finalize()
+    assert got == want, [i // 32 for i in range(0, len(want), 32) if got[i:i + 32] != want[i:i + 32]][:6]
+    assert OV.verify_proof(oparams, S_TOXIC, opk, [[]], got, multiopen="shplonk")
+    pk.free()

@@ -102,3 +102,8 @@ def test_lookup_permute_vs_oracle(emu_ctx, n, distinct):
 
 def test_create_proof_with_a_lookup_equals_the_oracle(emu_ctx):
     PC.check_lookup_proof_bytes(emu_ctx, 5)
+
+
+@pytest.mark.parametrize("which", ["bench", "lookup"])
+def test_shplonk_proof_bytes_equal_the_oracle(emu_ctx, which):
+    PC.check_shplonk_proof_bytes(emu_ctx, which)

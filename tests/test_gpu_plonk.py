@@ -95,3 +95,8 @@ def test_params_serde_round_trip(gpu_ctx, fmt):
         if fmt == "RawBytes":
             with pytest.raises(h.H2BError):
                 serde.read_params(gpu_ctx, io.BytesIO(bytes(bad)), fmt)
+
+
+@pytest.mark.parametrize("which", ["bench", "lookup"])
+def test_shplonk_proof_bytes_equal_the_oracle(gpu_ctx, which):
+    PC.check_shplonk_proof_bytes(gpu_ctx, which, k=6)

@@ -155,3 +155,31 @@ def test_lookup_outside_the_table_fails(lookup_k5):
     bad[0][0] = 1 << 40  # q_lk = 1 on row 0 and 2^40 is not in the table
     with pytest.raises(AssertionError):
         _prove(params, pk, bad)
+
+
+def test_lagrange_interpolate_and_vanishing():
+    pts = [3, 7, 11, 12345]
+    poly = [5, 0, 9, 2]
+    evals = [O.eval_polynomial(poly, p) for p in pts]
+    assert OV.lagrange_interpolate(pts, evals) == poly
+    assert OV.lagrange_interpolate([4], [9]) == [9]
+    assert OV.evaluate_vanishing_polynomial(pts, 7) == 0
+    assert OV.evaluate_vanishing_polynomial([1, 2], 5) == 12
+
+
+@pytest.mark.parametrize("which", ["bench", "lookup"])
+def test_shplonk_proofs_verify(bench_k5, lookup_k5, which):
+    params, cs, pk, advice = bench_k5 if which == "bench" else lookup_k5
+    t = OV.Blake2bWrite()
+    OV.create_proof(params, pk, [lambda phase, ch: dict(enumerate(advice))], [[]], OV.XorShiftRng(b"\x05" * 16), t,
+                    multiopen="shplonk")
+    proof = t.finalize()
+    assert OV.verify_proof(params, S_TOXIC, pk, [[]], proof, multiopen="shplonk")
+    assert not OV.verify_proof(params, S_TOXIC, pk, [[]], proof, multiopen="gwc")
+    for pos in (10, len(proof) - 40, len(proof) - 3):
+        bad = bytearray(proof)
+        bad[pos] ^= 1
+        assert not OV.verify_proof(params, S_TOXIC, pk, [[]], bytes(bad), multiopen="shplonk")
+    # always two opening points whatever the number of rotation sets
+    gwc = _prove(params, pk, advice)
+    assert len(proof) <= len(gwc)
