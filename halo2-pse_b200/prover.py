@@ -288,6 +288,21 @@ def _as_limbs(values, n: int) -> np.ndarray:
     return out
 
 
+def _lookup_compress_graphs(cs: ConstraintSystem):
+    """theta-compression of every lookup's input and table expressions over the Lagrange rows
+    (lookup/prover.rs:82-104), as interpreter graphs."""
+    out = []
+    for lookup in cs.lookups:
+        pair = []
+        for exprs in (lookup.input_expressions, lookup.table_expressions):
+            g = GraphEvaluator()
+            parts = tuple(g.add_expression(e) for e in exprs)
+            g.add_calculation((C_HORNER, _vs(VS_CONSTANT, 0), parts, _vs(VS_THETA)))
+            pair.append(g)
+        out.append(tuple(pair))
+    return out
+
+
 def keygen(params: ParamsKZG, cs: ConstraintSystem, fixed_values: Sequence, copies: Sequence = ()) -> ProvingKey:
     """keygen_vk + keygen_pk for a circuit handed over as its assigned fixed columns (what
     Assembly::assign_fixed collects) and its copy constraints (Assembly::copy):
@@ -361,17 +376,7 @@ def keygen(params: ParamsKZG, cs: ConstraintSystem, fixed_values: Sequence, copi
     l_blind.free()
 
     pk.ev = Evaluator(cs)  # keygen.rs:353
-    # theta-compression of every lookup's input and table expressions over the Lagrange rows
-    # (lookup/prover.rs:82-104), as interpreter graphs
-    pk.lookup_compress = []
-    for lookup in cs.lookups:
-        pair = []
-        for exprs in (lookup.input_expressions, lookup.table_expressions):
-            g = GraphEvaluator()
-            parts = tuple(g.add_expression(e) for e in exprs)
-            g.add_calculation((C_HORNER, _vs(VS_CONSTANT, 0), parts, _vs(VS_THETA)))
-            pair.append(g)
-        pk.lookup_compress.append(tuple(pair))
+    pk.lookup_compress = _lookup_compress_graphs(cs)
     pk.pinned = pinned_debug(cs, k, dom.extended_k, omega, pk.fixed_commitments, pk.perm_commitments)
     hsh = hashlib.blake2b(digest_size=64, person=b"Halo2-Verify-Key")
     hsh.update(len(pk.pinned).to_bytes(8, "little") + pk.pinned.encode())

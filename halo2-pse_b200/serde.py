@@ -237,3 +237,133 @@ def params_to_bytes(params: ParamsKZG, fmt: str = RAW_BYTES) -> bytes:
     w = io.BytesIO()
     write_params(params, w, fmt)
     return w.getvalue()
+
+
+# ---- VerifyingKey / ProvingKey write and read (plonk.rs:60-160, 300-354; poly.rs:152-177; helpers.rs:112-146) ----
+def _g1_point_write(p, fmt: str) -> bytes:
+    from .api import g1_encode
+    from .prover import g1_to_bytes
+    return g1_to_bytes(p) if fmt == PROCESSED else g1_encode([p]).tobytes()
+
+
+def _g1_point_read(ctx: Context, reader: BinaryIO, fmt: str):
+    from .api import g1_decode
+    size = 32 if fmt == PROCESSED else 64
+    raw = reader.read(size)
+    if len(raw) != size:
+        raise H2BError(_ffi.H2B_ERR_LENGTH, "unexpected end of file")
+    b = _read_g1(ctx, io.BytesIO(raw), 1, fmt)  # validation / decompression on the device, like the bases
+    p = g1_decode(b.download())[0]
+    b.free()
+    return p
+
+
+def _field_op(ctx: Context, op: int, arr: np.ndarray) -> np.ndarray:
+    out = np.empty_like(arr)
+    ctx._check(ctx.lib.h2b_test_field_op(ctx.h, 0, op, C.c_void_p(arr.ctypes.data), C.c_void_p(arr.ctypes.data),
+                                         C.c_void_p(out.ctypes.data), arr.shape[0]))
+    return out
+
+
+def _poly_write(ctx: Context, buf, count: int, writer: BinaryIO, fmt: str) -> None:
+    """Polynomial::write: u32 big-endian length, then the elements (Processed: canonical repr; else raw limbs)."""
+    writer.write(count.to_bytes(4, "big"))
+    limbs = buf.download(count)
+    if fmt == PROCESSED:
+        limbs = _field_op(ctx, 5, limbs)  # Montgomery -> canonical (to_repr), on the device
+    writer.write(limbs.tobytes())
+
+
+def _poly_read(ctx: Context, reader: BinaryIO, fmt: str, expect: int):
+    head = reader.read(4)
+    if len(head) != 4:
+        raise H2BError(_ffi.H2B_ERR_LENGTH, "unexpected end of file")
+    count = int.from_bytes(head, "big")
+    if count != expect:
+        raise H2BError(_ffi.H2B_ERR_LENGTH, "polynomial length does not match the domain")
+    raw = reader.read(count * 32)
+    if len(raw) != count * 32:
+        raise H2BError(_ffi.H2B_ERR_LENGTH, "unexpected end of file")
+    limbs = np.frombuffer(raw, dtype=np.uint64).reshape(count, 4)
+    if fmt != RAW_BYTES_UNCHECKED:  # from_repr / read_raw reject values >= r
+        top = limbs[:, 3].astype(object) << 192 | limbs[:, 2].astype(object) << 128 | \
+            limbs[:, 1].astype(object) << 64 | limbs[:, 0].astype(object)
+        if any(int(v) >= R_MOD for v in top):
+            raise H2BError(_ffi.H2B_ERR_ARG, "Invalid prime field point encoding")
+    if fmt == PROCESSED:
+        limbs = _field_op(ctx, 4, np.ascontiguousarray(limbs))  # canonical -> Montgomery
+    return ctx.upload_fr(limbs)
+
+
+def _poly_vec_write(ctx, bufs, count, writer, fmt) -> None:
+    writer.write(len(bufs).to_bytes(4, "big"))
+    for b in bufs:
+        _poly_write(ctx, b, count, writer, fmt)
+
+
+def _poly_vec_read(ctx, reader, fmt, expect, expect_len):
+    head = reader.read(4)
+    if len(head) != 4 or int.from_bytes(head, "big") != expect_len:
+        raise H2BError(_ffi.H2B_ERR_LENGTH, "polynomial vector does not match the constraint system")
+    return [_poly_read(ctx, reader, fmt, expect) for _ in range(expect_len)]
+
+
+def write_vk(pk, writer: BinaryIO, fmt: str = RAW_BYTES) -> None:
+    """VerifyingKey::write (plonk.rs:73-91); the mirror has no selectors."""
+    writer.write(int(pk.k).to_bytes(4, "big"))
+    writer.write(len(pk.fixed_commitments).to_bytes(4, "big"))
+    for c in pk.fixed_commitments:
+        writer.write(_g1_point_write(c, fmt))
+    for c in pk.perm_commitments:  # permutation::VerifyingKey::write
+        writer.write(_g1_point_write(c, fmt))
+
+
+def write_pk(pk, writer: BinaryIO, fmt: str = RAW_BYTES) -> None:
+    """ProvingKey::write (plonk.rs:307-318)."""
+    ctx, n, ext = pk.domain.ctx, pk.n, pk.domain.extended_len()
+    write_vk(pk, writer, fmt)
+    for b in (pk.l0, pk.l_last, pk.l_active_row):
+        _poly_write(ctx, b, ext, writer, fmt)
+    _poly_vec_write(ctx, pk.fixed_values, n, writer, fmt)
+    _poly_vec_write(ctx, pk.fixed_polys, n, writer, fmt)
+    _poly_vec_write(ctx, pk.fixed_cosets, ext, writer, fmt)
+    _poly_vec_write(ctx, pk.permutations, n, writer, fmt)        # permutation::ProvingKey::write
+    _poly_vec_write(ctx, pk.permutation_polys, n, writer, fmt)
+    _poly_vec_write(ctx, pk.permutation_cosets, ext, writer, fmt)
+
+
+def read_pk(params: ParamsKZG, cs, reader: BinaryIO, fmt: str = RAW_BYTES):
+    """ProvingKey::read::<_, ConcreteCircuit> (plonk.rs:331-354): `cs` is what ConcreteCircuit::configure builds.
+    The polynomials go straight to the device; the vk hash is recomputed as from_parts does."""
+    import hashlib
+    from .api import EvaluationDomain
+    from .plonk import Evaluator
+    from .prover import ProvingKey, _lookup_compress_graphs, pinned_debug
+    ctx = params.ctx
+    head = reader.read(8)
+    if len(head) != 8:
+        raise H2BError(_ffi.H2B_ERR_LENGTH, "unexpected end of file")
+    k, nfixed = int.from_bytes(head[:4], "big"), int.from_bytes(head[4:], "big")
+    if k != params.k or nfixed != cs.num_fixed_columns:
+        raise H2BError(_ffi.H2B_ERR_LENGTH, "the key does not match the parameters / constraint system")
+    pk = ProvingKey()
+    pk.params, pk.cs, pk.k, pk.n = params, cs, k, 1 << k
+    pk.domain = EvaluationDomain(ctx, cs.degree(), k)
+    n, ext, ncols = pk.n, pk.domain.extended_len(), len(cs.permutation.columns)
+    pk.fixed_commitments = [_g1_point_read(ctx, reader, fmt) for _ in range(nfixed)]
+    pk.perm_commitments = [_g1_point_read(ctx, reader, fmt) for _ in range(ncols)]
+    pk.l0, pk.l_last, pk.l_active_row = (_poly_read(ctx, reader, fmt, ext) for _ in range(3))
+    pk.fixed_values = _poly_vec_read(ctx, reader, fmt, n, nfixed)
+    pk.fixed_polys = _poly_vec_read(ctx, reader, fmt, n, nfixed)
+    pk.fixed_cosets = _poly_vec_read(ctx, reader, fmt, ext, nfixed)
+    pk.permutations = _poly_vec_read(ctx, reader, fmt, n, ncols)
+    pk.permutation_polys = _poly_vec_read(ctx, reader, fmt, n, ncols)
+    pk.permutation_cosets = _poly_vec_read(ctx, reader, fmt, ext, ncols)
+    pk.ev = Evaluator(cs)
+    pk.lookup_compress = _lookup_compress_graphs(cs)
+    pk.pinned = pinned_debug(cs, k, pk.domain.extended_k, pk.domain.constant("omega"), pk.fixed_commitments,
+                             pk.perm_commitments)
+    hsh = hashlib.blake2b(digest_size=64, person=b"Halo2-Verify-Key")
+    hsh.update(len(pk.pinned).to_bytes(8, "little") + pk.pinned.encode())
+    pk.transcript_repr = int.from_bytes(hsh.digest(), "little") % R_MOD
+    return pk

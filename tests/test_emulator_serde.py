@@ -72,3 +72,43 @@ def test_invalid_points_are_rejected(emu_ctx, params):
         serde.read_params(emu_ctx, io.BytesIO(bytes(comp)), serde.PROCESSED)
     with pytest.raises(h.H2BError):
         serde.read_params(emu_ctx, io.BytesIO(bytes(comp[:100])), serde.PROCESSED)  # truncated
+
+
+@pytest.mark.parametrize("fmt", [serde.PROCESSED, serde.RAW_BYTES, serde.RAW_BYTES_UNCHECKED])
+def test_proving_key_round_trip_proves_the_same_bytes(emu_ctx, fmt):
+    """ProvingKey::write / read (plonk.rs:307-354): a key read back from bytes yields the same proof."""
+    from tests import plonk_cases as PC
+    k = 5
+    params = h.ParamsKZG.setup(emu_ctx, k, PC.S_TOXIC)
+    fixed, advice, copies = PC.lookup_circuit(k)
+    pk = h.keygen(params, PC.build_lookup_cs(), fixed, copies)
+    w = io.BytesIO()
+    serde.write_pk(pk, w, fmt)
+    blob = w.getvalue()
+    n, ext, point = 1 << k, pk.domain.extended_len(), (32 if fmt == serde.PROCESSED else 64)
+    assert len(blob) == 8 + (3 + 2) * point + 3 * (4 + 32 * ext) + 2 * (4 + 3 * (4 + 32 * n)) + (4 + 3 * (4 + 32 * ext)) \
+        + 2 * (4 + 2 * (4 + 32 * n)) + (4 + 2 * (4 + 32 * ext))
+    back = serde.read_pk(params, PC.build_lookup_cs(), io.BytesIO(blob), fmt)
+    assert back.pinned == pk.pinned and back.transcript_repr == pk.transcript_repr
+    w2 = io.BytesIO()
+    serde.write_pk(back, w2, fmt)
+    assert w2.getvalue() == blob
+
+    def prove(key):
+        t = h.Blake2bWrite()
+        h.create_proof(params, key, [lambda phase, ch: dict(enumerate(advice))], [[]], h.XorShiftRng(b"\x01" * 16), t)
+        return t.finalize()
+
+    assert prove(back) == prove(pk)
+    with pytest.raises(h.H2BError):
+        serde.read_pk(params, PC.build_cs("bench"), io.BytesIO(blob), fmt)  # another circuit's constraint system
+    with pytest.raises(h.H2BError):
+        serde.read_pk(params, PC.build_lookup_cs(), io.BytesIO(blob[:-7]), fmt)
+    if fmt != serde.RAW_BYTES_UNCHECKED:
+        bad = bytearray(blob)
+        off = 8 + 5 * point + 4  # first element of l0: make it >= r
+        bad[off:off + 32] = b"\xff" * 32
+        with pytest.raises(h.H2BError):
+            serde.read_pk(params, PC.build_lookup_cs(), io.BytesIO(bytes(bad)), fmt)
+    pk.free()
+    back.free()
