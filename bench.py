@@ -240,6 +240,87 @@ def gpu_opmix(ctx, h):
 
 
 PROOF_K = 20
+EVALH_K, EVALH_CPU_K = 20, 18
+
+
+def evalh_case(h, ctx_or_none, k, np):
+    """Random extended-domain columns for the bench circuit's evaluate_h at k (device buffers or host arrays)."""
+    from halo2_pse_b200 import circuits
+    cs = circuits.standard_plonk_cs()
+    ek = k + 2  # degree 5
+    names = ["fixed"] * cs.num_fixed_columns + ["advice"] * cs.num_advice_columns + ["l0", "l_last", "l_act"] + \
+            ["sigma"] * len(cs.permutation.columns) + ["z"]
+    return cs, ek, names
+
+
+def gpu_evaluate_h(ctx, h):
+    """Evaluator::evaluate_h kernels (custom gates + permutation argument) of the bench circuit on 2^22 rows."""
+    import ctypes as C
+    import numpy as np
+    from halo2_pse_b200.plonk import _ptr_array
+    cs, ek, names = evalh_case(h, ctx, EVALH_K, np)
+    dom = h.EvaluationDomain(ctx, cs.degree(), EVALH_K)
+    ext = dom.extended_len()
+    bufs = [ctx.synth_scalars(ext, seed=4000 + i) for i in range(len(names))]
+    fixed, advice = bufs[:4], bufs[4:7]
+    l0, l_last, l_act = bufs[7:10]
+    sigma, zs = bufs[10:13], bufs[13:14]
+    values = ctx.alloc(ext * 32)
+    ctx.memset(values, 0)
+    ev = h.Evaluator(cs)
+    cols, keep = h.make_eval_columns(fixed, advice, [], [], 11, 13, 17, 19)
+    g = ev.custom_gates.compile(ctx)
+    pc = cs.permutation.columns
+    ctype = np.asarray([c.column_type for c in pc], dtype=np.uint32)
+    cidx = np.asarray([c.index for c in pc], dtype=np.uint32)
+    sg, zz = _ptr_array(sigma), _ptr_array(zs)
+    ctx.set_profile(True)
+    tg, tp = [], []
+    for _ in range(5):
+        ctx._check(ctx.lib.h2b_evaluate_h_gates(dom.h, g, C.byref(cols), values.ptr))
+        tg.append(ctx.last_kernel_ms())
+        ctx._check(ctx.lib.h2b_evaluate_h_permutation(dom.h, C.byref(cols), C.c_void_p(ctype.ctypes.data),
+                                                      C.c_void_p(cidx.ctypes.data), len(pc), sg, zz, 1, cs.degree() - 2,
+                                                      cs.blinding_factors(), l0.ptr, l_last.ptr, l_act.ptr, values.ptr))
+        tp.append(ctx.last_kernel_ms())
+    ctx.set_profile(False)
+    gm, pm = sorted(tg)[2], sorted(tp)[2]
+    for b in bufs + [values]:
+        b.free()
+    ev.free()
+    dom.free()
+    mulmods = 6 * ext, 21 * ext  # field multiplications per row: gate graph, permutation constraints
+    return {"what": f"evaluate_h of benches/plonk.rs MyCircuit at k={EVALH_K}: 2^{ek} extended rows, device-resident cosets",
+            "gates_ms": gm, "permutation_ms": pm, "mrows_per_s": ext / ((gm + pm) * 1e-3) / 1e6,
+            "gates_GBps_algorithmic": 9 * 32 * ext / (gm * 1e-3) / 1e9,
+            "permutation_Gmulmod_s": mulmods[1] / (pm * 1e-3) / 1e9,
+            "graph": {"instructions": int(ctx.lib.h2b_graph_num_instructions(g)), "slots": int(ctx.lib.h2b_graph_num_slots(g))}}
+
+
+def cpu_evaluate_h():
+    """The same on the host cores: oracle/ref_cpu.cpp's restatement of evaluation.rs:280-444 (bounded sample)."""
+    import numpy as np
+    import halo2_pse_b200 as h
+    from tests import helpers as H
+    oc = H.load_oracle_c()
+    threads = host_threads()
+    cs, ek, names = evalh_case(h, None, EVALH_CPU_K, np)
+    dom = oc.domain(cs.degree(), EVALH_CPU_K, threads)
+    ext = 1 << ek
+    arrs = [H.rand_fr_limbs(900 + i, ext) for i in range(len(names))]
+    ev = h.Evaluator(cs)  # the calculation list (plain data)
+    gg = ev.custom_gates
+    graph = oc.graph(gg.encode(), H.fr_enc(gg.constants), gg.rotations, gg.num_intermediates)
+    values = np.zeros((ext, 4), dtype=np.uint64)
+    t0 = time.perf_counter()
+    oc.evaluate_h(dom, graph, arrs[:4], arrs[4:7], [], [], 11, 13, 17, 19, [tuple(c) for c in cs.permutation.columns],
+                  arrs[10:13], arrs[13:14], cs.degree() - 2, cs.blinding_factors(), arrs[7], arrs[8], arrs[9], [], [],
+                  values, threads)
+    dt = time.perf_counter() - t0
+    oc.lib.oracle_graph_free(graph)
+    dom.free()
+    return {"seconds": dt, "mrows_per_s": ext / dt / 1e6, "cores": threads, "kind": "port",
+            "sample": f"bench circuit at k={EVALH_CPU_K} (2^{ek} rows), gates + permutation argument"}
 
 
 def gpu_create_proof(ctx, h):
@@ -547,10 +628,11 @@ def run_ours(args):
         sb.free()
 
     opmix = gpu_opmix(ctx, h) if (rank == 0 and world == 1) else None
-    proof = None
+    proof = evalh = None
     if rank == 0 and world == 1:
         pctx = h.Context(local)  # its own context: scratch and MSM workspace sized for k = 20, not for the k = 24 runs
         proof = gpu_create_proof(pctx, h)
+        evalh = gpu_evaluate_h(pctx, h)
         pctx.close()
     if rank == 0:
         total_pts = world * n * args.steps
@@ -581,6 +663,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(steps=1)
             line["create_proof_opmix"] = {"what": OPMIX, "gpu": opmix, "cpu": cpu_opmix()}
             line["create_proof"] = proof
+            line["evaluate_h"] = {"gpu": evalh, "cpu": cpu_evaluate_h()}
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     barrier()

@@ -15,6 +15,8 @@
 //   divide_by_vanishing_poly / distribute_powers_zeta / ifft
 //                                        halo2_proofs/src/poly/domain.rs:226-361
 //   ParamsKZG::commit_lagrange / commit  halo2_proofs/src/poly/kzg/commitment.rs:281-292, 327-334
+//   Evaluator::evaluate_h, GraphEvaluator::evaluate, Calculation::evaluate
+//                                        halo2_proofs/src/plonk/evaluation.rs:36-180, 280-522, 700-746
 //
 // The field and curve arithmetic is NOT in the reference tree: it is
 // halo2curves 0.3.1 (halo2_proofs/Cargo.toml:51).  It is restated here from the
@@ -33,6 +35,7 @@
 #include <cmath>
 #include <functional>
 #include <thread>
+#include <array>
 #include <vector>
 
 typedef unsigned __int128 u128;
@@ -793,6 +796,265 @@ int oracle_synth_bases(uint64_t a, uint64_t d, size_t n, int threads, uint64_t* 
       v[i] = Aff{fmul(pts[i].x, zi2), fmul(pts[i].y, fmul(zi2, zi))};
     }
   });
+  return 0;
+}
+
+
+}  // extern "C"
+
+namespace {
+// ---------------------------------------------------------------------------
+// Evaluator::evaluate_h                                   plonk/evaluation.rs:280-522
+// The calculation stream is the reference's enums flattened in declaration order (the same words the
+// product's h2b_graph_new takes): op, target, operands...; an operand is (kind, a, b).
+// ---------------------------------------------------------------------------
+struct EvalGraph {
+  struct Calc {
+    uint32_t op, target;
+    std::vector<std::array<uint32_t, 3>> src;  // Horner: [start, factor, parts...]
+  };
+  std::vector<Calc> calcs;
+  std::vector<Fr> constants;
+  std::vector<int32_t> rotations;
+  uint32_t num_intermediates;
+};
+
+struct EvalCols {
+  const Fr* const* fixed;
+  const Fr* const* advice;
+  const Fr* const* instance;
+  const Fr* challenges;
+  Fr beta, gamma, theta, y;
+};
+
+static bool parse_graph(const uint32_t* w, size_t n_words, const uint64_t* constants, uint32_t n_constants,
+                        const int32_t* rotations, uint32_t n_rotations, uint32_t n_inter, EvalGraph* g) {
+  size_t pos = 0;
+  auto rd3 = [&](std::array<uint32_t, 3>& s) {
+    if (pos + 3 > n_words) return false;
+    s = {w[pos], w[pos + 1], w[pos + 2]};
+    pos += 3;
+    return true;
+  };
+  while (pos < n_words) {
+    if (pos + 2 > n_words) return false;
+    EvalGraph::Calc c;
+    c.op = w[pos], c.target = w[pos + 1];
+    pos += 2;
+    int nsrc = (c.op <= 2) ? 2 : 1;  // Add, Sub, Mul take two operands; Square, Double, Negate, Store one
+    if (c.op == 6) {                 // Horner(start, factor, nparts, parts...)
+      std::array<uint32_t, 3> s;
+      if (!rd3(s)) return false;
+      c.src.push_back(s);
+      if (!rd3(s)) return false;
+      c.src.push_back(s);
+      if (pos >= n_words) return false;
+      nsrc = (int)w[pos++];
+    }
+    for (int i = 0; i < nsrc; ++i) {
+      std::array<uint32_t, 3> s;
+      if (!rd3(s)) return false;
+      c.src.push_back(s);
+    }
+    g->calcs.push_back(c);
+  }
+  for (uint32_t i = 0; i < n_constants; ++i)
+    g->constants.push_back(Fr{{constants[4 * i], constants[4 * i + 1], constants[4 * i + 2], constants[4 * i + 3]}});
+  g->rotations.assign(rotations, rotations + n_rotations);
+  g->num_intermediates = n_inter;
+  return true;
+}
+
+// get_rotation_idx                                                    evaluation.rs:32-34
+static inline size_t rot_idx(size_t idx, int32_t rot, int32_t rot_scale, int64_t isize) {
+  int64_t v = ((int64_t)idx + (int64_t)rot * rot_scale) % isize;
+  return (size_t)(v < 0 ? v + isize : v);
+}
+
+// GraphEvaluator::evaluate                                            evaluation.rs:700-746
+static Fr graph_evaluate(const EvalGraph& g, std::vector<Fr>& inter, std::vector<size_t>& rots, const EvalCols& c,
+                         const Fr& previous, size_t idx, int32_t rot_scale, int64_t isize) {
+  for (size_t r = 0; r < g.rotations.size(); ++r) rots[r] = rot_idx(idx, g.rotations[r], rot_scale, isize);
+  auto get = [&](const std::array<uint32_t, 3>& s) -> Fr {  // ValueSource::get, evaluation.rs:69-105
+    switch (s[0]) {
+      case 0: return g.constants[s[1]];
+      case 1: return inter[s[1]];
+      case 2: return c.fixed[s[1]][rots[s[2]]];
+      case 3: return c.advice[s[1]][rots[s[2]]];
+      case 4: return c.instance[s[1]][rots[s[2]]];
+      case 5: return c.challenges[s[1]];
+      case 6: return c.beta;
+      case 7: return c.gamma;
+      case 8: return c.theta;
+      case 9: return c.y;
+      default: return previous;
+    }
+  };
+  for (const auto& k : g.calcs) {  // Calculation::evaluate, evaluation.rs:131-179
+    Fr v;
+    switch (k.op) {
+      case 0: v = fadd(get(k.src[0]), get(k.src[1])); break;
+      case 1: v = fsub(get(k.src[0]), get(k.src[1])); break;
+      case 2: v = fmul(get(k.src[0]), get(k.src[1])); break;
+      case 3: { Fr a = get(k.src[0]); v = fsqr(a); break; }
+      case 4: v = fdbl(get(k.src[0])); break;
+      case 5: v = fneg(get(k.src[0])); break;
+      case 6: {
+        const Fr factor = get(k.src[1]);
+        v = get(k.src[0]);
+        for (size_t i = 2; i < k.src.size(); ++i) v = fadd(fmul(v, factor), get(k.src[i]));
+        break;
+      }
+      default: v = get(k.src[0]); break;
+    }
+    inter[k.target] = v;
+  }
+  return g.calcs.empty() ? Fr::zero() : inter[g.calcs.back().target];
+}
+
+// chunks_mut(chunk_size) with chunk_size = ceil(size / num_threads)     evaluation.rs:336-362
+template <class Fn>
+static void chunked_scope(size_t size, int threads, Fn f) {
+  const size_t chunk = (size + (size_t)threads - 1) / (size_t)threads;
+  std::vector<std::thread> pool;
+  for (size_t start = 0; start < size; start += chunk) {
+    const size_t len = std::min(chunk, size - start);
+    pool.emplace_back([=]() { f(start, len); });
+  }
+  for (auto& t : pool) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+void* oracle_graph_new(const uint32_t* words, size_t n_words, const uint64_t* constants, uint32_t n_constants,
+                       const int32_t* rotations, uint32_t n_rotations, uint32_t num_intermediates) {
+  EvalGraph* g = new EvalGraph();
+  if (!parse_graph(words, n_words, constants, n_constants, rotations, n_rotations, num_intermediates, g)) {
+    delete g;
+    return nullptr;
+  }
+  return g;
+}
+void oracle_graph_free(void* g) { delete reinterpret_cast<EvalGraph*>(g); }
+
+// One circuit instance's contribution to h over the extended domain, in place on `values` (host arrays):
+// custom gates, then the permutation argument (n_sets > 0), then every lookup.
+//   scalars: beta, gamma, theta, y (4 x 4 u64);  column pointers: arrays of pointers to 2^extended_k elements
+//   lookups: per lookup a graph handle and 3 cosets (product, permuted_input, permuted_table)
+int oracle_evaluate_h(void* domain, void* gates_graph, const uint64_t* const* fixed, const uint64_t* const* advice,
+                      const uint64_t* const* instance, const uint64_t* challenges, const uint64_t* scalars,
+                      const uint32_t* perm_col_type, const uint32_t* perm_col_index, uint32_t n_perm_cols,
+                      const uint64_t* const* sigma_cosets, const uint64_t* const* z_cosets, uint32_t n_sets,
+                      uint32_t chunk_len, uint32_t blinding_factors, const uint64_t* l0_, const uint64_t* l_last_,
+                      const uint64_t* l_active_, void* const* lookup_graphs, const uint64_t* const* lookup_cosets,
+                      uint32_t n_lookups, uint64_t* values_, int threads) {
+  const Domain* d = reinterpret_cast<const Domain*>(domain);
+  threads = clamp_threads(threads);
+  const size_t size = (size_t)1 << d->extended_k;
+  const int32_t rot_scale = 1 << (d->extended_k - d->k);
+  const int64_t isize = (int64_t)size;
+  auto F4 = [](const uint64_t* p) { return Fr{{p[0], p[1], p[2], p[3]}}; };
+  EvalCols c;
+  c.fixed = reinterpret_cast<const Fr* const*>(fixed);
+  c.advice = reinterpret_cast<const Fr* const*>(advice);
+  c.instance = reinterpret_cast<const Fr* const*>(instance);
+  c.challenges = reinterpret_cast<const Fr*>(challenges);
+  c.beta = F4(scalars), c.gamma = F4(scalars + 4), c.theta = F4(scalars + 8), c.y = F4(scalars + 12);
+  Fr* values = reinterpret_cast<Fr*>(values_);
+  const Fr* l0 = reinterpret_cast<const Fr*>(l0_);
+  const Fr* l_last = reinterpret_cast<const Fr*>(l_last_);
+  const Fr* l_active = reinterpret_cast<const Fr*>(l_active_);
+  const Fr one = Fr::one();
+  const Fr y = c.y, beta = c.beta, gamma = c.gamma;
+
+  // custom gates (:335-362)
+  const EvalGraph& gg = *reinterpret_cast<const EvalGraph*>(gates_graph);
+  chunked_scope(size, threads, [&](size_t start, size_t len) {
+    std::vector<Fr> inter(gg.num_intermediates, Fr::zero());
+    std::vector<size_t> rots(gg.rotations.size(), 0);
+    for (size_t i = 0; i < len; ++i) {
+      const size_t idx = start + i;
+      values[idx] = graph_evaluate(gg, inter, rots, c, values[idx], idx, rot_scale, isize);
+    }
+  });
+
+  // permutations (:364-444)
+  if (n_sets) {
+    static const uint64_t kZeta[4] = {0x8b17ea66b99c90ddull, 0x5bfc41088d8daaa7ull, 0xb3c4d79d41a91758ull, 0x0ull};
+    static const uint64_t kDelta[4] = {0x870e56bbe533e9a2ull, 0x5b5f898e5e963f25ull, 0x64ec26aad4c86e71ull,
+                                       0x09226b6e22c6f0caull};
+    const Fr delta_start = fmul(beta, from_canonical<FrP>(kZeta));
+    const Fr DELTA = from_canonical<FrP>(kDelta);
+    const int32_t last_rotation = -(int32_t)(blinding_factors + 1);
+    auto column = [&](uint32_t j) -> const Fr* {
+      switch (perm_col_type[j]) {
+        case 0: return c.advice[perm_col_index[j]];
+        case 1: return c.fixed[perm_col_index[j]];
+        default: return c.instance[perm_col_index[j]];
+      }
+    };
+    const Fr* const* z = reinterpret_cast<const Fr* const*>(z_cosets);
+    const Fr* const* sg = reinterpret_cast<const Fr* const*>(sigma_cosets);
+    parallelize(values, size, threads, [&](Fr* vals, size_t len, size_t start) {
+      const uint64_t e[4] = {(uint64_t)start, 0, 0, 0};
+      Fr beta_term = fpow(d->extended_omega, e);
+      for (size_t i = 0; i < len; ++i) {
+        const size_t idx = start + i;
+        const size_t r_next = rot_idx(idx, 1, rot_scale, isize);
+        const size_t r_last = rot_idx(idx, last_rotation, rot_scale, isize);
+        Fr v = vals[i];
+        v = fadd(fmul(v, y), fmul(fsub(one, z[0][idx]), l0[idx]));
+        const Fr zl = z[n_sets - 1][idx];
+        v = fadd(fmul(v, y), fmul(fsub(fmul(zl, zl), zl), l_last[idx]));
+        for (uint32_t s2 = 1; s2 < n_sets; ++s2)
+          v = fadd(fmul(v, y), fmul(fsub(z[s2][idx], z[s2 - 1][r_last]), l0[idx]));
+        Fr current_delta = fmul(delta_start, beta_term);
+        for (uint32_t s2 = 0; s2 < n_sets; ++s2) {
+          const uint32_t c0 = s2 * chunk_len, c1 = std::min(c0 + chunk_len, n_perm_cols);
+          Fr left = z[s2][r_next];
+          for (uint32_t j = c0; j < c1; ++j)
+            left = fmul(left, fadd(fadd(column(j)[idx], fmul(beta, sg[j][idx])), gamma));
+          Fr right = z[s2][idx];
+          for (uint32_t j = c0; j < c1; ++j) {
+            right = fmul(right, fadd(fadd(column(j)[idx], current_delta), gamma));
+            current_delta = fmul(current_delta, DELTA);
+          }
+          v = fadd(fmul(v, y), fmul(fsub(left, right), l_active[idx]));
+        }
+        vals[i] = v;
+        beta_term = fmul(beta_term, d->extended_omega);
+      }
+    });
+  }
+
+  // lookups (:446-519)
+  for (uint32_t n = 0; n < n_lookups; ++n) {
+    const EvalGraph& lg = *reinterpret_cast<const EvalGraph*>(lookup_graphs[n]);
+    const Fr* product = reinterpret_cast<const Fr*>(lookup_cosets[3 * n]);
+    const Fr* pin = reinterpret_cast<const Fr*>(lookup_cosets[3 * n + 1]);
+    const Fr* ptab = reinterpret_cast<const Fr*>(lookup_cosets[3 * n + 2]);
+    parallelize(values, size, threads, [&](Fr* vals, size_t len, size_t start) {
+      std::vector<Fr> inter(lg.num_intermediates, Fr::zero());
+      std::vector<size_t> rots(lg.rotations.size(), 0);
+      for (size_t i = 0; i < len; ++i) {
+        const size_t idx = start + i;
+        const Fr table_value = graph_evaluate(lg, inter, rots, c, Fr::zero(), idx, rot_scale, isize);
+        const size_t r_next = rot_idx(idx, 1, rot_scale, isize), r_prev = rot_idx(idx, -1, rot_scale, isize);
+        const Fr a_minus_s = fsub(pin[idx], ptab[idx]);
+        Fr v = vals[i];
+        v = fadd(fmul(v, y), fmul(fsub(one, product[idx]), l0[idx]));
+        v = fadd(fmul(v, y), fmul(fsub(fmul(product[idx], product[idx]), product[idx]), l_last[idx]));
+        v = fadd(fmul(v, y),
+                 fmul(fsub(fmul(fmul(product[r_next], fadd(pin[idx], beta)), fadd(ptab[idx], gamma)),
+                           fmul(product[idx], table_value)),
+                      l_active[idx]));
+        v = fadd(fmul(v, y), fmul(a_minus_s, l0[idx]));
+        v = fadd(fmul(v, y), fmul(fmul(a_minus_s, fsub(pin[idx], pin[r_prev])), l_active[idx]));
+        vals[i] = v;
+      }
+    });
+  }
   return 0;
 }
 

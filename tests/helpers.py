@@ -50,6 +50,10 @@ class OracleC:
         lib.oracle_eval_polynomial.argtypes = [P, SZ, P, I, P]
         lib.oracle_kate_division.argtypes = [P, SZ, P, P]
         lib.oracle_inner_product.argtypes = [P, P, SZ, P]
+        lib.oracle_graph_new.argtypes = [P, SZ, P, U32, P, U32, U32]
+        lib.oracle_graph_new.restype = P
+        lib.oracle_graph_free.argtypes = [P]
+        lib.oracle_evaluate_h.argtypes = [P, P, P, P, P, P, P, P, P, U32, P, P, U32, U32, U32, P, P, P, P, P, U32, P, I]
         self.lib = lib
 
     @staticmethod
@@ -110,6 +114,37 @@ class OracleC:
         out = np.zeros((n, 8), dtype=np.uint64)
         self.lib.oracle_synth_bases(a, d, n, threads, self._p(out))
         return out
+
+    def graph(self, words: np.ndarray, constants: np.ndarray, rotations, num_intermediates: int):
+        """A GraphEvaluator's calculation stream (the reference's enums, flattened) for oracle_evaluate_h."""
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        c = np.ascontiguousarray(constants, dtype=np.uint64).reshape(-1, 4)
+        r = np.ascontiguousarray(rotations, dtype=np.int32)
+        g = self.lib.oracle_graph_new(self._p(w), w.size, self._p(c), c.shape[0], self._p(r), r.size, num_intermediates)
+        assert g, "malformed calculation stream"
+        return g
+
+    def evaluate_h(self, dom: "OracleCDomain", gates_graph, fixed, advice, instance, challenges, beta, gamma, theta, y,
+                   perm_columns, sigma_cosets, z_cosets, chunk_len, blinding_factors, l0, l_last, l_active,
+                   lookup_graphs, lookup_cosets, values: np.ndarray, threads: int = 0) -> np.ndarray:
+        """Evaluator::evaluate_h for one circuit instance, in place on `values` ((2^ek, 4) uint64)."""
+        def ptrs(arrs):
+            a = (C.c_void_p * max(len(arrs), 1))()
+            for i, x in enumerate(arrs):
+                a[i] = x.ctypes.data
+            return a
+        ch = np.ascontiguousarray(challenges if len(challenges) else np.zeros((1, 4), dtype=np.uint64), dtype=np.uint64)
+        sc = np.ascontiguousarray(np.concatenate([fr_enc([v]) for v in (beta, gamma, theta, y)]), dtype=np.uint64)
+        ct = np.asarray([c[0] for c in perm_columns] or [0], dtype=np.uint32)
+        ci = np.asarray([c[1] for c in perm_columns] or [0], dtype=np.uint32)
+        lg = (C.c_void_p * max(len(lookup_graphs), 1))(*lookup_graphs)
+        rc = self.lib.oracle_evaluate_h(dom.h, gates_graph, ptrs(fixed), ptrs(advice), ptrs(instance), self._p(ch),
+                                        self._p(sc), self._p(ct), self._p(ci), len(perm_columns), ptrs(sigma_cosets),
+                                        ptrs(z_cosets), len(z_cosets), chunk_len, blinding_factors, self._p(l0),
+                                        self._p(l_last), self._p(l_active), lg, ptrs(lookup_cosets), len(lookup_graphs),
+                                        self._p(values), threads)
+        assert rc == 0
+        return values
 
     def domain(self, j: int, k: int, threads: int = 0) -> "OracleCDomain":
         return OracleCDomain(self, j, k, threads)

@@ -345,3 +345,88 @@ def check_shplonk_proof_bytes(ctx: h.Context, which: str, k: int = 5, seed: byte
     assert got == want, [i // 32 for i in range(0, len(want), 32) if got[i:i + 32] != want[i:i + 32]][:6]
     assert OV.verify_proof(oparams, S_TOXIC, opk, [[]], got, multiopen="shplonk")
     pk.free()
+
+
+# ---------------------------------------------------------------------------
+# the C++ restatement of evaluate_h (oracle/ref_cpu.cpp): checker at sizes the big-integer oracle cannot reach
+# ---------------------------------------------------------------------------
+def oracle_c_h(oc, cs: h.ConstraintSystem, case, threads: int = 0):
+    """h over the extended domain from oracle_evaluate_h, with cosets from the C++ domain transforms."""
+    import numpy as np
+    dom = oc.domain(cs.degree(), case.k, threads)
+    ext = lambda vals: dom.coeff_to_extended(vals if isinstance(vals, np.ndarray) else H.fr_enc(vals))  # noqa: E731
+    ev = h.Evaluator(cs)  # the calculation lists (plain data); interpreted by the C++ restatement
+
+    def graph(g):
+        return oc.graph(g.encode(), H.fr_enc(g.constants), g.rotations, g.num_intermediates)
+
+    gates, lgs = graph(ev.custom_gates), [graph(g) for g in ev.lookups]
+    fixed = [ext(p) for p in case.fixed_polys]
+    l0, l_last, l_act = ext(case.l0), ext(case.l_last), ext(case.l_active)
+    sigma = [ext(p) for p in case.sigma_polys]
+    values = np.zeros((1 << dom.extended_k, 4), dtype=np.uint64)
+    for c in case.circuits:
+        lcos = []
+        for l in c.lookups:
+            lcos += [ext(l.product), ext(l.permuted_input), ext(l.permuted_table)]
+        oc.evaluate_h(dom, gates, fixed, [ext(p) for p in c.advice], [ext(p) for p in c.instance],
+                      H.fr_enc(case.challenges), case.beta, case.gamma, case.theta, case.y,
+                      [tuple(col) for col in cs.permutation.columns], sigma, [ext(p) for p in c.z], cs.degree() - 2,
+                      cs.blinding_factors(), l0, l_last, l_act, lgs, lcos, values, threads)
+    for g in [gates] + lgs:
+        oc.lib.oracle_graph_free(g)
+    dom.free()
+    return values
+
+
+def random_case_limbs(cs: h.ConstraintSystem, k: int, seed: int, n_circuits: int = 1):
+    """random_case() with numpy limb arrays instead of Python integers (large k)."""
+    n = 1 << k
+    ctr = [seed * 1000]
+
+    def rp():
+        ctr[0] += 1
+        return H.rand_fr_limbs(ctr[0], n)
+    case = SimpleNamespace(k=k, n=n)
+    case.fixed_polys = [rp() for _ in range(cs.num_fixed_columns)]
+    case.l0, case.l_last, case.l_active = rp(), rp(), rp()
+    case.sigma_polys = [rp() for _ in cs.permutation.columns]
+    chunk = cs.degree() - 2
+    n_sets = (len(cs.permutation.columns) + chunk - 1) // chunk
+    case.circuits = [SimpleNamespace(advice=[rp() for _ in range(cs.num_advice_columns)],
+                                     instance=[rp() for _ in range(cs.num_instance_columns)],
+                                     z=[rp() for _ in range(n_sets)],
+                                     lookups=[SimpleNamespace(product=rp(), permuted_input=rp(), permuted_table=rp())
+                                              for _ in cs.lookups]) for _ in range(n_circuits)]
+    rng = random.Random(seed)
+    case.challenges = H.rand_fr(rng, cs.num_challenges)
+    case.y, case.beta, case.gamma, case.theta = H.rand_fr(rng, 4)
+    return case
+
+
+def device_h_limbs(ctx: h.Context, cs: h.ConstraintSystem, case):
+    """device_h() for limb-array cases; returns (2^ek, 4) limbs."""
+    dom = h.EvaluationDomain(ctx, cs.degree(), case.k)
+    up = ctx.upload_fr
+
+    def coset(limbs):
+        src = up(limbs)
+        out = ctx.alloc(dom.extended_len() * 32)
+        dom.coeff_to_extended_device(src, out)
+        src.free()
+        return out
+    pk = SimpleNamespace(domain=dom, cs=cs, fixed_cosets=[coset(p) for p in case.fixed_polys], l0=coset(case.l0),
+                         l_last=coset(case.l_last), l_active_row=coset(case.l_active),
+                         permutation_cosets=[coset(p) for p in case.sigma_polys])
+    ev = h.Evaluator(cs)
+    perms = [SimpleNamespace(sets=[SimpleNamespace(permutation_product_coset=coset(z)) for z in c.z])
+             for c in case.circuits]
+    lookups = [[SimpleNamespace(product_poly=up(l.product), permuted_input_poly=up(l.permuted_input),
+                                permuted_table_poly=up(l.permuted_table)) for l in c.lookups] for c in case.circuits]
+    values = ev.evaluate_h(pk, [[up(p) for p in c.advice] for c in case.circuits],
+                           [[up(p) for p in c.instance] for c in case.circuits], case.challenges, case.y, case.beta,
+                           case.gamma, case.theta, lookups, perms)
+    out = values.download(dom.extended_len())
+    ev.free()
+    dom.free()
+    return out

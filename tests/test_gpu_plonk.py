@@ -100,3 +100,13 @@ def test_params_serde_round_trip(gpu_ctx, fmt):
 @pytest.mark.parametrize("which", ["bench", "lookup"])
 def test_shplonk_proof_bytes_equal_the_oracle(gpu_ctx, which):
     PC.check_shplonk_proof_bytes(gpu_ctx, which, k=6)
+
+
+@pytest.mark.parametrize("variant,k,ncirc", [("bench", 12, 1), ("rich", 11, 2)])
+def test_evaluate_h_vs_cpp_restatement_at_larger_k(gpu_ctx, oracle_c, variant, k, ncirc):
+    """2^13 .. 2^14 extended rows: every row of h equal to the C++ restatement of evaluate_h."""
+    cs = PC.build_cs(variant)
+    case = PC.random_case_limbs(cs, k, seed=k, n_circuits=ncirc)
+    want = PC.oracle_c_h(oracle_c, cs, case)
+    got = PC.device_h_limbs(gpu_ctx, cs, case)
+    assert got.shape == want.shape and (got == want).all()

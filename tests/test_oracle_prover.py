@@ -183,3 +183,15 @@ def test_shplonk_proofs_verify(bench_k5, lookup_k5, which):
     # always two opening points whatever the number of rotation sets
     gwc = _prove(params, pk, advice)
     assert len(proof) <= len(gwc)
+
+
+@pytest.mark.parametrize("variant,ncirc", [("bench", 1), ("rich", 2)])
+def test_cpp_evaluate_h_matches_the_big_integer_oracle(oracle_c, variant, ncirc):
+    """oracle/ref_cpu.cpp's restatement of evaluate_h (GraphEvaluator interpreter, permutation and lookup
+    loops on threads) against the direct expression-tree evaluation of oracle/plonk.py."""
+    from tests import helpers as H
+    cs = PC.build_cs(variant)
+    case = PC.random_case(cs, 4, seed=77, n_circuits=ncirc)
+    want = PC.oracle_h(cs, case)
+    got = H.fr_dec(PC.oracle_c_h(oracle_c, cs, case, threads=3))
+    assert got == want
