@@ -285,6 +285,7 @@ def gpu_evaluate_h(ctx, h):
         tp.append(ctx.last_kernel_ms())
     ctx.set_profile(False)
     gm, pm = sorted(tg)[2], sorted(tp)[2]
+    graph_info = {"instructions": int(ctx.lib.h2b_graph_num_instructions(g)), "slots": int(ctx.lib.h2b_graph_num_slots(g))}
     for b in bufs + [values]:
         b.free()
     ev.free()
@@ -294,7 +295,7 @@ def gpu_evaluate_h(ctx, h):
             "gates_ms": gm, "permutation_ms": pm, "mrows_per_s": ext / ((gm + pm) * 1e-3) / 1e6,
             "gates_GBps_algorithmic": 9 * 32 * ext / (gm * 1e-3) / 1e9,
             "permutation_Gmulmod_s": mulmods[1] / (pm * 1e-3) / 1e9,
-            "graph": {"instructions": int(ctx.lib.h2b_graph_num_instructions(g)), "slots": int(ctx.lib.h2b_graph_num_slots(g))}}
+            "graph": graph_info}
 
 
 def cpu_evaluate_h():

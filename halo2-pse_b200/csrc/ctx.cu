@@ -279,6 +279,15 @@ extern "C" int h2b_ctx_create(int device, h2b_ctx** out) {
     delete ctx;
     return H2B_ERR_CUDA;
   }
+#ifndef H2B_EMU
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = 16ull << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+#endif
   for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
   for (int i = 0; i < 6; ++i) cudaEventCreate(&ctx->pass_ev[i]);
@@ -335,11 +344,28 @@ extern "C" int h2b_ctx_last_ntt_passes(h2b_ctx* ctx, float* ms, int cap) {
   return n;
 }
 
+// Caller-visible device buffers come from the device's stream-ordered memory pool on the context's stream:
+// a prover allocates and frees dozens of polynomial-sized buffers per proof, and cudaMalloc / cudaFree would
+// each synchronise the whole device.  Freed blocks stay cached in the pool (release threshold 16 GiB).
 extern "C" int h2b_device_alloc(h2b_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return H2B_ERR_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+#ifndef H2B_EMU
+  cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 1, ctx->stream);
+  if (e == cudaErrorMemoryAllocation) {  // give cached blocks back and retry once
+    cudaGetLastError();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaMemPoolTrimTo(pool, 0);
+    }
+    e = cudaMallocAsync(out, bytes ? bytes : 1, ctx->stream);
+  }
+  H2B_CUDA(ctx, e);
+#else
   H2B_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+#endif
   return H2B_OK;
 }
 
@@ -347,8 +373,12 @@ extern "C" void h2b_device_free(h2b_ctx* ctx, void* p) {
   if (!ctx || !p) return;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
+#ifndef H2B_EMU
+  cudaFreeAsync(p, ctx->stream);  // ordered after every kernel of this context that may still read it
+#else
   cudaStreamSynchronize(ctx->stream);
   cudaFree(p);
+#endif
 }
 
 extern "C" int h2b_host_alloc(size_t bytes, void** out) {
