@@ -324,42 +324,73 @@ def cpu_evaluate_h():
             "sample": f"bench circuit at k={EVALH_CPU_K} (2^{ek} rows), gates + permutation argument"}
 
 
-def gpu_create_proof(ctx, h):
+def gpu_create_proof(ctx, h, world=1, barrier=None, max_over_ranks=None):
     """keygen + create_proof (KZG/bn256, GWC, Blake2b) of the reference's bench circuit at k = 20 with every
-    commitment, transform, quotient evaluation and opening on the GPU; the witness starts in host memory."""
+    commitment, transform, quotient evaluation and opening on the GPU; the witness starts in host memory.
+    world > 1: ONE proof on all GPUs -- the base vectors are sharded by point range (dist.ShardedBases), every
+    commitment runs on every GPU at once, the rest of the prover is replicated (the Fiat-Shamir chain does not
+    shard); proof bytes are compared with the single-GPU prover's on every rank."""
+    import hashlib
     from halo2_pse_b200 import circuits
     k = PROOF_K
     t0 = time.perf_counter()
-    params = h.ParamsKZG.setup(ctx, k, 0x1234567890ABCDEF1234567890ABCDEF, precompute=True)
+    params = h.ParamsKZG.setup(ctx, k, 0x1234567890ABCDEF1234567890ABCDEF, precompute=(world == 1))
     t_setup = time.perf_counter() - t0
     cs = circuits.standard_plonk_cs()
     fixed, advice, copies = circuits.my_circuit(k, 0xDEADBEEF)
+    witness = lambda phase, ch: dict(enumerate(advice))  # noqa: E731
+    single_digest = None
+    if world > 1:
+        from halo2_pse_b200 import dist as D
+        # the single-GPU proof of the same circuit and rng seed, on this rank alone, as the check value
+        pk1 = h.keygen(params, cs, fixed, copies)
+        tr = h.Blake2bWrite()
+        h.create_proof(params, pk1, [witness], [[]], h.CounterRng(1234 + 3), tr)
+        single_digest = hashlib.sha256(tr.finalize()).hexdigest()
+        pk1.free()
+        params = D.shard_params(params)  # keeps this rank's range (+ window table), frees the full vectors
+        barrier()
     t0 = time.perf_counter()
     pk = h.keygen(params, cs, fixed, copies)
     ctx.sync()
     t_keygen = time.perf_counter() - t0
-    witness = lambda phase, ch: dict(enumerate(advice))  # noqa: E731
     best = None
+    digest = None
     for rep in range(4):
         timings = {}
         tr = h.Blake2bWrite()
         l0 = ctx.launches
+        if barrier:
+            barrier()
         t0 = time.perf_counter()
         h.create_proof(params, pk, [witness], [[]], h.CounterRng(1234 + rep), tr, timings=timings)
         ctx.sync()
         dt = time.perf_counter() - t0
+        if max_over_ranks:
+            (dt,) = max_over_ranks(dt)
+        proof_bytes = tr.finalize()
+        digest = hashlib.sha256(proof_bytes).hexdigest()
         if rep and (best is None or dt < best[0]):
-            best = (dt, timings, ctx.launches - l0, len(tr.finalize()))
+            best = (dt, timings, ctx.launches - l0, len(proof_bytes))
     pk.free()
     params.g.free()
     params.g_lagrange.free()
-    return {"what": f"create_proof of benches/plonk.rs MyCircuit at k={k} over KZG/bn256 (ProverGWC, Blake2bWrite, "
-                    "Challenge255): 11 MSMs, 7 iNTT 2^20, 4 coset NTT 2^22, evaluate_h on 2^22 rows, 1 inverse coset "
-                    "NTT, 17 Horner evaluations, 2 Kate divisions; witness columns start in host memory; proof bytes "
-                    "are checked against the big-integer oracle and the restated verifier in tests/ (k = 5, 6, 14)",
-            "seconds": best[0], "stages_seconds": {kk: round(v, 5) for kk, v in best[1].items()},
-            "gpu_launches": best[2], "proof_bytes": best[3], "keygen_seconds": t_keygen,
-            "setup_seconds_untimed_host_bookkeeping": t_setup, "wall_clock": "host perf_counter, best of 3 after 1 warm-up"}
+    out = {"what": f"create_proof of benches/plonk.rs MyCircuit at k={k} over KZG/bn256 (ProverGWC, Blake2bWrite, "
+                   "Challenge255): 11 MSMs, 7 iNTT 2^20, 4 coset NTT 2^22, evaluate_h on 2^22 rows, 1 inverse coset "
+                   "NTT, 17 Horner evaluations, 2 Kate divisions; witness columns start in host memory; proof bytes "
+                   "are checked against the big-integer oracle and the restated verifier in tests/ (k = 5, 6, 14)",
+           "seconds": best[0], "stages_seconds": {kk: round(v, 5) for kk, v in best[1].items()},
+           "gpu_launches": best[2], "proof_bytes": best[3], "keygen_seconds": t_keygen,
+           "setup_seconds_untimed_host_bookkeeping": t_setup, "wall_clock": "host perf_counter, best of 3 after 1 warm-up"}
+    if world > 1:
+        same = 0.0 if digest == single_digest else 1.0
+        (bad,) = max_over_ranks(same)
+        out["n_gpus"] = world
+        out["sharding"] = ("ONE proof on all GPUs: g / g_lagrange sharded by contiguous point range (each rank holds "
+                           "n/N bases + its window table), every commitment = N local MSMs + all-gather of 64-byte "
+                           "partial points; transforms, quotient evaluation and openings replicated; seconds = max over ranks")
+        out["proof_bytes_equal_single_gpu_prover_on_every_rank"] = bad == 0.0
+    return out
 
 
 def run_reference(args):
@@ -635,6 +666,10 @@ def run_ours(args):
         proof = gpu_create_proof(pctx, h)
         evalh = gpu_evaluate_h(pctx, h)
         pctx.close()
+    elif world > 1 and not os.environ.get("H2B_BENCH_NO_PROOF"):
+        pctx = h.Context(local)
+        proof = gpu_create_proof(pctx, h, world, barrier, max_over_ranks)
+        pctx.close()
     if rank == 0:
         total_pts = world * n * args.steps
         line = {
@@ -660,6 +695,8 @@ def run_ours(args):
             line["four_step_ntt"] = four
         if strong:
             line["msm_k26_sharded"] = strong
+        if world > 1 and proof:
+            line["create_proof"] = proof
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(steps=1)
             line["create_proof_opmix"] = {"what": OPMIX, "gpu": opmix, "cpu": cpu_opmix()}

@@ -464,8 +464,9 @@ class ParamsKZG:
         self.ctx = ctx
         self.k = k
         self.n = 1 << k
-        self.g = g if isinstance(g, Bases) else Bases(ctx, g, self.n)
-        self.g_lagrange = g_lagrange if isinstance(g_lagrange, Bases) else Bases(ctx, g_lagrange, self.n)
+        # anything with the Bases interface passes through (dist.ShardedBases: one range per GPU)
+        self.g = g if hasattr(g, "msm") else Bases(ctx, g, self.n)
+        self.g_lagrange = g_lagrange if hasattr(g_lagrange, "msm") else Bases(ctx, g_lagrange, self.n)
         self.g2 = self.s_g2 = None  # the two G2 points of the verifier half (host integers; see serde.py)
 
     @classmethod

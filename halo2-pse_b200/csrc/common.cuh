@@ -61,6 +61,12 @@ struct h2b_ctx {
   float last_pass_ms[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   int last_npass = 0;
   bool ntt_attr_done = false;
+  // pinned ring for copies from / to PAGEABLE host slices (a Rust Vec, a numpy array): kCopySlots
+  // slots of kCopyChunk bytes, filled by a few host threads while the DMA engine drains them
+  void* copy_slot[16] = {nullptr};
+  cudaEvent_t copy_slot_ev[16] = {nullptr};
+  bool copy_pool_ready = false;
+  struct CopyWorkers* copy_workers = nullptr;  // persistent host threads of the staged copies (ctx.cu)
 };
 
 struct h2b_bases {
@@ -176,6 +182,13 @@ H2B_D void st_fp(Fp<P>* p, const Fp<P>& r) {
 
 int ensure_scratch(h2b_ctx* ctx, size_t bytes);
 int ensure_stage(h2b_ctx* ctx, int which, size_t bytes);
+// Host <-> device copies enqueued on `stream` that do not depend on the host slice being pinned:
+// pinned (or small) slices take one cudaMemcpyAsync; pageable ones are staged through the context's
+// pinned ring by several host threads (the driver's own pageable path is one memcpy thread, ~10 GB/s).
+// h2d returns when every chunk is staged (the DMA may still be in flight on `stream`, as with
+// cudaMemcpyAsync); d2h returns when the bytes are in `dst`.
+int copy_h2d_any(h2b_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, cudaStream_t stream);
+int copy_d2h_any(h2b_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t stream);
 
 // ntt.cu
 int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t log_n, const TwTable** out);

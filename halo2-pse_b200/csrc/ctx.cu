@@ -5,7 +5,68 @@
 
 #include <string.h>
 
+#include <condition_variable>
 #include <functional>
+#include <mutex>
+#include <thread>
+
+// Persistent host threads for the staged copies: spawning (and CUDA-initialising) fresh threads per
+// call costs more than a 32 MiB copy takes.  Worker t >= 1 runs job(t) of the current generation;
+// the caller runs job(0) itself and waits for the rest.
+struct CopyWorkers {
+  std::vector<std::thread> threads;
+  std::mutex m;
+  std::condition_variable cv_job, cv_done;
+  std::function<void(int)> job;
+  uint64_t generation = 0;
+  int active = 0, pending = 0;
+  bool stop = false;
+
+  explicit CopyWorkers(int n, int device) {
+    for (int t = 1; t < n; ++t)
+      threads.emplace_back([this, t, device] {
+        cudaSetDevice(device);
+        uint64_t seen = 0;
+        for (;;) {
+          std::function<void(int)> f;
+          {
+            std::unique_lock<std::mutex> lk(m);
+            cv_job.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            if (t >= active) continue;
+            f = job;
+          }
+          f(t);
+          {
+            std::lock_guard<std::mutex> lk(m);
+            if (--pending == 0) cv_done.notify_one();
+          }
+        }
+      });
+  }
+  void run(int T, const std::function<void(int)>& f) {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      job = f;
+      active = T;
+      pending = T - 1;
+      ++generation;
+    }
+    cv_job.notify_all();
+    f(0);
+    std::unique_lock<std::mutex> lk(m);
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  ~CopyWorkers() {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      stop = true;
+    }
+    cv_job.notify_all();
+    for (auto& t : threads) t.join();
+  }
+};
 
 namespace h2b {
 
@@ -27,6 +88,122 @@ int ensure_scratch(h2b_ctx* ctx, size_t bytes) {
 }
 int ensure_stage(h2b_ctx* ctx, int which, size_t bytes) {
   return grow(ctx, &ctx->stage[which], &ctx->stage_bytes[which], bytes);
+}
+
+// ---------------------------------------------------------------------------
+// Copies from / to pageable host memory through a pinned ring
+// ---------------------------------------------------------------------------
+static constexpr size_t kCopyChunk = 2u << 20;  // bytes per slot
+static constexpr int kCopySlots = 16;           // 2 per thread, up to 8 threads
+static constexpr size_t kCopyStagedMin = 4u << 20;
+
+static int copy_threads() {
+  static int n = [] {
+    int v = 0;
+    if (const char* e = getenv("H2B_COPY_THREADS")) v = atoi(e);
+    if (v <= 0) {
+      const unsigned hw = std::thread::hardware_concurrency();
+      v = hw >= 16 ? 8 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
+    }
+    return v > kCopySlots / 2 ? kCopySlots / 2 : v;
+  }();
+  return n;
+}
+
+static bool host_is_pageable(const void* p) {
+#ifdef H2B_EMU
+  (void)p;
+  return getenv("H2B_EMU_STAGED_COPY") != nullptr;  // the emulator has no pinned memory: opt in (tests)
+#else
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+#endif
+}
+
+static int copy_pool_init(h2b_ctx* ctx) {
+  if (ctx->copy_pool_ready) return H2B_OK;
+  for (int i = 0; i < kCopySlots; ++i) {
+    H2B_CUDA(ctx, cudaMallocHost(&ctx->copy_slot[i], kCopyChunk));
+    H2B_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_slot_ev[i], cudaEventDisableTiming));
+  }
+  ctx->copy_workers = new CopyWorkers(copy_threads(), ctx->device);
+  ctx->copy_pool_ready = true;
+  return H2B_OK;
+}
+
+template <bool TO_DEVICE>
+static int copy_staged(h2b_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+  H2B_TRY(copy_pool_init(ctx));
+  const size_t nchunks = (bytes + kCopyChunk - 1) / kCopyChunk;
+  const int T = (int)std::min<size_t>((size_t)copy_threads(), nchunks);
+  cudaError_t errs[kCopySlots / 2];
+  auto work = [&](int t) {
+    cudaError_t e = cudaSuccess;
+    size_t it = 0;
+    // d2h: the host-side memcpy of a chunk runs one iteration behind its DMA
+    size_t pend_off[2] = {0, 0}, pend_len[2] = {0, 0};
+    for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess; c += (size_t)T, ++it) {
+      const int slot = 2 * t + (int)(it & 1);
+      const size_t off = c * kCopyChunk, len = std::min(kCopyChunk, bytes - off);
+      if (it >= 2 || !TO_DEVICE) e = cudaEventSynchronize(ctx->copy_slot_ev[slot]);  // slot drained / filled
+      if (e != cudaSuccess) break;
+      if (TO_DEVICE) {
+        memcpy(ctx->copy_slot[slot], (const char*)src + off, len);
+        e = cudaMemcpyAsync((char*)dst + off, ctx->copy_slot[slot], len, cudaMemcpyHostToDevice, stream);
+      } else {
+        if (pend_len[it & 1]) memcpy((char*)dst + pend_off[it & 1], ctx->copy_slot[slot], pend_len[it & 1]);
+        e = cudaMemcpyAsync(ctx->copy_slot[slot], (const char*)src + off, len, cudaMemcpyDeviceToHost, stream);
+        pend_off[it & 1] = off;
+        pend_len[it & 1] = len;
+      }
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->copy_slot_ev[slot], stream);
+    }
+    if (!TO_DEVICE)
+      for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        const size_t j = it + (size_t)b;  // the two chunks still in flight, oldest first
+        if (!pend_len[j & 1]) continue;
+        e = cudaEventSynchronize(ctx->copy_slot_ev[2 * t + (int)(j & 1)]);
+        if (e == cudaSuccess) memcpy((char*)dst + pend_off[j & 1], ctx->copy_slot[2 * t + (int)(j & 1)], pend_len[j & 1]);
+        pend_len[j & 1] = 0;
+      }
+    errs[t] = e;
+  };
+  ctx->copy_workers->run(T, work);
+  for (int t = 0; t < T; ++t)
+    if (errs[t] != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, H2B_ERR_CUDA, std::string("staged copy: ") + cudaGetErrorString(errs[t]));
+    }
+  if (TO_DEVICE) {
+    // the ring is reused by the next call: its slots must be drained before they are overwritten, which
+    // the per-slot events guarantee (first two uses of a slot per call skip the wait only if the previous
+    // call's events completed -- make that true here)
+    for (int t = 0; t < T; ++t)
+      for (int b = 0; b < 2; ++b) H2B_CUDA(ctx, cudaEventSynchronize(ctx->copy_slot_ev[2 * t + b]));
+  }
+  return H2B_OK;
+}
+
+int copy_h2d_any(h2b_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return H2B_OK;
+  if (bytes < kCopyStagedMin || copy_threads() < 2 || !host_is_pageable(src_host)) {
+    H2B_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, stream));
+    return H2B_OK;
+  }
+  return copy_staged<true>(ctx, dst_dev, src_host, bytes, stream);
+}
+
+int copy_d2h_any(h2b_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return H2B_OK;
+  if (bytes < kCopyStagedMin || copy_threads() < 2 || !host_is_pageable(dst_host)) {
+    H2B_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+    return H2B_OK;
+  }
+  return copy_staged<false>(ctx, dst_host, src_dev, bytes, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -310,6 +487,11 @@ extern "C" void h2b_ctx_destroy(h2b_ctx* ctx) {
     if (ctx->pass_ev[i]) cudaEventDestroy(ctx->pass_ev[i]);
   for (int i = 0; i < 8; ++i)
     if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
+  delete ctx->copy_workers;
+  for (int i = 0; i < 16; ++i) {
+    if (ctx->copy_slot[i]) cudaFreeHost(ctx->copy_slot[i]);
+    if (ctx->copy_slot_ev[i]) cudaEventDestroy(ctx->copy_slot_ev[i]);
+  }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -393,7 +575,7 @@ extern "C" int h2b_copy_h2d(h2b_ctx* ctx, void* dst_dev, const void* src_host, s
   if (!ctx) return H2B_ERR_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
-  H2B_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  H2B_TRY(copy_h2d_any(ctx, dst_dev, src_host, bytes, ctx->stream));
   H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return H2B_OK;
 }
@@ -402,7 +584,7 @@ extern "C" int h2b_copy_d2h(h2b_ctx* ctx, void* dst_host, const void* src_dev, s
   if (!ctx) return H2B_ERR_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
-  H2B_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  H2B_TRY(copy_d2h_any(ctx, dst_host, src_dev, bytes, ctx->stream));
   H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return H2B_OK;
 }

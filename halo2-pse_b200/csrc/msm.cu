@@ -790,10 +790,9 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
       if (h_scalars) {
         Fr* dst = const_cast<Fr*>(d_scalars) + i0;
         if (nchunk == 1) {
-          H2B_CUDA(ctx, cudaMemcpyAsync(dst, h_scalars + i0, (i1 - i0) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+          H2B_TRY(copy_h2d_any(ctx, dst, h_scalars + i0, (i1 - i0) * sizeof(Fr), st));
         } else {
-          H2B_CUDA(ctx, cudaMemcpyAsync(dst, h_scalars + i0, (i1 - i0) * sizeof(Fr), cudaMemcpyHostToDevice,
-                                        ctx->copy_stream));
+          H2B_TRY(copy_h2d_any(ctx, dst, h_scalars + i0, (i1 - i0) * sizeof(Fr), ctx->copy_stream));
           H2B_CUDA(ctx, cudaEventRecord(ctx->copy_ev[ci], ctx->copy_stream));
           H2B_CUDA(ctx, cudaStreamWaitEvent(st, ctx->copy_ev[ci], 0));
         }
@@ -1006,7 +1005,7 @@ extern "C" int h2b_g1_mul_generator(h2b_ctx* ctx, const h2b_fr* scalars, int loc
   const Fr* d_sc = reinterpret_cast<const Fr*>(scalars);
   if (loc != H2B_DEVICE) {
     H2B_TRY(ensure_stage(ctx, 0, n * sizeof(Fr)));
-    H2B_CUDA(ctx, cudaMemcpyAsync(ctx->stage[0], scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    H2B_TRY(copy_h2d_any(ctx, ctx->stage[0], scalars, n * sizeof(Fr), ctx->stream));
     d_sc = reinterpret_cast<const Fr*>(ctx->stage[0]);
   }
   G1Affine* d_out = reinterpret_cast<G1Affine*>(out);
@@ -1037,10 +1036,12 @@ extern "C" int h2b_bases_upload(h2b_ctx* ctx, const h2b_g1_affine* bases, size_t
   b->n = n;
   b->d_pts = nullptr;
   cudaError_t e = cudaMalloc((void**)&b->d_pts, (n ? n : 1) * sizeof(G1Affine));
-  if (e == cudaSuccess && n)
-    e = cudaMemcpyAsync(b->d_pts, bases, n * sizeof(G1Affine),
-                        loc == H2B_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                        ctx->stream);
+  if (e == cudaSuccess && n) {
+    if (loc == H2B_DEVICE)
+      e = cudaMemcpyAsync(b->d_pts, bases, n * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx->stream);
+    else if (copy_h2d_any(ctx, b->d_pts, bases, n * sizeof(G1Affine), ctx->stream) != H2B_OK)
+      e = cudaErrorInvalidValue;
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
     if (b->d_pts) cudaFree(b->d_pts);

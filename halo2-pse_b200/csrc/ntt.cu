@@ -659,15 +659,12 @@ struct Staged {
     }
     H2B_TRY(ensure_stage(ctx, which, count * sizeof(Fr)));
     dev = reinterpret_cast<Fr*>(ctx->stage[which]);
-    if (copy)
-      H2B_CUDA(ctx, cudaMemcpyAsync(dev, p, count * sizeof(Fr), cudaMemcpyHostToDevice,
-                                    ctx->stream));
+    if (copy) H2B_TRY(copy_h2d_any(ctx, dev, p, count * sizeof(Fr), ctx->stream));
     return H2B_OK;
   }
   int out(h2b_fr* p, int loc, size_t count) {
     if (loc == H2B_DEVICE) return H2B_OK;
-    H2B_CUDA(ctx,
-             cudaMemcpyAsync(p, dev, count * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    H2B_TRY(copy_d2h_any(ctx, p, dev, count * sizeof(Fr), ctx->stream));
     H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return H2B_OK;
   }
@@ -718,7 +715,7 @@ extern "C" int h2b_domain_new(h2b_ctx* ctx, uint32_t j, uint32_t k, h2b_domain**
   if (!ctx) return H2B_ERR_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   if (!out) return fail(ctx, H2B_ERR_ARG, "null pointer");
-  if (j < 2) return fail(ctx, H2B_ERR_ARG, "j < 2");
+  if (j < 1) return fail(ctx, H2B_ERR_ARG, "j < 1");  // j = 1 (quotient degree 0, extended_k = k) is what the reference's own tests build (domain.rs:494, kzg/commitment.rs:374)
   // Fr::ROOT_OF_UNITY (order 2^28) and Fr::ZETA, canonical values
   static const uint64_t kRoot[4] = {0xd34f1ed960c37c9cull, 0x3215cf6dd39329c8ull,
                                     0x98865ea93dd31f74ull, 0x03ddb9f5166d18b7ull};
@@ -885,10 +882,10 @@ extern "C" int h2b_extended_to_coeff_batch(h2b_domain* d, const h2b_fr* in, size
   if (!d) return H2B_ERR_ARG;
   h2b_ctx* ctx = d->ctx;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  if (!in || !out) return fail(ctx, H2B_ERR_ARG, "null pointer");
-  if (ncols == 0) return H2B_OK;
   const size_t ne = (size_t)1 << d->extended_k;
   const size_t nq = ((size_t)1 << d->k) * d->quotient_poly_degree;
+  if (!in || (!out && nq)) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (ncols == 0 || nq == 0) return H2B_OK;  // j = 1: truncate(0), an empty Vec (domain.rs:299-300)
   if (in_stride < ne || out_stride < nq)
     return fail(ctx, H2B_ERR_LENGTH, "stride shorter than the polynomial");  // domain.rs:282
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -234,7 +234,7 @@ int stage_in(h2b_ctx* ctx, int which, const h2b_fr* p, int loc, size_t count, co
     return H2B_OK;
   }
   H2B_TRY(ensure_stage(ctx, which, (count ? count : 1) * sizeof(Fr)));
-  H2B_CUDA(ctx, cudaMemcpyAsync(ctx->stage[which], p, count * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  H2B_TRY(copy_h2d_any(ctx, ctx->stage[which], p, count * sizeof(Fr), ctx->stream));
   *dev = reinterpret_cast<const Fr*>(ctx->stage[which]);
   return H2B_OK;
 }

@@ -97,19 +97,110 @@ class ShardedMSM:
             sp, loc, n = C.c_void_p(arr.ctypes.data), _ffi.H2B_HOST, arr.shape[0]
         self.ctx._check(self.ctx.lib.h2b_msm_affine(self.ctx.h, self.bases.h, 0, sp, loc, n,
                                                     C.c_void_p(out.ctypes.data)))
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
-            return g1_decode(out)[0]
-        world = dist.get_world_size(self.group)
-        dev = _group_device(self.group)
-        mine = torch.from_numpy(out.view(np.int64)).to(dev)
-        parts = torch.empty(world * 8, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(parts, mine, group=self.group)
-        allp = np.ascontiguousarray(parts.cpu().numpy().view(np.uint64)).reshape(world, 8)
-        total = np.zeros(8, dtype=np.uint64)
-        rc = self.ctx.lib.h2b_g1_sum(C.c_void_p(allp.ctypes.data), world, C.c_void_p(total.ctypes.data))
-        if rc != 0:
-            raise H2BError(rc, "h2b_g1_sum")
-        return g1_decode(total)[0]
+        return _gather_fold(self.ctx, out, self.group)
+
+
+def _gather_fold(ctx: Context, out: np.ndarray, group=None):
+    """All-gather of every rank's 64-byte partial point, folded in rank order with h2b_g1_sum
+    (`.fold` of the per-chunk results, arithmetic.rs:153); the same affine point on every rank."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return g1_decode(out)[0]
+    world = dist.get_world_size(group)
+    dev = _group_device(group)
+    mine = torch.from_numpy(out.view(np.int64)).to(dev)
+    parts = torch.empty(world * 8, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(parts, mine, group=group)
+    allp = np.ascontiguousarray(parts.cpu().numpy().view(np.uint64)).reshape(world, 8)
+    total = np.zeros(8, dtype=np.uint64)
+    rc = ctx.lib.h2b_g1_sum(C.c_void_p(allp.ctypes.data), world, C.c_void_p(total.ctypes.data))
+    if rc != 0:
+        raise H2BError(rc, "h2b_g1_sum")
+    return g1_decode(total)[0]
+
+
+class ShardedBases:
+    """A base vector of a ParamsKZG (`g` or `g_lagrange`) sharded by contiguous point range over the
+    ranks of `group`, behind the interface of `api.Bases`: `msm(scalars, n, offset, scalar_offset)`
+    is best_multiexp(scalars[scalar_offset..][..n], bases[offset..offset + n]) and returns the same
+    affine point on every rank.  Rank g keeps only bases[start_g, end_g) (and its window table) on its
+    device; every rank passes the WHOLE scalar vector (the prover's polynomials are replicated, the
+    Fiat-Shamir chain is not shardable) and multiplies its own range of it.  No data-path collective:
+    the partial points (64 B per rank) are all-gathered and folded.
+
+    This is what makes `create_proof` a multi-GPU call: `ParamsKZG(ctx, k, ShardedBases, ShardedBases)`
+    goes through `keygen` / `create_proof` unchanged and every commitment runs on all GPUs at once."""
+
+    def __init__(self, ctx: Context, local: Bases, n_total: int, start: int, group=None):
+        self.ctx, self.local, self.n, self.start, self.group = ctx, local, n_total, start, group
+        self.end = start + len(local)
+
+    @classmethod
+    def from_full(cls, ctx: Context, full: Bases, group=None, precompute: bool = True,
+                  free_full: bool = True) -> "ShardedBases":
+        """Keep this rank's range of a replicated device-resident base vector (device-to-device copy)."""
+        import torch.distributed as dist
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n = len(full)
+        s, e = shard_range(n, rank, world)
+        base_ptr = int(ctx.lib.h2b_bases_device_ptr(full.h) or 0)
+        local = Bases(ctx, C.c_void_p(base_ptr + s * 64), e - s, H2B_DEVICE)
+        if precompute and e > s:
+            local.precompute()
+        if free_full:
+            full.free()
+        return cls(ctx, local, n, s, group)
+
+    def __len__(self) -> int:
+        return self.n
+
+    @property
+    def table_window_bits(self) -> int:
+        return self.local.table_window_bits
+
+    def precompute(self, window_bits: int = 0) -> "ShardedBases":
+        if len(self.local):
+            self.local.precompute(window_bits)
+        return self
+
+    def msm(self, scalars, n: Optional[int] = None, offset: int = 0, affine: bool = True, scalar_offset: int = 0):
+        if not isinstance(scalars, DeviceBuffer):
+            arr = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+            n = arr.shape[0] - scalar_offset if n is None else n
+        elif n is None:
+            raise H2BError(_ffi.H2B_ERR_ARG, "n required for device scalars")
+        if offset + n > self.n:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert!(bases.len() >= size)")  # poly/kzg/commitment.rs:290,332
+        lo, hi = max(self.start, offset), min(self.end, offset + n)
+        out = np.zeros(8, dtype=np.uint64)  # identity if this rank's range misses the slice
+        if hi > lo:
+            so = scalar_offset + (lo - offset)
+            if isinstance(scalars, DeviceBuffer):
+                if (so + hi - lo) * 32 > scalars.nbytes:
+                    raise H2BError(_ffi.H2B_ERR_LENGTH, "scalar slice outside the buffer")
+                sp, loc = scalars.at(so * 32), H2B_DEVICE
+            else:
+                sub = arr[so:so + hi - lo]
+                sp, loc = C.c_void_p(sub.ctypes.data), _ffi.H2B_HOST
+            self.ctx._check(self.ctx.lib.h2b_msm_affine(self.ctx.h, self.local.h, lo - self.start, sp, loc,
+                                                        hi - lo, C.c_void_p(out.ctypes.data)))
+        return _gather_fold(self.ctx, out, self.group)
+
+    def free(self) -> None:
+        self.local.free()
+
+
+def shard_params(params, group=None, precompute: bool = True):
+    """ParamsKZG with `g` and `g_lagrange` replaced by their ShardedBases (the replicated full vectors
+    are released): keygen and create_proof on the result commit on every GPU of the group."""
+    from .api import ParamsKZG
+    out = ParamsKZG(params.ctx, params.k,
+                    ShardedBases.from_full(params.ctx, params.g, group, precompute),
+                    ShardedBases.from_full(params.ctx, params.g_lagrange, group, precompute))
+    out.g2, out.s_g2 = params.g2, params.s_g2
+    return out
 
 
 class FourStepNTT:

@@ -1,0 +1,483 @@
+// halo2_b200.hpp -- C++ host side above the C ABI (include/halo2_b200.h): the reference's own
+// function and type names for the hot path, so that code written against halo2_proofs reads the
+// same here.  The reference is Rust (no cargo/rustc in this image); this header is the compiled-code
+// mirror a caller links instead of the Rust crate, and the model for the Rust shim in INTEGRATION.md.
+//
+//   halo2_proofs::arithmetic::best_multiexp / best_fft / eval_polynomial / kate_division /
+//                             compute_inner_product            halo2_proofs/src/arithmetic.rs:132,171,304,348,334
+//   halo2_proofs::poly::Polynomial<Basis>, Rotation             halo2_proofs/src/poly.rs:52-72, 229-330
+//   halo2_proofs::poly::EvaluationDomain                        halo2_proofs/src/poly/domain.rs:19-480
+//   halo2_proofs::poly::kzg::ParamsKZG (commit half)            halo2_proofs/src/poly/kzg/commitment.rs:23-131, 281-334
+//
+// Error behaviour: where the reference panics (assert_eq! on lengths, assert!(bases.len() >= size)),
+// these throw halo2_proofs::Panic with the reference's file:line in the message; a CUDA / allocation
+// failure throws BackendError.  There is no CPU fallback: every call goes to the CUDA library, and
+// without a usable device the first call throws.
+//
+// Threading: every calling thread gets its own context (stream + scratch) on first use, as the ABI
+// asks of concurrent callers (rayon workers call the transforms concurrently in
+// plonk/permutation/keygen.rs:214-234); objects that own device state (EvaluationDomain, ParamsKZG)
+// are bound to the context of the thread that built them and may be used from any thread (the ABI
+// serialises calls per context).
+#ifndef HALO2_B200_HPP
+#define HALO2_B200_HPP
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "halo2_b200.h"
+
+namespace halo2_proofs {
+
+struct Panic : std::logic_error {  // the reference's panic!/assert!
+  using std::logic_error::logic_error;
+};
+struct BackendError : std::runtime_error {  // no counterpart in the reference (it cannot fail this way)
+  using std::runtime_error::runtime_error;
+};
+
+namespace detail {
+struct Backend {
+  h2b_ctx* ctx = nullptr;
+  Backend() {
+    const char* e = std::getenv("H2B_DEVICE");
+    const int rc = h2b_ctx_create(e ? std::atoi(e) : 0, &ctx);
+    if (rc != H2B_OK) throw BackendError("h2b_ctx_create failed (no CUDA device? there is no CPU fallback): rc=" + std::to_string(rc));
+  }
+  ~Backend() {
+    if (ctx) h2b_ctx_destroy(ctx);
+  }
+  Backend(const Backend&) = delete;
+  Backend& operator=(const Backend&) = delete;
+};
+inline Backend& backend() {
+  thread_local Backend b;
+  return b;
+}
+inline void check(h2b_ctx* ctx, int rc, const char* panic_msg) {
+  if (rc == H2B_OK) return;
+  if (rc == H2B_ERR_LENGTH || rc == H2B_ERR_ARG || rc == H2B_ERR_BAD_OMEGA) throw Panic(panic_msg);
+  throw BackendError(std::string(ctx ? h2b_last_error(ctx) : "backend error") + " (rc=" + std::to_string(rc) + ")");
+}
+inline void host_op(int field, int op, const void* a, const void* b, void* out) {
+  if (h2b_host_field_op(field, op, static_cast<const h2b_fr*>(a), static_cast<const h2b_fr*>(b ? b : a),
+                        static_cast<h2b_fr*>(out), 1) != H2B_OK)
+    throw BackendError("h2b_host_field_op");
+}
+}  // namespace detail
+
+// ---------------------------------------------------------------------------------------------
+// bn256::Fr / bn256::G1Affine / bn256::G1 (halo2curves 0.3.1): same bytes as the ABI types.  The
+// host-side operators below are for the O(#columns) scalars around the kernels (challenges, omega
+// powers); they run the library's host code path, not the GPU.
+// ---------------------------------------------------------------------------------------------
+template <int FIELD>
+struct Field : h2b_fr {
+  static Field zero() {
+    Field z;
+    std::memset(&z, 0, sizeof z);
+    return z;
+  }
+  static Field from_raw(uint64_t l0, uint64_t l1 = 0, uint64_t l2 = 0, uint64_t l3 = 0) {  // canonical limbs -> Montgomery
+    Field c, r;
+    c.l[0] = l0, c.l[1] = l1, c.l[2] = l2, c.l[3] = l3;
+    detail::host_op(FIELD, 4, &c, nullptr, &r);
+    return r;
+  }
+  static Field from(uint64_t v) { return from_raw(v); }
+  static Field one() { return from_raw(1); }
+  Field to_repr_limbs() const {  // Montgomery -> canonical little-endian limbs (to_repr)
+    Field r;
+    detail::host_op(FIELD, 5, this, nullptr, &r);
+    return r;
+  }
+  Field operator*(const Field& o) const { return bin(0, o); }
+  Field operator+(const Field& o) const { return bin(1, o); }
+  Field operator-(const Field& o) const { return bin(2, o); }
+  Field operator-() const { return un(6); }
+  Field square() const { return un(3); }
+  Field invert() const { return un(7); }  // 0 -> 0 (callers check is_zero where CtOption matters)
+  Field& operator*=(const Field& o) { return *this = *this * o; }
+  Field& operator+=(const Field& o) { return *this = *this + o; }
+  Field& operator-=(const Field& o) { return *this = *this - o; }
+  bool operator==(const Field& o) const { return std::memcmp(l, o.l, sizeof l) == 0; }
+  bool operator!=(const Field& o) const { return !(*this == o); }
+  bool is_zero() const { return (l[0] | l[1] | l[2] | l[3]) == 0; }
+  Field pow_vartime(uint64_t e) const {
+    Field r = one(), b = *this;
+    for (; e; e >>= 1, b = b.square())
+      if (e & 1) r *= b;
+    return r;
+  }
+
+ private:
+  Field bin(int op, const Field& o) const {
+    Field r;
+    detail::host_op(FIELD, op, this, &o, &r);
+    return r;
+  }
+  Field un(int op) const {
+    Field r;
+    detail::host_op(FIELD, op, this, nullptr, &r);
+    return r;
+  }
+};
+using Fr = Field<0>;
+using Fq = Field<1>;
+static_assert(sizeof(Fr) == 32 && sizeof(Fq) == 32, "Fr/Fq are four u64 limbs");
+
+struct G1Affine {
+  Fq x, y;  // identity = (0, 0)
+  static G1Affine identity() { return G1Affine{Fq::zero(), Fq::zero()}; }
+  static G1Affine generator() { return G1Affine{Fq::from(1), Fq::from(2)}; }
+  bool is_identity() const { return x.is_zero() && y.is_zero(); }
+  bool operator==(const G1Affine& o) const { return x == o.x && y == o.y; }
+  bool operator!=(const G1Affine& o) const { return !(*this == o); }
+  G1Affine operator+(const G1Affine& o) const {
+    G1Affine r;
+    if (h2b_host_g1_op(0, reinterpret_cast<const h2b_g1_affine*>(this), reinterpret_cast<const h2b_g1_affine*>(&o),
+                       reinterpret_cast<h2b_g1_affine*>(&r), 1) != H2B_OK)
+      throw BackendError("h2b_host_g1_op");
+    return r;
+  }
+};
+static_assert(sizeof(G1Affine) == 64, "G1Affine is {x, y}");
+
+struct G1 {  // Jacobian (x/z^2, y/z^3), identity has z = 0
+  Fq x, y, z;
+  G1Affine to_affine() const {
+    if (z.is_zero()) return G1Affine::identity();
+    const Fq zi = z.invert(), zi2 = zi.square();
+    return G1Affine{x * zi2, y * zi2 * zi};
+  }
+  bool operator==(const G1& o) const { return to_affine() == o.to_affine(); }
+  bool operator!=(const G1& o) const { return !(*this == o); }
+};
+static_assert(sizeof(G1) == 96, "G1 is {x, y, z}");
+
+// ---------------------------------------------------------------------------------------------
+// halo2_proofs::arithmetic
+// ---------------------------------------------------------------------------------------------
+namespace arithmetic {
+
+/// best_multiexp(coeffs, bases) -> C::Curve                                   arithmetic.rs:132
+inline G1 best_multiexp(const Fr* coeffs, size_t n_coeffs, const G1Affine* bases, size_t n_bases) {
+  if (n_coeffs != n_bases) throw Panic("assertion failed: `(left == right)` coeffs.len() == bases.len() (arithmetic.rs:133)");
+  h2b_ctx* ctx = detail::backend().ctx;
+  G1 out;
+  detail::check(ctx, h2b_best_multiexp(ctx, coeffs, reinterpret_cast<const h2b_g1_affine*>(bases), n_coeffs,
+                                       reinterpret_cast<h2b_g1*>(&out)), "best_multiexp (arithmetic.rs:133)");
+  return out;
+}
+inline G1 best_multiexp(const std::vector<Fr>& coeffs, const std::vector<G1Affine>& bases) {
+  return best_multiexp(coeffs.data(), coeffs.size(), bases.data(), bases.size());
+}
+
+/// best_fft(a, omega, log_n): in place, natural order                        arithmetic.rs:171
+/// omega must be a primitive 2^log_n-th root of unity (every non-bench caller passes one).
+inline void best_fft(Fr* a, size_t len, const Fr& omega, uint32_t log_n) {
+  if (log_n >= 64 || len != (size_t(1) << log_n)) throw Panic("assertion failed: `(left == right)` a.len() == 1 << log_n (arithmetic.rs:184)");
+  h2b_ctx* ctx = detail::backend().ctx;
+  detail::check(ctx, h2b_best_fft(ctx, a, H2B_HOST, &omega, log_n), "best_fft: omega is not a primitive 2^log_n-th root of unity");
+}
+inline void best_fft(std::vector<Fr>& a, const Fr& omega, uint32_t log_n) { best_fft(a.data(), a.size(), omega, log_n); }
+
+/// eval_polynomial(poly, point)                                              arithmetic.rs:304
+inline Fr eval_polynomial(const Fr* poly, size_t n, const Fr& point) {
+  h2b_ctx* ctx = detail::backend().ctx;
+  Fr out = Fr::zero();
+  if (n) detail::check(ctx, h2b_eval_polynomial(ctx, poly, H2B_HOST, n, &point, &out), "eval_polynomial");
+  return out;
+}
+inline Fr eval_polynomial(const std::vector<Fr>& poly, const Fr& point) { return eval_polynomial(poly.data(), poly.size(), point); }
+
+/// compute_inner_product(a, b)                                               arithmetic.rs:334
+inline Fr compute_inner_product(const std::vector<Fr>& a, const std::vector<Fr>& b) {
+  if (a.size() != b.size()) throw Panic("assertion failed: `(left == right)` a.len() == b.len() (arithmetic.rs:336)");
+  h2b_ctx* ctx = detail::backend().ctx;
+  Fr out = Fr::zero();
+  if (!a.empty()) detail::check(ctx, h2b_inner_product(ctx, a.data(), b.data(), H2B_HOST, a.size(), &out), "compute_inner_product");
+  return out;
+}
+
+/// kate_division(a, b): a(X) / (X - b), remainder dropped                    arithmetic.rs:348
+inline std::vector<Fr> kate_division(const std::vector<Fr>& a, const Fr& b) {
+  if (a.empty()) throw Panic("attempt to subtract with overflow: a.len() - 1 (arithmetic.rs:354)");
+  std::vector<Fr> q(a.size() - 1);
+  h2b_ctx* ctx = detail::backend().ctx;
+  if (!q.empty()) detail::check(ctx, h2b_kate_division(ctx, a.data(), H2B_HOST, a.size(), &b, q.data()), "kate_division");
+  return q;
+}
+}  // namespace arithmetic
+
+// ---------------------------------------------------------------------------------------------
+// halo2_proofs::poly
+// ---------------------------------------------------------------------------------------------
+namespace poly {
+
+struct Coeff {};                  // poly.rs:52
+struct LagrangeCoeff {};          // poly.rs:57
+struct ExtendedLagrangeCoeff {};  // poly.rs:63
+
+struct Rotation {  // poly.rs:311
+  int32_t v;
+  static Rotation cur() { return Rotation{0}; }
+  static Rotation prev() { return Rotation{-1}; }
+  static Rotation next() { return Rotation{1}; }
+};
+
+struct Blind {  // commitment.rs:198 -- drawn for every commitment, ignored by ParamsKZG::commit*
+  Fr v = Fr::one();
+};
+
+/// Polynomial<F, B>: a Vec<F> tagged with its basis                          poly.rs:69-72
+template <class Basis>
+struct Polynomial {
+  std::vector<Fr> values;
+  size_t len() const { return values.size(); }
+  size_t num_coeffs() const { return values.size(); }
+  Fr& operator[](size_t i) { return values[i]; }
+  const Fr& operator[](size_t i) const { return values[i]; }
+  std::vector<Fr>::iterator begin() { return values.begin(); }
+  std::vector<Fr>::iterator end() { return values.end(); }
+  std::vector<Fr>::const_iterator begin() const { return values.begin(); }
+  std::vector<Fr>::const_iterator end() const { return values.end(); }
+
+  /// poly + &poly / poly - &poly / poly * scalar                             poly.rs:229, 243, 278
+  Polynomial operator+(const Polynomial& rhs) const { return zip(rhs, 0); }
+  Polynomial operator-(const Polynomial& rhs) const { return zip(rhs, 1); }
+  Polynomial operator*(const Fr& scalar) const {
+    Polynomial out = *this;
+    h2b_ctx* ctx = detail::backend().ctx;
+    if (!out.values.empty()) detail::check(ctx, h2b_poly_scale(ctx, out.values.data(), H2B_HOST, out.values.size(), &scalar), "Polynomial * scalar");
+    return out;
+  }
+  /// rotate (Lagrange basis only in the reference)                           poly.rs:259
+  Polynomial rotate(Rotation r) const {
+    Polynomial out = *this;
+    const size_t n = values.size();
+    if (n == 0) return out;
+    const size_t s = static_cast<size_t>(r.v < 0 ? -static_cast<int64_t>(r.v) : r.v) % n;
+    for (size_t i = 0; i < n; ++i) out.values[i] = values[r.v >= 0 ? (i + s) % n : (i + n - s) % n];
+    return out;
+  }
+
+ private:
+  Polynomial zip(const Polynomial& rhs, int sub) const {
+    if (rhs.values.size() != values.size()) throw Panic("Polynomial +/-: lengths differ (poly.rs:229-256)");
+    Polynomial out = *this;
+    h2b_ctx* ctx = detail::backend().ctx;
+    if (!values.empty())
+      detail::check(ctx, (sub ? h2b_poly_sub : h2b_poly_add)(ctx, out.values.data(), rhs.values.data(), H2B_HOST, values.size()), "Polynomial +/-");
+    return out;
+  }
+};
+
+/// EvaluationDomain<G> for G = bn256::Fr                                     poly/domain.rs:19-480
+class EvaluationDomain {
+ public:
+  /// EvaluationDomain::new(j, k)                                             domain.rs:39
+  EvaluationDomain(uint32_t j, uint32_t k) : ctx_(detail::backend().ctx) {
+    h2b_domain* d = nullptr;
+    detail::check(ctx_, h2b_domain_new(ctx_, j, k, &d), "EvaluationDomain::new: extended_k exceeds Fr::S = 28 (domain.rs:54-61)");
+    dom_.reset(d, h2b_domain_free);
+    n_ = uint64_t(1) << h2b_domain_k(d);
+    omega = constant(0), omega_inv = constant(1), extended_omega = constant(2), extended_omega_inv = constant(3);
+    g_coset = constant(4), g_coset_inv = constant(5), ifft_divisor = constant(6), extended_ifft_divisor = constant(7);
+    barycentric_weight = ifft_divisor;  // 1/n (domain.rs:115)
+  }
+  Fr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv, ifft_divisor, extended_ifft_divisor,
+      barycentric_weight;
+
+  uint32_t k() const { return h2b_domain_k(dom_.get()); }                                  // :364
+  uint32_t extended_k() const { return h2b_domain_extended_k(dom_.get()); }                // :369
+  size_t extended_len() const { return size_t(1) << extended_k(); }                        // :374
+  Fr get_omega() const { return omega; }                                                   // :379
+  Fr get_omega_inv() const { return omega_inv; }                                           // :385
+  Fr get_extended_omega() const { return extended_omega; }                                 // :390
+  size_t get_quotient_poly_degree() const { return h2b_domain_quotient_len(dom_.get()) / n_; }  // :463
+
+  Polynomial<LagrangeCoeff> lagrange_from_vec(std::vector<Fr> values) const {              // :147
+    if (values.size() != n_) throw Panic("assertion failed: `(left == right)` values.len() == self.n (domain.rs:148)");
+    return Polynomial<LagrangeCoeff>{std::move(values)};
+  }
+  Polynomial<Coeff> coeff_from_vec(std::vector<Fr> values) const {                         // :159
+    if (values.size() != n_) throw Panic("assertion failed: `(left == right)` values.len() == self.n (domain.rs:160)");
+    return Polynomial<Coeff>{std::move(values)};
+  }
+  Polynomial<Coeff> empty_coeff() const { return {std::vector<Fr>(n_, Fr::zero())}; }       // :169
+  Polynomial<LagrangeCoeff> empty_lagrange() const { return {std::vector<Fr>(n_, Fr::zero())}; }  // :177
+  Polynomial<LagrangeCoeff> constant_lagrange(const Fr& s) const { return {std::vector<Fr>(n_, s)}; }  // :197
+  Polynomial<ExtendedLagrangeCoeff> empty_extended() const { return {std::vector<Fr>(extended_len(), Fr::zero())}; }  // :206
+  Polynomial<ExtendedLagrangeCoeff> constant_extended(const Fr& s) const { return {std::vector<Fr>(extended_len(), s)}; }  // :215
+
+  /// lagrange_to_coeff(a): consumes the Lagrange vector, returns the coefficients        domain.rs:226
+  Polynomial<Coeff> lagrange_to_coeff(Polynomial<LagrangeCoeff> a) const {
+    if (a.values.size() != n_) throw Panic("assertion failed: `(left == right)` a.values.len() == 1 << self.k (domain.rs:227)");
+    detail::check(ctx_, h2b_lagrange_to_coeff(dom_.get(), a.values.data(), H2B_HOST), "lagrange_to_coeff");
+    return Polynomial<Coeff>{std::move(a.values)};
+  }
+  /// coeff_to_extended(a): zeta-coset evaluations over the extended domain               domain.rs:240
+  Polynomial<ExtendedLagrangeCoeff> coeff_to_extended(const Polynomial<Coeff>& a) const {
+    if (a.values.size() != n_) throw Panic("assertion failed: `(left == right)` a.values.len() == 1 << self.k (domain.rs:244)");
+    Polynomial<ExtendedLagrangeCoeff> out{std::vector<Fr>(extended_len())};
+    detail::check(ctx_, h2b_coeff_to_extended(dom_.get(), a.values.data(), out.values.data(), H2B_HOST), "coeff_to_extended");
+    return out;
+  }
+  /// rotate_extended(poly, rotation)                                                     domain.rs:257
+  Polynomial<ExtendedLagrangeCoeff> rotate_extended(const Polynomial<ExtendedLagrangeCoeff>& p, Rotation r) const {
+    const int64_t step = int64_t(1) << (extended_k() - k());
+    Polynomial<ExtendedLagrangeCoeff> out{std::vector<Fr>(p.values.size())};
+    const size_t n = p.values.size();
+    const size_t s = static_cast<size_t>((r.v < 0 ? -int64_t(r.v) : int64_t(r.v)) * step) % (n ? n : 1);
+    for (size_t i = 0; i < n; ++i) out.values[i] = p.values[r.v >= 0 ? (i + s) % n : (i + n - s) % n];
+    return out;
+  }
+  /// extended_to_coeff(a) -> Vec<G> of n * quotient_poly_degree coefficients             domain.rs:281
+  std::vector<Fr> extended_to_coeff(const Polynomial<ExtendedLagrangeCoeff>& a) const {
+    if (a.values.size() != extended_len()) throw Panic("assertion failed: `(left == right)` a.values.len() == self.extended_len() (domain.rs:282)");
+    std::vector<Fr> out(h2b_domain_quotient_len(dom_.get()));
+    detail::check(ctx_, h2b_extended_to_coeff(dom_.get(), a.values.data(), out.data(), H2B_HOST, 0), "extended_to_coeff");
+    return out;
+  }
+  /// divide_by_vanishing_poly(a)                                                         domain.rs:307
+  Polynomial<ExtendedLagrangeCoeff> divide_by_vanishing_poly(Polynomial<ExtendedLagrangeCoeff> a) const {
+    if (a.values.size() != extended_len()) throw Panic("assertion failed: `(left == right)` a.values.len() == 1 << self.extended_k (domain.rs:311)");
+    detail::check(ctx_, h2b_divide_by_vanishing_poly(dom_.get(), a.values.data(), H2B_HOST), "divide_by_vanishing_poly");
+    return a;
+  }
+  /// the only call order in the reference (plonk/vanishing/prover.rs:84-87), fused into one transform
+  std::vector<Fr> divide_by_vanishing_poly_then_extended_to_coeff(const Polynomial<ExtendedLagrangeCoeff>& a) const {
+    if (a.values.size() != extended_len()) throw Panic("assertion failed: `(left == right)` a.values.len() == self.extended_len() (domain.rs:282,311)");
+    std::vector<Fr> out(h2b_domain_quotient_len(dom_.get()));
+    detail::check(ctx_, h2b_extended_to_coeff(dom_.get(), a.values.data(), out.data(), H2B_HOST, 1), "extended_to_coeff");
+    return out;
+  }
+  /// rotate_omega(value, rotation)                                                       domain.rs:396
+  Fr rotate_omega(const Fr& value, Rotation r) const {
+    return r.v >= 0 ? value * omega.pow_vartime(uint64_t(r.v)) : value * omega_inv.pow_vartime(uint64_t(-int64_t(r.v)));
+  }
+  /// l_i_range(x, xn, rotations)                                                         domain.rs:435
+  std::vector<Fr> l_i_range(const Fr& x, const Fr& xn, const std::vector<int32_t>& rotations) const {
+    std::vector<Fr> results;
+    results.reserve(rotations.size());
+    for (int32_t r : rotations) results.push_back((x - rotate_omega(Fr::one(), Rotation{r})).invert());
+    const Fr common = (xn - Fr::one()) * barycentric_weight;
+    for (size_t i = 0; i < rotations.size(); ++i) results[i] = rotate_omega(results[i] * common, Rotation{rotations[i]});
+    return results;
+  }
+
+  h2b_domain* raw() const { return dom_.get(); }
+
+ private:
+  Fr constant(uint32_t which) const {
+    Fr out;
+    detail::check(ctx_, h2b_domain_constant(dom_.get(), which, &out), "h2b_domain_constant");
+    return out;
+  }
+  h2b_ctx* ctx_;
+  std::shared_ptr<h2b_domain> dom_;
+  uint64_t n_ = 0;
+};
+
+namespace kzg {
+/// ParamsKZG<Bn256>: the commit half (k, n, g, g_lagrange); the bases are uploaded once and stay on
+/// the device with their window table                                       poly/kzg/commitment.rs:23-31
+class ParamsKZG {
+ public:
+  /// from the two base vectors of an existing SRS (what read_custom yields, commitment.rs:160-244)
+  static ParamsKZG from_parts(uint32_t k, const std::vector<G1Affine>& g, const std::vector<G1Affine>& g_lagrange,
+                              bool precompute = true) {
+    const size_t n = size_t(1) << k;
+    if (g.size() != n || g_lagrange.size() != n) throw Panic("ParamsKZG: g and g_lagrange must hold 2^k points (commitment.rs:108-116)");
+    ParamsKZG p;
+    p.ctx_ = detail::backend().ctx;
+    p.k_ = k;
+    p.n_ = n;
+    p.g_ = upload(p.ctx_, g.data(), n, H2B_HOST, precompute);
+    p.g_lagrange_ = upload(p.ctx_, g_lagrange.data(), n, H2B_HOST, precompute);
+    return p;
+  }
+  /// ParamsKZG::setup(k, rng) with `s = Fr::random(rng)` handed in (MUST NOT be used in production, as
+  /// the reference says): g[i] = [s^i] G, g_lagrange[i] = [(s^n - 1)/n * w^i / (s - w^i)] G; the 2n scalar
+  /// multiplications run on the GPU                                           commitment.rs:61-129
+  static ParamsKZG setup(uint32_t k, const Fr& s, bool precompute = true) {
+    if (k > 28) throw Panic("assertion failed: k <= E::Scalar::S (commitment.rs:64)");
+    const size_t n = size_t(1) << k;
+    Fr root = Fr::from_raw(0xd34f1ed960c37c9cull, 0x3215cf6dd39329c8ull, 0x98865ea93dd31f74ull, 0x03ddb9f5166d18b7ull);  // ROOT_OF_UNITY
+    for (uint32_t i = k; i < 28; ++i) root = root.square();  // :90-93
+    std::vector<Fr> powers(n), lag(n), dens(n), pre(n);
+    Fr cur = Fr::one(), w = Fr::one(), run = Fr::one();
+    for (size_t i = 0; i < n; ++i) {
+      powers[i] = cur, cur *= s;
+      dens[i] = s - w, lag[i] = w, w *= root;  // lag holds w^i for now
+      pre[i] = run, run *= dens[i];
+    }
+    const Fr multiplier = (s.pow_vartime(n) - Fr::one()) * Fr::from(n).invert();  // :96
+    Fr inv = run.invert();
+    for (size_t i = n; i-- > 0;) {
+      lag[i] = multiplier * lag[i] * (inv * pre[i]);  // :101-102
+      inv *= dens[i];
+    }
+    ParamsKZG p;
+    p.ctx_ = detail::backend().ctx;
+    p.k_ = k;
+    p.n_ = n;
+    for (int which = 0; which < 2; ++which) {
+      void* dev = nullptr;
+      detail::check(p.ctx_, h2b_device_alloc(p.ctx_, n * sizeof(G1Affine), &dev), "h2b_device_alloc");
+      const int rc = h2b_g1_mul_generator(p.ctx_, (which ? lag : powers).data(), H2B_HOST, n, static_cast<h2b_g1_affine*>(dev), H2B_DEVICE);
+      std::shared_ptr<h2b_bases> b;
+      if (rc == H2B_OK) b = upload(p.ctx_, static_cast<const G1Affine*>(dev), n, H2B_DEVICE, precompute);
+      h2b_device_free(p.ctx_, dev);
+      detail::check(p.ctx_, rc, "h2b_g1_mul_generator");
+      (which ? p.g_lagrange_ : p.g_) = b;
+    }
+    return p;
+  }
+
+  uint32_t k() const { return k_; }       // commitment.rs:254
+  uint64_t n() const { return n_; }       // commitment.rs:258
+  std::vector<G1Affine> get_g() const { return download(g_.get()); }  // commitment.rs:316
+  std::vector<G1Affine> get_g_lagrange() const { return download(g_lagrange_.get()); }
+
+  /// commit_lagrange(poly, _)                                                 commitment.rs:281-292
+  G1 commit_lagrange(const Polynomial<LagrangeCoeff>& poly, const Blind& = Blind{}) const { return msm(g_lagrange_.get(), poly.values, "assertion failed: bases.len() >= size (commitment.rs:290)"); }
+  /// commit(poly, _)                                                          commitment.rs:327-334
+  G1 commit(const Polynomial<Coeff>& poly, const Blind& = Blind{}) const { return msm(g_.get(), poly.values, "assertion failed: bases.len() >= size (commitment.rs:332)"); }
+
+ private:
+  static std::shared_ptr<h2b_bases> upload(h2b_ctx* ctx, const G1Affine* pts, size_t n, int loc, bool precompute) {
+    h2b_bases* b = nullptr;
+    detail::check(ctx, h2b_bases_upload(ctx, reinterpret_cast<const h2b_g1_affine*>(pts), n, loc, &b), "h2b_bases_upload");
+    std::shared_ptr<h2b_bases> sp(b, h2b_bases_free);
+    if (precompute) detail::check(ctx, h2b_bases_precompute(ctx, b, 0), "h2b_bases_precompute");
+    return sp;
+  }
+  std::vector<G1Affine> download(const h2b_bases* b) const {
+    std::vector<G1Affine> out(h2b_bases_len(b));
+    detail::check(ctx_, h2b_copy_d2h(ctx_, out.data(), h2b_bases_device_ptr(b), out.size() * sizeof(G1Affine)), "h2b_copy_d2h");
+    return out;
+  }
+  G1 msm(const h2b_bases* b, const std::vector<Fr>& scalars, const char* panic_msg) const {
+    if (scalars.size() > n_) throw Panic(panic_msg);
+    G1 out;
+    detail::check(ctx_, h2b_msm(ctx_, b, 0, scalars.data(), H2B_HOST, scalars.size(), reinterpret_cast<h2b_g1*>(&out)), panic_msg);
+    return out;
+  }
+  h2b_ctx* ctx_ = nullptr;
+  uint32_t k_ = 0;
+  uint64_t n_ = 0;
+  std::shared_ptr<h2b_bases> g_, g_lagrange_;
+};
+}  // namespace kzg
+}  // namespace poly
+}  // namespace halo2_proofs
+
+#endif  // HALO2_B200_HPP

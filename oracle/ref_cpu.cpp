@@ -507,7 +507,7 @@ const uint64_t kZeta[4] = {0x8b17ea66b99c90ddull, 0x5bfc41088d8daaa7ull, 0xb3c4d
 const uint32_t kS = 28;
 
 Domain* domain_new(uint32_t j, uint32_t k, int threads) {  // domain.rs:39-142
-  if (j < 2 || k > kS) return nullptr;
+  if (j < 1 || k > kS) return nullptr;  // j = 1: quotient degree 0, extended_k = k (the reference's own tests, domain.rs:494)
   Domain* d = new Domain();
   d->threads = clamp_threads(threads);
   d->j = j;

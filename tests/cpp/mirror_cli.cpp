@@ -1,0 +1,88 @@
+// File-driven entry to the C++ host mirror (include/halo2_b200.hpp) so the Python test-suite can hand it
+// seeded inputs and compare its outputs bit for bit with the oracle:  mirror_cli <op> <in.bin> <out.bin> [args]
+#include <cstdio>
+#include <string>
+
+#include "halo2_b200.hpp"
+
+using namespace halo2_proofs;
+
+static std::vector<uint8_t> slurp(const char* path) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) throw std::runtime_error(std::string("cannot read ") + path);
+  std::fseek(f, 0, SEEK_END);
+  std::vector<uint8_t> b(static_cast<size_t>(std::ftell(f)));
+  std::fseek(f, 0, SEEK_SET);
+  if (!b.empty() && std::fread(b.data(), 1, b.size(), f) != b.size()) throw std::runtime_error("short read");
+  std::fclose(f);
+  return b;
+}
+static void spit(const char* path, const void* p, size_t n) {
+  FILE* f = std::fopen(path, "wb");
+  if (!f || (n && std::fwrite(p, 1, n, f) != n)) throw std::runtime_error(std::string("cannot write ") + path);
+  std::fclose(f);
+}
+template <class T>
+static std::vector<T> take(const std::vector<uint8_t>& b, size_t off_bytes, size_t count) {
+  if (off_bytes + count * sizeof(T) > b.size()) throw std::runtime_error("input file too short");
+  std::vector<T> v(count);
+  if (count) std::memcpy(static_cast<void*>(v.data()), b.data() + off_bytes, count * sizeof(T));
+  return v;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 4) return 64;
+  const std::string op = argv[1];
+  auto arg = [&](int i) { return static_cast<uint32_t>(std::atoi(argv[4 + i])); };
+  try {
+    const auto in = slurp(argv[2]);
+    if (op == "best_fft") {  // in: a[2^k], omega
+      const uint32_t k = arg(0);
+      auto a = take<Fr>(in, 0, size_t(1) << k);
+      const Fr omega = take<Fr>(in, a.size() * 32, 1)[0];
+      arithmetic::best_fft(a, omega, k);
+      spit(argv[3], a.data(), a.size() * 32);
+    } else if (op == "best_multiexp") {  // in: coeffs[n], bases[n]; out: affine sum
+      const size_t n = arg(0);
+      const auto c = take<Fr>(in, 0, n);
+      const auto b = take<G1Affine>(in, n * 32, n);
+      const G1Affine r = arithmetic::best_multiexp(c, b).to_affine();
+      spit(argv[3], &r, 64);
+    } else if (op == "lagrange_to_coeff" || op == "coeff_to_extended") {
+      poly::EvaluationDomain d(arg(0), arg(1));
+      auto v = take<Fr>(in, 0, size_t(1) << arg(1));
+      if (op == "lagrange_to_coeff") {
+        const auto r = d.lagrange_to_coeff(d.lagrange_from_vec(v));
+        spit(argv[3], r.values.data(), r.len() * 32);
+      } else {
+        const auto r = d.coeff_to_extended(d.coeff_from_vec(v));
+        spit(argv[3], r.values.data(), r.len() * 32);
+      }
+    } else if (op == "extended_to_coeff") {  // args: j k divide_by_vanishing(0 | 1 two calls | 2 fused)
+      poly::EvaluationDomain d(arg(0), arg(1));
+      poly::Polynomial<poly::ExtendedLagrangeCoeff> a{take<Fr>(in, 0, d.extended_len())};
+      const auto r = arg(2) == 0 ? d.extended_to_coeff(a)
+                     : arg(2) == 1 ? d.extended_to_coeff(d.divide_by_vanishing_poly(a))
+                                   : d.divide_by_vanishing_poly_then_extended_to_coeff(a);
+      spit(argv[3], r.data(), r.size() * 32);
+    } else if (op == "commit") {  // in: s, poly[2^k]; out: commit(poly), commit_lagrange(poly), g[1], g_lagrange[0]
+      const uint32_t k = arg(0);
+      const Fr s = take<Fr>(in, 0, 1)[0];
+      const auto v = take<Fr>(in, 32, size_t(1) << k);
+      const auto params = poly::kzg::ParamsKZG::setup(k, s);
+      const G1Affine out[4] = {params.commit(poly::Polynomial<poly::Coeff>{v}).to_affine(),
+                               params.commit_lagrange(poly::Polynomial<poly::LagrangeCoeff>{v}).to_affine(),
+                               params.get_g()[1], params.get_g_lagrange()[0]};
+      spit(argv[3], out, sizeof out);
+    } else {
+      return 64;
+    }
+  } catch (const Panic& e) {
+    std::printf("panic: %s\n", e.what());
+    return 101;  // the exit status of a Rust panic
+  } catch (const std::exception& e) {
+    std::printf("error: %s\n", e.what());
+    return 2;
+  }
+  return 0;
+}

@@ -190,9 +190,13 @@ def oracle_bench_proof(k: int, a: int, seed: bytes):
     return params, pk, t.finalize()
 
 
-def device_bench_proof(ctx: h.Context, k: int, a: int, seed: bytes, precompute: bool = False, timings=None):
-    """The same proof through keygen / create_proof of the product on `ctx`."""
+def device_bench_proof(ctx: h.Context, k: int, a: int, seed: bytes, precompute: bool = False, timings=None,
+                       params_hook=None):
+    """The same proof through keygen / create_proof of the product on `ctx`; params_hook (e.g.
+    dist.shard_params) may replace the ParamsKZG before keygen."""
     params = h.ParamsKZG.setup(ctx, k, S_TOXIC, precompute=precompute)
+    if params_hook is not None:
+        params = params_hook(params)
     cs = build_cs("bench")
     fixed, advice, copies = bench_circuit(k, a)
     pk = h.keygen(params, cs, fixed, copies)

@@ -1,0 +1,115 @@
+"""The C++ host side above the C ABI (include/halo2_b200.hpp: the reference's own names -- best_multiexp,
+best_fft, EvaluationDomain, Polynomial, ParamsKZG::commit / commit_lagrange): (1) its self-checking tests,
+written after the reference's own unit tests (tests/cpp/test_mirror.cpp); (2) bit-exact parity with the
+oracle on seeded inputs through a file-driven CLI (tests/cpp/mirror_cli.cpp).  The CPU suite links the
+TEST-ONLY emulator build of the kernels, the `-m gpu` suite the product library on cuda:0."""
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import halo2_pse_b200  # noqa: F401
+from halo2_pse_b200 import build
+from oracle import bn256 as O
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPP = os.path.join(ROOT, "tests", "cpp")
+OUT = os.path.join(CPP, "_build")
+
+
+def _build(name: str, lib: str, tag: str) -> str:
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, f"{name}_{tag}")
+    src = os.path.join(CPP, name + ".cpp")
+    deps = [src, os.path.join(ROOT, "include", "halo2_b200.hpp"), os.path.join(ROOT, "include", "halo2_b200.h"), lib]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        libdir, libname = os.path.dirname(lib), os.path.basename(lib)[3:-3]
+        subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
+                        "-L" + libdir, "-l" + libname, "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    return exe
+
+
+def _run(exe, *args, timeout=600):
+    return subprocess.run([exe, *map(str, args)], capture_output=True, text=True, timeout=timeout)
+
+
+def _self_tests(lib, tag, big_k):
+    r = _run(_build("test_mirror", lib, tag), big_k)
+    assert r.returncode == 0 and "all mirror tests passed" in r.stdout, r.stdout + r.stderr
+
+
+def _parity(lib, tag, tmp_path, oc, ks, msm_ns, commit_k):
+    cli = _build("mirror_cli", lib, tag)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+
+    def call(op, blobs, *args, expect=0):
+        with open(fin, "wb") as f:
+            for b in blobs:
+                f.write(np.ascontiguousarray(b, dtype=np.uint64).tobytes())
+        r = _run(cli, op, fin, fout, *args)
+        assert r.returncode == expect, (op, args, r.stdout, r.stderr)
+        return np.fromfile(fout, dtype=np.uint64) if expect == 0 else r.stdout
+
+    for k in ks:  # best_fft and the domain transforms against the C++ restatement of arithmetic.rs / domain.rs
+        n = 1 << k
+        a = H.rand_fr_limbs(100 + k, n)
+        w = H.fr_enc([O.omega_for(k)])
+        assert (call("best_fft", [a, w], k).reshape(-1, 4) == oc.best_fft(a, w[0], k, 0)).all(), k
+        for j in (1, 3, 5):
+            od = oc.domain(j, k, 0)
+            assert (call("lagrange_to_coeff", [a], j, k).reshape(-1, 4) == od.lagrange_to_coeff(a)).all(), (j, k)
+            ext = od.coeff_to_extended(a)
+            assert (call("coeff_to_extended", [a], j, k).reshape(-1, 4) == ext).all(), (j, k)
+            e = H.rand_fr_limbs(200 + k + j, ext.shape[0])
+            assert (call("extended_to_coeff", [e], j, k, 0).reshape(-1, 4) == od.extended_to_coeff(e)).all(), (j, k)
+            want = od.extended_to_coeff(od.divide_by_vanishing_poly(e))
+            for mode in (1, 2):  # two calls, and the fused form
+                assert (call("extended_to_coeff", [e], j, k, mode).reshape(-1, 4) == want).all(), (j, k, mode)
+            od.free()
+    rng = random.Random(77)
+    for n in msm_ns:  # best_multiexp against multiexp_serial / best_multiexp of the restatement
+        hs = [rng.randrange(1, 1 << 64) for _ in range(n)]
+        bases = oc.g1_mul_gen(hs) if n else np.zeros((0, 8), dtype=np.uint64)
+        sc = H.rand_fr_limbs(300 + n, n) if n else np.zeros((0, 4), dtype=np.uint64)
+        if n > 4:
+            sc[1] = 0  # a zero scalar contributes nothing (arithmetic.rs:86)
+        got = call("best_multiexp", [sc, bases], n).reshape(1, 8)
+        want = oc.best_multiexp(sc, bases, 0) if n else np.zeros((1, 8), dtype=np.uint64)
+        assert H.g1_dec(got) == H.g1_dec(want), n
+    # ParamsKZG::setup + commit / commit_lagrange against the big-integer restatement of kzg/commitment.rs
+    s = 0x1234567890ABCDEF1234567890ABCDEF
+    op = O.ParamsKZG.setup(commit_k, s)
+    poly = H.rand_fr_limbs(400, 1 << commit_k)
+    pts = H.g1_dec(call("commit", [H.fr_enc([s]), poly], commit_k).reshape(4, 8))
+    vals = H.fr_dec(poly)
+    assert pts[0] == op.commit(vals) and pts[1] == op.commit_lagrange(vals)
+    assert pts[2] == op.g[1] and pts[3] == op.g_lagrange[0]
+    # contract violations exit like a Rust panic (status 101) with the reference's file:line
+    out = call("best_fft", [H.rand_fr_limbs(1, 8), H.fr_enc([3])], 3, expect=101)
+    assert "panic" in out
+    out = call("lagrange_to_coeff", [H.rand_fr_limbs(1, 8)], 6, 27, expect=101)  # extended_k = 30 > Fr::S
+    assert "extended_k" in out
+    out = call("lagrange_to_coeff", [H.rand_fr_limbs(1, 8)], 3, 4, expect=2)  # 8 elements for a 2^4 domain: the CLI's own I/O error
+    assert "too short" in out
+
+
+def test_cpp_mirror_self_tests_emulator(emu_lib_path):
+    _self_tests(emu_lib_path, "emu", 6)
+
+
+def test_cpp_mirror_parity_emulator(emu_lib_path, oracle_c, tmp_path):
+    _parity(emu_lib_path, "emu", tmp_path, oracle_c, ks=(0, 1, 5, 8), msm_ns=(0, 1, 33, 700), commit_k=4)
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_self_tests_gpu():
+    _self_tests(build.build_product(), "gpu", 12)
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_parity_gpu(oracle_c, tmp_path):
+    _parity(build.build_product(), "gpu", tmp_path, oracle_c, ks=(0, 3, 10, 16, 18), msm_ns=(0, 1, 1000, 70001),
+            commit_k=6)

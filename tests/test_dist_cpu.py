@@ -59,6 +59,15 @@ def _worker(rank, world, port, emu, q):
             D.FourStepNTT(ctx, k, omega).run(mine)
             got = mine.numpy().view(np.uint64).reshape(-1, 4)
             assert (got == want[rank * loc:(rank + 1) * loc]).all(), (k, rank)
+        # ---- create_proof with every commitment sharded over the ranks (ShardedBases) ----
+        # k = 5: n = 32 bases, 16 per rank at world 2, 8 at world 4; the witness-polynomial commitments of
+        # the multiopen cover n - 1 points, so the last rank's range is cut short.
+        from tests import plonk_cases as PC
+        seed = b"\x07" * 16
+        _, pk, got = PC.device_bench_proof(ctx, 5, 0xDEADBEEF, seed, params_hook=lambda p: D.shard_params(p))
+        _, opk, want = PC.oracle_bench_proof(5, 0xDEADBEEF, seed)
+        assert pk.pinned == opk.debug and got == want, rank  # same vk, same proof bytes as the big-integer oracle
+        pk.free()
         ctx.close()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover

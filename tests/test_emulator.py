@@ -284,3 +284,26 @@ def test_kzg_setup_on_device(emu_ctx):
     out = np.zeros((4, 8), dtype=np.uint64)
     emu_ctx._check(emu_ctx.lib.h2b_g1_mul_generator(emu_ctx.h, sc.ctypes.data, h.H2B_HOST, 4, out.ctypes.data, h.H2B_HOST))
     assert H.g1_dec(out) == [None, O.G1_GEN, O.g1_mul(O.G1_GEN, 2), O.g1_neg(O.G1_GEN)]
+
+
+def test_pageable_copies_through_the_pinned_ring(emu_ctx, oracle_c, monkeypatch):
+    """copy_h2d_any / copy_d2h_any (csrc/ctx.cu): host slices that are not pinned go through the context's
+    pinned ring on several host threads.  The emulator has no pinned memory, so the staged path is opted
+    in; sizes cover one short chunk, a ragged tail and more chunks than slots (2 MiB chunks, 16 slots)."""
+    monkeypatch.setenv("H2B_EMU_STAGED_COPY", "1")
+    monkeypatch.setenv("H2B_COPY_THREADS", "3")
+    rs = np.random.RandomState(7)
+    for nbytes in (4 << 20, (6 << 20) + 32, (38 << 20) + 96):
+        a = rs.randint(0, 1 << 62, size=(nbytes // 32, 4), dtype=np.int64).astype(np.uint64)
+        buf = emu_ctx.alloc(nbytes)
+        buf.upload(a)
+        assert (buf.download(a.shape[0]) == a).all(), nbytes
+        buf.free()
+    # a drop-in call on host slices above the staging threshold: best_fft at k = 17 (4 MiB in and out)
+    k = 17
+    a = H.rand_fr_limbs(5, 1 << k)
+    w = H.fr_enc([O.omega_for(k)])[0]
+    want = oracle_c.best_fft(a, w, k, 0)
+    got = a.copy()
+    emu_ctx.best_fft(got, w.reshape(1, 4), k)
+    assert (got == want).all()

@@ -649,3 +649,29 @@ def test_msm_k26_properties(gpu_ctx):
     assert B.msm(a, n=m) == O.g1_mul(O.G1_GEN, sum(c * x for c, x in zip(s, hs)) % O.R_MOD)
     a.free()
     B.free()
+
+
+def test_pageable_host_slices(gpu_ctx, oracle_c):
+    """Drop-in calls on PAGEABLE host slices (a Rust Vec, a numpy array): staged through the pinned ring by
+    several host threads (copy_h2d_any / copy_d2h_any); same results as with pinned buffers."""
+    rs = np.random.RandomState(11)
+    for nbytes in (4 << 20, (6 << 20) + 32, (70 << 20) + 96):
+        a = rs.randint(0, 1 << 62, size=(nbytes // 32, 4), dtype=np.int64).astype(np.uint64)
+        buf = gpu_ctx.alloc(nbytes)
+        buf.upload(a)
+        assert (buf.download(a.shape[0]) == a).all(), nbytes
+        buf.free()
+    k = 20
+    a = H.rand_fr_limbs(9, 1 << k)
+    w = H.fr_enc([O.omega_for(k)])[0]
+    want = oracle_c.best_fft(a, w, k, 0)
+    got = a.copy()
+    gpu_ctx.best_fft(got, w.reshape(1, 4), k)
+    assert (got == want).all()
+    n = (1 << 18) + 5  # MSM with pageable scalars: 8 chunks of 1 MiB (direct) and, below, one staged 8 MiB copy
+    bases = gpu_ctx.synth_bases(n, 0x77)
+    sc = H.rand_fr_limbs(10, n)
+    pinned = gpu_ctx.pinned((n, 4))
+    pinned.array[:] = sc
+    assert bases.msm(sc) == bases.msm(pinned.array)
+    bases.free()
