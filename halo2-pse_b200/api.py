@@ -16,7 +16,8 @@ computes on the CPU.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence, Tuple
+import os
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -126,12 +127,14 @@ class DeviceBuffer:
         ctx._check(ctx.lib.h2b_device_alloc(ctx.h, nbytes, C.byref(p)))
         self.ptr = p
 
-    def upload(self, arr: np.ndarray, offset_bytes: int = 0) -> "DeviceBuffer":
+    def upload(self, arr: np.ndarray, offset_bytes: int = 0, ctx: Optional["Context"] = None) -> "DeviceBuffer":
+        """Host -> device copy, complete on return.  `ctx`: a sibling context whose stream (and pinned ring)
+        carries the copy instead of the owner's -- the buffer must not be in use on the owner's stream."""
         a = np.ascontiguousarray(arr)
         if offset_bytes + a.nbytes > self.nbytes:
             raise H2BError(_ffi.H2B_ERR_LENGTH, "upload larger than the buffer")
-        self.ctx._check(self.ctx.lib.h2b_copy_h2d(self.ctx.h, C.c_void_p(self.ptr.value + offset_bytes),
-                                                  _ptr(a), a.nbytes))
+        ctx = self.ctx if ctx is None else ctx
+        ctx._check(ctx.lib.h2b_copy_h2d(ctx.h, C.c_void_p(self.ptr.value + offset_bytes), _ptr(a), a.nbytes))
         return self
 
     def download(self, count: int, offset_bytes: int = 0, width: int = 4) -> np.ndarray:
@@ -190,8 +193,21 @@ class Context:
             raise H2BError(rc, "h2b_ctx_create failed: no usable CUDA device (there is no CPU fallback)")
         self.h = h
         self.device = device
+        self._lib_path = lib_path
+        self._aux: List["Context"] = []
+
+    def aux(self, i: int = 0) -> "Context":
+        """A sibling context on the same device (own stream, scratch and MSM workspace): independent
+        commitments run on both at once, the way the reference runs rayon par_iter around (not inside)
+        its commits (poly/kzg/multiopen/shplonk/prover.rs:179-196)."""
+        while len(self._aux) <= i:
+            self._aux.append(Context(self.device, self._lib_path))
+        return self._aux[i]
 
     def close(self) -> None:
+        for a in self._aux:
+            a.close()
+        self._aux = []
         if self.h is not None:
             self.lib.h2b_ctx_destroy(self.h)
             self.h = None
@@ -209,7 +225,7 @@ class Context:
 
     @property
     def launches(self) -> int:
-        return int(self.lib.h2b_ctx_launches(self.h))
+        return int(self.lib.h2b_ctx_launches(self.h)) + sum(a.launches for a in self._aux)
 
     @property
     def stream(self) -> int:
@@ -396,6 +412,53 @@ class Context:
         self._check(self.lib.h2b_best_fft_batch(self.h, buf.ptr, H2B_DEVICE, _ptr(w), log_n, ncols, stride))
 
 
+def msm_many_mixed_raw(jobs: Sequence[tuple], concurrent: bool = True, pre: Optional[Sequence] = None) -> List[np.ndarray]:
+    """Independent commitments: jobs[i] = (bases, scalars, n, offset, scalar_offset), any base sets of one
+    device; pre[i](ctx), if given, runs right before job i on the context that will compute it (the upload of
+    a witness column: copies of later columns then overlap the commitments of earlier ones).
+    With more than one job they are dealt round-robin to the first base set's context and its siblings (one
+    host thread and one stream each, H2B_COMMIT_WAYS of them, default 3), so that the latency-bound tail of
+    one MSM (bucket reduction, short sort passes) runs under the throughput-bound accumulation of the
+    others -- the reference's rayon par_iter around (not inside) its commits
+    (poly/kzg/multiopen/shplonk/prover.rs:179-196)."""
+    if not jobs:
+        return []
+    jobs = [tuple(j) + (None, 0, 0)[len(j) - 2:] for j in jobs]
+    main = jobs[0][0].ctx
+    ways = min(len(jobs), max(1, int(os.environ.get("H2B_COMMIT_WAYS", "3"))))
+    if ways < 2 or not concurrent:
+        outs = []
+        for i, j in enumerate(jobs):
+            if pre is not None and pre[i] is not None:
+                pre[i](main)
+            outs.append(j[0].msm_raw(main, *j[1:]))
+        return outs
+    import threading
+    ctxs = [main] + [main.aux(i) for i in range(ways - 1)]
+    main.sync()  # the scalars were produced on the main stream
+    outs: List[Optional[np.ndarray]] = [None] * len(jobs)
+    errs: list = []
+
+    def run(ctx, idxs):
+        try:
+            for i in idxs:
+                if pre is not None and pre[i] is not None:
+                    pre[i](ctx)
+                outs[i] = jobs[i][0].msm_raw(ctx, *jobs[i][1:])
+        except Exception as e:  # re-raised on the calling thread
+            errs.append(e)
+
+    threads = [threading.Thread(target=run, args=(ctxs[w], range(w, len(jobs), ways))) for w in range(1, ways)]
+    for t in threads:
+        t.start()
+    run(ctxs[0], range(0, len(jobs), ways))
+    for t in threads:
+        t.join()
+    if errs:
+        raise errs[0]
+    return outs
+
+
 class Bases:
     """Device-resident, immutable affine bases: ParamsKZG.g or .g_lagrange
     (poly/kzg/commitment.rs:23-31)."""
@@ -429,6 +492,37 @@ class Bases:
         p = self.ctx.lib.h2b_bases_device_ptr(self.h)
         self.ctx._check(self.ctx.lib.h2b_copy_d2h(self.ctx.h, _ptr(out), p, out.nbytes))
         return out
+
+    def msm_raw(self, ctx: "Context", scalars, n: Optional[int] = None, offset: int = 0,
+                scalar_offset: int = 0) -> np.ndarray:
+        """The affine sum as its 8 limbs, computed on `ctx` (this base set's context or a sibling on the
+        same device: the bases are immutable, any stream may read them)."""
+        if isinstance(scalars, DeviceBuffer):
+            if n is None:
+                raise H2BError(_ffi.H2B_ERR_ARG, "n required for device scalars")
+            if (scalar_offset + n) * 32 > scalars.nbytes:
+                raise H2BError(_ffi.H2B_ERR_LENGTH, "scalar slice outside the buffer")
+            sp, loc = scalars.at(scalar_offset * 32), H2B_DEVICE
+        else:
+            arr = _fr_array(scalars)[scalar_offset:]
+            n = arr.shape[0] if n is None else n
+            sp, loc = _ptr(arr), H2B_HOST
+        out = np.zeros(8, dtype=np.uint64)
+        ctx._check(ctx.lib.h2b_msm_affine(ctx.h, self.h, offset, sp, loc, n, _ptr(out)))
+        return out
+
+    def msm_many_raw(self, jobs: Sequence[tuple], concurrent: bool = True, pre: Optional[Sequence] = None) -> List[np.ndarray]:
+        """Independent commitments on this base set: jobs[i] = (scalars, n, offset, scalar_offset); see
+        msm_many_mixed_raw."""
+        return msm_many_mixed_raw([(self,) + tuple(j) for j in jobs], concurrent, pre)
+
+    @staticmethod
+    def msm_many_mixed(jobs: Sequence[tuple], concurrent: bool = True, pre: Optional[Sequence] = None) -> list:
+        """jobs[i] = (bases, scalars, n, offset, scalar_offset) over any base sets of one device."""
+        return [g1_decode(o)[0] for o in msm_many_mixed_raw(jobs, concurrent, pre)]
+
+    def msm_many(self, jobs: Sequence[tuple], concurrent: bool = True, pre: Optional[Sequence] = None) -> list:
+        return [g1_decode(o)[0] for o in self.msm_many_raw(jobs, concurrent, pre)]
 
     def msm(self, scalars, n: Optional[int] = None, offset: int = 0, affine: bool = True, scalar_offset: int = 0):
         """best_multiexp(scalars[scalar_offset..][..n], &bases[offset..offset+n]); scalars are host limbs

@@ -40,6 +40,12 @@ struct h2b_ctx {
   cudaStream_t stream = nullptr;
   // second stream + events for host->device copies overlapped with compute (drop-in calls on host slices)
   cudaStream_t copy_stream = nullptr;
+  // `stream` is created at the highest priority; the one long throughput-bound kernel of an MSM (bucket
+  // accumulation, level 0) is launched on this LOW-priority stream instead, fenced by two events: when several
+  // contexts commit at once, the short latency-bound kernels of one MSM (sort passes, scans, bucket reduction)
+  // get the SM slots that free up first and run under the accumulation of another MSM instead of behind it
+  cudaStream_t bulk_stream = nullptr;
+  cudaEvent_t bulk_ev[2] = {nullptr, nullptr};
   cudaEvent_t copy_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::recursive_mutex mu;
   std::string last_error;
@@ -120,17 +126,23 @@ inline int fail(h2b_ctx* ctx, int code, const std::string& msg) {
 // test build, tests/emu/cuda_runtime.h) the same call runs the kernel on the
 // fiber emulator; the product build never defines H2B_EMU.
 template <class... KArgs, class... Args>
-inline int launch(h2b_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                  Args&&... args) {
+inline int launch_on(h2b_ctx* ctx, cudaStream_t stream, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                     Args&&... args) {
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return H2B_OK;
 #ifdef H2B_EMU
+  (void)stream;
   emu::launch(grid, block, smem, [&]() { kern(args...); });
 #else
-  kern<<<grid, block, smem, ctx->stream>>>(std::forward<Args>(args)...);
+  kern<<<grid, block, smem, stream>>>(std::forward<Args>(args)...);
   H2B_CUDA(ctx, cudaGetLastError());
 #endif
   ctx->launches++;
   return H2B_OK;
+}
+template <class... KArgs, class... Args>
+inline int launch(h2b_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                  Args&&... args) {
+  return launch_on(ctx, ctx->stream, kern, grid, block, smem, std::forward<Args>(args)...);
 }
 
 #ifdef H2B_EMU

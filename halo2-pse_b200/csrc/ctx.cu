@@ -93,7 +93,17 @@ int ensure_stage(h2b_ctx* ctx, int which, size_t bytes) {
 // ---------------------------------------------------------------------------
 // Copies from / to pageable host memory through a pinned ring
 // ---------------------------------------------------------------------------
-static constexpr size_t kCopyChunk = 2u << 20;  // bytes per slot
+static constexpr size_t kCopySlotBytes = 2u << 20;  // bytes per slot
+static size_t copy_chunk() {  // bytes staged per DMA: small enough that the first DMA starts early
+  static size_t v = [] {
+    size_t kb = 1024;
+    if (const char* e = getenv("H2B_COPY_CHUNK_KB")) kb = (size_t)atoi(e);
+    if (kb < 64) kb = 64;
+    if (kb << 10 > kCopySlotBytes) kb = kCopySlotBytes >> 10;
+    return kb << 10;
+  }();
+  return v;
+}
 static constexpr int kCopySlots = 16;           // 2 per thread, up to 8 threads
 static constexpr size_t kCopyStagedMin = 4u << 20;
 
@@ -127,7 +137,7 @@ static bool host_is_pageable(const void* p) {
 static int copy_pool_init(h2b_ctx* ctx) {
   if (ctx->copy_pool_ready) return H2B_OK;
   for (int i = 0; i < kCopySlots; ++i) {
-    H2B_CUDA(ctx, cudaMallocHost(&ctx->copy_slot[i], kCopyChunk));
+    H2B_CUDA(ctx, cudaMallocHost(&ctx->copy_slot[i], kCopySlotBytes));
     H2B_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_slot_ev[i], cudaEventDisableTiming));
   }
   ctx->copy_workers = new CopyWorkers(copy_threads(), ctx->device);
@@ -138,8 +148,10 @@ static int copy_pool_init(h2b_ctx* ctx) {
 template <bool TO_DEVICE>
 static int copy_staged(h2b_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
   H2B_TRY(copy_pool_init(ctx));
+  const size_t kCopyChunk = copy_chunk();
   const size_t nchunks = (bytes + kCopyChunk - 1) / kCopyChunk;
-  const int T = (int)std::min<size_t>((size_t)copy_threads(), nchunks);
+  // few threads for small copies (wake-ups cost more than they carry), all of them from ~64 MiB on
+  const int T = (int)std::min<size_t>((size_t)copy_threads(), std::max<size_t>(2, nchunks / 8));
   cudaError_t errs[kCopySlots / 2];
   auto work = [&](int t) {
     cudaError_t e = cudaSuccess;
@@ -447,10 +459,22 @@ extern "C" int h2b_ctx_create(int device, h2b_ctx** out) {
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
     ctx->sm_count = sms;
+  int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
+#ifndef H2B_EMU
+  if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_lo = prio_hi = 0;
+  if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->bulk_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) {
+    delete ctx;
+    return H2B_ERR_CUDA;
+  }
+#else
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return H2B_ERR_CUDA;
   }
+  ctx->bulk_stream = ctx->stream;
+#endif
+  for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&ctx->bulk_ev[i], cudaEventDisableTiming);
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -493,6 +517,9 @@ extern "C" void h2b_ctx_destroy(h2b_ctx* ctx) {
     if (ctx->copy_slot_ev[i]) cudaEventDestroy(ctx->copy_slot_ev[i]);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->bulk_ev[i]) cudaEventDestroy(ctx->bulk_ev[i]);
+  if (ctx->bulk_stream && ctx->bulk_stream != ctx->stream) cudaStreamDestroy(ctx->bulk_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -570,7 +570,7 @@ static MsmPlan msm_plan(size_t n, uint32_t table_c = 0) {
   p.pairs = (uint64_t)n * p.W;
   // chunk length of level 0: long enough to amortise the two boundary partials, short enough to
   // keep >= ~64k threads in flight (tuned on B200: k = 16 / 18 / 20 / 24)
-  p.L0 = p.pairs >= (1ull << 25) ? 128 : p.pairs >= (1ull << 23) ? 64 : p.pairs >= (1ull << 21) ? 32 : 16;
+  p.L0 = p.pairs >= (1ull << 25) ? 128 : p.pairs >= (1ull << 23) ? 48 : p.pairs >= (1ull << 21) ? 32 : 16;
   if (const char* e = getenv("H2B_MSM_L0")) {
     const int v = atoi(e);
     if (v >= 2 && v <= 4096) p.L0 = (uint32_t)v;
@@ -850,12 +850,18 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
 #endif
       if (level == 0) {
         Level0Src src{ws->vals_out, d_bases};
-        if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-        H2B_TRY(launch(ctx, msm_accum0_kernel, dim3((nchunks + 127) / 128), dim3(128), 0, src, keys,
-                       (const uint32_t*)(ws->n_level + level), L, (const uint32_t*)ws->cnt,
-                       (const uint32_t*)ws->incl, nchunks, ws->n_level + level + 1, ws->lkeys[o],
-                       ws->lpts[o], ws->buckets));
-        if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+        // the throughput-bound kernel goes to the low-priority stream (common.cuh: bulk_stream)
+        cudaStream_t bulk = ctx->bulk_stream;
+        H2B_CUDA(ctx, cudaEventRecord(ctx->bulk_ev[0], st));
+        H2B_CUDA(ctx, cudaStreamWaitEvent(bulk, ctx->bulk_ev[0], 0));
+        if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], bulk));
+        H2B_TRY(launch_on(ctx, bulk, msm_accum0_kernel, dim3((nchunks + 127) / 128), dim3(128), 0, src, keys,
+                          (const uint32_t*)(ws->n_level + level), L, (const uint32_t*)ws->cnt,
+                          (const uint32_t*)ws->incl, nchunks, ws->n_level + level + 1, ws->lkeys[o],
+                          ws->lpts[o], ws->buckets));
+        if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[1], bulk));
+        H2B_CUDA(ctx, cudaEventRecord(ctx->bulk_ev[1], bulk));
+        H2B_CUDA(ctx, cudaStreamWaitEvent(st, ctx->bulk_ev[1], 0));
       } else {
         LevelNSrc src{ws->lpts[o ^ 1]};
         H2B_TRY(launch(ctx, msm_accumN_kernel, dim3((nchunks + 127) / 128), dim3(128), 0, src, keys,
@@ -1132,7 +1138,9 @@ extern "C" void* h2b_bases_device_ptr(const h2b_bases* b) { return b ? (void*)b-
 
 static int msm_common(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
                       const h2b_fr* scalars, int loc, size_t n, G1Xyzz* acc) {
-  if (!bases || bases->ctx != ctx) return fail(ctx, H2B_ERR_ARG, "bases belong to another context");
+  // bases are immutable once uploaded (and precomputed): any context of the same device may read them,
+  // so that independent commitments can run concurrently on several contexts (one stream each)
+  if (!bases || bases->ctx->device != ctx->device) return fail(ctx, H2B_ERR_ARG, "bases live on another device");
   if (!scalars && n) return fail(ctx, H2B_ERR_ARG, "null pointer");
   // assert_eq!(coeffs.len(), bases.len()) / assert!(bases.len() >= size):
   // arithmetic.rs:133, kzg/commitment.rs:290,332

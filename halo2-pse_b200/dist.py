@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -100,24 +100,35 @@ class ShardedMSM:
         return _gather_fold(self.ctx, out, self.group)
 
 
-def _gather_fold(ctx: Context, out: np.ndarray, group=None):
-    """All-gather of every rank's 64-byte partial point, folded in rank order with h2b_g1_sum
-    (`.fold` of the per-chunk results, arithmetic.rs:153); the same affine point on every rank."""
+def _gather_fold_many(ctx: Context, outs: np.ndarray, group=None) -> list:
+    """outs: (m, 8) limbs, this rank's partial points of m independent MSMs.  ONE all-gather of m * 64
+    bytes per rank, each column folded in rank order with h2b_g1_sum (`.fold` of the per-chunk results,
+    arithmetic.rs:153); the same affine points on every rank."""
     import torch
     import torch.distributed as dist
+    outs = np.ascontiguousarray(outs, dtype=np.uint64).reshape(-1, 8)
+    m = outs.shape[0]
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return g1_decode(out)[0]
+        return g1_decode(outs)
     world = dist.get_world_size(group)
     dev = _group_device(group)
-    mine = torch.from_numpy(out.view(np.int64)).to(dev)
-    parts = torch.empty(world * 8, dtype=torch.int64, device=dev)
+    mine = torch.from_numpy(outs.view(np.int64).reshape(-1)).to(dev)
+    parts = torch.empty(world * m * 8, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(parts, mine, group=group)
-    allp = np.ascontiguousarray(parts.cpu().numpy().view(np.uint64)).reshape(world, 8)
-    total = np.zeros(8, dtype=np.uint64)
-    rc = ctx.lib.h2b_g1_sum(C.c_void_p(allp.ctypes.data), world, C.c_void_p(total.ctypes.data))
-    if rc != 0:
-        raise H2BError(rc, "h2b_g1_sum")
-    return g1_decode(total)[0]
+    allp = parts.cpu().numpy().view(np.uint64).reshape(world, m, 8)
+    res = []
+    for i in range(m):
+        col = np.ascontiguousarray(allp[:, i, :])
+        total = np.zeros(8, dtype=np.uint64)
+        rc = ctx.lib.h2b_g1_sum(C.c_void_p(col.ctypes.data), world, C.c_void_p(total.ctypes.data))
+        if rc != 0:
+            raise H2BError(rc, "h2b_g1_sum")
+        res.append(g1_decode(total)[0])
+    return res
+
+
+def _gather_fold(ctx: Context, out: np.ndarray, group=None):
+    return _gather_fold_many(ctx, out, group)[0]
 
 
 class ShardedBases:
@@ -165,28 +176,48 @@ class ShardedBases:
             self.local.precompute(window_bits)
         return self
 
-    def msm(self, scalars, n: Optional[int] = None, offset: int = 0, affine: bool = True, scalar_offset: int = 0):
+    def _local_job(self, scalars, n, offset, scalar_offset):
+        """This rank's part of best_multiexp(scalars[scalar_offset..][..n], bases[offset..offset + n]) as a job
+        for the local base set, or None if its range misses the slice."""
         if not isinstance(scalars, DeviceBuffer):
-            arr = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
-            n = arr.shape[0] - scalar_offset if n is None else n
+            scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+            n = scalars.shape[0] - scalar_offset if n is None else n
         elif n is None:
             raise H2BError(_ffi.H2B_ERR_ARG, "n required for device scalars")
         if offset + n > self.n:
             raise H2BError(_ffi.H2B_ERR_LENGTH, "assert!(bases.len() >= size)")  # poly/kzg/commitment.rs:290,332
         lo, hi = max(self.start, offset), min(self.end, offset + n)
-        out = np.zeros(8, dtype=np.uint64)  # identity if this rank's range misses the slice
-        if hi > lo:
-            so = scalar_offset + (lo - offset)
-            if isinstance(scalars, DeviceBuffer):
-                if (so + hi - lo) * 32 > scalars.nbytes:
-                    raise H2BError(_ffi.H2B_ERR_LENGTH, "scalar slice outside the buffer")
-                sp, loc = scalars.at(so * 32), H2B_DEVICE
-            else:
-                sub = arr[so:so + hi - lo]
-                sp, loc = C.c_void_p(sub.ctypes.data), _ffi.H2B_HOST
-            self.ctx._check(self.ctx.lib.h2b_msm_affine(self.ctx.h, self.local.h, lo - self.start, sp, loc,
-                                                        hi - lo, C.c_void_p(out.ctypes.data)))
-        return _gather_fold(self.ctx, out, self.group)
+        if hi <= lo:
+            return None
+        return (scalars, hi - lo, lo - self.start, scalar_offset + (lo - offset))
+
+    def msm_many(self, jobs: Sequence[tuple], concurrent: bool = True, pre: Optional[Sequence] = None) -> list:
+        return ShardedBases.msm_many_mixed([(self,) + tuple(j) for j in jobs], concurrent, pre)
+
+    @staticmethod
+    def msm_many_mixed(jobs: Sequence[tuple], concurrent: bool = True, pre: Optional[Sequence] = None) -> list:
+        """Independent commitments, jobs[i] = (sharded bases, scalars, n, offset, scalar_offset): the local parts
+        run on this GPU (several at a time, api.msm_many_mixed_raw), then ONE all-gather carries every job's
+        partial point.  pre[i](ctx) as in api.msm_many_mixed_raw."""
+        if not jobs:
+            return []
+        jobs = [tuple(j) + (None, 0, 0)[len(j) - 2:] for j in jobs]
+        first = jobs[0][0]
+        local = [j[0]._local_job(*j[1:]) for j in jobs]
+        outs = np.zeros((len(jobs), 8), dtype=np.uint64)  # identity where this rank's range misses the slice
+        live = [i for i, j in enumerate(local) if j is not None]
+        if pre is not None:
+            for i, j in enumerate(local):
+                if j is None and pre[i] is not None:
+                    pre[i](first.ctx)
+        lpre = None if pre is None else [pre[i] for i in live]
+        from .api import msm_many_mixed_raw
+        for i, o in zip(live, msm_many_mixed_raw([(jobs[i][0].local,) + local[i] for i in live], concurrent, lpre)):
+            outs[i] = o
+        return _gather_fold_many(first.ctx, outs, first.group)
+
+    def msm(self, scalars, n: Optional[int] = None, offset: int = 0, affine: bool = True, scalar_offset: int = 0):
+        return self.msm_many([(scalars, n, offset, scalar_offset)])[0]
 
     def free(self) -> None:
         self.local.free()

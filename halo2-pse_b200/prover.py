@@ -329,7 +329,7 @@ def keygen(params: ParamsKZG, cs: ConstraintSystem, fixed_values: Sequence, copi
 
     # fixed columns (keygen.rs:237-258, 300-316)
     pk.fixed_values = [ctx.upload_fr(_as_limbs(v, n)) for v in fixed_values]
-    pk.fixed_commitments = [params.g_lagrange.msm(b, n) for b in pk.fixed_values]
+    pk.fixed_commitments = params.g_lagrange.msm_many([(b, n) for b in pk.fixed_values])
     pk.fixed_polys = [to_coeff(b) for b in pk.fixed_values]
     pk.fixed_cosets = [to_coset(b) for b in pk.fixed_polys]
 
@@ -349,7 +349,7 @@ def keygen(params: ParamsKZG, cs: ConstraintSystem, fixed_values: Sequence, copi
         col.free()
     omega_powers.free()
     pk.permutations = [ctx.upload_fr(table[asm.mapping[i * n:(i + 1) * n]]) for i in range(len(pc))]
-    pk.perm_commitments = [params.g_lagrange.msm(b, n) for b in pk.permutations]
+    pk.perm_commitments = params.g_lagrange.msm_many([(b, n) for b in pk.permutations])
     pk.permutation_polys = [to_coeff(b) for b in pk.permutations]
     pk.permutation_cosets = [to_coset(b) for b in pk.permutation_polys]
 
@@ -485,20 +485,21 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
                     raise H2BError(_ffi.H2B_ERR_LENGTH, "Error::not_enough_rows_available")  # :228-230
                 host_cols.append(col)
             lap("witness")
-            bufs = []
+            bufs, uploads = [], []
             for col in host_cols:  # assigned rows, zero padding, then the blinding factors (:364-368)
                 b = ctx.alloc(n * 32)
-                if col.shape[0]:
-                    b.upload(col)
                 if col.shape[0] < unusable_rows_start:
                     ctx.memset(b, 0, (unusable_rows_start - col.shape[0]) * 32, col.shape[0] * 32)
                 b.upload(fr_encode([fr_random(rng) for _ in range(n - unusable_rows_start)]), unusable_rows_start * 32)
                 bufs.append(b)
+                # the assigned rows travel right before the column's commitment, on the context that computes
+                # it: the copy of the next column overlaps the commitment of this one
+                uploads.append((lambda c, b=b, col=col: b.upload(col, ctx=c)) if col.shape[0] else None)
             for _ in host_cols:    # Blind(Scalar::random(rng)) per column, ignored by KZG (:371-374)
                 fr_random(rng)
             lap("advice_upload")
-            for b in bufs:
-                transcript.write_point(params.g_lagrange.msm(b, n))  # :375-392
+            for point in params.g_lagrange.msm_many([(b, n) for b in bufs], pre=uploads):  # :375-392, independent commitments
+                transcript.write_point(point)
             for idx, b in zip(column_indices, bufs):
                 advice_values[ci][idx] = b
             lap("advice_commit")
@@ -532,12 +533,11 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
                                                   unusable_rows_start, lk.permuted_input.ptr, lk.permuted_table.ptr))
             for b in (lk.permuted_input, lk.permuted_table):  # blinding rows (:447-449)
                 b.upload(fr_encode([fr_random(rng) for _ in range(bf + 1)]), unusable_rows_start * 32)
-            commitments = []
             for name in ("permuted_input", "permuted_table"):  # commit_values (:114-125)
                 values = getattr(lk, name)
                 setattr(lk, name + "_poly", _Poly(ctx, to_coeff(values), n))
                 fr_random(rng)  # Blind
-                commitments.append(params.g_lagrange.msm(values, n))
+            commitments = params.g_lagrange.msm_many([(lk.permuted_input, n), (lk.permuted_table, n)])
             transcript.write_point(commitments[0])
             transcript.write_point(commitments[1])
             lks.append(lk)
@@ -559,6 +559,10 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
     class _Committed:
         pass
 
+    # The permutation products, the lookup products and the vanishing argument's random polynomial are
+    # committed between the same two challenges (gamma and y): their commitments are independent, so they are
+    # computed together after the last of them exists and written to the transcript in the reference's order.
+    deferred: List[tuple] = []   # (bases, Lagrange / coefficient buffer, n, free afterwards?)
     permutations = []
     for ci in range(len(instances)):
         def column_values(c):
@@ -580,13 +584,12 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
             z.upload(blinds, (n - bf) * 32)
             last_z = fr_decode(z.download(1, (n - (bf + 1)) * 32))[0]  # :165
             fr_random(rng)  # Blind (:167)
-            commitment = params.g_lagrange.msm(z, n)
-            dom.lagrange_to_coeff_device(z)
+            deferred.append((params.g_lagrange, z, n, True))
+            zc = to_coeff(z)
             st = _Set()
-            st.poly = _Poly(ctx, z, n)
+            st.poly = _Poly(ctx, zc, n)
             st.permutation_product_coset = ctx.alloc(ext * 32)
-            dom.coeff_to_extended_device(z, st.permutation_product_coset)
-            transcript.write_point(commitment)
+            dom.coeff_to_extended_device(zc, st.permutation_product_coset)
             committed.sets.append(st)
         permutations.append(committed)
     lap("permutation_commit")
@@ -602,10 +605,8 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
             frac.free()
             z.upload(fr_encode([fr_random(rng) for _ in range(bf)]), (n - bf) * 32)
             fr_random(rng)  # product_blind
-            commitment = params.g_lagrange.msm(z, n)
-            dom.lagrange_to_coeff_device(z)
-            lk.product_poly = _Poly(ctx, z, n)
-            transcript.write_point(commitment)
+            deferred.append((params.g_lagrange, z, n, True))
+            lk.product_poly = _Poly(ctx, to_coeff(z), n)
             for b in (lk.permuted_input, lk.permuted_table, lk.compressed_input, lk.compressed_table):
                 b.free()
     lap("lookup_product")
@@ -614,7 +615,12 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
     random_poly = _Poly(ctx, fr_random_device(ctx, rng, n), n)
     fr_random(rng)  # random_blind
     lap("random_poly")
-    transcript.write_point(params.g.msm(random_poly.buf, n))
+    deferred.append((params.g, random_poly.buf, n, False))
+    for point in type(params.g).msm_many_mixed([d[:3] for d in deferred]):
+        transcript.write_point(point)
+    for _, buf, _, release in deferred:
+        if release:
+            buf.free()
     lap("random_commit")
 
     y = transcript.squeeze_challenge_scalar()  # :478
@@ -642,8 +648,8 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
     for _ in range(n_pieces):
         fr_random(rng)  # h_blinds
     lap("h_to_coeff")
-    for i in range(n_pieces):
-        transcript.write_point(params.g.msm(h_coeff, n, offset=0, scalar_offset=i * n))
+    for point in params.g.msm_many([(h_coeff, n, 0, i * n) for i in range(n_pieces)]):
+        transcript.write_point(point)
     lap("h_commit")
 
     x = transcript.squeeze_challenge_scalar()  # :525
@@ -752,6 +758,7 @@ class ProverGWC:
             else:
                 sets.append((q[0], [q]))
         one_l = fr_encode([1])
+        witnesses = []
         for z, qs in sets:
             n = qs[0][1].n
             poly_batch = ctx.clone(qs[0][1].buf, n * 32)  # power_of_v = 1
@@ -766,10 +773,13 @@ class ProverGWC:
             # &poly_batch - eval_batch: the constant coefficient (poly.rs:298-305)
             c0 = fr_decode(poly_batch.download(1))[0]
             poly_batch.upload(fr_encode([(c0 - eval_batch) % R_MOD]))
-            witness = ctx.kate_division(poly_batch, z, n)
+            witnesses.append((ctx.kate_division(poly_batch, z, n), n - 1))
             poly_batch.free()
-            transcript.write_point(self.params.g.msm(witness, n - 1))
-            witness.free()
+        # the witness commitments depend on no challenge drawn in between: committed together (gwc/prover.rs:80-88)
+        for point in self.params.g.msm_many(witnesses):
+            transcript.write_point(point)
+        for w, _ in witnesses:
+            w.free()
 
 
 def lagrange_interpolate(points: Sequence[int], evals: Sequence[int]) -> List[int]:
