@@ -189,7 +189,11 @@ def _fmt_expr(e: Expression) -> str:
     return "%s(%s, %s)" % ("Sum" if k == "sum" else "Product", _fmt_expr(e.node[1]), _fmt_expr(e.node[2]))
 
 
-def pinned_debug(cs: ConstraintSystem, k: int, extended_k: int, omega: int, fixed_commitments, perm_commitments) -> str:
+def pinned_debug(cs: ConstraintSystem, k: int, extended_k: int, omega: int, fixed_commitments, perm_commitments,
+                 base_modulus: int = Q_MOD, scalar_modulus: int = R_MOD) -> str:
+    """format!("{:?}", vk.pinned()) (plonk.rs:192-203, circuit.rs:1399-1448): the string whose Blake2b hash
+    seeds every transcript.  tests/test_oracle.py checks it, character for character, against the reference's
+    golden verifying key of tests/plonk_api.rs (the moduli are parameters only for that test: it is over Vesta)."""
     lst = lambda items: "[" + ", ".join(items) + "]"  # noqa: E731
     col = lambda c: "Column { index: %d, column_type: %s }" % (c.index, _TYPE_NAME[c.column_type])  # noqa: E731
     qs = lambda q: lst("(%s, Rotation(%d))" % (col(c), r) for c, r in q)  # noqa: E731
@@ -212,7 +216,7 @@ def pinned_debug(cs: ConstraintSystem, k: int, extended_k: int, omega: int, fixe
     return ("PinnedVerificationKey { base_modulus: \"%s\", scalar_modulus: \"%s\", domain: PinnedEvaluationDomain "
             "{ k: %d, extended_k: %d, omega: %s }, cs: PinnedConstraintSystem { %s }, fixed_commitments: %s, "
             "permutation: VerifyingKey { commitments: %s } }" % (
-                _hex(Q_MOD), _hex(R_MOD), k, extended_k, _hex(omega), ", ".join(f),
+                _hex(base_modulus), _hex(scalar_modulus), k, extended_k, _hex(omega), ", ".join(f),
                 lst(pt(p) for p in fixed_commitments), lst(pt(p) for p in perm_commitments)))
 
 

@@ -15,9 +15,14 @@ tag 0.3.1, /root/reference/halo2_proofs/Cargo.toml:51) with ``ff 0.12`` and
 (alt_bn128): y^2 = x^3 + 3 over Fq, generator (1, 2), scalar field Fr with
 2-adicity 28 and multiplicative generator 7.
 
-PARITY UNPINNED by reference golden vectors: the reference holds no golden
-bytes for bn256 (its only pinned artefact, tests/plonk_api.rs:624-1020, is
-IPA/Vesta).  This oracle is pinned by (i) the definitional known-answer
+PARITY PARTLY PINNED.  Pinned against the reference's one golden artefact (the
+pinned verifying key of tests/plonk_api.rs:626-1019, fixture
+tests/golden/pinned_vk_plonk_api.json): EvaluationDomain::new's derivation of
+extended_k and omega (`domain_roots`, run there with the Vesta scalar field the
+key is over; tests/test_oracle.py::test_pinned_vk_of_the_reference).
+UNPINNED by reference golden vectors: the bn256 field / curve arithmetic, MSM
+and NTT outputs -- the reference holds no golden bytes for bn256 and cannot be
+built here.  For those this oracle is pinned by (i) the definitional known-answer
 vectors of SURVEY.md section 8c (``tests/golden/kat_bn256.json``), (ii) the
 reference's own test identities (kzg/commitment.rs:361-384 ``commit(ifft(a)) ==
 commit_lagrange(a)``, ntt round trips, NTT vs O(n^2) evaluation, MSM vs the
@@ -300,6 +305,20 @@ def dft_naive(a: Sequence[int], omega: int) -> List[int]:
     return out
 
 
+def domain_roots(j: int, k: int, modulus: int = R_MOD, root_of_unity: int = ROOT_OF_UNITY, s: int = S):
+    """(extended_k, extended_omega, omega) of EvaluationDomain::new(j, k), domain.rs:39-73, for any FieldExt
+    given by (modulus, ROOT_OF_UNITY, S).  The bn256 domain below goes through here; so does the pin against
+    the reference's golden verifying key, which is over the Vesta scalar field (tests/test_oracle.py)."""
+    n = 1 << k
+    ek = k
+    while (1 << ek) < n * (j - 1):  # :49-52
+        ek += 1
+    assert ek <= s
+    extended_omega = pow(root_of_unity, 1 << (s - ek), modulus)  # :54-61
+    omega = pow(extended_omega, 1 << (ek - k), modulus)  # :70-73
+    return ek, extended_omega, omega
+
+
 class EvaluationDomain:
     """domain.rs:19-361, field-element (G = Fr) instantiation."""
 
@@ -308,13 +327,8 @@ class EvaluationDomain:
         self.quotient_poly_degree = j - 1  # :41
         self.n = 1 << k
         self.k = k
-        ek = k
-        while (1 << ek) < self.n * self.quotient_poly_degree:  # :49-52
-            ek += 1
-        assert ek <= S
+        ek, self.extended_omega, self.omega = domain_roots(j, k)
         self.extended_k = ek
-        self.extended_omega = pow(ROOT_OF_UNITY, 1 << (S - ek), r)  # :54-61
-        self.omega = pow(self.extended_omega, 1 << (ek - k), r)  # :70-73
         self.g_coset = ZETA  # :81
         self.g_coset_inv = ZETA * ZETA % r  # :82
         orig = pow(ZETA, self.n, r)  # :88

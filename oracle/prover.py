@@ -19,8 +19,12 @@ GWC multi-opening, Blake2b transcript and `Challenge255`:
                                       shplonk/verifier.rs:52-148; arithmetic.rs:405-478
 * lookup argument (prover/verifier) -- src/plonk/lookup/prover.rs:55-475, src/plonk/lookup/verifier.rs:35-210
 
-PARITY UNPINNED by reference bytes: the reference cannot be built here (no Rust toolchain) and holds no bn256
-proof fixtures.  Encodings that live in the absent crate halo2curves 0.3.1 are restated from its published
+PARITY PARTLY PINNED.  Pinned, character for character, against the reference's golden verifying key
+(tests/plonk_api.rs:626-1019; tests/test_oracle.py::test_pinned_vk_of_the_reference): `pinned_vk_debug`, i.e. the
+Debug rendering of PinnedVerificationKey / PinnedConstraintSystem / Expression / Column / Rotation and of field
+elements and points (assumption A3 below, in the form pasta_curves prints them), and with it the input of the
+verifying-key hash that seeds every transcript.  UNPINNED by reference bytes: proofs themselves -- the reference
+cannot be built here (no Rust toolchain) and holds no bn256 proof fixtures.  Encodings that live in the absent crate halo2curves 0.3.1 are restated from its published
 source and are ASSUMPTIONS, listed in DESIGN.md: (A2) G1Affine::to_bytes = 32-byte LE x with bit 7 of byte 31
 = parity of y, identity = zeros; (A3) `{:?}` of Fr/Fq = "0x" + 64 lowercase hex digits, big-endian, of a point
 "(x, y)"; (A4) Fr::random(rng) and from_bytes_wide = the 512-bit little-endian integer mod r, eight
@@ -259,8 +263,11 @@ def _dbg_list(items) -> str:
     return "[" + ", ".join(items) + "]"
 
 
-def pinned_vk_debug(cs: CS, k: int, extended_k: int, omega: int, fixed_commitments, perm_commitments) -> str:
-    """format!("{:?}", vk.pinned())   plonk.rs:197, :220-230; circuit.rs:1398-1452; domain.rs:470-486"""
+def pinned_vk_debug(cs: CS, k: int, extended_k: int, omega: int, fixed_commitments, perm_commitments,
+                    base_modulus: int = Q_MOD, scalar_modulus: int = R_MOD) -> str:
+    """format!("{:?}", vk.pinned())   plonk.rs:197, :220-230; circuit.rs:1398-1452; domain.rs:470-486
+    PINNED: tests/test_oracle.py::test_pinned_vk_of_the_reference compares it character for character with the
+    reference's golden verifying key (tests/plonk_api.rs:626-1019; over Vesta, hence the modulus parameters)."""
     def col(t, i):
         return "Column { index: %d, column_type: %s }" % (i, _TYPE_NAME[t])
 
@@ -287,7 +294,7 @@ def pinned_vk_debug(cs: CS, k: int, extended_k: int, omega: int, fixed_commitmen
             "domain: PinnedEvaluationDomain { k: %d, extended_k: %d, omega: %s }, "
             "cs: PinnedConstraintSystem { %s }, fixed_commitments: %s, "
             "permutation: VerifyingKey { commitments: %s } }"
-            % (Q_MOD, R_MOD, k, extended_k, _dbg_fr(omega), ", ".join(f),
+            % (base_modulus, scalar_modulus, k, extended_k, _dbg_fr(omega), ", ".join(f),
                _dbg_list(_dbg_point(p) for p in fixed_commitments), _dbg_list(_dbg_point(p) for p in perm_commitments)))
 
 

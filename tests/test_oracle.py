@@ -235,3 +235,55 @@ def test_poly_helpers_oracles(oracle_c):
         # a(X) = q(X) (X - x) + a(x): check at a random point
         z = rng.randrange(O.R_MOD)
         assert (O.eval_polynomial(q, z) * (z - x) + ev) % O.R_MOD == O.eval_polynomial(a, z)
+
+
+def test_pinned_vk_of_the_reference():
+    """The reference's one golden artefact: the pinned verifying key of tests/plonk_api.rs:626-1019 (k = 5, IPA
+    over Vesta; fixture tests/golden/pinned_vk_plonk_api.json, made by make_pinned_vk_fixture.py).  It pins,
+    against bytes the reference itself asserts on:
+      * EvaluationDomain::new's derivation of extended_k and omega (domain.rs:39-73) -- same oracle code path as
+        bn256, with Vesta's scalar field (modulus, S = 32, generator 5) as the FieldExt;
+      * the ConstraintSystem bookkeeping of the host mirror (column counts, query indices and their order,
+        enable_equality's queries, lookup table queries, permutation column order, degree -> extended_k);
+      * `format!("{:?}", vk.pinned())`, the string every transcript is seeded with (plonk.rs:192-203), in the
+        oracle's and in the product mirror's formatter, character for character.
+    The commitments in the key are Vesta points from IPA parameters (hash-to-curve generators): they are passed
+    through as given; bn256 curve arithmetic has no golden vector in the reference."""
+    import halo2_pse_b200 as h
+    from halo2_pse_b200.prover import pinned_debug
+    from oracle import prover as OV
+    from tests import plonk_cases as PC
+
+    fx = H.load_golden("pinned_vk_plonk_api.json")
+    # plonk_api.rs:389-470 -- MyCircuit::configure, statement by statement
+    cs = h.ConstraintSystem()
+    e, a, b = cs.advice_column(), cs.advice_column(), cs.advice_column()
+    sf = cs.fixed_column()
+    c, d = cs.advice_column(), cs.advice_column()
+    p = cs.instance_column()
+    for col in (a, b, c):
+        cs.enable_equality(col)
+    sm, sa, sb, sc, sp = (cs.fixed_column() for _ in range(5))
+    sl = cs.fixed_column()  # lookup_table_column
+    a_ = cs.query_advice(a)
+    cs.lookup("lookup", [(a_, cs.query_fixed(sl))])  # the table column is queried after the closure ran
+    qd, qa, qsf = cs.query_advice(d, 1), cs.query_advice(a), cs.query_fixed(sf)
+    qe, qb, qc = cs.query_advice(e, -1), cs.query_advice(b), cs.query_advice(c)
+    qsa, qsb, qsc, qsm = cs.query_fixed(sa), cs.query_fixed(sb), cs.query_fixed(sc), cs.query_fixed(sm)
+    cs.create_gate("Combined add-mult", [qa * qsa + qb * qsb + qa * qb * qsm - (qc * qsc) + qsf * (qd * qe)])
+    qa, qp, qsp = cs.query_advice(a), cs.query_instance(p), cs.query_fixed(sp)
+    cs.create_gate("Public input", [qsp * (qa - qp)])
+    for col in (sf, e, d, p, sm, sa, sb, sc, sp):
+        cs.enable_equality(col)
+
+    # the domain, through the oracle's EvaluationDomain::new restatement with Vesta's scalar field
+    modulus = int(fx["scalar_modulus"], 16)
+    root = pow(5, (modulus - 1) >> 32, modulus)  # pasta Fp: S = 32, multiplicative generator 5
+    ek, _, omega = O.domain_roots(cs.degree(), fx["k"], modulus, root, 32)
+    assert ek == fx["extended_k"] and omega == int(fx["omega"], 16)
+
+    pts = lambda key: [(int(x, 16), int(y, 16)) for x, y in fx[key]]  # noqa: E731
+    args = (fx["k"], ek, omega, pts("fixed_commitments"), pts("permutation_commitments"))
+    mod = dict(base_modulus=int(fx["base_modulus"], 16), scalar_modulus=modulus)
+    assert pinned_debug(cs, *args, **mod) == fx["debug"]
+    assert OV.pinned_vk_debug(PC.oracle_cs(cs), *args, **mod) == fx["debug"]
