@@ -100,6 +100,21 @@ class ShardedMSM:
         return _gather_fold(self.ctx, out, self.group)
 
 
+class _CudaView:
+    """A device buffer of the library seen through __cuda_array_interface__ (torch.as_tensor shares the memory)."""
+
+    def __init__(self, ptr: int, nwords: int):
+        self.__cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def _as_tensor(buf: DeviceBuffer, nwords: int, dev):
+    """int64 tensor over the first `nwords` words of a DeviceBuffer, on the process group's device (no copy)."""
+    import torch
+    if dev.type == "cuda":
+        return torch.as_tensor(_CudaView(int(buf.ptr.value), nwords), device=dev)
+    return torch.frombuffer((C.c_int64 * nwords).from_address(int(buf.ptr.value)), dtype=torch.int64)
+
+
 def _gather_fold_many(ctx: Context, outs: np.ndarray, group=None) -> list:
     """outs: (m, 8) limbs, this rank's partial points of m independent MSMs.  ONE all-gather of m * 64
     bytes per rank, each column folded in rank order with h2b_g1_sum (`.fold` of the per-chunk results,
@@ -175,6 +190,39 @@ class ShardedBases:
         if len(self.local):
             self.local.precompute(window_bits)
         return self
+
+    def upload_columns(self, bufs: Sequence[DeviceBuffer], cols: Sequence[np.ndarray]) -> None:
+        """Host columns (the witness) -> the replicated device buffers of every rank, without every rank pulling
+        every byte over its own PCIe link and through its own host threads: rank g copies rows [start_g, end_g)
+        of each column from the host, then ONE in-place all-gather per column spreads them over NVLink.  Rows
+        past the end of a column (padding and blinding rows) were already written identically on every rank and
+        travel along unchanged."""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        per = self.n // world if world else self.n
+        if world == 1 or self.n % world or per * world != self.n:
+            for b, col in zip(bufs, cols):
+                if col.shape[0]:
+                    b.upload(col)
+            return
+        for b, col in zip(bufs, cols):
+            lo, hi = self.start, min(self.end, col.shape[0])
+            if hi > lo:
+                b.upload(col[lo:hi], lo * 32)
+        self.ctx.sync()
+        dev = _group_device(self.group)
+        for b in bufs:
+            full = _as_tensor(b, self.n * 4, dev)
+            mine = full[self.start * 4:(self.start + per) * 4]
+            if dev.type == "cuda":
+                dist.all_gather_into_tensor(full, mine, group=self.group)  # in place: `mine` is its own slot of `full`
+            else:
+                out = torch.empty_like(full)
+                dist.all_gather_into_tensor(out, mine.clone(), group=self.group)
+                full.copy_(out)
+        if dev.type == "cuda":
+            torch.cuda.current_stream().synchronize()
 
     def _local_job(self, scalars, n, offset, scalar_offset):
         """This rank's part of best_multiexp(scalars[scalar_offset..][..n], bases[offset..offset + n]) as a job

@@ -501,6 +501,10 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
                 uploads.append((lambda c, b=b, col=col: b.upload(col, ctx=c)) if col.shape[0] else None)
             for _ in host_cols:    # Blind(Scalar::random(rng)) per column, ignored by KZG (:371-374)
                 fr_random(rng)
+            spread = getattr(params.g_lagrange, "upload_columns", None)
+            if spread is not None:  # bases sharded over GPUs: each rank copies its own rows, NVLink does the rest
+                spread(bufs, host_cols)
+                uploads = None
             lap("advice_upload")
             for point in params.g_lagrange.msm_many([(b, n) for b in bufs], pre=uploads):  # :375-392, independent commitments
                 transcript.write_point(point)
