@@ -49,6 +49,8 @@ struct MsmWorkspace {
   uint32_t* lkeys[2] = {nullptr, nullptr};
   G1Xyzz* lpts[2] = {nullptr, nullptr};
   G1Xyzz* buckets = nullptr;
+  G1Xyzz* buckets2 = nullptr;  // bucket array of the later batches of an MSM whose host scalars arrive in batches
+  size_t cap_buckets2 = 0;
   G1Xyzz* seg[2] = {nullptr, nullptr};  // tree-sum ping-pong
   G1Xyzz* h_out = nullptr;              // pinned, W window sums
   // batched-affine accumulation (window-table MSMs)
@@ -76,6 +78,9 @@ static void ws_release(MsmWorkspace* ws) {
     cudaFree(ws->seg[i]);
   }
   cudaFree(ws->buckets);
+  if (ws->buckets2) cudaFree(ws->buckets2);
+  ws->buckets2 = nullptr;
+  ws->cap_buckets2 = 0;
   for (int i = 0; i < 2; ++i) {
     cudaFree(ws->akeys[i]);
     cudaFree(ws->apts[i]);
@@ -99,10 +104,11 @@ void msm_ws_free(h2b_ctx* ctx) {
 // 1. digits
 // ---------------------------------------------------------------------------
 // table_stride > 0 (window table): key = |d| - 1 for every window, val = w * table_stride + i
-// Processes scalars [i0, i1) of n.
-__global__ void msm_digits_kernel(const Fr* scalars, uint64_t n, uint32_t c, uint32_t W,
+// Processes scalars [i0, i1); the pair of (scalar i, window w) goes to slot w * row_stride + (i - row_base)
+// (row_stride = n, row_base = 0 for a whole MSM; a batch of scalars gets its own compact pair array).
+__global__ void msm_digits_kernel(const Fr* scalars, uint64_t row_stride, uint32_t c, uint32_t W,
                                   uint32_t* keys, uint32_t* vals, uint64_t table_stride, uint64_t i0,
-                                  uint64_t i1) {
+                                  uint64_t i1, uint64_t row_base) {
   for (uint64_t i = i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1;
        i += (uint64_t)gridDim.x * blockDim.x) {
     const Fr s = from_mont(ld_fp(scalars + i));  // to_repr(), arithmetic.rs:14
@@ -126,12 +132,13 @@ __global__ void msm_digits_kernel(const Fr* scalars, uint64_t n, uint32_t c, uin
       } else {
         carry = 0;
       }
+      const uint64_t slot = (uint64_t)w * row_stride + (i - row_base);
       if (table_stride) {
-        keys[(uint64_t)w * n + i] = d ? d - 1 : 0xffffffffu;
-        vals[(uint64_t)w * n + i] = (uint32_t)(w * table_stride + i) | (negf << 31);
+        keys[slot] = d ? d - 1 : 0xffffffffu;
+        vals[slot] = (uint32_t)(w * table_stride + i) | (negf << 31);
       } else {
-        keys[(uint64_t)w * n + i] = d ? w * half + d - 1 : 0xffffffffu;
-        vals[(uint64_t)w * n + i] = (uint32_t)i | (negf << 31);
+        keys[slot] = d ? w * half + d - 1 : 0xffffffffu;
+        vals[slot] = (uint32_t)i | (negf << 31);
       }
     }
   }
@@ -217,6 +224,9 @@ H2B_D void st_xyzz(G1Xyzz* dst, const G1Xyzz& p) {
   st_fp(&dst->zzz, p.zzz);
 }
 
+// A bucket is written exactly once per pass over a sorted pair list (at the level where its run is no longer
+// cut), with a plain store: lanes reach the ends of their runs at different iterations, so anything heavier
+// there (adding to an earlier batch's bucket, say) would be executed by the warp on almost every iteration.
 template <class Src>
 H2B_D void msm_accum_body(const Src& src, const uint32_t* keys, const uint32_t* n_cur, uint32_t L,
                           const uint32_t* cnt, const uint32_t* incl, uint32_t nchunks,
@@ -481,6 +491,17 @@ H2B_D G1Xyzz ld_xyzz(const G1Xyzz* p) {
   b.zz = ld_fp(&p->zz);
   b.zzz = ld_fp(&p->zzz);
   return b;
+}
+
+// buckets[i] += more[i]: folds the bucket array of a later batch of host scalars into the MSM's buckets
+__global__ void __launch_bounds__(128) msm_bucket_merge_kernel(G1Xyzz* buckets, const G1Xyzz* more, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const G1Xyzz m = ld_xyzz(more + i);
+  if (m.is_identity()) return;
+  G1Xyzz b = ld_xyzz(buckets + i);
+  xyzz_add(b, m);
+  st_xyzz(buckets + i, b);
 }
 
 // Segment s of window w covers buckets [s*M, (s+1)*M) (bucket index b holds
@@ -774,20 +795,65 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   cudaStream_t st = ctx->stream;
   (void)st;
 
-  // 1. digits (host scalars: chunked H2D on the copy stream, overlapped with the digit kernel)
+  // Host scalars on a window table: the MSM is cut into NB batches of points that share the bucket array.
+  // Batch b + 1 travels over PCIe (copy stream) while batch b is sorted and accumulated; batches after the
+  // first fill a second bucket array that one element-wise kernel folds into the first.  One bucket
+  // reduction at the end.  Everything else is one batch.
+  // (B200, PCIe 5: k = 24 49.2 -> 45.9 ms with 4 batches; neutral at k = 23, a loss below: smaller sorts)
+  uint64_t batch_min = 1ull << 22;  // points per batch; H2B_MSM_BATCH_MIN overrides (tests), 0 disables
+  if (const char* e = getenv("H2B_MSM_BATCH_MIN")) batch_min = strtoull(e, nullptr, 10);
+  const int NB = (h_scalars && table_stride && batch_min) ? (n >= 4 * batch_min ? 4 : n >= 2 * batch_min ? 2 : 1) : 1;
+  const uint64_t per_batch = (n + NB - 1) / NB;
+  H2B_CUDA(ctx, cudaMemsetAsync(ws->buckets, 0, (size_t)p.Wb * p.nb_per_window * sizeof(G1Xyzz), st));
+  // copy of batch b on the copy stream, event copy_ev[b]; queued right after the compute of batch b - 1, so
+  // that a pageable source (staged by host threads, which blocks this thread) overlaps that compute as well
+  auto queue_copy = [&](int b) -> int {
+    const uint64_t i0 = (uint64_t)b * per_batch, i1 = std::min<uint64_t>(n, i0 + per_batch);
+    if (b >= NB || i0 >= i1) return H2B_OK;
+    H2B_TRY(copy_h2d_any(ctx, const_cast<Fr*>(d_scalars) + i0, h_scalars + i0, (i1 - i0) * sizeof(Fr), ctx->copy_stream));
+    H2B_CUDA(ctx, cudaEventRecord(ctx->copy_ev[b], ctx->copy_stream));
+    return H2B_OK;
+  };
+  if (h_scalars && NB > 1) {
+    // the copy stream must not overwrite the staging buffer while an earlier call still reads it
+    H2B_CUDA(ctx, cudaEventRecord(ctx->copy_ev[7], st));
+    H2B_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[7], 0));
+    H2B_TRY(queue_copy(0));
+  }
+  for (int batch = 0; batch < NB; ++batch) {
+  const uint64_t b0 = (uint64_t)batch * per_batch, b1 = std::min<uint64_t>(n, b0 + per_batch);
+  if (b0 >= b1) break;
+  const uint64_t nbatch = b1 - b0;
+  const uint64_t pairs = NB > 1 ? nbatch * p.W : p.pairs;
+  // later batches fill a second bucket array, folded into the first by one element-wise kernel
+  const uint32_t nbuckets_all = p.Wb * p.nb_per_window;
+  G1Xyzz* target = ws->buckets;
+  if (batch > 0) {
+    if (ws->cap_buckets2 < nbuckets_all) {
+      H2B_CUDA(ctx, cudaStreamSynchronize(st));
+      if (ws->buckets2) cudaFree(ws->buckets2);
+      ws->buckets2 = nullptr;
+      ws->cap_buckets2 = 0;
+      H2B_CUDA(ctx, cudaMalloc((void**)&ws->buckets2, (size_t)nbuckets_all * sizeof(G1Xyzz)));
+      ws->cap_buckets2 = nbuckets_all;
+    }
+    target = ws->buckets2;
+    H2B_CUDA(ctx, cudaMemsetAsync(target, 0, (size_t)nbuckets_all * sizeof(G1Xyzz), st));
+  }
+  // 1. digits (host scalars, single batch: chunked H2D on the copy stream, overlapped with the digit kernel)
   {
     const uint64_t cap = (uint64_t)ctx->sm_count * 16;
-    const int nchunk = (h_scalars && n >= (1u << 16)) ? 8 : 1;
-    const uint64_t per = (n + nchunk - 1) / nchunk;
+    const int nchunk = (NB == 1 && h_scalars && n >= (1u << 16)) ? 8 : 1;
+    const uint64_t per = (nbatch + nchunk - 1) / nchunk;
     if (h_scalars && nchunk > 1) {
-      // the copy stream must not overwrite the staging buffer while an earlier call still reads it
       H2B_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], st));
       H2B_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
     }
+    if (NB > 1) H2B_CUDA(ctx, cudaStreamWaitEvent(st, ctx->copy_ev[batch], 0));
     for (int ci = 0; ci < nchunk; ++ci) {
-      const uint64_t i0 = (uint64_t)ci * per, i1 = std::min<uint64_t>(n, i0 + per);
+      const uint64_t i0 = b0 + (uint64_t)ci * per, i1 = std::min<uint64_t>(b1, i0 + per);
       if (i0 >= i1) break;
-      if (h_scalars) {
+      if (h_scalars && NB == 1) {
         Fr* dst = const_cast<Fr*>(d_scalars) + i0;
         if (nchunk == 1) {
           H2B_TRY(copy_h2d_any(ctx, dst, h_scalars + i0, (i1 - i0) * sizeof(Fr), st));
@@ -799,41 +865,39 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
       }
       const uint64_t want = (i1 - i0 + 255) / 256;
       H2B_TRY(launch(ctx, msm_digits_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0,
-                     d_scalars, (uint64_t)n, p.c, p.W, ws->keys_in, ws->vals_in, (uint64_t)table_stride, i0, i1));
+                     d_scalars, (uint64_t)nbatch, p.c, p.W, ws->keys_in, ws->vals_in, (uint64_t)table_stride, i0, i1, b0));
     }
   }
   // 2. sort
 #ifdef H2B_EMU
   {
-    std::vector<std::pair<uint32_t, uint32_t>> v(p.pairs);
-    for (uint64_t i = 0; i < p.pairs; ++i) v[i] = {ws->keys_in[i], ws->vals_in[i]};
+    std::vector<std::pair<uint32_t, uint32_t>> v(pairs);
+    for (uint64_t i = 0; i < pairs; ++i) v[i] = {ws->keys_in[i], ws->vals_in[i]};
     std::stable_sort(v.begin(), v.end(),
                      [](const std::pair<uint32_t, uint32_t>& a,
                         const std::pair<uint32_t, uint32_t>& b) { return a.first < b.first; });
-    for (uint64_t i = 0; i < p.pairs; ++i) {
+    for (uint64_t i = 0; i < pairs; ++i) {
       ws->keys_out[i] = v[i].first;
       ws->vals_out[i] = v[i].second;
     }
   }
 #else
   H2B_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ws->cub_temp, ws->cub_temp_bytes, ws->keys_in,
-                                                ws->keys_out, ws->vals_in, ws->vals_out, p.pairs,
+                                                ws->keys_out, ws->vals_in, ws->vals_out, pairs,
                                                 0, (int)p.kb + 1, st));
   ctx->launches += 1 + (p.kb + 1 + 7) / 8;  // onesweep: histogram + one pass per 8 key bits
 #endif
   H2B_TRY(launch(ctx, msm_find_valid_kernel, dim3(1), dim3(32), 0, (const uint32_t*)ws->keys_out,
-                 (uint64_t)p.pairs, p.kb, ws->n_level));
-  H2B_CUDA(ctx, cudaMemsetAsync(ws->buckets, 0,
-                                (size_t)p.Wb * p.nb_per_window * sizeof(G1Xyzz), st));
+                 (uint64_t)pairs, p.kb, ws->n_level));
 
   // 3. bucket accumulation: batched affine on a window table, else level-wise XYZZ chunks
   // (the batched-affine path is correct but not yet faster than the XYZZ chunks: opt-in)
   bool affine = false;
-  if (const char* e = getenv("H2B_MSM_ACC")) affine = table_stride != 0 && strcmp(e, "affine") == 0;
+  if (const char* e = getenv("H2B_MSM_ACC")) affine = table_stride != 0 && NB == 1 && strcmp(e, "affine") == 0;
   if (affine) {
     H2B_TRY(accumulate_affine(ctx, ws, p, d_bases));
   } else {
-    uint64_t nmax = p.pairs;
+    uint64_t nmax = pairs;
     const uint32_t* keys = ws->keys_out;
     for (int level = 0; level < kMaxLevels; ++level) {
       const uint32_t L = level == 0 ? p.L0 : p.LN;
@@ -854,12 +918,12 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
         cudaStream_t bulk = ctx->bulk_stream;
         H2B_CUDA(ctx, cudaEventRecord(ctx->bulk_ev[0], st));
         H2B_CUDA(ctx, cudaStreamWaitEvent(bulk, ctx->bulk_ev[0], 0));
-        if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], bulk));
+        if (ctx->profile && batch == 0) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[0], bulk));
         H2B_TRY(launch_on(ctx, bulk, msm_accum0_kernel, dim3((nchunks + 127) / 128), dim3(128), 0, src, keys,
                           (const uint32_t*)(ws->n_level + level), L, (const uint32_t*)ws->cnt,
                           (const uint32_t*)ws->incl, nchunks, ws->n_level + level + 1, ws->lkeys[o],
-                          ws->lpts[o], ws->buckets));
-        if (ctx->profile) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[1], bulk));
+                          ws->lpts[o], target));
+        if (ctx->profile && batch == 0) H2B_CUDA(ctx, cudaEventRecord(ctx->ev[1], bulk));
         H2B_CUDA(ctx, cudaEventRecord(ctx->bulk_ev[1], bulk));
         H2B_CUDA(ctx, cudaStreamWaitEvent(st, ctx->bulk_ev[1], 0));
       } else {
@@ -867,7 +931,7 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
         H2B_TRY(launch(ctx, msm_accumN_kernel, dim3((nchunks + 127) / 128), dim3(128), 0, src, keys,
                        (const uint32_t*)(ws->n_level + level), L, (const uint32_t*)ws->cnt,
                        (const uint32_t*)ws->incl, nchunks, ws->n_level + level + 1, ws->lkeys[o],
-                       ws->lpts[o], ws->buckets));
+                       ws->lpts[o], target));
       }
       if (nmax <= L) break;  // a single chunk cuts no run
       nmax = 2ull * nchunks;
@@ -875,6 +939,11 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
       if (level + 1 == kMaxLevels) return fail(ctx, H2B_ERR_ARG, "MSM level overflow");
     }
   }
+  if (batch > 0)
+    H2B_TRY(launch(ctx, msm_bucket_merge_kernel, dim3((nbuckets_all + 127) / 128), dim3(128), 0, ws->buckets,
+                   (const G1Xyzz*)ws->buckets2, nbuckets_all));
+  if (NB > 1) H2B_TRY(queue_copy(batch + 1));
+  }  // batches
 
   // 4. bucket reduction
   {

@@ -154,6 +154,14 @@ def test_msm_vs_oracle(emu_ctx, oracle_c, n, kind, monkeypatch):
             monkeypatch.setenv("H2B_MSM_ACC", "affine" if c else "xyzz")
             assert B.msm(S) == got
             assert B.msm(S[:1100], offset=200) == H.g1_dec(oracle_c.best_multiexp(S[:1100], bases[200:1300], 2))[0]
+        # host scalars in batches that share the bucket array (copy of batch b + 1 under the compute of batch b;
+        # later batches ADD to the buckets): 2 batches, then 4, then ragged
+        monkeypatch.setenv("H2B_MSM_ACC", "xyzz")
+        for batch_min in (700, 300, 375):
+            monkeypatch.setenv("H2B_MSM_BATCH_MIN", str(batch_min))
+            assert B.msm(S) == got, batch_min
+            assert B.msm(S[:1101], offset=200) == H.g1_dec(oracle_c.best_multiexp(S[:1101], bases[200:1301], 2))[0]
+        monkeypatch.delenv("H2B_MSM_BATCH_MIN")
     B.free()
 
 

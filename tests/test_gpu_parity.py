@@ -675,3 +675,25 @@ def test_pageable_host_slices(gpu_ctx, oracle_c):
     pinned.array[:] = sc
     assert bases.msm(sc) == bases.msm(pinned.array)
     bases.free()
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 4])
+def test_msm_host_scalars_in_batches(gpu_ctx, kind, monkeypatch):
+    """Host scalars on a window table are processed in batches that share the bucket array (the copy of batch
+    b + 1 runs under the compute of batch b, later batches add to the buckets): same point as the one-batch
+    device-resident MSM, for uniform / all-equal / 0-1 / sparse scalars, at sizes that give 2 and 4 batches
+    (the batch size is lowered from its default of 2^22 points to keep the test small)."""
+    monkeypatch.setenv("H2B_MSM_BATCH_MIN", str(1 << 20))
+    for n in ((1 << 21) + 3, (1 << 22) + 77):
+        bases = gpu_ctx.synth_bases(n, 0x99 + kind)
+        bases.precompute()
+        dev = gpu_ctx.synth_scalars(n, 41 + kind, kind)
+        want = bases.msm(dev, n)
+        host = dev.download(n)           # pageable numpy array
+        assert bases.msm(host) == want, (n, kind)
+        pinned = gpu_ctx.pinned((n, 4))
+        pinned.array[:] = host
+        assert bases.msm(pinned.array) == want, (n, kind)
+        pinned.free()
+        dev.free()
+        bases.free()
