@@ -206,21 +206,24 @@ class ShardedBases:
                 if col.shape[0]:
                     b.upload(col)
             return
+        self.ctx.sync()  # padding / blinding rows are in place before anything is gathered
+        dev = _group_device(self.group)
+        pending = []
         for b, col in zip(bufs, cols):
             lo, hi = self.start, min(self.end, col.shape[0])
             if hi > lo:
-                b.upload(col[lo:hi], lo * 32)
-        self.ctx.sync()
-        dev = _group_device(self.group)
-        for b in bufs:
+                b.upload(col[lo:hi], lo * 32)  # complete on return
             full = _as_tensor(b, self.n * 4, dev)
             mine = full[self.start * 4:(self.start + per) * 4]
             if dev.type == "cuda":
-                dist.all_gather_into_tensor(full, mine, group=self.group)  # in place: `mine` is its own slot of `full`
+                # in place (`mine` is its own slot of `full`), asynchronous: it runs under the next column's copy
+                pending.append(dist.all_gather_into_tensor(full, mine, group=self.group, async_op=True))
             else:
                 out = torch.empty_like(full)
                 dist.all_gather_into_tensor(out, mine.clone(), group=self.group)
                 full.copy_(out)
+        for w in pending:
+            w.wait()
         if dev.type == "cuda":
             torch.cuda.current_stream().synchronize()
 
