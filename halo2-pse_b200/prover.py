@@ -192,7 +192,7 @@ def _fmt_expr(e: Expression) -> str:
 def pinned_debug(cs: ConstraintSystem, k: int, extended_k: int, omega: int, fixed_commitments, perm_commitments,
                  base_modulus: int = Q_MOD, scalar_modulus: int = R_MOD) -> str:
     """format!("{:?}", vk.pinned()) (plonk.rs:192-203, circuit.rs:1399-1448): the string whose Blake2b hash
-    seeds every transcript.  tests/test_oracle.py checks it, character for character, against the reference's
+    seeds every transcript.  The CPU test-suite checks it, character for character, against the reference's
     golden verifying key of tests/plonk_api.rs (the moduli are parameters only for that test: it is over Vesta)."""
     lst = lambda items: "[" + ", ".join(items) + "]"  # noqa: E731
     col = lambda c: "Column { index: %d, column_type: %s }" % (c.index, _TYPE_NAME[c.column_type])  # noqa: E731
