@@ -354,6 +354,11 @@ def gpu_create_proof(ctx, h, world=1, barrier=None, max_over_ranks=None):
     pk = h.keygen(params, cs, fixed, copies)
     ctx.sync()
     t_keygen = time.perf_counter() - t0
+    # the circuit description holds millions of Python objects (2^20 copy constraints as tuples): park them in the
+    # permanent generation so that a generational collection inside the timed region does not walk them
+    import gc
+    gc.collect()
+    gc.freeze()
     best = None
     digest = None
     for rep in range(4):

@@ -63,6 +63,7 @@ SYMBOLS = {
     "h2b_bases_device_ptr": (_P, [_P]),
     "h2b_msm": (_I, [_P, _P, _SZ, _P, _I, _SZ, _P]),
     "h2b_msm_affine": (_I, [_P, _P, _SZ, _P, _I, _SZ, _P]),
+    "h2b_msm_multi_affine": (_I, [_P, _P, _SZ, _P, _U32, _SZ, _P]),
     "h2b_best_multiexp": (_I, [_P, _P, _P, _SZ, _P]),
     "h2b_msm_window_bits": (_U32, [_SZ]),
     "h2b_g1_mul_generator": (_I, [_P, _P, _I, _SZ, _P, _I]),

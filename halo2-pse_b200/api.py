@@ -417,7 +417,7 @@ def msm_many_mixed_raw(jobs: Sequence[tuple], concurrent: bool = True, pre: Opti
     device; pre[i](ctx), if given, runs right before job i on the context that will compute it (the upload of
     a witness column: copies of later columns then overlap the commitments of earlier ones).
     With more than one job they are dealt round-robin to the first base set's context and its siblings (one
-    host thread and one stream each, H2B_COMMIT_WAYS of them, default 3), so that the latency-bound tail of
+    host thread and one stream each, H2B_COMMIT_WAYS of them, default 2), so that the latency-bound tail of
     one MSM (bucket reduction, short sort passes) runs under the throughput-bound accumulation of the
     others -- the reference's rayon par_iter around (not inside) its commits
     (poly/kzg/multiopen/shplonk/prover.rs:179-196)."""
@@ -425,7 +425,13 @@ def msm_many_mixed_raw(jobs: Sequence[tuple], concurrent: bool = True, pre: Opti
         return []
     jobs = [tuple(j) + (None, 0, 0)[len(j) - 2:] for j in jobs]
     main = jobs[0][0].ctx
-    ways = min(len(jobs), max(1, int(os.environ.get("H2B_COMMIT_WAYS", "3"))))
+    b0, _, n0, off0, _ = jobs[0]
+    if (len(jobs) > 1 and concurrent and not os.environ.get("H2B_MSM_NO_MULTI") and b0.table_window_bits
+            and all(j[0] is b0 and isinstance(j[1], DeviceBuffer) and j[2] == n0 and j[3] == off0 for j in jobs)
+            and (pre is None or all(f is None for f in pre))):
+        # the same base slice under every job, device-resident scalars: ONE multi-column MSM
+        return b0.msm_multi_raw(main, [(j[1], j[4]) for j in jobs], n0, off0)
+    ways = min(len(jobs), max(1, int(os.environ.get("H2B_COMMIT_WAYS", "2"))))
     if ways < 2 or not concurrent:
         outs = []
         for i, j in enumerate(jobs):
@@ -510,6 +516,17 @@ class Bases:
         out = np.zeros(8, dtype=np.uint64)
         ctx._check(ctx.lib.h2b_msm_affine(ctx.h, self.h, offset, sp, loc, n, _ptr(out)))
         return out
+
+    def msm_multi_raw(self, ctx: "Context", cols: Sequence[tuple], n: int, offset: int = 0) -> List[np.ndarray]:
+        """cols[j] = (DeviceBuffer, scalar_offset): the commitments of all columns to bases[offset..offset + n] in one
+        pass (h2b_msm_multi_affine: shared digit / sort / accumulate / reduce pipeline, one bucket set per column)."""
+        for buf, so in cols:
+            if (so + n) * 32 > buf.nbytes:
+                raise H2BError(_ffi.H2B_ERR_LENGTH, "scalar slice outside the buffer")
+        ptrs = (C.c_void_p * len(cols))(*[buf.ptr.value + so * 32 for buf, so in cols])
+        out = np.zeros((len(cols), 8), dtype=np.uint64)
+        ctx._check(ctx.lib.h2b_msm_multi_affine(ctx.h, self.h, offset, ptrs, len(cols), n, _ptr(out)))
+        return [out[j].copy() for j in range(len(cols))]
 
     def msm_many_raw(self, jobs: Sequence[tuple], concurrent: bool = True, pre: Optional[Sequence] = None) -> List[np.ndarray]:
         """Independent commitments on this base set: jobs[i] = (scalars, n, offset, scalar_offset); see

@@ -215,8 +215,12 @@ void ntt_free_tables(h2b_ctx* ctx);
 // table_stride  > 0: `d_points` is a window table (w * table_stride + i), all windows share one bucket set.
 // h_scalars != nullptr: the scalars still live on the host; they are copied into d_scalars in chunks
 // on the copy stream while the digit kernel consumes the chunks already there.
+// ncols > 1 (window table, device scalars only): col_scalars[j] (HOST array of device pointers) are ncols
+// scalar vectors over the same bases; one digit/sort/accumulate/reduce pipeline with one bucket set per
+// column, out_host[0..ncols) receives the ncols sums.
 int msm_run(h2b_ctx* ctx, const G1Affine* d_points, const Fr* d_scalars, size_t n, G1Xyzz* out_host,
-            size_t table_stride = 0, uint32_t table_c = 0, const Fr* h_scalars = nullptr);
+            size_t table_stride = 0, uint32_t table_c = 0, const Fr* h_scalars = nullptr, uint32_t ncols = 1,
+            const Fr* const* col_scalars = nullptr);
 void msm_ws_free(h2b_ctx* ctx);
 
 }  // namespace h2b

@@ -108,7 +108,7 @@ void msm_ws_free(h2b_ctx* ctx) {
 // (row_stride = n, row_base = 0 for a whole MSM; a batch of scalars gets its own compact pair array).
 __global__ void msm_digits_kernel(const Fr* scalars, uint64_t row_stride, uint32_t c, uint32_t W,
                                   uint32_t* keys, uint32_t* vals, uint64_t table_stride, uint64_t i0,
-                                  uint64_t i1, uint64_t row_base) {
+                                  uint64_t i1, uint64_t row_base, uint32_t key_base) {
   for (uint64_t i = i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1;
        i += (uint64_t)gridDim.x * blockDim.x) {
     const Fr s = from_mont(ld_fp(scalars + i));  // to_repr(), arithmetic.rs:14
@@ -134,7 +134,7 @@ __global__ void msm_digits_kernel(const Fr* scalars, uint64_t row_stride, uint32
       }
       const uint64_t slot = (uint64_t)w * row_stride + (i - row_base);
       if (table_stride) {
-        keys[slot] = d ? d - 1 : 0xffffffffu;
+        keys[slot] = d ? key_base + d - 1 : 0xffffffffu;  // key_base: the bucket set of this column (multi-column MSM)
         vals[slot] = (uint32_t)(w * table_stride + i) | (negf << 31);
       } else {
         keys[slot] = d ? w * half + d - 1 : 0xffffffffu;
@@ -572,7 +572,7 @@ struct MsmPlan {
   uint32_t nb_per_window, nseg;
 };
 
-static MsmPlan msm_plan(size_t n, uint32_t table_c = 0) {
+static MsmPlan msm_plan(size_t n, uint32_t table_c = 0, uint32_t ncols = 1) {
   MsmPlan p;
   const uint32_t k = ceil_log2(n < 2 ? 2 : n);
   int c = (int)k - 4;
@@ -585,10 +585,10 @@ static MsmPlan msm_plan(size_t n, uint32_t table_c = 0) {
   if (table_c) c = (int)table_c;
   p.c = (uint32_t)c;
   p.W = (255 + p.c - 1) / p.c;
-  p.Wb = table_c ? 1 : p.W;
+  p.Wb = table_c ? ncols : p.W;  // one bucket set per column of a multi-column MSM on a window table
   p.nb_per_window = 1u << (p.c - 1);
   p.kb = ceil_log2((uint64_t)p.Wb * p.nb_per_window);
-  p.pairs = (uint64_t)n * p.W;
+  p.pairs = (uint64_t)n * p.W * (table_c ? ncols : 1);
   // chunk length of level 0: long enough to amortise the two boundary partials, short enough to
   // keep >= ~64k threads in flight (tuned on B200: k = 16 / 18 / 20 / 24)
   p.L0 = p.pairs >= (1ull << 25) ? 128 : p.pairs >= (1ull << 23) ? 48 : p.pairs >= (1ull << 21) ? 32 : 16;
@@ -617,19 +617,27 @@ static MsmPlan msm_plan(size_t n, uint32_t table_c = 0) {
 static int ws_ensure(h2b_ctx* ctx, const MsmPlan& p) {
   if (!ctx->msm_ws) ctx->msm_ws = new MsmWorkspace();
   MsmWorkspace* ws = ctx->msm_ws;
-  const size_t chunks0 = (size_t)((p.pairs + p.L0 - 1) / p.L0);
-  const size_t list = 2 * chunks0 + 16;
-  const size_t nbuckets = (size_t)p.Wb * p.nb_per_window;
-  const size_t nsegs = (size_t)p.Wb * p.nseg;
-  if (p.pairs <= ws->cap_pairs && chunks0 <= ws->cap_chunks && list <= ws->cap_list &&
+  size_t chunks0 = (size_t)((p.pairs + p.L0 - 1) / p.L0);
+  size_t list = 2 * chunks0 + 16;
+  size_t nbuckets = (size_t)p.Wb * p.nb_per_window;
+  size_t nsegs = (size_t)p.Wb * p.nseg;
+  size_t pairs = (size_t)p.pairs;
+  if (pairs <= ws->cap_pairs && chunks0 <= ws->cap_chunks && list <= ws->cap_list &&
       nbuckets <= ws->cap_buckets && nsegs <= ws->cap_seg)
     return H2B_OK;
+  // grow-only in EVERY dimension: plans of different shapes (one column, several columns, other chunk lengths)
+  // alternate inside one proof and must not evict each other
+  pairs = std::max(pairs, ws->cap_pairs);
+  chunks0 = std::max(chunks0, ws->cap_chunks);
+  list = std::max(list, ws->cap_list);
+  nbuckets = std::max(nbuckets, ws->cap_buckets);
+  nsegs = std::max(nsegs, ws->cap_seg);
   H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ws_release(ws);
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->keys_in, p.pairs * 4 + 64));
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->keys_out, p.pairs * 4 + 64));
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->vals_in, p.pairs * 4 + 64));
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->vals_out, p.pairs * 4 + 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->keys_in, pairs * 4 + 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->keys_out, pairs * 4 + 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->vals_in, pairs * 4 + 64));
+  H2B_CUDA(ctx, cudaMalloc((void**)&ws->vals_out, pairs * 4 + 64));
   H2B_CUDA(ctx, cudaMalloc((void**)&ws->cnt, chunks0 * 4 + 64));
   H2B_CUDA(ctx, cudaMalloc((void**)&ws->incl, chunks0 * 4 + 64));
   H2B_CUDA(ctx, cudaMalloc((void**)&ws->n_level, (kMaxLevels + 2) * 4));
@@ -643,13 +651,13 @@ static int ws_ensure(h2b_ctx* ctx, const MsmPlan& p) {
 #ifndef H2B_EMU
   size_t t1 = 0, t2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, t1, ws->keys_in, ws->keys_out, ws->vals_in,
-                                  ws->vals_out, p.pairs, 0, 32, ctx->stream);  // worst case: any key width
+                                  ws->vals_out, pairs, 0, 32, ctx->stream);  // worst case: any key width
   cub::DeviceScan::InclusiveSum(nullptr, t2, ws->cnt, ws->incl,
-                                (int)std::max<size_t>(chunks0, (size_t)(p.pairs / 2) + 2), ctx->stream);
+                                (int)std::max<size_t>(chunks0, (size_t)(pairs / 2) + 2), ctx->stream);
   ws->cub_temp_bytes = std::max(t1, t2) + 256;
   H2B_CUDA(ctx, cudaMalloc(&ws->cub_temp, ws->cub_temp_bytes));
 #endif
-  ws->cap_pairs = p.pairs;
+  ws->cap_pairs = pairs;
   ws->cap_chunks = chunks0;
   ws->cap_list = list;
   ws->cap_buckets = nbuckets;
@@ -783,11 +791,16 @@ static int accumulate_affine(h2b_ctx* ctx, MsmWorkspace* ws, const MsmPlan& p, c
 }
 
 int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n,
-            G1Xyzz* out_host, size_t table_stride, uint32_t table_c, const Fr* h_scalars) {
-  *out_host = G1Xyzz::identity();
+            G1Xyzz* out_host, size_t table_stride, uint32_t table_c, const Fr* h_scalars,
+            uint32_t ncols, const Fr* const* col_scalars) {
+  for (uint32_t j = 0; j < (ncols ? ncols : 1); ++j) out_host[j] = G1Xyzz::identity();
   if (n == 0) return H2B_OK;
   if (n >= (1ull << 31)) return fail(ctx, H2B_ERR_ARG, "MSM larger than 2^31 points");
-  const MsmPlan p = msm_plan(n, table_stride ? table_c : 0);
+  if (ncols > 1 && (!table_stride || h_scalars || !col_scalars))
+    return fail(ctx, H2B_ERR_ARG, "multi-column MSM needs a window table and device scalars");
+  if (ncols < 1) ncols = 1;
+  const MsmPlan p = msm_plan(n, table_stride ? table_c : 0, ncols);
+  if (p.pairs >= (1ull << 32) || p.Wb > 64) return fail(ctx, H2B_ERR_ARG, "multi-column MSM too large");
   if (table_stride && (uint64_t)p.W * table_stride >= (1ull << 31))
     return fail(ctx, H2B_ERR_ARG, "window table larger than 2^31 points");
   H2B_TRY(ws_ensure(ctx, p));
@@ -802,7 +815,7 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   // (B200, PCIe 5: k = 24 49.2 -> 45.9 ms with 4 batches; neutral at k = 23, a loss below: smaller sorts)
   uint64_t batch_min = 1ull << 22;  // points per batch; H2B_MSM_BATCH_MIN overrides (tests), 0 disables
   if (const char* e = getenv("H2B_MSM_BATCH_MIN")) batch_min = strtoull(e, nullptr, 10);
-  const int NB = (h_scalars && table_stride && batch_min) ? (n >= 4 * batch_min ? 4 : n >= 2 * batch_min ? 2 : 1) : 1;
+  const int NB = (h_scalars && table_stride && batch_min && ncols == 1) ? (n >= 4 * batch_min ? 4 : n >= 2 * batch_min ? 2 : 1) : 1;
   const uint64_t per_batch = (n + NB - 1) / NB;
   H2B_CUDA(ctx, cudaMemsetAsync(ws->buckets, 0, (size_t)p.Wb * p.nb_per_window * sizeof(G1Xyzz), st));
   // copy of batch b on the copy stream, event copy_ev[b]; queued right after the compute of batch b - 1, so
@@ -864,8 +877,12 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
         }
       }
       const uint64_t want = (i1 - i0 + 255) / 256;
-      H2B_TRY(launch(ctx, msm_digits_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0,
-                     d_scalars, (uint64_t)nbatch, p.c, p.W, ws->keys_in, ws->vals_in, (uint64_t)table_stride, i0, i1, b0));
+      for (uint32_t col = 0; col < ncols; ++col) {  // column `col` of a multi-column MSM: its own pair rows and bucket set
+        const uint64_t off = (uint64_t)col * p.W * nbatch;
+        H2B_TRY(launch(ctx, msm_digits_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0,
+                       ncols > 1 ? col_scalars[col] : d_scalars, (uint64_t)nbatch, p.c, p.W, ws->keys_in + off,
+                       ws->vals_in + off, (uint64_t)table_stride, i0, i1, b0, col * p.nb_per_window));
+      }
     }
   }
   // 2. sort
@@ -972,6 +989,7 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   G1Xyzz acc = G1Xyzz::identity();
   if (table_stride) {
     acc = ws->h_out[0];  // the table already carries the 2^(c*w) factors
+    for (uint32_t j = 1; j < ncols; ++j) out_host[j] = ws->h_out[j];
   } else {
     for (int w = (int)p.W - 1; w >= 0; --w) {
       for (uint32_t i = 0; i < p.c; ++i) acc = xyzz_double(acc);
@@ -1249,6 +1267,40 @@ extern "C" int h2b_msm(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
   G1Xyzz acc;
   H2B_TRY(msm_common(ctx, bases, base_offset, scalars, loc, n, &acc));
   xyzz_to_jacobian(acc, out);
+  return H2B_OK;
+}
+
+extern "C" int h2b_msm_multi_affine(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
+                                    const h2b_fr* const* scalars_dev, uint32_t ncols, size_t n,
+                                    h2b_g1_affine* out_affine) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (ncols == 0) return H2B_OK;
+  if (!out_affine || !scalars_dev) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (!bases || bases->ctx->device != ctx->device) return fail(ctx, H2B_ERR_ARG, "bases live on another device");
+  for (uint32_t j = 0; j < ncols; ++j)
+    if (!scalars_dev[j] && n) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (base_offset > bases->n || n > bases->n - base_offset)
+    return fail(ctx, H2B_ERR_LENGTH, "more scalars than bases");  // kzg/commitment.rs:290,332
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t W = bases->pre_c ? (255 + bases->pre_c - 1) / bases->pre_c : 0;
+  const bool fused = bases->d_table && n >= 1024 && ncols > 1 && ncols <= 64 &&
+                     (uint64_t)n * W * ncols < (1ull << 32) && !getenv("H2B_MSM_NO_MULTI");
+  G1Xyzz acc[64];
+  if (fused) {
+    H2B_TRY(msm_run(ctx, bases->d_table + base_offset, nullptr, n, acc, bases->n, bases->pre_c, nullptr, ncols,
+                    reinterpret_cast<const Fr* const*>(scalars_dev)));
+    for (uint32_t j = 0; j < ncols; ++j) {
+      const G1Affine a = xyzz_to_affine(acc[j]);
+      memcpy(out_affine + j, &a, sizeof a);
+    }
+    return H2B_OK;
+  }
+  for (uint32_t j = 0; j < ncols; ++j) {  // no window table (or too small / too large): one MSM per column
+    H2B_TRY(msm_common(ctx, bases, base_offset, scalars_dev[j], H2B_DEVICE, n, &acc[0]));
+    const G1Affine a = xyzz_to_affine(acc[0]);
+    memcpy(out_affine + j, &a, sizeof a);
+  }
   return H2B_OK;
 }
 

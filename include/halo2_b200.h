@@ -86,6 +86,15 @@ int h2b_msm(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset, const h2b_
 /* Same result, normalised: out_affine = to_affine(sum) ((0,0) for identity). */
 int h2b_msm_affine(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
                    const h2b_fr* scalars, int loc, size_t n, h2b_g1_affine* out_affine);
+/* `ncols` commitments on the same base slice in ONE pass: out_affine[j] = best_multiexp(scalars_dev[j][..n],
+ * &bases[offset..offset+n]).  scalars_dev is a host array of DEVICE pointers.  With a window table the columns
+ * share the digit / sort / accumulate / reduce pipeline (one bucket set per column), which amortises its
+ * latency-bound stages: the commitments no challenge separates -- the advice columns of a phase
+ * (plonk/prover.rs:375-392), the pieces of h (plonk/vanishing/prover.rs:100-113), the witness polynomials of a
+ * multi-opening (poly/kzg/multiopen/gwc/prover.rs:80-88).  Same points as ncols calls of h2b_msm_affine. */
+int h2b_msm_multi_affine(h2b_ctx* ctx, const h2b_bases* bases, size_t base_offset,
+                         const h2b_fr* const* scalars_dev, uint32_t ncols, size_t n,
+                         h2b_g1_affine* out_affine);
 /* One-shot drop-in with the exact shape of best_multiexp (host slices).  arithmetic.rs:132 */
 int h2b_best_multiexp(h2b_ctx* ctx, const h2b_fr* coeffs, const h2b_g1_affine* bases, size_t n,
                       h2b_g1* out);

@@ -154,6 +154,17 @@ def test_msm_vs_oracle(emu_ctx, oracle_c, n, kind, monkeypatch):
             monkeypatch.setenv("H2B_MSM_ACC", "affine" if c else "xyzz")
             assert B.msm(S) == got
             assert B.msm(S[:1100], offset=200) == H.g1_dec(oracle_c.best_multiexp(S[:1100], bases[200:1300], 2))[0]
+        # several columns over the same base slice in ONE pass (h2b_msm_multi_affine: one bucket set per column)
+        cols = [S, S[::-1].copy(), np.zeros_like(S), H.fr_enc([1] * n)]
+        dev = [emu_ctx.upload_fr(cc) for cc in cols]
+        want_cols = [B.msm(cc) for cc in cols]
+        assert B.msm_many([(d, n) for d in dev]) == want_cols
+        assert B.msm_many([(d, 1100, 200, 7) for d in dev]) == [B.msm(cc[7:1107], offset=200) for cc in cols]
+        monkeypatch.setenv("H2B_MSM_NO_MULTI", "1")   # the same jobs dealt to sibling contexts instead
+        assert B.msm_many([(d, n) for d in dev]) == want_cols
+        monkeypatch.delenv("H2B_MSM_NO_MULTI")
+        for d in dev:
+            d.free()
         # host scalars in batches that share the bucket array (copy of batch b + 1 under the compute of batch b;
         # later batches ADD to the buckets): 2 batches, then 4, then ragged
         monkeypatch.setenv("H2B_MSM_ACC", "xyzz")

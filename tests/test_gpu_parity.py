@@ -697,3 +697,26 @@ def test_msm_host_scalars_in_batches(gpu_ctx, kind, monkeypatch):
         pinned.free()
         dev.free()
         bases.free()
+
+
+@pytest.mark.parametrize("k,ncols", [(12, 2), (16, 5), (20, 4)])
+def test_msm_multi_column(gpu_ctx, k, ncols, monkeypatch):
+    """h2b_msm_multi_affine: several scalar vectors over the same resident bases in one digit / sort / accumulate /
+    reduce pass (one bucket set per column) give the points of separate MSMs -- uniform, all-equal, 0/1, sparse
+    and all-zero columns side by side, full length and a shorter prefix at an offset."""
+    n = (1 << k) + 9
+    bases = gpu_ctx.synth_bases(n, 0x55 + k)
+    bases.precompute()
+    kinds = [0, 1, 2, 4, 0][:ncols]
+    cols = [gpu_ctx.synth_scalars(n, 70 + j, kind) for j, kind in enumerate(kinds)]
+    gpu_ctx.memset(cols[-1], 0)  # an all-zero column: the identity
+    want = [bases.msm(c, n) for c in cols]
+    assert want[-1] is None
+    assert bases.msm_many([(c, n) for c in cols]) == want
+    m = n - 300
+    assert bases.msm_many([(c, m, 100, 50) for c in cols]) == [bases.msm(c, m, offset=100, scalar_offset=50) for c in cols]
+    monkeypatch.setenv("H2B_MSM_NO_MULTI", "1")  # sibling contexts instead of the fused pass
+    assert bases.msm_many([(c, n) for c in cols]) == want
+    for c in cols:
+        c.free()
+    bases.free()
