@@ -151,7 +151,8 @@ static int copy_staged(h2b_ctx* ctx, void* dst, const void* src, size_t bytes, c
   const size_t kCopyChunk = copy_chunk();
   const size_t nchunks = (bytes + kCopyChunk - 1) / kCopyChunk;
   // few threads for small copies (wake-ups cost more than they carry), all of them from ~64 MiB on
-  const int T = (int)std::min<size_t>((size_t)copy_threads(), std::max<size_t>(2, nchunks / 8));
+  const int T = (int)std::min<size_t>((size_t)copy_threads(),
+                                      nchunks >= 64 ? nchunks : std::min<size_t>(4, std::max<size_t>(2, nchunks / 4)));
   cudaError_t errs[kCopySlots / 2];
   auto work = [&](int t) {
     cudaError_t e = cudaSuccess;

@@ -208,15 +208,35 @@ class ShardedBases:
             return
         self.ctx.sync()  # padding / blinding rows are in place before anything is gathered
         dev = _group_device(self.group)
+        # this rank's rows of every column, the columns side by side on sibling contexts (one host thread, one
+        # stream and one pinned ring each): pageable copies are host-bound, not PCIe-bound
+        import threading
+        errs: list = []
+
+        def put(ctx, b, col):
+            try:
+                lo, hi = self.start, min(self.end, col.shape[0])
+                if hi > lo:
+                    b.upload(col[lo:hi], lo * 32, ctx=ctx)  # complete on return
+            except Exception as e:
+                errs.append(e)
+
+        threads = [threading.Thread(target=put, args=(self.ctx.aux(i - 1), b, col))
+                   for i, (b, col) in enumerate(zip(bufs, cols)) if i > 0]
+        for t in threads:
+            t.start()
+        if bufs:
+            put(self.ctx, bufs[0], cols[0])
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
         pending = []
-        for b, col in zip(bufs, cols):
-            lo, hi = self.start, min(self.end, col.shape[0])
-            if hi > lo:
-                b.upload(col[lo:hi], lo * 32)  # complete on return
+        for b in bufs:
             full = _as_tensor(b, self.n * 4, dev)
             mine = full[self.start * 4:(self.start + per) * 4]
             if dev.type == "cuda":
-                # in place (`mine` is its own slot of `full`), asynchronous: it runs under the next column's copy
+                # in place (`mine` is its own slot of `full`), asynchronous
                 pending.append(dist.all_gather_into_tensor(full, mine, group=self.group, async_op=True))
             else:
                 out = torch.empty_like(full)
