@@ -431,7 +431,10 @@ def msm_many_mixed_raw(jobs: Sequence[tuple], concurrent: bool = True, pre: Opti
             and (pre is None or all(f is None for f in pre))):
         # the same base slice under every job, device-resident scalars: ONE multi-column MSM
         return b0.msm_multi_raw(main, [(j[1], j[4]) for j in jobs], n0, off0)
-    ways = min(len(jobs), max(1, int(os.environ.get("H2B_COMMIT_WAYS", "2"))))
+    # 2 ways by default (more brings nothing once the accumulation kernels saturate the GPU); 3 when the jobs
+    # carry their own host->device copies, which keep a worker off the GPU for a while
+    has_copies = pre is not None and any(f is not None for f in pre)
+    ways = min(len(jobs), max(1, int(os.environ.get("H2B_COMMIT_WAYS", "3" if has_copies else "2"))))
     if ways < 2 or not concurrent:
         outs = []
         for i, j in enumerate(jobs):

@@ -7,6 +7,7 @@
 
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -73,6 +74,13 @@ struct h2b_ctx {
   cudaEvent_t copy_slot_ev[16] = {nullptr};
   bool copy_pool_ready = false;
   struct CopyWorkers* copy_workers = nullptr;  // persistent host threads of the staged copies (ctx.cu)
+  // h2b_device_alloc / h2b_device_free: sizes of the live blocks and a per-size cache of released ones.  A prover
+  // asks for the same few sizes (n and 2^extended_k elements) dozens of times per proof; a released block is
+  // handed to the next request of its size without a trip through the driver's pool (cudaMallocAsync answered
+  // in 1 - 8 ms now and then).  Stream-ordered like cudaMallocAsync: valid for work enqueued on `stream`.
+  std::unordered_map<void*, size_t> block_size;
+  std::unordered_map<size_t, std::vector<void*>> block_cache;
+  size_t block_cache_bytes = 0;
 };
 
 struct h2b_bases {

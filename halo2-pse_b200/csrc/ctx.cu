@@ -497,9 +497,13 @@ extern "C" int h2b_ctx_create(int device, h2b_ctx** out) {
   return H2B_OK;
 }
 
+static void block_cache_flush(h2b_ctx* ctx);
+
 extern "C" void h2b_ctx_destroy(h2b_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  block_cache_flush(ctx);
   cudaStreamSynchronize(ctx->stream);
   msm_ws_free(ctx);
   ntt_free_tables(ctx);
@@ -557,25 +561,51 @@ extern "C" int h2b_ctx_last_ntt_passes(h2b_ctx* ctx, float* ms, int cap) {
 // Caller-visible device buffers come from the device's stream-ordered memory pool on the context's stream:
 // a prover allocates and frees dozens of polynomial-sized buffers per proof, and cudaMalloc / cudaFree would
 // each synchronise the whole device.  Freed blocks stay cached in the pool (release threshold 16 GiB).
+static constexpr size_t kBlockCacheMax = 24ull << 30;  // bytes kept for reuse per context
+
+static void block_cache_flush(h2b_ctx* ctx) {
+  for (auto& kv : ctx->block_cache)
+    for (void* p : kv.second) {
+#ifndef H2B_EMU
+      cudaFreeAsync(p, ctx->stream);
+#else
+      cudaFree(p);
+#endif
+    }
+  ctx->block_cache.clear();
+  ctx->block_cache_bytes = 0;
+}
+
 extern "C" int h2b_device_alloc(h2b_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return H2B_ERR_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (bytes == 0) bytes = 1;
+  auto hit = ctx->block_cache.find(bytes);
+  if (hit != ctx->block_cache.end() && !hit->second.empty()) {
+    *out = hit->second.back();
+    hit->second.pop_back();
+    ctx->block_cache_bytes -= bytes;
+    ctx->block_size[*out] = bytes;
+    return H2B_OK;
+  }
 #ifndef H2B_EMU
-  cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 1, ctx->stream);
+  cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
   if (e == cudaErrorMemoryAllocation) {  // give cached blocks back and retry once
     cudaGetLastError();
+    block_cache_flush(ctx);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
       cudaStreamSynchronize(ctx->stream);
       cudaMemPoolTrimTo(pool, 0);
     }
-    e = cudaMallocAsync(out, bytes ? bytes : 1, ctx->stream);
+    e = cudaMallocAsync(out, bytes, ctx->stream);
   }
   H2B_CUDA(ctx, e);
 #else
-  H2B_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+  H2B_CUDA(ctx, cudaMalloc(out, bytes));
 #endif
+  ctx->block_size[*out] = bytes;
   return H2B_OK;
 }
 
@@ -583,6 +613,16 @@ extern "C" void h2b_device_free(h2b_ctx* ctx, void* p) {
   if (!ctx || !p) return;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
+  auto it = ctx->block_size.find(p);
+  if (it != ctx->block_size.end()) {
+    const size_t bytes = it->second;
+    ctx->block_size.erase(it);
+    if (bytes >= (1u << 16) && ctx->block_cache_bytes + bytes <= kBlockCacheMax) {
+      ctx->block_cache[bytes].push_back(p);  // ordered after every kernel of this context that may still read it
+      ctx->block_cache_bytes += bytes;
+      return;
+    }
+  }
 #ifndef H2B_EMU
   cudaFreeAsync(p, ctx->stream);  // ordered after every kernel of this context that may still read it
 #else
