@@ -326,3 +326,54 @@ def test_pageable_copies_through_the_pinned_ring(emu_ctx, oracle_c, monkeypatch)
     got = a.copy()
     emu_ctx.best_fft(got, w.reshape(1, 4), k)
     assert (got == want).all()
+
+
+def test_device_block_cache(emu_ctx):
+    """h2b_device_alloc / h2b_device_free keep released blocks per size and hand them to the next request of that
+    size (the prover asks for the same sizes dozens of times per proof); other sizes and small blocks go to the
+    allocator as before."""
+    a = emu_ctx.alloc(1 << 20)
+    pa = a.ptr.value
+    a.free()
+    b = emu_ctx.alloc(1 << 20)        # same size: the released block comes back
+    assert b.ptr.value == pa
+    c = emu_ctx.alloc(1 << 20)        # the cache is empty again: a new block
+    assert c.ptr.value != pa
+    d = emu_ctx.alloc((1 << 20) + 32)  # another size never takes a cached block of a different size
+    b.free()
+    e = emu_ctx.alloc((1 << 20) + 32)
+    assert e.ptr.value not in (pa, d.ptr.value)
+    small = emu_ctx.alloc(64)          # below the caching threshold
+    small.upload(np.arange(8, dtype=np.uint64))
+    assert (small.download(2).reshape(-1) == np.arange(8, dtype=np.uint64)).all()
+    for x in (c, d, e, small):
+        x.free()
+    # contents written through a recycled block are what the next kernel reads
+    v = H.rand_fr_limbs(3, 1 << 15)   # 1 MiB
+    f = emu_ctx.alloc(1 << 20)
+    f.upload(v)
+    assert (f.download(1 << 15) == v).all()
+    f.free()
+
+
+def test_msm_many_forms(emu_ctx, oracle_c):
+    """Bases.msm_many: no jobs, one job, jobs of different lengths (dealt to sibling contexts), jobs with their
+    own host->device copies (`pre`), host-array jobs."""
+    n = 1200
+    rng = random.Random(5)
+    bases = oracle_c.g1_mul_gen([rng.randrange(1, 1 << 64) for _ in range(n)])
+    B = h.Bases(emu_ctx, bases, n)
+    B.precompute(9)
+    cols = [H.rand_fr_limbs(40 + j, n) for j in range(3)]
+    want = [B.msm(c) for c in cols]
+    assert B.msm_many([]) == []
+    dev = [emu_ctx.upload_fr(c) for c in cols]
+    assert B.msm_many([(dev[0], n)]) == want[:1]
+    assert B.msm_many([(dev[0], n), (dev[1], 1100), (dev[2], n, 0, 0)]) == [want[0], B.msm(cols[1][:1100]), want[2]]
+    assert B.msm_many([(c,) for c in cols]) == want                       # host arrays
+    empty = [emu_ctx.alloc(n * 32) for _ in cols]                         # filled by the job's own copy
+    pre = [(lambda ctx, b=b, c=c: b.upload(c, ctx=ctx)) for b, c in zip(empty, cols)]
+    assert B.msm_many([(b, n) for b in empty], pre=pre) == want
+    for b in dev + empty:
+        b.free()
+    B.free()
