@@ -8,6 +8,8 @@
 //   halo2_proofs::poly::Polynomial<Basis>, Rotation             halo2_proofs/src/poly.rs:52-72, 229-330
 //   halo2_proofs::poly::EvaluationDomain                        halo2_proofs/src/poly/domain.rs:19-480
 //   halo2_proofs::poly::kzg::ParamsKZG (commit half)            halo2_proofs/src/poly/kzg/commitment.rs:23-131, 281-334
+//   halo2_proofs::transcript::Blake2bWrite (Challenge255)       halo2_proofs/src/transcript.rs:282-514
+//   halo2_proofs::poly::kzg::multiopen::ProverGWC               halo2_proofs/src/poly/kzg/multiopen/gwc/prover.rs:24-92
 //
 // Error behaviour: where the reference panics (assert_eq! on lengths, assert!(bases.len() >= size)),
 // these throw halo2_proofs::Panic with the reference's file:line in the message; a CUDA / allocation
@@ -476,6 +478,178 @@ class ParamsKZG {
   uint64_t n_ = 0;
   std::shared_ptr<h2b_bases> g_, g_lagrange_;
 };
+}  // namespace kzg
+}  // namespace poly
+
+// ---------------------------------------------------------------------------------------------
+// halo2_proofs::transcript -- Blake2bWrite<_, G1Affine, Challenge255<_>>      halo2_proofs/src/transcript.rs:282-514
+// Host-only (hashing is inherently sequential); BLAKE2b per RFC 7693 with the "Halo2-Transcript" personalisation.
+// ---------------------------------------------------------------------------------------------
+namespace transcript {
+class Blake2b {  // digest_size 64, no key, personalisation = 16 bytes
+ public:
+  explicit Blake2b(const char person[16]) {
+    static const uint64_t iv[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
+                                   0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
+    for (int i = 0; i < 8; ++i) h_[i] = iv[i];
+    h_[0] ^= 0x01010000ull ^ 64ull;  // depth 1, fanout 1, digest length 64
+    uint64_t p0, p1;
+    std::memcpy(&p0, person, 8);
+    std::memcpy(&p1, person + 8, 8);
+    h_[6] ^= p0;
+    h_[7] ^= p1;
+  }
+  void update(const void* data, size_t len) {
+    const uint8_t* in = static_cast<const uint8_t*>(data);
+    while (len) {
+      if (fill_ == 128) {  // a full buffer is compressed only when more input follows (the last block is special)
+        t_ += 128;
+        compress(false);
+        fill_ = 0;
+      }
+      const size_t take = len < 128 - fill_ ? len : 128 - fill_;
+      std::memcpy(buf_ + fill_, in, take);
+      fill_ += take, in += take, len -= take;
+    }
+  }
+  void digest(uint8_t out[64]) const {  // of a copy: the state keeps absorbing (hashlib's state.copy().digest())
+    Blake2b c = *this;
+    c.t_ += c.fill_;
+    std::memset(c.buf_ + c.fill_, 0, 128 - c.fill_);
+    c.compress(true);
+    std::memcpy(out, c.h_, 64);
+  }
+
+ private:
+  static uint64_t rotr(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+  void compress(bool last) {
+    static const uint8_t sigma[12][16] = {
+        {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+        {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+        {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+        {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+        {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+        {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}};
+    static const uint64_t iv[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
+                                   0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
+    uint64_t m[16], v[16];
+    std::memcpy(m, buf_, 128);
+    for (int i = 0; i < 8; ++i) v[i] = h_[i], v[i + 8] = iv[i];
+    v[12] ^= t_;  // messages are far below 2^64 bytes: the high counter word stays 0
+    if (last) v[14] = ~v[14];
+    auto G = [&](int a, int b, int c, int d, uint64_t x, uint64_t y) {
+      v[a] = v[a] + v[b] + x, v[d] = rotr(v[d] ^ v[a], 32), v[c] = v[c] + v[d], v[b] = rotr(v[b] ^ v[c], 24);
+      v[a] = v[a] + v[b] + y, v[d] = rotr(v[d] ^ v[a], 16), v[c] = v[c] + v[d], v[b] = rotr(v[b] ^ v[c], 63);
+    };
+    for (int r = 0; r < 12; ++r) {
+      const uint8_t* s = sigma[r];
+      G(0, 4, 8, 12, m[s[0]], m[s[1]]), G(1, 5, 9, 13, m[s[2]], m[s[3]]), G(2, 6, 10, 14, m[s[4]], m[s[5]]), G(3, 7, 11, 15, m[s[6]], m[s[7]]);
+      G(0, 5, 10, 15, m[s[8]], m[s[9]]), G(1, 6, 11, 12, m[s[10]], m[s[11]]), G(2, 7, 8, 13, m[s[12]], m[s[13]]), G(3, 4, 9, 14, m[s[14]], m[s[15]]);
+    }
+    for (int i = 0; i < 8; ++i) h_[i] ^= v[i] ^ v[i + 8];
+  }
+  uint64_t h_[8];
+  uint64_t t_ = 0;
+  uint8_t buf_[128] = {0};
+  size_t fill_ = 0;
+};
+
+/// Fr::from_bytes_wide: the 512-bit little-endian integer mod r (halo2curves 0.3.1)    transcript.rs:501
+inline Fr fr_from_bytes_wide(const uint8_t b[64]) {
+  uint64_t w[8];
+  std::memcpy(w, b, 64);
+  const Fr two256 = Fr::from_raw(0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full);  // 2^256 mod r
+  return Fr::from_raw(w[0], w[1], w[2], w[3]) + Fr::from_raw(w[4], w[5], w[6], w[7]) * two256;
+}
+
+class Blake2bWrite {
+ public:
+  Blake2bWrite() : state_("Halo2-Transcript") {}                                         // transcript.rs:296-303
+  /// squeeze_challenge_scalar through Challenge255                                      :320-332, :486-514
+  Fr squeeze_challenge_scalar() {
+    const uint8_t prefix = 0;  // BLAKE2B_PREFIX_CHALLENGE: stays absorbed
+    state_.update(&prefix, 1);
+    uint8_t d[64];
+    state_.digest(d);
+    return fr_from_bytes_wide(d);
+  }
+  void common_point(const G1Affine& p) {                                                   // :334-347
+    if (p.is_identity()) throw Panic("cannot write points at infinity to the transcript (transcript.rs:338)");
+    const uint8_t prefix = 1;
+    const Fq x = p.x.to_repr_limbs(), y = p.y.to_repr_limbs();
+    state_.update(&prefix, 1), state_.update(x.l, 32), state_.update(y.l, 32);
+  }
+  void common_scalar(const Fr& s) {                                                        // :349-355
+    const uint8_t prefix = 2;
+    const Fr c = s.to_repr_limbs();
+    state_.update(&prefix, 1), state_.update(c.l, 32);
+  }
+  void write_point(const G1Affine& p) {                                                    // :376-383, G1Affine::to_bytes
+    common_point(p);
+    const Fq x = p.x.to_repr_limbs(), y = p.y.to_repr_limbs();
+    uint8_t b[32];
+    std::memcpy(b, x.l, 32);
+    b[31] |= static_cast<uint8_t>((y.l[0] & 1) << 7);
+    writer_.insert(writer_.end(), b, b + 32);
+  }
+  void write_scalar(const Fr& s) {                                                         // :384-390
+    common_scalar(s);
+    const Fr c = s.to_repr_limbs();
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(c.l);
+    writer_.insert(writer_.end(), b, b + 32);
+  }
+  const std::vector<uint8_t>& finalize() const { return writer_; }                        // :407-410
+
+ private:
+  Blake2b state_;
+  std::vector<uint8_t> writer_;
+};
+}  // namespace transcript
+
+// ---------------------------------------------------------------------------------------------
+// halo2_proofs::poly::kzg::multiopen::ProverGWC              halo2_proofs/src/poly/kzg/multiopen/gwc/prover.rs:24-92
+// ---------------------------------------------------------------------------------------------
+namespace poly {
+struct ProverQuery {  // poly/query.rs:10-19 (blind omitted: KZG ignores it)
+  Fr point;
+  const Polynomial<Coeff>* poly;
+};
+namespace kzg {
+namespace multiopen {
+class ProverGWC {
+ public:
+  explicit ProverGWC(const ParamsKZG& params) : params_(params) {}
+  /// create_proof(rng, transcript, queries): one witness commitment per distinct point, in first-occurrence
+  /// order; the evaluations themselves were written by the caller (plonk/prover.rs:548-595)
+  void create_proof(transcript::Blake2bWrite& t, const std::vector<ProverQuery>& queries) const {
+    const Fr v = t.squeeze_challenge_scalar();                                             // :58
+    std::vector<std::pair<Fr, std::vector<const ProverQuery*>>> sets;                      // construct_intermediate_sets, gwc.rs:36-61
+    for (const auto& q : queries) {
+      bool found = false;
+      for (auto& s : sets)
+        if (s.first == q.point) s.second.push_back(&q), found = true;
+      if (!found) sets.push_back({q.point, {&q}});
+    }
+    for (const auto& s : sets) {                                                           // :61-89
+      const Fr& z = s.first;
+      Polynomial<Coeff> poly_batch = *s.second[0]->poly;
+      Fr eval_batch = arithmetic::eval_polynomial(poly_batch.values, z), power = Fr::one();
+      for (size_t i = 1; i < s.second.size(); ++i) {
+        power *= v;
+        poly_batch = poly_batch + (*s.second[i]->poly * power);  // poly_batch * v + poly, unrolled from the back
+        eval_batch += arithmetic::eval_polynomial(s.second[i]->poly->values, z) * power;
+      }
+      if (poly_batch.values.empty()) throw Panic("empty polynomial in a multi-opening");
+      poly_batch.values[0] -= eval_batch;                                                  // &poly_batch - eval_batch, poly.rs:298-305
+      Polynomial<Coeff> witness{arithmetic::kate_division(poly_batch.values, z)};          // :79
+      t.write_point(params_.commit(witness).to_affine());                                  // :80-88
+    }
+  }
+
+ private:
+  const ParamsKZG& params_;
+};
+}  // namespace multiopen
 }  // namespace kzg
 }  // namespace poly
 }  // namespace halo2_proofs

@@ -74,6 +74,40 @@ int main(int argc, char** argv) {
                                params.commit_lagrange(poly::Polynomial<poly::LagrangeCoeff>{v}).to_affine(),
                                params.get_g()[1], params.get_g_lagrange()[0]};
       spit(argv[3], out, sizeof out);
+    } else if (op == "transcript") {  // in: s0, s1 (Fr), p0, p1 (G1Affine); a fixed schedule of absorbs and squeezes
+      const auto sc = take<Fr>(in, 0, 2);
+      const auto pt = take<G1Affine>(in, 64, 2);
+      transcript::Blake2bWrite t;
+      t.common_scalar(sc[0]);
+      t.write_point(pt[0]);
+      t.write_scalar(t.squeeze_challenge_scalar());
+      t.write_scalar(sc[1]);
+      t.common_point(pt[1]);
+      t.write_point(pt[1]);
+      t.write_scalar(t.squeeze_challenge_scalar());
+      t.write_scalar(t.squeeze_challenge_scalar());
+      for (int i = 0; i < 9; ++i) t.write_scalar(sc[i & 1]);  // past one 128-byte block between squeezes
+      t.write_scalar(t.squeeze_challenge_scalar());
+      spit(argv[3], t.finalize().data(), t.finalize().size());
+    } else if (op == "gwc") {  // args: k npolys nqueries; in: s, polys, query points, query poly indices (limb 0)
+      const uint32_t k = arg(0), np = arg(1), nq = arg(2);
+      const size_t n = size_t(1) << k;
+      const Fr s = take<Fr>(in, 0, 1)[0];
+      std::vector<poly::Polynomial<poly::Coeff>> polys;
+      for (uint32_t i = 0; i < np; ++i) polys.push_back({take<Fr>(in, 32 + size_t(i) * n * 32, n)});
+      const auto points = take<Fr>(in, 32 + size_t(np) * n * 32, nq);
+      const auto idx = take<Fr>(in, 32 + size_t(np) * n * 32 + size_t(nq) * 32, nq);
+      const auto params = poly::kzg::ParamsKZG::setup(k, s);
+      transcript::Blake2bWrite t;
+      t.common_scalar(Fr::from(7));
+      std::vector<poly::ProverQuery> queries;
+      for (uint32_t q = 0; q < nq; ++q) {
+        const auto& pl = polys.at(idx[q].l[0]);
+        t.write_scalar(arithmetic::eval_polynomial(pl.values, points[q]));  // the evaluations go first (plonk/prover.rs:548-595)
+        queries.push_back({points[q], &pl});
+      }
+      poly::kzg::multiopen::ProverGWC(params).create_proof(t, queries);
+      spit(argv[3], t.finalize().data(), t.finalize().size());
     } else {
       return 64;
     }

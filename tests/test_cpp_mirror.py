@@ -96,6 +96,67 @@ def _parity(lib, tag, tmp_path, oc, ks, msm_ns, commit_k):
     assert "too short" in out
 
 
+def _transcript_and_gwc(lib, tag, tmp_path, ctx, k):
+    """Blake2bWrite / Challenge255 and ProverGWC of the C++ mirror against the Python mirror's (whose proofs are
+    byte-equal to the big-integer oracle's, tests/test_emulator_plonk.py / test_gpu_plonk.py)."""
+    import halo2_pse_b200 as h
+    from halo2_pse_b200.prover import _Poly
+    cli = _build("mirror_cli", lib, tag)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+
+    def call(op, blobs, *args):
+        with open(fin, "wb") as f:
+            for b in blobs:
+                f.write(np.ascontiguousarray(b, dtype=np.uint64).tobytes())
+        r = _run(cli, op, fin, fout, *args)
+        assert r.returncode == 0, (op, r.stdout, r.stderr)
+        return open(fout, "rb").read()
+
+    # transcript: the same schedule of absorbs and squeezes on both sides
+    rng = random.Random(3)
+    sc = [rng.randrange(O.R_MOD) for _ in range(2)]
+    pts = [O.g1_mul(O.G1_GEN, rng.randrange(1, O.R_MOD)) for _ in range(2)]
+    t = h.Blake2bWrite()
+    t.common_scalar(sc[0]), t.write_point(pts[0]), t.write_scalar(t.squeeze_challenge_scalar()), t.write_scalar(sc[1])
+    t.common_point(pts[1]), t.write_point(pts[1]), t.write_scalar(t.squeeze_challenge_scalar())
+    t.write_scalar(t.squeeze_challenge_scalar())
+    for i in range(9):
+        t.write_scalar(sc[i & 1])
+    t.write_scalar(t.squeeze_challenge_scalar())
+    assert call("transcript", [H.fr_enc(sc), H.g1_enc(pts)]) == t.finalize()
+
+    # multi-opening: 3 polynomials, 5 queries at 3 distinct points (first-occurrence order matters)
+    n, s = 1 << k, 0x1234567890ABCDEF1234567890ABCDEF
+    polys = [H.rand_fr_limbs(900 + i, n) for i in range(3)]
+    zs = [rng.randrange(O.R_MOD) for _ in range(3)]
+    q_idx, q_pt = [0, 1, 0, 2, 1], [zs[0], zs[0], zs[1], zs[2], zs[1]]
+    idx_limbs = np.zeros((5, 4), dtype=np.uint64)
+    idx_limbs[:, 0] = q_idx
+    got = call("gwc", [H.fr_enc([s])] + polys + [H.fr_enc(q_pt), idx_limbs], k, 3, 5)
+    params = h.ParamsKZG.setup(ctx, k, s)
+    dev = [_Poly(ctx, ctx.upload_fr(p), n) for p in polys]
+    t = h.Blake2bWrite()
+    t.common_scalar(7)
+    queries = [(z, dev[i]) for i, z in zip(q_idx, q_pt)]
+    for z, p in queries:
+        t.write_scalar(p.eval(z))
+    h.ProverGWC(params).create_proof(None, t, queries)
+    assert got == t.finalize()
+    for p in dev:
+        p.buf.free()
+    params.g.free()
+    params.g_lagrange.free()
+
+
+def test_cpp_mirror_transcript_and_gwc_emulator(emu_lib_path, emu_ctx, tmp_path):
+    _transcript_and_gwc(emu_lib_path, "emu", tmp_path, emu_ctx, 5)
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_transcript_and_gwc_gpu(gpu_ctx, tmp_path):
+    _transcript_and_gwc(build.build_product(), "gpu", tmp_path, gpu_ctx, 12)
+
+
 def test_cpp_mirror_self_tests_emulator(emu_lib_path):
     _self_tests(emu_lib_path, "emu", 6)
 
