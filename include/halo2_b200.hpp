@@ -27,7 +27,9 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <istream>
 #include <memory>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -388,6 +390,12 @@ class EvaluationDomain {
   uint64_t n_ = 0;
 };
 
+}  // namespace poly
+
+/// SerdeFormat                                                              halo2_proofs/src/helpers.rs:8-52
+enum class SerdeFormat { Processed, RawBytes, RawBytesUnchecked };
+
+namespace poly {
 namespace kzg {
 /// ParamsKZG<Bn256>: the commit half (k, n, g, g_lagrange); the bases are uploaded once and stay on
 /// the device with their window table                                       poly/kzg/commitment.rs:23-31
@@ -444,6 +452,50 @@ class ParamsKZG {
     return p;
   }
 
+  /// ParamsKZG::read_custom(reader, format)                                   commitment.rs:160-244
+  /// k (u32 LE), g[2^k], g_lagrange[2^k], g2, s_g2.  G1: Processed = 32-byte compressed points, decompressed
+  /// and checked on the GPU; RawBytes = the Montgomery limbs as they are, curve equation checked on the GPU;
+  /// RawBytesUnchecked = uploaded as they are.  The two G2 points belong to the verifier: they are kept as the
+  /// bytes of the file (64 B each when Processed, 128 B raw) and written back unchanged by write_custom in the
+  /// same format.
+  static ParamsKZG read_custom(std::istream& reader, SerdeFormat format, bool precompute = true) {
+    uint8_t kb[4];
+    if (!reader.read(reinterpret_cast<char*>(kb), 4)) throw std::runtime_error("io::Error: unexpected end of file");
+    const uint32_t k = uint32_t(kb[0]) | uint32_t(kb[1]) << 8 | uint32_t(kb[2]) << 16 | uint32_t(kb[3]) << 24;
+    if (k > 28) throw Panic("ParamsKZG::read: k exceeds Fr::S (commitment.rs:64)");
+    ParamsKZG p;
+    p.ctx_ = detail::backend().ctx;
+    p.k_ = k;
+    p.n_ = uint64_t(1) << k;
+    p.g_ = read_g1(p.ctx_, reader, p.n_, format, precompute);
+    p.g_lagrange_ = read_g1(p.ctx_, reader, p.n_, format, precompute);
+    const size_t g2len = format == SerdeFormat::Processed ? 64 : 128;
+    p.g2_bytes_.resize(2 * g2len);
+    if (!reader.read(reinterpret_cast<char*>(p.g2_bytes_.data()), std::streamsize(2 * g2len)))
+      throw std::runtime_error("io::Error: unexpected end of file");
+    p.g2_format_ = format;
+    return p;
+  }
+  /// ParamsKZG::write_custom(writer, format)                                  commitment.rs:142-158
+  void write_custom(std::ostream& writer, SerdeFormat format) const {
+    const bool raw = format != SerdeFormat::Processed;
+    if (g2_bytes_.empty() || (g2_format_ != SerdeFormat::Processed) != raw)
+      throw Panic("ParamsKZG::write: the G2 points are only held as the bytes of the file they were read from (same point encoding required)");
+    const uint8_t kb[4] = {uint8_t(k_), uint8_t(k_ >> 8), uint8_t(k_ >> 16), uint8_t(k_ >> 24)};
+    writer.write(reinterpret_cast<const char*>(kb), 4);
+    for (const h2b_bases* b : {g_.get(), g_lagrange_.get()}) {
+      if (raw) {
+        const auto pts = download(b);
+        writer.write(reinterpret_cast<const char*>(pts.data()), std::streamsize(pts.size() * sizeof(G1Affine)));
+      } else {
+        std::vector<uint8_t> out(n_ * 32);
+        detail::check(ctx_, h2b_g1_compress(ctx_, static_cast<const h2b_g1_affine*>(h2b_bases_device_ptr(b)), n_, 7, out.data()), "h2b_g1_compress");
+        writer.write(reinterpret_cast<const char*>(out.data()), std::streamsize(out.size()));
+      }
+    }
+    writer.write(reinterpret_cast<const char*>(g2_bytes_.data()), std::streamsize(g2_bytes_.size()));
+  }
+
   uint32_t k() const { return k_; }       // commitment.rs:254
   uint64_t n() const { return n_; }       // commitment.rs:258
   std::vector<G1Affine> get_g() const { return download(g_.get()); }  // commitment.rs:316
@@ -455,6 +507,28 @@ class ParamsKZG {
   G1 commit(const Polynomial<Coeff>& poly, const Blind& = Blind{}) const { return msm(g_.get(), poly.values, "assertion failed: bases.len() >= size (commitment.rs:332)"); }
 
  private:
+  static std::shared_ptr<h2b_bases> read_g1(h2b_ctx* ctx, std::istream& reader, size_t n, SerdeFormat format, bool precompute) {
+    const size_t size = format == SerdeFormat::Processed ? 32 : 64;
+    std::vector<uint8_t> raw(n * size);
+    if (!reader.read(reinterpret_cast<char*>(raw.data()), std::streamsize(raw.size()))) throw std::runtime_error("io::Error: unexpected end of file");
+    int ok = 1;
+    std::shared_ptr<h2b_bases> b;
+    if (format == SerdeFormat::Processed) {
+      void* dev = nullptr;
+      detail::check(ctx, h2b_device_alloc(ctx, n * sizeof(G1Affine), &dev), "h2b_device_alloc");
+      const int rc = h2b_g1_decompress(ctx, raw.data(), n, 7, static_cast<h2b_g1_affine*>(dev), &ok);
+      if (rc == H2B_OK && ok) b = upload(ctx, static_cast<const G1Affine*>(dev), n, H2B_DEVICE, precompute);
+      h2b_device_free(ctx, dev);
+      detail::check(ctx, rc, "h2b_g1_decompress");
+    } else {
+      b = upload(ctx, reinterpret_cast<const G1Affine*>(raw.data()), n, H2B_HOST, false);
+      if (format == SerdeFormat::RawBytes)
+        detail::check(ctx, h2b_g1_check_on_curve(ctx, static_cast<const h2b_g1_affine*>(h2b_bases_device_ptr(b.get())), n, &ok), "h2b_g1_check_on_curve");
+      if (ok && precompute) detail::check(ctx, h2b_bases_precompute(ctx, b.get(), 0), "h2b_bases_precompute");
+    }
+    if (!ok) throw std::runtime_error("io::Error: invalid point encoding (helpers.rs:27-44)");
+    return b;
+  }
   static std::shared_ptr<h2b_bases> upload(h2b_ctx* ctx, const G1Affine* pts, size_t n, int loc, bool precompute) {
     h2b_bases* b = nullptr;
     detail::check(ctx, h2b_bases_upload(ctx, reinterpret_cast<const h2b_g1_affine*>(pts), n, loc, &b), "h2b_bases_upload");
@@ -477,6 +551,8 @@ class ParamsKZG {
   uint32_t k_ = 0;
   uint64_t n_ = 0;
   std::shared_ptr<h2b_bases> g_, g_lagrange_;
+  std::vector<uint8_t> g2_bytes_;  // g2 then s_g2, as read (verifier half)
+  SerdeFormat g2_format_ = SerdeFormat::RawBytes;
 };
 }  // namespace kzg
 }  // namespace poly

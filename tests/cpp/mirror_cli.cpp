@@ -1,6 +1,7 @@
 // File-driven entry to the C++ host mirror (include/halo2_b200.hpp) so the Python test-suite can hand it
 // seeded inputs and compare its outputs bit for bit with the oracle:  mirror_cli <op> <in.bin> <out.bin> [args]
 #include <cstdio>
+#include <fstream>
 #include <string>
 
 #include "halo2_b200.hpp"
@@ -74,6 +75,20 @@ int main(int argc, char** argv) {
                                params.commit_lagrange(poly::Polynomial<poly::LagrangeCoeff>{v}).to_affine(),
                                params.get_g()[1], params.get_g_lagrange()[0]};
       spit(argv[3], out, sizeof out);
+    } else if (op == "params") {  // args: in_format out_format (0 Processed, 1 RawBytes, 2 RawBytesUnchecked) k_poly
+      // in.bin: [file length u64][params file][poly 2^k]; out.bin: [the file written back][commit][commit_lagrange]
+      const SerdeFormat fmts[3] = {SerdeFormat::Processed, SerdeFormat::RawBytes, SerdeFormat::RawBytesUnchecked};
+      uint64_t flen;
+      std::memcpy(&flen, in.data(), 8);
+      std::ifstream f(argv[2], std::ios::binary);
+      f.seekg(8);
+      const auto params = poly::kzg::ParamsKZG::read_custom(f, fmts[arg(0)]);
+      const auto v = take<Fr>(in, 8 + flen, size_t(1) << params.k());
+      std::ofstream o(argv[3], std::ios::binary);
+      params.write_custom(o, fmts[arg(1)]);
+      const G1Affine c[2] = {params.commit(poly::Polynomial<poly::Coeff>{v}).to_affine(),
+                             params.commit_lagrange(poly::Polynomial<poly::LagrangeCoeff>{v}).to_affine()};
+      o.write(reinterpret_cast<const char*>(c), sizeof c);
     } else if (op == "transcript") {  // in: s0, s1 (Fr), p0, p1 (G1Affine); a fixed schedule of absorbs and squeezes
       const auto sc = take<Fr>(in, 0, 2);
       const auto pt = take<G1Affine>(in, 64, 2);

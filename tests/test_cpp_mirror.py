@@ -148,6 +148,60 @@ def _transcript_and_gwc(lib, tag, tmp_path, ctx, k):
     params.g_lagrange.free()
 
 
+def _params_files(lib, tag, tmp_path, ctx, k):
+    """ParamsKZG::read_custom / write_custom of the C++ mirror in the three SerdeFormats against the Python
+    mirror's files (kzg/commitment.rs:142-244): the file written back is the file read, the commitments through
+    the loaded SRS are the Python mirror's, a corrupted point is rejected where the format checks points."""
+    import struct
+
+    import halo2_pse_b200 as h
+    from halo2_pse_b200 import serde
+    cli = _build("mirror_cli", lib, tag)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    params = h.ParamsKZG.setup(ctx, k, 0x1234567890ABCDEF1234567890ABCDEF)
+    poly = H.rand_fr_limbs(77, 1 << k)
+    want = H.g1_enc([params.commit(poly), params.commit_lagrange(poly)]).tobytes()
+    fmts = [serde.PROCESSED, serde.RAW_BYTES, serde.RAW_BYTES_UNCHECKED]
+    for i, fmt in enumerate(fmts):
+        blob = serde.params_to_bytes(params, fmt)
+        for j in ([i] if i == 0 else [1, 2]):  # the two raw formats share their bytes
+            with open(fin, "wb") as f:
+                f.write(struct.pack("<Q", len(blob)) + blob + poly.tobytes())
+            r = _run(cli, "params", fin, fout, i, j, k)
+            assert r.returncode == 0, (fmt, r.stdout, r.stderr)
+            out = open(fout, "rb").read()
+            assert out[:-128] == blob and out[-128:] == want, (fmt, j)
+        # a point that is not on the curve / not canonical
+        bad = bytearray(blob)
+        if i == 0:
+            bad[4 + 5 * 32 + 31] |= 0x3f   # x >= q: not canonical, whatever the square root would say
+        else:
+            bad[4 + 5 * 64 + 3] ^= 0x40    # off the curve
+        with open(fin, "wb") as f:
+            f.write(struct.pack("<Q", len(bad)) + bytes(bad) + poly.tobytes())
+        r = _run(cli, "params", fin, fout, i, i, k)
+        if fmt == serde.RAW_BYTES_UNCHECKED:
+            assert r.returncode == 0  # unchecked means unchecked (helpers.rs:46-50)
+        else:
+            assert r.returncode == 2 and "invalid point encoding" in r.stdout, (fmt, r.stdout)
+    # writing the G2 points in the other encoding would need G2 arithmetic the commit half does not carry
+    blob = serde.params_to_bytes(params, serde.RAW_BYTES)
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<Q", len(blob)) + blob + poly.tobytes())
+    assert _run(cli, "params", fin, fout, 1, 0, k).returncode == 101
+    params.g.free()
+    params.g_lagrange.free()
+
+
+def test_cpp_mirror_params_files_emulator(emu_lib_path, emu_ctx, tmp_path):
+    _params_files(emu_lib_path, "emu", tmp_path, emu_ctx, 5)
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_params_files_gpu(gpu_ctx, tmp_path):
+    _params_files(build.build_product(), "gpu", tmp_path, gpu_ctx, 10)
+
+
 def test_cpp_mirror_transcript_and_gwc_emulator(emu_lib_path, emu_ctx, tmp_path):
     _transcript_and_gwc(emu_lib_path, "emu", tmp_path, emu_ctx, 5)
 
