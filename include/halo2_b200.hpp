@@ -10,6 +10,7 @@
 //   halo2_proofs::poly::kzg::ParamsKZG (commit half)            halo2_proofs/src/poly/kzg/commitment.rs:23-131, 281-334
 //   halo2_proofs::transcript::Blake2bWrite (Challenge255)       halo2_proofs/src/transcript.rs:282-514
 //   halo2_proofs::poly::kzg::multiopen::ProverGWC               halo2_proofs/src/poly/kzg/multiopen/gwc/prover.rs:24-92
+//   halo2_proofs::poly::kzg::multiopen::ProverSHPLONK           halo2_proofs/src/poly/kzg/multiopen/shplonk/prover.rs:94-285
 //
 // Error behaviour: where the reference panics (assert_eq! on lengths, assert!(bases.len() >= size)),
 // these throw halo2_proofs::Panic with the reference's file:line in the message; a CUDA / allocation
@@ -720,6 +721,154 @@ class ProverGWC {
       Polynomial<Coeff> witness{arithmetic::kate_division(poly_batch.values, z)};          // :79
       t.write_point(params_.commit(witness).to_affine());                                  // :80-88
     }
+  }
+
+ private:
+  const ParamsKZG& params_;
+};
+}  // namespace multiopen
+}  // namespace kzg
+}  // namespace poly
+
+/// arithmetic::lagrange_interpolate on a handful of points (host)            halo2_proofs/src/arithmetic.rs:405-458
+namespace arithmetic {
+inline std::vector<Fr> lagrange_interpolate(const std::vector<Fr>& points, const std::vector<Fr>& evals) {
+  if (points.size() != evals.size()) throw Panic("assertion failed: `(left == right)` points.len() == evals.len() (arithmetic.rs:406)");
+  if (points.size() == 1) return {evals[0]};
+  std::vector<Fr> fin(points.size(), Fr::zero());
+  for (size_t j = 0; j < points.size(); ++j) {
+    std::vector<Fr> tmp{Fr::one()};
+    for (size_t k = 0; k < points.size(); ++k) {
+      if (k == j) continue;
+      const Fr denom = (points[j] - points[k]).invert();
+      std::vector<Fr> next(tmp.size() + 1, Fr::zero());
+      for (size_t i = 0; i < tmp.size(); ++i) {  // tmp(X) * (X - x_k) / (x_j - x_k)
+        next[i] += tmp[i] * (-(denom * points[k]));
+        next[i + 1] += tmp[i] * denom;
+      }
+      tmp.swap(next);
+    }
+    for (size_t i = 0; i < fin.size(); ++i) fin[i] += tmp[i] * evals[j];
+  }
+  return fin;
+}
+/// evaluate_vanishing_polynomial(roots, z)                                  arithmetic.rs:460-478
+inline Fr evaluate_vanishing_polynomial(const std::vector<Fr>& roots, const Fr& z) {
+  Fr acc = Fr::one();
+  for (const Fr& r : roots) acc *= z - r;
+  return acc;
+}
+}  // namespace arithmetic
+
+// ---------------------------------------------------------------------------------------------
+// halo2_proofs::poly::kzg::multiopen::ProverSHPLONK
+//            halo2_proofs/src/poly/kzg/multiopen/shplonk.rs:55-134, shplonk/prover.rs:94-285
+// ---------------------------------------------------------------------------------------------
+namespace poly {
+namespace kzg {
+namespace multiopen {
+class ProverSHPLONK {
+ public:
+  explicit ProverSHPLONK(const ParamsKZG& params) : params_(params) {}
+  void create_proof(transcript::Blake2bWrite& t, const std::vector<ProverQuery>& queries) const {
+    using Poly = Polynomial<Coeff>;
+    const size_t n = params_.n();
+    auto less = [](const Fr& a, const Fr& b) {  // Ord for Fr: the canonical integers (BTreeSet order of the rotation sets)
+      const Fr x = a.to_repr_limbs(), y = b.to_repr_limbs();
+      for (int i = 3; i >= 0; --i)
+        if (x.l[i] != y.l[i]) return x.l[i] < y.l[i];
+      return false;
+    };
+    auto sorted_unique = [&](std::vector<Fr> v) {
+      for (size_t i = 1; i < v.size(); ++i)
+        for (size_t j = i; j > 0 && less(v[j], v[j - 1]); --j) std::swap(v[j], v[j - 1]);
+      std::vector<Fr> u;
+      for (const Fr& x : v)
+        if (u.empty() || u.back() != x) u.push_back(x);
+      return u;
+    };
+    // construct_intermediate_sets (shplonk.rs:55-134): points per polynomial, polynomials per point set
+    std::vector<Fr> all_points;
+    std::vector<std::pair<const Poly*, std::vector<Fr>>> by_commitment;  // first-occurrence order, told apart by identity
+    for (const auto& q : queries) {
+      all_points.push_back(q.point);
+      bool found = false;
+      for (auto& c : by_commitment)
+        if (c.first == q.poly) c.second.push_back(q.point), found = true;
+      if (!found) by_commitment.push_back({q.poly, {q.point}});
+    }
+    const std::vector<Fr> super_points = sorted_unique(all_points);
+    struct RotationSet {
+      std::vector<Fr> points;                                        // ascending
+      std::vector<std::pair<const Poly*, std::vector<Fr>>> coms;     // polynomial, low-degree equivalent r(X)
+    };
+    std::vector<RotationSet> sets;
+    for (auto& c : by_commitment) {
+      const std::vector<Fr> pts = sorted_unique(c.second);
+      RotationSet* rs = nullptr;
+      for (auto& s : sets)
+        if (s.points == pts) rs = &s;
+      if (!rs) sets.push_back({pts, {}}), rs = &sets.back();
+      std::vector<Fr> evals;
+      for (const Fr& pt : pts) evals.push_back(arithmetic::eval_polynomial(c.first->values, pt));
+      rs->coms.push_back({c.first, arithmetic::lagrange_interpolate(pts, evals)});
+    }
+    const Fr y = t.squeeze_challenge_scalar();                                             // prover.rs:113
+    const Fr v = t.squeeze_challenge_scalar();                                             // :118
+    auto fma = [](Poly& acc, const std::vector<Fr>& p, const Fr& w) {  // acc[..p.len()] += p * w
+      Poly scaled = Poly{p} * w;
+      Poly head{std::vector<Fr>(acc.values.begin(), acc.values.begin() + p.size())};
+      head = head + scaled;
+      std::copy(head.values.begin(), head.values.end(), acc.values.begin());
+    };
+    // h(X) = sum_i v^i (sum_j y^j (p_j - r_j)) / Z_i                                      :120-177
+    Poly h_x{std::vector<Fr>(n, Fr::zero())};
+    Fr pv = Fr::one();
+    for (const auto& s : sets) {
+      Poly n_x{std::vector<Fr>(n, Fr::zero())};
+      Fr py = Fr::one();
+      for (const auto& c : s.coms) {
+        std::vector<Fr> num = c.first->values;
+        for (size_t i = 0; i < c.second.size(); ++i) num[i] -= c.second[i];
+        fma(n_x, num, py);
+        py *= y;
+      }
+      std::vector<Fr> q = n_x.values;
+      for (const Fr& pt : s.points) q = arithmetic::kate_division(q, pt);                  // div_by_vanishing
+      fma(h_x, q, pv);
+      pv *= v;
+    }
+    t.write_point(params_.commit(h_x).to_affine());                                        // :178-180
+    const Fr u = t.squeeze_challenge_scalar();                                             // :181
+    // l(X) = sum_i v^i z_i(u) sum_j y^j (p_j - r_j(u)) - Z_T(u) h(X)                      :183-232
+    Poly l_x{std::vector<Fr>(n, Fr::zero())};
+    std::vector<Fr> z_diffs;
+    pv = Fr::one();
+    for (const auto& s : sets) {
+      std::vector<Fr> others;
+      for (const Fr& p : super_points) {
+        bool in = false;
+        for (const Fr& q : s.points) in = in || q == p;
+        if (!in) others.push_back(p);
+      }
+      const Fr z_i = arithmetic::evaluate_vanishing_polynomial(others, u);
+      Fr py = Fr::one(), konst = Fr::zero();
+      for (const auto& c : s.coms) {
+        Fr r_eval = Fr::zero();
+        for (size_t i = c.second.size(); i-- > 0;) r_eval = r_eval * u + c.second[i];
+        const Fr w = py * z_i * pv;
+        fma(l_x, c.first->values, w);
+        konst += r_eval * w;
+        py *= y;
+      }
+      l_x.values[0] -= konst;
+      z_diffs.push_back(z_i);
+      pv *= v;
+    }
+    fma(l_x, h_x.values, -arithmetic::evaluate_vanishing_polynomial(super_points, u));
+    Poly h2{arithmetic::kate_division(l_x.values, u)};                                     // :240
+    h2 = h2 * z_diffs.at(0).invert();                                                      // :243-246
+    t.write_point(params_.commit(h2).to_affine());                                         // :248-250
   }
 
  private:

@@ -104,7 +104,7 @@ int main(int argc, char** argv) {
       for (int i = 0; i < 9; ++i) t.write_scalar(sc[i & 1]);  // past one 128-byte block between squeezes
       t.write_scalar(t.squeeze_challenge_scalar());
       spit(argv[3], t.finalize().data(), t.finalize().size());
-    } else if (op == "gwc") {  // args: k npolys nqueries; in: s, polys, query points, query poly indices (limb 0)
+    } else if (op == "gwc" || op == "shplonk") {  // args: k npolys nqueries; in: s, polys, query points, query poly indices (limb 0)
       const uint32_t k = arg(0), np = arg(1), nq = arg(2);
       const size_t n = size_t(1) << k;
       const Fr s = take<Fr>(in, 0, 1)[0];
@@ -121,7 +121,10 @@ int main(int argc, char** argv) {
         t.write_scalar(arithmetic::eval_polynomial(pl.values, points[q]));  // the evaluations go first (plonk/prover.rs:548-595)
         queries.push_back({points[q], &pl});
       }
-      poly::kzg::multiopen::ProverGWC(params).create_proof(t, queries);
+      if (op == "gwc")
+        poly::kzg::multiopen::ProverGWC(params).create_proof(t, queries);
+      else
+        poly::kzg::multiopen::ProverSHPLONK(params).create_proof(t, queries);
       spit(argv[3], t.finalize().data(), t.finalize().size());
     } else {
       return 64;

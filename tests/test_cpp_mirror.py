@@ -142,6 +142,14 @@ def _transcript_and_gwc(lib, tag, tmp_path, ctx, k):
         t.write_scalar(p.eval(z))
     h.ProverGWC(params).create_proof(None, t, queries)
     assert got == t.finalize()
+    # the same queries through SHPLONK (rotation sets {z0, z1}, {z0, z1} again for polynomial 1, {z2})
+    got = call("shplonk", [H.fr_enc([s])] + polys + [H.fr_enc(q_pt), idx_limbs], k, 3, 5)
+    t = h.Blake2bWrite()
+    t.common_scalar(7)
+    for z, p in queries:
+        t.write_scalar(p.eval(z))
+    h.ProverSHPLONK(params).create_proof(None, t, queries)
+    assert got == t.finalize()
     for p in dev:
         p.buf.free()
     params.g.free()
