@@ -4,7 +4,7 @@
 #include <fstream>
 #include <string>
 
-#include "halo2_b200.hpp"
+#include "halo2_b200_plonk.hpp"
 
 using namespace halo2_proofs;
 
@@ -75,6 +75,45 @@ int main(int argc, char** argv) {
                                params.commit_lagrange(poly::Polynomial<poly::LagrangeCoeff>{v}).to_affine(),
                                params.get_g()[1], params.get_g_lagrange()[0]};
       spit(argv[3], out, sizeof out);
+    } else if (op == "pinned_vk") {  // in.bin: text lines: k, extended_k, omega, base modulus, scalar modulus, #fixed, points...
+      // tests/plonk_api.rs:389-470 -- MyCircuit::configure of the reference's own test, statement by statement
+      using namespace plonk;
+      ConstraintSystem meta;
+      const Column e = meta.advice_column(), a = meta.advice_column(), b = meta.advice_column();
+      const Column sf = meta.fixed_column();
+      const Column c = meta.advice_column(), d = meta.advice_column();
+      const Column p = meta.instance_column();
+      meta.enable_equality(a), meta.enable_equality(b), meta.enable_equality(c);
+      const Column sm = meta.fixed_column(), sa = meta.fixed_column(), sb = meta.fixed_column(), sc = meta.fixed_column(),
+                   sp = meta.fixed_column();
+      const Column sl = meta.lookup_table_column();
+      {
+        const Expression a_ = meta.query_any(a, 0);
+        meta.lookup("lookup", {{a_, sl}});
+      }
+      {
+        const Expression qd = meta.query_advice(d, 1), qa = meta.query_advice(a, 0), qsf = meta.query_fixed(sf, 0);
+        const Expression qe = meta.query_advice(e, -1), qb = meta.query_advice(b, 0), qc = meta.query_advice(c, 0);
+        const Expression qsa = meta.query_fixed(sa, 0), qsb = meta.query_fixed(sb, 0), qsc = meta.query_fixed(sc, 0),
+                         qsm = meta.query_fixed(sm, 0);
+        meta.create_gate("Combined add-mult", {qa * qsa + qb * qsb + qa * qb * qsm - (qc * qsc) + qsf * (qd * qe)});
+      }
+      {
+        const Expression qa = meta.query_advice(a, 0), qp = meta.query_instance(p, 0), qsp = meta.query_fixed(sp, 0);
+        meta.create_gate("Public input", {qsp * (qa - qp)});
+      }
+      for (const Column& col : {sf, e, d, p, sm, sa, sb, sc, sp}) meta.enable_equality(col);
+      std::ifstream f(argv[2]);
+      std::vector<std::string> lines;
+      for (std::string line; std::getline(f, line);) lines.push_back(line);
+      const size_t nfixed = std::stoul(lines.at(5));
+      std::vector<std::string> fixed(lines.begin() + 6, lines.begin() + 6 + nfixed), perm(lines.begin() + 6 + nfixed, lines.end());
+      if (meta.degree() != 4 || meta.blinding_factors() != 5) throw std::runtime_error("degree / blinding_factors of the plonk_api circuit");
+      const std::string s = pinned_debug(meta, std::stoul(lines.at(0)), std::stoul(lines.at(1)), lines.at(2), fixed, perm, lines.at(3), lines.at(4));
+      const Fr repr = vk_transcript_repr(s);
+      std::ofstream o(argv[3], std::ios::binary);
+      o.write(reinterpret_cast<const char*>(repr.l), 32);
+      o << s;
     } else if (op == "params") {  // args: in_format out_format (0 Processed, 1 RawBytes, 2 RawBytesUnchecked) k_poly
       // in.bin: [file length u64][params file][poly 2^k]; out.bin: [the file written back][commit][commit_lagrange]
       const SerdeFormat fmts[3] = {SerdeFormat::Processed, SerdeFormat::RawBytes, SerdeFormat::RawBytesUnchecked};

@@ -156,6 +156,25 @@ def _transcript_and_gwc(lib, tag, tmp_path, ctx, k):
     params.g_lagrange.free()
 
 
+def test_cpp_mirror_pinned_vk_of_the_reference(emu_lib_path, tmp_path):
+    """include/halo2_b200_plonk.hpp: `configure()` of the reference's tests/plonk_api.rs rebuilt with the C++
+    ConstraintSystem (host-only: no kernel runs) gives, character for character, the reference's golden pinned
+    verifying key (tests/golden/pinned_vk_plonk_api.json); its transcript_repr hash equals the oracle's."""
+    from oracle import prover as OV
+    fx = H.load_golden("pinned_vk_plonk_api.json")
+    cli = _build("mirror_cli", emu_lib_path, "emu")
+    fin, fout = str(tmp_path / "in.txt"), str(tmp_path / "out.bin")
+    pt = lambda xy: "(%s, %s)" % tuple(xy)  # noqa: E731
+    lines = [str(fx["k"]), str(fx["extended_k"]), fx["omega"], fx["base_modulus"], fx["scalar_modulus"],
+             str(len(fx["fixed_commitments"]))] + [pt(p) for p in fx["fixed_commitments"] + fx["permutation_commitments"]]
+    open(fin, "w").write("\n".join(lines) + "\n")
+    r = _run(cli, "pinned_vk", fin, fout, 0)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = open(fout, "rb").read()
+    assert out[32:].decode() == fx["debug"]
+    assert H.fr_dec(np.frombuffer(out[:32], dtype=np.uint64).reshape(1, 4))[0] == OV.vk_transcript_repr(fx["debug"])
+
+
 def _params_files(lib, tag, tmp_path, ctx, k):
     """ParamsKZG::read_custom / write_custom of the C++ mirror in the three SerdeFormats against the Python
     mirror's files (kzg/commitment.rs:142-244): the file written back is the file read, the commitments through
