@@ -3,6 +3,7 @@
 //
 //   halo2_proofs::plonk::{Any, Column, Expression, ConstraintSystem}      halo2_proofs/src/plonk/circuit.rs:780-2060
 //   halo2_proofs::plonk::lookup::Argument, permutation::Argument         plonk/lookup.rs:10-60, plonk/permutation.rs:19-75
+//   halo2_proofs::plonk::{ValueSource, Calculation, GraphEvaluator, Evaluator::new}   plonk/evaluation.rs:38-277, 525-690
 //   halo2_proofs::plonk::pinned_debug  = format!("{:?}", vk.pinned())     plonk.rs:192-230, circuit.rs:1399-1448
 //   halo2_proofs::plonk::vk_transcript_repr                               plonk.rs:192-203
 //
@@ -93,6 +94,12 @@ class Expression {
     }
   }
   Kind kind() const { return n_->kind; }
+  const Fr& value() const { return n_->value; }            // Constant / Scaled
+  uint32_t column_index() const { return n_->b; }          // queries
+  uint32_t challenge_index() const { return n_->a; }       // Challenge
+  int32_t rotation() const { return n_->rot; }
+  const Expression& lhs() const { return *n_->l; }
+  const Expression& rhs() const { return *n_->r; }
 
  private:
   struct Node {
@@ -248,6 +255,149 @@ class ConstraintSystem {
     qs.push_back({c, at});
     if (c.column_type == Any::Advice) num_advice_queries[c.index] += 1;
     return uint32_t(qs.size() - 1);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// GraphEvaluator / Evaluator::new: expressions -> the calculation list the library compiles (h2b_graph_new)
+//                                                                 halo2_proofs/src/plonk/evaluation.rs:38-127, 183-277, 525-690
+// ---------------------------------------------------------------------------------------------
+struct ValueSource {  // variant order == the reference's derived PartialOrd (evaluation.rs:38-61) == the ABI's operand kinds
+  enum Kind : uint32_t { Constant, Intermediate, Fixed, Advice, Instance, Challenge, Beta, Gamma, Theta, Y, PreviousValue };
+  uint32_t kind = Constant, a = 0, b = 0;
+  bool operator==(const ValueSource& o) const { return kind == o.kind && a == o.a && b == o.b; }
+  bool operator<=(const ValueSource& o) const {
+    return kind != o.kind ? kind < o.kind : a != o.a ? a < o.a : b <= o.b;
+  }
+};
+
+struct Calculation {  // evaluation.rs:110-127; op numbering of include/halo2_b200.h
+  enum Op : uint32_t { Add, Sub, Mul, Square, Double, Negate, Horner, Store };
+  uint32_t op = Store;
+  std::vector<ValueSource> src;  // Horner: start, factor, then the parts
+  bool operator==(const Calculation& o) const { return op == o.op && src == o.src; }
+};
+
+class GraphEvaluator {
+ public:
+  std::vector<Fr> constants{Fr::zero(), Fr::one(), Fr::from(2)};  // fixed positions (:525-538)
+  std::vector<int32_t> rotations;
+  std::vector<std::pair<Calculation, uint32_t>> calculations;     // (calculation, target)
+  uint32_t num_intermediates = 0;
+
+  uint32_t add_rotation(int32_t r) {
+    for (size_t i = 0; i < rotations.size(); ++i)
+      if (rotations[i] == r) return uint32_t(i);
+    rotations.push_back(r);
+    return uint32_t(rotations.size() - 1);
+  }
+  ValueSource add_constant(const Fr& c) {
+    for (size_t i = 0; i < constants.size(); ++i)
+      if (constants[i] == c) return {ValueSource::Constant, uint32_t(i), 0};
+    constants.push_back(c);
+    return {ValueSource::Constant, uint32_t(constants.size() - 1), 0};
+  }
+  ValueSource add_calculation(const Calculation& c) {
+    for (const auto& e : calculations)
+      if (e.first == c) return {ValueSource::Intermediate, e.second, 0};
+    calculations.push_back({c, num_intermediates});
+    return {ValueSource::Intermediate, num_intermediates++, 0};
+  }
+  ValueSource add_expression(const Expression& e) {  // :590-690
+    const ValueSource zero{ValueSource::Constant, 0, 0}, one{ValueSource::Constant, 1, 0}, two{ValueSource::Constant, 2, 0};
+    auto calc = [&](uint32_t op, std::initializer_list<ValueSource> s) { return add_calculation(Calculation{op, s}); };
+    switch (e.kind()) {
+      case Expression::Constant: return add_constant(e.value());
+      case Expression::Fixed: return calc(Calculation::Store, {{ValueSource::Fixed, e.column_index(), add_rotation(e.rotation())}});
+      case Expression::Advice: return calc(Calculation::Store, {{ValueSource::Advice, e.column_index(), add_rotation(e.rotation())}});
+      case Expression::Instance: return calc(Calculation::Store, {{ValueSource::Instance, e.column_index(), add_rotation(e.rotation())}});
+      case Expression::Challenge: return calc(Calculation::Store, {{ValueSource::Challenge, e.challenge_index(), 0}});
+      case Expression::Negated: {
+        if (e.lhs().kind() == Expression::Constant) return add_constant(-e.lhs().value());
+        const ValueSource a = add_expression(e.lhs());
+        return a == zero ? a : calc(Calculation::Negate, {a});
+      }
+      case Expression::Sum: {
+        if (e.rhs().kind() == Expression::Negated) {  // undo subtraction stored as a + (-b)
+          const ValueSource a = add_expression(e.lhs()), b = add_expression(e.rhs().lhs());
+          if (a == zero) return calc(Calculation::Negate, {b});
+          if (b == zero) return a;
+          return calc(Calculation::Sub, {a, b});
+        }
+        const ValueSource a = add_expression(e.lhs()), b = add_expression(e.rhs());
+        if (a == zero) return b;
+        if (b == zero) return a;
+        return a <= b ? calc(Calculation::Add, {a, b}) : calc(Calculation::Add, {b, a});
+      }
+      case Expression::Product: {
+        const ValueSource a = add_expression(e.lhs()), b = add_expression(e.rhs());
+        if (a == zero || b == zero) return zero;
+        if (a == one) return b;
+        if (b == one) return a;
+        if (a == two) return calc(Calculation::Double, {b});
+        if (b == two) return calc(Calculation::Double, {a});
+        if (a == b) return calc(Calculation::Square, {a});
+        return a <= b ? calc(Calculation::Mul, {a, b}) : calc(Calculation::Mul, {b, a});
+      }
+      default: {  // Scaled
+        if (e.value().is_zero()) return zero;
+        if (e.value() == Fr::one()) return add_expression(e.lhs());
+        const ValueSource c = add_constant(e.value());
+        const ValueSource a = add_expression(e.lhs());
+        return calc(Calculation::Mul, {a, c});
+      }
+    }
+  }
+  /// the word stream of include/halo2_b200.h: op, target, operands (three words each); Horner: start, factor, nparts, parts
+  std::vector<uint32_t> encode() const {
+    std::vector<uint32_t> w;
+    auto put = [&](const ValueSource& s) { w.push_back(s.kind), w.push_back(s.a), w.push_back(s.b); };
+    for (const auto& e : calculations) {
+      w.push_back(e.first.op), w.push_back(e.second);
+      if (e.first.op == Calculation::Horner) {
+        put(e.first.src[0]), put(e.first.src[1]);
+        w.push_back(uint32_t(e.first.src.size() - 2));
+        for (size_t i = 2; i < e.first.src.size(); ++i) put(e.first.src[i]);
+      } else {
+        for (const auto& s : e.first.src) put(s);
+      }
+    }
+    return w;
+  }
+  /// h2b_graph_new on the calling thread's context (the library compiles the list once, as Evaluator::new does at keygen)
+  std::shared_ptr<h2b_graph> compile() const {
+    h2b_ctx* ctx = detail::backend().ctx;
+    const auto code = encode();
+    h2b_graph* g = nullptr;
+    detail::check(ctx, h2b_graph_new(ctx, code.data(), code.size(), constants.data(), uint32_t(constants.size()), rotations.data(),
+                                     uint32_t(rotations.size()), num_intermediates, &g), "h2b_graph_new: malformed calculation list");
+    return std::shared_ptr<h2b_graph>(g, h2b_graph_free);
+  }
+};
+
+/// Evaluator::new(cs): custom_gates (all gate polynomials folded with y onto the previous value) and one graph
+/// per lookup ((compressed input + beta) * (compressed table + gamma))                    evaluation.rs:224-277
+struct Evaluator {
+  GraphEvaluator custom_gates;
+  std::vector<GraphEvaluator> lookups;
+  explicit Evaluator(const ConstraintSystem& cs) {
+    Calculation horner{Calculation::Horner, {{ValueSource::PreviousValue, 0, 0}, {ValueSource::Y, 0, 0}}};
+    for (const auto& gate : cs.gates)
+      for (const auto& poly : gate.second) horner.src.push_back(custom_gates.add_expression(poly));
+    custom_gates.add_calculation(horner);
+    for (const auto& lk : cs.lookups) {
+      GraphEvaluator graph;
+      auto evaluate_lc = [&](const std::vector<Expression>& exprs) {
+        Calculation h{Calculation::Horner, {{ValueSource::Constant, 0, 0}, {ValueSource::Theta, 0, 0}}};
+        for (const auto& e : exprs) h.src.push_back(graph.add_expression(e));
+        return graph.add_calculation(h);
+      };
+      const ValueSource in = evaluate_lc(lk.input_expressions), tab = evaluate_lc(lk.table_expressions);
+      const ValueSource right_gamma = graph.add_calculation({Calculation::Add, {tab, {ValueSource::Gamma, 0, 0}}});
+      const ValueSource lc = graph.add_calculation({Calculation::Add, {in, {ValueSource::Beta, 0, 0}}});
+      graph.add_calculation({Calculation::Mul, {lc, right_gamma}});
+      lookups.push_back(std::move(graph));
+    }
   }
 };
 

@@ -31,6 +31,53 @@ static std::vector<T> take(const std::vector<uint8_t>& b, size_t off_bytes, size
   return v;
 }
 
+// tests/plonk_api.rs:389-470 -- MyCircuit::configure of the reference's own test, statement by statement
+static plonk::ConstraintSystem plonk_api_circuit() {
+  using namespace plonk;
+  ConstraintSystem meta;
+  const Column e = meta.advice_column(), a = meta.advice_column(), b = meta.advice_column();
+  const Column sf = meta.fixed_column();
+  const Column c = meta.advice_column(), d = meta.advice_column();
+  const Column p = meta.instance_column();
+  meta.enable_equality(a), meta.enable_equality(b), meta.enable_equality(c);
+  const Column sm = meta.fixed_column(), sa = meta.fixed_column(), sb = meta.fixed_column(), sc = meta.fixed_column(),
+               sp = meta.fixed_column();
+  const Column sl = meta.lookup_table_column();
+  {
+    const Expression a_ = meta.query_any(a, 0);
+    meta.lookup("lookup", {{a_, sl}});
+  }
+  {
+    const Expression qd = meta.query_advice(d, 1), qa = meta.query_advice(a, 0), qsf = meta.query_fixed(sf, 0);
+    const Expression qe = meta.query_advice(e, -1), qb = meta.query_advice(b, 0), qc = meta.query_advice(c, 0);
+    const Expression qsa = meta.query_fixed(sa, 0), qsb = meta.query_fixed(sb, 0), qsc = meta.query_fixed(sc, 0),
+                     qsm = meta.query_fixed(sm, 0);
+    meta.create_gate("Combined add-mult", {qa * qsa + qb * qsb + qa * qb * qsm - (qc * qsc) + qsf * (qd * qe)});
+  }
+  {
+    const Expression qa = meta.query_advice(a, 0), qp = meta.query_instance(p, 0), qsp = meta.query_fixed(sp, 0);
+    meta.create_gate("Public input", {qsp * (qa - qp)});
+  }
+  for (const Column& col : {sf, e, d, p, sm, sa, sb, sc, sp}) meta.enable_equality(col);
+  // a second gate set that exercises the rest of the graph compiler: constants, scaling, negation, doubling,
+  // squares, repeated sub-expressions, a challenge (not part of the reference's circuit: appended by `extra`)
+  return meta;
+}
+
+static void dump_graph(std::ofstream& o, const plonk::GraphEvaluator& g) {
+  auto u32 = [&](uint32_t v) { o.write(reinterpret_cast<const char*>(&v), 4); };
+  const auto w = g.encode();
+  u32(uint32_t(w.size()));
+  o.write(reinterpret_cast<const char*>(w.data()), std::streamsize(w.size() * 4));
+  u32(uint32_t(g.constants.size()));
+  o.write(reinterpret_cast<const char*>(g.constants.data()), std::streamsize(g.constants.size() * 32));
+  u32(uint32_t(g.rotations.size()));
+  o.write(reinterpret_cast<const char*>(g.rotations.data()), std::streamsize(g.rotations.size() * 4));
+  u32(g.num_intermediates);
+  const auto compiled = g.compile();  // the library accepts the list
+  u32(h2b_graph_num_instructions(compiled.get()));
+}
+
 int main(int argc, char** argv) {
   if (argc < 4) return 64;
   const std::string op = argv[1];
@@ -76,33 +123,8 @@ int main(int argc, char** argv) {
                                params.get_g()[1], params.get_g_lagrange()[0]};
       spit(argv[3], out, sizeof out);
     } else if (op == "pinned_vk") {  // in.bin: text lines: k, extended_k, omega, base modulus, scalar modulus, #fixed, points...
-      // tests/plonk_api.rs:389-470 -- MyCircuit::configure of the reference's own test, statement by statement
       using namespace plonk;
-      ConstraintSystem meta;
-      const Column e = meta.advice_column(), a = meta.advice_column(), b = meta.advice_column();
-      const Column sf = meta.fixed_column();
-      const Column c = meta.advice_column(), d = meta.advice_column();
-      const Column p = meta.instance_column();
-      meta.enable_equality(a), meta.enable_equality(b), meta.enable_equality(c);
-      const Column sm = meta.fixed_column(), sa = meta.fixed_column(), sb = meta.fixed_column(), sc = meta.fixed_column(),
-                   sp = meta.fixed_column();
-      const Column sl = meta.lookup_table_column();
-      {
-        const Expression a_ = meta.query_any(a, 0);
-        meta.lookup("lookup", {{a_, sl}});
-      }
-      {
-        const Expression qd = meta.query_advice(d, 1), qa = meta.query_advice(a, 0), qsf = meta.query_fixed(sf, 0);
-        const Expression qe = meta.query_advice(e, -1), qb = meta.query_advice(b, 0), qc = meta.query_advice(c, 0);
-        const Expression qsa = meta.query_fixed(sa, 0), qsb = meta.query_fixed(sb, 0), qsc = meta.query_fixed(sc, 0),
-                         qsm = meta.query_fixed(sm, 0);
-        meta.create_gate("Combined add-mult", {qa * qsa + qb * qsb + qa * qb * qsm - (qc * qsc) + qsf * (qd * qe)});
-      }
-      {
-        const Expression qa = meta.query_advice(a, 0), qp = meta.query_instance(p, 0), qsp = meta.query_fixed(sp, 0);
-        meta.create_gate("Public input", {qsp * (qa - qp)});
-      }
-      for (const Column& col : {sf, e, d, p, sm, sa, sb, sc, sp}) meta.enable_equality(col);
+      ConstraintSystem meta = plonk_api_circuit();
       std::ifstream f(argv[2]);
       std::vector<std::string> lines;
       for (std::string line; std::getline(f, line);) lines.push_back(line);
@@ -114,6 +136,24 @@ int main(int argc, char** argv) {
       std::ofstream o(argv[3], std::ios::binary);
       o.write(reinterpret_cast<const char*>(repr.l), 32);
       o << s;
+    } else if (op == "graph") {  // arg: 0 = the plonk_api circuit, 1 = with extra gates; out: custom_gates, then every lookup graph
+      using namespace plonk;
+      ConstraintSystem meta = plonk_api_circuit();
+      if (arg(0) == 1) {
+        const Column a{Any::Advice, 1}, b{Any::Advice, 2}, f{Any::Fixed, 0};
+        const Expression qa = meta.query_advice(a, 0), qb = meta.query_advice(b, 2), qf = meta.query_fixed(f, -1);
+        const Expression ch = meta.challenge_usable_after(0);
+        const Expression one = Expression::constant(Fr::one()), two = Expression::constant(Fr::from(2)), zero = Expression::constant(Fr::zero());
+        meta.create_gate("extra", {qf * (qa * qa * two - qb * Fr::from(7) + (-qa)) + zero * qa,
+                                   (qa + qb) * (qa + qb) * qf - qb * ch + qa * (-Fr::from(5)),
+                                   -(Expression::constant(Fr::from(3))) + two * qb - (qa * qb - qf) * one,
+                                   (qa - zero) * (qb * Fr::one()) * (qf * Fr::zero() + qa)});
+        meta.lookup("l1", {{qb * ch + one, Column{Any::Fixed, 6}}});
+      }
+      const Evaluator ev(meta);
+      std::ofstream o(argv[3], std::ios::binary);
+      dump_graph(o, ev.custom_gates);
+      for (const auto& g : ev.lookups) dump_graph(o, g);
     } else if (op == "params") {  // args: in_format out_format (0 Processed, 1 RawBytes, 2 RawBytesUnchecked) k_poly
       // in.bin: [file length u64][params file][poly 2^k]; out.bin: [the file written back][commit][commit_lagrange]
       const SerdeFormat fmts[3] = {SerdeFormat::Processed, SerdeFormat::RawBytes, SerdeFormat::RawBytesUnchecked};

@@ -175,6 +175,77 @@ def test_cpp_mirror_pinned_vk_of_the_reference(emu_lib_path, tmp_path):
     assert H.fr_dec(np.frombuffer(out[:32], dtype=np.uint64).reshape(1, 4))[0] == OV.vk_transcript_repr(fx["debug"])
 
 
+def _plonk_api_cs(extra: bool):
+    """MyCircuit::configure of tests/plonk_api.rs:389-470 through the Python mirror (the same statements as
+    tests/cpp/mirror_cli.cpp::plonk_api_circuit), optionally with the extra gates of the CLI's `graph 1`."""
+    import halo2_pse_b200 as h
+    cs = h.ConstraintSystem()
+    e, a, b = cs.advice_column(), cs.advice_column(), cs.advice_column()
+    sf = cs.fixed_column()
+    c, d = cs.advice_column(), cs.advice_column()
+    p = cs.instance_column()
+    for col in (a, b, c):
+        cs.enable_equality(col)
+    sm, sa, sb, sc, sp = (cs.fixed_column() for _ in range(5))
+    sl = cs.fixed_column()
+    a_ = cs.query_advice(a)
+    cs.lookup("lookup", [(a_, cs.query_fixed(sl))])
+    qd, qa, qsf = cs.query_advice(d, 1), cs.query_advice(a), cs.query_fixed(sf)
+    qe, qb, qc = cs.query_advice(e, -1), cs.query_advice(b), cs.query_advice(c)
+    qsa, qsb, qsc, qsm = cs.query_fixed(sa), cs.query_fixed(sb), cs.query_fixed(sc), cs.query_fixed(sm)
+    cs.create_gate("Combined add-mult", [qa * qsa + qb * qsb + qa * qb * qsm - (qc * qsc) + qsf * (qd * qe)])
+    qa, qp, qsp = cs.query_advice(a), cs.query_instance(p), cs.query_fixed(sp)
+    cs.create_gate("Public input", [qsp * (qa - qp)])
+    for col in (sf, e, d, p, sm, sa, sb, sc, sp):
+        cs.enable_equality(col)
+    if extra:
+        E = h.Expression
+        qa, qb, qf = cs.query_advice(a), cs.query_advice(b, 2), cs.query_fixed(sf, -1)
+        ch = cs.challenge_usable_after(0)
+        one, two, zero = E.constant(1), E.constant(2), E.constant(0)
+        cs.create_gate("extra", [qf * (qa * qa * two - qb * 7 + (-qa)) + zero * qa,
+                                 (qa + qb) * (qa + qb) * qf - qb * ch + qa * (O.R_MOD - 5),
+                                 -(E.constant(3)) + two * qb - (qa * qb - qf) * one,
+                                 (qa - zero) * (qb * 1) * (qf * 0 + qa)])
+        cs.lookup("l1", [(qb * ch + one, cs.query_fixed(sl))])
+    return cs
+
+
+@pytest.mark.parametrize("extra", [0, 1])
+def test_cpp_mirror_graph_evaluator(emu_lib_path, tmp_path, extra):
+    """GraphEvaluator / Evaluator::new of include/halo2_b200_plonk.hpp (plonk/evaluation.rs:224-277, 590-690): the
+    calculation list, constants, rotations and intermediate count of the custom-gates graph and of every lookup
+    graph equal the Python mirror's for the reference's plonk_api circuit (and with extra gates that reach the
+    constant folding, doubling, squaring, scaling and challenge branches); the library compiles each list."""
+    import struct
+
+    import halo2_pse_b200 as h
+    cli = _build("mirror_cli", emu_lib_path, "emu")
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    open(fin, "wb").write(b"")
+    r = _run(cli, "graph", fin, fout, extra)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = open(fout, "rb").read()
+    ev = h.Evaluator(_plonk_api_cs(bool(extra)))
+    off = 0
+    for g in [ev.custom_gates] + ev.lookups:
+        (nw,) = struct.unpack_from("<I", out, off)
+        words = np.frombuffer(out, dtype=np.uint32, count=nw, offset=off + 4)
+        off += 4 + 4 * nw
+        (nc,) = struct.unpack_from("<I", out, off)
+        consts = H.fr_dec(np.frombuffer(out, dtype=np.uint64, count=4 * nc, offset=off + 4).reshape(nc, 4))
+        off += 4 + 32 * nc
+        (nr,) = struct.unpack_from("<I", out, off)
+        rots = list(np.frombuffer(out, dtype=np.int32, count=nr, offset=off + 4))
+        off += 4 + 4 * nr
+        ni, ninstr = struct.unpack_from("<II", out, off)
+        off += 8
+        assert list(words) == list(g.encode())
+        assert consts == [c % O.R_MOD for c in g.constants] and rots == g.rotations and ni == g.num_intermediates
+        assert ninstr > 0
+    assert off == len(out)
+
+
 def _params_files(lib, tag, tmp_path, ctx, k):
     """ParamsKZG::read_custom / write_custom of the C++ mirror in the three SerdeFormats against the Python
     mirror's files (kzg/commitment.rs:142-244): the file written back is the file read, the commitments through
