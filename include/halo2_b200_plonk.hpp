@@ -6,6 +6,7 @@
 //   halo2_proofs::plonk::{ValueSource, Calculation, GraphEvaluator, Evaluator::new}   plonk/evaluation.rs:38-277, 525-690
 //   halo2_proofs::plonk::pinned_debug  = format!("{:?}", vk.pinned())     plonk.rs:192-230, circuit.rs:1399-1448
 //   halo2_proofs::plonk::vk_transcript_repr                               plonk.rs:192-203
+//   halo2_proofs::plonk::{keygen_pk, ProvingKey, permutation::Assembly}   plonk/keygen.rs:203-367, plonk/permutation/keygen.rs
 //
 // Bookkeeping only (no selectors, regions or floor planner: the prover reads the constraint system of the
 // verifying key, where selectors are already fixed columns, plonk/prover.rs:69-71).  tests/test_cpp_mirror.py
@@ -436,6 +437,130 @@ inline Fr vk_transcript_repr(const std::string& pinned) {
   uint8_t d[64];
   h.digest(d);
   return transcript::fr_from_bytes_wide(d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// keygen_vk + keygen_pk for a circuit handed over as its constraint system, its assigned fixed columns (what
+// Assembly::assign_fixed collects) and its copy constraints (Assembly::copy)
+//                       halo2_proofs/src/plonk/keygen.rs:203-367, plonk/permutation/keygen.rs:16-241, plonk.rs:171-305
+// Polynomials are host vectors, as in the reference's ProvingKey; every transform and commitment runs on the GPU
+// through the entry points of halo2_b200.hpp.
+// ---------------------------------------------------------------------------------------------
+struct CopyConstraint {
+  Column left_column;
+  size_t left_row;
+  Column right_column;
+  size_t right_row;
+};
+
+namespace permutation {
+/// Assembly: cycles of equal cells, merged smaller-into-larger                   plonk/permutation/keygen.rs:16-107
+class Assembly {
+ public:
+  Assembly(size_t n, const std::vector<Column>& columns) : n_(n), columns_(columns), mapping(n * columns.size()), aux_(mapping.size()), sizes_(mapping.size(), 1) {
+    for (size_t i = 0; i < mapping.size(); ++i) mapping[i] = aux_[i] = i;
+  }
+  void copy(const Column& lc, size_t lrow, const Column& rc, size_t rrow) {
+    const auto li = std::find(columns_.begin(), columns_.end(), lc), ri = std::find(columns_.begin(), columns_.end(), rc);
+    if (li == columns_.end() || ri == columns_.end()) throw Panic("Error::ColumnNotInPermutation (permutation/keygen.rs:55-62)");
+    if (lrow >= n_ || rrow >= n_) throw Panic("Error::BoundsFailure (permutation/keygen.rs:65-67)");
+    const size_t left = size_t(li - columns_.begin()) * n_ + lrow, right = size_t(ri - columns_.begin()) * n_ + rrow;
+    size_t left_cycle = aux_[left], right_cycle = aux_[right];
+    if (left_cycle == right_cycle) return;
+    if (sizes_[left_cycle] < sizes_[right_cycle]) std::swap(left_cycle, right_cycle);
+    sizes_[left_cycle] += sizes_[right_cycle];
+    for (size_t i = right_cycle;;) {
+      aux_[i] = left_cycle;
+      i = mapping[i];
+      if (i == right_cycle) break;
+    }
+    std::swap(mapping[left], mapping[right]);
+  }
+  std::vector<size_t> mapping;  // cell (column i, row j) as i * n + j  ->  the next cell of its cycle
+
+ private:
+  size_t n_;
+  std::vector<Column> columns_;
+  std::vector<size_t> aux_, sizes_;
+};
+}  // namespace permutation
+
+struct ProvingKey {  // plonk.rs:258-305 with the VerifyingKey inside it (:45-58)
+  ConstraintSystem cs;
+  std::shared_ptr<poly::EvaluationDomain> domain;
+  uint32_t k = 0;
+  size_t n = 0;
+  std::vector<G1Affine> fixed_commitments, permutation_commitments;
+  std::vector<poly::Polynomial<poly::LagrangeCoeff>> fixed_values, permutations;
+  std::vector<poly::Polynomial<poly::Coeff>> fixed_polys, permutation_polys;
+  std::vector<poly::Polynomial<poly::ExtendedLagrangeCoeff>> fixed_cosets, permutation_cosets;
+  poly::Polynomial<poly::ExtendedLagrangeCoeff> l0, l_last, l_active_row;
+  std::shared_ptr<Evaluator> ev;
+  std::string pinned;   // format!("{:?}", vk.pinned())
+  Fr transcript_repr;   // its hash, the first thing every transcript absorbs (plonk.rs:192-203)
+};
+
+inline ProvingKey keygen_pk(const poly::kzg::ParamsKZG& params, const ConstraintSystem& cs,
+                            const std::vector<std::vector<Fr>>& fixed_values, const std::vector<CopyConstraint>& copies) {
+  using namespace poly;
+  const size_t n = params.n();
+  if (n < cs.minimum_rows()) throw Panic("Error::not_enough_rows_available (keygen.rs:219-221)");
+  if (fixed_values.size() != cs.num_fixed_columns) throw Panic("one assignment per fixed column expected");
+  ProvingKey pk;
+  pk.cs = cs, pk.k = params.k(), pk.n = n;
+  pk.domain = std::make_shared<EvaluationDomain>(uint32_t(cs.degree()), params.k());
+  const EvaluationDomain& dom = *pk.domain;
+  // fixed columns (keygen.rs:237-258, 300-316)
+  for (const auto& col : fixed_values) {
+    if (col.size() > n) throw Panic("Error::not_enough_rows_available");
+    std::vector<Fr> v = col;
+    v.resize(n, Fr::zero());
+    pk.fixed_values.push_back(dom.lagrange_from_vec(std::move(v)));
+    pk.fixed_commitments.push_back(params.commit_lagrange(pk.fixed_values.back()).to_affine());
+    pk.fixed_polys.push_back(dom.lagrange_to_coeff(pk.fixed_values.back()));
+    pk.fixed_cosets.push_back(dom.coeff_to_extended(pk.fixed_polys.back()));
+  }
+  // permutation (permutation/keygen.rs:109-241): sigma_i[j] = delta^i' omega^j' for mapping[i][j] = (i', j')
+  const auto& pc = cs.permutation.columns;
+  permutation::Assembly assembly(n, pc);
+  for (const auto& c : copies) assembly.copy(c.left_column, c.left_row, c.right_column, c.right_row);
+  const Fr delta = Fr::from_raw(0x870e56bbe533e9a2ull, 0x5b5f898e5e963f25ull, 0x64ec26aad4c86e71ull, 0x09226b6e22c6f0caull);  // Fr::DELTA = 7^(2^28)
+  std::vector<Fr> omega_powers(n), deltaomega(pc.size() * n);
+  {
+    Fr cur = Fr::one();
+    for (size_t j = 0; j < n; ++j) omega_powers[j] = cur, cur *= dom.get_omega();
+    Fr d = Fr::one();
+    for (size_t i = 0; i < pc.size(); ++i, d *= delta)
+      for (size_t j = 0; j < n; ++j) deltaomega[i * n + j] = omega_powers[j] * d;
+  }
+  for (size_t i = 0; i < pc.size(); ++i) {
+    std::vector<Fr> sigma(n);
+    for (size_t j = 0; j < n; ++j) sigma[j] = deltaomega[assembly.mapping[i * n + j]];
+    pk.permutations.push_back(dom.lagrange_from_vec(std::move(sigma)));
+    pk.permutation_commitments.push_back(params.commit_lagrange(pk.permutations.back()).to_affine());
+    pk.permutation_polys.push_back(dom.lagrange_to_coeff(pk.permutations.back()));
+    pk.permutation_cosets.push_back(dom.coeff_to_extended(pk.permutation_polys.back()));
+  }
+  // l_0, l_blind, l_last, l_active_row (keygen.rs:322-350)
+  const size_t bf = cs.blinding_factors();
+  auto indicator = [&](size_t first, size_t last) {
+    auto v = dom.empty_lagrange();
+    for (size_t r = first; r < last; ++r) v[r] = Fr::one();
+    return dom.coeff_to_extended(dom.lagrange_to_coeff(v));
+  };
+  pk.l0 = indicator(0, 1);
+  const auto l_blind = indicator(n - bf, n);
+  pk.l_last = indicator(n - bf - 1, n - bf);
+  pk.l_active_row = dom.constant_extended(Fr::one()) - pk.l_last - l_blind;
+  pk.ev = std::make_shared<Evaluator>(cs);  // keygen.rs:353
+  std::vector<std::string> fc, pcm;
+  for (const auto& p : pk.fixed_commitments) fc.push_back(debug_point(p));
+  for (const auto& p : pk.permutation_commitments) pcm.push_back(debug_point(p));
+  pk.pinned = pinned_debug(cs, pk.k, dom.extended_k(), hex(dom.get_omega()), fc, pcm,
+                           "0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47",
+                           "0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001");
+  pk.transcript_repr = vk_transcript_repr(pk.pinned);
+  return pk;
 }
 
 }  // namespace plonk

@@ -64,6 +64,39 @@ static plonk::ConstraintSystem plonk_api_circuit() {
   return meta;
 }
 
+// benches/plonk.rs:203-270 -- MyCircuit (StandardPlonk: a, b, c; sm, sa, sb, sc) laid out by SimpleFloorPlanner:
+// iteration i puts raw_multiply on row 2i and raw_add on row 2i + 1, then copies a0 = a1 and b1 = c0
+struct BenchCircuit {
+  plonk::ConstraintSystem cs;
+  std::vector<std::vector<Fr>> fixed, advice;  // [sm, sa, sb, sc], [a, b, c]
+  std::vector<plonk::CopyConstraint> copies;
+};
+static BenchCircuit bench_circuit(uint32_t k, const Fr& a) {
+  using namespace plonk;
+  BenchCircuit bc;
+  ConstraintSystem& meta = bc.cs;
+  meta.set_minimum_degree(5);
+  const Column ca = meta.advice_column(), cb = meta.advice_column(), cc = meta.advice_column();
+  meta.enable_equality(ca), meta.enable_equality(cb), meta.enable_equality(cc);
+  const Column sm = meta.fixed_column(), sa = meta.fixed_column(), sb = meta.fixed_column(), sc = meta.fixed_column();
+  const Expression qa = meta.query_advice(ca), qb = meta.query_advice(cb), qc = meta.query_advice(cc);
+  const Expression qsa = meta.query_fixed(sa), qsb = meta.query_fixed(sb), qsc = meta.query_fixed(sc), qsm = meta.query_fixed(sm);
+  meta.create_gate("Combined add-mult", {qa * qsa + qb * qsb + qa * qb * qsm - (qc * qsc)});
+  const size_t iters = (size_t(1) << (k - 1)) - 3;
+  const Fr a2 = a * a, fin = a2 + a, one = Fr::one(), zero = Fr::zero();
+  bc.fixed.assign(4, {}), bc.advice.assign(3, {});
+  for (size_t i = 0; i < iters; ++i) {
+    // raw_multiply: (a, a, a^2), sa = sb = 0, sc = sm = 1;  raw_add: (a, a^2, a^2 + a), sa = sb = sc = 1, sm = 0
+    bc.advice[0].push_back(a), bc.advice[1].push_back(a), bc.advice[2].push_back(a2);
+    bc.fixed[0].push_back(one), bc.fixed[1].push_back(zero), bc.fixed[2].push_back(zero), bc.fixed[3].push_back(one);
+    bc.advice[0].push_back(a), bc.advice[1].push_back(a2), bc.advice[2].push_back(fin);
+    bc.fixed[0].push_back(zero), bc.fixed[1].push_back(one), bc.fixed[2].push_back(one), bc.fixed[3].push_back(one);
+    bc.copies.push_back({ca, 2 * i, ca, 2 * i + 1});
+    bc.copies.push_back({cb, 2 * i + 1, cc, 2 * i});
+  }
+  return bc;
+}
+
 static void dump_graph(std::ofstream& o, const plonk::GraphEvaluator& g) {
   auto u32 = [&](uint32_t v) { o.write(reinterpret_cast<const char*>(&v), 4); };
   const auto w = g.encode();
@@ -136,6 +169,14 @@ int main(int argc, char** argv) {
       std::ofstream o(argv[3], std::ios::binary);
       o.write(reinterpret_cast<const char*>(repr.l), 32);
       o << s;
+    } else if (op == "keygen") {  // args: k; in: s (Fr); out: transcript_repr (32 B) then the pinned verifying-key string
+      const Fr s = take<Fr>(in, 0, 1)[0];
+      const auto params = poly::kzg::ParamsKZG::setup(arg(0), s, false);
+      const BenchCircuit bc = bench_circuit(arg(0), Fr::from_raw(0xDEADBEEF));
+      const plonk::ProvingKey pk = plonk::keygen_pk(params, bc.cs, bc.fixed, bc.copies);
+      std::ofstream o(argv[3], std::ios::binary);
+      o.write(reinterpret_cast<const char*>(pk.transcript_repr.l), 32);
+      o << pk.pinned;
     } else if (op == "graph") {  // arg: 0 = the plonk_api circuit, 1 = with extra gates; out: custom_gates, then every lookup graph
       using namespace plonk;
       ConstraintSystem meta = plonk_api_circuit();

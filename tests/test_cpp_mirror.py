@@ -246,6 +246,22 @@ def test_cpp_mirror_graph_evaluator(emu_lib_path, tmp_path, extra):
     assert off == len(out)
 
 
+def test_cpp_mirror_keygen(emu_lib_path, tmp_path):
+    """keygen_pk of include/halo2_b200_plonk.hpp on the reference's bench circuit (benches/plonk.rs MyCircuit, built in
+    C++ with its copy constraints) at k = 5: the pinned verifying-key string -- fixed and permutation commitments,
+    omega, constraint system -- and its hash equal the big-integer oracle's keygen."""
+    from tests import plonk_cases as PC
+    cli = _build("mirror_cli", emu_lib_path, "emu")
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    open(fin, "wb").write(H.fr_enc([PC.S_TOXIC]).tobytes())
+    r = _run(cli, "keygen", fin, fout, 5)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = open(fout, "rb").read()
+    _, opk, _ = PC.oracle_bench_proof(5, 0xDEADBEEF, b"\x07" * 16)
+    assert out[32:].decode() == opk.debug
+    assert H.fr_dec(np.frombuffer(out[:32], dtype=np.uint64).reshape(1, 4))[0] == opk.transcript_repr
+
+
 def _params_files(lib, tag, tmp_path, ctx, k):
     """ParamsKZG::read_custom / write_custom of the C++ mirror in the three SerdeFormats against the Python
     mirror's files (kzg/commitment.rs:142-244): the file written back is the file read, the commitments through
