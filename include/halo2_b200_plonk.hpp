@@ -7,6 +7,7 @@
 //   halo2_proofs::plonk::pinned_debug  = format!("{:?}", vk.pinned())     plonk.rs:192-230, circuit.rs:1399-1448
 //   halo2_proofs::plonk::vk_transcript_repr                               plonk.rs:192-203
 //   halo2_proofs::plonk::{keygen_pk, ProvingKey, permutation::Assembly}   plonk/keygen.rs:203-367, plonk/permutation/keygen.rs
+//   halo2_proofs::plonk::create_proof (gates + permutation + instances)    plonk/prover.rs:37-651
 //
 // Bookkeeping only (no selectors, regions or floor planner: the prover reads the constraint system of the
 // verifying key, where selectors are already fixed columns, plonk/prover.rs:69-71).  tests/test_cpp_mirror.py
@@ -457,7 +458,8 @@ namespace permutation {
 /// Assembly: cycles of equal cells, merged smaller-into-larger                   plonk/permutation/keygen.rs:16-107
 class Assembly {
  public:
-  Assembly(size_t n, const std::vector<Column>& columns) : n_(n), columns_(columns), mapping(n * columns.size()), aux_(mapping.size()), sizes_(mapping.size(), 1) {
+  Assembly(size_t n, const std::vector<Column>& columns)
+      : mapping(n * columns.size()), n_(n), columns_(columns), aux_(mapping.size()), sizes_(mapping.size(), 1) {
     for (size_t i = 0; i < mapping.size(); ++i) mapping[i] = aux_[i] = i;
   }
   void copy(const Column& lc, size_t lrow, const Column& rc, size_t rrow) {
@@ -561,6 +563,268 @@ inline ProvingKey keygen_pk(const poly::kzg::ParamsKZG& params, const Constraint
                            "0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001");
   pk.transcript_repr = vk_transcript_repr(pk.pinned);
   return pk;
+}
+
+// ---------------------------------------------------------------------------------------------
+// create_proof<KZGCommitmentScheme<Bn256>, ProverGWC | ProverSHPLONK, Challenge255, R, Blake2bWrite>
+//                                                                          halo2_proofs/src/plonk/prover.rs:37-651
+// for constraint systems with gates, a permutation argument and instance columns in one phase (lookups and
+// challenge phases are carried by the Python mirror only, so far).  The witness is handed over as assigned advice
+// columns (the role of Circuit::synthesize through WitnessCollection, :143-285).  Host vectors between the steps,
+// as in the reference; every transform, commitment, grand product and the whole quotient evaluation run on the GPU.
+// ---------------------------------------------------------------------------------------------
+/// rand_xorshift::XorShiftRng::from_seed([u8; 16]); next_u64 = two next_u32, low word first
+class XorShiftRng {
+ public:
+  explicit XorShiftRng(const uint8_t seed[16]) {
+    std::memcpy(s_, seed, 16);
+    if (!(s_[0] | s_[1] | s_[2] | s_[3])) s_[0] = s_[1] = s_[2] = s_[3] = 0x0BAD5EED;
+  }
+  uint32_t next_u32() {
+    const uint32_t t = s_[0] ^ (s_[0] << 11);
+    s_[0] = s_[1], s_[1] = s_[2], s_[2] = s_[3];
+    s_[3] = s_[3] ^ (s_[3] >> 19) ^ (t ^ (t >> 8));
+    return s_[3];
+  }
+  uint64_t next_u64() {
+    const uint64_t lo = next_u32();
+    return (uint64_t(next_u32()) << 32) | lo;
+  }
+
+ private:
+  uint32_t s_[4];
+};
+
+/// Fr::random(rng): the 512-bit little-endian integer of eight next_u64 draws, mod r (halo2curves 0.3.1)
+template <class Rng>
+inline Fr fr_random(Rng& rng) {
+  uint8_t b[64];
+  for (int i = 0; i < 8; ++i) {
+    const uint64_t v = rng.next_u64();
+    std::memcpy(b + 8 * i, &v, 8);
+  }
+  return transcript::fr_from_bytes_wide(b);
+}
+
+namespace detail {
+class DeviceVec {  // a device-resident array of Fr on the calling thread's context
+ public:
+  explicit DeviceVec(size_t n) : ctx_(halo2_proofs::detail::backend().ctx), n_(n) {
+    halo2_proofs::detail::check(ctx_, h2b_device_alloc(ctx_, (n ? n : 1) * sizeof(Fr), &p_), "h2b_device_alloc");
+  }
+  explicit DeviceVec(const std::vector<Fr>& v) : DeviceVec(v.size()) {
+    if (!v.empty()) halo2_proofs::detail::check(ctx_, h2b_copy_h2d(ctx_, p_, v.data(), v.size() * sizeof(Fr)), "h2b_copy_h2d");
+  }
+  DeviceVec(const DeviceVec&) = delete;
+  DeviceVec& operator=(const DeviceVec&) = delete;
+  ~DeviceVec() { h2b_device_free(ctx_, p_); }
+  h2b_fr* ptr() const { return static_cast<h2b_fr*>(p_); }
+  void zero() { halo2_proofs::detail::check(ctx_, h2b_device_memset(ctx_, p_, 0, n_ * sizeof(Fr)), "h2b_device_memset"); }
+  std::vector<Fr> download() const {
+    std::vector<Fr> v(n_);
+    if (n_) halo2_proofs::detail::check(ctx_, h2b_copy_d2h(ctx_, v.data(), p_, n_ * sizeof(Fr)), "h2b_copy_d2h");
+    return v;
+  }
+
+ private:
+  h2b_ctx* ctx_;
+  void* p_ = nullptr;
+  size_t n_;
+};
+}  // namespace detail
+
+enum class Multiopen { GWC, SHPLONK };
+
+/// advice[i][c] / instances[i][c]: the assigned values of column c of circuit i (shorter than n: zero-padded)
+template <class Rng>
+inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& pk,
+                         const std::vector<std::vector<std::vector<Fr>>>& advice,
+                         const std::vector<std::vector<std::vector<Fr>>>& instances, Rng& rng,
+                         transcript::Blake2bWrite& transcript, Multiopen scheme = Multiopen::GWC) {
+  using namespace poly;
+  using detail::DeviceVec;
+  const ConstraintSystem& cs = pk.cs;
+  const EvaluationDomain& dom = *pk.domain;
+  h2b_ctx* ctx = halo2_proofs::detail::backend().ctx;
+  const size_t n = pk.n, bf = cs.blinding_factors(), ext = dom.extended_len();
+  if (!cs.lookups.empty() || cs.num_challenges) throw Panic("create_proof (C++ mirror): lookups and challenge phases are not carried yet");
+  if (advice.size() != instances.size()) throw Panic("one instance list per circuit");
+  for (const auto& inst : instances)
+    if (inst.size() != cs.num_instance_columns) throw Panic("Error::InvalidInstances (prover.rs:55-59)");
+  auto rot = [&](const Fr& v, int32_t r) { return dom.rotate_omega(v, Rotation{r}); };
+  auto eval = [](const Polynomial<Coeff>& p, const Fr& x) { return arithmetic::eval_polynomial(p.values, x); };
+
+  transcript.common_scalar(pk.transcript_repr);  // :62
+
+  // ---- instances (:79-138; QUERY_INSTANCE = false) ----
+  std::vector<std::vector<Polynomial<LagrangeCoeff>>> instance_values(instances.size());
+  std::vector<std::vector<Polynomial<Coeff>>> instance_polys(instances.size());
+  for (size_t ci = 0; ci < instances.size(); ++ci)
+    for (const auto& values : instances[ci]) {
+      if (values.size() > n - (bf + 1)) throw Panic("Error::InstanceTooLarge (prover.rs:93-95)");
+      for (const Fr& v : values) transcript.common_scalar(v);
+      std::vector<Fr> padded = values;
+      padded.resize(n, Fr::zero());
+      instance_values[ci].push_back(dom.lagrange_from_vec(padded));
+      instance_polys[ci].push_back(dom.lagrange_to_coeff(instance_values[ci].back()));
+    }
+
+  // ---- advice (:287-405) ----
+  const size_t unusable_rows_start = n - (bf + 1);
+  std::vector<std::vector<Polynomial<LagrangeCoeff>>> advice_values(advice.size());
+  for (size_t ci = 0; ci < advice.size(); ++ci) {
+    if (advice[ci].size() != cs.num_advice_columns) throw Panic("one assignment per advice column expected");
+    for (const auto& col : advice[ci]) {  // assigned rows, zero padding, then the blinding factors (:364-368)
+      if (col.size() > unusable_rows_start) throw Panic("Error::not_enough_rows_available (prover.rs:228-230)");
+      std::vector<Fr> v = col;
+      v.resize(unusable_rows_start, Fr::zero());
+      for (size_t r = unusable_rows_start; r < n; ++r) v.push_back(fr_random(rng));
+      advice_values[ci].push_back(dom.lagrange_from_vec(std::move(v)));
+    }
+    for (size_t c = 0; c < advice[ci].size(); ++c) fr_random(rng);  // Blind(Scalar::random(rng)), ignored by KZG (:371-374)
+    for (const auto& v : advice_values[ci]) transcript.write_point(params.commit_lagrange(v).to_affine());  // :375-392
+  }
+  const Fr theta = transcript.squeeze_challenge_scalar();  // :410
+  const Fr beta = transcript.squeeze_challenge_scalar();   // :440
+  const Fr gamma = transcript.squeeze_challenge_scalar();  // :443
+
+  // ---- permutation argument (:446-463, permutation/prover.rs:40-190) ----
+  struct Set {
+    Polynomial<Coeff> poly;
+    Polynomial<ExtendedLagrangeCoeff> coset;
+  };
+  std::vector<std::vector<Set>> permutations(advice.size());
+  const auto& pcols = cs.permutation.columns;
+  const size_t chunk_len = cs.degree() - 2;
+  for (size_t ci = 0; ci < advice.size(); ++ci) {
+    Fr last_z = Fr::one();
+    for (size_t s0 = 0; s0 < pcols.size(); s0 += chunk_len) {
+      const size_t m = std::min(chunk_len, pcols.size() - s0);
+      std::vector<std::unique_ptr<DeviceVec>> keep;
+      std::vector<const h2b_fr*> vals, sigmas;
+      for (size_t j = 0; j < m; ++j) {
+        const Column& c = pcols[s0 + j];
+        const std::vector<Fr>& column = c.column_type == Any::Advice ? advice_values[ci][c.index].values
+                                        : c.column_type == Any::Fixed ? pk.fixed_values[c.index].values
+                                                                      : instance_values[ci][c.index].values;
+        keep.emplace_back(new DeviceVec(column)), vals.push_back(keep.back()->ptr());
+        keep.emplace_back(new DeviceVec(pk.permutations[s0 + j].values)), sigmas.push_back(keep.back()->ptr());
+      }
+      DeviceVec frac(n), zdev(n);
+      halo2_proofs::detail::check(ctx, h2b_permutation_fractions(dom.raw(), vals.data(), sigmas.data(), uint32_t(m), uint32_t(s0), &beta, &gamma, frac.ptr()),
+                                  "h2b_permutation_fractions");
+      halo2_proofs::detail::check(ctx, h2b_running_product(ctx, frac.ptr(), H2B_DEVICE, n, &last_z, zdev.ptr()), "h2b_running_product");  // :150-158
+      std::vector<Fr> z = zdev.download();
+      for (size_t r = n - bf; r < n; ++r) z[r] = fr_random(rng);  // :161-163
+      last_z = z[n - (bf + 1)];                                   // :165
+      fr_random(rng);                                             // Blind (:167)
+      const auto zl = dom.lagrange_from_vec(std::move(z));
+      transcript.write_point(params.commit_lagrange(zl).to_affine());
+      Set st;
+      st.poly = dom.lagrange_to_coeff(zl);
+      st.coset = dom.coeff_to_extended(st.poly);
+      permutations[ci].push_back(std::move(st));
+    }
+  }
+
+  // ---- vanishing argument: random polynomial (vanishing/prover.rs:36-66) ----
+  Polynomial<Coeff> random_poly = dom.empty_coeff();
+  for (auto& c : random_poly) c = fr_random(rng);
+  fr_random(rng);  // random_blind
+  transcript.write_point(params.commit(random_poly).to_affine());
+
+  const Fr y = transcript.squeeze_challenge_scalar();  // :478
+
+  std::vector<std::vector<Polynomial<Coeff>>> advice_polys(advice.size());  // :481-499
+  for (size_t ci = 0; ci < advice.size(); ++ci)
+    for (const auto& v : advice_values[ci]) advice_polys[ci].push_back(dom.lagrange_to_coeff(v));
+
+  // ---- h(X): Evaluator::evaluate_h on the device (:502-520, evaluation.rs:280-522) ----
+  std::vector<Fr> h_ext;
+  {
+    DeviceVec values(ext);
+    values.zero();
+    auto upload_all = [](const std::vector<Polynomial<ExtendedLagrangeCoeff>>& polys, std::vector<std::unique_ptr<DeviceVec>>& keep,
+                         std::vector<const h2b_fr*>& ptrs) {
+      for (const auto& p : polys) keep.emplace_back(new DeviceVec(p.values)), ptrs.push_back(keep.back()->ptr());
+    };
+    std::vector<std::unique_ptr<DeviceVec>> fixed_keep, sigma_keep;
+    std::vector<const h2b_fr*> fixed_ptrs, sigma_ptrs;
+    upload_all(pk.fixed_cosets, fixed_keep, fixed_ptrs);
+    upload_all(pk.permutation_cosets, sigma_keep, sigma_ptrs);
+    const DeviceVec l0(pk.l0.values), l_last(pk.l_last.values), l_active_row(pk.l_active_row.values);
+    const auto graph = pk.ev->custom_gates.compile();
+    std::vector<uint32_t> ctype, cidx;
+    for (const auto& c : pcols) ctype.push_back(uint32_t(c.column_type)), cidx.push_back(c.index);
+    for (size_t ci = 0; ci < advice.size(); ++ci) {
+      std::vector<Polynomial<ExtendedLagrangeCoeff>> adv, inst, zs;
+      for (const auto& p : advice_polys[ci]) adv.push_back(dom.coeff_to_extended(p));    // :305-323
+      for (const auto& p : instance_polys[ci]) inst.push_back(dom.coeff_to_extended(p));
+      for (const auto& st : permutations[ci]) zs.push_back(st.coset);
+      std::vector<std::unique_ptr<DeviceVec>> keep;
+      std::vector<const h2b_fr*> adv_ptrs, inst_ptrs, z_ptrs;
+      upload_all(adv, keep, adv_ptrs), upload_all(inst, keep, inst_ptrs), upload_all(zs, keep, z_ptrs);
+      h2b_eval_columns cols;
+      std::memset(&cols, 0, sizeof cols);
+      cols.fixed = fixed_ptrs.data(), cols.n_fixed = uint32_t(fixed_ptrs.size());
+      cols.advice = adv_ptrs.data(), cols.n_advice = uint32_t(adv_ptrs.size());
+      cols.instance = inst_ptrs.data(), cols.n_instance = uint32_t(inst_ptrs.size());
+      cols.beta = beta, cols.gamma = gamma, cols.theta = theta, cols.y = y;
+      halo2_proofs::detail::check(ctx, h2b_evaluate_h_gates(dom.raw(), graph.get(), &cols, values.ptr()), "h2b_evaluate_h_gates");
+      if (!z_ptrs.empty())
+        halo2_proofs::detail::check(ctx, h2b_evaluate_h_permutation(dom.raw(), &cols, ctype.data(), cidx.data(), uint32_t(pcols.size()), sigma_ptrs.data(),
+                                                                    z_ptrs.data(), uint32_t(z_ptrs.size()), uint32_t(chunk_len), uint32_t(bf), l0.ptr(),
+                                                                    l_last.ptr(), l_active_row.ptr(), values.ptr()),
+                                    "h2b_evaluate_h_permutation");
+    }
+    h_ext = values.download();
+  }
+  // vanishing.construct (vanishing/prover.rs:69-121): divide by t(X), back to coefficients, n-sized pieces
+  const std::vector<Fr> h_coeff = dom.divide_by_vanishing_poly_then_extended_to_coeff(Polynomial<ExtendedLagrangeCoeff>{std::move(h_ext)});
+  const size_t n_pieces = h_coeff.size() / n;
+  for (size_t i = 0; i < n_pieces; ++i) fr_random(rng);  // h_blinds
+  std::vector<Polynomial<Coeff>> pieces;
+  for (size_t i = 0; i < n_pieces; ++i) {
+    pieces.push_back({std::vector<Fr>(h_coeff.begin() + i * n, h_coeff.begin() + (i + 1) * n)});
+    transcript.write_point(params.commit(pieces.back()).to_affine());
+  }
+
+  const Fr x = transcript.squeeze_challenge_scalar();  // :525
+  const Fr xn = x.pow_vartime(n);
+
+  // ---- evaluations (:548-581) ----
+  for (size_t ci = 0; ci < advice.size(); ++ci)
+    for (const auto& q : cs.advice_queries) transcript.write_scalar(eval(advice_polys[ci][q.first.index], rot(x, q.second)));
+  for (const auto& q : cs.fixed_queries) transcript.write_scalar(eval(pk.fixed_polys[q.first.index], rot(x, q.second)));
+  // vanishing.evaluate (vanishing/prover.rs:124-152): h_poly = fold(pieces.rev(), acc * xn + piece)
+  Polynomial<Coeff> h_poly = dom.empty_coeff();
+  for (size_t i = n_pieces; i-- > 0;) h_poly = (h_poly * xn) + pieces[i];
+  transcript.write_scalar(eval(random_poly, x));
+  for (const auto& p : pk.permutation_polys) transcript.write_scalar(eval(p, x));  // permutation/prover.rs:208-219
+  const Fr x_next = rot(x, 1), x_last = rot(x, -int32_t(bf + 1));
+  for (const auto& sets : permutations)                                           // permutation/prover.rs:222-266
+    for (size_t si = 0; si < sets.size(); ++si) {
+      transcript.write_scalar(eval(sets[si].poly, x));
+      transcript.write_scalar(eval(sets[si].poly, x_next));
+      if (si + 1 < sets.size()) transcript.write_scalar(eval(sets[si].poly, x_last));
+    }
+
+  // ---- the opening queries in the reference's order (:596-645) ----
+  std::vector<ProverQuery> queries;
+  for (size_t ci = 0; ci < advice.size(); ++ci) {
+    for (const auto& q : cs.advice_queries) queries.push_back({rot(x, q.second), &advice_polys[ci][q.first.index]});
+    const auto& sets = permutations[ci];
+    for (const auto& st : sets) queries.push_back({x, &st.poly}), queries.push_back({x_next, &st.poly});
+    for (size_t si = sets.size(); si-- > 1;) queries.push_back({x_last, &sets[si - 1].poly});  // .rev().skip(1)
+  }
+  for (const auto& q : cs.fixed_queries) queries.push_back({rot(x, q.second), &pk.fixed_polys[q.first.index]});
+  for (const auto& p : pk.permutation_polys) queries.push_back({x, &p});
+  queries.push_back({x, &h_poly});
+  queries.push_back({x, &random_poly});
+  if (scheme == Multiopen::GWC)
+    kzg::multiopen::ProverGWC(params).create_proof(transcript, queries);
+  else
+    kzg::multiopen::ProverSHPLONK(params).create_proof(transcript, queries);
 }
 
 }  // namespace plonk

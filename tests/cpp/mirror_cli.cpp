@@ -177,6 +177,16 @@ int main(int argc, char** argv) {
       std::ofstream o(argv[3], std::ios::binary);
       o.write(reinterpret_cast<const char*>(pk.transcript_repr.l), 32);
       o << pk.pinned;
+    } else if (op == "prove") {  // args: k scheme(0 GWC, 1 SHPLONK); in: s (Fr), rng seed (16 B); out: proof bytes
+      const Fr s = take<Fr>(in, 0, 1)[0];
+      const auto seed = take<uint8_t>(in, 32, 16);
+      const auto params = poly::kzg::ParamsKZG::setup(arg(0), s, false);
+      const BenchCircuit bc = bench_circuit(arg(0), Fr::from_raw(0xDEADBEEF));
+      const plonk::ProvingKey pk = plonk::keygen_pk(params, bc.cs, bc.fixed, bc.copies);
+      plonk::XorShiftRng rng(seed.data());
+      transcript::Blake2bWrite t;
+      plonk::create_proof(params, pk, {bc.advice}, {{}}, rng, t, arg(1) ? plonk::Multiopen::SHPLONK : plonk::Multiopen::GWC);
+      spit(argv[3], t.finalize().data(), t.finalize().size());
     } else if (op == "graph") {  // arg: 0 = the plonk_api circuit, 1 = with extra gates; out: custom_gates, then every lookup graph
       using namespace plonk;
       ConstraintSystem meta = plonk_api_circuit();

@@ -262,6 +262,58 @@ def test_cpp_mirror_keygen(emu_lib_path, tmp_path):
     assert H.fr_dec(np.frombuffer(out[:32], dtype=np.uint64).reshape(1, 4))[0] == opk.transcript_repr
 
 
+def _cpp_proof(lib, tag, tmp_path, k, scheme, seed):
+    from tests import plonk_cases as PC
+    cli = _build("mirror_cli", lib, tag)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    open(fin, "wb").write(H.fr_enc([PC.S_TOXIC]).tobytes() + seed)
+    r = _run(cli, "prove", fin, fout, k, scheme)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return open(fout, "rb").read()
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_create_proof_gpu(tmp_path):
+    """The C++ keygen_pk + create_proof against libhalo2b200.so on cuda:0: proof bytes of the bench circuit equal the
+    big-integer oracle's at k = 5 (GWC); a k = 9 proof is accepted by the restated reference verifier."""
+    from oracle import prover as OV
+    from tests import plonk_cases as PC
+    seed = b"\x07" * 16
+    lib = build.build_product()
+    oparams, opk, want = PC.oracle_bench_proof(5, 0xDEADBEEF, seed)
+    assert _cpp_proof(lib, "gpu", tmp_path, 5, 0, seed) == want
+    oparams, opk, want = PC.oracle_bench_proof(9, 0xDEADBEEF, seed)
+    got = _cpp_proof(lib, "gpu", tmp_path, 9, 0, seed)
+    assert got == want and OV.verify_proof(oparams, PC.S_TOXIC, opk, [[]], got)
+
+
+@pytest.mark.parametrize("scheme", [0, 1])
+def test_cpp_mirror_create_proof_bytes_equal_the_oracle(emu_lib_path, tmp_path, scheme):
+    """keygen_pk + create_proof of include/halo2_b200_plonk.hpp on the reference's bench circuit at k = 5 with a
+    seeded XorShiftRng: the proof bytes equal the big-integer oracle's (GWC), resp. the Python mirror's SHPLONK
+    proof (itself equal to the oracle's, tests/test_emulator_plonk.py), and the oracle's verifier accepts them."""
+    from oracle import prover as OV
+    from tests import plonk_cases as PC
+    seed = b"\x07" * 16
+    cli = _build("mirror_cli", emu_lib_path, "emu")
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    open(fin, "wb").write(H.fr_enc([PC.S_TOXIC]).tobytes() + seed)
+    r = _run(cli, "prove", fin, fout, 5, scheme)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = open(fout, "rb").read()
+    oparams, opk, want = PC.oracle_bench_proof(5, 0xDEADBEEF, seed)
+    if scheme == 0:
+        assert got == want, [i for i in range(0, len(want), 32) if got[i:i + 32] != want[i:i + 32]][:4]
+        assert OV.verify_proof(oparams, PC.S_TOXIC, opk, [[]], got)
+    else:
+        t = OV.Blake2bWrite()
+        _, advice, _ = PC.bench_circuit(5, 0xDEADBEEF)
+        OV.create_proof(oparams, opk, [lambda phase, ch: dict(enumerate(advice))], [[]], OV.XorShiftRng(seed), t,
+                        multiopen="shplonk")
+        assert got == t.finalize()
+        assert OV.verify_proof(oparams, PC.S_TOXIC, opk, [[]], got, multiopen="shplonk")
+
+
 def _params_files(lib, tag, tmp_path, ctx, k):
     """ParamsKZG::read_custom / write_custom of the C++ mirror in the three SerdeFormats against the Python
     mirror's files (kzg/commitment.rs:142-244): the file written back is the file read, the commitments through
