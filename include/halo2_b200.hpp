@@ -89,7 +89,7 @@ struct Field : h2b_fr {
     std::memset(&z, 0, sizeof z);
     return z;
   }
-  static Field from_raw(uint64_t l0, uint64_t l1 = 0, uint64_t l2 = 0, uint64_t l3 = 0) {  // canonical limbs -> Montgomery
+  static Field from_raw(uint64_t l0, uint64_t l1 = 0, uint64_t l2 = 0, uint64_t l3 = 0) {  // canonical limbs (a value < p) -> Montgomery
     Field c, r;
     c.l[0] = l0, c.l[1] = l1, c.l[2] = l2, c.l[3] = l3;
     detail::host_op(FIELD, 4, &c, nullptr, &r);
@@ -633,10 +633,12 @@ class Blake2b {  // digest_size 64, no key, personalisation = 16 bytes
 
 /// Fr::from_bytes_wide: the 512-bit little-endian integer mod r (halo2curves 0.3.1)    transcript.rs:501
 inline Fr fr_from_bytes_wide(const uint8_t b[64]) {
+  // four 128-bit digits: each is a canonical value (< r), which is what from_raw takes -- a raw 256-bit half can
+  // exceed r five times over, outside the range the Montgomery conversion is built for
   uint64_t w[8];
   std::memcpy(w, b, 64);
-  const Fr two256 = Fr::from_raw(0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full);  // 2^256 mod r
-  return Fr::from_raw(w[0], w[1], w[2], w[3]) + Fr::from_raw(w[4], w[5], w[6], w[7]) * two256;
+  const Fr t128 = Fr::from_raw(0, 0, 1, 0), t256 = t128.square(), t384 = t256 * t128;
+  return Fr::from_raw(w[0], w[1]) + Fr::from_raw(w[2], w[3]) * t128 + Fr::from_raw(w[4], w[5]) * t256 + Fr::from_raw(w[6], w[7]) * t384;
 }
 
 class Blake2bWrite {

@@ -187,6 +187,12 @@ int main(int argc, char** argv) {
       transcript::Blake2bWrite t;
       plonk::create_proof(params, pk, {bc.advice}, {{}}, rng, t, arg(1) ? plonk::Multiopen::SHPLONK : plonk::Multiopen::GWC);
       spit(argv[3], t.finalize().data(), t.finalize().size());
+    } else if (op == "rng") {  // in: 16-byte seed; out: arg(0) draws of Fr::random from XorShiftRng
+      const auto seed = take<uint8_t>(in, 0, 16);
+      plonk::XorShiftRng rng(seed.data());
+      std::vector<Fr> v(arg(0));
+      for (auto& x : v) x = plonk::fr_random(rng);
+      spit(argv[3], v.data(), v.size() * 32);
     } else if (op == "graph") {  // arg: 0 = the plonk_api circuit, 1 = with extra gates; out: custom_gates, then every lookup graph
       using namespace plonk;
       ConstraintSystem meta = plonk_api_circuit();

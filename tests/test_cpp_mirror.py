@@ -275,39 +275,53 @@ def _cpp_proof(lib, tag, tmp_path, k, scheme, seed):
 @pytest.mark.gpu
 def test_cpp_mirror_create_proof_gpu(tmp_path):
     """The C++ keygen_pk + create_proof against libhalo2b200.so on cuda:0: proof bytes of the bench circuit equal the
-    big-integer oracle's at k = 5 (GWC); a k = 9 proof is accepted by the restated reference verifier."""
+    big-integer oracle's at k = 5 (GWC) and k = 8 (SHPLONK), and the restated reference verifier accepts them."""
     from oracle import prover as OV
     from tests import plonk_cases as PC
     seed = b"\x07" * 16
     lib = build.build_product()
     oparams, opk, want = PC.oracle_bench_proof(5, 0xDEADBEEF, seed)
     assert _cpp_proof(lib, "gpu", tmp_path, 5, 0, seed) == want
-    oparams, opk, want = PC.oracle_bench_proof(9, 0xDEADBEEF, seed)
-    got = _cpp_proof(lib, "gpu", tmp_path, 9, 0, seed)
-    assert got == want and OV.verify_proof(oparams, PC.S_TOXIC, opk, [[]], got)
+    oparams, opk, _ = PC.oracle_bench_proof(8, 0xDEADBEEF, seed)
+    _, advice, _ = PC.bench_circuit(8, 0xDEADBEEF)
+    t = OV.Blake2bWrite()
+    OV.create_proof(oparams, opk, [lambda phase, ch: dict(enumerate(advice))], [[]], OV.XorShiftRng(seed), t,
+                    multiopen="shplonk")
+    got = _cpp_proof(lib, "gpu", tmp_path, 8, 1, seed)
+    assert got == t.finalize() and OV.verify_proof(oparams, PC.S_TOXIC, opk, [[]], got, multiopen="shplonk")
 
 
+def test_cpp_mirror_fr_random_stream(emu_lib_path, tmp_path):
+    """XorShiftRng + Fr::random (from_bytes_wide) of the C++ mirror: 5000 draws equal the Python mirror's -- a raw
+    256-bit half of the wide integer may exceed r five times over and must not go through from_raw as it is."""
+    from halo2_pse_b200.prover import XorShiftRng, fr_random
+    cli = _build("mirror_cli", emu_lib_path, "emu")
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    seed = bytes(range(1, 17))
+    open(fin, "wb").write(seed)
+    r = _run(cli, "rng", fin, fout, 5000)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rng = XorShiftRng(seed)
+    assert H.fr_dec(np.fromfile(fout, dtype=np.uint64).reshape(-1, 4)) == [fr_random(rng) for _ in range(5000)]
+
+
+@pytest.mark.parametrize("k", [5, 7])
 @pytest.mark.parametrize("scheme", [0, 1])
-def test_cpp_mirror_create_proof_bytes_equal_the_oracle(emu_lib_path, tmp_path, scheme):
+def test_cpp_mirror_create_proof_bytes_equal_the_oracle(emu_lib_path, tmp_path, scheme, k):
     """keygen_pk + create_proof of include/halo2_b200_plonk.hpp on the reference's bench circuit at k = 5 with a
     seeded XorShiftRng: the proof bytes equal the big-integer oracle's (GWC), resp. the Python mirror's SHPLONK
     proof (itself equal to the oracle's, tests/test_emulator_plonk.py), and the oracle's verifier accepts them."""
     from oracle import prover as OV
     from tests import plonk_cases as PC
     seed = b"\x07" * 16
-    cli = _build("mirror_cli", emu_lib_path, "emu")
-    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
-    open(fin, "wb").write(H.fr_enc([PC.S_TOXIC]).tobytes() + seed)
-    r = _run(cli, "prove", fin, fout, 5, scheme)
-    assert r.returncode == 0, r.stdout + r.stderr
-    got = open(fout, "rb").read()
-    oparams, opk, want = PC.oracle_bench_proof(5, 0xDEADBEEF, seed)
+    got = _cpp_proof(emu_lib_path, "emu", tmp_path, k, scheme, seed)
+    oparams, opk, want = PC.oracle_bench_proof(k, 0xDEADBEEF, seed)
     if scheme == 0:
         assert got == want, [i for i in range(0, len(want), 32) if got[i:i + 32] != want[i:i + 32]][:4]
         assert OV.verify_proof(oparams, PC.S_TOXIC, opk, [[]], got)
     else:
         t = OV.Blake2bWrite()
-        _, advice, _ = PC.bench_circuit(5, 0xDEADBEEF)
+        _, advice, _ = PC.bench_circuit(k, 0xDEADBEEF)
         OV.create_proof(oparams, opk, [lambda phase, ch: dict(enumerate(advice))], [[]], OV.XorShiftRng(seed), t,
                         multiopen="shplonk")
         assert got == t.finalize()
