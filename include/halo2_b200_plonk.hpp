@@ -498,6 +498,7 @@ struct ProvingKey {  // plonk.rs:258-305 with the VerifyingKey inside it (:45-58
   std::vector<poly::Polynomial<poly::ExtendedLagrangeCoeff>> fixed_cosets, permutation_cosets;
   poly::Polynomial<poly::ExtendedLagrangeCoeff> l0, l_last, l_active_row;
   std::shared_ptr<Evaluator> ev;
+  std::vector<std::pair<GraphEvaluator, GraphEvaluator>> lookup_compress;  // theta-compression of (input, table) expressions
   std::string pinned;   // format!("{:?}", vk.pinned())
   Fr transcript_repr;   // its hash, the first thing every transcript absorbs (plonk.rs:192-203)
 };
@@ -555,6 +556,16 @@ inline ProvingKey keygen_pk(const poly::kzg::ParamsKZG& params, const Constraint
   pk.l_last = indicator(n - bf - 1, n - bf);
   pk.l_active_row = dom.constant_extended(Fr::one()) - pk.l_last - l_blind;
   pk.ev = std::make_shared<Evaluator>(cs);  // keygen.rs:353
+  for (const auto& lk : cs.lookups) {       // compression over the Lagrange rows (lookup/prover.rs:82-104), as graphs
+    auto compress = [](const std::vector<Expression>& exprs) {
+      GraphEvaluator g;
+      Calculation h{Calculation::Horner, {{ValueSource::Constant, 0, 0}, {ValueSource::Theta, 0, 0}}};
+      for (const auto& e : exprs) h.src.push_back(g.add_expression(e));
+      g.add_calculation(h);
+      return g;
+    };
+    pk.lookup_compress.push_back({compress(lk.input_expressions), compress(lk.table_expressions)});
+  }
   std::vector<std::string> fc, pcm;
   for (const auto& p : pk.fixed_commitments) fc.push_back(debug_point(p));
   for (const auto& p : pk.permutation_commitments) pcm.push_back(debug_point(p));
@@ -568,8 +579,8 @@ inline ProvingKey keygen_pk(const poly::kzg::ParamsKZG& params, const Constraint
 // ---------------------------------------------------------------------------------------------
 // create_proof<KZGCommitmentScheme<Bn256>, ProverGWC | ProverSHPLONK, Challenge255, R, Blake2bWrite>
 //                                                                          halo2_proofs/src/plonk/prover.rs:37-651
-// for constraint systems with gates, a permutation argument and instance columns in one phase (lookups and
-// challenge phases are carried by the Python mirror only, so far).  The witness is handed over as assigned advice
+// for constraint systems with gates, lookups, a permutation argument and instance columns in one phase (challenge
+// phases are carried by the Python mirror only, so far).  The witness is handed over as assigned advice
 // columns (the role of Circuit::synthesize through WitnessCollection, :143-285).  Host vectors between the steps,
 // as in the reference; every transform, commitment, grand product and the whole quotient evaluation run on the GPU.
 // ---------------------------------------------------------------------------------------------
@@ -647,7 +658,7 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
   const EvaluationDomain& dom = *pk.domain;
   h2b_ctx* ctx = halo2_proofs::detail::backend().ctx;
   const size_t n = pk.n, bf = cs.blinding_factors(), ext = dom.extended_len();
-  if (!cs.lookups.empty() || cs.num_challenges) throw Panic("create_proof (C++ mirror): lookups and challenge phases are not carried yet");
+  if (cs.num_challenges) throw Panic("create_proof (C++ mirror): challenge phases are not carried yet");
   if (advice.size() != instances.size()) throw Panic("one instance list per circuit");
   for (const auto& inst : instances)
     if (inst.size() != cs.num_instance_columns) throw Panic("Error::InvalidInstances (prover.rs:55-59)");
@@ -685,6 +696,48 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
     for (const auto& v : advice_values[ci]) transcript.write_point(params.commit_lagrange(v).to_affine());  // :375-392
   }
   const Fr theta = transcript.squeeze_challenge_scalar();  // :410
+
+  // ---- lookups: permuted columns (:412-437, lookup/prover.rs:55-140) ----
+  struct Lookup {
+    std::vector<Fr> compressed_input, compressed_table, permuted_input, permuted_table;  // Lagrange
+    Polynomial<Coeff> permuted_input_poly, permuted_table_poly, product_poly;
+  };
+  std::vector<std::vector<Lookup>> lookups(advice.size());
+  for (size_t ci = 0; ci < advice.size() && !cs.lookups.empty(); ++ci) {
+    std::vector<std::unique_ptr<DeviceVec>> keep;
+    std::vector<const h2b_fr*> fixed_ptrs, adv_ptrs, inst_ptrs;
+    for (const auto& p : pk.fixed_values) keep.emplace_back(new DeviceVec(p.values)), fixed_ptrs.push_back(keep.back()->ptr());
+    for (const auto& p : advice_values[ci]) keep.emplace_back(new DeviceVec(p.values)), adv_ptrs.push_back(keep.back()->ptr());
+    for (const auto& p : instance_values[ci]) keep.emplace_back(new DeviceVec(p.values)), inst_ptrs.push_back(keep.back()->ptr());
+    h2b_eval_columns cols;
+    std::memset(&cols, 0, sizeof cols);
+    cols.fixed = fixed_ptrs.data(), cols.n_fixed = uint32_t(fixed_ptrs.size());
+    cols.advice = adv_ptrs.data(), cols.n_advice = uint32_t(adv_ptrs.size());
+    cols.instance = inst_ptrs.data(), cols.n_instance = uint32_t(inst_ptrs.size());
+    cols.theta = theta;
+    for (const auto& graphs : pk.lookup_compress) {
+      Lookup lk;
+      DeviceVec cin(n), ctab(n), pin(n), ptab(n);
+      cin.zero(), ctab.zero();
+      halo2_proofs::detail::check(ctx, h2b_graph_evaluate_lagrange(dom.raw(), graphs.first.compile().get(), &cols, cin.ptr()), "h2b_graph_evaluate_lagrange");
+      halo2_proofs::detail::check(ctx, h2b_graph_evaluate_lagrange(dom.raw(), graphs.second.compile().get(), &cols, ctab.ptr()), "h2b_graph_evaluate_lagrange");
+      const int rc = h2b_lookup_permute(ctx, cin.ptr(), ctab.ptr(), unusable_rows_start, pin.ptr(), ptab.ptr());
+      if (rc == H2B_ERR_CONSTRAINT) throw Panic("Error::ConstraintSystemFailure: a lookup input is not in the table (lookup/prover.rs:425-433)");
+      halo2_proofs::detail::check(ctx, rc, "h2b_lookup_permute");
+      lk.compressed_input = cin.download(), lk.compressed_table = ctab.download();
+      lk.permuted_input = pin.download(), lk.permuted_table = ptab.download();
+      for (auto* v : {&lk.permuted_input, &lk.permuted_table})  // blinding rows (:447-449)
+        for (size_t r = unusable_rows_start; r < n; ++r) (*v)[r] = fr_random(rng);
+      lk.permuted_input_poly = dom.lagrange_to_coeff(dom.lagrange_from_vec(lk.permuted_input));  // commit_values (:114-125)
+      fr_random(rng);                                                                          // Blind
+      lk.permuted_table_poly = dom.lagrange_to_coeff(dom.lagrange_from_vec(lk.permuted_table));
+      fr_random(rng);
+      transcript.write_point(params.commit_lagrange(dom.lagrange_from_vec(lk.permuted_input)).to_affine());
+      transcript.write_point(params.commit_lagrange(dom.lagrange_from_vec(lk.permuted_table)).to_affine());
+      lookups[ci].push_back(std::move(lk));
+    }
+  }
+
   const Fr beta = transcript.squeeze_challenge_scalar();   // :440
   const Fr gamma = transcript.squeeze_challenge_scalar();  // :443
 
@@ -726,6 +779,23 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
       permutations[ci].push_back(std::move(st));
     }
   }
+
+  // ---- lookups: grand products (:466-475, lookup/prover.rs:146-250) ----
+  for (auto& lks : lookups)
+    for (auto& lk : lks) {
+      const DeviceVec pin(lk.permuted_input), ptab(lk.permuted_table), cin(lk.compressed_input), ctab(lk.compressed_table);
+      DeviceVec frac(n), zdev(n);
+      halo2_proofs::detail::check(ctx, h2b_lookup_product_fractions(ctx, pin.ptr(), ptab.ptr(), cin.ptr(), ctab.ptr(), &beta, &gamma, n, frac.ptr()),
+                                  "h2b_lookup_product_fractions");
+      const Fr one = Fr::one();
+      halo2_proofs::detail::check(ctx, h2b_running_product(ctx, frac.ptr(), H2B_DEVICE, n, &one, zdev.ptr()), "h2b_running_product");  // :201-209
+      std::vector<Fr> z = zdev.download();
+      for (size_t r = n - bf; r < n; ++r) z[r] = fr_random(rng);
+      fr_random(rng);  // product_blind
+      const auto zl = dom.lagrange_from_vec(std::move(z));
+      transcript.write_point(params.commit_lagrange(zl).to_affine());
+      lk.product_poly = dom.lagrange_to_coeff(zl);
+    }
 
   // ---- vanishing argument: random polynomial (vanishing/prover.rs:36-66) ----
   Polynomial<Coeff> random_poly = dom.empty_coeff();
@@ -776,6 +846,14 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
                                                                     z_ptrs.data(), uint32_t(z_ptrs.size()), uint32_t(chunk_len), uint32_t(bf), l0.ptr(),
                                                                     l_last.ptr(), l_active_row.ptr(), values.ptr()),
                                     "h2b_evaluate_h_permutation");
+      for (size_t li = 0; li < lookups[ci].size(); ++li) {  // evaluation.rs:446-519: the three cosets live only here
+        const auto& lk = lookups[ci][li];
+        const DeviceVec product(dom.coeff_to_extended(lk.product_poly).values), pin(dom.coeff_to_extended(lk.permuted_input_poly).values),
+            ptab(dom.coeff_to_extended(lk.permuted_table_poly).values);
+        halo2_proofs::detail::check(ctx, h2b_evaluate_h_lookup(dom.raw(), pk.ev->lookups[li].compile().get(), &cols, product.ptr(), pin.ptr(), ptab.ptr(),
+                                                               l0.ptr(), l_last.ptr(), l_active_row.ptr(), values.ptr()),
+                                    "h2b_evaluate_h_lookup");
+      }
     }
     h_ext = values.download();
   }
@@ -808,6 +886,13 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
       transcript.write_scalar(eval(sets[si].poly, x_next));
       if (si + 1 < sets.size()) transcript.write_scalar(eval(sets[si].poly, x_last));
     }
+  const Fr x_inv = rot(x, -1);
+  for (const auto& lks : lookups)  // :588-595, lookup/prover.rs:253-283
+    for (const auto& lk : lks) {
+      transcript.write_scalar(eval(lk.product_poly, x)), transcript.write_scalar(eval(lk.product_poly, x_next));
+      transcript.write_scalar(eval(lk.permuted_input_poly, x)), transcript.write_scalar(eval(lk.permuted_input_poly, x_inv));
+      transcript.write_scalar(eval(lk.permuted_table_poly, x));
+    }
 
   // ---- the opening queries in the reference's order (:596-645) ----
   std::vector<ProverQuery> queries;
@@ -816,6 +901,10 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
     const auto& sets = permutations[ci];
     for (const auto& st : sets) queries.push_back({x, &st.poly}), queries.push_back({x_next, &st.poly});
     for (size_t si = sets.size(); si-- > 1;) queries.push_back({x_last, &sets[si - 1].poly});  // .rev().skip(1)
+    for (const auto& lk : lookups[ci]) {  // lookup/prover.rs:286-323
+      queries.push_back({x, &lk.product_poly}), queries.push_back({x, &lk.permuted_input_poly}), queries.push_back({x, &lk.permuted_table_poly});
+      queries.push_back({x_inv, &lk.permuted_input_poly}), queries.push_back({x_next, &lk.product_poly});
+    }
   }
   for (const auto& q : cs.fixed_queries) queries.push_back({rot(x, q.second), &pk.fixed_polys[q.first.index]});
   for (const auto& p : pk.permutation_polys) queries.push_back({x, &p});

@@ -187,6 +187,38 @@ int main(int argc, char** argv) {
       transcript::Blake2bWrite t;
       plonk::create_proof(params, pk, {bc.advice}, {{}}, rng, t, arg(1) ? plonk::Multiopen::SHPLONK : plonk::Multiopen::GWC);
       spit(argv[3], t.finalize().data(), t.finalize().size());
+    } else if (op == "prove_lookup") {  // args: k; in: s, seed (16 B), usable (u64), q_mul q_lk t a b [usable each], ncopies (u64), copies (4 x u64: column, row, column, row; advice)
+      // tests/plonk_cases.py::build_lookup_cs -- q_mul * (a * a - b) = 0, (q_lk * a) in t
+      using namespace plonk;
+      const Fr s = take<Fr>(in, 0, 1)[0];
+      const auto seed = take<uint8_t>(in, 32, 16);
+      const uint64_t usable = take<uint64_t>(in, 48, 1)[0];
+      ConstraintSystem meta;
+      const Column a = meta.advice_column(), b = meta.advice_column();
+      const Column q_mul = meta.fixed_column(), q_lk = meta.fixed_column(), t = meta.fixed_column();
+      meta.enable_equality(a), meta.enable_equality(b);
+      const Expression qa = meta.query_advice(a), qb = meta.query_advice(b);
+      const Expression qm = meta.query_fixed(q_mul), ql = meta.query_fixed(q_lk);
+      const Expression qt = meta.query_fixed(t);
+      (void)qt;
+      meta.create_gate("square", {qm * (qa * qa - qb)});
+      meta.lookup("range", {{ql * qa, t}});
+      std::vector<std::vector<Fr>> cols;
+      for (int c = 0; c < 5; ++c) cols.push_back(take<Fr>(in, 56 + size_t(c) * usable * 32, usable));
+      const size_t off = 56 + 5 * usable * 32;
+      const uint64_t ncopies = take<uint64_t>(in, off, 1)[0];
+      const auto raw = take<uint64_t>(in, off + 8, 4 * ncopies);
+      std::vector<CopyConstraint> copies;
+      for (uint64_t i = 0; i < ncopies; ++i)
+        copies.push_back({Column{Any::Advice, uint32_t(raw[4 * i])}, size_t(raw[4 * i + 1]), Column{Any::Advice, uint32_t(raw[4 * i + 2])}, size_t(raw[4 * i + 3])});
+      const auto params = poly::kzg::ParamsKZG::setup(arg(0), s, false);
+      const ProvingKey pk = keygen_pk(params, meta, {cols[0], cols[1], cols[2]}, copies);
+      XorShiftRng rng(seed.data());
+      transcript::Blake2bWrite tr;
+      create_proof(params, pk, {{cols[3], cols[4]}}, {{}}, rng, tr);
+      std::ofstream o(argv[3], std::ios::binary);
+      o.write(reinterpret_cast<const char*>(tr.finalize().data()), std::streamsize(tr.finalize().size()));
+      o << pk.pinned;
     } else if (op == "rng") {  // in: 16-byte seed; out: arg(0) draws of Fr::random from XorShiftRng
       const auto seed = take<uint8_t>(in, 0, 16);
       plonk::XorShiftRng rng(seed.data());

@@ -291,6 +291,50 @@ def test_cpp_mirror_create_proof_gpu(tmp_path):
     assert got == t.finalize() and OV.verify_proof(oparams, PC.S_TOXIC, opk, [[]], got, multiopen="shplonk")
 
 
+@pytest.mark.parametrize("k", [5, 6])
+def test_cpp_mirror_create_proof_with_a_lookup(emu_lib_path, tmp_path, k):
+    """The C++ create_proof on the lookup circuit of tests/plonk_cases.py (a gate, copy constraints, one lookup
+    argument): permute_expression_pair, the lookup grand product and its five constraints in h(X), evaluations and
+    openings in the reference's order -- same verifying key and same proof bytes as the big-integer oracle; an
+    input outside the table is Error::ConstraintSystemFailure (exit status 101)."""
+    import struct
+
+    from oracle import prover as OV
+    from tests import plonk_cases as PC
+    seed = b"\x21" * 16
+    fixed, advice, copies = PC.lookup_circuit(k)
+    oparams = O.ParamsKZG.setup(k, PC.S_TOXIC)
+    opk = OV.keygen(oparams, PC.oracle_cs(PC.build_lookup_cs()), fixed, copies)
+    t = OV.Blake2bWrite()
+    OV.create_proof(oparams, opk, [lambda phase, ch: dict(enumerate(advice))], [[]], OV.XorShiftRng(seed), t)
+    want = t.finalize()
+    cli = _build("mirror_cli", emu_lib_path, "emu")
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+
+    def run(adv):
+        usable = len(fixed[0])
+        blob = H.fr_enc([PC.S_TOXIC]).tobytes() + seed + struct.pack("<Q", usable)
+        for col in list(fixed) + list(adv):
+            blob += H.fr_enc(col).tobytes()
+        blob += struct.pack("<Q", len(copies))
+        for (lc, lr, rc, rr) in copies:
+            blob += struct.pack("<4Q", lc[1], lr, rc[1], rr)
+        open(fin, "wb").write(blob)
+        return _run(cli, "prove_lookup", fin, fout, k)
+
+    r = run(advice)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = open(fout, "rb").read()
+    assert out[len(want):].decode() == opk.debug
+    got = out[:len(want)]
+    assert got == want, [i // 32 for i in range(0, len(want), 32) if got[i:i + 32] != want[i:i + 32]][:6]
+    assert OV.verify_proof(oparams, PC.S_TOXIC, opk, [[]], got)
+    bad = [list(c) for c in advice]
+    bad[0][0] = 1 << 40
+    r = run(bad)
+    assert r.returncode == 101 and "ConstraintSystemFailure" in r.stdout
+
+
 def test_cpp_mirror_fr_random_stream(emu_lib_path, tmp_path):
     """XorShiftRng + Fr::random (from_bytes_wide) of the C++ mirror: 5000 draws equal the Python mirror's -- a raw
     256-bit half of the wide integer may exceed r five times over and must not go through from_raw as it is."""
