@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <functional>
 
 #include "halo2_b200.hpp"
 
@@ -579,8 +580,7 @@ inline ProvingKey keygen_pk(const poly::kzg::ParamsKZG& params, const Constraint
 // ---------------------------------------------------------------------------------------------
 // create_proof<KZGCommitmentScheme<Bn256>, ProverGWC | ProverSHPLONK, Challenge255, R, Blake2bWrite>
 //                                                                          halo2_proofs/src/plonk/prover.rs:37-651
-// for constraint systems with gates, lookups, a permutation argument and instance columns in one phase (challenge
-// phases are carried by the Python mirror only, so far).  The witness is handed over as assigned advice
+// for constraint systems with gates, lookups, a permutation argument, instance columns and challenge phases.  The witness is handed over as assigned advice
 // columns (the role of Circuit::synthesize through WitnessCollection, :143-285).  Host vectors between the steps,
 // as in the reference; every transform, commitment, grand product and the whole quotient evaluation run on the GPU.
 // ---------------------------------------------------------------------------------------------
@@ -646,20 +646,23 @@ class DeviceVec {  // a device-resident array of Fr on the calling thread's cont
 
 enum class Multiopen { GWC, SHPLONK };
 
-/// advice[i][c] / instances[i][c]: the assigned values of column c of circuit i (shorter than n: zero-padded)
+/// witness(circuit, phase, challenges) -> the assigned advice columns of that circuit (one vector per advice
+/// column; only the columns of `phase` are read; shorter than n: zero-padded): the role of Circuit::synthesize through
+/// WitnessCollection, called once per phase with the challenges squeezed so far (prover.rs:143-285, 287-405).
+using Witness = std::function<std::vector<std::vector<Fr>>(size_t circuit, uint32_t phase, const std::vector<Fr>& challenges)>;
+
+/// instances[i][c]: the values of instance column c of circuit i
 template <class Rng>
-inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& pk,
-                         const std::vector<std::vector<std::vector<Fr>>>& advice,
+inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& pk, const Witness& witness,
                          const std::vector<std::vector<std::vector<Fr>>>& instances, Rng& rng,
                          transcript::Blake2bWrite& transcript, Multiopen scheme = Multiopen::GWC) {
+  const size_t n_circuits = instances.size();  // one witness per instance list
   using namespace poly;
   using detail::DeviceVec;
   const ConstraintSystem& cs = pk.cs;
   const EvaluationDomain& dom = *pk.domain;
   h2b_ctx* ctx = halo2_proofs::detail::backend().ctx;
   const size_t n = pk.n, bf = cs.blinding_factors(), ext = dom.extended_len();
-  if (cs.num_challenges) throw Panic("create_proof (C++ mirror): challenge phases are not carried yet");
-  if (advice.size() != instances.size()) throw Panic("one instance list per circuit");
   for (const auto& inst : instances)
     if (inst.size() != cs.num_instance_columns) throw Panic("Error::InvalidInstances (prover.rs:55-59)");
   auto rot = [&](const Fr& v, int32_t r) { return dom.rotate_omega(v, Rotation{r}); };
@@ -682,18 +685,29 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
 
   // ---- advice (:287-405) ----
   const size_t unusable_rows_start = n - (bf + 1);
-  std::vector<std::vector<Polynomial<LagrangeCoeff>>> advice_values(advice.size());
-  for (size_t ci = 0; ci < advice.size(); ++ci) {
-    if (advice[ci].size() != cs.num_advice_columns) throw Panic("one assignment per advice column expected");
-    for (const auto& col : advice[ci]) {  // assigned rows, zero padding, then the blinding factors (:364-368)
-      if (col.size() > unusable_rows_start) throw Panic("Error::not_enough_rows_available (prover.rs:228-230)");
-      std::vector<Fr> v = col;
-      v.resize(unusable_rows_start, Fr::zero());
-      for (size_t r = unusable_rows_start; r < n; ++r) v.push_back(fr_random(rng));
-      advice_values[ci].push_back(dom.lagrange_from_vec(std::move(v)));
+  std::vector<std::vector<Polynomial<LagrangeCoeff>>> advice_values(n_circuits, std::vector<Polynomial<LagrangeCoeff>>(cs.num_advice_columns));
+  std::vector<Fr> challenges(cs.num_challenges, Fr::zero());
+  uint32_t last_phase = 0;
+  for (uint32_t p : cs.advice_column_phase) last_phase = std::max(last_phase, p);
+  for (uint32_t phase = 0; phase <= last_phase; ++phase) {
+    std::vector<size_t> column_indices;
+    for (size_t c = 0; c < cs.num_advice_columns; ++c)
+      if (cs.advice_column_phase[c] == phase) column_indices.push_back(c);
+    for (size_t ci = 0; ci < n_circuits; ++ci) {
+      const auto assigned = witness(ci, phase, challenges);
+      if (assigned.size() != cs.num_advice_columns) throw Panic("one assignment per advice column expected");
+      for (size_t c : column_indices) {  // assigned rows, zero padding, then the blinding factors (:364-368)
+        if (assigned[c].size() > unusable_rows_start) throw Panic("Error::not_enough_rows_available (prover.rs:228-230)");
+        std::vector<Fr> v = assigned[c];
+        v.resize(unusable_rows_start, Fr::zero());
+        for (size_t r = unusable_rows_start; r < n; ++r) v.push_back(fr_random(rng));
+        advice_values[ci][c] = dom.lagrange_from_vec(std::move(v));
+      }
+      for (size_t j = 0; j < column_indices.size(); ++j) fr_random(rng);  // Blind(Scalar::random(rng)), ignored by KZG (:371-374)
+      for (size_t c : column_indices) transcript.write_point(params.commit_lagrange(advice_values[ci][c]).to_affine());  // :375-392
     }
-    for (size_t c = 0; c < advice[ci].size(); ++c) fr_random(rng);  // Blind(Scalar::random(rng)), ignored by KZG (:371-374)
-    for (const auto& v : advice_values[ci]) transcript.write_point(params.commit_lagrange(v).to_affine());  // :375-392
+    for (size_t i = 0; i < cs.challenge_phase.size(); ++i)  // :394-403
+      if (cs.challenge_phase[i] == phase) challenges[i] = transcript.squeeze_challenge_scalar();
   }
   const Fr theta = transcript.squeeze_challenge_scalar();  // :410
 
@@ -702,8 +716,8 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
     std::vector<Fr> compressed_input, compressed_table, permuted_input, permuted_table;  // Lagrange
     Polynomial<Coeff> permuted_input_poly, permuted_table_poly, product_poly;
   };
-  std::vector<std::vector<Lookup>> lookups(advice.size());
-  for (size_t ci = 0; ci < advice.size() && !cs.lookups.empty(); ++ci) {
+  std::vector<std::vector<Lookup>> lookups(n_circuits);
+  for (size_t ci = 0; ci < n_circuits && !cs.lookups.empty(); ++ci) {
     std::vector<std::unique_ptr<DeviceVec>> keep;
     std::vector<const h2b_fr*> fixed_ptrs, adv_ptrs, inst_ptrs;
     for (const auto& p : pk.fixed_values) keep.emplace_back(new DeviceVec(p.values)), fixed_ptrs.push_back(keep.back()->ptr());
@@ -714,6 +728,7 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
     cols.fixed = fixed_ptrs.data(), cols.n_fixed = uint32_t(fixed_ptrs.size());
     cols.advice = adv_ptrs.data(), cols.n_advice = uint32_t(adv_ptrs.size());
     cols.instance = inst_ptrs.data(), cols.n_instance = uint32_t(inst_ptrs.size());
+    cols.challenges = challenges.data(), cols.n_challenges = uint32_t(challenges.size());
     cols.theta = theta;
     for (const auto& graphs : pk.lookup_compress) {
       Lookup lk;
@@ -746,10 +761,10 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
     Polynomial<Coeff> poly;
     Polynomial<ExtendedLagrangeCoeff> coset;
   };
-  std::vector<std::vector<Set>> permutations(advice.size());
+  std::vector<std::vector<Set>> permutations(n_circuits);
   const auto& pcols = cs.permutation.columns;
   const size_t chunk_len = cs.degree() - 2;
-  for (size_t ci = 0; ci < advice.size(); ++ci) {
+  for (size_t ci = 0; ci < n_circuits; ++ci) {
     Fr last_z = Fr::one();
     for (size_t s0 = 0; s0 < pcols.size(); s0 += chunk_len) {
       const size_t m = std::min(chunk_len, pcols.size() - s0);
@@ -805,8 +820,8 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
 
   const Fr y = transcript.squeeze_challenge_scalar();  // :478
 
-  std::vector<std::vector<Polynomial<Coeff>>> advice_polys(advice.size());  // :481-499
-  for (size_t ci = 0; ci < advice.size(); ++ci)
+  std::vector<std::vector<Polynomial<Coeff>>> advice_polys(n_circuits);  // :481-499
+  for (size_t ci = 0; ci < n_circuits; ++ci)
     for (const auto& v : advice_values[ci]) advice_polys[ci].push_back(dom.lagrange_to_coeff(v));
 
   // ---- h(X): Evaluator::evaluate_h on the device (:502-520, evaluation.rs:280-522) ----
@@ -826,7 +841,7 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
     const auto graph = pk.ev->custom_gates.compile();
     std::vector<uint32_t> ctype, cidx;
     for (const auto& c : pcols) ctype.push_back(uint32_t(c.column_type)), cidx.push_back(c.index);
-    for (size_t ci = 0; ci < advice.size(); ++ci) {
+    for (size_t ci = 0; ci < n_circuits; ++ci) {
       std::vector<Polynomial<ExtendedLagrangeCoeff>> adv, inst, zs;
       for (const auto& p : advice_polys[ci]) adv.push_back(dom.coeff_to_extended(p));    // :305-323
       for (const auto& p : instance_polys[ci]) inst.push_back(dom.coeff_to_extended(p));
@@ -839,6 +854,7 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
       cols.fixed = fixed_ptrs.data(), cols.n_fixed = uint32_t(fixed_ptrs.size());
       cols.advice = adv_ptrs.data(), cols.n_advice = uint32_t(adv_ptrs.size());
       cols.instance = inst_ptrs.data(), cols.n_instance = uint32_t(inst_ptrs.size());
+      cols.challenges = challenges.data(), cols.n_challenges = uint32_t(challenges.size());
       cols.beta = beta, cols.gamma = gamma, cols.theta = theta, cols.y = y;
       halo2_proofs::detail::check(ctx, h2b_evaluate_h_gates(dom.raw(), graph.get(), &cols, values.ptr()), "h2b_evaluate_h_gates");
       if (!z_ptrs.empty())
@@ -871,7 +887,7 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
   const Fr xn = x.pow_vartime(n);
 
   // ---- evaluations (:548-581) ----
-  for (size_t ci = 0; ci < advice.size(); ++ci)
+  for (size_t ci = 0; ci < n_circuits; ++ci)
     for (const auto& q : cs.advice_queries) transcript.write_scalar(eval(advice_polys[ci][q.first.index], rot(x, q.second)));
   for (const auto& q : cs.fixed_queries) transcript.write_scalar(eval(pk.fixed_polys[q.first.index], rot(x, q.second)));
   // vanishing.evaluate (vanishing/prover.rs:124-152): h_poly = fold(pieces.rev(), acc * xn + piece)
@@ -896,7 +912,7 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
 
   // ---- the opening queries in the reference's order (:596-645) ----
   std::vector<ProverQuery> queries;
-  for (size_t ci = 0; ci < advice.size(); ++ci) {
+  for (size_t ci = 0; ci < n_circuits; ++ci) {
     for (const auto& q : cs.advice_queries) queries.push_back({rot(x, q.second), &advice_polys[ci][q.first.index]});
     const auto& sets = permutations[ci];
     for (const auto& st : sets) queries.push_back({x, &st.poly}), queries.push_back({x_next, &st.poly});
@@ -914,6 +930,17 @@ inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& p
     kzg::multiopen::ProverGWC(params).create_proof(transcript, queries);
   else
     kzg::multiopen::ProverSHPLONK(params).create_proof(transcript, queries);
+}
+
+/// single-phase form: advice[i][c] = the assigned values of advice column c of circuit i
+template <class Rng>
+inline void create_proof(const poly::kzg::ParamsKZG& params, const ProvingKey& pk,
+                         const std::vector<std::vector<std::vector<Fr>>>& advice,
+                         const std::vector<std::vector<std::vector<Fr>>>& instances, Rng& rng,
+                         transcript::Blake2bWrite& transcript, Multiopen scheme = Multiopen::GWC) {
+  if (advice.size() != instances.size()) throw Panic("one instance list per circuit");
+  const Witness w = [&](size_t ci, uint32_t, const std::vector<Fr>&) { return advice[ci]; };
+  create_proof(params, pk, w, instances, rng, transcript, scheme);
 }
 
 }  // namespace plonk

@@ -219,6 +219,38 @@ int main(int argc, char** argv) {
       std::ofstream o(argv[3], std::ios::binary);
       o.write(reinterpret_cast<const char*>(tr.finalize().data()), std::streamsize(tr.finalize().size()));
       o << pk.pinned;
+    } else if (op == "prove_phases") {  // args: k; in: s, seed (16 B).  Two phases: b (phase 1) = a (phase 0) * challenge
+      using namespace plonk;
+      const Fr s = take<Fr>(in, 0, 1)[0];
+      const auto seed = take<uint8_t>(in, 32, 16);
+      ConstraintSystem meta;
+      const Column a = meta.advice_column(0), b = meta.advice_column(1);
+      const Column q = meta.fixed_column();
+      const Expression ch = meta.challenge_usable_after(0);
+      meta.enable_equality(a), meta.enable_equality(b);
+      const Expression qa = meta.query_advice(a), qb = meta.query_advice(b), qq = meta.query_fixed(q);
+      meta.create_gate("prod", {qq * (qb - qa * ch)});
+      const auto params = poly::kzg::ParamsKZG::setup(arg(0), s, false);
+      const size_t usable = params.n() - (meta.blinding_factors() + 1);
+      std::vector<Fr> av(usable), qv(usable, Fr::one());
+      for (size_t i = 0; i < usable; ++i) av[i] = Fr::from(i + 2);
+      av[2] = av[1];
+      const ProvingKey pk = keygen_pk(params, meta, {qv}, {{a, 1, a, 2}, {b, 1, b, 2}});
+      const Witness witness = [&](size_t, uint32_t phase, const std::vector<Fr>& challenges) {
+        std::vector<std::vector<Fr>> cols(2);
+        cols[0] = av;
+        if (phase == 1) {
+          cols[1] = av;
+          for (auto& x : cols[1]) x *= challenges.at(0);
+        }
+        return cols;
+      };
+      XorShiftRng rng(seed.data());
+      transcript::Blake2bWrite tr;
+      create_proof(params, pk, witness, {{}}, rng, tr);
+      std::ofstream o(argv[3], std::ios::binary);
+      o.write(reinterpret_cast<const char*>(tr.finalize().data()), std::streamsize(tr.finalize().size()));
+      o << pk.pinned;
     } else if (op == "rng") {  // in: 16-byte seed; out: arg(0) draws of Fr::random from XorShiftRng
       const auto seed = take<uint8_t>(in, 0, 16);
       plonk::XorShiftRng rng(seed.data());

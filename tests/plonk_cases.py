@@ -434,3 +434,56 @@ def device_h_limbs(ctx: h.Context, cs: h.ConstraintSystem, case):
     ev.free()
     dom.free()
     return out
+
+
+def build_phases_cs() -> h.ConstraintSystem:
+    """Two phases: a (phase 0), a challenge usable after phase 0, b (phase 1); gate q * (b - a * challenge)."""
+    cs = h.ConstraintSystem()
+    a, b = cs.advice_column(0), cs.advice_column(1)
+    q = cs.fixed_column()
+    ch = cs.challenge_usable_after(0)
+    cs.enable_equality(a)
+    cs.enable_equality(b)
+    qa, qb, qq = cs.query_advice(a), cs.query_advice(b), cs.query_fixed(q)
+    cs.create_gate("prod", [qq * (qb - qa * ch)])
+    return cs
+
+
+def phases_circuit(k: int):
+    """-> (fixed [q], witness(phase, challenges) -> columns, copies) satisfying build_phases_cs() on 2^k rows."""
+    cs = build_phases_cs()
+    usable = (1 << k) - (cs.blinding_factors() + 1)
+    a = [i + 2 for i in range(usable)]
+    a[2] = a[1]
+
+    def witness(phase, challenges):
+        if phase == 0:
+            return {0: a}
+        return {1: [x * challenges[0] % O.R_MOD for x in a]}
+
+    copies = [((h.ADVICE, 0), 1, (h.ADVICE, 0), 2), ((h.ADVICE, 1), 1, (h.ADVICE, 1), 2)]
+    return [[1] * usable], witness, copies
+
+
+def check_phases_proof_bytes(ctx: h.Context, k: int = 5, seed: bytes = b"\x42" * 16):
+    """A circuit with two advice phases and a challenge: same vk and proof bytes from the product's prover as from
+    the big-integer oracle, and the restated reference verifier accepts them.  -> (proof bytes, pinned vk)"""
+    from oracle import prover as OV
+    fixed, witness, copies = phases_circuit(k)
+    oparams = O.ParamsKZG.setup(k, S_TOXIC)
+    opk = OV.keygen(oparams, oracle_cs(build_phases_cs()), fixed, copies)
+    t = OV.Blake2bWrite()
+    OV.create_proof(oparams, opk, [witness], [[]], OV.XorShiftRng(seed), t)
+    want = t.finalize()
+    assert OV.verify_proof(oparams, S_TOXIC, opk, [[]], want)
+    params = h.ParamsKZG.setup(ctx, k, S_TOXIC)
+    pk = h.keygen(params, build_phases_cs(), fixed, copies)
+    t = h.Blake2bWrite()
+    h.create_proof(params, pk, [witness], [[]], h.XorShiftRng(seed), t)
+    got = t.finalize()
+    assert pk.pinned == opk.debug
+    assert got == want, [i // 32 for i in range(0, len(want), 32) if got[i:i + 32] != want[i:i + 32]][:6]
+    pk.free()
+    params.g.free()
+    params.g_lagrange.free()
+    return want, opk.debug

@@ -335,6 +335,22 @@ def test_cpp_mirror_create_proof_with_a_lookup(emu_lib_path, tmp_path, k):
     assert r.returncode == 101 and "ConstraintSystemFailure" in r.stdout
 
 
+def test_cpp_mirror_create_proof_with_two_phases(emu_lib_path, emu_ctx, tmp_path):
+    """The C++ create_proof with a Witness callback over two advice phases and a challenge in between: same
+    verifying key and proof bytes as the oracle (and as the Python mirror)."""
+    from tests import plonk_cases as PC
+    seed = b"\x42" * 16
+    want, debug = PC.check_phases_proof_bytes(emu_ctx, 5, seed)
+    cli = _build("mirror_cli", emu_lib_path, "emu")
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    open(fin, "wb").write(H.fr_enc([PC.S_TOXIC]).tobytes() + seed)
+    r = _run(cli, "prove_phases", fin, fout, 5)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = open(fout, "rb").read()
+    assert out[len(want):].decode() == debug
+    assert out[:len(want)] == want
+
+
 def test_cpp_mirror_fr_random_stream(emu_lib_path, tmp_path):
     """XorShiftRng + Fr::random (from_bytes_wide) of the C++ mirror: 5000 draws equal the Python mirror's -- a raw
     256-bit half of the wide integer may exceed r five times over and must not go through from_raw as it is."""

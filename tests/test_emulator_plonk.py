@@ -107,3 +107,9 @@ def test_create_proof_with_a_lookup_equals_the_oracle(emu_ctx):
 @pytest.mark.parametrize("which", ["bench", "lookup"])
 def test_shplonk_proof_bytes_equal_the_oracle(emu_ctx, which):
     PC.check_shplonk_proof_bytes(emu_ctx, which)
+
+
+def test_create_proof_with_two_phases_equals_the_oracle(emu_ctx):
+    """Advice columns in two phases with a challenge squeezed in between (prover.rs:287-405): proof bytes equal
+    the oracle's, the restated verifier accepts them."""
+    PC.check_phases_proof_bytes(emu_ctx, 5)

@@ -110,3 +110,7 @@ def test_evaluate_h_vs_cpp_restatement_at_larger_k(gpu_ctx, oracle_c, variant, k
     want = PC.oracle_c_h(oracle_c, cs, case)
     got = PC.device_h_limbs(gpu_ctx, cs, case)
     assert got.shape == want.shape and (got == want).all()
+
+
+def test_create_proof_with_two_phases_equals_the_oracle(gpu_ctx):
+    PC.check_phases_proof_bytes(gpu_ctx, 6)
