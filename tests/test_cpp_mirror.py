@@ -351,6 +351,26 @@ def test_cpp_mirror_create_proof_with_two_phases(emu_lib_path, emu_ctx, tmp_path
     assert out[:len(want)] == want
 
 
+def test_cpp_example_program(emu_lib_path):
+    """examples/prove_bench_circuit.cpp builds against the headers and proves the bench circuit (emulator, k = 5);
+    the verifying-key hash it prints is the oracle's."""
+    from tests import plonk_cases as PC
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, "prove_bench_circuit_emu")
+    libdir = os.path.dirname(emu_lib_path)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "prove_bench_circuit.cpp"), "-o", exe, "-L" + libdir,
+                    "-lhalo2b200_emu", "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    r = _run(exe, 5)
+    assert r.returncode == 0 and "proof 768 bytes" in r.stdout, r.stdout + r.stderr
+    # the example's SRS secret differs from the tests' S_TOXIC: its key hash is that of the same circuit under its own SRS
+    s = (0x1234567890ABCDEF << 64) | 0x1234567890ABCDEF
+    from oracle import prover as OV
+    fixed, _, copies = PC.bench_circuit(5, 0xDEADBEEF)
+    opk = OV.keygen(O.ParamsKZG.setup(5, s), PC.oracle_cs(PC.build_cs("bench")), fixed, copies)
+    assert ("vk transcript_repr = 0x%064x" % opk.transcript_repr) in r.stdout
+
+
 def test_cpp_mirror_fr_random_stream(emu_lib_path, tmp_path):
     """XorShiftRng + Fr::random (from_bytes_wide) of the C++ mirror: 5000 draws equal the Python mirror's -- a raw
     256-bit half of the wide integer may exceed r five times over and must not go through from_raw as it is."""
