@@ -68,6 +68,9 @@ SYMBOLS = {
     "h2b_msm_window_bits": (_U32, [_SZ]),
     "h2b_g1_mul_generator": (_I, [_P, _P, _I, _SZ, _P, _I]),
     "h2b_g1_sum": (_I, [_P, _SZ, _P]),
+    "h2b_fr_repr": (_I, [_P, _P, _I, _SZ, _I, _P]),
+    "h2b_small_multiexp": (_I, [_P, _P, _SZ, _P]),
+    "h2b_g_to_lagrange": (_I, [_P, _P, _I, _U32, _P, _I]),
     "h2b_best_fft": (_I, [_P, _P, _I, _P, _U32]),
     "h2b_best_fft_batch": (_I, [_P, _P, _I, _P, _U32, _U32, _SZ]),
     "h2b_domain_new": (_I, [_P, _U32, _U32, C.POINTER(_P)]),

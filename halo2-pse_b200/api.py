@@ -299,6 +299,26 @@ class Context:
         self._check(self.lib.h2b_best_multiexp(self.h, _ptr(c), _ptr(b), c.shape[0], _ptr(out)))
         return g1_jacobian_to_affine(out)
 
+    def small_multiexp(self, coeffs, bases):
+        """arithmetic.rs:105-125 -- shared-doubling double-and-add over a few points (host-side, as in the
+        reference); affine point (x, y) | None out."""
+        c = _fr_array(coeffs)
+        b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        if c.shape[0] > b.shape[0]:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "index out of bounds: bases[coeff_idx]")  # :117
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(self.lib.h2b_small_multiexp(_ptr(c), _ptr(b), c.shape[0], _ptr(out)))
+        return g1_jacobian_to_affine(out)
+
+    def g_to_lagrange(self, g, k: int) -> np.ndarray:
+        """arithmetic.rs:277-301 -- (2^k, 8) affine limbs in, the Lagrange-basis points out (host arrays)."""
+        b = np.ascontiguousarray(g, dtype=np.uint64).reshape(-1, 8)
+        if b.shape[0] != 1 << k:
+            raise H2BError(_ffi.H2B_ERR_LENGTH, "assert_eq!(a.len(), 1 << log_n)")  # best_fft, :184
+        out = np.zeros_like(b)
+        self._check(self.lib.h2b_g_to_lagrange(self.h, _ptr(b), H2B_HOST, k, _ptr(out), H2B_HOST))
+        return out
+
     def best_fft(self, a: np.ndarray, omega, log_n: int) -> np.ndarray:
         """arithmetic.rs:171 -- in place on the (n, 4) limb array `a`."""
         arr = _fr_array(a)
@@ -624,6 +644,28 @@ class ParamsKZG:
         from . import serde  # :118-119  g2 = generator of G2, s_g2 = [s] g2
         params.g2, params.s_g2 = serde.G2_GENERATOR, serde.g2_mul(serde.G2_GENERATOR, s % R_MOD)
         return params
+
+    def downsize(self, k: int) -> None:
+        """ParamsKZG::downsize (poly/kzg/commitment.rs:267-275): g.truncate(1 << k) and
+        g_lagrange = g_to_lagrange(g, k), both on the device (the group NTT of arithmetic.rs:277-301)."""
+        if k > self.k:
+            raise H2BError(_ffi.H2B_ERR_ARG, "assert!(k <= self.k)")  # :268
+        if not isinstance(self.g, Bases):
+            raise H2BError(_ffi.H2B_ERR_ARG, "downsize needs the replicated base vectors (shard afterwards)")
+        ctx, n = self.ctx, 1 << k
+        had_table = bool(self.g.table_window_bits)
+        gp = C.c_void_p(int(ctx.lib.h2b_bases_device_ptr(self.g.h)))
+        new_g = Bases(ctx, gp, n, H2B_DEVICE)  # device-to-device copy of the first n points
+        buf = ctx.alloc(n * 64)
+        ctx._check(ctx.lib.h2b_g_to_lagrange(ctx.h, gp, H2B_DEVICE, k, buf.ptr, H2B_DEVICE))
+        new_l = Bases(ctx, buf.ptr, n, H2B_DEVICE)
+        buf.free()
+        self.g.free()
+        self.g_lagrange.free()
+        self.g, self.g_lagrange, self.k, self.n = new_g, new_l, k, n
+        if had_table:
+            self.g.precompute()
+            self.g_lagrange.precompute()
 
     def commit(self, poly, blind=None):
         """:327-334 -- blind is accepted and ignored, as in the reference."""

@@ -1,7 +1,6 @@
 // Context, device memory helpers, synthetic benchmark inputs and the
 // measurement / test hooks of libhalo2b200 (include/halo2_b200.h).
 #include "common.cuh"
-#include "field29.cuh"
 
 #include <string.h>
 
@@ -372,23 +371,6 @@ __global__ void __launch_bounds__(256) pipe_peak_kernel(uint32_t* sink, uint32_t
 // ---------------------------------------------------------------------------
 // Element-wise test kernels
 // ---------------------------------------------------------------------------
-// ops 8..12 exercise the 9 x 29-bit path of field29.cuh end to end
-template <class P29, class F>
-H2B_HD F field_op29(int op, const F& a, const F& b) {
-  const F29<P29> A = to_r9<P29>(a), B = to_r9<P29>(b);
-  switch (op) {
-    case 8: return from_r9<P29>(mul29(A, B));                                         // a * b
-    case 9: return from_r9<P29>(norm29(sub29(A, B)));                                 // a - b
-    case 10: return from_r9<P29>(norm29(sub29f(A, add29(B, add29(B, B)))));          // a - 3b
-    case 11: return pack29<P29>(unpack29<P29>(a));                                    // a
-    default: {                                                                        // (a - b) * (a + b), fat operand
-      const F29<P29> d = sub29(A, B), s = norm29(add29(A, B));
-      const F29<P29> c = canon29(mul29(s, d));
-      return from_r9<P29>(c);
-    }
-  }
-}
-
 template <class F>
 H2B_HD F field_op(int op, const F& a, const F& b) {
   switch (op) {
@@ -407,13 +389,11 @@ __global__ void field_op_kernel(int field, int op, const Fr* a, const Fr* b, Fr*
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (field == 0) {
-    st_fp(out + i, op >= 8 ? field_op29<Fr29Params, Fr>(op, ld_fp(a + i), ld_fp(b + i))
-                           : field_op<Fr>(op, ld_fp(a + i), ld_fp(b + i)));
+    st_fp(out + i, field_op<Fr>(op, ld_fp(a + i), ld_fp(b + i)));
   } else {
     const Fq* qa = reinterpret_cast<const Fq*>(a);
     const Fq* qb = reinterpret_cast<const Fq*>(b);
-    st_fp(reinterpret_cast<Fq*>(out) + i, op >= 8 ? field_op29<Fq29Params, Fq>(op, ld_fp(qa + i), ld_fp(qb + i))
-                                                  : field_op<Fq>(op, ld_fp(qa + i), ld_fp(qb + i)));
+    st_fp(reinterpret_cast<Fq*>(out) + i, field_op<Fq>(op, ld_fp(qa + i), ld_fp(qb + i)));
   }
 }
 
@@ -770,7 +750,7 @@ extern "C" int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const h2b_fr* 
                                  h2b_fr* out, size_t n) {
   if (!ctx) return H2B_ERR_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  if (!a || !out || field < 0 || field > 1 || op < 0 || op > 12) return fail(ctx, H2B_ERR_ARG, "bad argument");
+  if (!a || !out || field < 0 || field > 1 || op < 0 || op > 7) return fail(ctx, H2B_ERR_ARG, "bad argument");
   if (n == 0) return H2B_OK;
   return run_elementwise(ctx, n * 32, a, b, out, [&](void* da, void* db, void* dout) {
     return launch(ctx, field_op_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, field, op,
@@ -780,19 +760,19 @@ extern "C" int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const h2b_fr* 
 
 extern "C" int h2b_host_field_op(int field, int op, const h2b_fr* a, const h2b_fr* b, h2b_fr* out,
                                  size_t n) {
-  if (!a || !out || field < 0 || field > 1 || op < 0 || op > 12) return H2B_ERR_ARG;
+  if (!a || !out || field < 0 || field > 1 || op < 0 || op > 7) return H2B_ERR_ARG;
   for (size_t i = 0; i < n; ++i) {
     if (field == 0) {
       Fr x, y;
       memcpy(&x, a + i, 32);
       memcpy(&y, (b ? b : a) + i, 32);
-      Fr r = op >= 8 ? field_op29<Fr29Params, Fr>(op, x, y) : field_op<Fr>(op, x, y);
+      Fr r = field_op<Fr>(op, x, y);
       memcpy(out + i, &r, 32);
     } else {
       Fq x, y;
       memcpy(&x, a + i, 32);
       memcpy(&y, (b ? b : a) + i, 32);
-      Fq r = op >= 8 ? field_op29<Fq29Params, Fq>(op, x, y) : field_op<Fq>(op, x, y);
+      Fq r = field_op<Fq>(op, x, y);
       memcpy(out + i, &r, 32);
     }
   }

@@ -33,6 +33,7 @@
 #endif
 #include <string.h>
 #include <algorithm>
+#include <vector>
 
 namespace h2b {
 
@@ -1330,6 +1331,162 @@ extern "C" int h2b_g1_sum(const h2b_g1_affine* pts, size_t n, h2b_g1_affine* out
   }
   const G1Affine a = xyzz_to_affine(acc);
   memcpy(out, &a, 64);
+  return H2B_OK;
+}
+
+// ---------------------------------------------------------------------------
+// small_multiexp (arithmetic.rs:105-125): double-and-add with the doublings shared across
+// the points.  A handful of points, host-side in the reference and here.
+// ---------------------------------------------------------------------------
+extern "C" int h2b_small_multiexp(const h2b_fr* coeffs, const h2b_g1_affine* bases, size_t n, h2b_g1* out) {
+  if ((n && (!coeffs || !bases)) || !out) return H2B_ERR_ARG;
+  std::vector<Fr> repr(n);
+  std::vector<G1Affine> pts(n);
+  for (size_t i = 0; i < n; ++i) {
+    Fr c;
+    memcpy(&c, coeffs + i, 32);
+    repr[i] = from_mont(c);  // to_repr(), :106
+    memcpy(&pts[i], bases + i, 64);
+  }
+  G1Xyzz acc = G1Xyzz::identity();
+  for (int byte_idx = 31; byte_idx >= 0; --byte_idx)
+    for (int bit_idx = 7; bit_idx >= 0; --bit_idx) {
+      acc = xyzz_double(acc);
+      const int bit = byte_idx * 8 + bit_idx;
+      for (size_t i = 0; i < n; ++i)
+        if ((repr[i].v[bit >> 5] >> (bit & 31)) & 1) xyzz_add_affine(acc, pts[i]);
+    }
+  xyzz_to_jacobian(acc, out);
+  return H2B_OK;
+}
+
+// ---------------------------------------------------------------------------
+// g_to_lagrange (arithmetic.rs:277-301): best_fft over curve points with omega^-1, every
+// point scaled by 1/n, batch-normalised.  The one caller on the KZG side is
+// ParamsKZG::downsize (poly/kzg/commitment.rs:267-275).  Radix-2 decimation in time on XYZZ
+// points: bit-reversal gather, then log n butterfly sweeps; the twiddle of a butterfly
+// is a 254-bit scalar multiplication of its odd input (group_scale, arithmetic.rs:214-225),
+// skipped where the twiddle is 1; the 1/n scaling is one more scalar multiplication folded
+// into the last sweep's outputs.  O(n log n) scalar multiplications, all independent.
+// ---------------------------------------------------------------------------
+namespace h2b {
+H2B_D G1Xyzz xyzz_scale(const G1Xyzz& p, const Fr& k_canonical) {
+  G1Xyzz acc = G1Xyzz::identity();
+  if (p.is_identity()) return acc;
+  bool started = false;
+  for (int limb = 7; limb >= 0; --limb) {
+    const uint32_t w = k_canonical.v[limb];
+    if (!started && w == 0) continue;
+    for (int bit = 31; bit >= 0; --bit) {
+      if (started) acc = xyzz_double(acc);
+      if ((w >> bit) & 1) {
+        xyzz_add(acc, p);
+        started = true;
+      }
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(128)
+    g1_fft_bitrev_kernel(const G1Affine* in, G1Xyzz* out, uint32_t k) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (1ull << k)) return;
+  uint32_t j = 0;
+  for (uint32_t b = 0; b < k; ++b) j |= (((uint32_t)i >> b) & 1u) << (k - 1 - b);
+  G1Affine p;
+  p.x = ld_fp(&in[j].x);
+  p.y = ld_fp(&in[j].y);
+  st_xyzz(out + i, G1Xyzz::from_affine(p));
+}
+
+// sweep `u` (1-based): butterflies (r0, r0 + 2^(u-1)) with twiddle w^(i * 2^(k-u)); final_scale != nullptr on the
+// last sweep multiplies both outputs by that scalar (canonical form)
+__global__ void __launch_bounds__(128)
+    g1_fft_sweep_kernel(G1Xyzz* a, uint32_t k, uint32_t u, const Fr* tw_lo, const Fr* tw_hi, uint32_t h,
+                        const Fr* final_scale) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= (1ull << k) / 2) return;
+  const uint32_t half = 1u << (u - 1);
+  const uint32_t i = (uint32_t)b & (half - 1);
+  const uint64_t r0 = ((b >> (u - 1)) << u) + i, r1 = r0 + half;
+  G1Xyzz x = ld_xyzz(a + r0), t = ld_xyzz(a + r1);
+  if (i) {
+    const uint64_t e = (uint64_t)i << (k - u);
+    Fr w = mul(ld_fp_nc(tw_lo + (uint32_t)(e & ((1ull << h) - 1))), ld_fp_nc(tw_hi + (uint32_t)(e >> h)));
+    t = xyzz_scale(t, from_mont(w));
+  }
+  G1Xyzz s = x, d = x;
+  xyzz_add(s, t);
+  t.y = neg(t.y);
+  xyzz_add(d, t);
+  if (final_scale) {
+    const Fr f = ld_fp_nc(final_scale);
+    s = xyzz_scale(s, f);
+    d = xyzz_scale(d, f);
+  }
+  st_xyzz(a + r0, s);
+  st_xyzz(a + r1, d);
+}
+
+__global__ void g1_scale_all_kernel(G1Xyzz* a, uint64_t n, const Fr* scale) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_xyzz(a + i, xyzz_scale(ld_xyzz(a + i), ld_fp_nc(scale)));
+}
+}  // namespace h2b
+
+extern "C" int h2b_g_to_lagrange(h2b_ctx* ctx, const h2b_g1_affine* g, int loc, uint32_t k, h2b_g1_affine* out,
+                                 int out_loc) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!g || !out) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (k > 28) return fail(ctx, H2B_ERR_ARG, "k > 28 (Fr two-adicity)");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)1 << k;
+  // omega_inv = ROOT_OF_UNITY_INV^(2^(S-k)), n_inv = TWO_INV^k        (arithmetic.rs:278-282)
+  static const uint64_t kRootInv[4] = {0x0ed3e50a414e6dbaull, 0xb22625f59115aba7ull, 0x1bbe587180f34361ull,
+                                       0x048127174daabc26ull};
+  Fr w;
+  for (int i = 0; i < 4; ++i) {
+    w.v[2 * i] = (uint32_t)kRootInv[i];
+    w.v[2 * i + 1] = (uint32_t)(kRootInv[i] >> 32);
+  }
+  w = to_mont(w);
+  for (uint32_t i = k; i < 28; ++i) w = sqr(w);
+  Fr n_inv = inv(add(Fr::one(), Fr::one()));
+  {
+    Fr acc = Fr::one();
+    for (uint32_t i = 0; i < k; ++i) acc = mul(acc, n_inv);
+    n_inv = from_mont(acc);  // canonical: the kernels walk its bits
+  }
+  const TwTable* tw;
+  H2B_TRY(ntt_get_table(ctx, w, k, &tw));
+  const G1Affine* d_in = reinterpret_cast<const G1Affine*>(g);
+  G1Affine* d_out = reinterpret_cast<G1Affine*>(out);
+  if (loc != H2B_DEVICE) {
+    H2B_TRY(ensure_stage(ctx, 0, n * sizeof(G1Affine)));
+    H2B_TRY(copy_h2d_any(ctx, ctx->stage[0], g, n * sizeof(G1Affine), ctx->stream));
+    d_in = reinterpret_cast<const G1Affine*>(ctx->stage[0]);
+  }
+  if (out_loc != H2B_DEVICE) {
+    H2B_TRY(ensure_stage(ctx, 1, n * sizeof(G1Affine)));
+    d_out = reinterpret_cast<G1Affine*>(ctx->stage[1]);
+  }
+  H2B_TRY(ensure_scratch(ctx, n * sizeof(G1Xyzz) + 64));
+  G1Xyzz* pts = reinterpret_cast<G1Xyzz*>(ctx->scratch);
+  Fr* d_scale = reinterpret_cast<Fr*>(pts + n);
+  H2B_CUDA(ctx, cudaMemcpyAsync(d_scale, &n_inv, sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  H2B_TRY(launch(ctx, g1_fft_bitrev_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, d_in, pts, k));
+  const uint32_t nb = (uint32_t)((n / 2 + 127) / 128);
+  for (uint32_t u = 1; u <= k; ++u)
+    H2B_TRY(launch(ctx, g1_fft_sweep_kernel, dim3(nb), dim3(128), 0, pts, k, u, (const Fr*)tw->d_lo,
+                   (const Fr*)tw->d_hi, tw->h, u == k ? (const Fr*)d_scale : (const Fr*)nullptr));
+  if (k == 0) H2B_TRY(launch(ctx, g1_scale_all_kernel, dim3(1), dim3(32), 0, pts, (uint64_t)1, (const Fr*)d_scale));
+  const uint32_t nblk = (uint32_t)(((n + kNormBatch - 1) / kNormBatch + 127) / 128);
+  H2B_TRY(launch(ctx, msm_table_normalize_kernel, dim3(nblk), dim3(128), 0, (const G1Xyzz*)pts, d_out, (uint64_t)n));
+  if (out_loc != H2B_DEVICE) H2B_TRY(copy_d2h_any(ctx, out, d_out, n * sizeof(G1Affine), ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return H2B_OK;
 }
 

@@ -723,9 +723,10 @@ extern "C" int h2b_domain_new(h2b_ctx* ctx, uint32_t j, uint32_t k, h2b_domain**
                                     0xb3c4d79d41a91758ull, 0x0ull};
   const uint32_t S = 28;
   const uint32_t qd = j - 1;  // quotient_poly_degree, domain.rs:41
+  if (k > S) return fail(ctx, H2B_ERR_ARG, "k exceeds Fr two-adicity 28");  // before any shift by k
   uint32_t ek = k;
   while (ek <= S && (1ull << ek) < (1ull << k) * qd) ++ek;  // domain.rs:49-52
-  if (k > S || ek > S) return fail(ctx, H2B_ERR_ARG, "extended_k exceeds Fr two-adicity 28");
+  if (ek > S) return fail(ctx, H2B_ERR_ARG, "extended_k exceeds Fr two-adicity 28");
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
 
   h2b_domain* d = new h2b_domain();

@@ -342,6 +342,51 @@ extern "C" int h2b_poly_scale(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n, const 
   return poly_elementwise(ctx, a, nullptr, loc, n, 2, scalar);
 }
 
+// Fr::to_repr / Fr::from_repr over a whole polynomial (SerdeFormat::Processed of Polynomial::write / read,
+// poly.rs + helpers.rs:54-94): Montgomery limbs <-> canonical little-endian integers.  from_repr rejects
+// values >= r (`ok` = 0), like the reference's CtOption; with check_only the limbs are only range-checked
+// (SerdeObject::read_raw of RawBytes).
+namespace h2b {
+__global__ void fr_repr_kernel(Fr* a, uint64_t n, int mode, int* bad) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    Fr x = ld_fp(a + i);
+    if (mode == 0) {
+      st_fp(a + i, from_mont(x));
+      continue;
+    }
+    uint32_t m[8], t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = FrParams::mod(j);
+    if (sub8(t, x.v, m) == 0) atomicOr(bad, 1);  // no borrow: x >= r
+    if (mode == 1) st_fp(a + i, to_mont(x));
+  }
+}
+}  // namespace h2b
+
+extern "C" int h2b_fr_repr(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n, int mode, int* ok) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if ((n && !a) || mode < 0 || mode > 2 || (mode && !ok)) return fail(ctx, H2B_ERR_ARG, "bad argument");
+  if (ok) *ok = 1;
+  if (n == 0) return H2B_OK;
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  const Fr* d_c;
+  H2B_TRY(stage_in(ctx, 0, a, loc, n, &d_c));
+  Fr* d = const_cast<Fr*>(d_c);
+  H2B_TRY(ensure_scratch(ctx, 64));
+  int* d_bad = reinterpret_cast<int*>(ctx->scratch);
+  H2B_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  const uint64_t want = (n + 255) / 256, cap = (uint64_t)ctx->sm_count * 16;
+  H2B_TRY(launch(ctx, fr_repr_kernel, dim3((uint32_t)(want < cap ? want : cap)), dim3(256), 0, d, (uint64_t)n, mode, d_bad));
+  int bad = 0;
+  H2B_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (loc != H2B_DEVICE && mode != 2)
+    H2B_CUDA(ctx, cudaMemcpyAsync(a, d, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ok) *ok = bad ? 0 : 1;
+  return H2B_OK;
+}
+
 extern "C" int h2b_batch_invert(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n) {
   if (!ctx) return H2B_ERR_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);

@@ -27,12 +27,22 @@ H2B_D bool g1_on_curve(const G1Affine& p) {
   return sqr(p.y) == add(mul(sqr(p.x), p.x), fq_three());
 }
 
+// limbs < q: SerdeObject::read_raw rejects non-canonical coordinates before it checks the curve equation.  A
+// residue such as x + q passes the Montgomery curve check, but the group law's is_zero() / == (P + P, P - P and
+// identity detection in ec.cuh) assume reduced limbs.
+H2B_D bool fq_is_canonical(const Fq& a) {
+  uint32_t m[8], t[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = FqParams::mod(j);
+  return sub8(t, a.v, m) != 0;  // borrow: a < q
+}
+
 __global__ void g1_check_kernel(const G1Affine* pts, uint64_t n, int* err) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     G1Affine p;
     p.x = ld_fp(&pts[i].x);
     p.y = ld_fp(&pts[i].y);
-    if (!g1_on_curve(p)) atomicOr(err, 1);
+    if (!fq_is_canonical(p.x) || !fq_is_canonical(p.y) || !g1_on_curve(p)) atomicOr(err, 1);
   }
 }
 

@@ -182,6 +182,29 @@ class ShardedBases:
     def __len__(self) -> int:
         return self.n
 
+    def check_replicated(self, what: str, digest: Optional[bytes]) -> None:
+        """Raise unless `digest` is the same on every rank of the group.
+
+        The sharded prover multiplies, on every rank, that rank's point range of a polynomial that is supposed
+        to be REPLICATED (same witness, same blinding rows): with per-rank entropy (an OsRng, as the reference
+        passes) the all-gathered commitment would be a sum of partial MSMs over different polynomials and the
+        proof silently invalid.  `create_proof` calls this with the rng's position before it draws anything and
+        with the transcript state after the openings.  digest = None (an rng that cannot report its state) is
+        only accepted if every rank passes None; the end-of-proof check still catches a divergence."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        world = dist.get_world_size(self.group)
+        dev = _group_device(self.group)
+        raw = (b"\x01" + digest[:31]) if digest is not None else bytes(32)
+        mine = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        parts = torch.empty(world * 32, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(parts, mine, group=self.group)
+        rows = parts.cpu().view(world, 32)
+        if not bool((rows == rows[0]).all()):
+            raise H2BError(_ffi.H2B_ERR_ARG, "sharded create_proof: ranks disagree on " + what)
+
     @property
     def table_window_bits(self) -> int:
         return self.local.table_window_bits
@@ -294,9 +317,28 @@ class ShardedBases:
         self.local.free()
 
 
+def broadcast_seed(seed: Optional[int] = None, group=None, src: int = 0) -> int:
+    """A 64-bit rng seed that is the same on every rank: rank `src`'s `seed` (or fresh OS entropy there) is
+    broadcast.  The sharded prover needs identical blinding factors on every rank (ShardedBases.check_replicated):
+    build the rng passed to create_proof from this, e.g. CounterRng(broadcast_seed())."""
+    import torch
+    import torch.distributed as dist
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return seed & ((1 << 64) - 1)
+    t = torch.tensor([(seed & ((1 << 64) - 1)) - (1 << 63)], dtype=torch.int64, device=_group_device(group))
+    dist.broadcast(t, src=src, group=group)
+    return int(t.item()) + (1 << 63)
+
+
 def shard_params(params, group=None, precompute: bool = True):
     """ParamsKZG with `g` and `g_lagrange` replaced by their ShardedBases (the replicated full vectors
-    are released): keygen and create_proof on the result commit on every GPU of the group."""
+    are released): keygen and create_proof on the result commit on every GPU of the group.
+
+    REQUIREMENT (checked by create_proof through ShardedBases.check_replicated, H2BError otherwise): every rank
+    passes the same witness and an rng in the same state -- e.g. CounterRng(broadcast_seed()) -- because the
+    polynomials are replicated and only the base vectors are sharded."""
     from .api import ParamsKZG
     out = ParamsKZG(params.ctx, params.k,
                     ShardedBases.from_full(params.ctx, params.g, group, precompute),

@@ -84,6 +84,16 @@ class Blake2bWrite:
     def finalize(self) -> bytes:
         return bytes(self.writer)
 
+    def state_digest(self) -> bytes:
+        """A digest of everything absorbed so far (the sharded prover compares it across ranks)."""
+        return self.state.copy().digest()[:32]
+
+
+def rng_state_digest(rng) -> Optional[bytes]:
+    """A digest of the rng's position in its stream, or None for an rng that cannot tell (OsRng-like)."""
+    f = getattr(rng, "state_digest", None)
+    return f() if f is not None else None
+
 
 # --------------------------------------------------------------------------
 # RngCore implementations (the reference only ever passes OsRng; a seeded rng is what makes proof
@@ -110,6 +120,9 @@ class XorShiftRng:
         lo = self.next_u32()
         return (self.next_u32() << 32) | lo
 
+    def state_digest(self) -> bytes:
+        return hashlib.sha256(b"xorshift" + b"".join(v.to_bytes(4, "little") for v in (self.x, self.y, self.z, self.w))).digest()
+
     def fill_u64(self, count: int) -> np.ndarray:
         return np.fromiter((self.next_u64() for _ in range(count)), dtype=np.uint64, count=count)
 
@@ -135,6 +148,9 @@ class CounterRng:
 
     def next_u64(self) -> int:
         return int(self.fill_u64(1)[0])
+
+    def state_digest(self) -> bytes:
+        return hashlib.sha256(b"counter" + self.seed.to_bytes(8, "little") + self.ctr.to_bytes(16, "little")).digest()
 
     def fill_fr_device(self, ctx: Context, n: int, out: DeviceBuffer) -> None:
         """n draws of Fr::random straight into device memory: the stream is generated by the same
@@ -344,7 +360,9 @@ def keygen(params: ParamsKZG, cs: ConstraintSystem, fixed_values: Sequence, copi
         asm.copy(*c)
     omega = dom.constant("omega")
     ones = np.tile(fr_encode([omega]), (n, 1))
-    omega_powers = ctx.running_product(ctx.upload_fr(ones), 1, n)  # [omega^0 .. omega^(n-1)]
+    ones_dev = ctx.upload_fr(ones)
+    omega_powers = ctx.running_product(ones_dev, 1, n)  # [omega^0 .. omega^(n-1)]
+    ones_dev.free()
     table = np.empty((max(len(pc), 1) * n, 4), dtype=np.uint64)   # deltaomega, flat (i', j')
     for i in range(len(pc)):
         col = ctx.clone(omega_powers, n * 32)
@@ -453,6 +471,12 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
         dom.lagrange_to_coeff_device(out)
         return out
 
+    # ONE proof on several GPUs (dist.ShardedBases): every rank must hold the same polynomials, hence draw the
+    # same blinding factors.  Checked here (rng position) and after the openings (transcript), never assumed.
+    replicated = getattr(params.g, "check_replicated", None)
+    if replicated is not None:
+        replicated("the rng passed to create_proof (same seed and position on every rank: dist.broadcast_seed)",
+                   rng_state_digest(rng))
     transcript.common_scalar(pk.transcript_repr)  # :62
 
     # ---- instances (:79-138; QUERY_INSTANCE = false) ----
@@ -725,6 +749,9 @@ def create_proof(params: ParamsKZG, pk: ProvingKey, witnesses: Sequence[Callable
     queries.append((x, h_poly))
     queries.append((x, random_poly))
     (prover or ProverGWC)(params).create_proof(rng, transcript, queries)
+    if replicated is not None:
+        replicated("the transcript at the end of create_proof (witness and rng must be identical on every rank)",
+                   transcript.state_digest())
     lap("multiopen")
 
     # per-proof device buffers

@@ -258,19 +258,16 @@ def _g1_point_read(ctx: Context, reader: BinaryIO, fmt: str):
     return p
 
 
-def _field_op(ctx: Context, op: int, arr: np.ndarray) -> np.ndarray:
-    out = np.empty_like(arr)
-    ctx._check(ctx.lib.h2b_test_field_op(ctx.h, 0, op, C.c_void_p(arr.ctypes.data), C.c_void_p(arr.ctypes.data),
-                                         C.c_void_p(out.ctypes.data), arr.shape[0]))
-    return out
-
-
 def _poly_write(ctx: Context, buf, count: int, writer: BinaryIO, fmt: str) -> None:
     """Polynomial::write: u32 big-endian length, then the elements (Processed: canonical repr; else raw limbs)."""
     writer.write(count.to_bytes(4, "big"))
-    limbs = buf.download(count)
-    if fmt == PROCESSED:
-        limbs = _field_op(ctx, 5, limbs)  # Montgomery -> canonical (to_repr), on the device
+    if fmt == PROCESSED:  # Montgomery -> canonical (to_repr) on a device copy
+        tmp = ctx.clone(buf, max(count, 1) * 32)
+        ctx._check(ctx.lib.h2b_fr_repr(ctx.h, tmp.ptr, H2B_DEVICE, count, 0, None))
+        limbs = tmp.download(count)
+        tmp.free()
+    else:
+        limbs = buf.download(count)
     writer.write(limbs.tobytes())
 
 
@@ -284,15 +281,14 @@ def _poly_read(ctx: Context, reader: BinaryIO, fmt: str, expect: int):
     raw = reader.read(count * 32)
     if len(raw) != count * 32:
         raise H2BError(_ffi.H2B_ERR_LENGTH, "unexpected end of file")
-    limbs = np.frombuffer(raw, dtype=np.uint64).reshape(count, 4)
-    if fmt != RAW_BYTES_UNCHECKED:  # from_repr / read_raw reject values >= r
-        top = limbs[:, 3].astype(object) << 192 | limbs[:, 2].astype(object) << 128 | \
-            limbs[:, 1].astype(object) << 64 | limbs[:, 0].astype(object)
-        if any(int(v) >= R_MOD for v in top):
+    buf = ctx.upload_fr(np.frombuffer(raw, dtype=np.uint64).reshape(count, 4))
+    if fmt != RAW_BYTES_UNCHECKED:  # from_repr / read_raw reject values >= r: checked (and converted) on the device
+        ok = C.c_int(1)
+        ctx._check(ctx.lib.h2b_fr_repr(ctx.h, buf.ptr, H2B_DEVICE, count, 1 if fmt == PROCESSED else 2, C.byref(ok)))
+        if not ok.value:
+            buf.free()
             raise H2BError(_ffi.H2B_ERR_ARG, "Invalid prime field point encoding")
-    if fmt == PROCESSED:
-        limbs = _field_op(ctx, 4, np.ascontiguousarray(limbs))  # canonical -> Montgomery
-    return ctx.upload_fr(limbs)
+    return buf
 
 
 def _poly_vec_write(ctx, bufs, count, writer, fmt) -> None:

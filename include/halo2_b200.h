@@ -110,6 +110,16 @@ int h2b_g1_mul_generator(h2b_ctx* ctx, const h2b_fr* scalars, int loc, size_t n,
  * (arithmetic.rs:153) when an MSM is sharded by point range across GPUs. */
 int h2b_g1_sum(const h2b_g1_affine* pts, size_t n, h2b_g1_affine* out);
 
+/* small_multiexp(coeffs, bases): double-and-add with shared doublings over a handful of points, on the
+ * host like the reference's (not a hot path).                 arithmetic.rs:105-125 */
+int h2b_small_multiexp(const h2b_fr* coeffs, const h2b_g1_affine* bases, size_t n, h2b_g1* out);
+/* g_to_lagrange(g.to_curve(), k): inverse FFT over the 2^k curve points g (omega^-1 butterflies with
+ * group_add / group_sub / group_scale), every point scaled by 1/n, batch-normalised.  arithmetic.rs:277-301
+ * The KZG caller is ParamsKZG::downsize(k): g.truncate(1 << k); g_lagrange = g_to_lagrange(g, k)
+ *                                                                  poly/kzg/commitment.rs:267-275 */
+int h2b_g_to_lagrange(h2b_ctx* ctx, const h2b_g1_affine* g, int loc, uint32_t k, h2b_g1_affine* out,
+                      int out_loc);
+
 /* ---- NTT --------------------------------------------------------------- */
 /* best_fft(a, omega, log_n): in place, natural order in and out.  arithmetic.rs:171
  * omega must be a primitive 2^log_n-th root of unity (every non-bench caller
@@ -168,6 +178,11 @@ int h2b_inner_product(h2b_ctx* ctx, const h2b_fr* a, const h2b_fr* b, int loc, s
 int h2b_poly_add(h2b_ctx* ctx, h2b_fr* lhs, const h2b_fr* rhs, int loc, size_t n);
 int h2b_poly_sub(h2b_ctx* ctx, h2b_fr* lhs, const h2b_fr* rhs, int loc, size_t n);
 int h2b_poly_scale(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n, const h2b_fr* scalar);
+/* Fr::to_repr / from_repr over n elements in place (Polynomial::write / read with SerdeFormat::Processed,
+ * helpers.rs:54-94): mode 0 = Montgomery limbs -> canonical little-endian integers; mode 1 = canonical ->
+ * Montgomery, *ok = 0 if any value is >= r (the reference's from_repr returns None); mode 2 = range check
+ * only (read_raw of SerdeFormat::RawBytes), data untouched. */
+int h2b_fr_repr(h2b_ctx* ctx, h2b_fr* a, int loc, size_t n, int mode, int* ok);
 
 /* The two data-parallel pieces of the grand-product constructions:
  * a[i] <- 1/a[i] in place, zeros stay zero (ff::BatchInvert, plonk/permutation/prover.rs:119), and
@@ -320,8 +335,7 @@ float h2b_ctx_last_kernel_ms(const h2b_ctx* ctx);
 /* durations (ms) of the passes of the last NTT call made in profile mode; returns their number */
 int h2b_ctx_last_ntt_passes(h2b_ctx* ctx, float* ms, int cap);
 /* Element-wise device ops (op: 0 mul, 1 add, 2 sub, 3 sqr, 4 to_mont, 5 from_mont,
- * 6 neg, 7 inv; through the 9 x 29-bit limb path: 8 mul, 9 sub, 10 a - 3b, 11 pack(unpack(a)),
- * 12 (a - b)(a + b)); field: 0 Fr, 1 Fq.  Host pointers. */
+ * 6 neg, 7 inv); field: 0 Fr, 1 Fq.  Host pointers. */
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const h2b_fr* a, const h2b_fr* b,
                       h2b_fr* out, size_t n);
 /* Same ops on the host code path of the same header (no device needed). */

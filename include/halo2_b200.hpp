@@ -184,6 +184,26 @@ inline G1 best_multiexp(const std::vector<Fr>& coeffs, const std::vector<G1Affin
   return best_multiexp(coeffs.data(), coeffs.size(), bases.data(), bases.size());
 }
 
+/// small_multiexp(coeffs, bases): shared-doubling double-and-add, host-side            arithmetic.rs:105-125
+inline G1 small_multiexp(const std::vector<Fr>& coeffs, const std::vector<G1Affine>& bases) {
+  if (coeffs.size() > bases.size()) throw Panic("index out of bounds: bases[coeff_idx] (arithmetic.rs:117)");
+  G1 out;
+  detail::check(nullptr, h2b_small_multiexp(coeffs.data(), reinterpret_cast<const h2b_g1_affine*>(bases.data()), coeffs.size(),
+                                            reinterpret_cast<h2b_g1*>(&out)), "small_multiexp");
+  return out;
+}
+
+/// g_to_lagrange(g_projective, k) -> Vec<C>: inverse FFT over curve points, 1/n, batch_normalize; takes the
+/// affine forms (the reference's caller builds the projective vector from them)    arithmetic.rs:277-301
+inline std::vector<G1Affine> g_to_lagrange(const std::vector<G1Affine>& g, uint32_t k) {
+  if (k >= 64 || g.size() != (size_t(1) << k)) throw Panic("assertion failed: `(left == right)` a.len() == 1 << log_n (arithmetic.rs:184)");
+  h2b_ctx* ctx = detail::backend().ctx;
+  std::vector<G1Affine> out(g.size());
+  detail::check(ctx, h2b_g_to_lagrange(ctx, reinterpret_cast<const h2b_g1_affine*>(g.data()), H2B_HOST, k,
+                                       reinterpret_cast<h2b_g1_affine*>(out.data()), H2B_HOST), "g_to_lagrange");
+  return out;
+}
+
 /// best_fft(a, omega, log_n): in place, natural order                        arithmetic.rs:171
 /// omega must be a primitive 2^log_n-th root of unity (every non-bench caller passes one).
 inline void best_fft(Fr* a, size_t len, const Fr& omega, uint32_t log_n) {
@@ -495,6 +515,23 @@ class ParamsKZG {
       }
     }
     writer.write(reinterpret_cast<const char*>(g2_bytes_.data()), std::streamsize(g2_bytes_.size()));
+  }
+
+  /// downsize(k): g.truncate(1 << k); g_lagrange = g_to_lagrange(g, k) -- on the device    commitment.rs:267-275
+  void downsize(uint32_t k) {
+    if (k > k_) throw Panic("assertion failed: k <= self.k (commitment.rs:268)");
+    const size_t n = size_t(1) << k;
+    const bool table = h2b_bases_table_window_bits(g_.get()) != 0;
+    const auto* gp = static_cast<const G1Affine*>(h2b_bases_device_ptr(g_.get()));
+    auto new_g = upload(ctx_, gp, n, H2B_DEVICE, table);
+    void* dev = nullptr;
+    detail::check(ctx_, h2b_device_alloc(ctx_, n * sizeof(G1Affine), &dev), "h2b_device_alloc");
+    const int rc = h2b_g_to_lagrange(ctx_, reinterpret_cast<const h2b_g1_affine*>(gp), H2B_DEVICE, k, static_cast<h2b_g1_affine*>(dev), H2B_DEVICE);
+    std::shared_ptr<h2b_bases> new_l;
+    if (rc == H2B_OK) new_l = upload(ctx_, static_cast<const G1Affine*>(dev), n, H2B_DEVICE, table);
+    h2b_device_free(ctx_, dev);
+    detail::check(ctx_, rc, "h2b_g_to_lagrange");
+    g_ = new_g, g_lagrange_ = new_l, k_ = k, n_ = n;
   }
 
   uint32_t k() const { return k_; }       // commitment.rs:254

@@ -228,6 +228,19 @@ def multiexp_serial(coeffs: Sequence[int], bases: Sequence[Point], acc):
     return acc
 
 
+def small_multiexp(coeffs: Sequence[int], bases: Sequence[Point]) -> Point:
+    """arithmetic.rs:105-125: double-and-add, doublings shared across the points."""
+    reprs = [(c % R_MOD).to_bytes(32, "little") for c in coeffs]  # to_repr(), :106
+    acc = (0, 1, 0)  # C::Curve::identity(), :107
+    for byte_idx in range(31, -1, -1):  # :110
+        for bit_idx in range(7, -1, -1):  # :112
+            acc = _jac_double(acc)  # :113
+            for coeff_idx in range(len(reprs)):  # :115
+                if (reprs[coeff_idx][byte_idx] >> bit_idx) & 1:  # :116-117
+                    acc = _jac_add(acc, _to_jac(bases[coeff_idx]))  # :118
+    return _to_affine(acc)
+
+
 def best_multiexp(coeffs: Sequence[int], bases: Sequence[Point], num_threads: int = 1) -> Point:
     """arithmetic.rs:132-159.  `num_threads` plays rayon's current_num_threads();
     it changes the chunking and the window size but never the result."""
@@ -287,6 +300,45 @@ def best_fft(a: List[int], omega: int, log_n: int) -> None:
                 a[start + half + i] = (u - t) % r
         chunk *= 2
         twiddle_chunk //= 2
+
+
+def best_fft_group(a: list, omega: int, log_n: int) -> None:
+    """best_fft over curve points (G = C::Curve, arithmetic.rs:171-234): the same butterflies with
+    group_add / group_sub and group_scale = point * scalar.  `a`: Jacobian points (None = identity)."""
+    n = len(a)
+    assert n == 1 << log_n  # :184
+    r = R_MOD
+    for k in range(n):  # :186-191
+        rk = _bitreverse(k, log_n)
+        if k < rk:
+            a[k], a[rk] = a[rk], a[k]
+    tw = [1] * max(n // 2, 1)  # :194-200
+    for i in range(1, n // 2):
+        tw[i] = tw[i - 1] * omega % r
+    chunk, twiddle_chunk = 2, n // 2
+    for _ in range(log_n):  # :202-230
+        half = chunk // 2
+        for start in range(0, n, chunk):
+            for i in range(half):
+                t = _jac_mul(a[start + half + i], tw[i * twiddle_chunk])
+                u = a[start + i]
+                a[start + i] = _jac_add(u, t)
+                a[start + half + i] = _jac_add(u, (t[0], (-t[1]) % Q_MOD, t[2]))
+        chunk *= 2
+        twiddle_chunk //= 2
+
+
+def g_to_lagrange(g: Sequence[Point], k: int) -> List[Point]:
+    """arithmetic.rs:277-301."""
+    r = R_MOD
+    n_inv = pow(pow(2, -1, r), k, r)  # TWO_INV.pow_vartime([k]), :278
+    omega_inv = ROOT_OF_UNITY_INV  # :279-282
+    for _ in range(k, S):
+        omega_inv = omega_inv * omega_inv % r
+    pts = [_to_jac(p) for p in g]
+    best_fft_group(pts, omega_inv, k)  # :285
+    pts = [_jac_mul(p, n_inv) for p in pts]  # :286-290
+    return batch_to_affine(pts)  # :292-298
 
 
 def dft_naive(a: Sequence[int], omega: int) -> List[int]:
@@ -459,6 +511,13 @@ class ParamsKZG:
             scalar = multiplier * rp % r * pow((s - rp) % r, -1, r) % r
             glj.append(_jac_mul(G, scalar))
         return cls(k, g, batch_to_affine(glj))
+
+    def downsize(self, k: int) -> None:
+        """kzg/commitment.rs:267-275"""
+        assert k <= self.k  # :268
+        self.k, self.n = k, 1 << k
+        self.g = self.g[: self.n]  # :273
+        self.g_lagrange = g_to_lagrange(self.g, k)  # :274
 
     def commit(self, poly: Sequence[int]) -> Point:
         # :327-334 (blind ignored)

@@ -19,7 +19,7 @@
 // Linear maps (the NTT) need no conversion at all: only the twiddles are put in
 // R9 form, since mont29(v, w * R9) = v * w whatever form v is in.
 #pragma once
-#include "field.cuh"
+#include "../halo2-pse_b200/csrc/field.cuh"
 
 namespace h2b {
 

@@ -2,7 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
-#include "../halo2-pse_b200/csrc/field29.cuh"
+#include "field29.cuh"
 using namespace h2b;
 
 template <int NCH, int W>

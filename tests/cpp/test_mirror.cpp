@@ -117,6 +117,29 @@ static void test_fft_and_multiexp_definitions() {
   CHECK(g[1] + g[1] == arithmetic::best_multiexp(std::vector<Fr>{Fr::from(10)}, std::vector<G1Affine>{G1Affine::generator()}).to_affine());
 }
 
+static void test_downsize_and_small_multiexp() {  // kzg/commitment.rs:267-275, arithmetic.rs:105-125, 277-301
+  const Fr s5 = Fr::from(0x1234567);
+  auto big = poly::kzg::ParamsKZG::setup(5, s5, false);
+  const auto small = poly::kzg::ParamsKZG::setup(3, s5, false);
+  // g_to_lagrange of the first 8 points of the k = 5 SRS is the k = 3 SRS's g_lagrange
+  auto g = big.get_g();
+  g.resize(8);
+  CHECK(arithmetic::g_to_lagrange(g, 3) == small.get_g_lagrange());
+  big.downsize(3);
+  CHECK(big.k() == 3 && big.n() == 8);
+  CHECK(big.get_g() == small.get_g());
+  CHECK(big.get_g_lagrange() == small.get_g_lagrange());
+  bool panicked = false;
+  try { big.downsize(4); } catch (const Panic&) { panicked = true; }
+  CHECK(panicked);
+  // small_multiexp == best_multiexp on a handful of points, zero and r - 1 scalars included
+  uint64_t st = 9;
+  std::vector<Fr> c = {random_fr(st), Fr::zero(), Fr::zero() - Fr::one(), random_fr(st)};
+  const std::vector<G1Affine> b(g.begin(), g.begin() + 4);
+  CHECK(arithmetic::small_multiexp(c, b) == arithmetic::best_multiexp(c, b));
+  CHECK(arithmetic::small_multiexp({}, {}).to_affine().is_identity());
+}
+
 static void test_extended_round_trip() {  // coeff_to_extended / extended_to_coeff / divide_by_vanishing_poly
   uint64_t s = 5;
   poly::EvaluationDomain domain(5, 6);  // j = 5: extended_k = k + 2
@@ -210,6 +233,7 @@ int main(int argc, char** argv) {
     test_commit_lagrange(big_k);
     test_fft_and_multiexp_definitions();
     test_extended_round_trip();
+    test_downsize_and_small_multiexp();
     test_poly_ops();
     test_panics();
   } catch (const std::exception& e) {

@@ -68,6 +68,17 @@ def _worker(rank, world, port, emu, q):
         _, opk, want = PC.oracle_bench_proof(5, 0xDEADBEEF, seed)
         assert pk.pinned == opk.debug and got == want, rank  # same vk, same proof bytes as the big-integer oracle
         pk.free()
+        # ---- the sharded prover refuses rngs that differ between ranks (silently invalid proofs otherwise) ----
+        try:
+            PC.device_bench_proof(ctx, 5, 0xDEADBEEF, bytes([7 + rank]) * 16, params_hook=lambda p: D.shard_params(p))
+        except h.H2BError as e:
+            assert "ranks disagree" in str(e), e
+        else:
+            raise AssertionError("per-rank rng seeds were accepted by the sharded create_proof")
+        # ... and a broadcast seed is the same everywhere
+        seed = D.broadcast_seed(1000 + rank)
+        assert seed == 1000
+        assert D.broadcast_seed() == D.broadcast_seed(None) or True  # fresh entropy: just exercises the path
         ctx.close()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover

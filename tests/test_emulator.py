@@ -377,3 +377,12 @@ def test_msm_many_forms(emu_ctx, oracle_c):
     for b in dev + empty:
         b.free()
     B.free()
+
+
+def test_small_multiexp_and_g_to_lagrange(emu_ctx):
+    """SURVEY.md 8a rows a3 and a12 on the emulator (arithmetic.rs:105-125, 277-301; kzg/commitment.rs:267-275)."""
+    from tests import group_cases as G
+    G.check_small_multiexp(emu_ctx)
+    G.check_g_to_lagrange_vs_oracle(emu_ctx)
+    G.check_downsize(emu_ctx, 6, 4)
+    G.check_downsize(emu_ctx, 5, 5, precompute=True)

@@ -64,6 +64,18 @@ def test_invalid_points_are_rejected(emu_ctx, params):
     with pytest.raises(h.H2BError):
         serde.read_params(emu_ctx, io.BytesIO(bytes(raw)), serde.RAW_BYTES)
     serde.read_params(emu_ctx, io.BytesIO(bytes(raw)), serde.RAW_BYTES_UNCHECKED)  # unchecked by definition
+    # non-canonical limbs: x + q satisfies the Montgomery curve equation but SerdeObject::read_raw rejects
+    # coordinates >= q before it looks at the curve (the group law's == / is_zero need reduced limbs)
+    raw = bytearray(serde.params_to_bytes(params, serde.RAW_BYTES))
+    for coord in (0, 32):
+        bad = bytearray(raw)
+        off = 4 + 64 * 2 + coord
+        v = int.from_bytes(bad[off:off + 32], "little") + O.Q_MOD
+        assert v < 1 << 256
+        bad[off:off + 32] = v.to_bytes(32, "little")
+        with pytest.raises(h.H2BError):
+            serde.read_params(emu_ctx, io.BytesIO(bytes(bad)), serde.RAW_BYTES)
+        serde.read_params(emu_ctx, io.BytesIO(bytes(bad)), serde.RAW_BYTES_UNCHECKED)
     comp = bytearray(serde.params_to_bytes(params, serde.PROCESSED))
     # x = 4 has x^3 + 3 = 67, a non-residue mod q?  find a non-point abscissa by search
     x = next(v for v in range(2, 50) if pow((v ** 3 + 3) % O.Q_MOD, (O.Q_MOD - 1) // 2, O.Q_MOD) != 1)

@@ -720,3 +720,14 @@ def test_msm_multi_column(gpu_ctx, k, ncols, monkeypatch):
     for c in cols:
         c.free()
     bases.free()
+
+
+def test_small_multiexp_and_g_to_lagrange(gpu_ctx):
+    """SURVEY.md 8a rows a3 and a12 (arithmetic.rs:105-125, 277-301; kzg/commitment.rs:267-275): vs the oracle at
+    small k, and downsize(k - d) of a 2^k SRS == setup(k - d) bit for bit up to k = 16."""
+    from tests import group_cases as G
+    G.check_small_multiexp(gpu_ctx)
+    G.check_g_to_lagrange_vs_oracle(gpu_ctx, ks=(0, 1, 2, 3, 5, 7))
+    G.check_downsize(gpu_ctx, 10, 9)
+    G.check_downsize(gpu_ctx, 12, 12, precompute=True)
+    G.check_downsize(gpu_ctx, 16, 15)
