@@ -541,22 +541,33 @@ def run_ours(args):
     windows = (255 + c_win - 1) // c_win
     adds = n * windows
     mults = adds * MULMODS_PER_ADD * MULTS_PER_MULMOD
-    pipe = {name: ctx.pipe_peak(name) for name in ("imad_wide", "carry_chain", "fr_mul")}
+    pipe = {name: ctx.pipe_peak(name) for name in ("imad", "imad_wide", "carry_chain", "fr_mul")}
+    # The integer roofline: 32x32->64 multiplies (IMAD.WIDE.U32), measured live.  Round 1 quoted 18.5 T/s here, but
+    # that benchmark multiplied two loop-invariant registers, ptxas hoisted the product and the loop timed 64-bit
+    # ADDS.  With operands that change every iteration (SASS checked: profiles/r2_pipe_rates_sass.txt) a wide
+    # multiply issues every 4 cycles per SM sub-partition -- 32 lanes/clk/SM = 9.3 T/s at 1965 MHz, with or
+    # without an addend or a carry; only the 32-bit IMAD runs at 64 lanes/clk/SM (scripts/mulbench/pipes.cu).
     mult_peak = pipe["imad_wide"][0]
+    executed = adds * 10 * 130  # what the kernel issues: 8M + 2S per mixed XYZZ addition, 130 IMAD.WIDE per product
     roofline = {
-        "kernel": "msm_accum0_kernel (bucket accumulation, level 0)", "bound": "int32-multiply (IMAD pipe)",
+        "kernel": "msm_accum0_kernel (bucket accumulation, level 0)", "bound": "int32-multiply (IMAD.WIDE pipe)",
         "achieved": mults / (acc_ms * 1e-3) / 1e12, "peak": mult_peak / 1e12, "unit": "Tmul/s",
         "frac": mults / (acc_ms * 1e-3) / mult_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at k=24, c=22 from the committed
         # ncu --set full capture profiles/r1_final_msm_accum0_ntt_pass_k24_ncu_full.txt (28.79 GB + 0.72 GB)
         "traffic": 29.52e9 if (k == 24 and c_win == 22) else None,
+        "frac_executed": executed / (acc_ms * 1e-3) / mult_peak,
+        "executed": "n*W*10*130 IMAD.WIDE actually issued (XYZZ mixed addition 8M+2S; 128 + 2 wide multiplies per "
+                    "Montgomery product); `frac` uses the survey's algorithmic 11*136 as the contract asks",
         "mulmod_ceiling_frac": (adds * 10 / (acc_ms * 1e-3)) / (pipe["fr_mul"][1] or 1.0),
-        "peak_source": "live register-only microbenchmark h2b_pipe_peak: plain IMAD.WIDE.U32 (32x32+64) rate",
+        "peak_source": "live register-only microbenchmark h2b_pipe_peak: IMAD.WIDE.U32 (32x32->64) with operands "
+                       "that change every iteration, 32 lanes/clk/SM; round 1's 18.5 T/s was a 64-bit-add loop",
         "algorithmic": f"n*W*{MULMODS_PER_ADD}*{MULTS_PER_MULMOD} 32x32 multiplies, n=2^{k}, c={c_win}, W={windows}",
         "kernel_ms": acc_ms, "ec_adds_per_s": adds / (acc_ms * 1e-3),
         "fr_mul_microbench_Tmul_s": pipe["fr_mul"][0] / 1e12,
         "imad_wide_Tmul_s": pipe["imad_wide"][0] / 1e12,
         "imad_wide_carry_chain_Tmul_s": pipe["carry_chain"][0] / 1e12,
+        "imad_32bit_Tmul_s": pipe["imad"][0] / 1e12,
     }
     slow = max(pass_ms)
     roofline_ntt = {
@@ -567,6 +578,10 @@ def run_ours(args):
         "traffic": 1.029e9 if k == 24 else None, "peak_source": peak_src,
         "algorithmic": f"64 B per element per pass (one read + one write), n=2^{k}", "pass_ms": pass_ms,
         "int_Tmul_s": (n / 2) * k * MULTS_PER_MULMOD / (sum(pass_ms) * 1e-3) / 1e12,
+        # the binding roofline of a 256-bit NTT (max of the two): (n/2) log2 n butterflies x 136 multiplies
+        "int_frac": (n / 2) * k * MULTS_PER_MULMOD / (sum(pass_ms) * 1e-3) / mult_peak,
+        "hbm_GBps_per_pass": [64.0 * n / (t * 1e-3) / 1e9 for t in pass_ms],
+        "transform_ms": sum(pass_ms),
     }
 
     # ---- end to end through the C ABI with HOST buffers ---------------------------

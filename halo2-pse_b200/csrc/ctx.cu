@@ -317,7 +317,12 @@ __global__ void __launch_bounds__(256) pipe_peak_kernel(uint32_t* sink, uint32_t
             asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(lo) : "r"(x), "r"(y));
             acc[j] = lo;
           } else {
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(x), "r"(y));
+            // 32 x 32 -> 64 with operands that change every iteration (the low word of this accumulator times the
+            // high word of its neighbour): IMAD.WIDE.U32 Rd, Ra, Rb, RZ in SASS.  Round 1 multiplied two
+            // loop-invariant registers here; ptxas hoisted the product and the loop timed 64-bit ADDS
+            // (IADD3 + IADD3.X, 64 lanes/clk/SM), which was then quoted as the IMAD.WIDE peak.
+            const uint32_t other = (uint32_t)(acc[(j + 1) & 15] >> 32);
+            asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(acc[j]) : "r"(lo), "r"(other));
           }
 #else
           acc[j] += (uint64_t)x * y;
