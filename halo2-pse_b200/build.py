@@ -46,7 +46,7 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-c", os.path.join(CSRC, src), "-o", obj]
+              os.environ.get("H2B_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")

@@ -26,7 +26,8 @@ struct TwTable {
   Fr* d_hi;        // omega^(i << h),    i < 2^(k-h)
   Fr* d_rt;        // omega_R^i, R = 2^min(k,9), i < R   (intra-pass roots)
   // single-multiplication inter-pass twiddles (optional; nullptr -> two-level lo/hi product)
-  Fr* d_full = nullptr;  // omega^i, i < 2^(k-1); omega^(i + 2^(k-1)) = -omega^i   (first pass)
+  Fr* d_out = nullptr;   // first pass: w^(jr * K) at output index K * m2 + jr, n entries (optional)
+  uint32_t out_s1 = 0;   // first digit width the table was built for
   Fr* d_mid = nullptr;   // (omega^(2^(k-mid_log)))^i, i < 2^mid_log               (later passes)
   uint32_t mid_log = 0;
 };

@@ -48,10 +48,22 @@ struct PassParams {
   uint32_t h;
   const Fr* rt;
   uint32_t rt_log;
-  // single-level inter-pass twiddle table: w = tw1[(jr*K) << tw1_shift], negated when
-  // tw1_half != 0 and the index has bit tw1_half set (table folded by omega^(n/2) = -1)
+  // single-level inter-pass twiddle table of the later passes: w = tw1[(jr*K) << tw1_shift]
   const Fr* tw1;
-  uint32_t tw1_shift, tw1_half;
+  uint32_t tw1_shift;
+  // first pass only: inter-pass twiddle of every OUTPUT element, tw_out[K * m_2 + jr] = w^(jr * K), read with
+  // the same coalesced pattern as the store (one multiplication, no gather)
+  const Fr* tw_out;
+};
+
+// What a pass does around its R-point column DFTs; a template parameter of the register kernel, so that each
+// instantiation carries only the multiplications it needs (the all-in-one kernel was 16.8k instructions = 268 KB
+// of straight-line code, and ncu showed it stalling on instruction fetch).
+enum PassKind {
+  KIND_TWOLEVEL = 0,  // not last: twiddle = tw_lo[e & mask] * tw_hi[e >> h]   (first pass without a table)
+  KIND_OUT_TABLE = 1, // first pass: twiddle read from tw_out at the output index
+  KIND_MID_TABLE = 2, // later passes: twiddle = tw1[(jr * K) << shift]
+  KIND_LAST = 3       // last pass: natural-order scatter, optional post-scale, truncation
 };
 
 struct Tile {
@@ -102,36 +114,58 @@ H2B_HD Tile tile_geom(const PassParams& p, uint64_t t) {
   return g;
 }
 
-H2B_D Fr load_in(const PassParams& p, const Fr* in, uint64_t gi) {
+// Out-of-line product for the twiddle multiplications of the register kernel (H2B_NTT_CALL_MUL): trades a call per
+// product for a 3x smaller kernel body.
+#if defined(H2B_NTT_CALL_MUL) && defined(__CUDA_ARCH__)
+__device__ __noinline__ Fr mul_tw(Fr a, Fr b) { return mul(a, b); }
+#else
+H2B_D Fr mul_tw(const Fr& a, const Fr& b) { return mul(a, b); }
+#endif
+
+template <bool PRE>
+H2B_D Fr load_in_t(const PassParams& p, const Fr* in, uint64_t gi) {
   Fr x = (gi < p.n_in) ? ld_fp(in + gi) : Fr::zero();
-  if (p.first && p.pre) x = mul(x, ld_fp_nc(p.pre + (uint32_t)gi % p.pre_mod));
+  if (PRE) x = mul(x, ld_fp_nc(p.pre + (uint32_t)gi % p.pre_mod));
   return x;
 }
+H2B_D Fr load_in(const PassParams& p, const Fr* in, uint64_t gi) {
+  return (p.first && p.pre) ? load_in_t<true>(p, in, gi) : load_in_t<false>(p, in, gi);
+}
 
-H2B_D void store_out(const PassParams& p, Fr* out, const Tile& g, uint32_t K, uint32_t c, Fr x) {
-  if (!p.last) {
-    if (p.tw1) {
-      uint64_t idx = ((g.jr0 + c) * (uint64_t)K) << p.tw1_shift;
-      bool negate = false;
-      if (p.tw1_half) {
-        negate = (idx >> p.tw1_half) & 1;
-        idx &= (1ull << p.tw1_half) - 1;
-      }
-      x = mul(x, ld_fp_nc(p.tw1 + idx));
-      if (negate) x = neg(x);
-    } else {
-      const uint64_t e = ((g.jr0 + c) * (uint64_t)K) << (p.k - p.lm);
-      const uint32_t elo = (uint32_t)e & ((1u << p.h) - 1u);
-      const uint32_t ehi = (uint32_t)(e >> p.h);
-      x = mul(x, ld_fp_nc(p.tw_lo + elo));
-      x = mul(x, ld_fp_nc(p.tw_hi + ehi));
-    }
-    st_fp(out + g.out_base + (uint64_t)K * g.out_rs + c, x);
-  } else {
+template <int KIND>
+H2B_D void store_out_t(const PassParams& p, Fr* out, const Tile& g, uint32_t K, uint32_t c, Fr x) {
+  if (KIND == KIND_LAST) {
     const uint64_t Ko = g.out_base + (uint64_t)K * g.out_rs + c;
-    if (p.post) x = mul(x, ld_fp_nc(p.post + (uint32_t)Ko % p.post_mod));
+    if (p.post) x = mul_tw(x, ld_fp_nc(p.post + (uint32_t)Ko % p.post_mod));
     if (Ko < p.n_out) st_fp(out + Ko, x);
+    return;
   }
+  const uint64_t o = g.out_base + (uint64_t)K * g.out_rs + c;
+  if (KIND == KIND_OUT_TABLE) {
+    x = mul_tw(x, ld_fp_nc(p.tw_out + o));
+  } else if (KIND == KIND_MID_TABLE) {
+    const uint64_t idx = ((g.jr0 + c) * (uint64_t)K) << p.tw1_shift;
+    x = mul_tw(x, ld_fp_nc(p.tw1 + idx));
+  } else {
+    const uint64_t e = ((g.jr0 + c) * (uint64_t)K) << (p.k - p.lm);
+    const uint32_t elo = (uint32_t)e & ((1u << p.h) - 1u);
+    const uint32_t ehi = (uint32_t)(e >> p.h);
+    x = mul_tw(x, ld_fp_nc(p.tw_lo + elo));
+    x = mul_tw(x, ld_fp_nc(p.tw_hi + ehi));
+  }
+  st_fp(out + o, x);
+}
+
+// the generic kernel keeps the run-time dispatch (tiny transforms only)
+H2B_D void store_out(const PassParams& p, Fr* out, const Tile& g, uint32_t K, uint32_t c, Fr x) {
+  if (p.last)
+    store_out_t<KIND_LAST>(p, out, g, K, c, x);
+  else if (p.tw_out)
+    store_out_t<KIND_OUT_TABLE>(p, out, g, K, c, x);
+  else if (p.tw1)
+    store_out_t<KIND_MID_TABLE>(p, out, g, K, c, x);
+  else
+    store_out_t<KIND_TWOLEVEL>(p, out, g, K, c, x);
 }
 
 H2B_HD uint32_t bitrev32(uint32_t x, uint32_t bits) {
@@ -211,7 +245,7 @@ H2B_D void dft8(Fr* x, const Fr* rt, uint32_t rt_log) {
   x[7] = sub(f0, f1);
 }
 
-template <int S>
+template <int S, int KIND, bool PRE>
 __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   constexpr int R = 1 << S, T = R / 8, LC = 11 - S, C = 1 << LC;
   constexpr int LM2 = S - 6, M2 = 1 << LM2;  // 8, 4, 2, 1
@@ -246,11 +280,11 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     const uint32_t row = a * T + u;
-    x[a] = load_in(p, in, g.in_base + row * g.in_rs + c * g.in_cs);
+    x[a] = load_in_t<PRE>(p, in, g.in_base + row * g.in_rs + c * g.in_cs);
   }
   dft8(x, p.rt, p.rt_log);
 #pragma unroll
-  for (int Ka = 1; Ka < 8; ++Ka) x[Ka] = mul(x[Ka], ld_fp_nc(p.rt + ((u * Ka) << rsh)));
+  for (int Ka = 1; Ka < 8; ++Ka) x[Ka] = mul_tw(x[Ka], ld_fp_nc(p.rt + ((u * Ka) << rsh)));
 #pragma unroll
   for (int Ka = 0; Ka < 8; ++Ka) put(Ka * T + u, x[Ka]);
   __syncthreads();
@@ -261,12 +295,12 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   dft8(x, p.rt, p.rt_log);
   if (M2 == 1) {
 #pragma unroll
-    for (int Ka2 = 0; Ka2 < 8; ++Ka2) store_out(p, out, g, Ka + 8 * Ka2, c, x[Ka2]);
+    for (int Ka2 = 0; Ka2 < 8; ++Ka2) store_out_t<KIND>(p, out, g, Ka + 8 * Ka2, c, x[Ka2]);
     return;
   }
 #pragma unroll
   for (int Ka2 = 1; Ka2 < 8; ++Ka2)
-    x[Ka2] = mul(x[Ka2], ld_fp_nc(p.rt + ((8 * b2 * Ka2) << rsh)));
+    x[Ka2] = mul_tw(x[Ka2], ld_fp_nc(p.rt + ((8 * b2 * Ka2) << rsh)));
 #pragma unroll
   for (int Ka2 = 0; Ka2 < 8; ++Ka2) put(Ka * T + Ka2 * M2 + b2, x[Ka2]);
   __syncthreads();
@@ -278,7 +312,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
     dft8(x, p.rt, p.rt_log);
     const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) store_out(p, out, g, K0 + 64 * i, c, x[i]);
+    for (int i = 0; i < 8; ++i) store_out_t<KIND>(p, out, g, K0 + 64 * i, c, x[i]);
   } else if (M2 == 4) {
     const Fr w4 = ld_fp_nc(p.rt + (1u << (p.rt_log - 2)));
 #pragma unroll
@@ -287,10 +321,10 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
       Fr v0 = get(gq * 4 + 0), v1 = get(gq * 4 + 1), v2 = get(gq * 4 + 2), v3 = get(gq * 4 + 3);
       Fr t0 = add(v0, v2), t1 = sub(v0, v2), t2 = add(v1, v3), t3 = mul(sub(v1, v3), w4);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
-      store_out(p, out, g, K0, c, add(t0, t2));
-      store_out(p, out, g, K0 + 64, c, add(t1, t3));
-      store_out(p, out, g, K0 + 128, c, sub(t0, t2));
-      store_out(p, out, g, K0 + 192, c, sub(t1, t3));
+      store_out_t<KIND>(p, out, g, K0, c, add(t0, t2));
+      store_out_t<KIND>(p, out, g, K0 + 64, c, add(t1, t3));
+      store_out_t<KIND>(p, out, g, K0 + 128, c, sub(t0, t2));
+      store_out_t<KIND>(p, out, g, K0 + 192, c, sub(t1, t3));
     }
   } else {
 #pragma unroll
@@ -298,8 +332,8 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
       const uint32_t gq = u + 16 * i;
       Fr v0 = get(gq * 2 + 0), v1 = get(gq * 2 + 1);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
-      store_out(p, out, g, K0, c, add(v0, v1));
-      store_out(p, out, g, K0 + 64, c, sub(v0, v1));
+      store_out_t<KIND>(p, out, g, K0, c, add(v0, v1));
+      store_out_t<KIND>(p, out, g, K0 + 64, c, sub(v0, v1));
     }
   }
 }
@@ -326,6 +360,17 @@ __global__ void pow_table_kernel(Fr* tab, Fr base, uint32_t shift, uint32_t coun
     e >>= 1;
   }
   tab[i] = r;
+}
+
+// tab[K * m2 + jr] = w^(jr * K), K < 2^s1, jr < m2 = 2^(k - s1): the first pass's inter-pass twiddles in the order
+// the pass stores its outputs (two-level product, once per (omega, k))
+__global__ void tw_out_table_kernel(Fr* tab, uint32_t k, uint32_t s1, const Fr* tw_lo, const Fr* tw_hi, uint32_t h) {
+  const uint64_t n = 1ull << k;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t K = i >> (k - s1), jr = i & ((1ull << (k - s1)) - 1);
+    const uint64_t e = jr * K;
+    st_fp(tab + i, mul(ld_fp_nc(tw_lo + (uint32_t)(e & ((1ull << h) - 1))), ld_fp_nc(tw_hi + (uint32_t)(e >> h))));
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -476,14 +521,23 @@ int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t k, const TwTable** out
       t.d_mid = nullptr;
       cudaGetLastError();
     }
-    // Measured on B200 at k = 24: the random 32-byte reads of a 256 MiB table cost more (2.18 ms)
-    // than the second multiplication they save (1.62 ms): opt-in only.
-    if (k <= 26 && getenv("H2B_NTT_FULL_TABLE") != nullptr) {
-      const uint32_t nfull = 1u << (k - 1);
-      if (cudaMalloc((void**)&t.d_full, (size_t)nfull * sizeof(Fr)) == cudaSuccess) {
-        H2B_TRY(launch(ctx, pow_table_kernel, dim3((nfull + 127) / 128), dim3(128), 0, t.d_full, omega, 0u, nfull));
+    // First pass: one table entry per OUTPUT element, streamed with the store's own coalesced pattern (n * 32 B:
+    // 512 MiB at k = 24).  One multiplication instead of the two of the two-level tables; the extra HBM read is
+    // free next to the arithmetic (a pass moves 64 B per element in the time of ~4 modular multiplications).
+    // (A folded table indexed by the exponent was measured slower in round 1: random 32-byte reads.)
+    uint32_t out_lo = 18, out_hi = 26;
+    if (const char* e = getenv("H2B_NTT_OUT_TABLE")) {
+      if (atoi(e) == 0) out_lo = 99;
+      else if (atoi(e) > 1) out_lo = (uint32_t)atoi(e);
+    }
+    if (k >= out_lo && k <= out_hi) {
+      const uint64_t nfull = 1ull << k;
+      if (cudaMalloc((void**)&t.d_out, (size_t)nfull * sizeof(Fr)) == cudaSuccess) {
+        H2B_TRY(launch(ctx, tw_out_table_kernel, dim3((uint32_t)ctx->sm_count * 16), dim3(256), 0, t.d_out, k, s[0],
+                       (const Fr*)t.d_lo, (const Fr*)t.d_hi, t.h));
+        t.out_s1 = s[0];
       } else {
-        t.d_full = nullptr;
+        t.d_out = nullptr;
         cudaGetLastError();
       }
     }
@@ -498,7 +552,7 @@ void ntt_free_tables(h2b_ctx* ctx) {
     cudaFree(t.d_lo);
     cudaFree(t.d_hi);
     cudaFree(t.d_rt);
-    if (t.d_full) cudaFree(t.d_full);
+    if (t.d_out) cudaFree(t.d_out);
     if (t.d_mid) cudaFree(t.d_mid);
   }
   ctx->tw.clear();
@@ -520,6 +574,29 @@ static int ntt_plan(uint32_t k, uint32_t* s) {
   return P;
 }
 
+// the register kernel for digit width s, pass kind and (first pass only) a fused pre-scale
+typedef void (*FastKernel)(PassParams);
+template <int S>
+static FastKernel fast_kernel(int kind, bool pre) {
+  switch (kind) {
+    case KIND_TWOLEVEL: return pre ? ntt_pass_fast<S, KIND_TWOLEVEL, true> : ntt_pass_fast<S, KIND_TWOLEVEL, false>;
+    case KIND_OUT_TABLE: return pre ? ntt_pass_fast<S, KIND_OUT_TABLE, true> : ntt_pass_fast<S, KIND_OUT_TABLE, false>;
+    case KIND_MID_TABLE: return ntt_pass_fast<S, KIND_MID_TABLE, false>;
+    default: return ntt_pass_fast<S, KIND_LAST, false>;  // a last pass is never the first one here (single passes are generic)
+  }
+}
+static FastKernel fast_kernel(uint32_t s, int kind, bool pre) {
+  switch (s) {
+    case 6: return fast_kernel<6>(kind, pre);
+    case 7: return fast_kernel<7>(kind, pre);
+    case 8: return fast_kernel<8>(kind, pre);
+    default: return fast_kernel<9>(kind, pre);
+  }
+}
+static int launch_fast(h2b_ctx* ctx, uint32_t s, int kind, bool pre, dim3 grid, const PassParams& p) {
+  return launch(ctx, fast_kernel(s, kind, pre), grid, dim3(256), 65536, p);
+}
+
 int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* tw, uint64_t n_in,
             const Fr* d_pre, uint32_t pre_mod, const Fr* d_post, uint32_t post_mod,
             uint64_t n_out, uint32_t batch, uint64_t in_stride, uint64_t out_stride) {
@@ -532,14 +609,11 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
   if (!ctx->ntt_attr_done) {
     H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_generic,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_fast<6>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_fast<7>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_fast<8>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_fast<9>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    for (uint32_t sw = 6; sw <= 9; ++sw)
+      for (int kind = 0; kind < 4; ++kind)
+        for (int pre = 0; pre < 2; ++pre)
+          H2B_CUDA(ctx, cudaFuncSetAttribute(fast_kernel(sw, kind, pre != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             65536));
     ctx->ntt_attr_done = true;
   }
 
@@ -585,10 +659,10 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       p.rt = tw->d_rt;
       p.rt_log = k < 9 ? k : 9;
       p.tw1 = nullptr;
-      p.tw1_shift = p.tw1_half = 0;
-      if (!p.last && pi == 0 && tw->d_full) {
-        p.tw1 = tw->d_full;
-        p.tw1_half = k - 1;
+      p.tw1_shift = 0;
+      p.tw_out = nullptr;
+      if (!p.last && pi == 0 && tw->d_out && tw->out_s1 == s[0]) {
+        p.tw_out = tw->d_out;
       } else if (!p.last && pi > 0 && tw->d_mid && lm <= tw->mid_log) {
         p.tw1 = tw->d_mid;
         p.tw1_shift = tw->mid_log - lm;
@@ -618,10 +692,9 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       const bool prof = ctx->profile && b0 == 0 && pi < 5;
       if (prof) H2B_CUDA(ctx, cudaEventRecord(ctx->pass_ev[pi], ctx->stream));
       if (fast) {
-        if (p.s == 6) H2B_TRY(launch(ctx, ntt_pass_fast<6>, grid, dim3(256), 65536, p));
-        if (p.s == 7) H2B_TRY(launch(ctx, ntt_pass_fast<7>, grid, dim3(256), 65536, p));
-        if (p.s == 8) H2B_TRY(launch(ctx, ntt_pass_fast<8>, grid, dim3(256), 65536, p));
-        if (p.s == 9) H2B_TRY(launch(ctx, ntt_pass_fast<9>, grid, dim3(256), 65536, p));
+        const int kind = p.last ? KIND_LAST : p.tw_out ? KIND_OUT_TABLE : p.tw1 ? KIND_MID_TABLE : KIND_TWOLEVEL;
+        const bool pre = p.first && p.pre;
+        H2B_TRY(launch_fast(ctx, p.s, kind, pre, grid, p));
       } else {
         H2B_TRY(launch(ctx, ntt_pass_generic, grid, dim3(256), 65536, p));
       }
