@@ -626,6 +626,7 @@ def run_ours(args):
         # result, for each exchange method, bit for bit on the device.
         w4 = h.EvaluationDomain(ctx, 2, k4).constant("omega")
         full = ctx.synth_scalars(1 << k4, SEED + 77, 0)
+        ctx.sync()  # generated on the library's stream; the clone below runs on torch's
         full_t = D._as_tensor(full, (1 << k4) * 4, dev)
         orig = full_t[rank * loc * 4:(rank + 1) * loc * 4].clone()
         torch.cuda.synchronize()

@@ -96,6 +96,7 @@ SYMBOLS = {
     "h2b_running_product": (_I, [_P, _P, _I, _SZ, _P, _P]),
     "h2b_fr_transpose_batch": (_I, [_P, _P, _P, _U32, _U32, _SZ, _U32, _SZ, _SZ]),
     "h2b_fr_transpose_scatter": (_I, [_P, _P, C.POINTER(_P), _U32, _U32, _U32, _U32]),
+    "h2b_best_fft_rows_scatter": (_I, [_P, _P, _P, _U32, _U32, C.POINTER(_P), _U32, _U64, _U64, _P, _U32]),
     "h2b_fr_permute3": (_I, [_P, _P, _P, _U32, _U32, _U32]),
     "h2b_fr_twiddle_rows": (_I, [_P, _P, _P, _U32, _U64, _U32, _U32]),
     "h2b_device_alloc": (_I, [_P, _SZ, C.POINTER(_P)]),

@@ -213,10 +213,19 @@ int copy_d2h_any(h2b_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes
 
 // ntt.cu
 int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t log_n, const TwTable** out);
+// sc != nullptr: the last pass of every row transform stores output Ko of row (row0 + batch member), times
+// tw's omega^(row * Ko) if tw != nullptr, into peers[Ko / cl][(Ko % cl) * R + row] instead of d_out (four-step NTT:
+// the row transforms fused with the distributed transpose that follows them).
+struct NttScatter {
+  Fr* peers[16];
+  uint32_t cl;
+  uint64_t R, row0;
+  const TwTable* tw;
+};
 int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t log_n, const TwTable* tw,
             uint64_t n_in, const Fr* d_pre, uint32_t pre_mod, const Fr* d_post,
             uint32_t post_mod, uint64_t n_out, uint32_t batch, uint64_t in_stride,
-            uint64_t out_stride);
+            uint64_t out_stride, const NttScatter* sc = nullptr);
 void ntt_free_tables(h2b_ctx* ctx);
 
 // msm.cu

@@ -26,6 +26,10 @@
 
 namespace h2b {
 
+struct PeerPtrs {
+  Fr* p[16];
+};
+
 struct PassParams {
   const Fr* in;
   Fr* out;
@@ -35,6 +39,9 @@ struct PassParams {
   uint32_t s;                        // log2 R_p
   uint32_t lc;                       // log2 C
   uint32_t first, last, single;
+  // sb: a SINGLE-pass transform (2^s points, s = 6..9) run by the register kernel: the C columns of a tile are C
+  // consecutive batch members instead of C consecutive strided columns of one transform
+  uint32_t sb;
   uint32_t s1;                       // log2 R_1
   uint32_t nmid;                     // number of middle digits (s_2 .. s_(P-1))
   uint32_t mid_s[4];                 // their widths, s_2 first
@@ -54,6 +61,15 @@ struct PassParams {
   // first pass only: inter-pass twiddle of every OUTPUT element, tw_out[K * m_2 + jr] = w^(jr * K), read with
   // the same coalesced pattern as the store (one multiplication, no gather)
   const Fr* tw_out;
+  // Last pass of a batch of ROW transforms fused with the distributed transpose that follows it in the four-step
+  // NTT (sc_cl != 0): output Ko of row (sc_row0 + batch member) is multiplied by w_big^(row * Ko) (sc_lo != nullptr)
+  // and stored straight into the buffer of the rank that owns it in the transposed matrix, at its final place
+  // sc_peers[Ko / sc_cl][(Ko % sc_cl) * sc_R + row] -- NVLink-mapped peer pointers: the exchange IS these stores.
+  PeerPtrs sc_peers;
+  uint32_t sc_cl, sc_h;
+  uint64_t sc_R, sc_row0;
+  const Fr* sc_lo;
+  const Fr* sc_hi;
 };
 
 // What a pass does around its R-point column DFTs; a template parameter of the register kernel, so that each
@@ -63,17 +79,20 @@ enum PassKind {
   KIND_TWOLEVEL = 0,  // not last: twiddle = tw_lo[e & mask] * tw_hi[e >> h]   (first pass without a table)
   KIND_OUT_TABLE = 1, // first pass: twiddle read from tw_out at the output index
   KIND_MID_TABLE = 2, // later passes: twiddle = tw1[(jr * K) << shift]
-  KIND_LAST = 3       // last pass: natural-order scatter, optional post-scale, truncation
+  KIND_LAST = 3,      // last pass: natural-order scatter, optional post-scale, truncation
+  KIND_LAST_PEER = 4  // last pass of row transforms, fused with the four-step exchange (peer stores, optional twiddle)
 };
 
 struct Tile {
   uint64_t in_base, in_rs, in_cs;
   uint64_t out_base, out_rs;
   uint64_t jr0;
+  uint32_t out_cm;  // multiplier of the column index in the output position (0 in sb mode: the column is a batch member)
 };
 
 H2B_HD Tile tile_geom(const PassParams& p, uint64_t t) {
   Tile g;
+  g.out_cm = p.sb ? 0u : 1u;
   if (p.single) {
     g.in_base = 0;
     g.in_rs = 1;
@@ -133,9 +152,23 @@ H2B_D Fr load_in(const PassParams& p, const Fr* in, uint64_t gi) {
 }
 
 template <int KIND>
-H2B_D void store_out_t(const PassParams& p, Fr* out, const Tile& g, uint32_t K, uint32_t c, Fr x) {
+H2B_D void store_out_t(const PassParams& p, Fr* out, const Tile& g, uint32_t K, uint32_t c, Fr x, uint64_t bidx) {
+  if (KIND == KIND_LAST_PEER) {
+    const uint64_t Ko = g.out_base + (uint64_t)K * g.out_rs + c * g.out_cm;
+    const uint64_t row = p.sc_row0 + bidx;
+    if (p.sc_lo) {
+      const uint64_t e = row * Ko;
+      if (e) {
+        x = mul_tw(x, ld_fp_nc(p.sc_lo + (uint32_t)(e & ((1ull << p.sc_h) - 1))));
+        x = mul_tw(x, ld_fp_nc(p.sc_hi + (uint32_t)(e >> p.sc_h)));
+      }
+    }
+    const uint32_t h = (uint32_t)(Ko / p.sc_cl);
+    st_fp(p.sc_peers.p[h] + (Ko - (uint64_t)h * p.sc_cl) * p.sc_R + row, x);
+    return;
+  }
   if (KIND == KIND_LAST) {
-    const uint64_t Ko = g.out_base + (uint64_t)K * g.out_rs + c;
+    const uint64_t Ko = g.out_base + (uint64_t)K * g.out_rs + c * g.out_cm;
     if (p.post) x = mul_tw(x, ld_fp_nc(p.post + (uint32_t)Ko % p.post_mod));
     if (Ko < p.n_out) st_fp(out + Ko, x);
     return;
@@ -158,14 +191,16 @@ H2B_D void store_out_t(const PassParams& p, Fr* out, const Tile& g, uint32_t K, 
 
 // the generic kernel keeps the run-time dispatch (tiny transforms only)
 H2B_D void store_out(const PassParams& p, Fr* out, const Tile& g, uint32_t K, uint32_t c, Fr x) {
-  if (p.last)
-    store_out_t<KIND_LAST>(p, out, g, K, c, x);
+  if (p.last && p.sc_cl)
+    store_out_t<KIND_LAST_PEER>(p, out, g, K, c, x, blockIdx.y);
+  else if (p.last)
+    store_out_t<KIND_LAST>(p, out, g, K, c, x, blockIdx.y);
   else if (p.tw_out)
-    store_out_t<KIND_OUT_TABLE>(p, out, g, K, c, x);
+    store_out_t<KIND_OUT_TABLE>(p, out, g, K, c, x, blockIdx.y);
   else if (p.tw1)
-    store_out_t<KIND_MID_TABLE>(p, out, g, K, c, x);
+    store_out_t<KIND_MID_TABLE>(p, out, g, K, c, x, blockIdx.y);
   else
-    store_out_t<KIND_TWOLEVEL>(p, out, g, K, c, x);
+    store_out_t<KIND_TWOLEVEL>(p, out, g, K, c, x, blockIdx.y);
 }
 
 H2B_HD uint32_t bitrev32(uint32_t x, uint32_t bits) {
@@ -255,8 +290,10 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   const uint32_t tid = threadIdx.x;
   const uint32_t c = tid & (C - 1), u = tid >> LC;
   const Tile g = tile_geom(p, blockIdx.x);
-  const Fr* in = p.in + (uint64_t)blockIdx.y * p.in_bstride;
-  Fr* out = p.out + (uint64_t)blockIdx.y * p.out_bstride;
+  // batch member of this thread's column: the grid row, or (sb) one of the C members of this tile
+  const uint64_t bidx = p.sb ? (uint64_t)blockIdx.x * C + c : (uint64_t)blockIdx.y;
+  const Fr* in = p.in + bidx * p.in_bstride;
+  Fr* out = p.out + bidx * p.out_bstride;
   const uint32_t rsh = p.rt_log - S;  // w_R^e = rt[e << rsh]
 
   auto slot = [&](uint32_t pos) -> uint32_t {
@@ -295,7 +332,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   dft8(x, p.rt, p.rt_log);
   if (M2 == 1) {
 #pragma unroll
-    for (int Ka2 = 0; Ka2 < 8; ++Ka2) store_out_t<KIND>(p, out, g, Ka + 8 * Ka2, c, x[Ka2]);
+    for (int Ka2 = 0; Ka2 < 8; ++Ka2) store_out_t<KIND>(p, out, g, Ka + 8 * Ka2, c, x[Ka2], bidx);
     return;
   }
 #pragma unroll
@@ -312,7 +349,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
     dft8(x, p.rt, p.rt_log);
     const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) store_out_t<KIND>(p, out, g, K0 + 64 * i, c, x[i]);
+    for (int i = 0; i < 8; ++i) store_out_t<KIND>(p, out, g, K0 + 64 * i, c, x[i], bidx);
   } else if (M2 == 4) {
     const Fr w4 = ld_fp_nc(p.rt + (1u << (p.rt_log - 2)));
 #pragma unroll
@@ -321,10 +358,10 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
       Fr v0 = get(gq * 4 + 0), v1 = get(gq * 4 + 1), v2 = get(gq * 4 + 2), v3 = get(gq * 4 + 3);
       Fr t0 = add(v0, v2), t1 = sub(v0, v2), t2 = add(v1, v3), t3 = mul(sub(v1, v3), w4);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
-      store_out_t<KIND>(p, out, g, K0, c, add(t0, t2));
-      store_out_t<KIND>(p, out, g, K0 + 64, c, add(t1, t3));
-      store_out_t<KIND>(p, out, g, K0 + 128, c, sub(t0, t2));
-      store_out_t<KIND>(p, out, g, K0 + 192, c, sub(t1, t3));
+      store_out_t<KIND>(p, out, g, K0, c, add(t0, t2), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 64, c, add(t1, t3), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 128, c, sub(t0, t2), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 192, c, sub(t1, t3), bidx);
     }
   } else {
 #pragma unroll
@@ -332,8 +369,8 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
       const uint32_t gq = u + 16 * i;
       Fr v0 = get(gq * 2 + 0), v1 = get(gq * 2 + 1);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
-      store_out_t<KIND>(p, out, g, K0, c, add(v0, v1));
-      store_out_t<KIND>(p, out, g, K0 + 64, c, sub(v0, v1));
+      store_out_t<KIND>(p, out, g, K0, c, add(v0, v1), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 64, c, sub(v0, v1), bidx);
     }
   }
 }
@@ -413,9 +450,6 @@ __global__ void __launch_bounds__(256)
 // the peer h = c / cl that owns column c of the transposed matrix, at its final place
 // dst_h[(c % cl) * R + rank*rows + r].  Peer buffers are NVLink-mapped device pointers
 // (symmetric memory), so the all-to-all IS these stores: no pack, no collective, no unpack.
-struct PeerPtrs {
-  Fr* p[16];
-};
 __global__ void __launch_bounds__(256)
     transpose_scatter_kernel(const Fr* in, PeerPtrs peers, uint32_t rank, uint32_t rows, uint32_t cols,
                              uint32_t cl, uint64_t R) {
@@ -582,7 +616,8 @@ static FastKernel fast_kernel(int kind, bool pre) {
     case KIND_TWOLEVEL: return pre ? ntt_pass_fast<S, KIND_TWOLEVEL, true> : ntt_pass_fast<S, KIND_TWOLEVEL, false>;
     case KIND_OUT_TABLE: return pre ? ntt_pass_fast<S, KIND_OUT_TABLE, true> : ntt_pass_fast<S, KIND_OUT_TABLE, false>;
     case KIND_MID_TABLE: return ntt_pass_fast<S, KIND_MID_TABLE, false>;
-    default: return ntt_pass_fast<S, KIND_LAST, false>;  // a last pass is never the first one here (single passes are generic)
+    case KIND_LAST_PEER: return ntt_pass_fast<S, KIND_LAST_PEER, false>;
+    default: return pre ? ntt_pass_fast<S, KIND_LAST, true> : ntt_pass_fast<S, KIND_LAST, false>;  // pre: single-pass (sb) only
   }
 }
 static FastKernel fast_kernel(uint32_t s, int kind, bool pre) {
@@ -599,7 +634,7 @@ static int launch_fast(h2b_ctx* ctx, uint32_t s, int kind, bool pre, dim3 grid, 
 
 int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* tw, uint64_t n_in,
             const Fr* d_pre, uint32_t pre_mod, const Fr* d_post, uint32_t post_mod,
-            uint64_t n_out, uint32_t batch, uint64_t in_stride, uint64_t out_stride) {
+            uint64_t n_out, uint32_t batch, uint64_t in_stride, uint64_t out_stride, const NttScatter* sc) {
   if (batch == 0) return H2B_OK;
   if (k > 28) return fail(ctx, H2B_ERR_ARG, "log_n > 28 (Fr two-adicity)");
   const uint64_t n = 1ull << k;
@@ -610,7 +645,7 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
     H2B_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_generic,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     for (uint32_t sw = 6; sw <= 9; ++sw)
-      for (int kind = 0; kind < 4; ++kind)
+      for (int kind = 0; kind < 5; ++kind)
         for (int pre = 0; pre < 2; ++pre)
           H2B_CUDA(ctx, cudaFuncSetAttribute(fast_kernel(sw, kind, pre != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              65536));
@@ -644,6 +679,7 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       p.first = pi == 0;
       p.last = pi == P - 1;
       p.single = P == 1;
+      p.sb = 0;
       p.s1 = s[0];
       p.nmid = 0;
       for (int i = 1; i + 1 < P; ++i) p.mid_s[p.nmid++] = s[i];
@@ -661,6 +697,21 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       p.tw1 = nullptr;
       p.tw1_shift = 0;
       p.tw_out = nullptr;
+      p.sc_cl = 0;
+      p.sc_lo = p.sc_hi = nullptr;
+      p.sc_h = 0;
+      p.sc_R = p.sc_row0 = 0;
+      if (sc && p.last) {
+        for (int i = 0; i < 16; ++i) p.sc_peers.p[i] = sc->peers[i];
+        p.sc_cl = sc->cl;
+        p.sc_R = sc->R;
+        p.sc_row0 = sc->row0 + b0;
+        if (sc->tw) {
+          p.sc_lo = sc->tw->d_lo;
+          p.sc_hi = sc->tw->d_hi;
+          p.sc_h = sc->tw->h;
+        }
+      }
       if (!p.last && pi == 0 && tw->d_out && tw->out_s1 == s[0]) {
         p.tw_out = tw->d_out;
       } else if (!p.last && pi > 0 && tw->d_mid && lm <= tw->mid_log) {
@@ -684,15 +735,23 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       // columns per tile
       uint32_t lc = 11 - p.s;
       const uint32_t avail = p.single ? 0 : (p.last ? p.s1 : lm - p.s);
-      const bool fast = !p.single && p.s >= 6 && p.s <= 9 && lc <= avail;
-      if (lc > avail) lc = avail;
+      bool fast = !p.single && p.s >= 6 && p.s <= 9 && lc <= avail;
+      // a single-pass transform of 64..512 points: the register kernel with batch members as tile columns
+      const bool sb = p.single && p.s >= 6 && p.s <= 9 && nb >= (1u << lc) && nb % (1u << lc) == 0 &&
+                      getenv("H2B_NTT_NO_SB") == nullptr;
+      if (sb) {
+        fast = true;
+        p.sb = 1;
+      } else if (lc > avail) {
+        lc = avail;
+      }
       p.lc = lc;
-      const uint32_t tiles = (uint32_t)(n >> (p.s + lc));
-      const dim3 grid(tiles, nb);
+      const uint32_t tiles = sb ? nb >> lc : (uint32_t)(n >> (p.s + lc));
+      const dim3 grid(tiles, sb ? 1u : nb);
       const bool prof = ctx->profile && b0 == 0 && pi < 5;
       if (prof) H2B_CUDA(ctx, cudaEventRecord(ctx->pass_ev[pi], ctx->stream));
       if (fast) {
-        const int kind = p.last ? KIND_LAST : p.tw_out ? KIND_OUT_TABLE : p.tw1 ? KIND_MID_TABLE : KIND_TWOLEVEL;
+        const int kind = (p.last && p.sc_cl) ? KIND_LAST_PEER : p.last ? KIND_LAST : p.tw_out ? KIND_OUT_TABLE : p.tw1 ? KIND_MID_TABLE : KIND_TWOLEVEL;
         const bool pre = p.first && p.pre;
         H2B_TRY(launch_fast(ctx, p.s, kind, pre, grid, p));
       } else {
@@ -1061,4 +1120,38 @@ extern "C" int h2b_fr_transpose_scatter(h2b_ctx* ctx, const h2b_fr* in, void* co
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
   return launch(ctx, transpose_scatter_kernel, dim3((cols + 31) / 32, (rows_local + 31) / 32), dim3(256), 0,
                 as_fr(in), peers, rank, rows_local, cols, cols / world, (uint64_t)rows_local * world);
+}
+
+// Row transforms of the four-step NTT fused with the distributed transpose that follows them: `nrows` best_fft's of
+// 2^log_n points each (rows_dev: nrows x 2^log_n, device, left untouched), output Ko of row r stored -- times
+// big_omega^((row0 + r) * Ko) if big_omega != nullptr -- into peer_out[Ko / cl][(Ko % cl) * total_rows + row0 + r],
+// cl = 2^log_n / world.  The peers' buffers are NVLink-mapped (symmetric memory): no separate twiddle pass, no
+// transpose kernel, no collective.
+extern "C" int h2b_best_fft_rows_scatter(h2b_ctx* ctx, const h2b_fr* rows_dev, const h2b_fr* omega, uint32_t log_n,
+                                         uint32_t nrows, void* const* peer_out, uint32_t world, uint64_t row0,
+                                         uint64_t total_rows, const h2b_fr* big_omega, uint32_t big_log_n) {
+  if (!ctx) return H2B_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (!rows_dev || !omega || !peer_out) return fail(ctx, H2B_ERR_ARG, "null pointer");
+  if (log_n > 28 || big_log_n > 28) return fail(ctx, H2B_ERR_ARG, "log_n > 28");
+  const uint64_t n = 1ull << log_n;
+  if (world == 0 || world > 16 || (world & (world - 1)) || n % world)
+    return fail(ctx, H2B_ERR_ARG, "bad world size for this row length");
+  if (nrows == 0) return H2B_OK;
+  if (row0 + nrows > total_rows) return fail(ctx, H2B_ERR_LENGTH, "rows outside the matrix");
+  if (big_omega && (row0 + nrows - 1) * (n - 1) >= (1ull << big_log_n))
+    return fail(ctx, H2B_ERR_LENGTH, "twiddle exponent exceeds 2^big_log_n");
+  H2B_CUDA(ctx, cudaSetDevice(ctx->device));
+  NttScatter sc;
+  for (uint32_t i = 0; i < 16; ++i) sc.peers[i] = i < world ? reinterpret_cast<Fr*>(peer_out[i]) : nullptr;
+  for (uint32_t i = 0; i < world; ++i)
+    if (!sc.peers[i] || sc.peers[i] == as_fr(rows_dev)) return fail(ctx, H2B_ERR_ARG, "null or aliased peer buffer");
+  sc.cl = (uint32_t)(n / world);
+  sc.R = total_rows;
+  sc.row0 = row0;
+  sc.tw = nullptr;
+  if (big_omega) H2B_TRY(ntt_get_table(ctx, *as_fr(big_omega), big_log_n, &sc.tw));
+  const TwTable* tw;
+  H2B_TRY(ntt_get_table(ctx, *as_fr(omega), log_n, &tw));
+  return ntt_run(ctx, as_fr(rows_dev), nullptr, log_n, tw, n, nullptr, 1, nullptr, 1, n, nrows, n, n, &sc);
 }

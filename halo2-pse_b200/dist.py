@@ -371,7 +371,12 @@ class FourStepNTT:
         if G & (G - 1):
             raise H2BError(_ffi.H2B_ERR_ARG, "world size must be a power of two")
         lg = G.bit_length() - 1
+        # n = n1 * n2.  On the p2p path n1 is at most 2^9, ONE pass of the register kernel, so that a transform makes
+        # 1 + 2 passes like the single-GPU schedule (8 + 9 + 9 bits at k = 26) instead of 2 + 2; H2B_FOURSTEP_SQUARE=1
+        # restores the square split.
         self.k1 = log_n // 2
+        if p2p is not False and self.k1 > 9 and not os.environ.get("H2B_FOURSTEP_SQUARE"):
+            self.k1 = 9
         self.k2 = log_n - self.k1
         if self.k1 < lg or self.k2 < lg:
             raise H2BError(_ffi.H2B_ERR_ARG, "transform too small to shard over this many ranks")
@@ -409,9 +414,29 @@ class FourStepNTT:
         ctx._check(ctx.lib.h2b_fr_transpose_scatter(ctx.h, src_ptr, self.peer[dst], self.world, self.rank,
                                                     rows_local, cols))
 
+    def _rows_scatter(self, src, dst: int, omega_l, log_len: int, rows: int, total_rows: int, twiddle: bool) -> None:
+        ctx = self.ctx
+        ctx._check(ctx.lib.h2b_best_fft_rows_scatter(
+            ctx.h, self._p(src), C.c_void_p(omega_l.ctypes.data), log_len, rows, self.peer[dst], self.world,
+            self.rank * rows, total_rows, C.c_void_p(self.w.ctypes.data) if twiddle else None, self.k))
+
+    # ONE fused transpose+exchange kernel, then two batches of row transforms whose LAST pass stores every output
+    # (times the four-step twiddle for the first batch) straight into the rank that owns it in the transposed
+    # matrix: 5 passes over the local slab (1 + 2 + 2 at k = 26) where the three-transpose schedule made 9, no
+    # twiddle kernel, no final copy.  NVLink carries 3 x (G-1)/G of the vector per transform.
+    exchanges = 3
+    passes_note = "transpose+exchange, row NTTs (+twiddle) with the 2nd exchange in their last pass, row NTTs with the 3rd"
+
+    @property
+    def nvlink_bytes(self) -> Optional[int]:
+        """Bytes this rank sends over NVLink per transform (p2p path)."""
+        if not self.p2p:
+            return None
+        return 3 * self.local * 32 * (self.world - 1) // self.world
+
     def _run_p2p(self, a):
-        """Three fused transpose+exchange kernels over NVLink peer memory, device-side barriers only;
-        everything is enqueued on the library's stream."""
+        """Everything is enqueued on the library's stream; device-side barriers between the steps.  The result is
+        returned in the symmetric buffer S1 (valid until the next run() on this object)."""
         ctx, G, torch = self.ctx, self.world, self.torch
         n1, n2 = self.n1, self.n2
         S1, S2 = self.S
@@ -421,21 +446,14 @@ class FourStepNTT:
             H1.barrier(0)  # every peer is done with S1 of the previous transform
             self._scatter(self._p(a), 0, n1 // G, n2)           # A[j1][j2] -> A^T[j2][j1] in S1
             H1.barrier(0)
-            rows = n2 // G
-            ctx._check(ctx.lib.h2b_best_fft_batch(ctx.h, self._p(S1), H2B_DEVICE,
-                                                  C.c_void_p(self.w1.ctypes.data), self.k1, rows, n1))
-            ctx._check(ctx.lib.h2b_fr_twiddle_rows(ctx.h, self._p(S1), C.c_void_p(self.w.ctypes.data), self.k,
-                                                   self.rank * rows, rows, n1))
-            self._scatter(self._p(S1), 1, rows, n1)               # -> B[K1][j2] in S2
+            # n1-point transforms of the rows j2 of A^T, times w^(j2*K1), stored as B[K1][j2] in the peers' S2
+            self._rows_scatter(S1, 1, self.w1, self.k1, n2 // G, n2, True)
             H2.barrier(0)
-            rows = n1 // G
-            ctx._check(ctx.lib.h2b_best_fft_batch(ctx.h, self._p(S2), H2B_DEVICE,
-                                                  C.c_void_p(self.w2.ctypes.data), self.k2, rows, n2))
-            self._scatter(self._p(S2), 0, rows, n2)               # C[K1][K2] -> natural order in S1
+            # n2-point transforms of the rows K1 of B; C[K1][K2] = X[K1 + n1*K2] stored in natural order in the peers' S1
+            self._rows_scatter(S2, 0, self.w2, self.k2, n1 // G, n1, False)
             H1.barrier(0)
-            a.copy_(S1)
         ctx.sync()
-        return a
+        return S1
 
     # -- helpers ---------------------------------------------------------
     def _p(self, t) -> C.c_void_p:
@@ -468,8 +486,9 @@ class FourStepNTT:
         ctx._check(ctx.lib.h2b_fr_permute3(ctx.h, self._p(src), self._p(dst), G, Cl, Rl))
 
     def run(self, a):
-        """a: int64 tensor of 4 * n/G limbs words (this rank's natural-order slice), transformed
-        in place; returns `a`."""
+        """a: int64 tensor of 4 * n/G limb words (this rank's natural-order slice).  Returns the tensor that holds
+        this rank's slice of the transform: `a` itself (transformed in place) on the collective path, the
+        symmetric buffer on the p2p path (valid until the next run(); `a` is left untouched there)."""
         if self.p2p:
             return self._run_p2p(a)
         ctx, G = self.ctx, self.world

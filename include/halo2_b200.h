@@ -288,6 +288,13 @@ int h2b_fr_transpose_batch(h2b_ctx* ctx, const h2b_fr* in, h2b_fr* out, uint32_t
  * buffer, own rank included) at its place in the row-sharded transposed matrix. */
 int h2b_fr_transpose_scatter(h2b_ctx* ctx, const h2b_fr* in, void* const* peer_out, uint32_t world,
                              uint32_t rank, uint32_t rows_local, uint32_t cols);
+/* Row transforms of the four-step NTT fused with the distributed transpose that follows them: nrows best_fft's of
+ * 2^log_n points (rows_dev, device, untouched); output Ko of row r, multiplied by big_omega^((row0 + r) * Ko) when
+ * big_omega is not NULL, is stored into peer_out[Ko / cl][(Ko % cl) * total_rows + row0 + r], cl = 2^log_n / world.
+ * peer_out: `world` device pointers (this rank's own buffer included), NVLink-mapped for the peers. */
+int h2b_best_fft_rows_scatter(h2b_ctx* ctx, const h2b_fr* rows_dev, const h2b_fr* omega, uint32_t log_n,
+                              uint32_t nrows, void* const* peer_out, uint32_t world, uint64_t row0,
+                              uint64_t total_rows, const h2b_fr* big_omega, uint32_t big_log_n);
 int h2b_fr_permute3(h2b_ctx* ctx, const h2b_fr* in, h2b_fr* out, uint32_t A, uint32_t B, uint32_t C);
 int h2b_fr_twiddle_rows(h2b_ctx* ctx, h2b_fr* a, const h2b_fr* omega, uint32_t log_n, uint64_t row0,
                         uint32_t nrows, uint32_t ncols);

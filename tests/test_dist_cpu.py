@@ -141,3 +141,71 @@ def test_transpose_scatter_kernel(emu_ctx):
         MT = np.ascontiguousarray(M.transpose(1, 0, 2))  # [Cn][R]
         for hh in range(G):
             assert (dst[hh].reshape(Cl, R, 4) == MT[hh * Cl:(hh + 1) * Cl]).all(), (G, hh)
+
+
+def test_rows_scatter_kernel_and_p2p_schedule(emu_ctx, oracle_c):
+    """The p2p four-step schedule with every rank emulated in one process: one transpose+exchange kernel, then two
+    batches of row transforms whose last pass stores (twiddled) outputs straight into the owning rank's buffer
+    (h2b_best_fft_rows_scatter).  Result == best_fft of the whole vector (arithmetic.rs:171)."""
+    import ctypes as C
+    from oracle import bn256 as O
+    from tests import helpers as H
+    import halo2_pse_b200 as h
+    lib, ctx = emu_ctx.lib, emu_ctx
+
+    def ptrs(bufs):
+        return (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+
+    for k, G in ((4, 1), (8, 2), (9, 4), (13, 8), (14, 2)):
+        n = 1 << k
+        k1 = k // 2
+        k2 = k - k1
+        n1, n2 = 1 << k1, 1 << k2
+        omega = O.omega_for(k)
+        w = H.fr_enc([omega])
+        w1 = H.fr_enc([pow(omega, n2, O.R_MOD)])
+        w2 = H.fr_enc([pow(omega, n1, O.R_MOD)])
+        a = H.rand_fr_limbs(k * 10 + G, n)
+        want = oracle_c.best_fft(a, w[0], k, 1)
+        loc = n // G
+        S1 = [np.zeros((loc, 4), dtype=np.uint64) for _ in range(G)]
+        S2 = [np.zeros((loc, 4), dtype=np.uint64) for _ in range(G)]
+        for g in range(G):  # A[j1][j2] -> A^T[j2][j1]
+            src = np.ascontiguousarray(a[g * loc:(g + 1) * loc])
+            ctx._check(lib.h2b_fr_transpose_scatter(ctx.h, C.c_void_p(src.ctypes.data), ptrs(S1), G, g, n1 // G, n2))
+        for g in range(G):  # n1-point row transforms of A^T, twiddle, -> B[K1][j2]
+            ctx._check(lib.h2b_best_fft_rows_scatter(ctx.h, C.c_void_p(S1[g].ctypes.data), C.c_void_p(w1.ctypes.data), k1,
+                                                     n2 // G, ptrs(S2), G, g * (n2 // G), n2, C.c_void_p(w.ctypes.data), k))
+        for g in range(G):  # n2-point row transforms of B -> natural order
+            ctx._check(lib.h2b_best_fft_rows_scatter(ctx.h, C.c_void_p(S2[g].ctypes.data), C.c_void_p(w2.ctypes.data), k2,
+                                                     n1 // G, ptrs(S1), G, g * (n1 // G), n1, None, k))
+        got = np.concatenate(S1)
+        assert (got == want).all(), (k, G)
+
+    # the register kernel's fused last pass (rows of 2^12 and 2^13 points: two passes) against row-wise best_fft
+    # ... and single-pass rows (64 / 512 points) through the register kernel with batch members as tile columns
+    for log_len, rows, G, row0, total in ((12, 3, 2, 5, 16), (13, 2, 4, 0, 2), (9, 8, 2, 0, 8), (6, 32, 4, 32, 64)):
+        L = 1 << log_len
+        big_k = 17
+        big = O.omega_for(big_k)
+        wl = H.fr_enc([O.omega_for(log_len)])
+        x = H.rand_fr_limbs(log_len, rows * L)
+        dst = [np.zeros(((L // G) * total, 4), dtype=np.uint64) for _ in range(G)]
+        ctx._check(lib.h2b_best_fft_rows_scatter(ctx.h, C.c_void_p(x.ctypes.data), C.c_void_p(wl.ctypes.data), log_len, rows,
+                                                 ptrs(dst), G, row0, total, C.c_void_p(H.fr_enc([big]).ctypes.data), big_k))
+        cl = L // G
+        for r in range(rows):
+            y = H.fr_dec(oracle_c.best_fft(x[r * L:(r + 1) * L], wl[0], log_len, 1))
+            row = row0 + r
+            for Ko in (0, 1, 2, cl - 1, cl, L - 1, 777 % L, 1234 % L, 37 % L):
+                exp = y[Ko] * pow(big, row * Ko, O.R_MOD) % O.R_MOD
+                got = H.fr_dec(dst[Ko // cl][(Ko % cl) * total + row])[0]
+                assert got == exp, (log_len, r, Ko)
+    # argument checks
+    x = H.rand_fr_limbs(1, 16)
+    d = [np.zeros((16, 4), dtype=np.uint64) for _ in range(2)]
+    w4 = H.fr_enc([O.omega_for(4)])
+    assert lib.h2b_best_fft_rows_scatter(ctx.h, C.c_void_p(x.ctypes.data), C.c_void_p(w4.ctypes.data), 4, 1, ptrs(d), 3, 0, 1,
+                                         None, 4) == h.H2B_ERR_ARG  # world not a power of two
+    assert lib.h2b_best_fft_rows_scatter(ctx.h, C.c_void_p(x.ctypes.data), C.c_void_p(w4.ctypes.data), 4, 2, ptrs(d), 2, 0, 1,
+                                         None, 4) == h.H2B_ERR_LENGTH  # rows outside the matrix

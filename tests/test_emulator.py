@@ -386,3 +386,47 @@ def test_small_multiexp_and_g_to_lagrange(emu_ctx):
     G.check_g_to_lagrange_vs_oracle(emu_ctx)
     G.check_downsize(emu_ctx, 6, 4)
     G.check_downsize(emu_ctx, 5, 5, precompute=True)
+
+
+@pytest.mark.parametrize("log_n,ncols", [(6, 32), (6, 64), (7, 16), (8, 24), (9, 4), (9, 12), (9, 5)])
+def test_single_pass_batches_on_the_register_kernel(emu_ctx, oracle_c, log_n, ncols, monkeypatch):
+    """Batches of 64..512-point transforms run the register kernel with batch members as tile columns (ncols a
+    multiple of the tile width) or the generic kernel (otherwise, or H2B_NTT_NO_SB): same results as best_fft per
+    column (arithmetic.rs:171), also through the scaled domain transforms (poly/domain.rs:226-303)."""
+    n = 1 << log_n
+    stride = n + 8
+    w = H.fr_enc([O.omega_for(log_n)])
+    a = H.rand_fr_limbs(log_n * 100 + ncols, ncols * stride)
+    want = a.copy()
+    for c in range(ncols):
+        want[c * stride:c * stride + n] = oracle_c.best_fft(a[c * stride:c * stride + n], w[0], log_n, 1)
+    for no_sb in (False, True):
+        if no_sb:
+            monkeypatch.setenv("H2B_NTT_NO_SB", "1")
+        buf = emu_ctx.upload_fr(a)
+        emu_ctx.best_fft_device(buf, w, log_n, ncols, stride)
+        assert (buf.download(ncols * stride) == want).all(), no_sb
+        buf.free()
+    monkeypatch.delenv("H2B_NTT_NO_SB")
+    if log_n - 2 >= 4:  # coeff_to_extended / extended_to_coeff in batches: extended_k = log_n, one pass with pre / post scaling
+        k = log_n - 2
+        d = h.EvaluationDomain(emu_ctx, 5, k)
+        od = oracle_c.domain(5, k, 1)
+        assert d.extended_k == log_n
+        m = 1 << k
+        cols = H.rand_fr_limbs(7 + log_n, ncols * m)
+        src, dst = emu_ctx.upload_fr(cols), emu_ctx.alloc(ncols * n * 32)
+        d.coeff_to_extended_device(src, dst, ncols)
+        got = dst.download(ncols * n)
+        for c in range(ncols):
+            assert (got[c * n:(c + 1) * n] == od.coeff_to_extended(cols[c * m:(c + 1) * m])).all(), c
+        back = emu_ctx.alloc(ncols * d.quotient_len * 32)
+        d.extended_to_coeff_device(dst, back, ncols, divide_by_vanishing=True)
+        gb = back.download(ncols * d.quotient_len)
+        for c in range(ncols):
+            ext = od.divide_by_vanishing_poly(got[c * n:(c + 1) * n])
+            assert (gb[c * d.quotient_len:(c + 1) * d.quotient_len] == od.extended_to_coeff(ext)).all(), c
+        for b in (src, dst, back):
+            b.free()
+        d.free()
+        od.free()

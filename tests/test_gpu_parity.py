@@ -731,3 +731,19 @@ def test_small_multiexp_and_g_to_lagrange(gpu_ctx):
     G.check_downsize(gpu_ctx, 10, 9)
     G.check_downsize(gpu_ctx, 12, 12, precompute=True)
     G.check_downsize(gpu_ctx, 16, 15)
+
+
+@pytest.mark.parametrize("k", [25, 26])
+def test_best_fft_vs_oracle_largest_sizes(gpu_ctx, oracle_c, k):
+    """best_fft at the sizes of configs[4] (k = 26: digits 8 + 9 + 9, the streamed first-pass twiddle table) against the
+    C++ restatement of arithmetic.rs:171-274, bit for bit, twice in a row on the same buffer."""
+    a = H.rand_fr_limbs(k, 1 << k)
+    w = H.fr_enc([O.omega_for(k)])
+    want = oracle_c.best_fft(a, w[0], k, 0)
+    buf = gpu_ctx.upload_fr(a)
+    gpu_ctx.best_fft_device(buf, w, k)
+    assert (buf.download(1 << k) == want).all()
+    want = oracle_c.best_fft(want, w[0], k, 0)
+    gpu_ctx.best_fft_device(buf, w, k)
+    assert (buf.download(1 << k) == want).all()
+    buf.free()
