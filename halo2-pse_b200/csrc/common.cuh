@@ -42,6 +42,8 @@ struct h2b_ctx {
   cudaStream_t stream = nullptr;
   // second stream + events for host->device copies overlapped with compute (drop-in calls on host slices)
   cudaStream_t copy_stream = nullptr;
+  // device->host leg of streamed host batches (PCIe is full duplex: it runs beside copy_stream's uploads)
+  cudaStream_t d2h_stream = nullptr;
   // `stream` is created at the highest priority; the one long throughput-bound kernel of an MSM (bucket
   // accumulation, level 0) is launched on this LOW-priority stream instead, fenced by two events: when several
   // contexts commit at once, the short latency-bound kernels of one MSM (sort passes, scans, bucket reduction)

@@ -507,6 +507,7 @@ extern "C" void h2b_ctx_destroy(h2b_ctx* ctx) {
     if (ctx->copy_slot_ev[i]) cudaEventDestroy(ctx->copy_slot_ev[i]);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   for (int i = 0; i < 2; ++i)
     if (ctx->bulk_ev[i]) cudaEventDestroy(ctx->bulk_ev[i]);
   if (ctx->bulk_stream && ctx->bulk_stream != ctx->stream) cudaStreamDestroy(ctx->bulk_stream);

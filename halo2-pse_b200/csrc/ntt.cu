@@ -24,6 +24,8 @@
 // and the last pass's store.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace h2b {
 
 struct PeerPtrs {
@@ -803,6 +805,77 @@ struct Staged {
 };
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// Host-pointer batches that are too large to stage at once (64 columns of 2^26 extended evaluations are 128 GiB):
+// column groups through two staging slots per direction.  Group g + 1 travels host -> device (copy stream) and
+// group g - 1 device -> host (its own stream; PCIe is full duplex) while group g is transformed.  `run(din, dout,
+// cols)` enqueues the transform of `cols` packed columns on the context's stream.
+// ---------------------------------------------------------------------------
+static size_t stream_slot_bytes() {
+  size_t v = (size_t)1 << 30;
+  if (const char* e = getenv("H2B_STREAM_SLOT_BYTES")) {
+    const long long x = atoll(e);
+    if (x >= 32) v = (size_t)x;
+  }
+  return v;
+}
+
+// columns per group, or 0 if the batch should take the plain (stage everything) path
+static uint32_t stream_group(uint32_t ncols, size_t in_count, size_t out_count) {
+  if (ncols < 2) return 0;
+  const size_t per = std::max(in_count, out_count) * sizeof(Fr);
+  const size_t slot = stream_slot_bytes();
+  if ((size_t)ncols * per <= slot) return 0;  // fits one slot: nothing to overlap
+  size_t g = slot / per;
+  if (g < 1) g = 1;
+  return (uint32_t)std::min<size_t>(g, (ncols + 1) / 2);  // at least two groups
+}
+
+template <class Run>
+static int host_batch_streamed(h2b_ctx* ctx, const h2b_fr* in, size_t in_stride, size_t in_count, h2b_fr* out,
+                               size_t out_stride, size_t out_count, uint32_t ncols, uint32_t group, Run run) {
+  H2B_TRY(ensure_stage(ctx, 0, 2 * (size_t)group * in_count * sizeof(Fr)));
+  H2B_TRY(ensure_stage(ctx, 1, 2 * (size_t)group * out_count * sizeof(Fr)));
+  if (!ctx->d2h_stream) H2B_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  cudaStream_t st = ctx->stream, up = ctx->copy_stream, down = ctx->d2h_stream;
+  cudaEvent_t *e_h2d = &ctx->copy_ev[0], *e_comp = &ctx->copy_ev[2], *e_d2h = &ctx->copy_ev[4];
+  Fr* din = reinterpret_cast<Fr*>(ctx->stage[0]);
+  Fr* dout = reinterpret_cast<Fr*>(ctx->stage[1]);
+  // the staging buffers may still be read by work queued earlier on the main stream
+  H2B_CUDA(ctx, cudaEventRecord(ctx->copy_ev[7], st));
+  H2B_CUDA(ctx, cudaStreamWaitEvent(up, ctx->copy_ev[7], 0));
+  H2B_CUDA(ctx, cudaStreamWaitEvent(down, ctx->copy_ev[7], 0));
+  const uint32_t ngroups = (ncols + group - 1) / group;
+  auto upload = [&](uint32_t g) -> int {
+    const uint32_t slot = g & 1, c0 = g * group, nc = std::min(group, ncols - c0);
+    if (g >= 2) H2B_CUDA(ctx, cudaStreamWaitEvent(up, e_comp[slot], 0));  // group g - 2 has left the slot
+    Fr* d = din + (size_t)slot * group * in_count;
+    for (uint32_t c = 0; c < nc; ++c)
+      H2B_TRY(copy_h2d_any(ctx, d + (size_t)c * in_count, in + (size_t)(c0 + c) * in_stride, in_count * sizeof(Fr), up));
+    H2B_CUDA(ctx, cudaEventRecord(e_h2d[slot], up));
+    return H2B_OK;
+  };
+  H2B_TRY(upload(0));
+  for (uint32_t g = 0; g < ngroups; ++g) {
+    const uint32_t slot = g & 1, c0 = g * group, nc = std::min(group, ncols - c0);
+    Fr* di = din + (size_t)slot * group * in_count;
+    Fr* dq = dout + (size_t)slot * group * out_count;
+    H2B_CUDA(ctx, cudaStreamWaitEvent(st, e_h2d[slot], 0));
+    if (g >= 2) H2B_CUDA(ctx, cudaStreamWaitEvent(st, e_d2h[slot], 0));  // group g - 2 has been read back
+    H2B_TRY(run(di, dq, nc));
+    H2B_CUDA(ctx, cudaEventRecord(e_comp[slot], st));
+    if (g + 1 < ngroups) H2B_TRY(upload(g + 1));
+    H2B_CUDA(ctx, cudaStreamWaitEvent(down, e_comp[slot], 0));
+    for (uint32_t c = 0; c < nc; ++c)
+      H2B_TRY(copy_d2h_any(ctx, out + (size_t)(c0 + c) * out_stride, dq + (size_t)c * out_count, out_count * sizeof(Fr),
+                           down));
+    H2B_CUDA(ctx, cudaEventRecord(e_d2h[slot], down));
+  }
+  H2B_CUDA(ctx, cudaStreamSynchronize(down));
+  H2B_CUDA(ctx, cudaStreamSynchronize(st));
+  return H2B_OK;
+}
+
 extern "C" int h2b_best_fft_batch(h2b_ctx* ctx, h2b_fr* a, int loc, const h2b_fr* omega,
                                   uint32_t log_n, uint32_t ncols, size_t stride) {
   if (!ctx) return H2B_ERR_ARG;
@@ -815,6 +888,11 @@ extern "C" int h2b_best_fft_batch(h2b_ctx* ctx, h2b_fr* a, int loc, const h2b_fr
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
   const TwTable* tw;
   H2B_TRY(ntt_get_table(ctx, *as_fr(omega), log_n, &tw));
+  if (loc != H2B_DEVICE)
+    if (const uint32_t group = stream_group(ncols, n, n))
+      return host_batch_streamed(ctx, a, stride, n, a, stride, n, ncols, group, [&](Fr* di, Fr* dq, uint32_t nc) {
+        return ntt_run(ctx, di, dq, log_n, tw, n, nullptr, 1, nullptr, 1, n, nc, n, n);
+      });
   Staged st{ctx, 0};
   const size_t count = (size_t)(ncols - 1) * stride + n;
   H2B_TRY(st.in(a, loc, count, true));
@@ -967,6 +1045,11 @@ extern "C" int h2b_lagrange_to_coeff_batch(h2b_domain* d, h2b_fr* a, int loc, ui
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
   const TwTable* tw;
   H2B_TRY(ntt_get_table(ctx, d->omega_inv, d->k, &tw));
+  if (loc != H2B_DEVICE)
+    if (const uint32_t group = stream_group(ncols, n, n))
+      return host_batch_streamed(ctx, a, stride, n, a, stride, n, ncols, group, [&](Fr* di, Fr* dq, uint32_t nc) {
+        return ntt_run(ctx, di, dq, d->k, tw, n, nullptr, 1, d->d_ifft_post, 1, n, nc, n, n);
+      });
   Staged st{ctx, 0};
   const size_t count = (size_t)(ncols - 1) * stride + n;
   H2B_TRY(st.in(a, loc, count, true));
@@ -993,6 +1076,13 @@ extern "C" int h2b_coeff_to_extended_batch(h2b_domain* d, const h2b_fr* in, size
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
   const TwTable* tw;
   H2B_TRY(ntt_get_table(ctx, d->extended_omega, d->extended_k, &tw));
+  if (loc != H2B_DEVICE)
+    if (const uint32_t group = stream_group(ncols, n, ne))
+      return host_batch_streamed(ctx, in, in_stride, n, out, out_stride, ne, ncols, group,
+                                 [&](Fr* di, Fr* dq, uint32_t nc) {
+                                   return ntt_run(ctx, di, dq, d->extended_k, tw, n, d->d_zeta_in, 3, nullptr, 1, ne, nc, n,
+                                                  ne);
+                                 });
   Staged sin{ctx, 0}, sout{ctx, 1};
   const size_t cin = (size_t)(ncols - 1) * in_stride + n;
   const size_t cout = (size_t)(ncols - 1) * out_stride + ne;
@@ -1024,6 +1114,14 @@ extern "C" int h2b_extended_to_coeff_batch(h2b_domain* d, const h2b_fr* in, size
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
   const TwTable* tw;
   H2B_TRY(ntt_get_table(ctx, d->extended_omega_inv, d->extended_k, &tw));
+  if (loc != H2B_DEVICE)
+    if (const uint32_t group = stream_group(ncols, ne, nq))
+      return host_batch_streamed(ctx, in, in_stride, ne, out, out_stride, nq, ncols, group,
+                                 [&](Fr* di, Fr* dq, uint32_t nc) {
+                                   return ntt_run(ctx, di, dq, d->extended_k, tw, ne,
+                                                  divide_by_vanishing ? d->d_t_inv : nullptr,
+                                                  (uint32_t)d->t_evaluations.size(), d->d_ext_post, 3, nq, nc, ne, nq);
+                                 });
   Staged sin{ctx, 0}, sout{ctx, 1};
   const size_t cin = (size_t)(ncols - 1) * in_stride + ne;
   const size_t cout = (size_t)(ncols - 1) * out_stride + nq;

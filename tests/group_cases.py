@@ -75,3 +75,40 @@ def check_downsize(ctx, k_from: int, k_to: int, s: int = 0x1234567, precompute: 
     for p in (big, small):
         p.g.free()
         p.g_lagrange.free()
+
+
+def check_streamed_host_batches(ctx, oc, k: int, ncols: int, slot_cols: float, monkeypatch):
+    """The *_batch entry points on HOST columns that exceed one staging slot: column groups, double-buffered
+    (H2B_STREAM_SLOT_BYTES sets the slot; ragged last group, padded strides).  Every column equals the oracle's
+    single-column transform (poly/domain.rs:226-303, arithmetic.rs:171)."""
+    import ctypes as C
+    d = h.EvaluationDomain(ctx, 5, k)
+    od = oc.domain(5, k, 0)
+    n, ne, nq = 1 << k, d.extended_len(), d.quotient_len
+    monkeypatch.setenv("H2B_STREAM_SLOT_BYTES", str(int(slot_cols * ne * 32)))
+    P = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    sin, sout = n + 3, ne + 5
+    cols = H.rand_fr_limbs(k * 7 + ncols, ncols * sin)
+    out = np.zeros((ncols * sout, 4), dtype=np.uint64)
+    ctx._check(ctx.lib.h2b_coeff_to_extended_batch(d.h, P(cols), sin, P(out), sout, h.H2B_HOST, ncols))
+    for c in range(ncols):
+        assert (out[c * sout:c * sout + ne] == od.coeff_to_extended(cols[c * sin:c * sin + n])).all(), ("c2e", c)
+        assert not out[c * sout + ne:(c + 1) * sout].any()  # the padding between columns is not touched
+    # extended_to_coeff (with the fused vanishing division), host in -> host out, in place on the same array
+    q = np.zeros((ncols * nq, 4), dtype=np.uint64)
+    ctx._check(ctx.lib.h2b_extended_to_coeff_batch(d.h, P(out), sout, P(q), nq, h.H2B_HOST, ncols, 1))
+    for c in range(ncols):
+        want = od.extended_to_coeff(od.divide_by_vanishing_poly(out[c * sout:c * sout + ne]))
+        assert (q[c * nq:(c + 1) * nq] == want).all(), ("e2c", c)
+    # lagrange_to_coeff and best_fft, in place
+    a = cols.copy()
+    ctx._check(ctx.lib.h2b_lagrange_to_coeff_batch(d.h, P(a), h.H2B_HOST, ncols, sin))
+    w = H.fr_enc([O.omega_for(k)])
+    b = cols.copy()
+    ctx._check(ctx.lib.h2b_best_fft_batch(ctx.h, P(b), h.H2B_HOST, P(w), k, ncols, sin))
+    for c in range(ncols):
+        assert (a[c * sin:c * sin + n] == od.lagrange_to_coeff(cols[c * sin:c * sin + n])).all(), ("l2c", c)
+        assert (b[c * sin:c * sin + n] == oc.best_fft(cols[c * sin:c * sin + n], w[0], k, 0)).all(), ("fft", c)
+        assert (a[c * sin + n:(c + 1) * sin] == cols[c * sin + n:(c + 1) * sin]).all()
+    d.free()
+    od.free()

@@ -430,3 +430,9 @@ def test_single_pass_batches_on_the_register_kernel(emu_ctx, oracle_c, log_n, nc
             b.free()
         d.free()
         od.free()
+
+
+@pytest.mark.parametrize("k,ncols,slot_cols", [(6, 7, 2.0), (9, 5, 1.0), (10, 9, 3.5)])
+def test_streamed_host_batches(emu_ctx, oracle_c, monkeypatch, k, ncols, slot_cols):
+    from tests import group_cases as G
+    G.check_streamed_host_batches(emu_ctx, oracle_c, k, ncols, slot_cols, monkeypatch)

@@ -747,3 +747,11 @@ def test_best_fft_vs_oracle_largest_sizes(gpu_ctx, oracle_c, k):
     gpu_ctx.best_fft_device(buf, w, k)
     assert (buf.download(1 << k) == want).all()
     buf.free()
+
+
+@pytest.mark.parametrize("k,ncols,slot_cols", [(10, 9, 3.5), (16, 13, 4.0), (18, 6, 1.0)])
+def test_streamed_host_batches(gpu_ctx, oracle_c, monkeypatch, k, ncols, slot_cols):
+    """configs[2] beyond HBM: host columns streamed through two staging slots per direction (csrc/ntt.cu
+    host_batch_streamed), uploads, transforms and read-backs of neighbouring groups overlapped."""
+    from tests import group_cases as G
+    G.check_streamed_host_batches(gpu_ctx, oracle_c, k, ncols, slot_cols, monkeypatch)
