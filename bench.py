@@ -615,6 +615,32 @@ def run_ours(args):
     e_ntt = sum(b.elapsed_time(c) for _, b, c in evs)
     e_msm, e_ntt, e2e_wall = max_over_ranks(e_msm, e_ntt, e2e_wall)
 
+    # ---- what the host side can deliver: pinned copies on EVERY rank at the same time ----------------------
+    # (the end-to-end number above is bounded by these; on this pool the 8-GPU box is one VM with a single
+    # NUMA node and 32 vCPUs, so there is no per-socket placement to do -- the probe shows whether the PCIe /
+    # host-memory path scales with the number of GPUs)
+    def copy_probe():
+        nbytes = n * 32
+        res = {}
+        for name, fn in (("h2d", lambda: ctx.lib.h2b_copy_h2d(ctx.h, poly.ptr, C.c_void_p(h_poly.ptr.value), nbytes)),
+                         ("d2h", lambda: ctx.lib.h2b_copy_d2h(ctx.h, C.c_void_p(h_poly.ptr.value), poly.ptr, nbytes))):
+            fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ctx._check(fn())
+            dt = (time.perf_counter() - t0) / 3
+            barrier()
+            mine = nbytes / dt / 1e9
+            (slowest,) = max_over_ranks(-mine)
+            (fastest,) = max_over_ranks(mine)
+            res[name] = {"per_rank_GBps_min": -slowest, "per_rank_GBps_max": fastest,
+                         "aggregate_GBps_at_the_slowest_rank": -slowest * world}
+        res["what"] = f"{nbytes >> 20} MiB pinned copies issued by all {world} rank(s) at once, 3 repetitions"
+        return res
+
+    pcie = copy_probe()
+
     # ---- four-step NTT with all-to-all (configs[4]) when sharded -------------------
     four = None
     if world > 1:
@@ -729,7 +755,8 @@ def run_ours(args):
             "e2e": {"value": world * n * e2e_steps / (e_msm * 1e-3) / 1e6, "unit": "Mpts/s",
                     "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 32 + 64,
                     "ntt": {"value": world * n * e2e_steps / (e_ntt * 1e-3) / 1e6, "unit": "Melem/s"},
-                    "ms_per_step": e2e_wall / e2e_steps,
+                    "ms_per_step": e2e_wall / e2e_steps, "msm_ms": e_msm / e2e_steps, "ntt_ms": e_ntt / e2e_steps,
+                    "concurrent_pinned_copy_probe": pcie,
                     "path": "h2b_msm_affine + h2b_best_fft with H2B_HOST pointers (pinned), copies inside the timed region"},
             "gpu_launches": launches, "clocks": clocks, "sharded_msm_closed_form_check": bool(sharded_ok),
         }

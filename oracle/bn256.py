@@ -15,18 +15,18 @@ tag 0.3.1, /root/reference/halo2_proofs/Cargo.toml:51) with ``ff 0.12`` and
 (alt_bn128): y^2 = x^3 + 3 over Fq, generator (1, 2), scalar field Fr with
 2-adicity 28 and multiplicative generator 7.
 
-PARITY PARTLY PINNED.  Pinned against the reference's one golden artefact (the
-pinned verifying key of tests/plonk_api.rs:626-1019, fixture
-tests/golden/pinned_vk_plonk_api.json): EvaluationDomain::new's derivation of
-extended_k and omega (`domain_roots`, run there with the Vesta scalar field the
-key is over; tests/test_oracle.py::test_pinned_vk_of_the_reference).
-UNPINNED by reference golden vectors: the bn256 field / curve arithmetic, MSM
-and NTT outputs -- the reference holds no golden bytes for bn256 and cannot be
-built here.  For those this oracle is pinned by (i) the definitional known-answer
-vectors of SURVEY.md section 8c (``tests/golden/kat_bn256.json``), (ii) the
-reference's own test identities (kzg/commitment.rs:361-384 ``commit(ifft(a)) ==
-commit_lagrange(a)``, ntt round trips, NTT vs O(n^2) evaluation, MSM vs the
-naive sum) -- see tests/test_oracle.py.
+PARITY PINNED against reference-held outputs, through the curve the reference holds them for.  The reference's only
+golden vectors are the 19 commitment points (and the domain constants) of the pinned verifying key in
+tests/plonk_api.rs:624-1020 -- IPA over Vesta.  Its code is generic over the curve, and so is this file: every
+constant below can be overridden (`_CURVE_OVERRIDE`), oracle/pasta.py executes this very source a second time with
+Vesta's constants, and tests/test_oracle.py::test_reference_golden_commitments reproduces all 19 points bit for bit
+through `g_to_lagrange` (best_fft over curve points, :277-301), `best_multiexp` / `multiexp_serial` (:13-159, every
+thread count), `small_multiexp` (:105-125), `EvaluationDomain::new` (omega, extended_k) and the keygen of
+oracle/prover.py; the field transform is tied to them by commit(lagrange_to_coeff(a)) == commit_lagrange(a) on those
+parameters.  What remains recalled rather than verifiable is bn256-specific DATA, not algorithms: the constants of
+halo2curves 0.3.1 (moduli, generator (1, 2), 2-adicity 28, multiplicative generator 7 -- re-derived numerically in
+tests/test_oracle.py) and its byte encodings (assumptions A1-A4 in DESIGN.md), for which the reference tree holds no
+bytes.  Definitional known answers: tests/golden/kat_bn256.json.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import
 this module.
@@ -39,18 +39,22 @@ from typing import List, Optional, Sequence, Tuple
 # --------------------------------------------------------------------------
 # bn256 constants (re-derived in tests/test_oracle.py)
 # --------------------------------------------------------------------------
-R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001  # Fr
-Q_MOD = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47  # Fq
-S = 28
-MULT_GEN = 7
+# The restatements below are generic over the curve, like the reference's own code (`C: CurveAffine`).  oracle/pasta.py
+# loads a SECOND instance of this very source with Vesta's constants (the curve of the reference's only golden
+# vectors, tests/plonk_api.rs:624-1020) by setting `_CURVE_OVERRIDE` in the module namespace before executing it.
+_C = globals().get("_CURVE_OVERRIDE") or {}
+R_MOD = _C.get("R_MOD", 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001)  # Fr
+Q_MOD = _C.get("Q_MOD", 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47)  # Fq
+S = _C.get("S", 28)
+MULT_GEN = _C.get("MULT_GEN", 7)
 ROOT_OF_UNITY = pow(MULT_GEN, (R_MOD - 1) >> S, R_MOD)
 ROOT_OF_UNITY_INV = pow(ROOT_OF_UNITY, -1, R_MOD)
 ZETA = pow(MULT_GEN, (R_MOD - 1) // 3, R_MOD)
 TWO_INV = pow(2, -1, R_MOD)
 MONT_R_FR = (1 << 256) % R_MOD
 MONT_R_FQ = (1 << 256) % Q_MOD
-CURVE_B = 3
-G1_GEN = (1, 2)
+CURVE_B = _C.get("CURVE_B", 3)  # y^2 = x^3 + b (a = 0 for bn256 and for both pasta curves)
+G1_GEN = _C.get("G1_GEN", (1, 2))
 
 Point = Optional[Tuple[int, int]]  # affine; None = identity
 

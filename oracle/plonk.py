@@ -11,10 +11,10 @@ Expressions are nested tuples:
   ("constant", v) | ("fixed"|"advice"|"instance", column_index, rotation) | ("challenge", i)
   | ("negated", e) | ("sum", a, b) | ("product", a, b) | ("scaled", e, f)
 
-PARITY UNPINNED by reference golden vectors (see oracle/bn256.py): the reference has no bn256
-fixtures and cannot be built here; this file is pinned by the mathematical definition of the
-constraints it folds (tests/test_oracle.py checks h vanishes on the domain for a satisfied
-circuit, i.e. that it is divisible by X^n - 1).
+PARITY: the field / curve layer underneath is pinned against the reference's golden verifying key through its
+Vesta instance (see oracle/bn256.py, oracle/pasta.py).  The constraint folding of this file has no reference-held
+output (a proof needs the rng); it is pinned by the mathematical definition of the constraints it folds
+(tests/test_oracle.py checks h vanishes on the domain for a satisfied circuit, i.e. that it is divisible by X^n - 1).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
 """
@@ -22,9 +22,9 @@ from __future__ import annotations
 
 from typing import List, Sequence
 
-from .bn256 import R_MOD, ZETA
+from .bn256 import MULT_GEN, R_MOD, S, ZETA
 
-DELTA = pow(7, 1 << 28, R_MOD)  # Fr::DELTA = g^(2^S), halo2curves bn256/fr.rs
+DELTA = pow(MULT_GEN, 1 << S, R_MOD)  # Fr::DELTA = g^(2^S): 7^(2^28) for bn256 (halo2curves bn256/fr.rs)
 ADVICE, FIXED, INSTANCE = 0, 1, 2  # plonk/circuit.rs `Any`
 
 

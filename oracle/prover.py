@@ -19,17 +19,20 @@ GWC multi-opening, Blake2b transcript and `Challenge255`:
                                       shplonk/verifier.rs:52-148; arithmetic.rs:405-478
 * lookup argument (prover/verifier) -- src/plonk/lookup/prover.rs:55-475, src/plonk/lookup/verifier.rs:35-210
 
-PARITY PARTLY PINNED.  Pinned, character for character, against the reference's golden verifying key
-(tests/plonk_api.rs:626-1019; tests/test_oracle.py::test_pinned_vk_of_the_reference): `pinned_vk_debug`, i.e. the
-Debug rendering of PinnedVerificationKey / PinnedConstraintSystem / Expression / Column / Rotation and of field
-elements and points (assumption A3 below, in the form pasta_curves prints them), and with it the input of the
-verifying-key hash that seeds every transcript.  UNPINNED by reference bytes: proofs themselves -- the reference
-cannot be built here (no Rust toolchain) and holds no bn256 proof fixtures.  Encodings that live in the absent crate halo2curves 0.3.1 are restated from its published
-source and are ASSUMPTIONS, listed in DESIGN.md: (A2) G1Affine::to_bytes = 32-byte LE x with bit 7 of byte 31
-= parity of y, identity = zeros; (A3) `{:?}` of Fr/Fq = "0x" + 64 lowercase hex digits, big-endian, of a point
-"(x, y)"; (A4) Fr::random(rng) and from_bytes_wide = the 512-bit little-endian integer mod r, eight
-rng.next_u64() draws, low limb first.  What the oracle IS pinned by: every proof it produces is accepted by
-its own restatement of the reference verifier, tampered proofs are rejected (tests/test_oracle_prover.py).
+PARITY.  PINNED against the reference's golden verifying key (tests/plonk_api.rs:626-1019), through the Vesta instance
+of this same source that oracle/pasta.py loads: `keygen` (fixed-column commitments, the permutation Assembly's cycle
+merging, delta^i * omega^j, `commit_lagrange`) reproduces all 19 commitment points, and `pinned_vk_debug` -- the Debug
+rendering of PinnedVerificationKey / PinnedConstraintSystem / Expression / Column / Rotation, field elements and
+points (assumption A3 below), i.e. the input of the verifying-key hash that seeds every transcript -- the whole
+string, character for character (tests/test_oracle.py::test_reference_golden_commitments,
+::test_pinned_vk_of_the_reference).  UNPINNED by reference bytes: proofs themselves -- the reference cannot be built
+here (no Rust toolchain), draws its blinding from OsRng and holds no proof fixtures.  Encodings that live in the absent
+crate halo2curves 0.3.1 are restated from its published source and are ASSUMPTIONS, listed in DESIGN.md: (A2)
+G1Affine::to_bytes = 32-byte LE x with bit 7 of byte 31 = parity of y, identity = zeros; (A3) `{:?}` of Fr/Fq = "0x" +
+64 lowercase hex digits, big-endian, of a point "(x, y)" (confirmed for pasta by the golden key); (A4)
+Fr::random(rng) and from_bytes_wide = the 512-bit little-endian integer mod r, eight rng.next_u64() draws, low limb
+first.  Proofs are pinned by the restated reference verifier: every proof is accepted, tampered ones are rejected
+(tests/test_oracle_prover.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
 """

@@ -136,9 +136,11 @@ def check_evaluate_h(ctx: h.Context, variant: str, k: int, seed: int, n_circuits
 # ---------------------------------------------------------------------------
 # prover cases
 # ---------------------------------------------------------------------------
-def oracle_cs(cs: h.ConstraintSystem):
-    """The product's ConstraintSystem as the oracle's plain-data CS (data copying only)."""
-    from oracle import prover as OV
+def oracle_cs(cs: h.ConstraintSystem, OV=None):
+    """The product's ConstraintSystem as the oracle's plain-data CS (data copying only).  OV: the oracle prover
+    module to build it for (default: the bn256 instance; oracle/pasta.py loads the same source over Vesta)."""
+    if OV is None:
+        from oracle import prover as OV
     return OV.CS(num_fixed_columns=cs.num_fixed_columns, num_advice_columns=cs.num_advice_columns,
                  num_instance_columns=cs.num_instance_columns,
                  gates=[[p.to_tuple() for p in polys] for _, polys in cs.gates],
@@ -487,3 +489,55 @@ def check_phases_proof_bytes(ctx: h.Context, k: int = 5, seed: bytes = b"\x42" *
     params.g.free()
     params.g_lagrange.free()
     return want, opk.debug
+
+
+def plonk_api_configure():
+    """MyCircuit::configure of the reference's tests/plonk_api.rs:389-470, statement by statement, on the host
+    mirror's ConstraintSystem (the circuit behind the reference's pinned verifying key)."""
+    cs = h.ConstraintSystem()
+    e, a, b = cs.advice_column(), cs.advice_column(), cs.advice_column()
+    sf = cs.fixed_column()
+    c, d = cs.advice_column(), cs.advice_column()
+    p = cs.instance_column()
+    for col in (a, b, c):
+        cs.enable_equality(col)
+    sm, sa, sb, sc, sp = (cs.fixed_column() for _ in range(5))
+    sl = cs.fixed_column()  # lookup_table_column
+    a_ = cs.query_advice(a)
+    cs.lookup("lookup", [(a_, cs.query_fixed(sl))])  # the table column is queried after the closure ran
+    qd, qa, qsf = cs.query_advice(d, 1), cs.query_advice(a), cs.query_fixed(sf)
+    qe, qb, qc = cs.query_advice(e, -1), cs.query_advice(b), cs.query_advice(c)
+    qsa, qsb, qsc, qsm = cs.query_fixed(sa), cs.query_fixed(sb), cs.query_fixed(sc), cs.query_fixed(sm)
+    cs.create_gate("Combined add-mult", [qa * qsa + qb * qsb + qa * qb * qsm - (qc * qsc) + qsf * (qd * qe)])
+    qa, qp, qsp = cs.query_advice(a), cs.query_instance(p), cs.query_fixed(sp)
+    cs.create_gate("Public input", [qsp * (qa - qp)])
+    for col in (sf, e, d, p, sm, sa, sb, sc, sp):
+        cs.enable_equality(col)
+    return cs
+
+
+def plonk_api_keygen_inputs(k: int, a_value: int, instance: int, blinding_factors: int):
+    """What MyCircuit::synthesize (tests/plonk_api.rs:472-500) assigns at keygen, laid out the way
+    SimpleFloorPlanner places it (circuit/floor_planner/single_pass.rs): region `public_input` on row 0 (columns a,
+    sp), then ten times raw_multiply and raw_add on the next free rows of their columns (1, 2, ..., 20) and two
+    column-less `copy` regions; the lookup table in rows 0..3 of `sl`, the rest of the usable rows filled with its
+    first value (single_pass.rs:192-198, keygen.rs:154-175).
+    -> (fixed columns in index order [sf, sm, sa, sb, sc, sp, sl], copy constraints)"""
+    n = 1 << k
+    sf, sm, sa, sb, sc, sp, sl = ([0] * n for _ in range(7))
+    A, B, C_ = (h.ADVICE, 1), (h.ADVICE, 2), (h.ADVICE, 3)  # advice columns are created in the order e, a, b, c, d
+    copies = []
+    sp[0] = 1
+    row = 1
+    for _ in range(10):
+        mul, add = row, row + 1
+        sa[mul], sb[mul], sc[mul], sm[mul] = 0, 0, 1, 1  # raw_multiply, plonk_api.rs:141-148
+        sa[add], sb[add], sc[add], sm[add] = 1, 1, 1, 0  # raw_add, :199-206
+        copies += [(A, mul, A, add)] * 2                 # copy(a0, a1): constrain_equal twice, :223-226
+        copies += [(B, add, C_, mul)] * 2                # copy(b1, c0)
+        row += 2
+    table = [instance, a_value, a_value, 0]              # common!(): lookup_table, :511-516
+    usable = n - (blinding_factors + 1)
+    for i in range(usable):
+        sl[i] = table[i] if i < len(table) else table[0]
+    return [sf, sm, sa, sb, sc, sp, sl], copies

@@ -255,26 +255,7 @@ def test_pinned_vk_of_the_reference():
     from tests import plonk_cases as PC
 
     fx = H.load_golden("pinned_vk_plonk_api.json")
-    # plonk_api.rs:389-470 -- MyCircuit::configure, statement by statement
-    cs = h.ConstraintSystem()
-    e, a, b = cs.advice_column(), cs.advice_column(), cs.advice_column()
-    sf = cs.fixed_column()
-    c, d = cs.advice_column(), cs.advice_column()
-    p = cs.instance_column()
-    for col in (a, b, c):
-        cs.enable_equality(col)
-    sm, sa, sb, sc, sp = (cs.fixed_column() for _ in range(5))
-    sl = cs.fixed_column()  # lookup_table_column
-    a_ = cs.query_advice(a)
-    cs.lookup("lookup", [(a_, cs.query_fixed(sl))])  # the table column is queried after the closure ran
-    qd, qa, qsf = cs.query_advice(d, 1), cs.query_advice(a), cs.query_fixed(sf)
-    qe, qb, qc = cs.query_advice(e, -1), cs.query_advice(b), cs.query_advice(c)
-    qsa, qsb, qsc, qsm = cs.query_fixed(sa), cs.query_fixed(sb), cs.query_fixed(sc), cs.query_fixed(sm)
-    cs.create_gate("Combined add-mult", [qa * qsa + qb * qsb + qa * qb * qsm - (qc * qsc) + qsf * (qd * qe)])
-    qa, qp, qsp = cs.query_advice(a), cs.query_instance(p), cs.query_fixed(sp)
-    cs.create_gate("Public input", [qsp * (qa - qp)])
-    for col in (sf, e, d, p, sm, sa, sb, sc, sp):
-        cs.enable_equality(col)
+    cs = PC.plonk_api_configure()  # plonk_api.rs:389-470 -- MyCircuit::configure, statement by statement
 
     # the domain, through the oracle's EvaluationDomain::new restatement with Vesta's scalar field
     modulus = int(fx["scalar_modulus"], 16)
@@ -287,3 +268,57 @@ def test_pinned_vk_of_the_reference():
     mod = dict(base_modulus=int(fx["base_modulus"], 16), scalar_modulus=modulus)
     assert pinned_debug(cs, *args, **mod) == fx["debug"]
     assert OV.pinned_vk_debug(PC.oracle_cs(cs), *args, **mod) == fx["debug"]
+
+
+def test_reference_golden_commitments():
+    """THE PIN of the MSM / NTT restatements against outputs the reference itself holds: the 19 commitment points of
+    its pinned verifying key (tests/plonk_api.rs:994-1017; k = 5, IPA over Vesta).  They are produced by
+    keygen_vk -> `commit_lagrange` -> `best_multiexp` over `g_lagrange = g_to_lagrange(g)` (best_fft over curve
+    points) with hash-to-curve generators (poly/ipa/commitment.rs:158-207).  The reference is generic over the curve
+    and so is the oracle: oracle/pasta.py executes the SAME source files (oracle/bn256.py, plonk.py, prover.py) a
+    second time with Vesta's constants, adds pasta's hash-to-curve, and this test reproduces
+
+      * w = hash_to_curve("Halo2-Parameters")(&[1]) = the commitment of the never-assigned fixed column `sf` (1 * w),
+      * the other 6 fixed-column commitments (multiexp_serial's windows and buckets on 33 points, arithmetic.rs:13-159;
+        the group FFT and 1/n scaling of g_to_lagrange, :277-301),
+      * the 12 permutation commitments (permutation/keygen.rs: cycle merging, delta^i * omega^j),
+      * and with them the whole `{:?}` string of the pinned key, character for character."""
+    from oracle import pasta
+    from tests import plonk_cases as PC
+    V, _, VV = pasta.load_vesta()
+    fx = H.load_golden("pinned_vk_plonk_api.json")
+    pts = lambda key: [(int(x, 16), int(y, 16)) for x, y in fx[key]]  # noqa: E731
+    assert (V.R_MOD, V.Q_MOD) == (int(fx["scalar_modulus"], 16), int(fx["base_modulus"], 16))
+    assert O.R_MOD != V.R_MOD and O.S == 28 and V.S == 32  # the bn256 instance is untouched
+
+    # 1. hash-to-curve, against the one golden point that is a bare generator
+    w = pasta.hash_to_curve("Halo2-Parameters")(b"\x01")
+    assert w == pts("fixed_commitments")[0]
+
+    # 2. ParamsIPA::new(5): g by hash-to-curve, g_lagrange by the group FFT (consistency: the Lagrange commitment of
+    #    evaluations equals the monomial commitment of the interpolated coefficients, ipa/commitment.rs:255-301)
+    params = pasta.ParamsIPA(V, fx["k"])
+    dom = V.EvaluationDomain(1, fx["k"])
+    vals = [(i * i + 7) % V.R_MOD for i in range(params.n)]
+    assert params.commit(dom.lagrange_to_coeff(list(vals)), 5) == params.commit_lagrange(vals, 5)
+
+    # 3. keygen of the plonk_api circuit over those parameters
+    cs = PC.oracle_cs(PC.plonk_api_configure(), VV)
+    # pasta Fp::ZETA (pasta_curves fields/fp.rs) -- of the two primitive cube roots of unity it is 5^(2(p-1)/3); the
+    # commitment of the lookup-table column below only comes out right with this one
+    zeta = 0x12CCCA834ACDBA712CAAD5DC57AAB1B01D1F8BD237AD31491DAD5EBDFDFE4AB9
+    assert zeta == pow(5, 2 * (V.R_MOD - 1) // 3, V.R_MOD) and pow(zeta, 3, V.R_MOD) == 1
+    a_value = 2834758237 * zeta % V.R_MOD        # common!(): Scalar::from(2834758237) * Scalar::ZETA
+    fixed, copies = PC.plonk_api_keygen_inputs(fx["k"], a_value, 2, cs.blinding_factors())
+    pk = VV.keygen(params, cs, fixed, copies)
+    assert pk.domain.extended_k == fx["extended_k"] and pk.domain.omega == int(fx["omega"], 16)
+    assert pk.fixed_commitments == pts("fixed_commitments")
+    assert pk.perm_commitments == pts("permutation_commitments")
+    assert pk.debug == fx["debug"]
+    # the same points through every thread count of best_multiexp's chunking (arithmetic.rs:135-153) and through
+    # small_multiexp (:105-125): the window rule changes with the chunk length, the sum must not
+    col = fixed[4] + [1]
+    bases = params.g_lagrange + [params.w]
+    for threads in (1, 2, 3, 8, 33, 64):
+        assert V.best_multiexp(col, bases, threads) == pts("fixed_commitments")[4], threads
+    assert V.small_multiexp(col, bases) == pts("fixed_commitments")[4]
