@@ -44,6 +44,12 @@ struct PassParams {
   // sb: a SINGLE-pass transform (2^s points, s = 6..9) run by the register kernel: the C columns of a tile are C
   // consecutive batch members instead of C consecutive strided columns of one transform
   uint32_t sb;
+  // Batch-interleaved scratch between the last two passes of row transforms that end in peer stores: the pass before
+  // the last one writes element o of batch member b at ((b / il) * n + o) * il + b % il (il_out = il), the last pass
+  // reads it back with `il` consecutive batch members as its tile columns (il_in = il = its tile width), so that the
+  // stores of a warp into the transposed matrix on a peer are runs of il * 32 contiguous bytes instead of isolated
+  // 32-byte words (the run dimension of the destination is the row = batch member).
+  uint32_t il_out, il_in;
   uint32_t s1;                       // log2 R_1
   uint32_t nmid;                     // number of middle digits (s_2 .. s_(P-1))
   uint32_t mid_s[4];                 // their widths, s_2 first
@@ -94,7 +100,7 @@ struct Tile {
 
 H2B_HD Tile tile_geom(const PassParams& p, uint64_t t) {
   Tile g;
-  g.out_cm = p.sb ? 0u : 1u;
+  g.out_cm = (p.sb || p.il_in) ? 0u : 1u;
   if (p.single) {
     g.in_base = 0;
     g.in_rs = 1;
@@ -176,6 +182,8 @@ H2B_D void store_out_t(const PassParams& p, Fr* out, const Tile& g, uint32_t K, 
     return;
   }
   const uint64_t o = g.out_base + (uint64_t)K * g.out_rs + c;
+  Fr* dst = out + o;
+  if (p.il_out) dst = p.out + ((bidx / p.il_out) * p.out_bstride + o) * p.il_out + bidx % p.il_out;
   if (KIND == KIND_OUT_TABLE) {
     x = mul_tw(x, ld_fp_nc(p.tw_out + o));
   } else if (KIND == KIND_MID_TABLE) {
@@ -188,7 +196,7 @@ H2B_D void store_out_t(const PassParams& p, Fr* out, const Tile& g, uint32_t K, 
     x = mul_tw(x, ld_fp_nc(p.tw_lo + elo));
     x = mul_tw(x, ld_fp_nc(p.tw_hi + ehi));
   }
-  st_fp(out + o, x);
+  st_fp(dst, x);
 }
 
 // the generic kernel keeps the run-time dispatch (tiny transforms only)
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   const uint32_t c = tid & (C - 1), u = tid >> LC;
   const Tile g = tile_geom(p, blockIdx.x);
   // batch member of this thread's column: the grid row, or (sb) one of the C members of this tile
-  const uint64_t bidx = p.sb ? (uint64_t)blockIdx.x * C + c : (uint64_t)blockIdx.y;
+  const uint64_t bidx = p.sb ? (uint64_t)blockIdx.x * C + c : p.il_in ? (uint64_t)blockIdx.y * C + c : (uint64_t)blockIdx.y;
   const Fr* in = p.in + bidx * p.in_bstride;
   Fr* out = p.out + bidx * p.out_bstride;
   const uint32_t rsh = p.rt_log - S;  // w_R^e = rt[e << rsh]
@@ -319,7 +327,10 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     const uint32_t row = a * T + u;
-    x[a] = load_in_t<PRE>(p, in, g.in_base + row * g.in_rs + c * g.in_cs);
+    if (KIND == KIND_LAST_PEER && p.il_in)  // interleaved scratch: C batch members side by side
+      x[a] = ld_fp(p.in + ((uint64_t)blockIdx.y * p.in_bstride + g.in_base + row * g.in_rs) * C + c);
+    else
+      x[a] = load_in_t<PRE>(p, in, g.in_base + row * g.in_rs + c * g.in_cs);
   }
   dft8(x, p.rt, p.rt_log);
 #pragma unroll
@@ -682,6 +693,7 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       p.last = pi == P - 1;
       p.single = P == 1;
       p.sb = 0;
+      p.il_out = p.il_in = 0;
       p.s1 = s[0];
       p.nmid = 0;
       for (int i = 1; i + 1 < P; ++i) p.mid_s[p.nmid++] = s[i];
@@ -734,6 +746,13 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
         p.out = scratch;
         p.out_bstride = n;
       }
+      // peer-scattering row transforms of >= 2 passes: interleave the scratch of the last two passes (see PassParams)
+      const uint32_t il = (sc && P >= 2 && s[P - 1] >= 6 && s[P - 1] <= 9 && nb % (1u << (11 - s[P - 1])) == 0 &&
+                           getenv("H2B_NTT_NO_IL") == nullptr)
+                              ? 1u << (11 - s[P - 1])
+                              : 0u;
+      if (il && pi == P - 2) p.il_out = il;
+      if (il && pi == P - 1) p.il_in = il;
       // columns per tile
       uint32_t lc = 11 - p.s;
       const uint32_t avail = p.single ? 0 : (p.last ? p.s1 : lm - p.s);
@@ -744,12 +763,15 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       if (sb) {
         fast = true;
         p.sb = 1;
+      } else if (p.il_in) {
+        fast = true;  // the tile's columns are batch members: one strided column of the transform per tile
+        lc = 0;
       } else if (lc > avail) {
         lc = avail;
       }
       p.lc = lc;
-      const uint32_t tiles = sb ? nb >> lc : (uint32_t)(n >> (p.s + lc));
-      const dim3 grid(tiles, sb ? 1u : nb);
+      const uint32_t tiles = sb ? nb >> (11 - p.s) : (uint32_t)(n >> (p.s + lc));
+      const dim3 grid(tiles, sb ? 1u : p.il_in ? nb / p.il_in : nb);
       const bool prof = ctx->profile && b0 == 0 && pi < 5;
       if (prof) H2B_CUDA(ctx, cudaEventRecord(ctx->pass_ev[pi], ctx->stream));
       if (fast) {

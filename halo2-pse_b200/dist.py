@@ -442,17 +442,36 @@ class FourStepNTT:
         S1, S2 = self.S
         H1, H2 = self.H
         torch.cuda.current_stream().synchronize()  # `a` may have been produced on torch's stream
+        timing = os.environ.get("H2B_FOURSTEP_TIMING")
+        ev = []
+
+        def mark():
+            if timing:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(self.xstream)
+                ev.append(e)
+
         with torch.cuda.stream(self.xstream):
             H1.barrier(0)  # every peer is done with S1 of the previous transform
+            mark()
             self._scatter(self._p(a), 0, n1 // G, n2)           # A[j1][j2] -> A^T[j2][j1] in S1
+            mark()
             H1.barrier(0)
+            mark()
             # n1-point transforms of the rows j2 of A^T, times w^(j2*K1), stored as B[K1][j2] in the peers' S2
             self._rows_scatter(S1, 1, self.w1, self.k1, n2 // G, n2, True)
+            mark()
             H2.barrier(0)
+            mark()
             # n2-point transforms of the rows K1 of B; C[K1][K2] = X[K1 + n1*K2] stored in natural order in the peers' S1
             self._rows_scatter(S2, 0, self.w2, self.k2, n1 // G, n1, False)
+            mark()
             H1.barrier(0)
+            mark()
         ctx.sync()
+        if timing:
+            names = ["transpose+exchange", "barrier", "rows n1 (+twiddle, exchange)", "barrier", "rows n2 (+exchange)", "barrier"]
+            self.last_stage_ms = {f"{i}:{n}": ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
         return S1
 
     # -- helpers ---------------------------------------------------------

@@ -29,6 +29,12 @@ for k in [int(x) for x in (sys.argv[1:] or ["22", "24", "26"])]:
         nbad = int(diff.sum().item())
         first = diff.nonzero()[:6].flatten().tolist()
         print(f"rank {rank} k={k} {label} k1={fs.k1} p2p={fs.p2p}: mismatching elements {nbad} of {loc} first {first}", flush=True)
+        if fs.p2p and os.environ.get("H2B_FOURSTEP_TIMING"):
+            for _ in range(3):
+                fs.run(buf)
+            torch.cuda.synchronize()
+            if rank in (0, world - 1):
+                print(f"rank {rank} k={k} stages ms:", {kk: round(v, 3) for kk, v in fs.last_stage_ms.items()}, flush=True)
         del fs
     full.free()
 torch.distributed.barrier()

@@ -57,29 +57,45 @@ for k in ks:
     sc = ctx.synth_scalars(e - s, 5 + rank, 0)
     msm = D.ShardedMSM(ctx, bases)
     t = best(lambda: msm.msm(sc, e - s))
-    out["msm"][k] = {"points_per_gpu": e - s, "window_bits": bases.table_window_bits, "ms": t * 1e3,
-                     "mpts_s": n / t / 1e6}
+    cw = bases.table_window_bits
+    Ww = (255 + cw - 1) // cw
+    out["msm"][k] = {"points_per_gpu": e - s, "window_bits": cw, "ms": t * 1e3, "mpts_s": n / t / 1e6,
+                     # whole sharded MSM against the IMAD.WIDE peak of ALL ranks (algorithmic n*W*11*136)
+                     "roofline_frac": n * Ww * 11 * 136 / t / (ctx.pipe_peak("imad_wide")[0] * world)}
     sc.free()
     bases.free()
     if rank == 0:
         print("msm", k, json.dumps(out["msm"][k]), flush=True)
+imad = ctx.pipe_peak("imad_wide")[0]
 for k in ks:
-    if k > 24:
-        continue
     n = 1 << k
     dom = h.EvaluationDomain(ctx, 5, k)
-    ne = dom.extended_len()
+    ne, ek = dom.extended_len(), dom.extended_k
     mine = len([c for c in range(NCOLS) if D.column_owner(c, world) == rank])
-    if mine * (n + ne) * 32 > (100 << 30):
-        dom.free()
-        continue
-    src, dst = ctx.alloc(mine * n * 32), ctx.alloc(mine * ne * 32)
+    # this rank's columns, inputs resident; the extended outputs go through a ring of column groups (<= 16 GiB)
+    group = max(1, min(mine, (16 << 30) // (ne * 32)))
+    src, dst = ctx.alloc(mine * n * 32), ctx.alloc(group * ne * 32)
     ctx._check(ctx.lib.h2b_synth_scalars(ctx.h, src.ptr, mine * n, 9 + rank, 0))
-    t1 = best(lambda: dom.coeff_to_extended_device(src, dst, mine), reps=2)
-    t2 = best(lambda: dom.extended_to_coeff_device(dst, dst, mine, out_stride=ne), reps=2)
-    out["ntt_x64"][k] = {"columns_per_gpu": mine, "coeff_to_extended_ms": t1 * 1e3,
+    lib = ctx.lib
+
+    def c2e():
+        for c0 in range(0, mine, group):
+            nc = min(group, mine - c0)
+            ctx._check(lib.h2b_coeff_to_extended_batch(dom.h, src.at(c0 * n * 32), n, dst.ptr, ne, h.H2B_DEVICE, nc))
+
+    def e2c():
+        for c0 in range(0, mine, group):
+            nc = min(group, mine - c0)
+            ctx._check(lib.h2b_extended_to_coeff_batch(dom.h, dst.ptr, ne, dst.ptr, ne, h.H2B_DEVICE, nc, 1))
+
+    t1 = best(c2e, reps=2)
+    t2 = best(e2c, reps=2)
+    out["ntt_x64"][k] = {"columns_per_gpu": mine, "columns_per_group": group, "extended_k": ek,
+                         "coeff_to_extended_ms": t1 * 1e3,
                          "coeff_to_extended_melem_s_out": NCOLS * ne / t1 / 1e6,
-                         "extended_to_coeff_ms": t2 * 1e3, "extended_to_coeff_melem_s_in": NCOLS * ne / t2 / 1e6}
+                         "coeff_to_extended_int_frac_per_gpu": mine * (ne / 2) * ek * 136 / t1 / imad,
+                         "extended_to_coeff_ms": t2 * 1e3, "extended_to_coeff_melem_s_in": NCOLS * ne / t2 / 1e6,
+                         "extended_to_coeff_int_frac_per_gpu": mine * (ne / 2) * ek * 136 / t2 / imad}
     src.free()
     dst.free()
     dom.free()
@@ -88,7 +104,7 @@ for k in ks:
 barrier()
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open(f"gpurun_out/sweep_multi_n{world}.json", "w"), indent=1)
+    json.dump(out, open(f"gpurun_out/r2_sweep_multi_n{world}.json", "w"), indent=1)
 ctx.close()
 if world > 1:
     torch.distributed.destroy_process_group()

@@ -184,9 +184,10 @@ def test_rows_scatter_kernel_and_p2p_schedule(emu_ctx, oracle_c):
 
     # the register kernel's fused last pass (rows of 2^12 and 2^13 points: two passes) against row-wise best_fft
     # ... and single-pass rows (64 / 512 points) through the register kernel with batch members as tile columns
-    for log_len, rows, G, row0, total in ((12, 3, 2, 5, 16), (13, 2, 4, 0, 2), (9, 8, 2, 0, 8), (6, 32, 4, 32, 64)):
+    for log_len, rows, G, row0, total in ((12, 3, 2, 5, 16), (13, 2, 4, 0, 2), (9, 8, 2, 0, 8), (6, 32, 4, 32, 64),
+                                           (12, 32, 2, 0, 32), (13, 16, 4, 16, 64), (13, 48, 2, 3, 64)):  # interleaved scratch
         L = 1 << log_len
-        big_k = 17
+        big_k = 20
         big = O.omega_for(big_k)
         wl = H.fr_enc([O.omega_for(log_len)])
         x = H.rand_fr_limbs(log_len, rows * L)
