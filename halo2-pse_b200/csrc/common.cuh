@@ -203,6 +203,12 @@ H2B_D void st_fp(Fp<P>* p, const Fp<P>& r) {
 #endif
 }
 
+// cudaMalloc for the library's own long-lived buffers (workspaces, scratch, tables): on an out-of-memory answer the
+// context's cache of released caller blocks and the stream-ordered pool are given back to the driver and the
+// allocation is tried once more -- gigabytes can sit idle there.  Rule for the block cache: a block may
+// only be released (h2b_device_free) after every stream that touched it has been fenced into ctx->stream; every entry
+// point of this library ends in such a fence.
+cudaError_t dev_malloc(h2b_ctx* ctx, void** out, size_t bytes);
 int ensure_scratch(h2b_ctx* ctx, size_t bytes);
 int ensure_stage(h2b_ctx* ctx, int which, size_t bytes);
 // Host <-> device copies enqueued on `stream` that do not depend on the host slice being pinned:

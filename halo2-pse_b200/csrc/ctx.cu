@@ -77,7 +77,7 @@ static int grow(h2b_ctx* ctx, void** p, size_t* cap, size_t bytes) {
     *p = nullptr;
     *cap = 0;
   }
-  H2B_CUDA(ctx, cudaMalloc(p, bytes));
+  H2B_CUDA(ctx, dev_malloc(ctx, p, bytes));
   *cap = bytes;
   return H2B_OK;
 }
@@ -560,6 +560,20 @@ static void block_cache_flush(h2b_ctx* ctx) {
     }
   ctx->block_cache.clear();
   ctx->block_cache_bytes = 0;
+}
+
+cudaError_t h2b::dev_malloc(h2b_ctx* ctx, void** out, size_t bytes) {
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaErrorMemoryAllocation) return e;
+  cudaGetLastError();
+  cudaStreamSynchronize(ctx->stream);
+  block_cache_flush(ctx);
+#ifndef H2B_EMU
+  cudaStreamSynchronize(ctx->stream);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+#endif
+  return cudaMalloc(out, bytes);
 }
 
 extern "C" int h2b_device_alloc(h2b_ctx* ctx, size_t bytes, void** out) {

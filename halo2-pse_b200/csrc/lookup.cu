@@ -119,18 +119,20 @@ uint32_t grid_for(h2b_ctx* ctx, uint64_t n, uint32_t threads) {
   return (uint32_t)(want < cap ? want : cap);
 }
 
-struct DevMem {  // frees on scope exit
+struct DevMem {  // scratch of one call, released on scope exit: the context's stream-ordered pool and block cache
+  h2b_ctx* ctx;    // (cudaMalloc / cudaFree would synchronise the whole device 16 times per lookup)
   std::vector<void*> ptrs;
+  explicit DevMem(h2b_ctx* c) : ctx(c) {}
   ~DevMem() {
-    for (void* p : ptrs) cudaFree(p);
+    for (void* p : ptrs) h2b_device_free(ctx, p);
   }
   template <class T>
   cudaError_t get(T** out, size_t count) {
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
-    if (e == cudaSuccess) ptrs.push_back(p);
+    const int rc = h2b_device_alloc(ctx, (count ? count : 1) * sizeof(T), &p);
+    if (rc == H2B_OK) ptrs.push_back(p);
     *out = reinterpret_cast<T*>(p);
-    return e;
+    return rc == H2B_OK ? cudaSuccess : cudaErrorMemoryAllocation;
   }
 };
 
@@ -193,7 +195,7 @@ extern "C" int h2b_lookup_permute(h2b_ctx* ctx, const h2b_fr* input_dev, const h
   if (usable_rows > (1ull << 31)) return fail(ctx, H2B_ERR_ARG, "too many rows");
   H2B_CUDA(ctx, cudaSetDevice(ctx->device));
   const uint32_t n = (uint32_t)usable_rows;
-  DevMem mem;
+  DevMem mem(ctx);
   Fr *canon, *s_canon, *s_mont, *t_canon, *t_mont, *leftover;
   uint32_t *perm, *perm_alt, *key, *key_alt, *rep_flag, *rep_rank, *left_flag, *left_rank;
   int* d_err;

@@ -635,19 +635,19 @@ static int ws_ensure(h2b_ctx* ctx, const MsmPlan& p) {
   nsegs = std::max(nsegs, ws->cap_seg);
   H2B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ws_release(ws);
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->keys_in, pairs * 4 + 64));
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->keys_out, pairs * 4 + 64));
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->vals_in, pairs * 4 + 64));
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->vals_out, pairs * 4 + 64));
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->cnt, chunks0 * 4 + 64));
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->incl, chunks0 * 4 + 64));
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->n_level, (kMaxLevels + 2) * 4));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->keys_in, pairs * 4 + 64));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->keys_out, pairs * 4 + 64));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->vals_in, pairs * 4 + 64));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->vals_out, pairs * 4 + 64));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->cnt, chunks0 * 4 + 64));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->incl, chunks0 * 4 + 64));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->n_level, (kMaxLevels + 2) * 4));
   for (int i = 0; i < 2; ++i) {
-    H2B_CUDA(ctx, cudaMalloc((void**)&ws->lkeys[i], list * 4));
-    H2B_CUDA(ctx, cudaMalloc((void**)&ws->lpts[i], list * sizeof(G1Xyzz)));
-    H2B_CUDA(ctx, cudaMalloc((void**)&ws->seg[i], (nsegs + 256) * sizeof(G1Xyzz)));
+    H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->lkeys[i], list * 4));
+    H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->lpts[i], list * sizeof(G1Xyzz)));
+    H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->seg[i], (nsegs + 256) * sizeof(G1Xyzz)));
   }
-  H2B_CUDA(ctx, cudaMalloc((void**)&ws->buckets, nbuckets * sizeof(G1Xyzz)));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->buckets, nbuckets * sizeof(G1Xyzz)));
   H2B_CUDA(ctx, cudaMallocHost((void**)&ws->h_out, 64 * sizeof(G1Xyzz)));
 #ifndef H2B_EMU
   size_t t1 = 0, t2 = 0;
@@ -656,7 +656,7 @@ static int ws_ensure(h2b_ctx* ctx, const MsmPlan& p) {
   cub::DeviceScan::InclusiveSum(nullptr, t2, ws->cnt, ws->incl,
                                 (int)std::max<size_t>(chunks0, (size_t)(pairs / 2) + 2), ctx->stream);
   ws->cub_temp_bytes = std::max(t1, t2) + 256;
-  H2B_CUDA(ctx, cudaMalloc(&ws->cub_temp, ws->cub_temp_bytes));
+  H2B_CUDA(ctx, dev_malloc(ctx, &ws->cub_temp, ws->cub_temp_bytes));
 #endif
   ws->cap_pairs = pairs;
   ws->cap_chunks = chunks0;
@@ -700,12 +700,12 @@ static int accumulate_affine(h2b_ctx* ctx, MsmWorkspace* ws, const MsmPlan& p, c
     ws->astage = nullptr;
     ws->cap_aff = ws->cap_slots = 0;
     for (int i = 0; i < 2; ++i) {
-      H2B_CUDA(ctx, cudaMalloc((void**)&ws->akeys[i], cap * 4));
-      H2B_CUDA(ctx, cudaMalloc((void**)&ws->apts[i], cap * sizeof(G1Affine)));
+      H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->akeys[i], cap * 4));
+      H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->apts[i], cap * sizeof(G1Affine)));
     }
-    H2B_CUDA(ctx, cudaMalloc((void**)&ws->acnt, slots * 4));
-    H2B_CUDA(ctx, cudaMalloc((void**)&ws->apre, slots * sizeof(Fq)));
-    H2B_CUDA(ctx, cudaMalloc((void**)&ws->astage,
+    H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->acnt, slots * 4));
+    H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->apre, slots * sizeof(Fq)));
+    H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->astage,
                              2 * std::min<size_t>(slots, kStageTile) * sizeof(G1Affine)));
     if (!ws->h_scalar) H2B_CUDA(ctx, cudaMallocHost((void**)&ws->h_scalar, 64));
     ws->cap_aff = cap;
@@ -848,7 +848,7 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
       if (ws->buckets2) cudaFree(ws->buckets2);
       ws->buckets2 = nullptr;
       ws->cap_buckets2 = 0;
-      H2B_CUDA(ctx, cudaMalloc((void**)&ws->buckets2, (size_t)nbuckets_all * sizeof(G1Xyzz)));
+      H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->buckets2, (size_t)nbuckets_all * sizeof(G1Xyzz)));
       ws->cap_buckets2 = nbuckets_all;
     }
     target = ws->buckets2;
@@ -1129,7 +1129,7 @@ extern "C" int h2b_bases_upload(h2b_ctx* ctx, const h2b_g1_affine* bases, size_t
   b->ctx = ctx;
   b->n = n;
   b->d_pts = nullptr;
-  cudaError_t e = cudaMalloc((void**)&b->d_pts, (n ? n : 1) * sizeof(G1Affine));
+  cudaError_t e = dev_malloc(ctx, (void**)&b->d_pts, (n ? n : 1) * sizeof(G1Affine));
   if (e == cudaSuccess && n) {
     if (loc == H2B_DEVICE)
       e = cudaMemcpyAsync(b->d_pts, bases, n * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx->stream);
@@ -1188,8 +1188,8 @@ extern "C" int h2b_bases_precompute(h2b_ctx* ctx, h2b_bases* b, uint32_t window_
   }
   G1Affine* table = nullptr;
   G1Xyzz* tmp = nullptr;
-  H2B_CUDA(ctx, cudaMalloc((void**)&table, (size_t)W * b->n * sizeof(G1Affine)));
-  cudaError_t e = cudaMalloc((void**)&tmp, b->n * sizeof(G1Xyzz));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&table, (size_t)W * b->n * sizeof(G1Affine)));
+  cudaError_t e = dev_malloc(ctx, (void**)&tmp, b->n * sizeof(G1Xyzz));
   if (e != cudaSuccess) {
     cudaFree(table);
     return fail(ctx, H2B_ERR_OOM, cudaGetErrorString(e));

@@ -546,9 +546,9 @@ int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t k, const TwTable** out
   t.h = (k + 1) / 2;
   const uint32_t nlo = 1u << t.h, nhi = 1u << (k - t.h);
   const uint32_t rt_log = k < 9 ? k : 9;
-  H2B_CUDA(ctx, cudaMalloc((void**)&t.d_lo, (size_t)nlo * sizeof(Fr)));
-  H2B_CUDA(ctx, cudaMalloc((void**)&t.d_hi, (size_t)nhi * sizeof(Fr)));
-  H2B_CUDA(ctx, cudaMalloc((void**)&t.d_rt, ((size_t)1 << rt_log) * sizeof(Fr)));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&t.d_lo, (size_t)nlo * sizeof(Fr)));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&t.d_hi, (size_t)nhi * sizeof(Fr)));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&t.d_rt, ((size_t)1 << rt_log) * sizeof(Fr)));
   H2B_TRY(launch(ctx, pow_table_kernel, dim3((nlo + 127) / 128), dim3(128), 0, t.d_lo, omega, 0u,
                  nlo));
   H2B_TRY(launch(ctx, pow_table_kernel, dim3((nhi + 127) / 128), dim3(128), 0, t.d_hi, omega, t.h,
@@ -561,7 +561,7 @@ int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t k, const TwTable** out
     ntt_plan(k, s);
     t.mid_log = k - s[0];
     const uint32_t nmid = 1u << t.mid_log;
-    if (cudaMalloc((void**)&t.d_mid, (size_t)nmid * sizeof(Fr)) == cudaSuccess) {
+    if (dev_malloc(ctx, (void**)&t.d_mid, (size_t)nmid * sizeof(Fr)) == cudaSuccess) {
       H2B_TRY(launch(ctx, pow_table_kernel, dim3((nmid + 127) / 128), dim3(128), 0, t.d_mid, omega, k - t.mid_log,
                      nmid));
     } else {
@@ -579,7 +579,7 @@ int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t k, const TwTable** out
     }
     if (k >= out_lo && k <= out_hi) {
       const uint64_t nfull = 1ull << k;
-      if (cudaMalloc((void**)&t.d_out, (size_t)nfull * sizeof(Fr)) == cudaSuccess) {
+      if (dev_malloc(ctx, (void**)&t.d_out, (size_t)nfull * sizeof(Fr)) == cudaSuccess) {
         H2B_TRY(launch(ctx, tw_out_table_kernel, dim3((uint32_t)ctx->sm_count * 16), dim3(256), 0, t.d_out, k, s[0],
                        (const Fr*)t.d_lo, (const Fr*)t.d_hi, t.h));
         t.out_s1 = s[0];
