@@ -107,7 +107,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # Same configuration as the GPU arm (BASELINE.json: k = 24): one pass is ~10-25 s of host time.
 CPU_MSM_LOG, CPU_NTT_LOG = K_LOG, K_LOG
-CPU_ARM_BUDGET_S = 240.0  # the reference arm stops starting new passes after this much timed work
+CPU_ARM_BUDGET_S = 150.0  # the reference arm stops starting new passes after this much timed work
 
 
 def cpu_pass(oc, H, O, scalars, bases, ntt_in, omega, threads):
@@ -562,8 +562,8 @@ def run_ours(args):
         "achieved": mults / (acc_ms * 1e-3) / 1e12, "peak": mult_peak / 1e12, "unit": "Tmul/s",
         "frac": mults / (acc_ms * 1e-3) / mult_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at k=24, c=22 from the committed
-        # ncu --set full capture profiles/r1_final_msm_accum0_ntt_pass_k24_ncu_full.txt (28.79 GB + 0.72 GB)
-        "traffic": 29.52e9 if (k == 24 and c_win == 22) else None,
+        # ncu --set full capture profiles/r2_msm_accum0_ntt_passes_k24_ncu_full.txt (28.65 GB + 0.52 GB)
+        "traffic": 29.17e9 if (k == 24 and c_win == 22) else None,
         "frac_executed": executed / (acc_ms * 1e-3) / mult_peak,
         "executed": "n*W*10*130 IMAD.WIDE actually issued (XYZZ mixed addition 8M+2S; 128 + 2 wide multiplies per "
                     "Montgomery product); `frac` uses the survey's algorithmic 11*136 as the contract asks",
@@ -582,8 +582,9 @@ def run_ours(args):
         "kernel": "ntt_pass_fast<8> (one radix-256 pass over HBM)", "bound": "hbm",
         "achieved": 64.0 * n / (slow * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": 64.0 * n / (slow * 1e-3) / 1e9 / peaks["hbm_gbs"],
-        # same capture: 537.5 MB read + 491.5 MB written per pass at k=24 (= the algorithmic 2 x 512 MiB)
-        "traffic": 1.029e9 if k == 24 else None, "peak_source": peak_src,
+        # same capture, slowest pass (the first): 1 074 MB read (512 MiB of input + the 512 MiB twiddle stream) +
+        # 505 MB written at k=24; the other passes move the algorithmic 2 x 512 MiB (538 + 479 MB)
+        "traffic": 1.579e9 if k == 24 else None, "peak_source": peak_src,
         "algorithmic": f"64 B per element per pass (one read + one write), n=2^{k}", "pass_ms": pass_ms,
         "int_Tmul_s": (n / 2) * k * MULTS_PER_MULMOD / (sum(pass_ms) * 1e-3) / 1e12,
         # the binding roofline of a 256-bit NTT (max of the two): (n/2) log2 n butterflies x 136 multiplies
