@@ -43,8 +43,14 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
 
+    hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
+
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        # objects are rebuilt per source: a change to one .cu file recompiles that file only
+        if not force and not verbose and not os.environ.get("H2B_NVCC_EXTRA") and \
+                not _stale(obj, [os.path.join(CSRC, src)] + hdrs):
+            return obj
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
               os.environ.get("H2B_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)

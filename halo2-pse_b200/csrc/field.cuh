@@ -393,12 +393,55 @@ H2B_HD Fp<P> to_mont(const Fp<P>& a) {
   return mul(a, Fp<P>::r2());
 }
 
-// Montgomery -> canonical residue (multiply by 1)
+// r = t / 2^256 mod p for a 16-word t < p * 2^256: the reduction half of `mul` alone (64 + 8 multiplies), on the same
+// two interleaved column accumulators.  The high words join at the end: columns >= 8 must start empty, because the
+// ends of the chains (E[8], O[7]) do not capture a carry-out.
+template <class P, bool HIGH>
+H2B_HD Fp<P> mont_reduce(const uint32_t* t) {
+  uint32_t A[2][18];
+#pragma unroll
+  for (int c = 0; c < 18; ++c) {
+    A[0][c] = c < 8 ? t[c] : 0u;
+    A[1][c] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int s0 = i & 1, s1 = s0 ^ 1;
+    uint32_t* E = &A[s0][i];
+    uint32_t* O = &A[s1][i + 1];
+    uint32_t x;
+    if (i == 0) {
+      x = A[0][0] + A[1][0];
+    } else {
+#ifdef __CUDA_ARCH__
+      uint32_t tmp;
+      asm("add.cc.u32 %1, %2, %3;\n\taddc.u32 %0, %4, %5;"
+          : "=r"(x), "=r"(tmp)
+          : "r"(A[0][i - 1]), "r"(A[1][i - 1]), "r"(A[0][i]), "r"(A[1][i]));
+#else
+      x = A[0][i] + A[1][i] + (uint32_t)(((uint64_t)A[0][i - 1] + A[1][i - 1]) >> 32);
+#endif
+    }
+    const uint32_t m = x * P::INV;
+    if (i == 0)
+      chain_mad_top<false>(E[0], E[1], E[2], E[3], E[4], E[5], E[6], E[7], E[8], P::mod(0), P::mod(2), P::mod(4),
+                           P::mod(6), m, 0u, 0u);
+    else
+      chain_mad_top<true>(E[0], E[1], E[2], E[3], E[4], E[5], E[6], E[7], E[8], P::mod(0), P::mod(2), P::mod(4),
+                          P::mod(6), m, A[0][i - 1], A[1][i - 1]);
+    chain_mad(O[0], O[1], O[2], O[3], O[4], O[5], O[6], O[7], P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+  }
+  Fp<P> r;
+  add8_seed(r.v, &A[0][8], &A[1][8], A[0][7], A[1][7]);  // <= p
+  if (HIGH) add8(r.v, r.v, t + 8);                       // + floor(t / 2^256) < p: below 2p
+  reduce_once(r);
+  return r;
+}
+
+// Montgomery -> canonical residue: a / R mod p, the reduction alone (half the multiplies of a product by 1)
 template <class P>
 H2B_HD Fp<P> from_mont(const Fp<P>& a) {
-  Fp<P> o = Fp<P>::zero();
-  o.v[0] = 1;
-  return mul(a, o);
+  return mont_reduce<P, false>(a.v);
 }
 
 // a^e for a small public exponent (host finishers, table builders)
