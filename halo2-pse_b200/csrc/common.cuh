@@ -191,6 +191,20 @@ H2B_D Fp<P> ld_fp_nc(const Fp<P>* p) {
 #endif
   return r;
 }
+// the same with a 64-byte L2 fill: isolated 64-byte gathers (a table point) should not pull the other half of the line
+template <class P>
+H2B_D Fp<P> ld_fp_nc64(const Fp<P>* p) {
+  Fp<P> r;
+#ifdef __CUDA_ARCH__
+  asm volatile("ld.global.nc.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]),
+                 "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+#else
+  r = *p;
+#endif
+  return r;
+}
 template <class P>
 H2B_D void st_fp(Fp<P>* p, const Fp<P>& r) {
 #ifdef __CUDA_ARCH__

@@ -3,7 +3,7 @@
 // Replaces halo2curves 0.3.1 `bn256::G1Affine` / `bn256::G1` group operations
 // as used by /root/reference/halo2_proofs/src/arithmetic.rs:48,59-68,95-99.
 // Accumulators are kept in extended Jacobian ("XYZZ": x = X/ZZ, y = Y/ZZZ,
-// ZZ^3 = ZZZ^2) coordinates: mixed addition 8M+2S, full addition 12M+2S.
+// ZZ^3 = ZZZ^2) coordinates: mixed addition 8M+2S, full addition 12M+2S; the two products of y3 share one Montgomery reduction (mul_sub).
 // All exceptional cases (identity operands, P + P, P + (-P)) are handled, so
 // every routine is a complete group law on the curve.
 #pragma once
@@ -51,7 +51,7 @@ H2B_HD G1Xyzz xyzz_double_affine(const G1Affine& p) {
   Fq xx = sqr(p.x);
   Fq m = add(dbl(xx), xx);
   r.x = sub(sqr(m), dbl(s));
-  r.y = sub(mul(m, sub(s, r.x)), mul(w, p.y));
+  r.y = mul_sub(m, sub(s, r.x), w, p.y);
   r.zz = v;
   r.zzz = w;
   return r;
@@ -68,7 +68,7 @@ H2B_HD G1Xyzz xyzz_double(const G1Xyzz& p) {
   Fq xx = sqr(p.x);
   Fq m = add(dbl(xx), xx);
   r.x = sub(sqr(m), dbl(s));
-  r.y = sub(mul(m, sub(s, r.x)), mul(w, p.y));
+  r.y = mul_sub(m, sub(s, r.x), w, p.y);
   r.zz = mul(v, p.zz);
   r.zzz = mul(w, p.zzz);
   return r;
@@ -101,7 +101,7 @@ H2B_HD void xyzz_add_affine(G1Xyzz& acc, const G1Affine& p) {
   Fq ppp = mul(pp_, pp);
   Fq q = mul(acc.x, pp);
   Fq x3 = sub(sub(sqr(r), ppp), dbl(q));
-  Fq y3 = sub(mul(r, sub(q, x3)), mul(acc.y, ppp));
+  Fq y3 = mul_sub(r, sub(q, x3), acc.y, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = mul(acc.zz, pp);
@@ -134,7 +134,7 @@ H2B_HD void xyzz_add(G1Xyzz& acc, const G1Xyzz& b) {
   Fq ppp = mul(pp_, pp);
   Fq q = mul(u1, pp);
   Fq x3 = sub(sub(sqr(r), ppp), dbl(q));
-  Fq y3 = sub(mul(r, sub(q, x3)), mul(s1, ppp));
+  Fq y3 = mul_sub(r, sub(q, x3), s1, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = mul(mul(acc.zz, b.zz), pp);

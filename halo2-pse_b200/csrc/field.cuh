@@ -250,6 +250,143 @@ H2B_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   return mask;
 }
 
+
+// c[0 .. 2K-1] += {lo,hi}(x[0]*b), {lo,hi}(x[2]*b), ... (K products, operands two apart); c[2K] += carry.
+template <int K>
+H2B_HD void chain_mad_k(uint32_t* c, const uint32_t* x, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  if (K == 1) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2])
+        : "r"(x[0]), "r"(b));
+  }
+  else if (K == 2) {
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4])
+        : "r"(x[0]), "r"(x[2]), "r"(b));
+  }
+  else if (K == 3) {
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6])
+        : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(b));
+  }
+  else if (K == 4) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), "+r"(c[8])
+        : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(b));
+  }
+#else
+  uint64_t carry = 0;
+  for (int k = 0; k < K; ++k) {
+    uint64_t p = (uint64_t)x[2 * k] * b;
+    uint64_t s = (uint64_t)c[2 * k] + (uint32_t)p + carry;
+    c[2 * k] = (uint32_t)s;
+    carry = s >> 32;
+    s = (uint64_t)c[2 * k + 1] + (uint32_t)(p >> 32) + carry;
+    c[2 * k + 1] = (uint32_t)s;
+    carry = s >> 32;
+  }
+  c[2 * K] += (uint32_t)carry;
+#endif
+}
+
+// r = a + b over 16 limbs (caller guarantees no overflow past 2^512)
+H2B_HD void add16(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32 %0, %16, %32;\n\t"
+      "addc.cc.u32 %1, %17, %33;\n\t"
+      "addc.cc.u32 %2, %18, %34;\n\t"
+      "addc.cc.u32 %3, %19, %35;\n\t"
+      "addc.cc.u32 %4, %20, %36;\n\t"
+      "addc.cc.u32 %5, %21, %37;\n\t"
+      "addc.cc.u32 %6, %22, %38;\n\t"
+      "addc.cc.u32 %7, %23, %39;\n\t"
+      "addc.cc.u32 %8, %24, %40;\n\t"
+      "addc.cc.u32 %9, %25, %41;\n\t"
+      "addc.cc.u32 %10, %26, %42;\n\t"
+      "addc.cc.u32 %11, %27, %43;\n\t"
+      "addc.cc.u32 %12, %28, %44;\n\t"
+      "addc.cc.u32 %13, %29, %45;\n\t"
+      "addc.cc.u32 %14, %30, %46;\n\t"
+      "addc.u32 %15, %31, %47;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]), "r"(b[10]), "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
+#else
+  uint64_t carry = 0;
+  for (int i = 0; i < 16; ++i) {
+    uint64_t s = (uint64_t)a[i] + b[i] + carry;
+    r[i] = (uint32_t)s;
+    carry = s >> 32;
+  }
+#endif
+}
+
+// t[0..15] = 2 * s[0..15] + sum_i a[i]^2 * 2^(64 i)   (the result is known to fit: it is a square below 2^512)
+H2B_HD void sqr_finish16(uint32_t* t, const uint32_t* s, const uint32_t* a) {
+#ifdef __CUDA_ARCH__
+  uint32_t d[16];
+  d[0] = s[0] << 1;
+#pragma unroll
+  for (int k = 1; k < 16; ++k) d[k] = __funnelshift_l(s[k - 1], s[k], 1);
+  asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+      "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+      "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+      "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+      "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+      "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+      "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+      "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+      "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+      "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+      "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+      "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+      "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+      "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+      "madc.hi.u32 %15, %23, %23, %15;"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7]), "+r"(d[8]),
+        "+r"(d[9]), "+r"(d[10]), "+r"(d[11]), "+r"(d[12]), "+r"(d[13]), "+r"(d[14]), "+r"(d[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#pragma unroll
+  for (int k = 0; k < 16; ++k) t[k] = d[k];
+#else
+  uint64_t carry = 0;
+  uint32_t prev = 0;
+  for (int i = 0; i < 8; ++i) {
+    const uint64_t p = (uint64_t)a[i] * a[i];
+    const uint32_t d0 = (s[2 * i] << 1) | (prev >> 31), d1 = (s[2 * i + 1] << 1) | (s[2 * i] >> 31);
+    prev = s[2 * i + 1];
+    uint64_t x = (uint64_t)d0 + (uint32_t)p + carry;
+    t[2 * i] = (uint32_t)x;
+    carry = x >> 32;
+    x = (uint64_t)d1 + (uint32_t)(p >> 32) + carry;
+    t[2 * i + 1] = (uint32_t)x;
+    carry = x >> 32;
+  }
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // Field element
 // ---------------------------------------------------------------------------
@@ -383,10 +520,6 @@ H2B_HD Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
-template <class P>
-H2B_HD Fp<P> sqr(const Fp<P>& a) {
-  return mul(a, a);
-}
 
 template <class P>
 H2B_HD Fp<P> to_mont(const Fp<P>& a) {
@@ -436,6 +569,71 @@ H2B_HD Fp<P> mont_reduce(const uint32_t* t) {
   if (HIGH) add8(r.v, r.v, t + 8);                       // + floor(t / 2^256) < p: below 2p
   reduce_once(r);
   return r;
+}
+
+// Montgomery square a*a/R mod p: the 28 products a_i*a_j (i < j) once, doubled, plus the 8 squares a_i^2 (36 wide
+// multiplies instead of 64), then the Montgomery reduction alone (64 + 8): 108 wide multiplies against 136 of `mul`.
+// Rows i = 0..6 multiply a_i into a_(i+1..7); the products with i + j odd and those with i + j even go to separate
+// accumulators (so that consecutive products of a chain own consecutive column pairs), as in `mul`.
+template <class P>
+H2B_HD Fp<P> sqr(const Fp<P>& a) {
+#ifdef H2B_SQR_IS_MUL
+  return mul(a, a);
+#else
+  uint32_t A[2][17];
+#pragma unroll
+  for (int c = 0; c < 17; ++c) A[0][c] = A[1][c] = 0;
+  // odd accumulator: j = i + 1, i + 3, ... at columns 2i + 1 ...;  even accumulator: j = i + 2, i + 4, ... at 2i + 2 ...
+  chain_mad_k<4>(&A[1][1], &a.v[1], a.v[0]);
+  chain_mad_k<3>(&A[0][2], &a.v[2], a.v[0]);
+  chain_mad_k<3>(&A[1][3], &a.v[2], a.v[1]);
+  chain_mad_k<3>(&A[0][4], &a.v[3], a.v[1]);
+  chain_mad_k<3>(&A[1][5], &a.v[3], a.v[2]);
+  chain_mad_k<2>(&A[0][6], &a.v[4], a.v[2]);
+  chain_mad_k<2>(&A[1][7], &a.v[4], a.v[3]);
+  chain_mad_k<2>(&A[0][8], &a.v[5], a.v[3]);
+  chain_mad_k<2>(&A[1][9], &a.v[5], a.v[4]);
+  chain_mad_k<1>(&A[0][10], &a.v[6], a.v[4]);
+  chain_mad_k<1>(&A[1][11], &a.v[6], a.v[5]);
+  chain_mad_k<1>(&A[0][12], &a.v[7], a.v[5]);
+  chain_mad_k<1>(&A[1][13], &a.v[7], a.v[6]);
+  uint32_t s16[16], t[16];
+  add16(s16, &A[0][0], &A[1][0]);  // the off-diagonal sum: below 2^511
+  sqr_finish16(t, s16, a.v);
+  return mont_reduce<P, true>(t);
+#endif
+}
+
+// t[0..15] = a * b as integers (64 wide multiplies), on the two column accumulators of `mul`: row i sends its even-j
+// products to accumulator i & 1 at columns i .., its odd-j products to the other at columns i + 1 ...  Rows go in
+// ascending order, so the column that takes a chain's carry-out is still empty or holds an earlier carry (0 or 1).
+template <class P>
+H2B_HD void mul_wide16(uint32_t* t, const Fp<P>& a, const Fp<P>& b) {
+  uint32_t A[2][18];
+#pragma unroll
+  for (int c = 0; c < 18; ++c) A[0][c] = A[1][c] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    chain_mad_k<4>(&A[i & 1][i], &a.v[0], b.v[i]);
+    chain_mad_k<4>(&A[(i & 1) ^ 1][i + 1], &a.v[1], b.v[i]);
+  }
+  add16(t, &A[0][0], &A[1][0]);
+}
+
+// a*b - c*d (Montgomery form): both products share ONE reduction (2 * 64 + 64 + 8 wide multiplies instead of
+// 2 * 136).  a*b + (p - c)*d < 2 p^2 < p * 2^256, the precondition of mont_reduce.
+template <class P>
+H2B_HD Fp<P> mul_sub(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+  Fp<P> nc;
+  uint32_t m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = P::mod(i);
+  sub8(nc.v, m, c.v);  // p - c in (0, p]: p itself stands for 0, the bound above still holds
+  uint32_t t[16], u[16];
+  mul_wide16(t, a, b);
+  mul_wide16(u, nc, d);
+  add16(t, t, u);
+  return mont_reduce<P, true>(t);
 }
 
 // Montgomery -> canonical residue: a / R mod p, the reduction alone (half the multiplies of a product by 1)

@@ -54,6 +54,8 @@ struct MsmWorkspace {
   size_t cap_buckets2 = 0;
   G1Xyzz* seg[2] = {nullptr, nullptr};  // tree-sum ping-pong
   G1Xyzz* h_out = nullptr;              // pinned, W window sums
+  G1Xyzz* rc = nullptr;                 // two-dimensional bucket reduction: partial sums, V, shifted bit sums
+  size_t cap_rc = 0;
   // batched-affine accumulation (window-table MSMs)
   size_t cap_aff = 0, cap_slots = 0;
   uint32_t* akeys[2] = {nullptr, nullptr};
@@ -79,6 +81,7 @@ static void ws_release(MsmWorkspace* ws) {
     cudaFree(ws->seg[i]);
   }
   cudaFree(ws->buckets);
+  if (ws->rc) cudaFree(ws->rc);
   if (ws->buckets2) cudaFree(ws->buckets2);
   ws->buckets2 = nullptr;
   ws->cap_buckets2 = 0;
@@ -199,8 +202,8 @@ struct Level0Src {
     const uint32_t v = vals[i];
     const G1Affine* src = bases + (v & 0x7fffffffu);
     G1Affine p;
-    p.x = ld_fp_nc(&src->x);
-    p.y = ld_fp_nc(&src->y);
+    p.x = ld_fp_nc64(&src->x);
+    p.y = ld_fp_nc64(&src->y);
     if (v >> 31) p.y = neg(p.y);
     xyzz_add_affine(acc, p);
   }
@@ -559,6 +562,120 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------
+// 4b. two-dimensional bucket reduction (bucket sets of 2^m >= 4096 buckets)
+//
+// sum_b (b + 1) B[b] with b = hi * T + lo (T = 2^h columns, R = 2^(m - h) rows) is
+//   sum_lo (lo + 1) C[lo]  +  T * sum_hi hi * Rw[hi],   C = column sums, Rw = row sums:
+// two PLAIN sums per bucket, every one of them independent of the others (the running sums of arithmetic.rs:95-99
+// are a serial chain per segment, and a segment pays a double-and-add for its offset: as many group operations
+// again as the chain itself at the segment lengths that keep the GPU busy).  The two weighted sums that are left
+// have T entries each: per weight bit a subset sum (tree), shifted by doublings, then one sum of the shifted points.
+// ---------------------------------------------------------------------------
+static const uint32_t kRcJ = 16;  // buckets per thread in the first pass
+
+// pass A: thread t < nb/J sums J rows of one column, thread nb/J <= t < 2 nb/J sums J columns of one row
+__global__ void __launch_bounds__(128)
+    msm_bucket_rc_kernel(const G1Xyzz* buckets, uint32_t m, uint32_t h, uint32_t nsets, G1Xyzz* part) {
+  const uint32_t per_set = 2u << (m - 4);
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsets * per_set) return;
+  const uint32_t w = t / per_set, tl = t % per_set, half = per_set / 2, T = 1u << h;
+  const G1Xyzz* B = buckets + ((uint64_t)w << m);
+  const G1Xyzz* src;
+  uint32_t stride;
+  if (tl < half) {  // rows [rp * J, +J) of column lo
+    const uint32_t lo = tl & (T - 1), rp = tl >> h;
+    src = B + (((uint64_t)rp * kRcJ) << h) + lo;
+    stride = T;
+  } else {  // columns [q * J, +J) of row hi
+    src = B + (uint64_t)(tl - half) * kRcJ;
+    stride = 1;
+  }
+  G1Xyzz acc = ld_xyzz(src);
+  G1Xyzz nxt = ld_xyzz(src + stride);
+  for (uint32_t j = 2; j <= kRcJ; ++j) {  // the load of element j is in flight while element j - 1 is added
+    const G1Xyzz b = nxt;
+    if (j < kRcJ) nxt = ld_xyzz(src + (uint64_t)j * stride);
+    xyzz_add(acc, b);
+  }
+  st_xyzz(part + (uint64_t)w * per_set + tl, acc);
+}
+
+// pass B: a block sums 256 consecutive partials = 256 / len whole groups (a group = the len = R/J partials of a column
+// or the T/J partials of a row; len is a power of two <= 256) by halving in shared memory: every level keeps whole
+// warps busy until fewer than 32 additions are left (a warp per group would issue 5 levels with idle lanes per group).
+// V[w][lo] = C[lo];  V[w][T + hi - 1] = Rw[hi] for hi >= 1 (weight hi = index + 1 as in the column half);
+// the rest of the row half stays at the identity (cleared by the caller).
+// Column partials are stored [row group][lo]: the group of column lo is strided by T, hence the gather below.
+__global__ void __launch_bounds__(128)
+    msm_rc_group_kernel(const G1Xyzz* part, uint32_t m, uint32_t h, uint32_t nsets, G1Xyzz* V) {
+  __shared__ G1Xyzz sm[256];
+  const uint32_t T = 1u << h, R = 1u << (m - h), half = 1u << (m - 4), per_set = 2 * half;
+  const uint32_t blocks_per_half = half / 256, tid = threadIdx.x;
+  const uint32_t w = blockIdx.x / (2 * blocks_per_half), bl = blockIdx.x % (2 * blocks_per_half);
+  const bool rows = bl >= blocks_per_half;
+  const uint32_t e0 = (rows ? bl - blocks_per_half : bl) * 256;  // first entry of this block, in group-major order
+  const uint32_t len = rows ? T / kRcJ : R / kRcJ;
+  const G1Xyzz* P = part + (uint64_t)w * per_set + (rows ? half : 0);
+  for (uint32_t i = tid; i < 256; i += 128) {
+    const uint32_t e = e0 + i;  // entry e = group e / len, member e % len
+    sm[i] = rows ? ld_xyzz(P + e) : ld_xyzz(P + (((uint64_t)(e % len)) << h) + e / len);
+  }
+  __syncthreads();
+  const uint32_t groups = 256 / len;
+  for (uint32_t cur = len; cur > 1; cur >>= 1) {
+    const uint32_t hl = cur / 2;  // group g keeps its live members at sm[g * len + 0 .. cur)
+    for (uint32_t i = tid; i < groups * hl; i += 128) {
+      const uint32_t g = i / hl, j = i % hl;
+      G1Xyzz a = sm[g * len + j];
+      xyzz_add(a, sm[g * len + j + hl]);
+      sm[g * len + j] = a;
+    }
+    __syncthreads();
+  }
+  if (tid < groups) {
+    const uint32_t g = e0 / len + tid;  // column lo or row hi
+    G1Xyzz* out = V + (uint64_t)w * 2 * T;
+    if (!rows)
+      st_xyzz(out + g, sm[tid * len]);
+    else if (g >= 1)
+      st_xyzz(out + T + g - 1, sm[tid * len]);
+  }
+}
+
+// pass C: block (bit, set * 2 + half, split) sums the entries of its slice whose weight (index + 1) has `bit` set,
+// then shifts the sum by `bit` doublings (+ h for the row half: the factor T).
+__global__ void __launch_bounds__(128)
+    msm_rc_bits_kernel(const G1Xyzz* V, uint32_t h, uint32_t nsplit, G1Xyzz* out) {
+  __shared__ G1Xyzz sm[128];
+  const uint32_t T = 1u << h, bit = blockIdx.x, sa = blockIdx.y, sp = blockIdx.z, tid = threadIdx.x;
+  const uint32_t slice = T / nsplit;
+  const G1Xyzz* A = V + (uint64_t)sa * T;
+  G1Xyzz acc = G1Xyzz::identity();
+  for (uint32_t i = sp * slice + tid; i < (sp + 1) * slice; i += 128)
+    if (((i + 1) >> bit) & 1) {
+      const G1Xyzz b = ld_xyzz(A + i);
+      xyzz_add(acc, b);
+    }
+  sm[tid] = acc;
+  __syncthreads();
+  for (uint32_t s = 64; s > 0; s >>= 1) {
+    if (tid < s) {
+      G1Xyzz a = sm[tid];
+      xyzz_add(a, sm[tid + s]);
+      sm[tid] = a;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    G1Xyzz r = sm[0];
+    const uint32_t nd = bit + ((sa & 1) ? h : 0);
+    for (uint32_t i = 0; i < nd; ++i) r = xyzz_double(r);
+    st_xyzz(out + ((uint64_t)sa * gridDim.x + bit) * nsplit + sp, r);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
 static uint32_t ceil_log2(uint64_t x) {
@@ -813,17 +930,46 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   // Batch b + 1 travels over PCIe (copy stream) while batch b is sorted and accumulated; batches after the
   // first fill a second bucket array that one element-wise kernel folds into the first.  One bucket
   // reduction at the end.  Everything else is one batch.
-  // (B200, PCIe 5: k = 24 49.2 -> 45.9 ms with 4 batches; neutral at k = 23, a loss below: smaller sorts)
+  // (B200, PCIe 5: k = 24 49.2 ms in one batch, 45.9 with 4 equal batches, 42.6 with 3 growing ones; a loss below k = 23)
   uint64_t batch_min = 1ull << 22;  // points per batch; H2B_MSM_BATCH_MIN overrides (tests), 0 disables
   if (const char* e = getenv("H2B_MSM_BATCH_MIN")) batch_min = strtoull(e, nullptr, 10);
-  const int NB = (h_scalars && table_stride && batch_min && ncols == 1) ? (n >= 4 * batch_min ? 4 : n >= 2 * batch_min ? 2 : 1) : 1;
-  const uint64_t per_batch = (n + NB - 1) / NB;
+  // Batch sizes grow geometrically: only the copy of batch 0 is exposed, and the copy of batch b + 1 hides under the
+  // compute of batch b as long as it is not more than compute/copy (~ 3-4 on PCIe 5) times larger.
+  // H2B_MSM_BATCH_PLAN = "w0,w1,..." overrides the relative weights (at most 7 batches).
+  uint64_t bstart[9] = {0};
+  int NB = 1;
+  if (h_scalars && table_stride && batch_min && ncols == 1 && n >= 2 * batch_min) {
+    uint32_t wts[8] = {1, 4, 16, 0, 0, 0, 0, 0};  // B200 + PCIe 5, k = 24: 1,1,1,1 45.5 ms; 1,3,9 43.2; 1,4,16 42.6; 1,5,20 42.6
+    int nw = n >= 4 * batch_min ? 3 : 2;
+    if (const char* e = getenv("H2B_MSM_BATCH_PLAN")) {
+      nw = 0;
+      for (const char* q = e; *q && nw < 7;) {
+        char* end = nullptr;
+        const unsigned long v = strtoul(q, &end, 10);
+        if (end == q) break;
+        if (v) wts[nw++] = (uint32_t)v;
+        q = *end ? end + 1 : end;
+      }
+      if (nw == 0) { wts[0] = 1; nw = 1; }
+    }
+    uint64_t tot = 0, run = 0, prev = 0;
+    for (int i = 0; i < nw; ++i) tot += wts[i];
+    NB = 0;
+    for (int i = 0; i < nw; ++i) {
+      run += wts[i];
+      const uint64_t e1 = i + 1 == nw ? (uint64_t)n : ((n * run / tot) & ~(uint64_t)(n >= 65536 ? 255 : 0));
+      if (e1 > prev) bstart[++NB] = prev = e1;
+    }
+  } else {
+    bstart[1] = n;
+  }
   H2B_CUDA(ctx, cudaMemsetAsync(ws->buckets, 0, (size_t)p.Wb * p.nb_per_window * sizeof(G1Xyzz), st));
   // copy of batch b on the copy stream, event copy_ev[b]; queued right after the compute of batch b - 1, so
   // that a pageable source (staged by host threads, which blocks this thread) overlaps that compute as well
   auto queue_copy = [&](int b) -> int {
-    const uint64_t i0 = (uint64_t)b * per_batch, i1 = std::min<uint64_t>(n, i0 + per_batch);
-    if (b >= NB || i0 >= i1) return H2B_OK;
+    if (b >= NB) return H2B_OK;
+    const uint64_t i0 = bstart[b], i1 = bstart[b + 1];
+    if (i0 >= i1) return H2B_OK;
     H2B_TRY(copy_h2d_any(ctx, const_cast<Fr*>(d_scalars) + i0, h_scalars + i0, (i1 - i0) * sizeof(Fr), ctx->copy_stream));
     H2B_CUDA(ctx, cudaEventRecord(ctx->copy_ev[b], ctx->copy_stream));
     return H2B_OK;
@@ -835,8 +981,8 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
     H2B_TRY(queue_copy(0));
   }
   for (int batch = 0; batch < NB; ++batch) {
-  const uint64_t b0 = (uint64_t)batch * per_batch, b1 = std::min<uint64_t>(n, b0 + per_batch);
-  if (b0 >= b1) break;
+  const uint64_t b0 = bstart[batch], b1 = bstart[batch + 1];
+  if (b0 >= b1) continue;
   const uint64_t nbatch = b1 - b0;
   const uint64_t pairs = NB > 1 ? nbatch * p.W : p.pairs;
   // later batches fill a second bucket array, folded into the first by one element-wise kernel
@@ -963,8 +1109,38 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   if (NB > 1) H2B_TRY(queue_copy(batch + 1));
   }  // batches
 
-  // 4. bucket reduction
-  {
+  // 4. bucket reduction: two-dimensional for bucket sets of >= 2^12 buckets (H2B_MSM_RC=0: the segmented running
+  //    sums everywhere), else segmented running sums
+  const bool rc_enabled = !(getenv("H2B_MSM_RC") && atoi(getenv("H2B_MSM_RC")) == 0);
+  if (rc_enabled && p.c - 1 >= 12) {
+    const uint32_t m = p.c - 1, h = (m + 1) / 2, T = 1u << h, R = 1u << (m - h);
+    const uint32_t nbits = h + 1, nsplit = T >= 1024 ? 8 : T / 128 ? T / 128 : 1;  // 2 * nbits * nsplit <= 256
+    const size_t n_part = (size_t)p.Wb * (p.nb_per_window / 8), n_v = (size_t)p.Wb * 2 * T,
+                 n_bits = (size_t)p.Wb * 2 * nbits * nsplit;
+    if (ws->cap_rc < n_part + n_v + n_bits) {
+      H2B_CUDA(ctx, cudaStreamSynchronize(st));
+      if (ws->rc) cudaFree(ws->rc);
+      ws->rc = nullptr;
+      ws->cap_rc = 0;
+      H2B_CUDA(ctx, dev_malloc(ctx, (void**)&ws->rc, (n_part + n_v + n_bits) * sizeof(G1Xyzz)));
+      ws->cap_rc = n_part + n_v + n_bits;
+    }
+    G1Xyzz* part = ws->rc;
+    G1Xyzz* V = part + n_part;
+    G1Xyzz* bits = V + n_v;
+    H2B_CUDA(ctx, cudaMemsetAsync(V, 0, n_v * sizeof(G1Xyzz), st));
+    const uint32_t ta = p.Wb * (p.nb_per_window / 8);
+    H2B_TRY(launch(ctx, msm_bucket_rc_kernel, dim3((ta + 127) / 128), dim3(128), 0, (const G1Xyzz*)ws->buckets, m, h,
+                   p.Wb, part));
+    H2B_TRY(launch(ctx, msm_rc_group_kernel, dim3(p.Wb * (p.nb_per_window / 8 / 256)), dim3(128), 0,
+                   (const G1Xyzz*)part, m, h, p.Wb, V));
+    H2B_TRY(launch(ctx, msm_rc_bits_kernel, dim3(nbits, 2 * p.Wb, nsplit), dim3(128), 0, (const G1Xyzz*)V, h, nsplit,
+                   bits));
+    const uint32_t np = 2 * nbits * nsplit;  // <= 2 * 13 * 8 shifted points per set
+    H2B_TRY(launch(ctx, msm_tree_sum_kernel, dim3(1, p.Wb), dim3(256), 256 * sizeof(G1Xyzz), (const G1Xyzz*)bits, np,
+                   1u, ws->seg[0]));
+    H2B_CUDA(ctx, cudaMemcpyAsync(ws->h_out, ws->seg[0], p.Wb * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, st));
+  } else {
     const uint32_t total = p.Wb * p.nseg;
     H2B_TRY(launch(ctx, msm_bucket_seg_kernel, dim3((total + 127) / 128), dim3(128), 0,
                    (const G1Xyzz*)ws->buckets, p.nb_per_window, p.lM, p.nseg, total, ws->seg[0]));

@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256) k_mul(uint32_t* sink, int iters, uint32_t
   for (int j = 0; j < 8; ++j) b.v[j] = F::r2().v[j] ^ (blockIdx.x + seed) & 0x0fffffff;
   for (int i = 0; i < iters; ++i)
 #pragma unroll
-    for (int c = 0; c < CH; ++c) a[c] = V == 0 ? mul(a[c], b) : V == 1 ? mul_dfma(a[c], b) : V == 2 ? sqr_dfma(a[c]) : mul_dfma(a[c], a[(c + 1) % CH]);
+    for (int c = 0; c < CH; ++c) a[c] = V == 0 ? mul(a[c], b) : V == 1 ? mul_dfma(a[c], b) : V == 2 ? sqr_dfma(a[c]) : V == 4 ? sqr(a[c]) : mul_dfma(a[c], a[(c + 1) % CH]);
   uint32_t s = 0;
   for (int c = 0; c < CH; ++c) for (int j = 0; j < 8; ++j) s ^= a[c].v[j];
   if (s == 0x12345678u) sink[0] = s;
@@ -27,9 +27,9 @@ __global__ void k_check(const uint32_t* a, const uint32_t* b, uint32_t* bad, int
   F x, y;
   for (int j = 0; j < 8; ++j) { x.v[j] = a[i * 8 + j]; y.v[j] = b[i * 8 + j]; }
   for (int k = 0; k < 4; ++k) { reduce_once(x); reduce_once(y); }
-  F r0 = mul(x, y), r1 = mul_dfma(x, y), s0 = mul(x, x), s1 = sqr_dfma(x);
+  F r0 = mul(x, y), r1 = mul_dfma(x, y), s0 = mul(x, x), s1 = sqr_dfma(x), s2 = sqr(x);
   uint32_t d = 0;
-  for (int j = 0; j < 8; ++j) d += (r0.v[j] != r1.v[j]) + (s0.v[j] != s1.v[j]);
+  for (int j = 0; j < 8; ++j) d += (r0.v[j] != r1.v[j]) + (s0.v[j] != s1.v[j]) + (s0.v[j] != s2.v[j]);
   if (d) atomicAdd(bad, 1u);
 }
 
@@ -71,7 +71,7 @@ static int check(const char* name) {
   k_check<F><<<(n + 127) / 128, 128>>>(da, db, dbad, n);
   uint32_t bad = 1;
   cudaMemcpy(&bad, dbad, 4, cudaMemcpyDeviceToHost);
-  printf("%s: mul_dfma / sqr_dfma vs mul on %d operand pairs: %u mismatches\n", name, n, bad);
+  printf("%s: mul_dfma / sqr_dfma / sqr vs mul on %d operand pairs: %u mismatches\n", name, n, bad);
   return bad != 0;
 }
 
@@ -92,6 +92,8 @@ int main() {
     printf("  dfma mul (both unpacked)    CH=4: %.2f G mulmod/s\n", run(k_mul<Fq, 4, 3>, blocks, 512, 4, sink) / 1e9);
     printf("  dfma sqr                    CH=1: %.2f G mulmod/s\n", run(k_mul<Fq, 1, 2>, blocks, 2048, 1, sink) / 1e9);
     printf("  dfma sqr                    CH=2: %.2f G mulmod/s\n", run(k_mul<Fq, 2, 2>, blocks, 1024, 2, sink) / 1e9);
+    printf("  integer sqr (36 + 72 wide)  CH=1: %.2f G mulmod/s\n", run(k_mul<Fq, 1, 4>, blocks, 2048, 1, sink) / 1e9);
+    printf("  integer sqr (36 + 72 wide)  CH=2: %.2f G mulmod/s\n", run(k_mul<Fq, 2, 4>, blocks, 1024, 2, sink) / 1e9);
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(e));

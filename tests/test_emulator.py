@@ -147,7 +147,7 @@ def test_msm_vs_oracle(emu_ctx, oracle_c, n, kind, monkeypatch):
     if n > 10:  # prefix / offset forms used by commit on shorter polynomials
         assert B.msm(S[:10], offset=3) == H.g1_dec(oracle_c.best_multiexp(S[:10], bases[3:13], 1))[0]
     if n >= 1024:  # window table: all windows share one bucket set
-        for c in (0, 5, 11):
+        for c in (0, 5, 13):  # 13: two-dimensional bucket reduction (>= 2^12 buckets)
             B.precompute(c)
             auto = min(range(8, 25), key=lambda cc: (n * ((255 + cc - 1) // cc) + 2.8 * (1 << (cc - 1)), cc))
             assert B.table_window_bits == (c or auto)
