@@ -556,17 +556,20 @@ def run_ours(args):
     # multiply issues every 4 cycles per SM sub-partition -- 32 lanes/clk/SM = 9.3 T/s at 1965 MHz, with or
     # without an addend or a carry; only the 32-bit IMAD runs at 64 lanes/clk/SM (scripts/mulbench/pipes.cu).
     mult_peak = pipe["imad_wide"][0]
-    executed = adds * 10 * 130  # what the kernel issues: 8M + 2S per mixed XYZZ addition, 130 IMAD.WIDE per product
+    # what the kernel issues per mixed XYZZ addition (8M + 2S): 6 products x 128, 2 dedicated squarings x 100, and the two
+    # products of y3 on ONE shared Montgomery reduction (64 + 64 + 64) = 1160 IMAD.WIDE (round 1 / early round 2: 10 x 130)
+    executed = adds * 1160
     roofline = {
         "kernel": "msm_accum0_kernel (bucket accumulation, level 0)", "bound": "int32-multiply (IMAD.WIDE pipe)",
         "achieved": mults / (acc_ms * 1e-3) / 1e12, "peak": mult_peak / 1e12, "unit": "Tmul/s",
         "frac": mults / (acc_ms * 1e-3) / mult_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at k=24, c=22 from the committed
-        # ncu --set full capture profiles/r2_msm_accum0_ntt_passes_k24_ncu_full.txt (28.65 GB + 0.52 GB)
-        "traffic": 29.17e9 if (k == 24 and c_win == 22) else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at k=24, c=22 (ncu, profiles/r2b_accum0_dram_k24.csv:
+        # 15.91 GB + 0.52 GB with 64-byte L2 fills for the table gathers; 28.65 + 0.52 GB before)
+        "traffic": 16.43e9 if (k == 24 and c_win == 22) else None,
         "frac_executed": executed / (acc_ms * 1e-3) / mult_peak,
-        "executed": "n*W*10*130 IMAD.WIDE actually issued (XYZZ mixed addition 8M+2S; 128 + 2 wide multiplies per "
-                    "Montgomery product); `frac` uses the survey's algorithmic 11*136 as the contract asks",
+        "executed": "n*W*1160 IMAD.WIDE actually issued per XYZZ mixed addition (6 products x 128, 2 squarings x 100, "
+                    "y3's two products on one shared reduction: 192); `frac` uses the survey's algorithmic 11*136 as "
+                    "the contract asks, so it can exceed 1",
         "mulmod_ceiling_frac": (adds * 10 / (acc_ms * 1e-3)) / (pipe["fr_mul"][1] or 1.0),
         "peak_source": "live register-only microbenchmark h2b_pipe_peak: IMAD.WIDE.U32 (32x32->64) with operands "
                        "that change every iteration, 32 lanes/clk/SM; round 1's 18.5 T/s was a 64-bit-add loop",
