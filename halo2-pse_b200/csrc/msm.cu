@@ -185,6 +185,45 @@ __global__ void msm_count_kernel(const uint32_t* keys, const uint32_t* n_cur, ui
   cnt[t] = (kf == kl) ? (head | tail) : head + tail;
 }
 
+// the same counts and their inclusive scan in ONE launch, for chunk lists short enough for one block (the levels after
+// the first: three launches -- count, scan-state init, scan -- become one)
+static const uint32_t kFusedScanMax = 32768;
+__global__ void __launch_bounds__(1024)
+    msm_count_scan_kernel(const uint32_t* keys, const uint32_t* n_cur, uint32_t L, uint32_t nchunks, uint32_t* cnt,
+                          uint32_t* incl) {
+  __shared__ uint32_t part[1024];
+  const uint32_t tid = threadIdx.x, per = (nchunks + 1023) / 1024;
+  const uint32_t N = *n_cur;
+  const uint32_t t0 = tid * per, t1 = t0 + per < nchunks ? t0 + per : nchunks;
+  uint32_t sum = 0;
+  for (uint32_t t = t0; t < t1; ++t) {
+    const uint64_t start = (uint64_t)t * L;
+    uint32_t c = 0;
+    if (start < N) {
+      const uint64_t end = start + L < N ? start + L : N;
+      const uint32_t kf = keys[start], kl = keys[end - 1];
+      const uint32_t head = start > 0 && keys[start - 1] == kf;
+      const uint32_t tail = end < N && keys[end] == kl;
+      c = (kf == kl) ? (head | tail) : head + tail;
+    }
+    cnt[t] = c;
+    sum += c;
+  }
+  part[tid] = sum;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {  // Hillis-Steele over the 1024 thread totals
+    const uint32_t v = tid >= d ? part[tid - d] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[tid] - sum;
+  for (uint32_t t = t0; t < t1; ++t) {
+    run += cnt[t];
+    incl[t] = run;
+  }
+}
+
 #ifdef H2B_EMU
 static void emu_inclusive_scan(const uint32_t* in, uint32_t* out, size_t n) {
   uint32_t s = 0;
@@ -593,12 +632,12 @@ __global__ void __launch_bounds__(256)
 // again as the chain itself at the segment lengths that keep the GPU busy).  The two weighted sums that are left
 // have T entries each: per weight bit a subset sum (tree), shifted by doublings, then one sum of the shifted points.
 // ---------------------------------------------------------------------------
-static const uint32_t kRcJ = 16;  // buckets per thread in the first pass
 
 // pass A: thread t < nb/J sums J rows of one column, thread nb/J <= t < 2 nb/J sums J columns of one row
+// (J = 2^lj buckets per thread: 16 for large bucket sets, 4 for small ones, where the serial chain is what costs)
 __global__ void __launch_bounds__(128)
-    msm_bucket_rc_kernel(const G1Xyzz* buckets, uint32_t m, uint32_t h, uint32_t nsets, G1Xyzz* part) {
-  const uint32_t per_set = 2u << (m - 4);
+    msm_bucket_rc_kernel(const G1Xyzz* buckets, uint32_t m, uint32_t h, uint32_t lj, uint32_t nsets, G1Xyzz* part) {
+  const uint32_t per_set = 2u << (m - lj), J = 1u << lj;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nsets * per_set) return;
   const uint32_t w = t / per_set, tl = t % per_set, half = per_set / 2, T = 1u << h;
@@ -607,17 +646,17 @@ __global__ void __launch_bounds__(128)
   uint32_t stride;
   if (tl < half) {  // rows [rp * J, +J) of column lo
     const uint32_t lo = tl & (T - 1), rp = tl >> h;
-    src = B + (((uint64_t)rp * kRcJ) << h) + lo;
+    src = B + (((uint64_t)rp << lj) << h) + lo;
     stride = T;
   } else {  // columns [q * J, +J) of row hi
-    src = B + (uint64_t)(tl - half) * kRcJ;
+    src = B + ((uint64_t)(tl - half) << lj);
     stride = 1;
   }
   G1Xyzz acc = ld_xyzz(src);
   G1Xyzz nxt = ld_xyzz(src + stride);
-  for (uint32_t j = 2; j <= kRcJ; ++j) {  // the load of element j is in flight while element j - 1 is added
+  for (uint32_t j = 2; j <= J; ++j) {  // the load of element j is in flight while element j - 1 is added
     const G1Xyzz b = nxt;
-    if (j < kRcJ) nxt = ld_xyzz(src + (uint64_t)j * stride);
+    if (j < J) nxt = ld_xyzz(src + (uint64_t)j * stride);
     xyzz_add(acc, b);
   }
   st_xyzz(part + (uint64_t)w * per_set + tl, acc);
@@ -630,14 +669,14 @@ __global__ void __launch_bounds__(128)
 // the rest of the row half stays at the identity (cleared by the caller).
 // Column partials are stored [row group][lo]: the group of column lo is strided by T, hence the gather below.
 __global__ void __launch_bounds__(128)
-    msm_rc_group_kernel(const G1Xyzz* part, uint32_t m, uint32_t h, uint32_t nsets, G1Xyzz* V) {
+    msm_rc_group_kernel(const G1Xyzz* part, uint32_t m, uint32_t h, uint32_t lj, uint32_t nsets, G1Xyzz* V) {
   __shared__ G1Xyzz sm[256];
-  const uint32_t T = 1u << h, R = 1u << (m - h), half = 1u << (m - 4), per_set = 2 * half;
+  const uint32_t T = 1u << h, R = 1u << (m - h), half = 1u << (m - lj), per_set = 2 * half;
   const uint32_t blocks_per_half = half / 256, tid = threadIdx.x;
   const uint32_t w = blockIdx.x / (2 * blocks_per_half), bl = blockIdx.x % (2 * blocks_per_half);
   const bool rows = bl >= blocks_per_half;
   const uint32_t e0 = (rows ? bl - blocks_per_half : bl) * 256;  // first entry of this block, in group-major order
-  const uint32_t len = rows ? T / kRcJ : R / kRcJ;
+  const uint32_t len = rows ? T >> lj : R >> lj;
   const G1Xyzz* P = part + (uint64_t)w * per_set + (rows ? half : 0);
   for (uint32_t i = tid; i < 256; i += 128) {
     const uint32_t e = e0 + i;  // entry e = group e / len, member e % len
@@ -1089,15 +1128,20 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
       const uint32_t L = level == 0 ? p.L0 : p.LN;
       const uint32_t nchunks = (uint32_t)((nmax + L - 1) / L);
       const int o = level & 1;
-      H2B_TRY(launch(ctx, msm_count_kernel, dim3((nchunks + 255) / 256), dim3(256), 0, keys,
-                     (const uint32_t*)(ws->n_level + level), L, nchunks, ws->cnt));
+      if (nchunks <= kFusedScanMax) {
+        H2B_TRY(launch(ctx, msm_count_scan_kernel, dim3(1), dim3(1024), 0, keys,
+                       (const uint32_t*)(ws->n_level + level), L, nchunks, ws->cnt, ws->incl));
+      } else {
+        H2B_TRY(launch(ctx, msm_count_kernel, dim3((nchunks + 255) / 256), dim3(256), 0, keys,
+                       (const uint32_t*)(ws->n_level + level), L, nchunks, ws->cnt));
 #ifdef H2B_EMU
-      emu_inclusive_scan(ws->cnt, ws->incl, nchunks);
+        emu_inclusive_scan(ws->cnt, ws->incl, nchunks);
 #else
-      H2B_CUDA(ctx, cub::DeviceScan::InclusiveSum(ws->cub_temp, ws->cub_temp_bytes, ws->cnt,
-                                                  ws->incl, (int)nchunks, st));
-      ctx->launches += 1;
+        H2B_CUDA(ctx, cub::DeviceScan::InclusiveSum(ws->cub_temp, ws->cub_temp_bytes, ws->cnt,
+                                                    ws->incl, (int)nchunks, st));
+        ctx->launches += 2;  // scan-state init + scan
 #endif
+      }
       if (level == 0) {
         Level0Src src{ws->vals_out, d_bases};
         // the throughput-bound kernel goes to the low-priority stream (common.cuh: bulk_stream)
@@ -1137,7 +1181,8 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   if (rc_enabled && p.c - 1 >= 12) {
     const uint32_t m = p.c - 1, h = (m + 1) / 2, T = 1u << h, R = 1u << (m - h);
     const uint32_t nbits = h + 1, nsplit = T >= 1024 ? 8 : T / 128 ? T / 128 : 1;  // 2 * nbits * nsplit <= 256
-    const size_t n_part = (size_t)p.Wb * (p.nb_per_window / 8), n_v = (size_t)p.Wb * 2 * T,
+    const uint32_t lj = m >= 18 ? 4 : m == 17 ? 3 : 2;  // buckets per thread of the first pass: 16 / 8 / 4
+    const size_t n_part = (size_t)p.Wb * ((size_t)2 << (m - lj)), n_v = (size_t)p.Wb * 2 * T,
                  n_bits = (size_t)p.Wb * 2 * nbits * nsplit;
     if (ws->cap_rc < n_part + n_v + n_bits) {
       H2B_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1151,11 +1196,10 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
     G1Xyzz* V = part + n_part;
     G1Xyzz* bits = V + n_v;
     H2B_CUDA(ctx, cudaMemsetAsync(V, 0, n_v * sizeof(G1Xyzz), st));
-    const uint32_t ta = p.Wb * (p.nb_per_window / 8);
+    const uint32_t ta = p.Wb * (2u << (m - lj));
     H2B_TRY(launch(ctx, msm_bucket_rc_kernel, dim3((ta + 127) / 128), dim3(128), 0, (const G1Xyzz*)ws->buckets, m, h,
-                   p.Wb, part));
-    H2B_TRY(launch(ctx, msm_rc_group_kernel, dim3(p.Wb * (p.nb_per_window / 8 / 256)), dim3(128), 0,
-                   (const G1Xyzz*)part, m, h, p.Wb, V));
+                   lj, p.Wb, part));
+    H2B_TRY(launch(ctx, msm_rc_group_kernel, dim3(ta / 256), dim3(128), 0, (const G1Xyzz*)part, m, h, lj, p.Wb, V));
     H2B_TRY(launch(ctx, msm_rc_bits_kernel, dim3(nbits, 2 * p.Wb, nsplit), dim3(128), 0, (const G1Xyzz*)V, h, nsplit,
                    bits));
     const uint32_t np = 2 * nbits * nsplit;  // <= 2 * 13 * 8 shifted points per set
