@@ -281,18 +281,13 @@ H2B_D void st_xyzz(G1Xyzz* dst, const G1Xyzz& p) {
 // A bucket is written exactly once per pass over a sorted pair list (at the level where its run is no longer
 // cut), with a plain store: lanes reach the ends of their runs at different iterations, so anything heavier
 // there (adding to an earlier batch's bucket, say) would be executed by the warp on almost every iteration.
+// chunk t of the N sorted entries; its partial sums (runs cut by a chunk boundary) go to slots o, o + 1 of the next list
 template <class Src>
-H2B_D void msm_accum_body(const Src& src, const uint32_t* keys, const uint32_t* n_cur, uint32_t L,
-                          const uint32_t* cnt, const uint32_t* incl, uint32_t nchunks,
-                          uint32_t* n_next, uint32_t* okeys, G1Xyzz* opts, G1Xyzz* buckets) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nchunks) return;
-  if (t == nchunks - 1) *n_next = incl[t];
-  const uint32_t N = *n_cur;
+H2B_D void msm_accum_chunk(const Src& src, const uint32_t* keys, uint32_t N, uint32_t L, uint32_t t, uint32_t o,
+                           uint32_t* okeys, G1Xyzz* opts, G1Xyzz* buckets) {
   const uint64_t start = (uint64_t)t * L;
   if (start >= N) return;
   const uint64_t end = start + L < N ? start + L : N;
-  uint32_t o = incl[t] - cnt[t];
   uint32_t cur = keys[start];
   const bool head = start > 0 && keys[start - 1] == cur;
   const bool tail = end < N && keys[end] == keys[end - 1];
@@ -330,6 +325,16 @@ H2B_D void msm_accum_body(const Src& src, const uint32_t* keys, const uint32_t* 
   }
 }
 
+template <class Src>
+H2B_D void msm_accum_body(const Src& src, const uint32_t* keys, const uint32_t* n_cur, uint32_t L,
+                          const uint32_t* cnt, const uint32_t* incl, uint32_t nchunks,
+                          uint32_t* n_next, uint32_t* okeys, G1Xyzz* opts, G1Xyzz* buckets) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  if (t == nchunks - 1) *n_next = incl[t];
+  msm_accum_chunk(src, keys, *n_cur, L, t, incl[t] - cnt[t], okeys, opts, buckets);
+}
+
 #ifndef H2B_ACC0_MINB
 #define H2B_ACC0_MINB 4  // 126 registers with the operand prefetch: 4 blocks per SM (3 blocks at 142 registers: 37.9 vs 36.9 ms at k = 24)
 #endif
@@ -345,6 +350,48 @@ __global__ void __launch_bounds__(128)
                       const uint32_t* cnt, const uint32_t* incl, uint32_t nchunks, uint32_t* n_next,
                       uint32_t* okeys, G1Xyzz* opts, G1Xyzz* buckets) {
   msm_accum_body(src, keys, n_cur, L, cnt, incl, nchunks, n_next, okeys, opts, buckets);
+}
+
+// Every remaining level in ONE launch, once the list is short enough for one block (at most 128 chunks of L entries:
+// in practice a handful of entries, the host only knows the bound): count, scan and accumulate per level with the
+// two lists ping-ponging, until a level cuts no run.  `from` = index (0 / 1) of the list this level reads.
+static const uint32_t kFinishChunks = 128;
+__global__ void __launch_bounds__(128)
+    msm_finish_levels_kernel(uint32_t* lkeys0, uint32_t* lkeys1, G1Xyzz* lpts0, G1Xyzz* lpts1, uint32_t from,
+                             const uint32_t* n_cur, uint32_t L, G1Xyzz* buckets) {
+  __shared__ uint32_t sc[kFinishChunks];
+  __shared__ uint32_t sN;
+  const uint32_t tid = threadIdx.x;
+  uint32_t N = *n_cur;
+  for (uint32_t guard = 0; guard < 32 && N > 0; ++guard) {
+    const uint32_t* keys = from ? lkeys1 : lkeys0;
+    const LevelNSrc src{from ? lpts1 : lpts0};
+    uint32_t* okeys = from ? lkeys0 : lkeys1;
+    G1Xyzz* opts = from ? lpts0 : lpts1;
+    const uint64_t start = (uint64_t)tid * L;
+    uint32_t c = 0;
+    if (start < N) {
+      const uint64_t end = start + L < N ? start + L : N;
+      const uint32_t kf = keys[start], kl = keys[end - 1];
+      const uint32_t head = start > 0 && keys[start - 1] == kf;
+      const uint32_t tail = end < N && keys[end] == kl;
+      c = (kf == kl) ? (head | tail) : head + tail;
+    }
+    sc[tid] = c;
+    __syncthreads();
+    for (uint32_t d = 1; d < kFinishChunks; d <<= 1) {
+      const uint32_t v = tid >= d ? sc[tid - d] : 0;
+      __syncthreads();
+      sc[tid] += v;
+      __syncthreads();
+    }
+    msm_accum_chunk(src, keys, N, L, tid, sc[tid] - c, okeys, opts, buckets);
+    if (tid == kFinishChunks - 1) sN = sc[tid];
+    __syncthreads();  // the next level reads what this one wrote (block-wide visibility of global stores)
+    N = sN;
+    from ^= 1;
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1128,6 +1175,11 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
       const uint32_t L = level == 0 ? p.L0 : p.LN;
       const uint32_t nchunks = (uint32_t)((nmax + L - 1) / L);
       const int o = level & 1;
+      if (level >= 1 && nchunks <= kFinishChunks) {  // short enough for one block: all remaining levels in one launch
+        H2B_TRY(launch(ctx, msm_finish_levels_kernel, dim3(1), dim3(kFinishChunks), 0, ws->lkeys[0], ws->lkeys[1],
+                       ws->lpts[0], ws->lpts[1], (uint32_t)(o ^ 1), (const uint32_t*)(ws->n_level + level), L, target));
+        break;
+      }
       if (nchunks <= kFusedScanMax) {
         H2B_TRY(launch(ctx, msm_count_scan_kernel, dim3(1), dim3(1024), 0, keys,
                        (const uint32_t*)(ws->n_level + level), L, nchunks, ws->cnt, ws->incl));
