@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhalo2b200.so")
 SOURCES = ["ctx.cu", "ntt.cu", "msm.cu", "poly.cu", "evalh.cu", "prover.cu", "lookup.cu", "serde.cu"]
-HEADERS = ["common.cuh", "field.cuh", "ec.cuh", os.path.join(ROOT, "include", "halo2_b200.h")]
+HEADERS = ["common.cuh", "field.cuh", "shoup_chains.cuh", "ec.cuh", os.path.join(ROOT, "include", "halo2_b200.h")]
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_LIB = os.path.join(EMU_DIR, "_build", "libhalo2b200_emu.so")
 

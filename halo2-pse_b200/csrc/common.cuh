@@ -25,6 +25,7 @@ struct TwTable {
   Fr* d_lo;        // omega^i,           i < 2^h
   Fr* d_hi;        // omega^(i << h),    i < 2^(k-h)
   Fr* d_rt;        // omega_R^i, R = 2^min(k,9), i < R   (intra-pass roots)
+  Fr* d_rts = nullptr;  // the same roots for mul_shoup: [2i] = plain value, [2i + 1] = floor(value * 2^256 / r)
   // single-multiplication inter-pass twiddles (optional; nullptr -> two-level lo/hi product)
   Fr* d_out = nullptr;   // first pass: w^(jr * K) at output index K * m2 + jr, n entries (optional)
   uint32_t out_s1 = 0;   // first digit width the table was built for
@@ -51,6 +52,11 @@ struct h2b_ctx {
   cudaStream_t bulk_stream = nullptr;
   cudaEvent_t bulk_ev[2] = {nullptr, nullptr};
   cudaEvent_t copy_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // host-scalar MSMs in batches: timing events around every batch's copy (copy stream) and compute (main stream),
+  // created on first use; their ratio (time to copy a point / time to accumulate it, running average) sizes the
+  // batches of the next call -- 0.25 alone on PCIe 5, 0.6 when eight ranks share the host's memory path
+  cudaEvent_t plan_ev[28] = {nullptr};
+  float msm_copy_ratio = 0.f;
   std::recursive_mutex mu;
   std::string last_error;
   // grow-only device scratch (NTT ping buffer)

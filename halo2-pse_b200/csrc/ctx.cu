@@ -503,6 +503,8 @@ extern "C" void h2b_ctx_destroy(h2b_ctx* ctx) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 6; ++i)
     if (ctx->pass_ev[i]) cudaEventDestroy(ctx->pass_ev[i]);
+  for (int i = 0; i < 28; ++i)
+    if (ctx->plan_ev[i]) cudaEventDestroy(ctx->plan_ev[i]);
   for (int i = 0; i < 8; ++i)
     if (ctx->copy_ev[i]) cudaEventDestroy(ctx->copy_ev[i]);
   delete ctx->copy_workers;

@@ -22,6 +22,8 @@
 #define H2B_D inline
 #endif
 
+#include "shoup_chains.cuh"  // generated carry chains of mul_shoup (below)
+
 namespace h2b {
 
 // ---------------------------------------------------------------------------
@@ -634,6 +636,115 @@ H2B_HD Fp<P> mul_sub(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>
   mul_wide16(u, nc, d);
   add16(t, t, u);
   return mont_reduce<P, true>(t);
+}
+
+// ---------------------------------------------------------------------------
+// Product by a FIXED multiplier (Shoup): x * w mod p for a plain (non-Montgomery) w < p with the precomputed
+// w' = floor(w * 2^256 / p).  q = floor(x * w' / 2^256) is floor(x * w / p) or one less, so x*w - q*p lies in [0, 2p);
+// both products of that difference are needed modulo 2^256 only, and of x * w' only the top half:
+//   28 + 8 (low 256 bits of x*w)  +  36 + 7 (columns >= 7 of x*w', the guard column's high words only)
+//   + 28 + 8 (low 256 bits of q*p)  =  92 wide, 7 high and 16 low multiplies against 128 wide + 8 low of `mul`.
+// Dropping the columns below the guard makes q at most one smaller again: the result is in [0, 3p), two conditional
+// subtractions.  x in Montgomery form gives x*w in Montgomery form: the transforms multiply by table constants only
+// (roots of unity), so their intra-pass products take this path (csrc/ntt.cu).
+// ---------------------------------------------------------------------------
+// r[0..7] = low 256 bits of x * y
+H2B_HD void mul_low8(uint32_t* r, const uint32_t* x, const uint32_t* y) {
+  uint32_t A[2][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) A[0][c] = A[1][c] = 0;
+  // row i multiplies y[i] into x[0 .. 7-i]: even-j products to accumulator i & 1 at column i, odd-j to the other at i + 1
+  chain_low<4, false>(&A[0][0], &x[0], y[0]);
+  chain_low<3, true>(&A[1][1], &x[1], y[0]);
+  chain_low<3, true>(&A[1][1], &x[0], y[1]);
+  chain_low<3, false>(&A[0][2], &x[1], y[1]);
+  chain_low<3, false>(&A[0][2], &x[0], y[2]);
+  chain_low<2, true>(&A[1][3], &x[1], y[2]);
+  chain_low<2, true>(&A[1][3], &x[0], y[3]);
+  chain_low<2, false>(&A[0][4], &x[1], y[3]);
+  chain_low<2, false>(&A[0][4], &x[0], y[4]);
+  chain_low<1, true>(&A[1][5], &x[1], y[4]);
+  chain_low<1, true>(&A[1][5], &x[0], y[5]);
+  chain_low<1, false>(&A[0][6], &x[1], y[5]);
+  chain_low<1, false>(&A[0][6], &x[0], y[6]);
+  chain_low<0, true>(&A[1][7], &x[1], y[6]);
+  chain_low<0, true>(&A[1][7], &x[0], y[7]);
+  add8(r, A[0], A[1]);  // modulo 2^256
+}
+
+// q[0..7] = floor(x * y / 2^256) or one less (columns below 6 and the low words of column 6 are dropped)
+H2B_HD void mul_high8(uint32_t* q, const uint32_t* x, const uint32_t* y) {
+  uint32_t H[2][10];  // columns 7 .. 16
+#pragma unroll
+  for (int c = 0; c < 10; ++c) H[0][c] = H[1][c] = 0;
+  // row i multiplies y[i] into x[6-i] (high word only, column 7) and x[7-i .. 7]; products with i + j even go to
+  // accumulator 0, odd to accumulator 1; rows ascend, so every carry-out lands on an empty word or an earlier carry
+  chain_high<true, 0>(&H[0][0], &x[6], y[0]);
+  chain_high<false, 1>(&H[1][0], &x[7], y[0]);
+  chain_high<true, 1>(&H[0][0], &x[5], y[1]);
+  chain_high<false, 1>(&H[1][0], &x[6], y[1]);
+  chain_high<true, 1>(&H[0][0], &x[4], y[2]);
+  chain_high<false, 2>(&H[1][0], &x[5], y[2]);
+  chain_high<true, 2>(&H[0][0], &x[3], y[3]);
+  chain_high<false, 2>(&H[1][0], &x[4], y[3]);
+  chain_high<true, 2>(&H[0][0], &x[2], y[4]);
+  chain_high<false, 3>(&H[1][0], &x[3], y[4]);
+  chain_high<true, 3>(&H[0][0], &x[1], y[5]);
+  chain_high<false, 3>(&H[1][0], &x[2], y[5]);
+  chain_high<true, 3>(&H[0][0], &x[0], y[6]);
+  chain_high<false, 4>(&H[1][0], &x[1], y[6]);
+  chain_high<false, 4>(&H[0][1], &x[1], y[7]);
+  chain_high<false, 4>(&H[1][0], &x[0], y[7]);
+  add8_seed(q, &H[0][1], &H[1][1], H[0][0], H[1][0]);  // columns 8 .. 15 + the carry out of column 7
+}
+
+// x * w mod p, given w (plain, < p) and wp = floor(w * 2^256 / p)
+template <class P>
+H2B_HD Fp<P> mul_shoup(const Fp<P>& x, const Fp<P>& w, const Fp<P>& wp) {
+  uint32_t q[8], lo[8], qp[8], pm[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pm[i] = P::mod(i);
+  mul_high8(q, x.v, wp.v);
+  mul_low8(lo, x.v, w.v);
+  mul_low8(qp, q, pm);
+  Fp<P> r;
+  sub8(r.v, lo, qp);  // exact: the true difference is below 3p < 2^256
+  reduce_once(r);
+  reduce_once(r);
+  return r;
+}
+
+// wp = floor(w * 2^256 / p) for a plain w < p, from its Montgomery form wm = w * 2^256 mod p:
+// w * 2^256 = wp * p + wm, so wp = -wm * p^-1 modulo 2^256 (table builders; generic loops)
+template <class P>
+H2B_HD Fp<P> shoup_companion(const Fp<P>& wm) {
+  uint32_t pm[8], inv[8], t[8], u[8];
+  for (int i = 0; i < 8; ++i) {
+    pm[i] = P::mod(i);
+    inv[i] = 0;
+  }
+  inv[0] = 1;
+  for (int it = 0; it < 8; ++it) {  // Newton: inv <- inv * (2 - p * inv) doubles the correct low bits (1 -> 256)
+    mul_low8(t, pm, inv);
+    uint32_t borrow = 0;
+    for (int i = 0; i < 8; ++i) {  // u = 2 - t
+      const uint64_t d = (uint64_t)(i == 0 ? 2u : 0u) - t[i] - borrow;
+      u[i] = (uint32_t)d;
+      borrow = (uint32_t)(d >> 32) & 1u;
+    }
+    mul_low8(t, inv, u);
+    for (int i = 0; i < 8; ++i) inv[i] = t[i];
+  }
+  uint32_t neg[8];
+  uint32_t borrow = 0;
+  for (int i = 0; i < 8; ++i) {  // neg = 2^256 - wm
+    const uint64_t d = (uint64_t)0 - wm.v[i] - borrow;
+    neg[i] = (uint32_t)d;
+    borrow = (uint32_t)(d >> 32) & 1u;
+  }
+  Fp<P> r;
+  mul_low8(r.v, neg, inv);
+  return r;
 }
 
 // Montgomery -> canonical residue: a / R mod p, the reduction alone (half the multiplies of a product by 1)

@@ -116,17 +116,9 @@ __global__ void msm_digits_kernel(const Fr* scalars, uint64_t row_stride, uint32
   for (uint64_t i = i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1;
        i += (uint64_t)gridDim.x * blockDim.x) {
     const Fr s = from_mont(ld_fp(scalars + i));  // to_repr(), arithmetic.rs:14
-    uint32_t carry = 0;
-    const uint32_t half = 1u << (c - 1);
-    for (uint32_t w = 0; w < W; ++w) {
-      const uint32_t bit = w * c;
-      uint32_t d = 0;
-      if (bit < 256) {
-        const uint32_t limb = bit >> 5, sh = bit & 31;
-        uint64_t two = s.v[limb];
-        if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
-        d = (uint32_t)(two >> sh) & ((1u << c) - 1u);
-      }
+    uint32_t carry = 0, w = 0;
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1u;
+    auto emit = [&](uint32_t d) {
       d += carry;
       uint32_t negf = 0;
       if (d > half) {
@@ -144,6 +136,25 @@ __global__ void msm_digits_kernel(const Fr* scalars, uint64_t row_stride, uint32
         keys[slot] = d ? w * half + d - 1 : 0xffffffffu;
         vals[slot] = (uint32_t)i | (negf << 31);
       }
+      ++w;
+    };
+    // the limbs stream through a 64-bit window (static limb indices: a run-time index into s.v would put the scalar
+    // in local memory); fewer than c bits wait in `buf` when a limb joins, so 32 + c - 1 <= 64 bits are live
+    uint64_t buf = 0;
+    uint32_t have = 0;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      buf |= (uint64_t)s.v[l] << have;
+      have += 32;
+      while (have >= c && w < W) {
+        emit((uint32_t)buf & mask);
+        buf >>= c;
+        have -= c;
+      }
+    }
+    while (w < W) {  // the bits above 256 are zero
+      emit((uint32_t)buf & mask);
+      buf >>= c;
     }
   }
 }
@@ -1042,12 +1053,14 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   uint64_t batch_min = 1ull << 22;  // points per batch; H2B_MSM_BATCH_MIN overrides (tests), 0 disables
   if (const char* e = getenv("H2B_MSM_BATCH_MIN")) batch_min = strtoull(e, nullptr, 10);
   // Batch sizes grow geometrically: only the copy of batch 0 is exposed, and the copy of batch b + 1 hides under the
-  // compute of batch b as long as it is not more than compute/copy (~ 3-4 on PCIe 5) times larger.
-  // H2B_MSM_BATCH_PLAN = "w0,w1,..." overrides the relative weights (at most 7 batches).
+  // compute of batch b as long as it is not more than compute/copy times larger.  That ratio is measured (events
+  // around every batch's copy and compute of the previous calls on this context): 4 alone on PCIe 5 (weights 1,4,16:
+  // k = 24 45.5 ms with four equal batches -> 42.6), below 2 when eight ranks share the host's memory path (five
+  // batches growing by 1.6).  H2B_MSM_BATCH_PLAN = "w0,w1,..." fixes the relative weights (at most 7 batches).
   uint64_t bstart[9] = {0};
   int NB = 1;
   if (h_scalars && table_stride && batch_min && ncols == 1 && n >= 2 * batch_min) {
-    uint32_t wts[8] = {1, 4, 16, 0, 0, 0, 0, 0};  // B200 + PCIe 5, k = 24: 1,1,1,1 45.5 ms; 1,3,9 43.2; 1,4,16 42.6; 1,5,20 42.6
+    double wts[8] = {1, 4, 16, 0, 0, 0, 0, 0};
     int nw = n >= 4 * batch_min ? 3 : 2;
     if (const char* e = getenv("H2B_MSM_BATCH_PLAN")) {
       nw = 0;
@@ -1055,22 +1068,33 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
         char* end = nullptr;
         const unsigned long v = strtoul(q, &end, 10);
         if (end == q) break;
-        if (v) wts[nw++] = (uint32_t)v;
+        if (v) wts[nw++] = (double)v;
         q = *end ? end + 1 : end;
       }
       if (nw == 0) { wts[0] = 1; nw = 1; }
+    } else if (ctx->msm_copy_ratio > 0.f && n >= 4 * batch_min) {
+      double g = 0.95 / ctx->msm_copy_ratio;
+      g = g > 4.0 ? 4.0 : g < 1.25 ? 1.25 : g;
+      nw = g >= 3.0 ? 3 : g >= 1.8 ? 4 : 5;
+      while (nw > 2 && n < (uint64_t)nw * batch_min) --nw;
+      for (int i = 0; i < nw; ++i) wts[i] = i ? wts[i - 1] * g : 1.0;
     }
-    uint64_t tot = 0, run = 0, prev = 0;
+    double tot = 0, run = 0;
+    uint64_t prev = 0;
     for (int i = 0; i < nw; ++i) tot += wts[i];
     NB = 0;
     for (int i = 0; i < nw; ++i) {
       run += wts[i];
-      const uint64_t e1 = i + 1 == nw ? (uint64_t)n : ((n * run / tot) & ~(uint64_t)(n >= 65536 ? 255 : 0));
-      if (e1 > prev) bstart[++NB] = prev = e1;
+      const uint64_t e1 = i + 1 == nw ? (uint64_t)n : ((uint64_t)((double)n * (run / tot)) & ~(uint64_t)(n >= 65536 ? 255 : 0));
+      if (e1 > prev && e1 <= n) bstart[++NB] = prev = e1;
     }
+    bstart[NB] = n;
   } else {
     bstart[1] = n;
   }
+  const bool plan_timing = NB > 1;
+  if (plan_timing && !ctx->plan_ev[0])
+    for (int i = 0; i < 28; ++i) H2B_CUDA(ctx, cudaEventCreate(&ctx->plan_ev[i]));
   H2B_CUDA(ctx, cudaMemsetAsync(ws->buckets, 0, (size_t)p.Wb * p.nb_per_window * sizeof(G1Xyzz), st));
   // copy of batch b on the copy stream, event copy_ev[b]; queued right after the compute of batch b - 1, so
   // that a pageable source (staged by host threads, which blocks this thread) overlaps that compute as well
@@ -1078,7 +1102,9 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
     if (b >= NB) return H2B_OK;
     const uint64_t i0 = bstart[b], i1 = bstart[b + 1];
     if (i0 >= i1) return H2B_OK;
+    if (plan_timing) H2B_CUDA(ctx, cudaEventRecord(ctx->plan_ev[4 * b], ctx->copy_stream));
     H2B_TRY(copy_h2d_any(ctx, const_cast<Fr*>(d_scalars) + i0, h_scalars + i0, (i1 - i0) * sizeof(Fr), ctx->copy_stream));
+    if (plan_timing) H2B_CUDA(ctx, cudaEventRecord(ctx->plan_ev[4 * b + 1], ctx->copy_stream));
     H2B_CUDA(ctx, cudaEventRecord(ctx->copy_ev[b], ctx->copy_stream));
     return H2B_OK;
   };
@@ -1118,6 +1144,7 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
       H2B_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
     }
     if (NB > 1) H2B_CUDA(ctx, cudaStreamWaitEvent(st, ctx->copy_ev[batch], 0));
+    if (plan_timing) H2B_CUDA(ctx, cudaEventRecord(ctx->plan_ev[4 * batch + 2], st));  // stamped once the copy has landed
     for (int ci = 0; ci < nchunk; ++ci) {
       const uint64_t i0 = b0 + (uint64_t)ci * per, i1 = std::min<uint64_t>(b1, i0 + per);
       if (i0 >= i1) break;
@@ -1224,6 +1251,7 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   if (batch > 0)
     H2B_TRY(launch(ctx, msm_bucket_merge_kernel, dim3((nbuckets_all + 127) / 128), dim3(128), 0, ws->buckets,
                    (const G1Xyzz*)ws->buckets2, nbuckets_all));
+  if (plan_timing) H2B_CUDA(ctx, cudaEventRecord(ctx->plan_ev[4 * batch + 3], st));
   if (NB > 1) H2B_TRY(queue_copy(batch + 1));
   }  // batches
 
@@ -1278,6 +1306,21 @@ int msm_run(h2b_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   if (ctx->profile) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_kernel_ms = ms;
+  }
+  if (plan_timing) {  // copy time per point over compute time per point, for the next call's batch sizes
+    float copy_ms = 0, comp_ms = 0;
+    bool ok = true;
+    for (int b = 0; b < NB; ++b) {
+      float a = 0, c2 = 0;
+      ok = ok && cudaEventElapsedTime(&a, ctx->plan_ev[4 * b], ctx->plan_ev[4 * b + 1]) == cudaSuccess &&
+           cudaEventElapsedTime(&c2, ctx->plan_ev[4 * b + 2], ctx->plan_ev[4 * b + 3]) == cudaSuccess;
+      copy_ms += a;
+      comp_ms += c2;
+    }
+    if (ok && comp_ms > 0.f && copy_ms > 0.f) {
+      const float r = copy_ms / comp_ms;
+      ctx->msm_copy_ratio = ctx->msm_copy_ratio > 0.f ? 0.5f * ctx->msm_copy_ratio + 0.5f * r : r;
+    }
   }
 
   // 5. combine windows, top first: acc = 2^c * acc + R_w   (arithmetic.rs:46-49)

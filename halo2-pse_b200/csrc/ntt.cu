@@ -63,6 +63,9 @@ struct PassParams {
   uint32_t h;
   const Fr* rt;
   uint32_t rt_log;
+  // the intra-pass roots as (plain value, Shoup companion) pairs: the register kernel multiplies by them with
+  // mul_shoup (92 wide multiplies instead of 128; 29 of the 37 products of a pass)
+  const Fr* rts;
   // single-level inter-pass twiddle table of the later passes: w = tw1[(jr*K) << tw1_shift]
   const Fr* tw1;
   uint32_t tw1_shift;
@@ -264,18 +267,24 @@ __global__ void __launch_bounds__(256) ntt_pass_generic(PassParams p) {
 // ---------------------------------------------------------------------------
 // 8-point DFT, natural order in and out: x[K] <- sum_a x[a] * w8^(a*K).
 // w8 = rt[N/8], w4 = rt[N/4], w8^3 = rt[3N/8] with N = 2^rt_log.
-H2B_D void dft8(Fr* x, const Fr* rt, uint32_t rt_log) {
+// x * rts-root number i (a table constant: Shoup product)
+H2B_D Fr mul_root(const Fr& x, const Fr* rts, uint32_t i) {
+  return mul_shoup(x, ld_fp_nc(rts + 2 * i), ld_fp_nc(rts + 2 * i + 1));
+}
+
+H2B_D void dft8(Fr* x, const Fr* rts, uint32_t rt_log) {
   Fr s0 = add(x[0], x[4]), d0 = sub(x[0], x[4]);
   Fr s1 = add(x[1], x[5]), d1 = sub(x[1], x[5]);
   Fr s2 = add(x[2], x[6]), d2 = sub(x[2], x[6]);
   Fr s3 = add(x[3], x[7]), d3 = sub(x[3], x[7]);
-  const Fr w4 = ld_fp_nc(rt + (1u << (rt_log - 2)));
-  d1 = mul(d1, ld_fp_nc(rt + (1u << (rt_log - 3))));
-  d2 = mul(d2, w4);
-  d3 = mul(d3, ld_fp_nc(rt + (3u << (rt_log - 3))));
+  const uint32_t i4 = 1u << (rt_log - 2);
+  const Fr w4 = ld_fp_nc(rts + 2 * i4), w4s = ld_fp_nc(rts + 2 * i4 + 1);
+  d1 = mul_root(d1, rts, 1u << (rt_log - 3));
+  d2 = mul_shoup(d2, w4, w4s);
+  d3 = mul_root(d3, rts, 3u << (rt_log - 3));
   // even outputs from s, odd outputs from d
   Fr e0 = add(s0, s2), f0 = sub(s0, s2);
-  Fr e1 = add(s1, s3), f1 = mul(sub(s1, s3), w4);
+  Fr e1 = add(s1, s3), f1 = mul_shoup(sub(s1, s3), w4, w4s);
   x[0] = add(e0, e1);
   x[4] = sub(e0, e1);
   x[2] = add(f0, f1);
@@ -283,7 +292,7 @@ H2B_D void dft8(Fr* x, const Fr* rt, uint32_t rt_log) {
   e0 = add(d0, d2);
   f0 = sub(d0, d2);
   e1 = add(d1, d3);
-  f1 = mul(sub(d1, d3), w4);
+  f1 = mul_shoup(sub(d1, d3), w4, w4s);
   x[1] = add(e0, e1);
   x[5] = sub(e0, e1);
   x[3] = add(f0, f1);
@@ -332,9 +341,9 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
     else
       x[a] = load_in_t<PRE>(p, in, g.in_base + row * g.in_rs + c * g.in_cs);
   }
-  dft8(x, p.rt, p.rt_log);
+  dft8(x, p.rts, p.rt_log);
 #pragma unroll
-  for (int Ka = 1; Ka < 8; ++Ka) x[Ka] = mul_tw(x[Ka], ld_fp_nc(p.rt + ((u * Ka) << rsh)));
+  for (int Ka = 1; Ka < 8; ++Ka) x[Ka] = mul_root(x[Ka], p.rts, (u * Ka) << rsh);
 #pragma unroll
   for (int Ka = 0; Ka < 8; ++Ka) put(Ka * T + u, x[Ka]);
   __syncthreads();
@@ -342,7 +351,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   const uint32_t Ka = u >> LM2, b2 = u & (M2 - 1);
 #pragma unroll
   for (int a2 = 0; a2 < 8; ++a2) x[a2] = get(Ka * T + a2 * M2 + b2);
-  dft8(x, p.rt, p.rt_log);
+  dft8(x, p.rts, p.rt_log);
   if (M2 == 1) {
 #pragma unroll
     for (int Ka2 = 0; Ka2 < 8; ++Ka2) store_out_t<KIND>(p, out, g, Ka + 8 * Ka2, c, x[Ka2], bidx);
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   }
 #pragma unroll
   for (int Ka2 = 1; Ka2 < 8; ++Ka2)
-    x[Ka2] = mul_tw(x[Ka2], ld_fp_nc(p.rt + ((8 * b2 * Ka2) << rsh)));
+    x[Ka2] = mul_root(x[Ka2], p.rts, (8 * b2 * Ka2) << rsh);
 #pragma unroll
   for (int Ka2 = 0; Ka2 < 8; ++Ka2) put(Ka * T + Ka2 * M2 + b2, x[Ka2]);
   __syncthreads();
@@ -359,17 +368,18 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
     const uint32_t gq = u;  // 64 threads per column, one group each
 #pragma unroll
     for (int b = 0; b < 8; ++b) x[b] = get(gq * 8 + b);
-    dft8(x, p.rt, p.rt_log);
+    dft8(x, p.rts, p.rt_log);
     const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
 #pragma unroll
     for (int i = 0; i < 8; ++i) store_out_t<KIND>(p, out, g, K0 + 64 * i, c, x[i], bidx);
   } else if (M2 == 4) {
-    const Fr w4 = ld_fp_nc(p.rt + (1u << (p.rt_log - 2)));
+    const uint32_t i4 = 1u << (p.rt_log - 2);
+    const Fr w4 = ld_fp_nc(p.rts + 2 * i4), w4s = ld_fp_nc(p.rts + 2 * i4 + 1);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const uint32_t gq = u + 32 * i;
       Fr v0 = get(gq * 4 + 0), v1 = get(gq * 4 + 1), v2 = get(gq * 4 + 2), v3 = get(gq * 4 + 3);
-      Fr t0 = add(v0, v2), t1 = sub(v0, v2), t2 = add(v1, v3), t3 = mul(sub(v1, v3), w4);
+      Fr t0 = add(v0, v2), t1 = sub(v0, v2), t2 = add(v1, v3), t3 = mul_shoup(sub(v1, v3), w4, w4s);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
       store_out_t<KIND>(p, out, g, K0, c, add(t0, t2), bidx);
       store_out_t<KIND>(p, out, g, K0 + 64, c, add(t1, t3), bidx);
@@ -396,6 +406,15 @@ __global__ void scale_mod_kernel(Fr* a, uint64_t n, const Fr* tab, uint32_t mod)
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x)
     st_fp(a + i, mul(ld_fp(a + i), ld_fp_nc(tab + (uint32_t)i % mod)));
+}
+
+// out[2i] = plain value of the Montgomery-form tab[i], out[2i + 1] = its Shoup companion (mul_shoup's operands)
+__global__ void shoup_table_kernel(const Fr* tab, Fr* out, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const Fr wm = ld_fp(tab + i);
+  st_fp(out + 2 * i, from_mont(wm));
+  st_fp(out + 2 * i + 1, shoup_companion(wm));
 }
 
 // tab[i] = base^(i << shift), i < count
@@ -555,6 +574,9 @@ int ntt_get_table(h2b_ctx* ctx, const Fr& omega, uint32_t k, const TwTable** out
                  nhi));
   H2B_TRY(launch(ctx, pow_table_kernel, dim3(((1u << rt_log) + 127) / 128), dim3(128), 0, t.d_rt,
                  omega, k - rt_log, 1u << rt_log));
+  H2B_CUDA(ctx, dev_malloc(ctx, (void**)&t.d_rts, ((size_t)2 << rt_log) * sizeof(Fr)));
+  H2B_TRY(launch(ctx, shoup_table_kernel, dim3(((1u << rt_log) + 127) / 128), dim3(128), 0, (const Fr*)t.d_rt, t.d_rts,
+                 1u << rt_log));
   // single-level tables (later passes: 2^(k-6) entries at most; first pass: folded full table, opt-in)
   if (k > 8) {
     uint32_t s[4];
@@ -599,6 +621,7 @@ void ntt_free_tables(h2b_ctx* ctx) {
     cudaFree(t.d_lo);
     cudaFree(t.d_hi);
     cudaFree(t.d_rt);
+    if (t.d_rts) cudaFree(t.d_rts);
     if (t.d_out) cudaFree(t.d_out);
     if (t.d_mid) cudaFree(t.d_mid);
   }
@@ -707,6 +730,7 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       p.tw_hi = tw->d_hi;
       p.h = tw->h;
       p.rt = tw->d_rt;
+      p.rts = tw->d_rts;
       p.rt_log = k < 9 ? k : 9;
       p.tw1 = nullptr;
       p.tw1_shift = 0;

@@ -11,11 +11,30 @@ __global__ void __launch_bounds__(256) k_mul(uint32_t* sink, int iters, uint32_t
   F a[CH], b;
   for (int c = 0; c < CH; ++c) for (int j = 0; j < 8; ++j) a[c].v[j] = F::one().v[j] ^ (threadIdx.x * 131 + c * 7 + seed) & 0x0fffffff;
   for (int j = 0; j < 8; ++j) b.v[j] = F::r2().v[j] ^ (blockIdx.x + seed) & 0x0fffffff;
+  F bw = from_mont(b), bs = shoup_companion(b);
   for (int i = 0; i < iters; ++i)
 #pragma unroll
-    for (int c = 0; c < CH; ++c) a[c] = V == 0 ? mul(a[c], b) : V == 1 ? mul_dfma(a[c], b) : V == 2 ? sqr_dfma(a[c]) : V == 4 ? sqr(a[c]) : mul_dfma(a[c], a[(c + 1) % CH]);
+    for (int c = 0; c < CH; ++c) a[c] = V == 5 ? mul_shoup(a[c], bw, bs) : V == 0 ? mul(a[c], b) : V == 1 ? mul_dfma(a[c], b) : V == 2 ? sqr_dfma(a[c]) : V == 4 ? sqr(a[c]) : mul_dfma(a[c], a[(c + 1) % CH]);
   uint32_t s = 0;
   for (int c = 0; c < CH; ++c) for (int j = 0; j < 8; ++j) s ^= a[c].v[j];
+  if (s == 0x12345678u) sink[0] = s;
+}
+
+// radix-2 butterfly chain (a, c) -> (a + w c, a - w c): the transform's inner operation, Montgomery or Shoup product
+template <class F, int V>
+__global__ void __launch_bounds__(256) k_bfly(uint32_t* sink, int iters, uint32_t seed) {
+  F a, c, b;
+  for (int j = 0; j < 8; ++j) { a.v[j] = F::one().v[j] ^ (threadIdx.x * 131 + seed) & 0x0fffffff; c.v[j] = F::r2().v[j] ^ (threadIdx.x * 17 + seed) & 0x0fffffff; }
+  for (int j = 0; j < 8; ++j) b.v[j] = F::r2().v[j] ^ (blockIdx.x + seed) & 0x0fffffff;
+  F bw = from_mont(b), bs = shoup_companion(b);
+  for (int i = 0; i < iters; ++i) {
+    F t = V == 0 ? mul(c, b) : mul_shoup(c, bw, bs);
+    F na = add(a, t);
+    c = sub(a, t);
+    a = na;
+  }
+  uint32_t s = 0;
+  for (int j = 0; j < 8; ++j) s ^= a.v[j] ^ c.v[j];
   if (s == 0x12345678u) sink[0] = s;
 }
 
@@ -28,8 +47,10 @@ __global__ void k_check(const uint32_t* a, const uint32_t* b, uint32_t* bad, int
   for (int j = 0; j < 8; ++j) { x.v[j] = a[i * 8 + j]; y.v[j] = b[i * 8 + j]; }
   for (int k = 0; k < 4; ++k) { reduce_once(x); reduce_once(y); }
   F r0 = mul(x, y), r1 = mul_dfma(x, y), s0 = mul(x, x), s1 = sqr_dfma(x), s2 = sqr(x);
+  F yy = y; if (yy.is_zero()) yy = F::one();
+  F sh = mul_shoup(x, from_mont(yy), shoup_companion(yy)), sh0 = mul(x, yy);
   uint32_t d = 0;
-  for (int j = 0; j < 8; ++j) d += (r0.v[j] != r1.v[j]) + (s0.v[j] != s1.v[j]) + (s0.v[j] != s2.v[j]);
+  for (int j = 0; j < 8; ++j) d += (r0.v[j] != r1.v[j]) + (s0.v[j] != s1.v[j]) + (s0.v[j] != s2.v[j]) + (sh.v[j] != sh0.v[j]);
   if (d) atomicAdd(bad, 1u);
 }
 
@@ -71,7 +92,7 @@ static int check(const char* name) {
   k_check<F><<<(n + 127) / 128, 128>>>(da, db, dbad, n);
   uint32_t bad = 1;
   cudaMemcpy(&bad, dbad, 4, cudaMemcpyDeviceToHost);
-  printf("%s: mul_dfma / sqr_dfma / sqr vs mul on %d operand pairs: %u mismatches\n", name, n, bad);
+  printf("%s: mul_dfma / sqr_dfma / sqr / mul_shoup vs mul on %d operand pairs: %u mismatches\n", name, n, bad);
   return bad != 0;
 }
 
@@ -92,6 +113,10 @@ int main() {
     printf("  dfma mul (both unpacked)    CH=4: %.2f G mulmod/s\n", run(k_mul<Fq, 4, 3>, blocks, 512, 4, sink) / 1e9);
     printf("  dfma sqr                    CH=1: %.2f G mulmod/s\n", run(k_mul<Fq, 1, 2>, blocks, 2048, 1, sink) / 1e9);
     printf("  dfma sqr                    CH=2: %.2f G mulmod/s\n", run(k_mul<Fq, 2, 2>, blocks, 1024, 2, sink) / 1e9);
+    printf("  shoup mul (fixed multiplier) CH=1: %.2f G mulmod/s\n", run(k_mul<Fq, 1, 5>, blocks, 2048, 1, sink) / 1e9);
+    printf("  shoup mul (fixed multiplier) CH=2: %.2f G mulmod/s\n", run(k_mul<Fq, 2, 5>, blocks, 1024, 2, sink) / 1e9);
+    printf("  butterfly, Montgomery product: %.2f G butterflies/s\n", run(k_bfly<Fq, 0>, blocks, 2048, 1, sink) / 1e9);
+    printf("  butterfly, Shoup product:      %.2f G butterflies/s\n", run(k_bfly<Fq, 1>, blocks, 2048, 1, sink) / 1e9);
     printf("  integer sqr (36 + 72 wide)  CH=1: %.2f G mulmod/s\n", run(k_mul<Fq, 1, 4>, blocks, 2048, 1, sink) / 1e9);
     printf("  integer sqr (36 + 72 wide)  CH=2: %.2f G mulmod/s\n", run(k_mul<Fq, 2, 4>, blocks, 1024, 2, sink) / 1e9);
   }

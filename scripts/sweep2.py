@@ -1,7 +1,7 @@
 """Round-2 sweep k = 16..26 on ONE GPU (BASELINE.json configs[1], [2]), every number with its roofline fraction.
 
   MSM   uniform + witness-like scalars: ms, Mpts/s, the accumulation kernel's share, fraction of the IMAD.WIDE peak
-        (algorithmic n*W*11*136 as SURVEY.md 8d defines it, and the 10*130 wide multiplies actually issued).
+        (algorithmic n*W*11*136 as SURVEY.md 8d defines it, and the 1160 wide multiplies per mixed addition actually issued).
   NTT   best_fft / lagrange_to_coeff / coeff_to_extended / extended_to_coeff (j = 5): ms, Melem/s, per-pass ms, HBM GB/s
         per pass against the measured peak, integer fraction ((n/2) log2 n * 136 multiplies).
   x64   the 64-column batches of configs[2] at EVERY k: inputs device-resident (64 * n * 32 B, 128 GiB at k = 26), the
@@ -21,12 +21,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import halo2_pse_b200 as h  # noqa: E402
 
 ks = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else list(range(16, 27, 2))
-out_path = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/r2_sweep_1gpu.json"
+out_path = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/r2b_sweep_1gpu.json"
 HOST_K_MAX = int(os.environ.get("H2B_SWEEP_HOST_K", "20"))
 peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) \
     if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
 HBM = peaks["hbm_gbs"]
 out = {"msm": {}, "ntt": {}, "x64": {}, "peaks": {"hbm_gbs": HBM}}
+# H2B_SWEEP_PARTS=msm re-measures the MSM rows only, on top of an earlier sweep file (H2B_SWEEP_BASE): the transform
+# rows of that file stay valid as long as csrc/ntt.cu has not changed since
+PARTS = os.environ.get("H2B_SWEEP_PARTS", "msm,ntt,x64").split(",")
+if os.environ.get("H2B_SWEEP_BASE"):
+    out = json.load(open(os.environ["H2B_SWEEP_BASE"]))
+    out["note"] = "msm rows re-measured after the late-round-2 MSM changes; ntt / x64 rows from the earlier round-2 sweep (csrc/ntt.cu unchanged)"
 
 
 def best(ctx, fn, reps=3):
@@ -49,6 +55,8 @@ ctx.close()
 
 for k in ks:
     n = 1 << k
+    if "msm" not in PARTS:
+        break
     # ---------------- MSM (its own context: the workspace is released before the transforms) ----------------
     ctx = h.Context(0)
     bases = ctx.synth_bases(n, 0x6B7A67).precompute()
@@ -70,15 +78,18 @@ for k in ks:
             r.update({"accum_kernel_ms": a_ms, "accum_share": a_ms / (t * 1e3),
                       "roofline_frac": n * W * 11 * 136 / (t) / imad,                     # whole MSM, algorithmic
                       "roofline_frac_accum_kernel": n * W * 11 * 136 / (a_ms * 1e-3) / imad,
-                      "roofline_frac_executed_accum_kernel": n * W * 10 * 130 / (a_ms * 1e-3) / imad,
+                      "roofline_frac_executed_accum_kernel": n * W * 1160 / (a_ms * 1e-3) / imad,
                       "ec_adds_per_s": n * W / t})
         row[name] = r
         sc.free()
     bases.free()
     ctx.close()
-    out["msm"][k] = row
+    out["msm"][str(k)] = row
+    out["msm"].pop(k, None)
     print("msm", k, json.dumps(row), flush=True)
     flush()
+    if "ntt" not in PARTS:
+        continue
 
     # ---------------- single transforms ----------------
     ctx = h.Context(0)

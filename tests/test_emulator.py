@@ -172,6 +172,14 @@ def test_msm_vs_oracle(emu_ctx, oracle_c, n, kind, monkeypatch):
             monkeypatch.setenv("H2B_MSM_BATCH_MIN", str(batch_min))
             assert B.msm(S) == got, batch_min
             assert B.msm(S[:1101], offset=200) == H.g1_dec(oracle_c.best_multiexp(S[:1101], bases[200:1301], 2))[0]
+        # batch sizes: the default geometric plan above, the plan adapted to the measured copy/compute ratio (every call
+        # after the first), and fixed plans
+        monkeypatch.setenv("H2B_MSM_BATCH_MIN", "200")
+        for plan in (None, "1,1,1,1,1,1,1", "5,2,1", "7"):
+            if plan:
+                monkeypatch.setenv("H2B_MSM_BATCH_PLAN", plan)
+            assert B.msm(S) == got, plan
+        monkeypatch.delenv("H2B_MSM_BATCH_PLAN")
         monkeypatch.delenv("H2B_MSM_BATCH_MIN")
     B.free()
 

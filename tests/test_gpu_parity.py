@@ -694,6 +694,12 @@ def test_msm_host_scalars_in_batches(gpu_ctx, kind, monkeypatch):
         pinned = gpu_ctx.pinned((n, 4))
         pinned.array[:] = host
         assert bases.msm(pinned.array) == want, (n, kind)
+        # the batch sizes of the calls above follow the measured copy/compute ratio of the calls before them;
+        # fixed plans: seven equal batches, shrinking batches, a single weight
+        for plan in ("1,1,1,1,1,1,1", "5,2,1", "7"):
+            monkeypatch.setenv("H2B_MSM_BATCH_PLAN", plan)
+            assert bases.msm(pinned.array) == want, (n, kind, plan)
+        monkeypatch.delenv("H2B_MSM_BATCH_PLAN")
         pinned.free()
         dev.free()
         bases.free()
