@@ -828,12 +828,12 @@ static MsmPlan msm_plan(size_t n, uint32_t table_c = 0, uint32_t ncols = 1) {
   p.pairs = (uint64_t)n * p.W * (table_c ? ncols : 1);
   // chunk length of level 0: long enough to amortise the two boundary partials, short enough to
   // keep >= ~64k threads in flight (tuned on B200: k = 16 / 18 / 20 / 24)
-  p.L0 = p.pairs >= (1ull << 25) ? 128 : p.pairs >= (1ull << 23) ? 48 : p.pairs >= (1ull << 21) ? 32 : 16;
+  p.L0 = p.pairs >= (1ull << 25) ? 128 : p.pairs >= (1ull << 23) ? 48 : p.pairs >= (1ull << 21) ? 24 : 16;
   if (const char* e = getenv("H2B_MSM_L0")) {
     const int v = atoi(e);
     if (v >= 2 && v <= 4096) p.L0 = (uint32_t)v;
   }
-  p.LN = 16;
+  p.LN = p.pairs >= (1ull << 26) ? 16 : 8;  // short lists: the serial chain of a chunk is what costs (re-swept late in round 2)
   if (const char* e = getenv("H2B_MSM_LN")) {
     const int v = atoi(e);
     if (v >= 2 && v <= 4096) p.LN = (uint32_t)v;
