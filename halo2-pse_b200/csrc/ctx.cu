@@ -386,6 +386,8 @@ H2B_HD F field_op(int op, const F& a, const F& b) {
     case 4: return to_mont(a);
     case 5: return from_mont(a);
     case 6: return neg(a);
+    case 8: return mul_sub(a, b, add(a, b), sub(a, b));  // a b - (a + b)(a - b), two products on one reduction
+    case 9: return mul_shoup(a, from_mont(b), shoup_companion(b));  // b as a fixed multiplier: = mul(a, b)
     default: return inv(a);
   }
 }
@@ -776,7 +778,7 @@ extern "C" int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const h2b_fr* 
                                  h2b_fr* out, size_t n) {
   if (!ctx) return H2B_ERR_ARG;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-  if (!a || !out || field < 0 || field > 1 || op < 0 || op > 7) return fail(ctx, H2B_ERR_ARG, "bad argument");
+  if (!a || !out || field < 0 || field > 1 || op < 0 || op > 9) return fail(ctx, H2B_ERR_ARG, "bad argument");
   if (n == 0) return H2B_OK;
   return run_elementwise(ctx, n * 32, a, b, out, [&](void* da, void* db, void* dout) {
     return launch(ctx, field_op_kernel, dim3((uint32_t)((n + 127) / 128)), dim3(128), 0, field, op,
@@ -786,7 +788,7 @@ extern "C" int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const h2b_fr* 
 
 extern "C" int h2b_host_field_op(int field, int op, const h2b_fr* a, const h2b_fr* b, h2b_fr* out,
                                  size_t n) {
-  if (!a || !out || field < 0 || field > 1 || op < 0 || op > 7) return H2B_ERR_ARG;
+  if (!a || !out || field < 0 || field > 1 || op < 0 || op > 9) return H2B_ERR_ARG;
   for (size_t i = 0; i < n; ++i) {
     if (field == 0) {
       Fr x, y;

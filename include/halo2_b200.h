@@ -342,7 +342,8 @@ float h2b_ctx_last_kernel_ms(const h2b_ctx* ctx);
 /* durations (ms) of the passes of the last NTT call made in profile mode; returns their number */
 int h2b_ctx_last_ntt_passes(h2b_ctx* ctx, float* ms, int cap);
 /* Element-wise device ops (op: 0 mul, 1 add, 2 sub, 3 sqr, 4 to_mont, 5 from_mont,
- * 6 neg, 7 inv); field: 0 Fr, 1 Fq.  Host pointers. */
+ * 6 neg, 7 inv, 8 mul_sub(a, b, a + b, a - b), 9 mul_shoup with b as the fixed multiplier); field: 0 Fr, 1 Fq.
+ * Host pointers. */
 int h2b_test_field_op(h2b_ctx* ctx, int field, int op, const h2b_fr* a, const h2b_fr* b,
                       h2b_fr* out, size_t n);
 /* Same ops on the host code path of the same header (no device needed). */

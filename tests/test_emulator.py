@@ -28,7 +28,9 @@ def test_host_field_ops_match_big_integers(emu_ctx):
         A, B = H.to_limbs(a, mod), H.to_limbs(b, mod)
         for op, f in ((0, lambda x, y: x * y % mod), (1, lambda x, y: (x + y) % mod),
                       (2, lambda x, y: (x - y) % mod), (3, lambda x, y: x * x % mod),
-                      (6, lambda x, y: -x % mod)):
+                      (6, lambda x, y: -x % mod),
+                      (8, lambda x, y: (x * y - (x + y) * (x - y)) % mod),   # mul_sub: two products, one reduction
+                      (9, lambda x, y: x * y % mod)):                         # mul_shoup: y as a fixed multiplier
             out = np.zeros_like(A)
             assert emu_ctx.lib.h2b_host_field_op(field, op, A.ctypes.data, B.ctypes.data, out.ctypes.data, len(a)) == 0
             assert H.from_limbs(out, mod) == [f(x, y) for x, y in zip(a, b)], (field, op)

@@ -34,7 +34,9 @@ def test_device_field_ops(gpu_ctx):
         A, B = H.to_limbs(a, mod), H.to_limbs(b, mod)
         for op, f in ((0, lambda x, y: x * y % mod), (1, lambda x, y: (x + y) % mod),
                       (2, lambda x, y: (x - y) % mod), (3, lambda x, y: x * x % mod),
-                      (6, lambda x, y: -x % mod)):
+                      (6, lambda x, y: -x % mod),
+                      (8, lambda x, y: (x * y - (x + y) * (x - y)) % mod),   # mul_sub: two products, one reduction
+                      (9, lambda x, y: x * y % mod)):                         # mul_shoup: y as a fixed multiplier
             out = np.zeros_like(A)
             gpu_ctx._check(gpu_ctx.lib.h2b_test_field_op(gpu_ctx.h, field, op, A.ctypes.data, B.ctypes.data,
                                                          out.ctypes.data, len(a)))
