@@ -14,8 +14,8 @@ for k in [int(a) for a in sys.argv[1:]] or [16, 20]:
     dev = ctx.synth_scalars(n, 1, 0)
     want = bases.msm(dev, n)
     res = []
-    for ln in (8, 16, 32):
-        for l0 in (0, 16, 24, 32, 48, 64, 96, 128, 192):
+    for ln in [int(x) for x in os.environ.get("LNS", "8,16,32").split(",")]:
+        for l0 in [int(x) for x in os.environ.get("L0S", "0,16,24,32,48,64,96,128,192").split(",")]:
             os.environ["H2B_MSM_LN"] = str(ln)
             if l0:
                 os.environ["H2B_MSM_L0"] = str(l0)
