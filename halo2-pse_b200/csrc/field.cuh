@@ -477,8 +477,8 @@ H2B_HD Fp<P> dbl(const Fp<P>& a) {
   return add(a, a);
 }
 
-// Montgomery product a*b/R mod p.
-template <class P>
+// Montgomery product a*b/R mod p.  REDUCE = false leaves the result below 2p (lazy residues, see add_lazy).
+template <class P, bool REDUCE = true>
 H2B_HD Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
   // A[s][c]: absolute column c of the accumulator collecting the products
   // a_j*b_i (and m_i*p_j) with (i + j) & 1 == s.
@@ -518,7 +518,7 @@ H2B_HD Fp<P> mul(const Fp<P>& a, const Fp<P>& b) {
   }
   Fp<P> r;
   add8_seed(r.v, &A[0][8], &A[1][8], A[0][7], A[1][7]);
-  reduce_once(r);
+  if (REDUCE) reduce_once(r);
   return r;
 }
 
@@ -699,7 +699,8 @@ H2B_HD void mul_high8(uint32_t* q, const uint32_t* x, const uint32_t* y) {
 }
 
 // x * w mod p, given w (plain, < p) and wp = floor(w * 2^256 / p)
-template <class P>
+// FULL = false: one conditional subtraction only, the result is below 2p for any x < 4p (lazy residues)
+template <class P, bool FULL = true>
 H2B_HD Fp<P> mul_shoup(const Fp<P>& x, const Fp<P>& w, const Fp<P>& wp) {
   uint32_t q[8], lo[8], qp[8], pm[8];
 #pragma unroll
@@ -708,10 +709,54 @@ H2B_HD Fp<P> mul_shoup(const Fp<P>& x, const Fp<P>& w, const Fp<P>& wp) {
   mul_low8(lo, x.v, w.v);
   mul_low8(qp, q, pm);
   Fp<P> r;
-  sub8(r.v, lo, qp);  // exact: the true difference is below 3p < 2^256
+  sub8(r.v, lo, qp);  // exact: the true difference is below p (2 + x / 2^256) < 3p < 2^256
   reduce_once(r);
-  reduce_once(r);
+  if (FULL) reduce_once(r);
   return r;
+}
+
+// ---------------------------------------------------------------------------
+// Lazy residues: values kept in [0, 2p) (4p < 2^256 leaves the room).  The transforms run on them inside and between
+// their passes and reduce once at the very end: a product then needs no final subtraction at all (Montgomery: inputs
+// below 2p and p give (2p*p + R*p)/R < 1.38p) or one instead of two (Shoup), and additions / subtractions cost what
+// they cost on canonical residues.
+// ---------------------------------------------------------------------------
+template <class P>
+H2B_HD constexpr uint32_t mod2(int i) {  // limb i of 2p
+  return (P::mod(i) << 1) | (i ? P::mod(i - 1) >> 31 : 0u);
+}
+
+// a + b for a, b in [0, 2p): result in [0, 2p)
+template <class P>
+H2B_HD Fp<P> add_lazy(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  add8(r.v, a.v, b.v);  // below 4p < 2^256
+  uint32_t m[8], t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = mod2<P>(i);
+  const uint32_t borrow = sub8(t, r.v, m);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = borrow ? r.v[i] : t[i];
+  return r;
+}
+
+// a - b for a, b in [0, 2p): result in [0, 2p)
+template <class P>
+H2B_HD Fp<P> sub_lazy(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  const uint32_t mask = sub8(r.v, a.v, b.v);
+  uint32_t m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = mod2<P>(i) & mask;
+  add8(r.v, r.v, m);
+  return r;
+}
+
+// [0, 2p) -> [0, p)
+template <class P>
+H2B_HD Fp<P> canon(Fp<P> a) {
+  reduce_once(a);
+  return a;
 }
 
 // wp = floor(w * 2^256 / p) for a plain w < p, from its Montgomery form wm = w * 2^256 mod p:

@@ -50,6 +50,9 @@ struct PassParams {
   // stores of a warp into the transposed matrix on a peer are runs of il * 32 contiguous bytes instead of isolated
   // 32-byte words (the run dimension of the destination is the row = batch member).
   uint32_t il_out, il_in;
+  // lazy_out: this pass and the next one both run on the register kernel, which computes on lazy residues ([0, 2p),
+  // field.cuh): the scratch between them keeps the unreduced values, the last pass reduces once
+  uint32_t lazy_out;
   uint32_t s1;                       // log2 R_1
   uint32_t nmid;                     // number of middle digits (s_2 .. s_(P-1))
   uint32_t mid_s[4];                 // their widths, s_2 first
@@ -151,6 +154,8 @@ __device__ __noinline__ Fr mul_tw(Fr a, Fr b) { return mul(a, b); }
 #else
 H2B_D Fr mul_tw(const Fr& a, const Fr& b) { return mul(a, b); }
 #endif
+// the same without the final subtraction: a below 2p, b canonical -> below 1.38p
+H2B_D Fr mul_tw_lazy(const Fr& a, const Fr& b) { return mul<FrParams, false>(a, b); }
 
 template <bool PRE>
 H2B_D Fr load_in_t(const PassParams& p, const Fr* in, uint64_t gi) {
@@ -167,12 +172,12 @@ H2B_D void store_out_t(const PassParams& p, Fr* out, const Tile& g, uint32_t K, 
   if (KIND == KIND_LAST_PEER) {
     const uint64_t Ko = g.out_base + (uint64_t)K * g.out_rs + c * g.out_cm;
     const uint64_t row = p.sc_row0 + bidx;
-    if (p.sc_lo) {
+    if (p.sc_lo && row * Ko) {
       const uint64_t e = row * Ko;
-      if (e) {
-        x = mul_tw(x, ld_fp_nc(p.sc_lo + (uint32_t)(e & ((1ull << p.sc_h) - 1))));
-        x = mul_tw(x, ld_fp_nc(p.sc_hi + (uint32_t)(e >> p.sc_h)));
-      }
+      x = mul_tw_lazy(x, ld_fp_nc(p.sc_lo + (uint32_t)(e & ((1ull << p.sc_h) - 1))));
+      x = mul_tw(x, ld_fp_nc(p.sc_hi + (uint32_t)(e >> p.sc_h)));
+    } else {
+      x = canon(x);  // the register kernel hands over lazy residues
     }
     const uint32_t h = (uint32_t)(Ko / p.sc_cl);
     st_fp(p.sc_peers.p[h] + (Ko - (uint64_t)h * p.sc_cl) * p.sc_R + row, x);
@@ -180,7 +185,10 @@ H2B_D void store_out_t(const PassParams& p, Fr* out, const Tile& g, uint32_t K, 
   }
   if (KIND == KIND_LAST) {
     const uint64_t Ko = g.out_base + (uint64_t)K * g.out_rs + c * g.out_cm;
-    if (p.post) x = mul_tw(x, ld_fp_nc(p.post + (uint32_t)Ko % p.post_mod));
+    if (p.post)
+      x = mul_tw(x, ld_fp_nc(p.post + (uint32_t)Ko % p.post_mod));
+    else
+      x = canon(x);  // the register kernel hands over lazy residues
     if (Ko < p.n_out) st_fp(out + Ko, x);
     return;
   }
@@ -188,17 +196,18 @@ H2B_D void store_out_t(const PassParams& p, Fr* out, const Tile& g, uint32_t K, 
   Fr* dst = out + o;
   if (p.il_out) dst = p.out + ((bidx / p.il_out) * p.out_bstride + o) * p.il_out + bidx % p.il_out;
   if (KIND == KIND_OUT_TABLE) {
-    x = mul_tw(x, ld_fp_nc(p.tw_out + o));
+    x = mul_tw_lazy(x, ld_fp_nc(p.tw_out + o));
   } else if (KIND == KIND_MID_TABLE) {
     const uint64_t idx = ((g.jr0 + c) * (uint64_t)K) << p.tw1_shift;
-    x = mul_tw(x, ld_fp_nc(p.tw1 + idx));
+    x = mul_tw_lazy(x, ld_fp_nc(p.tw1 + idx));
   } else {
     const uint64_t e = ((g.jr0 + c) * (uint64_t)K) << (p.k - p.lm);
     const uint32_t elo = (uint32_t)e & ((1u << p.h) - 1u);
     const uint32_t ehi = (uint32_t)(e >> p.h);
-    x = mul_tw(x, ld_fp_nc(p.tw_lo + elo));
-    x = mul_tw(x, ld_fp_nc(p.tw_hi + ehi));
+    x = mul_tw_lazy(x, ld_fp_nc(p.tw_lo + elo));
+    x = mul_tw_lazy(x, ld_fp_nc(p.tw_hi + ehi));
   }
+  if (!p.lazy_out) x = canon(x);  // the next pass is the generic kernel (canonical residues only)
   st_fp(dst, x);
 }
 
@@ -267,36 +276,37 @@ __global__ void __launch_bounds__(256) ntt_pass_generic(PassParams p) {
 // ---------------------------------------------------------------------------
 // 8-point DFT, natural order in and out: x[K] <- sum_a x[a] * w8^(a*K).
 // w8 = rt[N/8], w4 = rt[N/4], w8^3 = rt[3N/8] with N = 2^rt_log.
-// x * rts-root number i (a table constant: Shoup product)
+// x * rts-root number i (a table constant: Shoup product), lazy residues in and out
 H2B_D Fr mul_root(const Fr& x, const Fr* rts, uint32_t i) {
-  return mul_shoup(x, ld_fp_nc(rts + 2 * i), ld_fp_nc(rts + 2 * i + 1));
+  return mul_shoup<FrParams, false>(x, ld_fp_nc(rts + 2 * i), ld_fp_nc(rts + 2 * i + 1));
 }
 
+// 8-point DFT on lazy residues ([0, 2p) in and out)
 H2B_D void dft8(Fr* x, const Fr* rts, uint32_t rt_log) {
-  Fr s0 = add(x[0], x[4]), d0 = sub(x[0], x[4]);
-  Fr s1 = add(x[1], x[5]), d1 = sub(x[1], x[5]);
-  Fr s2 = add(x[2], x[6]), d2 = sub(x[2], x[6]);
-  Fr s3 = add(x[3], x[7]), d3 = sub(x[3], x[7]);
+  Fr s0 = add_lazy(x[0], x[4]), d0 = sub_lazy(x[0], x[4]);
+  Fr s1 = add_lazy(x[1], x[5]), d1 = sub_lazy(x[1], x[5]);
+  Fr s2 = add_lazy(x[2], x[6]), d2 = sub_lazy(x[2], x[6]);
+  Fr s3 = add_lazy(x[3], x[7]), d3 = sub_lazy(x[3], x[7]);
   const uint32_t i4 = 1u << (rt_log - 2);
   const Fr w4 = ld_fp_nc(rts + 2 * i4), w4s = ld_fp_nc(rts + 2 * i4 + 1);
   d1 = mul_root(d1, rts, 1u << (rt_log - 3));
-  d2 = mul_shoup(d2, w4, w4s);
+  d2 = mul_shoup<FrParams, false>(d2, w4, w4s);
   d3 = mul_root(d3, rts, 3u << (rt_log - 3));
   // even outputs from s, odd outputs from d
-  Fr e0 = add(s0, s2), f0 = sub(s0, s2);
-  Fr e1 = add(s1, s3), f1 = mul_shoup(sub(s1, s3), w4, w4s);
-  x[0] = add(e0, e1);
-  x[4] = sub(e0, e1);
-  x[2] = add(f0, f1);
-  x[6] = sub(f0, f1);
-  e0 = add(d0, d2);
-  f0 = sub(d0, d2);
-  e1 = add(d1, d3);
-  f1 = mul_shoup(sub(d1, d3), w4, w4s);
-  x[1] = add(e0, e1);
-  x[5] = sub(e0, e1);
-  x[3] = add(f0, f1);
-  x[7] = sub(f0, f1);
+  Fr e0 = add_lazy(s0, s2), f0 = sub_lazy(s0, s2);
+  Fr e1 = add_lazy(s1, s3), f1 = mul_shoup<FrParams, false>(sub_lazy(s1, s3), w4, w4s);
+  x[0] = add_lazy(e0, e1);
+  x[4] = sub_lazy(e0, e1);
+  x[2] = add_lazy(f0, f1);
+  x[6] = sub_lazy(f0, f1);
+  e0 = add_lazy(d0, d2);
+  f0 = sub_lazy(d0, d2);
+  e1 = add_lazy(d1, d3);
+  f1 = mul_shoup<FrParams, false>(sub_lazy(d1, d3), w4, w4s);
+  x[1] = add_lazy(e0, e1);
+  x[5] = sub_lazy(e0, e1);
+  x[3] = add_lazy(f0, f1);
+  x[7] = sub_lazy(f0, f1);
 }
 
 template <int S, int KIND, bool PRE>
@@ -379,12 +389,12 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
     for (int i = 0; i < 2; ++i) {
       const uint32_t gq = u + 32 * i;
       Fr v0 = get(gq * 4 + 0), v1 = get(gq * 4 + 1), v2 = get(gq * 4 + 2), v3 = get(gq * 4 + 3);
-      Fr t0 = add(v0, v2), t1 = sub(v0, v2), t2 = add(v1, v3), t3 = mul_shoup(sub(v1, v3), w4, w4s);
+      Fr t0 = add_lazy(v0, v2), t1 = sub_lazy(v0, v2), t2 = add_lazy(v1, v3), t3 = mul_shoup<FrParams, false>(sub_lazy(v1, v3), w4, w4s);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
-      store_out_t<KIND>(p, out, g, K0, c, add(t0, t2), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 64, c, add(t1, t3), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 128, c, sub(t0, t2), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 192, c, sub(t1, t3), bidx);
+      store_out_t<KIND>(p, out, g, K0, c, add_lazy(t0, t2), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 64, c, add_lazy(t1, t3), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 128, c, sub_lazy(t0, t2), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 192, c, sub_lazy(t1, t3), bidx);
     }
   } else {
 #pragma unroll
@@ -392,8 +402,8 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
       const uint32_t gq = u + 16 * i;
       Fr v0 = get(gq * 2 + 0), v1 = get(gq * 2 + 1);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
-      store_out_t<KIND>(p, out, g, K0, c, add(v0, v1), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 64, c, sub(v0, v1), bidx);
+      store_out_t<KIND>(p, out, g, K0, c, add_lazy(v0, v1), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 64, c, sub_lazy(v0, v1), bidx);
     }
   }
 }
@@ -707,6 +717,29 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
   for (uint32_t b0 = 0; b0 < batch; b0 += group) {
     const uint32_t nb = (batch - b0 < group) ? batch - b0 : group;
     uint32_t lm = k;
+    // which passes run on the register kernel (the rule of the loop below, evaluated ahead: a pass hands lazy residues
+    // to the next one only if both do)
+    bool fastv[5] = {false, false, false, false, false};
+    {
+      const uint32_t ilq = (sc && P >= 2 && s[P - 1] >= 6 && s[P - 1] <= 9 && nb % (1u << (11 - s[P - 1])) == 0 &&
+                            getenv("H2B_NTT_NO_IL") == nullptr)
+                               ? 1u << (11 - s[P - 1])
+                               : 0u;
+      uint32_t lmq = k;
+      for (int pi = 0; pi < P; ++pi) {
+        const bool lastq = pi == P - 1, singleq = P == 1;
+        const uint32_t lcq = 11 - s[pi];
+        const uint32_t availq = singleq ? 0 : (lastq ? s[0] : lmq - s[pi]);
+        bool f = !singleq && s[pi] >= 6 && s[pi] <= 9 && lcq <= availq;
+        if (singleq && s[pi] >= 6 && s[pi] <= 9 && nb >= (1u << lcq) && nb % (1u << lcq) == 0 &&
+            getenv("H2B_NTT_NO_SB") == nullptr)
+          f = true;
+        else if (ilq && lastq)
+          f = true;
+        fastv[pi] = f;
+        lmq -= s[pi];
+      }
+    }
     for (int pi = 0; pi < P; ++pi) {
       PassParams p;
       p.k = k;
@@ -717,6 +750,7 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
       p.single = P == 1;
       p.sb = 0;
       p.il_out = p.il_in = 0;
+      p.lazy_out = (pi + 1 < P && fastv[pi] && fastv[pi + 1] && getenv("H2B_NTT_NO_LAZY") == nullptr) ? 1u : 0u;
       p.s1 = s[0];
       p.nmid = 0;
       for (int i = 1; i + 1 < P; ++i) p.mid_s[p.nmid++] = s[i];
@@ -794,6 +828,7 @@ int ntt_run(h2b_ctx* ctx, const Fr* d_in, Fr* d_out, uint32_t k, const TwTable* 
         lc = avail;
       }
       p.lc = lc;
+      if (fast != fastv[pi]) return fail(ctx, H2B_ERR_ARG, "internal: NTT pass plan mismatch");  // lazy_out relies on it
       const uint32_t tiles = sb ? nb >> (11 - p.s) : (uint32_t)(n >> (p.s + lc));
       const dim3 grid(tiles, sb ? 1u : p.il_in ? nb / p.il_in : nb);
       const bool prof = ctx->profile && b0 == 0 && pi < 5;
