@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   auto slot = [&](uint32_t pos) -> uint32_t {
     return ((pos ^ ((pos >> LM2) & (M2 - 1))) << LC) + c;
   };
+#ifdef H2B_NTT_SMEM_PLANES
   auto put = [&](uint32_t pos, const Fr& v) {
     const uint32_t w = slot(pos);
 #pragma unroll
@@ -340,8 +341,32 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
     for (int l = 0; l < 8; ++l) v.v[l] = sm[l * PLANE + w];
     return v;
   };
+#else
+  // an element = two 16-byte words (4 shared-memory accesses per exchange instead of 16); a 128-bit access is served
+  // per quarter-warp = 8 consecutive columns, 32 bytes apart: the halves swap on bit 2 of the element index, so that
+  // the eight 16-byte words land on all 32 banks
+  uint4* sm4 = reinterpret_cast<uint4*>(sm);
+  auto put = [&](uint32_t pos, const Fr& v) {
+    const uint32_t w = slot(pos), hs = (w >> 2) & 1u;
+    sm4[2 * w + hs] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    sm4[2 * w + (hs ^ 1u)] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+  };
+  auto get = [&](uint32_t pos) -> Fr {
+    const uint32_t w = slot(pos), hs = (w >> 2) & 1u;
+    const uint4 a = sm4[2 * w + hs], b = sm4[2 * w + (hs ^ 1u)];
+    Fr v;
+    v.v[0] = a.x; v.v[1] = a.y; v.v[2] = a.z; v.v[3] = a.w;
+    v.v[4] = b.x; v.v[5] = b.y; v.v[6] = b.z; v.v[7] = b.w;
+    return v;
+  };
+#endif
 
   Fr x[8];
+  // Two forms of the same rounds.  Measured on B200 (k = 24 / 26): the looped form is faster for the passes that are
+  // not the last one at S <= 8 (1.26 -> 1.22, 1.23 -> 1.22 ms), slower for last passes (0.94 -> 0.99) and for S = 9
+  // (three looped rounds spill 200 bytes): each pass kind takes its better form.
+  constexpr bool LOOPED = S <= 8 && KIND != KIND_LAST && KIND != KIND_LAST_PEER;
+  if constexpr (!LOOPED) {
   // round 1: b = u, elements a*T + u
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
@@ -406,6 +431,80 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
       store_out_t<KIND>(p, out, g, K0 + 64, c, sub_lazy(v0, v1), bidx);
     }
   }
+  } else {
+  // The radix-8 rounds share ONE copy of their code (a loop that is not unrolled): the kernel is straight-line
+  // multi-precision arithmetic, ~10 k instructions when every round is inlined, and ncu showed 0.7 - 1.0 stall cycles
+  // per issue on instruction fetch.  Round r works in place on the shared-memory positions base + j * stride:
+  //   round 0: elements j*T + u (from global memory), twiddles w_R^(u j);
+  //   round 1: (Ka, b2) = (u / M2, u % M2), elements Ka*T + j*M2 + b2, twiddles w_R^(8 b2 j);
+  //   round 2 (S = 9 only): elements 8u + j, no twiddles: straight to the output.
+  const uint32_t Ka = u >> LM2, b2 = u & (M2 - 1);
+  constexpr int NR8 = M2 == 8 ? 3 : 2;  // radix-8 rounds
+  uint32_t base = u, stride = T, e = u;
+#pragma unroll 1
+  for (int round = 0; round < NR8; ++round) {
+    if (round == 0) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const uint32_t row = a * T + u;
+        if (KIND == KIND_LAST_PEER && p.il_in)  // interleaved scratch: C batch members side by side
+          x[a] = ld_fp(p.in + ((uint64_t)blockIdx.y * p.in_bstride + g.in_base + row * g.in_rs) * C + c);
+        else
+          x[a] = load_in_t<PRE>(p, in, g.in_base + row * g.in_rs + c * g.in_cs);
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 8; ++a) x[a] = get(base + a * stride);
+    }
+    dft8(x, p.rts, p.rt_log);
+    if (round == NR8 - 1 && (M2 == 1 || M2 == 8)) break;  // the last radix-8 round of S = 6 and S = 9 feeds the output
+#pragma unroll
+    for (int j = 1; j < 8; ++j) x[j] = mul_root(x[j], p.rts, (e * j) << rsh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) put(base + j * stride, x[j]);
+    __syncthreads();
+    if (round == 0) {
+      base = Ka * T + b2;
+      stride = M2;
+      e = 8 * b2;
+    } else {
+      base = u * 8;
+      stride = 1;
+    }
+  }
+  if (M2 == 1) {
+#pragma unroll
+    for (int Ka2 = 0; Ka2 < 8; ++Ka2) store_out_t<KIND>(p, out, g, Ka + 8 * Ka2, c, x[Ka2], bidx);
+  } else if (M2 == 8) {
+    const uint32_t K0 = (u >> 3) + 8 * (u & 7);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) store_out_t<KIND>(p, out, g, K0 + 64 * i, c, x[i], bidx);
+  } else if (M2 == 4) {
+    const uint32_t i4 = 1u << (p.rt_log - 2);
+    const Fr w4 = ld_fp_nc(p.rts + 2 * i4), w4s = ld_fp_nc(p.rts + 2 * i4 + 1);
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t gq = u + 32 * i;
+      Fr v0 = get(gq * 4 + 0), v1 = get(gq * 4 + 1), v2 = get(gq * 4 + 2), v3 = get(gq * 4 + 3);
+      Fr t0 = add_lazy(v0, v2), t1 = sub_lazy(v0, v2), t2 = add_lazy(v1, v3),
+         t3 = mul_shoup<FrParams, false>(sub_lazy(v1, v3), w4, w4s);
+      const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
+      store_out_t<KIND>(p, out, g, K0, c, add_lazy(t0, t2), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 64, c, add_lazy(t1, t3), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 128, c, sub_lazy(t0, t2), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 192, c, sub_lazy(t1, t3), bidx);
+    }
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t gq = u + 16 * i;
+      Fr v0 = get(gq * 2 + 0), v1 = get(gq * 2 + 1);
+      const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
+      store_out_t<KIND>(p, out, g, K0, c, add_lazy(v0, v1), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 64, c, sub_lazy(v0, v1), bidx);
+    }
+  }
+  }  // LOOPED
 }
 
 // ---------------------------------------------------------------------------
