@@ -32,7 +32,7 @@ out = {"msm": {}, "ntt": {}, "x64": {}, "peaks": {"hbm_gbs": HBM}}
 PARTS = os.environ.get("H2B_SWEEP_PARTS", "msm,ntt,x64").split(",")
 if os.environ.get("H2B_SWEEP_BASE"):
     out = json.load(open(os.environ["H2B_SWEEP_BASE"]))
-    out["note"] = "msm rows re-measured after the late-round-2 MSM changes; ntt / x64 rows from the earlier round-2 sweep (csrc/ntt.cu unchanged)"
+    out.setdefault("notes", []).append("rows of " + ",".join(PARTS) + " at k = " + ",".join(str(x) for x in ks) + " re-measured on top of " + os.environ["H2B_SWEEP_BASE"])
 
 
 def best(ctx, fn, reps=3):
@@ -55,39 +55,38 @@ ctx.close()
 
 for k in ks:
     n = 1 << k
-    if "msm" not in PARTS:
-        break
-    # ---------------- MSM (its own context: the workspace is released before the transforms) ----------------
-    ctx = h.Context(0)
-    bases = ctx.synth_bases(n, 0x6B7A67).precompute()
-    c = bases.table_window_bits
-    W = (255 + c - 1) // c
-    row = {"window_bits": c, "windows": W}
-    for kind, name in ((0, "uniform"), (1, "all_equal"), (2, "zero_one"), (3, "16bit"), (4, "90pct_zero")):
-        sc = ctx.synth_scalars(n, 5, kind)
-        t = best(ctx, lambda: bases.msm(sc, n=n))
-        r = {"ms": t * 1e3, "mpts_s": n / t / 1e6}
-        if kind == 0:
-            ctx.set_profile(True)
-            acc = []
-            for _ in range(3):
-                bases.msm(sc, n=n)
-                acc.append(ctx.last_kernel_ms())
-            ctx.set_profile(False)
-            a_ms = sorted(acc)[1]
-            r.update({"accum_kernel_ms": a_ms, "accum_share": a_ms / (t * 1e3),
-                      "roofline_frac": n * W * 11 * 136 / (t) / imad,                     # whole MSM, algorithmic
-                      "roofline_frac_accum_kernel": n * W * 11 * 136 / (a_ms * 1e-3) / imad,
-                      "roofline_frac_executed_accum_kernel": n * W * 1160 / (a_ms * 1e-3) / imad,
-                      "ec_adds_per_s": n * W / t})
-        row[name] = r
-        sc.free()
-    bases.free()
-    ctx.close()
-    out["msm"][str(k)] = row
-    out["msm"].pop(k, None)
-    print("msm", k, json.dumps(row), flush=True)
-    flush()
+    if "msm" in PARTS:
+        # ---------------- MSM (its own context: the workspace is released before the transforms) ----------------
+        ctx = h.Context(0)
+        bases = ctx.synth_bases(n, 0x6B7A67).precompute()
+        c = bases.table_window_bits
+        W = (255 + c - 1) // c
+        row = {"window_bits": c, "windows": W}
+        for kind, name in ((0, "uniform"), (1, "all_equal"), (2, "zero_one"), (3, "16bit"), (4, "90pct_zero")):
+            sc = ctx.synth_scalars(n, 5, kind)
+            t = best(ctx, lambda: bases.msm(sc, n=n))
+            r = {"ms": t * 1e3, "mpts_s": n / t / 1e6}
+            if kind == 0:
+                ctx.set_profile(True)
+                acc = []
+                for _ in range(3):
+                    bases.msm(sc, n=n)
+                    acc.append(ctx.last_kernel_ms())
+                ctx.set_profile(False)
+                a_ms = sorted(acc)[1]
+                r.update({"accum_kernel_ms": a_ms, "accum_share": a_ms / (t * 1e3),
+                          "roofline_frac": n * W * 11 * 136 / (t) / imad,                     # whole MSM, algorithmic
+                          "roofline_frac_accum_kernel": n * W * 11 * 136 / (a_ms * 1e-3) / imad,
+                          "roofline_frac_executed_accum_kernel": n * W * 1160 / (a_ms * 1e-3) / imad,
+                          "ec_adds_per_s": n * W / t})
+            row[name] = r
+            sc.free()
+        bases.free()
+        ctx.close()
+        out["msm"][str(k)] = row
+        out["msm"].pop(k, None)
+        print("msm", k, json.dumps(row), flush=True)
+        flush()
     if "ntt" not in PARTS:
         continue
 
@@ -124,7 +123,7 @@ for k in ks:
     timed("extended_to_coeff", lambda: dom.extended_to_coeff_device(ext, q, divide_by_vanishing=True), ek, ne, "melem_s_in")
     for x in (a, ext, q):
         x.free()
-    out["ntt"][k] = r
+    out["ntt"][str(k)] = r
     print("ntt", k, json.dumps(r), flush=True)
     flush()
 
@@ -176,7 +175,7 @@ for k in ks:
             x["host_error"] = str(e)[:300]
     dom.free()
     ctx.close()
-    out["x64"][k] = x
+    out["x64"][str(k)] = x
     print("x64", k, json.dumps(x), flush=True)
     flush()
 print("wrote", out_path)
