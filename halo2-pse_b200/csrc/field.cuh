@@ -752,6 +752,19 @@ H2B_HD Fp<P> sub_lazy(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// a - b + 2p for a, b in [0, 2p): in (0, 4p), NOT brought back below 2p -- for a difference that goes straight into a
+// Shoup product (which takes any operand below 4p and returns a lazy residue)
+template <class P>
+H2B_HD Fp<P> sub_wide(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  sub8(r.v, a.v, b.v);  // modulo 2^256; the true value a - b + 2p is positive and below 4p < 2^256
+  uint32_t m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = mod2<P>(i);
+  add8(r.v, r.v, m);
+  return r;
+}
+
 // [0, 2p) -> [0, p)
 template <class P>
 H2B_HD Fp<P> canon(Fp<P> a) {
