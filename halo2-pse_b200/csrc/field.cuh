@@ -752,6 +752,14 @@ H2B_HD Fp<P> sub_lazy(const Fp<P>& a, const Fp<P>& b) {
   return r;
 }
 
+// a + b for a, b in [0, 2p), NOT brought back below 2p (below 4p): for a sum that goes straight into a product
+template <class P>
+H2B_HD Fp<P> add_wide(const Fp<P>& a, const Fp<P>& b) {
+  Fp<P> r;
+  add8(r.v, a.v, b.v);
+  return r;
+}
+
 // a - b + 2p for a, b in [0, 2p): in (0, 4p), NOT brought back below 2p -- for a difference that goes straight into a
 // Shoup product (which takes any operand below 4p and returns a lazy residue)
 template <class P>

@@ -281,7 +281,20 @@ H2B_D Fr mul_root(const Fr& x, const Fr* rts, uint32_t i) {
   return mul_shoup<FrParams, false>(x, ld_fp_nc(rts + 2 * i), ld_fp_nc(rts + 2 * i + 1));
 }
 
-// 8-point DFT on lazy residues ([0, 2p) in and out)
+// a + b / a - b whose only consumer is a product (Shoup with any multiplier, Montgomery with a canonical one: both take
+// an operand below 4p and return a lazy residue): W leaves them uncorrected
+template <bool W>
+H2B_D Fr addw(const Fr& a, const Fr& b) {
+  return W ? add_wide(a, b) : add_lazy(a, b);
+}
+template <bool W>
+H2B_D Fr subw(const Fr& a, const Fr& b) {
+  return W ? sub_wide(a, b) : sub_lazy(a, b);
+}
+
+// 8-point DFT on lazy residues ([0, 2p) in; out: x[0] in [0, 2p), x[1..7] below 4p if WIDE -- every one of them is
+// multiplied by a twiddle next -- else in [0, 2p))
+template <bool WIDE>
 H2B_D void dft8(Fr* x, const Fr* rts, uint32_t rt_log) {
   // differences that feed a Shoup product directly stay uncorrected (sub_wide: below 4p)
   Fr s0 = add_lazy(x[0], x[4]), d0 = sub_lazy(x[0], x[4]);
@@ -297,17 +310,17 @@ H2B_D void dft8(Fr* x, const Fr* rts, uint32_t rt_log) {
   Fr e0 = add_lazy(s0, s2), f0 = sub_lazy(s0, s2);
   Fr e1 = add_lazy(s1, s3), f1 = mul_shoup<FrParams, false>(sub_wide(s1, s3), w4, w4s);
   x[0] = add_lazy(e0, e1);
-  x[4] = sub_lazy(e0, e1);
-  x[2] = add_lazy(f0, f1);
-  x[6] = sub_lazy(f0, f1);
+  x[4] = subw<WIDE>(e0, e1);
+  x[2] = addw<WIDE>(f0, f1);
+  x[6] = subw<WIDE>(f0, f1);
   e0 = add_lazy(d0, d2);
   f0 = sub_lazy(d0, d2);
   e1 = add_lazy(d1, d3);
   f1 = mul_shoup<FrParams, false>(sub_wide(d1, d3), w4, w4s);
-  x[1] = add_lazy(e0, e1);
-  x[5] = sub_lazy(e0, e1);
-  x[3] = add_lazy(f0, f1);
-  x[7] = sub_lazy(f0, f1);
+  x[1] = addw<WIDE>(e0, e1);
+  x[5] = subw<WIDE>(e0, e1);
+  x[3] = addw<WIDE>(f0, f1);
+  x[7] = subw<WIDE>(f0, f1);
 }
 
 template <int S, int KIND, bool PRE>
@@ -377,7 +390,11 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   // Two forms of the same rounds.  Measured on B200 (k = 24 / 26): the looped form is faster for the passes that are
   // not the last one at S <= 8 (1.26 -> 1.22, 1.23 -> 1.22 ms), slower for last passes (0.94 -> 0.99) and for S = 9
   // (three looped rounds spill 200 bytes): each pass kind takes its better form.
-  constexpr bool LOOPED = S <= 8 && KIND != KIND_LAST && KIND != KIND_LAST_PEER;
+  constexpr bool LASTK = KIND == KIND_LAST || KIND == KIND_LAST_PEER;
+  constexpr bool LOOPED = S <= 8 && !LASTK;
+  // outputs that a twiddle product consumes next may stay below 4p (dft8<true>, addw / subw<true>): every output of a
+  // round that is followed by intra-pass twiddles, and every output of a pass that is not the last one
+  constexpr bool WOUT = !LASTK;
   if constexpr (!LOOPED) {
   // round 1: b = u, elements a*T + u
 #pragma unroll
@@ -388,7 +405,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
     else
       x[a] = load_in_t<PRE>(p, in, g.in_base + row * g.in_rs + c * g.in_cs);
   }
-  dft8(x, p.rts, p.rt_log);
+  dft8<true>(x, p.rts, p.rt_log);
 #pragma unroll
   for (int Ka = 1; Ka < 8; ++Ka) x[Ka] = mul_root(x[Ka], p.rts, (u * Ka) << rsh);
 #pragma unroll
@@ -398,7 +415,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
   const uint32_t Ka = u >> LM2, b2 = u & (M2 - 1);
 #pragma unroll
   for (int a2 = 0; a2 < 8; ++a2) x[a2] = get(Ka * T + a2 * M2 + b2);
-  dft8(x, p.rts, p.rt_log);
+  dft8<(M2 != 1) || WOUT>(x, p.rts, p.rt_log);
   if (M2 == 1) {
 #pragma unroll
     for (int Ka2 = 0; Ka2 < 8; ++Ka2) store_out_t<KIND>(p, out, g, Ka + 8 * Ka2, c, x[Ka2], bidx);
@@ -415,7 +432,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
     const uint32_t gq = u;  // 64 threads per column, one group each
 #pragma unroll
     for (int b = 0; b < 8; ++b) x[b] = get(gq * 8 + b);
-    dft8(x, p.rts, p.rt_log);
+    dft8<WOUT>(x, p.rts, p.rt_log);
     const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
 #pragma unroll
     for (int i = 0; i < 8; ++i) store_out_t<KIND>(p, out, g, K0 + 64 * i, c, x[i], bidx);
@@ -428,10 +445,10 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
       Fr v0 = get(gq * 4 + 0), v1 = get(gq * 4 + 1), v2 = get(gq * 4 + 2), v3 = get(gq * 4 + 3);
       Fr t0 = add_lazy(v0, v2), t1 = sub_lazy(v0, v2), t2 = add_lazy(v1, v3), t3 = mul_shoup<FrParams, false>(sub_wide(v1, v3), w4, w4s);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
-      store_out_t<KIND>(p, out, g, K0, c, add_lazy(t0, t2), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 64, c, add_lazy(t1, t3), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 128, c, sub_lazy(t0, t2), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 192, c, sub_lazy(t1, t3), bidx);
+      store_out_t<KIND>(p, out, g, K0, c, addw<WOUT>(t0, t2), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 64, c, addw<WOUT>(t1, t3), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 128, c, subw<WOUT>(t0, t2), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 192, c, subw<WOUT>(t1, t3), bidx);
     }
   } else {
 #pragma unroll
@@ -439,8 +456,8 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
       const uint32_t gq = u + 16 * i;
       Fr v0 = get(gq * 2 + 0), v1 = get(gq * 2 + 1);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
-      store_out_t<KIND>(p, out, g, K0, c, add_lazy(v0, v1), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 64, c, sub_lazy(v0, v1), bidx);
+      store_out_t<KIND>(p, out, g, K0, c, addw<WOUT>(v0, v1), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 64, c, subw<WOUT>(v0, v1), bidx);
     }
   }
   } else {
@@ -468,7 +485,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
 #pragma unroll
       for (int a = 0; a < 8; ++a) x[a] = get(base + a * stride);
     }
-    dft8(x, p.rts, p.rt_log);
+    dft8<true>(x, p.rts, p.rt_log);
     if (round == NR8 - 1 && (M2 == 1 || M2 == 8)) break;  // the last radix-8 round of S = 6 and S = 9 feeds the output
 #pragma unroll
     for (int j = 1; j < 8; ++j) x[j] = mul_root(x[j], p.rts, (e * j) << rsh);
@@ -501,10 +518,10 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
       Fr t0 = add_lazy(v0, v2), t1 = sub_lazy(v0, v2), t2 = add_lazy(v1, v3),
          t3 = mul_shoup<FrParams, false>(sub_wide(v1, v3), w4, w4s);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
-      store_out_t<KIND>(p, out, g, K0, c, add_lazy(t0, t2), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 64, c, add_lazy(t1, t3), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 128, c, sub_lazy(t0, t2), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 192, c, sub_lazy(t1, t3), bidx);
+      store_out_t<KIND>(p, out, g, K0, c, addw<WOUT>(t0, t2), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 64, c, addw<WOUT>(t1, t3), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 128, c, subw<WOUT>(t0, t2), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 192, c, subw<WOUT>(t1, t3), bidx);
     }
   } else {
 #pragma unroll 1
@@ -512,8 +529,8 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_fast(PassParams p) {
       const uint32_t gq = u + 16 * i;
       Fr v0 = get(gq * 2 + 0), v1 = get(gq * 2 + 1);
       const uint32_t K0 = (gq >> 3) + 8 * (gq & 7);
-      store_out_t<KIND>(p, out, g, K0, c, add_lazy(v0, v1), bidx);
-      store_out_t<KIND>(p, out, g, K0 + 64, c, sub_lazy(v0, v1), bidx);
+      store_out_t<KIND>(p, out, g, K0, c, addw<WOUT>(v0, v1), bidx);
+      store_out_t<KIND>(p, out, g, K0 + 64, c, subw<WOUT>(v0, v1), bidx);
     }
   }
   }  // LOOPED
