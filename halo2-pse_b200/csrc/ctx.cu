@@ -469,10 +469,6 @@ extern "C" int h2b_ctx_create(int device, h2b_ctx** out) {
     return H2B_ERR_CUDA;
   }
 #ifndef H2B_EMU
-  if (const char* e = getenv("H2B_L2_FETCH")) {  // experiment: L2 fetch granularity for the 64-byte table gathers
-    const int v = atoi(e);
-    if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
-  }
   {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
