@@ -40,6 +40,23 @@ def test_host_field_ops_match_big_integers(emu_ctx):
             assert (out2 == out).all()
 
 
+def test_field_product_variants_host(tmp_path):
+    """csrc/field.cuh's product variants against the plain Montgomery product, on the host emulation of the same carry
+    chains the kernels compile (tests/cpp/test_field_variants.cpp): dedicated squaring, two products on one reduction,
+    the Shoup product for fixed multipliers, lazy residues ([0, 2p), and below 4p where a product follows) with their
+    stated ranges.  Random operands and edge values in both fields; the GPU suite checks the device paths
+    (test_device_field_ops ops 3, 8, 9; every NTT / MSM parity test)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_field_variants")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-DH2B_EMU", os.path.join(root, "tests", "cpp", "test_field_variants.cpp"),
+                    "-o", exe], check=True, capture_output=True, text=True)
+    r = subprocess.run([exe, "60000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Fr: 60000 iterations, 0 mismatches" in r.stdout and "Fq: 60000 iterations, 0 mismatches" in r.stdout
+
+
 def test_golden_best_fft(emu_ctx):
     for v in KAT["best_fft"]:
         a = _np(v["in"], 4)
